@@ -1,0 +1,290 @@
+"""CPU restatement (NumPy) of dynax's rollout hot path.  TEST INFRASTRUCTURE ONLY.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import this module.  Nothing under ``dynax_b200/``
+imports it: the product path is the CUDA library and fails loudly without it.
+
+Parity status
+-------------
+* Forward rollout (RC and dense LTI): **pinned** by the reference's own golden
+  vectors -- ``tests/test_simulator.py:24-36`` (golden #1) and
+  ``tests/test_gymwrapper_basics.py:7-12`` (golden #2) -- see
+  ``tests/golden/`` and ``tests/test_oracle_golden.py``.
+* Gradient / loss / MPC cost / RK4-MLP: **parity unpinned by the reference** (it
+  holds no gradient, RK4 or cost test).  The hand adjoint here is pinned instead
+  against torch autograd (fp64) over this same restated loop
+  (``tests/test_oracle_adjoint.py``).
+* The reference is JAX/Flax; neither is installed in this image, so the
+  reference itself cannot be run here (``import jax`` -> ModuleNotFoundError).
+
+Each function cites the reference file:line it follows (paths relative to
+``/root/reference``).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+# Parameter order used everywhere in this repo (RC.py:176-182 declaration order).
+RC_PARAM_NAMES = ("Cai", "Cwe", "Cwi", "Re", "Ri", "Rw", "Rg")
+
+# examples/1-forward.py:41-43 == dynax/wrapper/envs/rc.py:25-27
+RC_NOMINAL = np.array([10384.31640625, 499089.09375, 1321535.125,
+                       1.5348844528198242, 0.5000327825546265, 1.000040054321289,
+                       20.119935989379883], dtype=np.float64)
+
+# examples/3-inverse.py:66-85
+RC_LB = np.array([3.0e3, 5.0e4, 5.0e5, 1.0, 0.5, 1.0, 5.0], dtype=np.float64)
+RC_UB = np.array([3.0e4, 5.0e5, 5.0e6, 1.0e1, 5.0, 1.0e1, 5.0e1], dtype=np.float64)
+
+
+# --------------------------------------------------------------------------------------
+# A3: theta -> A, B, C, D          dynax/models/RC.py:201-210, 222-230, 236-239, 245-246
+# --------------------------------------------------------------------------------------
+def rc_abcd(theta, dtype=np.float32):
+    """theta[..., 7] -> A[...,3,3], B[...,3,5], C[...,1,3], D[...,1,5].
+
+    Expressions are written exactly as in RC.py so fp32 rounding of the coefficients
+    matches the reference (e.g. ``-1/Cai*(1/Rg+1/Ri)`` is ``((-1)/Cai)*(1/Rg+1/Ri)``).
+    """
+    th = np.asarray(theta, dtype=dtype)
+    Cai, Cwe, Cwi, Re, Ri, Rw, Rg = (th[..., i] for i in range(7))
+    one = dtype(1)
+    lead = th.shape[:-1]
+    A = np.zeros(lead + (3, 3), dtype=dtype)
+    A[..., 0, 0] = -one / Cai * (one / Rg + one / Ri)      # RC.py:203
+    A[..., 0, 2] = one / (Cai * Ri)                         # RC.py:204
+    A[..., 1, 1] = -one / Cwe * (one / Re + one / Rw)      # RC.py:205
+    A[..., 1, 2] = one / (Cwe * Rw)                         # RC.py:206
+    A[..., 2, 0] = one / (Cwi * Ri)                         # RC.py:207
+    A[..., 2, 1] = one / (Cwi * Rw)                         # RC.py:208
+    A[..., 2, 2] = -one / Cwi * (one / Rw + one / Ri)      # RC.py:209
+    B = np.zeros(lead + (3, 5), dtype=dtype)
+    B[..., 0, 0] = one / (Cai * Rg)                         # RC.py:224
+    B[..., 0, 1] = one / Cai                                # RC.py:225
+    B[..., 0, 2] = one / Cai                                # RC.py:226
+    B[..., 1, 0] = one / (Cwe * Re)                         # RC.py:227
+    B[..., 1, 3] = one / Cwe                                # RC.py:228
+    B[..., 2, 4] = one / Cwi                                # RC.py:229
+    C = np.zeros(lead + (1, 3), dtype=dtype)
+    C[..., 0, 0] = one                                      # RC.py:237-238
+    D = np.zeros(lead + (1, 5), dtype=dtype)                # RC.py:246
+    return A, B, C, D
+
+
+# --------------------------------------------------------------------------------------
+# A1 + A2: the scan body             dynax/simulators/simulator.py:36-43
+#                                    dynax/core/base_block_state_space.py:59-61, 68-71
+# --------------------------------------------------------------------------------------
+def _bmv(M, v):
+    """Batched mat-vec: M[N,r,c] (or [1,r,c]) times v[N,c] -> [N,r]."""
+    return np.einsum("nrc,nc->nr", M, v)
+
+
+def lti_rollout(A, B, C, D, x0, u, dt, dtype=np.float32, discrete=False):
+    """Batched restatement of ``DifferentiableSimulator`` over a linear block SSM.
+
+    A[N|1,n,n], B[N|1,n,m], C[N|1,p,n], D[N|1,p,m], x0[N,n], u[T,N|1,m].
+    Returns xsol[T,N,n] (x_{k+1}, post-update) and ysol[T,N,p] (y(x_k,u_k), pre-update):
+    simulator.py:38-43.  ``discrete=True`` replaces the Euler residual update by
+    ``x = rhs`` (tests/test_forward_simulation.py:30-36 steps a discrete model directly).
+    """
+    A, B, C, D = (np.asarray(M, dtype=dtype) for M in (A, B, C, D))
+    x = np.array(x0, dtype=dtype, copy=True)
+    u = np.asarray(u, dtype=dtype)
+    T = u.shape[0]
+    N, n = x.shape
+    p = C.shape[-2]
+    dt = dtype(dt)
+    xsol = np.empty((T, N, n), dtype=dtype)
+    ysol = np.empty((T, N, p), dtype=dtype)
+    for k in range(T):
+        uk = np.broadcast_to(u[k], (N, u.shape[-1]))
+        rhs = _bmv(A, x) + _bmv(B, uk)          # base_block_state_space.py:61  fxx(x)+fxu(u)
+        y = _bmv(C, x) + _bmv(D, uk)            # base_block_state_space.py:69  fyx(x)+fyu(u)
+        if discrete:
+            x = rhs
+        else:
+            x = x + dt * rhs                    # simulator.py:40   states += dt*rhs
+        xsol[k] = x                             # simulator.py:43   emit post-update state
+        ysol[k] = y                             #                   and pre-update output
+    return xsol, ysol
+
+
+def rc_rollout(theta, x0, u, dt, dtype=np.float32):
+    """theta[N|1,7], x0[N,3], u[T,N|1,5] -> xsol[T,N,3], ysol[T,N,1]."""
+    theta = np.atleast_2d(np.asarray(theta))
+    A, B, C, D = rc_abcd(theta, dtype)
+    return lti_rollout(A, B, C, D, x0, u, dt, dtype)
+
+
+def rc_rollout_single(theta, x0, u, dt, dtype=np.float32):
+    """Unbatched signature of the reference: theta[7], x0[3], u[T,5] -> xsol[T,3], ysol[T,1]."""
+    xs, ys = rc_rollout(np.asarray(theta)[None], np.asarray(x0)[None], np.asarray(u)[:, None, :], dt, dtype)
+    return xs[:, 0], ys[:, 0]
+
+
+# --------------------------------------------------------------------------------------
+# A6: loss                           examples/3-inverse.py:96-110
+# --------------------------------------------------------------------------------------
+def bound_penalty(theta, lb, ub, dtype=np.float64):
+    """sum_j relu(theta_j-ub_j)/ub_j + relu(lb_j-theta_j)/ub_j  (normaliser is ub for both)."""
+    th = np.asarray(theta, dtype=dtype)
+    lb = np.asarray(lb, dtype=dtype)
+    ub = np.asarray(ub, dtype=dtype)
+    over = np.maximum(th - ub, 0) / ub          # 3-inverse.py:104
+    under = np.maximum(lb - th, 0) / ub         # 3-inverse.py:105
+    return (over + under).sum(-1)
+
+
+def bound_penalty_grad(theta, lb, ub, dtype=np.float64):
+    th = np.asarray(theta, dtype=dtype)
+    lb = np.asarray(lb, dtype=dtype)
+    ub = np.asarray(ub, dtype=dtype)
+    return (th > ub).astype(dtype) / ub - (th < lb).astype(dtype) / ub
+
+
+def rc_loss(theta, x0, u, target, dt, lb=None, ub=None, dtype=np.float32):
+    """loss[N] = mean_k (y_k - target_k)^2 (+ bound penalty).  target[T,N|1]."""
+    _, ys = rc_rollout(theta, x0, u, dt, dtype)
+    r = ys[..., 0] - np.asarray(target, dtype=dtype)
+    loss = np.mean(r * r, axis=0, dtype=dtype)              # 3-inverse.py:100
+    if lb is not None:
+        loss = loss + bound_penalty(np.atleast_2d(theta), lb, ub, dtype)
+    return loss
+
+
+# --------------------------------------------------------------------------------------
+# A5: reverse-mode gradient (discrete adjoint == what jax.value_and_grad derives through
+#     lax.scan for this body; examples/3-inverse.py:112).  Derived in SURVEY.md section 8(a) A5.
+# --------------------------------------------------------------------------------------
+def lti_vjp(A, B, C, D, x0, u, dt, g_xsol, g_ysol, dtype=np.float64, discrete=False):
+    """General-cotangent VJP of ``lti_rollout``.
+
+    g_xsol[T,N,n] / g_ysol[T,N,p] are dL/dxsol and dL/dysol (either may be None == 0).
+    Returns dict of per-system gradients gA[N,n,n], gB[N,n,m], gC[N,p,n], gD[N,p,m],
+    gx0[N,n], gu[T,N,m].  (If A.. or u were shared the caller sums over N.)
+    """
+    A, B, C, D = (np.asarray(M, dtype=dtype) for M in (A, B, C, D))
+    u = np.asarray(u, dtype=dtype)
+    T = u.shape[0]
+    x0 = np.asarray(x0, dtype=dtype)
+    N, n = x0.shape
+    m = u.shape[-1]
+    p = C.shape[-2]
+    dt = dtype(dt)
+    # forward sweep storing x_k (the residuals XLA would store)
+    xs = np.empty((T + 1, N, n), dtype=dtype)
+    xs[0] = x0
+    for k in range(T):
+        uk = np.broadcast_to(u[k], (N, m))
+        rhs = _bmv(A, xs[k]) + _bmv(B, uk)
+        xs[k + 1] = rhs if discrete else xs[k] + dt * rhs
+    gA = np.zeros((N, n, n), dtype=dtype)
+    gB = np.zeros((N, n, m), dtype=dtype)
+    gC = np.zeros((N, p, n), dtype=dtype)
+    gD = np.zeros((N, p, m), dtype=dtype)
+    gu = np.zeros((T, N, m), dtype=dtype)
+    a = np.zeros((N, n), dtype=dtype)            # adjoint of x_{k+1}
+    AT = np.swapaxes(A, -1, -2)
+    BT = np.swapaxes(B, -1, -2)
+    CT = np.swapaxes(C, -1, -2)
+    DT = np.swapaxes(D, -1, -2)
+    for k in range(T - 1, -1, -1):
+        if g_xsol is not None:
+            a = a + np.asarray(g_xsol[k], dtype=dtype)      # xsol[k] = x_{k+1}
+        gy = np.zeros((N, p), dtype=dtype) if g_ysol is None else np.asarray(g_ysol[k], dtype=dtype)
+        uk = np.broadcast_to(u[k], (N, m))
+        s = a if discrete else dt * a                       # cotangent of rhs
+        gA += s[:, :, None] * xs[k][:, None, :]
+        gB += s[:, :, None] * uk[:, None, :]
+        gC += gy[:, :, None] * xs[k][:, None, :]
+        gD += gy[:, :, None] * uk[:, None, :]
+        gu[k] = _bmv(BT, s) + _bmv(DT, gy)
+        a = (0 if discrete else a) + _bmv(AT, s) + _bmv(CT, gy)
+    return dict(gA=gA, gB=gB, gC=gC, gD=gD, gx0=a, gu=gu)
+
+
+def rc_chain(theta, gA, gB, dtype=np.float64):
+    """dL/dtheta[N,7] from dL/dA[N,3,3], dL/dB[N,3,5] for the 4R3C parameterisation
+    (derivative of the expressions at RC.py:203-209, 224-229)."""
+    th = np.atleast_2d(np.asarray(theta, dtype=dtype))
+    Cai, Cwe, Cwi, Re, Ri, Rw, Rg = (th[:, i] for i in range(7))
+    iCai, iCwe, iCwi, iRe, iRi, iRw, iRg = (1 / v for v in (Cai, Cwe, Cwi, Re, Ri, Rw, Rg))
+    A00 = -iCai * (iRg + iRi); A02 = iCai * iRi
+    A11 = -iCwe * (iRe + iRw); A12 = iCwe * iRw
+    A20 = iCwi * iRi; A21 = iCwi * iRw; A22 = -iCwi * (iRw + iRi)
+    B00 = iCai * iRg; B01 = iCai; B10 = iCwe * iRe; B13 = iCwe; B24 = iCwi
+    g = np.zeros_like(th)
+    g[:, 0] = -iCai * (gA[:, 0, 0] * A00 + gA[:, 0, 2] * A02 + gB[:, 0, 0] * B00 + (gB[:, 0, 1] + gB[:, 0, 2]) * B01)
+    g[:, 1] = -iCwe * (gA[:, 1, 1] * A11 + gA[:, 1, 2] * A12 + gB[:, 1, 0] * B10 + gB[:, 1, 3] * B13)
+    g[:, 2] = -iCwi * (gA[:, 2, 0] * A20 + gA[:, 2, 1] * A21 + gA[:, 2, 2] * A22 + gB[:, 2, 4] * B24)
+    g[:, 3] = iCwe * iRe * iRe * (gA[:, 1, 1] - gB[:, 1, 0])
+    g[:, 4] = iRi * iRi * (iCai * (gA[:, 0, 0] - gA[:, 0, 2]) + iCwi * (gA[:, 2, 2] - gA[:, 2, 0]))
+    g[:, 5] = iRw * iRw * (iCwe * (gA[:, 1, 1] - gA[:, 1, 2]) + iCwi * (gA[:, 2, 2] - gA[:, 2, 1]))
+    g[:, 6] = iCai * iRg * iRg * (gA[:, 0, 0] - gB[:, 0, 0])
+    return g
+
+
+def rc_vjp(theta, x0, u, dt, g_xsol, g_ysol, dtype=np.float64):
+    """VJP of rc_rollout: returns gtheta[N,7], gx0[N,3], gu[T,N,5]."""
+    theta = np.atleast_2d(np.asarray(theta, dtype=dtype))
+    A, B, C, D = rc_abcd(theta, dtype)
+    r = lti_vjp(A, B, C, D, x0, u, dt, g_xsol, g_ysol, dtype)
+    return rc_chain(theta, r["gA"], r["gB"], dtype), r["gx0"], r["gu"]
+
+
+def rc_loss_grad(theta, x0, u, target, dt, lb=None, ub=None, dtype=np.float64):
+    """loss[N], grad[N,7] of examples/3-inverse.py:96-112 for a batch of candidates.
+
+    theta[N,7], x0[N,3], u[T,N|1,5], target[T,N|1].
+    """
+    theta = np.atleast_2d(np.asarray(theta, dtype=dtype))
+    x0 = np.asarray(x0, dtype=dtype)
+    N = x0.shape[0]
+    _, ys = rc_rollout(theta, x0, u, dt, dtype)
+    T = ys.shape[0]
+    r = ys[..., 0] - np.asarray(target, dtype=dtype)
+    loss = np.mean(r * r, axis=0)
+    gy = (2.0 / T) * r                                      # d mean(r^2) / dy_k
+    g, _, _ = rc_vjp(theta, x0, u, dt, None, gy[..., None].astype(dtype), dtype)
+    if lb is not None:
+        loss = loss + bound_penalty(theta, lb, ub, dtype)
+        g = g + bound_penalty_grad(theta, lb, ub, dtype)
+    return loss.astype(dtype), g.astype(dtype)
+
+
+# --------------------------------------------------------------------------------------
+# Synthetic workloads; shared by tests and bench so that any system
+# of a large GPU run can be regenerated on the host.
+# --------------------------------------------------------------------------------------
+def spectral_radius_euler(theta, dt):
+    A, _, _, _ = rc_abcd(np.atleast_2d(theta), np.float64)
+    M = np.eye(3)[None] + dt * A
+    return np.abs(np.linalg.eigvals(M)).max(-1)
+
+
+def synth_theta(N, seed, spread=0.2, dt=3600.0):
+    """theta_i = nominal * exp(U(-spread, spread)), Euler-stable at dt (asserted)."""
+    rng = np.random.default_rng(seed)
+    th = RC_NOMINAL[None] * np.exp(rng.uniform(-spread, spread, size=(N, 7)))
+    assert spectral_radius_euler(th, dt).max() < 1.0, "unstable synthetic theta"
+    return th.astype(np.float32)
+
+
+def synth_x0(N, seed):
+    rng = np.random.default_rng(seed + 1)
+    return (np.array([20.0, 30.0, 26.0])[None] + rng.uniform(-1, 1, size=(N, 3))).astype(np.float32)
+
+
+def synth_u(T, N, seed):
+    """u[T,N,5] fp32: [Tao, qCon_i, qHVAC, qRad_e, qRad_i] in degC / kW."""
+    rng = np.random.default_rng(seed + 2)
+    k = np.arange(T, dtype=np.float64)[:, None]
+    phi = rng.uniform(0, 2 * np.pi, size=(1, N))
+    u = np.empty((T, N, 5), dtype=np.float32)
+    u[..., 0] = 15 + 10 * np.sin(2 * np.pi * k / 8760) + 6 * np.sin(2 * np.pi * k / 24 + phi) + rng.normal(size=(T, N))
+    u[..., 1] = rng.uniform(0, 1, size=(T, N))
+    u[..., 2] = -rng.uniform(0, 5, size=(T, N))
+    u[..., 3] = rng.uniform(0, 2, size=(T, N)) * (np.sin(2 * np.pi * k / 24) > 0)
+    u[..., 4] = rng.uniform(0, 1, size=(T, N))
+    return u
