@@ -1,0 +1,70 @@
+"""ctypes binding of libdynax_b200.so -- the C-ABI declared in include/dynax_b200.h.
+
+There is deliberately NO fallback: if the shared library is missing this module raises, and
+if no sm_100 device is present every compute entry point returns DYNAX_ERR_NO_DEVICE, which
+``check`` turns into a ``DynaxError``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdynax_b200.so")
+
+# flags / ops (include/dynax_b200.h)
+SHARED_THETA, SHARED_U, SHARED_TARGET, DISCRETE = 1, 2, 4, 8
+OP_RC_FORWARD, OP_RC_LOSS_GRAD, OP_RC_VJP, OP_LTI_FORWARD, OP_LTI_VJP = 0, 1, 2, 3, 4
+
+_f = ctypes.c_void_p       # device or host float* passed as an integer address
+_i64 = ctypes.c_int64
+_u32 = ctypes.c_uint32
+_int = ctypes.c_int
+_flt = ctypes.c_float
+_sz = ctypes.c_size_t
+
+# name -> (restype, argtypes): every symbol include/dynax_b200.h declares
+SIGNATURES = {
+    "dynax_version": (_int, []),
+    "dynax_last_error": (ctypes.c_char_p, []),
+    "dynax_device_check": (_int, []),
+    "dynax_workspace_bytes": (_sz, [_int, _i64, _i64, _int, _int, _int, _u32]),
+    "dynax_lti_supported": (_int, [_int, _int, _int]),
+    "dynax_rc_forward_f32": (_int, [_f] * 6 + [_i64, _i64, _flt, _u32, _f]),
+    "dynax_rc_loss_grad_f32": (_int, [_f] * 9 + [_i64, _i64, _flt, _u32, _f, _sz, _f]),
+    "dynax_rc_vjp_f32": (_int, [_f] * 8 + [_i64, _i64, _flt, _u32, _f, _sz, _f]),
+    "dynax_lti_forward_f32": (_int, [_f] * 9 + [_i64, _i64, _int, _int, _int, _flt, _u32, _f]),
+    "dynax_lti_vjp_f32": (_int, [_f] * 14 + [_i64, _i64, _int, _int, _int, _flt, _u32, _f, _sz, _f]),
+    "dynax_rc_forward_host_f32": (_int, [_f] * 6 + [_i64, _i64, _flt, _u32, _i64]),
+    "dynax_rc_loss_grad_host_f32": (_int, [_f] * 8 + [_i64, _i64, _flt, _u32, _i64]),
+    "dynax_host_release": (_int, []),
+}
+
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -m dynax_b200.build` "
+                "(dynax_b200 has no CPU or PyTorch fallback)")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)       # AttributeError if the .so lacks a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = L
+    return _LIB
+
+
+class DynaxError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"dynax_b200 error {code}: {msg}")
+        self.code = code
+
+
+def check(rc):
+    if rc != 0:
+        raise DynaxError(rc, lib().dynax_last_error().decode(errors="replace"))

@@ -1,0 +1,49 @@
+// Host-side plumbing shared by the C-ABI translation units: error reporting, device checks,
+// launch helpers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/dynax_b200.h"
+
+namespace dynax {
+
+char *last_error_buf();  // thread-local, defined in rc_api.cu
+constexpr int kErrBufLen = 512;
+
+inline int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(last_error_buf(), kErrBufLen, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define DYNAX_CUDA_TRY(expr)                                                                     \
+    do {                                                                                         \
+        cudaError_t e_ = (expr);                                                                 \
+        if (e_ != cudaSuccess)                                                                   \
+            return ::dynax::fail(DYNAX_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), \
+                                 __FILE__, __LINE__);                                            \
+    } while (0)
+
+// There is no CPU fallback: refuse to run unless the current device is Blackwell (cc 10.x).
+int require_sm100();
+
+inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+struct DeviceInfo {
+    int sm_count;
+    int smem_optin;
+};
+int device_info(DeviceInfo *out);
+
+template <class Kernel>
+inline int set_smem(Kernel k, size_t bytes) {
+    DYNAX_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return DYNAX_OK;
+}
+
+}  // namespace dynax

@@ -1,0 +1,236 @@
+// Host-buffer entry points: what a reference user calls with NumPy / JAX-CPU arrays.
+//
+// The system axis is cut into tiles; tile i+1's host->device copy (a strided 2-D copy out of the
+// caller's [T,N,m] array) runs on a second stream while tile i's kernel and its device->host copy
+// run on the first, so with pinned host memory the call is PCIe-bound, not latency-bound.
+// Device scratch is cached across calls (grow-only) and released by dynax_host_release().
+#include <mutex>
+#include <string.h>
+
+#include "api_common.cuh"
+
+using namespace dynax;
+
+namespace {
+
+struct Slot {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+};
+
+struct HostCtx {
+    std::mutex mu;
+    cudaStream_t streams[2] = {nullptr, nullptr};
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    Slot slots[2][8];
+    int device = -1;
+};
+
+HostCtx &ctx() {
+    static HostCtx c;
+    return c;
+}
+
+int ensure_ctx(HostCtx &c) {
+    int dev = 0;
+    DYNAX_CUDA_TRY(cudaGetDevice(&dev));
+    if (c.device != dev) {
+        for (int b = 0; b < 2; ++b) {
+            if (c.streams[b]) cudaStreamDestroy(c.streams[b]);
+            if (c.done[b]) cudaEventDestroy(c.done[b]);
+            for (auto &s : c.slots[b]) {
+                if (s.ptr) cudaFree(s.ptr);
+                s = Slot();
+            }
+            DYNAX_CUDA_TRY(cudaStreamCreateWithFlags(&c.streams[b], cudaStreamNonBlocking));
+            DYNAX_CUDA_TRY(cudaEventCreateWithFlags(&c.done[b], cudaEventDisableTiming));
+        }
+        c.device = dev;
+    }
+    return DYNAX_OK;
+}
+
+int reserve(Slot &s, size_t bytes, void **out) {
+    if (bytes > s.bytes) {
+        if (s.ptr) DYNAX_CUDA_TRY(cudaFree(s.ptr));
+        s = Slot();
+        DYNAX_CUDA_TRY(cudaMalloc(&s.ptr, bytes));
+        s.bytes = bytes;
+    }
+    *out = s.ptr;
+    return DYNAX_OK;
+}
+
+int64_t pick_tile(int64_t N, int64_t T, int64_t tile_systems, int bytes_per_system_step) {
+    int64_t nt = tile_systems;
+    if (nt <= 0) {
+        const int64_t budget = 512ll << 20;  // ~512 MB of streamed input per tile
+        nt = budget / (T > 0 ? T * bytes_per_system_step : 1);
+        if (nt < 4096) nt = 4096;
+    }
+    if (nt > N) nt = N;
+    if (nt < N) nt = (nt + 127) / 128 * 128;  // keep interior tiles TMA-aligned
+    if (nt > N) nt = N;
+    return nt;
+}
+
+// strided [T, nt, w] block out of a [T, N, w] host array (or back)
+int copy_tile(float *dst, size_t dpitch_f, const float *src, size_t spitch_f, int64_t nt, int w, int64_t T,
+              cudaMemcpyKind kind, cudaStream_t st) {
+    DYNAX_CUDA_TRY(cudaMemcpy2DAsync(dst, dpitch_f * sizeof(float), src, spitch_f * sizeof(float),
+                                     (size_t)nt * w * sizeof(float), (size_t)T, kind, st));
+    return DYNAX_OK;
+}
+
+#define TRY(expr)                       \
+    do {                                \
+        int rc_ = (expr);               \
+        if (rc_ != DYNAX_OK) return rc_; \
+    } while (0)
+
+}  // namespace
+
+extern "C" {
+
+int dynax_host_release(void) {
+    HostCtx &c = ctx();
+    std::lock_guard<std::mutex> lk(c.mu);
+    for (int b = 0; b < 2; ++b) {
+        for (auto &s : c.slots[b]) {
+            if (s.ptr) cudaFree(s.ptr);
+            s = Slot();
+        }
+    }
+    return DYNAX_OK;
+}
+
+int dynax_rc_forward_host_f32(const float *theta, const float *x0, const float *u, float *xsol, float *ysol,
+                              float *x_final, int64_t N, int64_t T, float dt, uint32_t flags, int64_t tile_systems) {
+    if (N < 0 || T < 0) return fail(DYNAX_ERR_INVALID_ARGUMENT, "negative N or T");
+    if (N == 0) return DYNAX_OK;
+    if (!theta || !x0 || !u) return fail(DYNAX_ERR_INVALID_ARGUMENT, "theta, x0 and u must be non-NULL");
+    TRY(require_sm100());
+    HostCtx &c = ctx();
+    std::lock_guard<std::mutex> lk(c.mu);
+    TRY(ensure_ctx(c));
+    const bool sth = flags & DYNAX_SHARED_THETA, su = flags & DYNAX_SHARED_U;
+    const int64_t nt = pick_tile(N, T, tile_systems, 36);
+    int b = 0;
+    for (int64_t n0 = 0; n0 < N; n0 += nt, b ^= 1) {
+        const int64_t cur = (N - n0) < nt ? (N - n0) : nt;
+        cudaStream_t st = c.streams[b];
+        // the previous use of this buffer set finished its D2H when its event fired
+        DYNAX_CUDA_TRY(cudaEventSynchronize(c.done[b]));
+        float *d_th, *d_x0, *d_u, *d_xs = nullptr, *d_ys = nullptr, *d_xf = nullptr;
+        TRY(reserve(c.slots[b][0], sizeof(float) * 7 * (sth ? 1 : cur), (void **)&d_th));
+        TRY(reserve(c.slots[b][1], sizeof(float) * 3 * cur, (void **)&d_x0));
+        TRY(reserve(c.slots[b][2], sizeof(float) * 5 * (size_t)T * (su ? 1 : cur) + 16, (void **)&d_u));
+        if (xsol) TRY(reserve(c.slots[b][3], sizeof(float) * 3 * (size_t)T * cur + 16, (void **)&d_xs));
+        if (ysol) TRY(reserve(c.slots[b][4], sizeof(float) * (size_t)T * cur + 16, (void **)&d_ys));
+        if (x_final) TRY(reserve(c.slots[b][5], sizeof(float) * 3 * cur, (void **)&d_xf));
+        DYNAX_CUDA_TRY(cudaMemcpyAsync(d_th, theta + (sth ? 0 : n0 * 7), sizeof(float) * 7 * (sth ? 1 : cur),
+                                       cudaMemcpyHostToDevice, st));
+        DYNAX_CUDA_TRY(cudaMemcpyAsync(d_x0, x0 + n0 * 3, sizeof(float) * 3 * cur, cudaMemcpyHostToDevice, st));
+        if (T > 0) {
+            if (su) DYNAX_CUDA_TRY(cudaMemcpyAsync(d_u, u, sizeof(float) * 5 * T, cudaMemcpyHostToDevice, st));
+            else TRY(copy_tile(d_u, (size_t)cur * 5, u + n0 * 5, (size_t)N * 5, cur, 5, T, cudaMemcpyHostToDevice, st));
+        }
+        TRY(dynax_rc_forward_f32(d_th, d_x0, d_u, d_xs, d_ys, d_xf, cur, T, dt, flags, st));
+        if (T > 0 && xsol)
+            TRY(copy_tile(xsol + n0 * 3, (size_t)N * 3, d_xs, (size_t)cur * 3, cur, 3, T, cudaMemcpyDeviceToHost, st));
+        if (T > 0 && ysol)
+            TRY(copy_tile(ysol + n0, (size_t)N, d_ys, (size_t)cur, cur, 1, T, cudaMemcpyDeviceToHost, st));
+        if (x_final)
+            DYNAX_CUDA_TRY(cudaMemcpyAsync(x_final + n0 * 3, d_xf, sizeof(float) * 3 * cur, cudaMemcpyDeviceToHost, st));
+        DYNAX_CUDA_TRY(cudaEventRecord(c.done[b], st));
+    }
+    DYNAX_CUDA_TRY(cudaStreamSynchronize(c.streams[0]));
+    DYNAX_CUDA_TRY(cudaStreamSynchronize(c.streams[1]));
+    return DYNAX_OK;
+}
+
+int dynax_rc_loss_grad_host_f32(const float *theta, const float *x0, const float *u, const float *target,
+                                const float *lb, const float *ub, float *loss, float *g_theta, int64_t N,
+                                int64_t T, float dt, uint32_t flags, int64_t tile_systems) {
+    if (N < 0 || T < 1) return fail(DYNAX_ERR_INVALID_ARGUMENT, "need N >= 0 and T >= 1");
+    if (N == 0) return DYNAX_OK;
+    if (!theta || !x0 || !u || !target || !loss || !g_theta)
+        return fail(DYNAX_ERR_INVALID_ARGUMENT, "theta, x0, u, target, loss, g_theta must be non-NULL");
+    if ((lb == nullptr) != (ub == nullptr)) return fail(DYNAX_ERR_INVALID_ARGUMENT, "lb and ub go together");
+    TRY(require_sm100());
+    HostCtx &c = ctx();
+    std::lock_guard<std::mutex> lk(c.mu);
+    TRY(ensure_ctx(c));
+    const bool sth = flags & DYNAX_SHARED_THETA, su = flags & DYNAX_SHARED_U, stg = flags & DYNAX_SHARED_TARGET;
+    const int64_t nt = pick_tile(N, T, tile_systems, 24);
+    const int64_t ntiles = (N + nt - 1) / nt;
+    // shared-theta partial sums per tile land here and are reduced on the host in fp64
+    float(*part)[8] = sth ? new float[ntiles][8] : nullptr;
+    int b = 0;
+    int rc = DYNAX_OK;
+    int64_t tile = 0;
+    for (int64_t n0 = 0; n0 < N && rc == DYNAX_OK; n0 += nt, b ^= 1, ++tile) {
+        const int64_t cur = (N - n0) < nt ? (N - n0) : nt;
+        cudaStream_t st = c.streams[b];
+        auto body = [&]() -> int {
+            DYNAX_CUDA_TRY(cudaEventSynchronize(c.done[b]));
+            float *d_th, *d_x0, *d_u, *d_tg, *d_out, *d_bounds = nullptr;
+            void *d_ws;
+            const size_t ws_bytes = dynax_workspace_bytes(DYNAX_OP_RC_LOSS_GRAD, cur, T, 3, 5, 1, flags);
+            TRY(reserve(c.slots[b][0], sizeof(float) * 7 * (sth ? 1 : cur), (void **)&d_th));
+            TRY(reserve(c.slots[b][1], sizeof(float) * 3 * cur, (void **)&d_x0));
+            TRY(reserve(c.slots[b][2], sizeof(float) * 5 * (size_t)T * (su ? 1 : cur) + 16, (void **)&d_u));
+            TRY(reserve(c.slots[b][3], sizeof(float) * (size_t)T * (stg ? 1 : cur) + 16, (void **)&d_tg));
+            TRY(reserve(c.slots[b][4], sizeof(float) * 8 * cur, (void **)&d_out));  // loss[cur] | grad[cur,7]
+            TRY(reserve(c.slots[b][5], ws_bytes, &d_ws));
+            if (lb && !sth) {
+                TRY(reserve(c.slots[b][6], sizeof(float) * 16, (void **)&d_bounds));
+                DYNAX_CUDA_TRY(cudaMemcpyAsync(d_bounds, lb, sizeof(float) * 7, cudaMemcpyHostToDevice, st));
+                DYNAX_CUDA_TRY(cudaMemcpyAsync(d_bounds + 8, ub, sizeof(float) * 7, cudaMemcpyHostToDevice, st));
+            }
+            DYNAX_CUDA_TRY(cudaMemcpyAsync(d_th, theta + (sth ? 0 : n0 * 7), sizeof(float) * 7 * (sth ? 1 : cur),
+                                           cudaMemcpyHostToDevice, st));
+            DYNAX_CUDA_TRY(cudaMemcpyAsync(d_x0, x0 + n0 * 3, sizeof(float) * 3 * cur, cudaMemcpyHostToDevice, st));
+            if (su) DYNAX_CUDA_TRY(cudaMemcpyAsync(d_u, u, sizeof(float) * 5 * T, cudaMemcpyHostToDevice, st));
+            else TRY(copy_tile(d_u, (size_t)cur * 5, u + n0 * 5, (size_t)N * 5, cur, 5, T, cudaMemcpyHostToDevice, st));
+            if (stg) DYNAX_CUDA_TRY(cudaMemcpyAsync(d_tg, target, sizeof(float) * T, cudaMemcpyHostToDevice, st));
+            else TRY(copy_tile(d_tg, (size_t)cur, target + n0, (size_t)N, cur, 1, T, cudaMemcpyHostToDevice, st));
+            float *d_loss = d_out, *d_g = d_out + cur;
+            TRY(dynax_rc_loss_grad_f32(d_th, d_x0, d_u, d_tg, d_bounds, d_bounds ? d_bounds + 8 : nullptr, d_loss, d_g,
+                                       nullptr, cur, T, dt, flags, d_ws, ws_bytes, st));
+            if (sth) {
+                DYNAX_CUDA_TRY(cudaMemcpyAsync(&part[tile][0], d_loss, sizeof(float), cudaMemcpyDeviceToHost, st));
+                DYNAX_CUDA_TRY(cudaMemcpyAsync(&part[tile][1], d_g, sizeof(float) * 7, cudaMemcpyDeviceToHost, st));
+            } else {
+                DYNAX_CUDA_TRY(cudaMemcpyAsync(loss + n0, d_loss, sizeof(float) * cur, cudaMemcpyDeviceToHost, st));
+                DYNAX_CUDA_TRY(cudaMemcpyAsync(g_theta + n0 * 7, d_g, sizeof(float) * 7 * cur, cudaMemcpyDeviceToHost, st));
+            }
+            DYNAX_CUDA_TRY(cudaEventRecord(c.done[b], st));
+            return DYNAX_OK;
+        };
+        rc = body();
+    }
+    cudaError_t e0 = cudaStreamSynchronize(c.streams[0]);
+    cudaError_t e1 = cudaStreamSynchronize(c.streams[1]);
+    if (rc == DYNAX_OK && (e0 != cudaSuccess || e1 != cudaSuccess))
+        rc = fail(DYNAX_ERR_CUDA, "stream sync failed: %s", cudaGetErrorString(e0 != cudaSuccess ? e0 : e1));
+    if (rc == DYNAX_OK && sth) {
+        double L = 0.0, g[7] = {0, 0, 0, 0, 0, 0, 0};
+        for (int64_t t = 0; t < ntiles; ++t) {
+            L += part[t][0];
+            for (int j = 0; j < 7; ++j) g[j] += part[t][1 + j];
+        }
+        if (lb)  // the box penalty counts once for the shared parameter set (3-inverse.py:103-107)
+            for (int j = 0; j < 7; ++j) {
+                const double th = theta[j], lo = lb[j], hi = ub[j];
+                if (th > hi) { L += (th - hi) / hi; g[j] += 1.0 / hi; }
+                if (th < lo) { L += (lo - th) / hi; g[j] -= 1.0 / hi; }
+            }
+        loss[0] = (float)L;
+        for (int j = 0; j < 7; ++j) g_theta[j] = (float)g[j];
+    }
+    delete[] part;
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,50 @@
+// Kernel launch helpers shared by rc_api.cu and lti_api.cu.
+#pragma once
+#include "api_common.cuh"
+#include "rollout_adj.cuh"
+#include "rollout_fwd.cuh"
+
+namespace dynax {
+
+// Scratch layout: [0, kAccBytes) fp64 accumulators for shared-parameter sums, then checkpoints.
+constexpr size_t kAccBytes = 1024;
+constexpr int kMinKC = 8;  // smallest checkpoint interval any instantiated config uses
+
+inline size_t adj_workspace_bytes(int64_t N, int64_t T, int n) {
+    const int64_t C = (T + kMinKC - 1) / kMinKC;
+    return kAccBytes + sizeof(float) * (size_t)C * (size_t)n * (size_t)N;
+}
+
+template <class Model, int TN, int KF, int S, bool SHARED_U, int MINB>
+int launch_fwd(const FwdParams<Model> &P, cudaStream_t st) {
+    using Cfg = FwdCfg<Model, TN, KF, S, SHARED_U>;
+    auto kern = rollout_fwd_kernel<Model, TN, KF, S, SHARED_U, MINB>;
+    int rc = set_smem(kern, Cfg::SMEM_BYTES);
+    if (rc != DYNAX_OK) return rc;
+    const int64_t grid = (P.N + TN - 1) / TN;
+    if (grid > 0x7fffffffLL) return fail(DYNAX_ERR_INVALID_ARGUMENT, "N too large for one launch");
+    kern<<<(unsigned)grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(P);
+    DYNAX_CUDA_TRY(cudaGetLastError());
+    return DYNAX_OK;
+}
+
+template <class Model, int TN, int KC, int S, int MODE, bool SHARED_U, bool SHARED_TGT, int MINB>
+int launch_adj(const AdjParams<Model> &P, cudaStream_t st) {
+    using Cfg = AdjCfg<Model, TN, KC, S, MODE, SHARED_U, SHARED_TGT>;
+    static_assert(KC >= kMinKC, "workspace sizing assumes KC >= kMinKC");
+    auto kern = rollout_adj_kernel<Model, TN, KC, S, MODE, SHARED_U, SHARED_TGT, MINB>;
+    int rc = set_smem(kern, Cfg::SMEM_BYTES);
+    if (rc != DYNAX_OK) return rc;
+    const int64_t grid = (P.N + TN - 1) / TN;
+    if (grid > 0x7fffffffLL) return fail(DYNAX_ERR_INVALID_ARGUMENT, "N too large for one launch");
+    if (P.shared_theta) DYNAX_CUDA_TRY(cudaMemsetAsync(P.shared_acc, 0, kAccBytes, st));
+    kern<<<(unsigned)grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(P);
+    DYNAX_CUDA_TRY(cudaGetLastError());
+    if (P.shared_theta) {
+        shared_finalize_kernel<Model, MODE><<<1, 32, 0, st>>>(P.shared_acc, P.mp, P.gp, P.lb, P.ub, P.loss);
+        DYNAX_CUDA_TRY(cudaGetLastError());
+    }
+    return DYNAX_OK;
+}
+
+}  // namespace dynax

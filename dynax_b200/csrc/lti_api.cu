@@ -1,0 +1,121 @@
+// C-ABI entry points for dense linear block SSMs (DiscreteLinearSSM / ContinuousLinearSSM,
+// /root/reference/dynax/core/{discrete,continuous}_block_state_space.py:5-54).
+// Kernels are instantiated for a fixed list of (n,m,p); dynax_lti_supported() reports it.
+#include <string.h>
+
+#include "launch.cuh"
+
+// X(n, m, p): (4,3,4) is the shape of the reference's own test
+// (tests/test_forward_simulation.py:17-20); (3,5,1) is the 4R3C shape with free matrices.
+#define DYNAX_LTI_DIMS(X) \
+    X(1, 1, 1) X(2, 1, 1) X(2, 2, 1) X(2, 2, 2) X(3, 1, 1) X(3, 3, 1) X(3, 3, 3) X(3, 5, 1) X(4, 1, 1) X(4, 2, 2) X(4, 3, 4) X(4, 4, 4)
+
+namespace dynax {
+
+template <int n, int m, int p>
+static int lti_forward_t(const FwdParams<DenseModel<n, m, p>> &P, bool shared_u, cudaStream_t st) {
+    using M = DenseModel<n, m, p>;
+    if (shared_u) return launch_fwd<M, 128, 4, 2, true, 2>(P, st);
+    return launch_fwd<M, 128, 4, 2, false, 2>(P, st);
+}
+
+template <int n, int m, int p>
+static int lti_vjp_t(const AdjParams<DenseModel<n, m, p>> &P, bool shared_u, cudaStream_t st) {
+    using M = DenseModel<n, m, p>;
+    if (shared_u) return launch_adj<M, 128, 8, 2, ADJ_VJP, true, false, 1>(P, st);
+    return launch_adj<M, 128, 8, 2, ADJ_VJP, false, false, 1>(P, st);
+}
+
+}  // namespace dynax
+
+using namespace dynax;
+
+extern "C" {
+
+int dynax_lti_supported(int n, int m, int p) {
+#define X(a, b, c) \
+    if (n == a && m == b && p == c) return 1;
+    DYNAX_LTI_DIMS(X)
+#undef X
+    return 0;
+}
+
+int dynax_lti_forward_f32(const float *A, const float *B, const float *C, const float *D, const float *x0,
+                          const float *u, float *xsol, float *ysol, float *x_final, int64_t N, int64_t T, int n,
+                          int m, int p, float dt, uint32_t flags, void *stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (N < 0 || T < 0) return fail(DYNAX_ERR_INVALID_ARGUMENT, "negative N or T");
+    if (N == 0) return DYNAX_OK;
+    if (!A || !B || !C || !D || !x0 || !u) return fail(DYNAX_ERR_INVALID_ARGUMENT, "A,B,C,D,x0,u must be non-NULL");
+    if (flags & ~(DYNAX_SHARED_THETA | DYNAX_SHARED_U | DYNAX_DISCRETE))
+        return fail(DYNAX_ERR_INVALID_ARGUMENT, "unsupported flags 0x%x for lti_forward", flags);
+    if (!dynax_lti_supported(n, m, p))
+        return fail(DYNAX_ERR_UNSUPPORTED_DIMS, "no dense-LTI kernel instantiated for (n,m,p)=(%d,%d,%d)", n, m, p);
+    int rc = require_sm100();
+    if (rc != DYNAX_OK) return rc;
+    if (N == 0) return DYNAX_OK;
+    if (T == 0) {
+        if (x_final) DYNAX_CUDA_TRY(cudaMemcpyAsync(x_final, x0, sizeof(float) * n * N, cudaMemcpyDeviceToDevice, st));
+        return DYNAX_OK;
+    }
+    const bool rows16 = (N % 4) == 0;
+    const int bulk_in = rows16 && aligned16(u);
+    const int bulk_out = rows16 && (!xsol || aligned16(xsol)) && (!ysol || aligned16(ysol));
+#define X(a, b, c)                                                                     \
+    if (n == a && m == b && p == c) {                                                  \
+        FwdParams<DenseModel<a, b, c>> P;                                              \
+        P.mp.A = A; P.mp.B = B; P.mp.C = C; P.mp.D = D;                                \
+        P.mp.shared = (flags & DYNAX_SHARED_THETA) ? 1 : 0;                            \
+        P.x0 = x0; P.u = u; P.xsol = xsol; P.ysol = ysol; P.x_final = x_final;         \
+        P.N = N; P.T = T; P.dt = dt; P.discrete = (flags & DYNAX_DISCRETE) ? 1 : 0;    \
+        P.bulk_in = bulk_in; P.bulk_out = bulk_out;                                    \
+        return lti_forward_t<a, b, c>(P, (flags & DYNAX_SHARED_U) != 0, st);           \
+    }
+    DYNAX_LTI_DIMS(X)
+#undef X
+    return fail(DYNAX_ERR_UNSUPPORTED_DIMS, "unreachable");
+}
+
+int dynax_lti_vjp_f32(const float *A, const float *B, const float *C, const float *D, const float *x0,
+                      const float *u, const float *g_xsol, const float *g_ysol, float *g_A, float *g_B, float *g_C,
+                      float *g_D, float *g_x0, float *g_u, int64_t N, int64_t T, int n, int m, int p, float dt,
+                      uint32_t flags, void *ws, size_t ws_bytes, void *stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (N < 0 || T < 1) return fail(DYNAX_ERR_INVALID_ARGUMENT, "need N >= 0 and T >= 1");
+    if (N == 0) return DYNAX_OK;
+    if (!A || !B || !C || !D || !x0 || !u) return fail(DYNAX_ERR_INVALID_ARGUMENT, "A,B,C,D,x0,u must be non-NULL");
+    if (flags & ~(DYNAX_SHARED_THETA | DYNAX_SHARED_U | DYNAX_DISCRETE))
+        return fail(DYNAX_ERR_INVALID_ARGUMENT, "unsupported flags 0x%x for lti_vjp", flags);
+    if (!g_xsol && !g_ysol) return fail(DYNAX_ERR_INVALID_ARGUMENT, "need g_xsol or g_ysol");
+    if (g_u && (flags & DYNAX_SHARED_U))
+        return fail(DYNAX_ERR_INVALID_ARGUMENT, "g_u is not available with DYNAX_SHARED_U");
+    if (!dynax_lti_supported(n, m, p))
+        return fail(DYNAX_ERR_UNSUPPORTED_DIMS, "no dense-LTI kernel instantiated for (n,m,p)=(%d,%d,%d)", n, m, p);
+    int rc = require_sm100();
+    if (rc != DYNAX_OK) return rc;
+    if (N == 0) return DYNAX_OK;
+    const size_t need = adj_workspace_bytes(N, T, n);
+    if (!ws || ws_bytes < need)
+        return fail(DYNAX_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", need, ws ? ws_bytes : (size_t)0);
+    if (!aligned16(ws)) return fail(DYNAX_ERR_WORKSPACE, "workspace must be 16-byte aligned");
+    const int bulk = (N % 4) == 0 && aligned16(u) && (!g_xsol || aligned16(g_xsol)) && (!g_ysol || aligned16(g_ysol));
+#define X(a, b, c)                                                                               \
+    if (n == a && m == b && p == c) {                                                            \
+        AdjParams<DenseModel<a, b, c>> P;                                                        \
+        memset(&P, 0, sizeof(P));                                                                \
+        P.mp.A = A; P.mp.B = B; P.mp.C = C; P.mp.D = D;                                          \
+        P.mp.shared = (flags & DYNAX_SHARED_THETA) ? 1 : 0;                                      \
+        P.gp.gA = g_A; P.gp.gB = g_B; P.gp.gC = g_C; P.gp.gD = g_D;                              \
+        P.x0 = x0; P.u = u; P.g_xsol = g_xsol; P.g_ysol = g_ysol; P.g_x0 = g_x0; P.g_u = g_u;    \
+        P.shared_acc = reinterpret_cast<double *>(ws);                                           \
+        P.ckpt = reinterpret_cast<float *>(reinterpret_cast<char *>(ws) + kAccBytes);            \
+        P.N = N; P.T = T; P.dt = dt; P.discrete = (flags & DYNAX_DISCRETE) ? 1 : 0;              \
+        P.shared_theta = (flags & DYNAX_SHARED_THETA) ? 1 : 0; P.bulk = bulk;                    \
+        return lti_vjp_t<a, b, c>(P, (flags & DYNAX_SHARED_U) != 0, st);                         \
+    }
+    DYNAX_LTI_DIMS(X)
+#undef X
+    return fail(DYNAX_ERR_UNSUPPORTED_DIMS, "unreachable");
+}
+
+}  // extern "C"

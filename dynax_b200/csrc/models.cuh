@@ -1,0 +1,242 @@
+// Per-system model policies: coefficients live in registers, one thread == one system.
+//
+//   RCModel            Continuous4R3C / Discrete4R3C     /root/reference/dynax/models/RC.py:21-249
+//   DenseModel<n,m,p>  Discrete/ContinuousLinearSSM      dynax/core/{discrete,continuous}_block_state_space.py:5-54
+//
+// Both implement the split form of BaseBlockSSM (dynax/core/base_block_state_space.py:59-71):
+//   rhs = fxx(x) + fxu(u) = A x + B u          y = fyx(x) + fyu(u) = C x + D u
+// and the pieces of its transpose that the discrete adjoint needs.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dynax {
+
+struct RCModel {
+    static constexpr int n = 3, m = 5, p = 1;
+    static constexpr int NG = 13;   // accumulators: the 7 non-zeros of A and 6 of B
+    static constexpr int NOUT = 7;  // d/d[Cai,Cwe,Cwi,Re,Ri,Rw,Rg]
+    static constexpr bool HAS_BOX = true;  // parameter box penalty of examples/3-inverse.py:66-85,103-107
+
+    struct Ptrs {
+        const float *theta;  // [N,7] or [1,7]
+        int64_t stride;      // 7, or 0 when shared
+    };
+    struct GradPtrs {
+        float *g_theta;  // [N,7] (or [7] when shared)
+    };
+
+    float A00, A02, A11, A12, A20, A21, A22;
+    float B00, B01, B02, B10, B13, B24;
+
+    // theta -> A, B with the reference's expression shapes so coefficient rounding matches
+    // (RC.py:203-209, 224-229).  IEEE division: the library is built without fast-math.
+    __device__ __forceinline__ void load(const Ptrs &P, int64_t i) {
+        const float *th = P.theta + i * P.stride;
+        const float Cai = __ldg(th + 0), Cwe = __ldg(th + 1), Cwi = __ldg(th + 2), Re = __ldg(th + 3),
+                    Ri = __ldg(th + 4), Rw = __ldg(th + 5), Rg = __ldg(th + 6);
+        A00 = -1.0f / Cai * (1.0f / Rg + 1.0f / Ri);
+        A02 = 1.0f / (Cai * Ri);
+        A11 = -1.0f / Cwe * (1.0f / Re + 1.0f / Rw);
+        A12 = 1.0f / (Cwe * Rw);
+        A20 = 1.0f / (Cwi * Ri);
+        A21 = 1.0f / (Cwi * Rw);
+        A22 = -1.0f / Cwi * (1.0f / Rw + 1.0f / Ri);
+        B00 = 1.0f / (Cai * Rg);
+        B01 = 1.0f / Cai;
+        B02 = 1.0f / Cai;
+        B10 = 1.0f / (Cwe * Re);
+        B13 = 1.0f / Cwe;
+        B24 = 1.0f / Cwi;
+    }
+
+    // rhs = A x + B u  (structural zeros of A and B skipped: x + 0*y == x exactly for finite y)
+    __device__ __forceinline__ void rhs(const float *x, const float *u, float *r) const {
+        const float bu0 = B00 * u[0] + B01 * u[1] + B02 * u[2];
+        const float bu1 = B10 * u[0] + B13 * u[3];
+        const float bu2 = B24 * u[4];
+        const float ax0 = A00 * x[0] + A02 * x[2];
+        const float ax1 = A11 * x[1] + A12 * x[2];
+        const float ax2 = A20 * x[0] + A21 * x[1] + A22 * x[2];
+        r[0] = ax0 + bu0;
+        r[1] = ax1 + bu1;
+        r[2] = ax2 + bu2;
+    }
+
+    // y = C x + D u with C=[1,0,0], D=0  (RC.py:236-249)
+    __device__ __forceinline__ void out(const float *x, const float *, float *y) const { y[0] = x[0]; }
+
+    // G_A += s x^T, G_B += s u^T on the sparsity pattern (s = cotangent of rhs).  C, D are constants.
+    __device__ __forceinline__ void accum(float *G, const float *s, const float *, const float *x,
+                                          const float *u) const {
+        G[0] = fmaf(s[0], x[0], G[0]);    // A00
+        G[1] = fmaf(s[0], x[2], G[1]);    // A02
+        G[2] = fmaf(s[1], x[1], G[2]);    // A11
+        G[3] = fmaf(s[1], x[2], G[3]);    // A12
+        G[4] = fmaf(s[2], x[0], G[4]);    // A20
+        G[5] = fmaf(s[2], x[1], G[5]);    // A21
+        G[6] = fmaf(s[2], x[2], G[6]);    // A22
+        G[7] = fmaf(s[0], u[0], G[7]);    // B00
+        G[8] = fmaf(s[0], u[1], G[8]);    // B01
+        G[9] = fmaf(s[0], u[2], G[9]);    // B02
+        G[10] = fmaf(s[1], u[0], G[10]);  // B10
+        G[11] = fmaf(s[1], u[3], G[11]);  // B13
+        G[12] = fmaf(s[2], u[4], G[12]);  // B24
+    }
+
+    // ax = A^T s + C^T gy
+    __device__ __forceinline__ void adj_x(const float *s, const float *gy, float *ax) const {
+        ax[0] = (A00 * s[0] + A20 * s[2]) + gy[0];
+        ax[1] = A11 * s[1] + A21 * s[2];
+        ax[2] = A02 * s[0] + A12 * s[1] + A22 * s[2];
+    }
+
+    // gu = B^T s + D^T gy
+    __device__ __forceinline__ void adj_u(const float *s, const float *, float *gu) const {
+        gu[0] = B00 * s[0] + B10 * s[1];
+        gu[1] = B01 * s[0];
+        gu[2] = B02 * s[0];
+        gu[3] = B13 * s[1];
+        gu[4] = B24 * s[2];
+    }
+
+    // Chain rule dL/dtheta from dL/dA, dL/dB (derivatives of RC.py:203-209,224-229), in fp64.
+    __device__ __forceinline__ void finalize(const double *G, const Ptrs &P, int64_t i, double *g) const {
+        const float *th = P.theta + i * P.stride;
+        const double iCai = 1.0 / (double)th[0], iCwe = 1.0 / (double)th[1], iCwi = 1.0 / (double)th[2];
+        const double iRe = 1.0 / (double)th[3], iRi = 1.0 / (double)th[4], iRw = 1.0 / (double)th[5],
+                     iRg = 1.0 / (double)th[6];
+        const double gA00 = G[0], gA02 = G[1], gA11 = G[2], gA12 = G[3], gA20 = G[4], gA21 = G[5], gA22 = G[6];
+        const double gB00 = G[7], gB01 = G[8], gB02 = G[9], gB10 = G[10], gB13 = G[11], gB24 = G[12];
+        g[0] = -iCai * (gA00 * (double)A00 + gA02 * (double)A02 + gB00 * (double)B00 + (gB01 + gB02) * (double)B01);
+        g[1] = -iCwe * (gA11 * (double)A11 + gA12 * (double)A12 + gB10 * (double)B10 + gB13 * (double)B13);
+        g[2] = -iCwi * (gA20 * (double)A20 + gA21 * (double)A21 + gA22 * (double)A22 + gB24 * (double)B24);
+        g[3] = iCwe * iRe * iRe * (gA11 - gB10);
+        g[4] = iRi * iRi * (iCai * (gA00 - gA02) + iCwi * (gA22 - gA20));
+        g[5] = iRw * iRw * (iCwe * (gA11 - gA12) + iCwi * (gA22 - gA21));
+        g[6] = iCai * iRg * iRg * (gA00 - gB00);
+    }
+
+    __device__ __forceinline__ static float *grad_addr(const GradPtrs &Gp, int64_t i, int j) {
+        return Gp.g_theta ? Gp.g_theta + i * 7 + j : nullptr;
+    }
+};
+
+template <int N_, int M_, int P_>
+struct DenseModel {
+    static constexpr int n = N_, m = M_, p = P_;
+    static constexpr int NG = n * n + n * m + p * n + p * m;
+    static constexpr int NOUT = NG;
+    static constexpr bool HAS_BOX = false;
+
+    struct Ptrs {
+        const float *A, *B, *C, *D;  // [N|1, rows, cols] row-major matrices
+        int64_t shared;              // 1 -> one set for all systems
+    };
+    struct GradPtrs {
+        float *gA, *gB, *gC, *gD;  // each may be NULL
+    };
+
+    float A[n * n], B[n * m], C[p * n], D[p * m];
+
+    __device__ __forceinline__ void load(const Ptrs &P, int64_t i) {
+        const int64_t s = P.shared ? 0 : i;
+#pragma unroll
+        for (int k = 0; k < n * n; ++k) A[k] = __ldg(P.A + s * (n * n) + k);
+#pragma unroll
+        for (int k = 0; k < n * m; ++k) B[k] = __ldg(P.B + s * (n * m) + k);
+#pragma unroll
+        for (int k = 0; k < p * n; ++k) C[k] = __ldg(P.C + s * (p * n) + k);
+#pragma unroll
+        for (int k = 0; k < p * m; ++k) D[k] = __ldg(P.D + s * (p * m) + k);
+    }
+
+    __device__ __forceinline__ void rhs(const float *x, const float *u, float *r) const {
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+            float ax = A[i * n] * x[0];
+#pragma unroll
+            for (int j = 1; j < n; ++j) ax = fmaf(A[i * n + j], x[j], ax);
+            float bu = B[i * m] * u[0];
+#pragma unroll
+            for (int j = 1; j < m; ++j) bu = fmaf(B[i * m + j], u[j], bu);
+            r[i] = ax + bu;  // fxx(x) + fxu(u)   base_block_state_space.py:61
+        }
+    }
+
+    __device__ __forceinline__ void out(const float *x, const float *u, float *y) const {
+#pragma unroll
+        for (int i = 0; i < p; ++i) {
+            float cx = C[i * n] * x[0];
+#pragma unroll
+            for (int j = 1; j < n; ++j) cx = fmaf(C[i * n + j], x[j], cx);
+            float du = D[i * m] * u[0];
+#pragma unroll
+            for (int j = 1; j < m; ++j) du = fmaf(D[i * m + j], u[j], du);
+            y[i] = cx + du;  // fyx(x) + fyu(u)   base_block_state_space.py:69
+        }
+    }
+
+    __device__ __forceinline__ void accum(float *G, const float *s, const float *gy, const float *x,
+                                          const float *u) const {
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+#pragma unroll
+            for (int j = 0; j < n; ++j) G[i * n + j] = fmaf(s[i], x[j], G[i * n + j]);
+#pragma unroll
+            for (int j = 0; j < m; ++j) G[n * n + i * m + j] = fmaf(s[i], u[j], G[n * n + i * m + j]);
+        }
+#pragma unroll
+        for (int i = 0; i < p; ++i) {
+#pragma unroll
+            for (int j = 0; j < n; ++j)
+                G[n * n + n * m + i * n + j] = fmaf(gy[i], x[j], G[n * n + n * m + i * n + j]);
+#pragma unroll
+            for (int j = 0; j < m; ++j)
+                G[n * n + n * m + p * n + i * m + j] = fmaf(gy[i], u[j], G[n * n + n * m + p * n + i * m + j]);
+        }
+    }
+
+    __device__ __forceinline__ void adj_x(const float *s, const float *gy, float *ax) const {
+#pragma unroll
+        for (int j = 0; j < n; ++j) {
+            float v = A[j] * s[0];
+#pragma unroll
+            for (int i = 1; i < n; ++i) v = fmaf(A[i * n + j], s[i], v);
+            float w = C[j] * gy[0];
+#pragma unroll
+            for (int i = 1; i < p; ++i) w = fmaf(C[i * n + j], gy[i], w);
+            ax[j] = v + w;
+        }
+    }
+
+    __device__ __forceinline__ void adj_u(const float *s, const float *gy, float *gu) const {
+#pragma unroll
+        for (int j = 0; j < m; ++j) {
+            float v = B[j] * s[0];
+#pragma unroll
+            for (int i = 1; i < n; ++i) v = fmaf(B[i * m + j], s[i], v);
+            float w = D[j] * gy[0];
+#pragma unroll
+            for (int i = 1; i < p; ++i) w = fmaf(D[i * m + j], gy[i], w);
+            gu[j] = v + w;
+        }
+    }
+
+    __device__ __forceinline__ void finalize(const double *G, const Ptrs &, int64_t, double *g) const {
+#pragma unroll
+        for (int k = 0; k < NG; ++k) g[k] = G[k];
+    }
+
+    __device__ __forceinline__ static float *grad_addr(const GradPtrs &Gp, int64_t i, int j) {
+        if (j < n * n) return Gp.gA ? Gp.gA + i * (n * n) + j : nullptr;
+        j -= n * n;
+        if (j < n * m) return Gp.gB ? Gp.gB + i * (n * m) + j : nullptr;
+        j -= n * m;
+        if (j < p * n) return Gp.gC ? Gp.gC + i * (p * n) + j : nullptr;
+        j -= p * n;
+        return Gp.gD ? Gp.gD + i * (p * m) + j : nullptr;
+    }
+};
+
+}  // namespace dynax

@@ -1,0 +1,175 @@
+// C-ABI entry points for the 4R3C RC model (device-pointer flavour) + library-wide helpers.
+// See include/dynax_b200.h for the contract and the reference code each entry replaces.
+#include <stdlib.h>
+#include <string.h>
+
+#include "launch.cuh"
+
+namespace dynax {
+
+char *last_error_buf() {
+    static thread_local char buf[kErrBufLen] = {0};
+    return buf;
+}
+
+int require_sm100() {
+    int dev = -1;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess)
+        return fail(DYNAX_ERR_NO_DEVICE, "no CUDA device: %s (dynax_b200 has no CPU fallback)", cudaGetErrorString(e));
+    int major = 0;
+    e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (e != cudaSuccess) return fail(DYNAX_ERR_NO_DEVICE, "cudaDeviceGetAttribute: %s", cudaGetErrorString(e));
+    if (major != 10)
+        return fail(DYNAX_ERR_NO_DEVICE, "device %d is compute capability %d.x; this library is sm_100a only", dev, major);
+    return DYNAX_OK;
+}
+
+int device_info(DeviceInfo *out) {
+    int dev = 0;
+    DYNAX_CUDA_TRY(cudaGetDevice(&dev));
+    DYNAX_CUDA_TRY(cudaDeviceGetAttribute(&out->sm_count, cudaDevAttrMultiProcessorCount, dev));
+    DYNAX_CUDA_TRY(cudaDeviceGetAttribute(&out->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    return DYNAX_OK;
+}
+
+static int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
+// ------------------------------------------------------------------------------------------
+static int rc_forward(const float *theta, const float *x0, const float *u, float *xsol, float *ysol,
+                      float *x_final, int64_t N, int64_t T, float dt, uint32_t flags, cudaStream_t st) {
+    if (N < 0 || T < 0) return fail(DYNAX_ERR_INVALID_ARGUMENT, "negative N or T");
+    if (N == 0) return DYNAX_OK;
+    if (!theta || !x0 || !u) return fail(DYNAX_ERR_INVALID_ARGUMENT, "theta, x0 and u must be non-NULL");
+    if (flags & ~(DYNAX_SHARED_THETA | DYNAX_SHARED_U | DYNAX_DISCRETE))
+        return fail(DYNAX_ERR_INVALID_ARGUMENT, "unsupported flags 0x%x for rc_forward", flags);
+    int rc = require_sm100();
+    if (rc != DYNAX_OK) return rc;
+    if (N == 0) return DYNAX_OK;
+    if (T == 0) {  // empty scan: nothing to emit, final state is the initial state
+        if (x_final) DYNAX_CUDA_TRY(cudaMemcpyAsync(x_final, x0, sizeof(float) * 3 * N, cudaMemcpyDeviceToDevice, st));
+        return DYNAX_OK;
+    }
+    FwdParams<RCModel> P;
+    P.mp.theta = theta;
+    P.mp.stride = (flags & DYNAX_SHARED_THETA) ? 0 : 7;
+    P.x0 = x0; P.u = u; P.xsol = xsol; P.ysol = ysol; P.x_final = x_final;
+    P.N = N; P.T = T; P.dt = dt;
+    P.discrete = (flags & DYNAX_DISCRETE) ? 1 : 0;
+    const bool rows16 = (N % 4) == 0;  // every [*,N,w] row starts and ends on a 16-byte boundary
+    P.bulk_in = rows16 && aligned16(u);
+    P.bulk_out = rows16 && (!xsol || aligned16(xsol)) && (!ysol || aligned16(ysol));
+    if (env_int("DYNAX_NO_BULK", 0)) P.bulk_in = P.bulk_out = 0;
+    if (flags & DYNAX_SHARED_U) return launch_fwd<RCModel, 128, 4, 4, true, 4>(P, st);
+    switch (env_int("DYNAX_FWD_CFG", 0)) {
+        default:
+        case 0: return launch_fwd<RCModel, 128, 2, 4, false, 6>(P, st);
+        case 1: return launch_fwd<RCModel, 128, 4, 4, false, 3>(P, st);
+        case 2: return launch_fwd<RCModel, 64, 4, 4, false, 6>(P, st);
+        case 3: return launch_fwd<RCModel, 128, 8, 2, false, 3>(P, st);
+    }
+}
+
+template <int MODE>
+static int rc_adjoint(const float *theta, const float *x0, const float *u, const float *target, const float *lb,
+                      const float *ub, const float *g_xsol, const float *g_ysol, float *loss, float *g_theta,
+                      float *g_x0, float *g_u, int64_t N, int64_t T, float dt, uint32_t flags, void *ws,
+                      size_t ws_bytes, cudaStream_t st) {
+    if (N < 0 || T < 1) return fail(DYNAX_ERR_INVALID_ARGUMENT, "need N >= 0 and T >= 1");
+    if (N == 0) return DYNAX_OK;
+    if (!theta || !x0 || !u) return fail(DYNAX_ERR_INVALID_ARGUMENT, "theta, x0 and u must be non-NULL");
+    const uint32_t allowed = DYNAX_SHARED_THETA | DYNAX_SHARED_U | DYNAX_DISCRETE | (MODE == ADJ_MSE ? DYNAX_SHARED_TARGET : 0u);
+    if (flags & ~allowed) return fail(DYNAX_ERR_INVALID_ARGUMENT, "unsupported flags 0x%x", flags);
+    if (MODE == ADJ_MSE && (!target || !loss)) return fail(DYNAX_ERR_INVALID_ARGUMENT, "target and loss must be non-NULL");
+    if (MODE == ADJ_MSE && ((lb == nullptr) != (ub == nullptr)))
+        return fail(DYNAX_ERR_INVALID_ARGUMENT, "lb and ub must both be given or both be NULL");
+    if (MODE == ADJ_VJP && !g_xsol && !g_ysol) return fail(DYNAX_ERR_INVALID_ARGUMENT, "need g_xsol or g_ysol");
+    if (MODE == ADJ_VJP && g_u && (flags & DYNAX_SHARED_U))
+        return fail(DYNAX_ERR_INVALID_ARGUMENT, "g_u is not available with DYNAX_SHARED_U (sum it on the caller side)");
+    int rc = require_sm100();
+    if (rc != DYNAX_OK) return rc;
+    if (N == 0) return DYNAX_OK;
+    const size_t need = adj_workspace_bytes(N, T, 3);
+    if (!ws || ws_bytes < need)
+        return fail(DYNAX_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", need, ws ? ws_bytes : (size_t)0);
+    if (!aligned16(ws)) return fail(DYNAX_ERR_WORKSPACE, "workspace must be 16-byte aligned");
+
+    AdjParams<RCModel> P;
+    memset(&P, 0, sizeof(P));
+    P.mp.theta = theta;
+    P.mp.stride = (flags & DYNAX_SHARED_THETA) ? 0 : 7;
+    P.gp.g_theta = g_theta;
+    P.x0 = x0; P.u = u; P.target = target; P.lb = lb; P.ub = ub; P.loss = loss;
+    P.g_xsol = g_xsol; P.g_ysol = g_ysol; P.g_x0 = g_x0; P.g_u = g_u;
+    P.shared_acc = reinterpret_cast<double *>(ws);
+    P.ckpt = reinterpret_cast<float *>(reinterpret_cast<char *>(ws) + kAccBytes);
+    P.N = N; P.T = T; P.dt = dt;
+    P.discrete = (flags & DYNAX_DISCRETE) ? 1 : 0;
+    P.shared_theta = (flags & DYNAX_SHARED_THETA) ? 1 : 0;
+    P.bulk = (N % 4) == 0 && aligned16(u) && (!target || aligned16(target)) && (!g_xsol || aligned16(g_xsol)) &&
+             (!g_ysol || aligned16(g_ysol));
+    if (env_int("DYNAX_NO_BULK", 0)) P.bulk = 0;
+    const bool su = flags & DYNAX_SHARED_U, stg = flags & DYNAX_SHARED_TARGET;
+    if constexpr (MODE == ADJ_VJP) {
+        if (su) return launch_adj<RCModel, 128, 8, 2, ADJ_VJP, true, false, 2>(P, st);
+        return launch_adj<RCModel, 128, 8, 2, ADJ_VJP, false, false, 2>(P, st);
+    } else {
+        if (su && stg) return launch_adj<RCModel, 128, 16, 2, ADJ_MSE, true, true, 2>(P, st);
+        if (su) return launch_adj<RCModel, 128, 16, 2, ADJ_MSE, true, false, 2>(P, st);
+        if (stg) return launch_adj<RCModel, 128, 16, 2, ADJ_MSE, false, true, 2>(P, st);
+        switch (env_int("DYNAX_ADJ_CFG", 0)) {
+            default:
+            case 0: return launch_adj<RCModel, 128, 16, 2, ADJ_MSE, false, false, 2>(P, st);
+            case 1: return launch_adj<RCModel, 64, 16, 2, ADJ_MSE, false, false, 4>(P, st);
+            case 2: return launch_adj<RCModel, 128, 8, 4, ADJ_MSE, false, false, 2>(P, st);
+            case 3: return launch_adj<RCModel, 64, 16, 4, ADJ_MSE, false, false, 2>(P, st);
+            case 4: return launch_adj<RCModel, 128, 8, 2, ADJ_MSE, false, false, 4>(P, st);
+        }
+    }
+}
+
+}  // namespace dynax
+
+using namespace dynax;
+
+extern "C" {
+
+int dynax_version(void) { return DYNAX_ABI_VERSION; }
+
+const char *dynax_last_error(void) { return last_error_buf(); }
+
+int dynax_device_check(void) { return require_sm100(); }
+
+size_t dynax_workspace_bytes(int op, int64_t N, int64_t T, int n, int m, int p, uint32_t flags) {
+    (void)m; (void)p; (void)flags;
+    switch (op) {
+        case DYNAX_OP_RC_LOSS_GRAD:
+        case DYNAX_OP_RC_VJP: return adj_workspace_bytes(N, T, 3);
+        case DYNAX_OP_LTI_VJP: return adj_workspace_bytes(N, T, n);
+        default: return 0;
+    }
+}
+
+int dynax_rc_forward_f32(const float *theta, const float *x0, const float *u, float *xsol, float *ysol,
+                         float *x_final, int64_t N, int64_t T, float dt, uint32_t flags, void *stream) {
+    return rc_forward(theta, x0, u, xsol, ysol, x_final, N, T, dt, flags, static_cast<cudaStream_t>(stream));
+}
+
+int dynax_rc_loss_grad_f32(const float *theta, const float *x0, const float *u, const float *target,
+                           const float *lb, const float *ub, float *loss, float *g_theta, float *g_x0, int64_t N,
+                           int64_t T, float dt, uint32_t flags, void *ws, size_t ws_bytes, void *stream) {
+    return rc_adjoint<ADJ_MSE>(theta, x0, u, target, lb, ub, nullptr, nullptr, loss, g_theta, g_x0, nullptr, N, T, dt,
+                               flags, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int dynax_rc_vjp_f32(const float *theta, const float *x0, const float *u, const float *g_xsol, const float *g_ysol,
+                     float *g_theta, float *g_x0, float *g_u, int64_t N, int64_t T, float dt, uint32_t flags,
+                     void *ws, size_t ws_bytes, void *stream) {
+    return rc_adjoint<ADJ_VJP>(theta, x0, u, nullptr, nullptr, nullptr, g_xsol, g_ysol, nullptr, g_theta, g_x0, g_u, N,
+                               T, dt, flags, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

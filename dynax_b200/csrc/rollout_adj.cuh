@@ -1,0 +1,367 @@
+// Reverse-mode kernel: loss + gradient (or a general VJP) of the rollout in ONE launch.
+// Replaces jax.value_and_grad through the nn.scan (/root/reference/examples/3-inverse.py:96-112):
+// instead of storing the per-step residuals x_k like XLA's scan transpose, it is a CHECKPOINTED
+// discrete adjoint:
+//
+//   phase 1 (forward sweep)  stream u forward; every KC steps store the state (3 floats) to `ckpt`
+//   phase 2 (reverse sweep)  for each KC-step segment, last to first: reload the checkpoint,
+//                            recompute the KC states into REGISTERS, then run the adjoint recurrence
+//                               s = dt*a;  G_A += s x_k^T;  G_B += s u_k^T;  a = a + A^T s + C^T g^y_k
+//                            backwards over the segment.
+//
+// One thread == one system.  u (and target / cotangent) tiles of KC rows are staged in shared
+// memory by a producer warp with cp.async.bulk (TMA 1-D) into an S-stage mbarrier ring that runs
+// straight through both phases; a tile is read twice from smem (recompute + reverse) but only
+// once per sweep from HBM, so traffic is 2*(4m+4) B/step + 24/KC B/step of checkpoints.
+//
+// Numerics (SURVEY.md finding #9): states and adjoint are fp32; the outer-product sums are fp32
+// within a segment and folded into fp64 totals once per segment, which removes the O(T) fp32
+// accumulation error that dominates an all-fp32 BPTT.
+#pragma once
+#include "models.cuh"
+#include "ptx.cuh"
+#include "rollout_fwd.cuh"  // align4i
+
+namespace dynax {
+
+enum : int { ADJ_MSE = 0, ADJ_VJP = 1 };
+
+template <class Model>
+struct AdjParams {
+    typename Model::Ptrs mp;
+    typename Model::GradPtrs gp;
+    const float *x0;      // [N,n]
+    const float *u;       // [T,N,m] or [T,1,m]
+    const float *target;  // MSE: [T,N] or [T]
+    const float *lb, *ub; // MSE: [NOUT] or NULL
+    float *loss;          // MSE: [N] (per-system) -- unused when shared_theta (goes to shared_acc)
+    const float *g_xsol;  // VJP: [T,N,n] or NULL
+    const float *g_ysol;  // VJP: [T,N,p] or NULL
+    float *g_x0;          // [N,n] or NULL
+    float *g_u;           // VJP: [T,N,m] or NULL
+    float *ckpt;          // ws: [C][n][N]
+    double *shared_acc;   // ws: [NOUT+1] when shared_theta (zeroed by the caller)
+    int64_t N, T;
+    float dt;
+    int discrete, bulk, shared_theta;
+};
+
+template <class Model, int TN, int KC, int S, int MODE, bool SHARED_U, bool SHARED_TGT>
+struct AdjCfg {
+    static constexpr int n = Model::n, m = Model::m, p = Model::p;
+    static constexpr int U_ROW = SHARED_U ? m : TN * m;
+    static constexpr int A1_ROW = (MODE == ADJ_MSE) ? (SHARED_TGT ? 1 : TN) : TN * p;  // target | g_y
+    static constexpr int A2_ROW = (MODE == ADJ_MSE) ? 0 : TN * n;                      // g_x
+    static constexpr int U_OFF = 0;
+    static constexpr int A1_OFF = align4i(KC * U_ROW);
+    static constexpr int A2_OFF = A1_OFF + align4i(KC * A1_ROW);
+    static constexpr int STAGE = A2_OFF + align4i(KC * A2_ROW);
+    static constexpr int NBAR = 2 * S;
+    static constexpr size_t SMEM_BYTES = sizeof(float) * (size_t)(S * STAGE) + sizeof(uint64_t) * NBAR;
+    static constexpr int THREADS = TN + 32;
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <class Model, int TN, int KC, int S, int MODE, bool SHARED_U, bool SHARED_TGT, int MINB>
+__global__ void __launch_bounds__(TN + 32, MINB) rollout_adj_kernel(const AdjParams<Model> P) {
+    using Cfg = AdjCfg<Model, TN, KC, S, MODE, SHARED_U, SHARED_TGT>;
+    constexpr int n = Cfg::n, m = Cfg::m, p = Cfg::p;
+    constexpr int NG = Model::NG, NOUT = Model::NOUT;
+    constexpr int U_ROW = Cfg::U_ROW, A1_ROW = Cfg::A1_ROW, A2_ROW = Cfg::A2_ROW;
+    static_assert(MODE == ADJ_VJP || p == 1, "fused MSE assumes a scalar output");
+    static_assert((TN % 32) == 0 && (S & (S - 1)) == 0, "TN multiple of 32, S power of two");
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *s_in = reinterpret_cast<float *>(smem_raw);
+    uint64_t *full = reinterpret_cast<uint64_t *>(s_in + S * Cfg::STAGE);
+    uint64_t *empty = full + S;
+
+    const int tid = threadIdx.x;
+    const int64_t N = P.N, T = P.T;
+    const int64_t n0 = (int64_t)blockIdx.x * TN;
+    const int valid = (int)((N - n0) < TN ? (N - n0) : TN);
+    const int64_t C = (T + KC - 1) / KC;  // number of segments
+    const int64_t Q = 2 * C - 1;          // chunks through the ring: C-1 forward + C reverse
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            ptx::mbar_init(&full[s], 1);
+            ptx::mbar_init(&empty[s], TN / 32);
+        }
+        ptx::fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (tid >= TN) {
+        // ------------------------------- producer warp -------------------------------
+        const int lane = tid - TN;
+        const uint64_t pol = ptx::policy_evict_first();
+
+        // Copy `rows` rows of one stream into the stage.  pass 0: plain loads by all lanes (shared
+        // streams, or everything when !bulk); pass 1: TMA bulk copies by lane 0.
+        auto stream = [&](int pass, float *dst, int row_stride, const float *g, int w, bool shared, int64_t k0,
+                          int rows, uint64_t *bar) -> uint32_t {
+            if (g == nullptr) return 0;
+            if (shared) {
+                if (pass == 0) {
+                    const float *src = g + k0 * w;
+                    for (int r = 0; r < rows; ++r)
+                        for (int i = lane; i < w; i += 32) dst[r * row_stride + i] = __ldg(src + r * w + i);
+                }
+                return 0;
+            }
+            if (!P.bulk) {
+                if (pass == 0)
+                    for (int r = 0; r < rows; ++r) {
+                        const float *src = g + ((k0 + r) * N + n0) * w;
+                        for (int i = lane; i < valid * w; i += 32) dst[r * row_stride + i] = __ldg(src + i);
+                    }
+                return 0;
+            }
+            const uint32_t row_bytes = (uint32_t)valid * w * 4u;
+            if (pass == 1 && lane == 0)
+                for (int r = 0; r < rows; ++r)
+                    ptx::bulk_g2s(dst + r * row_stride, g + ((k0 + r) * N + n0) * w, row_bytes, bar, pol);
+            return row_bytes * (uint32_t)rows;
+        };
+
+        auto load_q = [&](int64_t q) {
+            const int s = (int)(q % S);
+            float *st = s_in + s * Cfg::STAGE;
+            const bool fwd = q < C - 1;
+            const int64_t seg = fwd ? q : (2 * C - 2 - q);
+            const int64_t k0 = seg * KC;
+            const int rows = (int)((T - k0) < KC ? (T - k0) : KC);
+            uint32_t bytes = 0;
+#pragma unroll
+            for (int pass = 0; pass < 2; ++pass) {
+                uint32_t b = stream(pass, st + Cfg::U_OFF, U_ROW, P.u, m, SHARED_U, k0, rows, &full[s]);
+                if (!fwd) {
+                    if (MODE == ADJ_MSE) {
+                        b += stream(pass, st + Cfg::A1_OFF, A1_ROW, P.target, 1, SHARED_TGT, k0, rows, &full[s]);
+                    } else {
+                        b += stream(pass, st + Cfg::A1_OFF, A1_ROW, P.g_ysol, p, false, k0, rows, &full[s]);
+                        b += stream(pass, st + Cfg::A2_OFF, A2_ROW, P.g_xsol, n, false, k0, rows, &full[s]);
+                    }
+                }
+                if (pass == 0) {
+                    bytes = b;
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (bytes) ptx::mbar_arrive_expect_tx(&full[s], bytes);
+                        else ptx::mbar_arrive(&full[s]);
+                    }
+                }
+            }
+        };
+
+        for (int64_t q = 0; q < Q && q < S; ++q) load_q(q);
+        for (int64_t q = 0; q + S < Q; ++q) {
+            ptx::mbar_wait(&empty[q % S], (uint32_t)((q / S) & 1));
+            load_q(q + S);
+        }
+        return;
+    }
+
+    // --------------------------------- consumers ---------------------------------
+    const int lane = tid & 31;
+    const bool active = tid < valid;
+    const int64_t i = active ? (n0 + tid) : (N - 1);
+    Model M;
+    M.load(P.mp, i);
+    float xc[n];  // state at the start of the current chunk / segment
+#pragma unroll
+    for (int d = 0; d < n; ++d) xc[d] = __ldg(P.x0 + i * n + d);
+    const float dt = P.dt;
+    const bool discrete = P.discrete != 0;
+    float *ck = P.ckpt + (n0 + tid);  // ckpt[(seg*n + d)*N + system]; only touched when active
+
+    int64_t q = 0;
+    // ---- phase 1: forward sweep over segments 0..C-2, checkpointing the state at each start
+    for (; q < C - 1; ++q) {
+        const int s = (int)(q % S);
+        if (active) {
+#pragma unroll
+            for (int d = 0; d < n; ++d) ck[(q * n + d) * N] = xc[d];
+        }
+        ptx::mbar_wait(&full[s], (uint32_t)((q / S) & 1));
+        const float *in = s_in + s * Cfg::STAGE + Cfg::U_OFF + (SHARED_U ? 0 : tid * m);
+#pragma unroll
+        for (int j = 0; j < KC; ++j) {
+            float u[m], r[n];
+#pragma unroll
+            for (int d = 0; d < m; ++d) u[d] = in[j * U_ROW + d];
+            M.rhs(xc, u, r);
+#pragma unroll
+            for (int d = 0; d < n; ++d) xc[d] = discrete ? r[d] : fmaf(dt, r[d], xc[d]);
+        }
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&empty[s]);
+    }
+
+    // ---- phase 2: reverse sweep
+    float a[n];  // adjoint of x_{k+1}
+    float Gp[NG];
+    double Gt[NG];
+    float sq = 0.f;
+    double sqt = 0.0;
+#pragma unroll
+    for (int d = 0; d < n; ++d) a[d] = 0.f;
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+        Gp[g] = 0.f;
+        Gt[g] = 0.0;
+    }
+    const float c2T = 2.0f / (float)T;
+
+    for (int64_t seg = C - 1; seg >= 0; --seg, ++q) {
+        const int s = (int)(q % S);
+        const int64_t k0 = seg * KC;
+        const int rows = (int)((T - k0) < KC ? (T - k0) : KC);
+        float xs[KC][n];
+#pragma unroll
+        for (int d = 0; d < n; ++d) xs[0][d] = xc[d];
+        if (seg > 0 && active) {  // prefetch the next (earlier) segment's checkpoint
+#pragma unroll
+            for (int d = 0; d < n; ++d) xc[d] = ck[((seg - 1) * n + d) * N];
+        }
+        ptx::mbar_wait(&full[s], (uint32_t)((q / S) & 1));
+        const float *st = s_in + s * Cfg::STAGE;
+        const float *in = st + Cfg::U_OFF + (SHARED_U ? 0 : tid * m);
+
+        // recompute x_{k0+1} .. x_{k0+rows-1} into registers
+#pragma unroll
+        for (int j = 0; j + 1 < KC; ++j) {
+            if (j + 1 < rows) {
+                float u[m], r[n];
+#pragma unroll
+                for (int d = 0; d < m; ++d) u[d] = in[j * U_ROW + d];
+                M.rhs(xs[j], u, r);
+#pragma unroll
+                for (int d = 0; d < n; ++d) xs[j + 1][d] = discrete ? r[d] : fmaf(dt, r[d], xs[j][d]);
+            }
+        }
+        // adjoint recurrence, k = k0+rows-1 .. k0
+#pragma unroll
+        for (int j = KC - 1; j >= 0; --j) {
+            if (j < rows) {
+                float u[m], gy[p], sv[n], ax[n];
+#pragma unroll
+                for (int d = 0; d < m; ++d) u[d] = in[j * U_ROW + d];
+                if (MODE == ADJ_MSE) {
+                    float y[p];
+                    M.out(xs[j], u, y);
+                    const float tg = st[Cfg::A1_OFF + j * A1_ROW + (SHARED_TGT ? 0 : tid)];
+                    const float res = y[0] - tg;  // 3-inverse.py:100
+                    sq = fmaf(res, res, sq);
+                    gy[0] = c2T * res;  // d mean(res^2)/dy_k
+                } else {
+#pragma unroll
+                    for (int d = 0; d < p; ++d)
+                        gy[d] = P.g_ysol ? st[Cfg::A1_OFF + j * A1_ROW + tid * p + d] : 0.f;
+                    if (P.g_xsol) {
+#pragma unroll
+                        for (int d = 0; d < n; ++d) a[d] += st[Cfg::A2_OFF + j * A2_ROW + tid * n + d];
+                    }
+                }
+#pragma unroll
+                for (int d = 0; d < n; ++d) sv[d] = discrete ? a[d] : dt * a[d];  // cotangent of rhs
+                M.accum(Gp, sv, gy, xs[j], u);
+                if (MODE == ADJ_VJP && P.g_u != nullptr && active) {
+                    float gu[m];
+                    M.adj_u(sv, gy, gu);
+                    float *dst = P.g_u + ((k0 + j) * N + i) * m;
+#pragma unroll
+                    for (int d = 0; d < m; ++d) dst[d] = gu[d];
+                }
+                M.adj_x(sv, gy, ax);
+#pragma unroll
+                for (int d = 0; d < n; ++d) a[d] = discrete ? ax[d] : (a[d] + ax[d]);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&empty[s]);
+        // fold the segment's fp32 partial sums into the fp64 totals
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+            Gt[g] += (double)Gp[g];
+            Gp[g] = 0.f;
+        }
+        if (MODE == ADJ_MSE) {
+            sqt += (double)sq;
+            sq = 0.f;
+        }
+    }
+
+    // ---- finalize: chain rule to the model parameters, loss, penalty, outputs
+    double g[NOUT];
+    M.finalize(Gt, P.mp, i, g);
+    double loss = (MODE == ADJ_MSE) ? sqt / (double)T : 0.0;
+    if (MODE == ADJ_MSE && P.lb != nullptr && P.ub != nullptr && !P.shared_theta) {
+        if constexpr (Model::HAS_BOX) {  // RC parameter box (3-inverse.py:66-85, 103-107; normaliser = ub)
+            const float *th = P.mp.theta + i * P.mp.stride;
+#pragma unroll
+            for (int j = 0; j < NOUT; ++j) {
+                const double t = (double)th[j], lo = (double)P.lb[j], hi = (double)P.ub[j];
+                if (t > hi) { loss += (t - hi) / hi; g[j] += 1.0 / hi; }
+                if (t < lo) { loss += (lo - t) / hi; g[j] -= 1.0 / hi; }
+            }
+        }
+    }
+    if (P.g_x0 != nullptr && active) {
+#pragma unroll
+        for (int d = 0; d < n; ++d) P.g_x0[i * n + d] = a[d];
+    }
+    if (!P.shared_theta) {
+        if (active) {
+#pragma unroll
+            for (int j = 0; j < NOUT; ++j) {
+                float *dst = Model::grad_addr(P.gp, i, j);
+                if (dst) *dst = (float)g[j];
+            }
+            if (MODE == ADJ_MSE && P.loss) P.loss[i] = (float)loss;
+        }
+    } else {
+        // Sum over the CTA's systems (warp shuffle -> one fp64 atomic per warp and output).
+#pragma unroll
+        for (int j = 0; j < NOUT; ++j) {
+            const double v = warp_sum(active ? g[j] : 0.0);
+            if (lane == 0) atomicAdd(P.shared_acc + j, v);
+        }
+        if (MODE == ADJ_MSE) {
+            const double v = warp_sum(active ? loss : 0.0);
+            if (lane == 0) atomicAdd(P.shared_acc + NOUT, v);
+        }
+    }
+}
+
+// Converts the fp64 shared-parameter accumulators to the caller's fp32 outputs; adds the bound
+// penalty ONCE for the fused-MSE op.
+template <class Model, int MODE>
+__global__ void shared_finalize_kernel(const double *acc, typename Model::Ptrs mp, typename Model::GradPtrs gp,
+                                       const float *lb, const float *ub, float *loss) {
+    constexpr int NOUT = Model::NOUT;
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double L = (MODE == ADJ_MSE) ? acc[NOUT] : 0.0;
+    for (int j = 0; j < NOUT; ++j) {
+        double g = acc[j];
+        if constexpr (MODE == ADJ_MSE && Model::HAS_BOX) {
+            if (lb != nullptr && ub != nullptr) {
+                const double t = (double)mp.theta[j], lo = (double)lb[j], hi = (double)ub[j];
+                if (t > hi) { L += (t - hi) / hi; g += 1.0 / hi; }
+                if (t < lo) { L += (lo - t) / hi; g -= 1.0 / hi; }
+            }
+        }
+        float *dst = Model::grad_addr(gp, 0, j);
+        if (dst) *dst = (float)g;
+    }
+    if (MODE == ADJ_MSE && loss) *loss = (float)L;
+}
+
+}  // namespace dynax

@@ -1,0 +1,225 @@
+// Forward rollout kernel: DifferentiableSimulator.__call__ for N systems at once
+// (/root/reference/dynax/simulators/simulator.py:36-53 -- the nn.scan body and its lift).
+//
+// Mapping: one thread == one system; the model coefficients and the state live in registers
+// for the whole horizon.  A CTA owns TN consecutive systems and streams the time axis:
+//
+//   producer warp (1 elected lane)  u[k0:k0+KF, n0:n0+TN, :]  --cp.async.bulk (TMA 1-D)-->  smem ring (S stages)
+//   TN consumer threads             read their m inputs per step from smem (stride m words: conflict-free
+//                                   for odd m), step the state, write x_{k+1}/y_k into an smem out-tile
+//   producer warp                   out-tile --cp.async.bulk--> xsol/ysol rows (fully coalesced 16B-multiple rows)
+//
+// Synchronisation is mbarrier-only (full/empty per in-stage, ofull/ofree per out-stage); warps of a
+// CTA drift freely within the ring.  If N is not a multiple of 4 (rows not 16-byte multiples) the
+// producer warp falls back to plain coalesced ld/st for that launch -- same pipeline, no TMA.
+#pragma once
+#include "models.cuh"
+#include "ptx.cuh"
+
+namespace dynax {
+
+template <class Model>
+struct FwdParams {
+    typename Model::Ptrs mp;
+    const float *x0;  // [N,n]
+    const float *u;   // [T,N,m] or [T,1,m]
+    float *xsol;      // [T,N,n] or NULL
+    float *ysol;      // [T,N,p] or NULL
+    float *x_final;   // [N,n] or NULL
+    int64_t N, T;
+    float dt;
+    int discrete;
+    int bulk_in, bulk_out;
+};
+
+__host__ __device__ constexpr int align4i(int x) { return (x + 3) & ~3; }
+
+template <class Model, int TN, int KF, int S, bool SHARED_U>
+struct FwdCfg {
+    static constexpr int n = Model::n, m = Model::m, p = Model::p;
+    static constexpr int IN_ROW = SHARED_U ? m : TN * m;
+    static constexpr int IN_STAGE = align4i(KF * IN_ROW);
+    static constexpr int XO_STAGE = KF * TN * n;
+    static constexpr int YO_STAGE = KF * TN * p;
+    static constexpr int NBAR = 2 * S + 4;
+    static constexpr size_t SMEM_BYTES =
+        sizeof(float) * (size_t)(S * IN_STAGE + 2 * XO_STAGE + 2 * YO_STAGE) + sizeof(uint64_t) * NBAR;
+    static constexpr int THREADS = TN + 32;
+};
+
+template <class Model, int TN, int KF, int S, bool SHARED_U, int MINB>
+__global__ void __launch_bounds__(TN + 32, MINB) rollout_fwd_kernel(const FwdParams<Model> P) {
+    using Cfg = FwdCfg<Model, TN, KF, S, SHARED_U>;
+    constexpr int n = Cfg::n, m = Cfg::m, p = Cfg::p;
+    constexpr int IN_ROW = Cfg::IN_ROW, IN_STAGE = Cfg::IN_STAGE, XO_STAGE = Cfg::XO_STAGE,
+                  YO_STAGE = Cfg::YO_STAGE;
+    static_assert((TN % 32) == 0 && (S & (S - 1)) == 0, "TN multiple of 32, S power of two");
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *s_in = reinterpret_cast<float *>(smem_raw);
+    float *s_xo = s_in + S * IN_STAGE;
+    float *s_yo = s_xo + 2 * XO_STAGE;
+    uint64_t *full = reinterpret_cast<uint64_t *>(s_yo + 2 * YO_STAGE);
+    uint64_t *empty = full + S;
+    uint64_t *ofull = empty + S;
+    uint64_t *ofree = ofull + 2;
+
+    const int tid = threadIdx.x;
+    const int64_t N = P.N, T = P.T;
+    const int64_t n0 = (int64_t)blockIdx.x * TN;
+    const int valid = (int)((N - n0) < TN ? (N - n0) : TN);
+    const bool emit_x = P.xsol != nullptr, emit_y = P.ysol != nullptr;
+    const bool emit = emit_x || emit_y;
+    const int64_t C = (T + KF - 1) / KF;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            ptx::mbar_init(&full[s], 1);
+            ptx::mbar_init(&empty[s], TN / 32);
+        }
+        ptx::mbar_init(&ofull[0], TN / 32);
+        ptx::mbar_init(&ofull[1], TN / 32);
+        ptx::mbar_init(&ofree[0], 1);
+        ptx::mbar_init(&ofree[1], 1);
+        ptx::fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (tid >= TN) {
+        // ------------------------------- producer warp -------------------------------
+        const int lane = tid - TN;
+        const uint64_t pol = ptx::policy_evict_first();
+
+        auto load_chunk = [&](int64_t c) {
+            const int s = (int)(c % S);
+            const int64_t k0 = c * KF;
+            const int rows = (int)((T - k0) < KF ? (T - k0) : KF);
+            float *dst = s_in + s * IN_STAGE;
+            if (SHARED_U) {
+                const float *src = P.u + k0 * m;  // [T,1,m] is contiguous in k
+                for (int i = lane; i < rows * m; i += 32) dst[i] = __ldg(src + i);
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&full[s]);
+            } else if (P.bulk_in) {
+                if (lane == 0) {
+                    const uint32_t row_bytes = (uint32_t)valid * m * 4u;
+                    ptx::mbar_arrive_expect_tx(&full[s], row_bytes * (uint32_t)rows);
+                    for (int r = 0; r < rows; ++r)
+                        ptx::bulk_g2s(dst + r * IN_ROW, P.u + ((k0 + r) * N + n0) * m, row_bytes, &full[s], pol);
+                }
+            } else {
+                for (int r = 0; r < rows; ++r) {
+                    const float *src = P.u + ((k0 + r) * N + n0) * m;
+                    for (int i = lane; i < valid * m; i += 32) dst[r * IN_ROW + i] = __ldg(src + i);
+                }
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&full[s]);
+            }
+        };
+
+        auto store_chunk = [&](int64_t c) {
+            const int o = (int)(c & 1);
+            const int64_t k0 = c * KF;
+            const int rows = (int)((T - k0) < KF ? (T - k0) : KF);
+            const float *sx = s_xo + o * XO_STAGE;
+            const float *sy = s_yo + o * YO_STAGE;
+            if (P.bulk_out) {
+                if (lane == 0) {
+                    for (int r = 0; r < rows; ++r) {
+                        if (emit_x)
+                            ptx::bulk_s2g(P.xsol + ((k0 + r) * N + n0) * n, sx + r * TN * n, (uint32_t)valid * n * 4u);
+                        if (emit_y)
+                            ptx::bulk_s2g(P.ysol + ((k0 + r) * N + n0) * p, sy + r * TN * p, (uint32_t)valid * p * 4u);
+                    }
+                    ptx::bulk_commit();
+                    ptx::bulk_wait_read<0>();  // out-tile may be overwritten once TMA has read it
+                    ptx::mbar_arrive(&ofree[o]);
+                }
+            } else {
+                for (int r = 0; r < rows; ++r) {
+                    if (emit_x) {
+                        float *dst = P.xsol + ((k0 + r) * N + n0) * n;
+                        for (int i = lane; i < valid * n; i += 32) dst[i] = sx[r * TN * n + i];
+                    }
+                    if (emit_y) {
+                        float *dst = P.ysol + ((k0 + r) * N + n0) * p;
+                        for (int i = lane; i < valid * p; i += 32) dst[i] = sy[r * TN * p + i];
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&ofree[o]);
+            }
+        };
+
+        for (int64_t c = 0; c < C && c < S; ++c) load_chunk(c);
+        for (int64_t c = 0; c < C; ++c) {
+            const int s = (int)(c % S);
+            ptx::mbar_wait(&empty[s], (uint32_t)((c / S) & 1));  // consumers are done with chunk c
+            if (c + S < C) load_chunk(c + S);
+            if (emit) {
+                ptx::mbar_wait(&ofull[c & 1], (uint32_t)((c >> 1) & 1));
+                store_chunk(c);
+            }
+        }
+        if (lane == 0) ptx::bulk_wait<0>();
+        return;
+    }
+
+    // --------------------------------- consumers ---------------------------------
+    const int lane = tid & 31;
+    const bool active = tid < valid;
+    const int64_t i = active ? (n0 + tid) : (N - 1);  // idle lanes shadow the last system; never stored
+    Model M;
+    M.load(P.mp, i);
+    float x[n];
+#pragma unroll
+    for (int d = 0; d < n; ++d) x[d] = __ldg(P.x0 + i * n + d);
+    const float dt = P.dt;
+    const bool discrete = P.discrete != 0;
+
+    for (int64_t c = 0; c < C; ++c) {
+        const int s = (int)(c % S);
+        const int o = (int)(c & 1);
+        const int64_t k0 = c * KF;
+        const int rows = (int)((T - k0) < KF ? (T - k0) : KF);
+        ptx::mbar_wait(&full[s], (uint32_t)((c / S) & 1));
+        if (emit) ptx::mbar_wait(&ofree[o], (uint32_t)(((c >> 1) & 1) ^ 1));
+        const float *in = s_in + s * IN_STAGE + (SHARED_U ? 0 : tid * m);
+        float *xo = s_xo + o * XO_STAGE + tid * n;
+        float *yo = s_yo + o * YO_STAGE + tid * p;
+#pragma unroll
+        for (int j = 0; j < KF; ++j) {
+            if (j < rows) {
+                float u[m], r[n];
+#pragma unroll
+                for (int d = 0; d < m; ++d) u[d] = in[j * IN_ROW + d];
+                if (emit_y) {
+                    float y[p];
+                    M.out(x, u, y);  // y_k from the PRE-update state (simulator.py:38)
+#pragma unroll
+                    for (int d = 0; d < p; ++d) yo[j * TN * p + d] = y[d];
+                }
+                M.rhs(x, u, r);
+#pragma unroll
+                for (int d = 0; d < n; ++d) x[d] = discrete ? r[d] : fmaf(dt, r[d], x[d]);  // simulator.py:40
+                if (emit_x) {
+#pragma unroll
+                    for (int d = 0; d < n; ++d) xo[j * TN * n + d] = x[d];  // x_{k+1} (simulator.py:43)
+                }
+            }
+        }
+        if (emit) ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            ptx::mbar_arrive(&empty[s]);
+            if (emit) ptx::mbar_arrive(&ofull[o]);
+        }
+    }
+    if (P.x_final != nullptr && active) {
+#pragma unroll
+        for (int d = 0; d < n; ++d) P.x_final[i * n + d] = x[d];
+    }
+}
+
+}  // namespace dynax

@@ -1,0 +1,82 @@
+"""NumPy-buffer front end of the *_host C-ABI entry points (no torch involved).
+
+This is the call a reference user makes with host arrays (the reference's own arrays live on the
+host when it runs on XLA:CPU): the library tiles the system axis, overlaps H2D / kernel / D2H on two
+streams and returns NumPy results.  Pass pinned memory (e.g. ``torch.empty(..., pin_memory=True).numpy()``)
+for full PCIe rate; pageable memory works but copies are staged by the driver.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from ._lib import DISCRETE, SHARED_TARGET, SHARED_THETA, SHARED_U, check, lib
+
+__all__ = ["rc_forward", "rc_loss_grad", "release"]
+
+
+def _f32(a):
+    a = np.asarray(a)
+    if a.dtype != np.float32 or not a.flags["C_CONTIGUOUS"]:
+        a = np.ascontiguousarray(a, dtype=np.float32)
+    return a
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data
+
+
+def _canon(theta, x0, u):
+    theta, x0, u = _f32(theta), _f32(x0), _f32(u)
+    if x0.ndim != 2 or x0.shape[1] != 3:
+        raise ValueError(f"x0 must be [N,3], got {x0.shape}")
+    N = x0.shape[0]
+    if theta.ndim == 1:
+        theta = theta[None]
+    if theta.shape[1:] != (7,) or theta.shape[0] not in (1, N):
+        raise ValueError(f"theta must be [N,7] or [7], got {theta.shape}")
+    if u.ndim == 2:
+        u = u[:, None, :]
+    if u.ndim != 3 or u.shape[2] != 5 or u.shape[1] not in (1, N):
+        raise ValueError(f"u must be [T,N,5] or [T,5], got {u.shape}")
+    flags = (SHARED_THETA if (theta.shape[0] == 1 and N != 1) else 0) | (SHARED_U if (u.shape[1] == 1 and N != 1) else 0)
+    return theta, x0, u, N, u.shape[0], flags
+
+
+def rc_forward(theta, x0, u, dt, emit_x=True, emit_y=True, emit_final=False, discrete=False, tile_systems=0,
+               out=None):
+    """theta[N,7]|[7], x0[N,3], u[T,N,5]|[T,5] (host) -> xsol[T,N,3], ysol[T,N,1], x_final[N,3] (host)."""
+    theta, x0, u, N, T, flags = _canon(theta, x0, u)
+    out = out or {}
+    xs = out.get("xsol", np.empty((T, N, 3), np.float32)) if emit_x else None
+    ys = out.get("ysol", np.empty((T, N, 1), np.float32)) if emit_y else None
+    xf = out.get("x_final", np.empty((N, 3), np.float32)) if emit_final else None
+    check(lib().dynax_rc_forward_host_f32(_p(theta), _p(x0), _p(u), _p(xs), _p(ys), _p(xf), N, T, float(dt),
+                                          flags | (DISCRETE if discrete else 0), int(tile_systems)))
+    return xs, ys, xf
+
+
+def rc_loss_grad(theta, x0, u, target, dt, lb=None, ub=None, discrete=False, tile_systems=0):
+    """Fused loss + gradient of examples/3-inverse.py:96-112 on host buffers -> loss[N|1], grad[N,7]|[7]."""
+    theta, x0, u, N, T, flags = _canon(theta, x0, u)
+    target = _f32(target)
+    if target.shape == (T, N) and N != 1:
+        pass
+    elif target.size == T:
+        target = target.reshape(T)
+        flags |= SHARED_TARGET if N != 1 else 0
+    else:
+        raise ValueError(f"target must be [T,N] or [T], got {target.shape}")
+    if (lb is None) != (ub is None):
+        raise ValueError("lb and ub must be given together")
+    lb = None if lb is None else _f32(lb).reshape(7)
+    ub = None if ub is None else _f32(ub).reshape(7)
+    shared = bool(flags & SHARED_THETA)
+    loss = np.empty((1 if shared else N,), np.float32)
+    grad = np.empty((7,) if shared else (N, 7), np.float32)
+    check(lib().dynax_rc_loss_grad_host_f32(_p(theta), _p(x0), _p(u), _p(target), _p(lb), _p(ub), _p(loss), _p(grad),
+                                            N, T, float(dt), flags | (DISCRETE if discrete else 0), int(tile_systems)))
+    return loss, grad
+
+
+def release():
+    check(lib().dynax_host_release())

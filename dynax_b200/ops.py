@@ -1,0 +1,298 @@
+"""Torch-tensor glue over the C-ABI (device pointers + the current CUDA stream).
+
+PyTorch is plumbing here (device memory, streams, autograd bookkeeping); every number is
+produced by libdynax_b200.so.  All tensors must be CUDA float32; nothing falls back to torch ops.
+
+The autograd Functions are the ``custom_vjp`` analogue of the north-star's
+``jax.ffi`` + ``jax.custom_vjp`` binding (see INTEGRATION.md for that stub).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import DISCRETE, SHARED_TARGET, SHARED_THETA, SHARED_U, check, lib
+
+__all__ = ["rc_forward", "rc_loss_grad", "rc_vjp", "lti_forward", "lti_vjp", "rc_rollout", "lti_rollout",
+           "lti_supported"]
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32c(t, name):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name}: expected a torch.Tensor, got {type(t).__name__}")
+    if not t.is_cuda:
+        raise ValueError(f"{name}: must be a CUDA tensor (dynax_b200 has no CPU path); "
+                         "use the *_host functions for NumPy buffers")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name}: must be float32, got {t.dtype}")
+    return t.contiguous()
+
+
+def _canon_batch(theta_like_dims, x0, u, n, m):
+    """Normalise shapes.  Returns (x0[N,n], u[T,Nu,m], N, T, shared_u)."""
+    if x0.dim() != 2 or x0.shape[1] != n:
+        raise ValueError(f"x0 must be [N,{n}], got {tuple(x0.shape)}")
+    N = x0.shape[0]
+    if u.dim() == 2:
+        u = u[:, None, :]
+    if u.dim() != 3 or u.shape[2] != m:
+        raise ValueError(f"u must be [T,N,{m}] (or [T,1,{m}] / [T,{m}] shared), got {tuple(u.shape)}")
+    T = u.shape[0]
+    if u.shape[1] == N and N != 1:
+        shared_u = False
+    elif u.shape[1] == 1:
+        shared_u = N != 1
+    else:
+        raise ValueError(f"u has {u.shape[1]} systems but x0 has {N}")
+    return x0, u, N, T, shared_u
+
+
+def _ws(nbytes, device):
+    return torch.empty((max(int(nbytes), 16),), dtype=torch.uint8, device=device)
+
+
+# ----------------------------------------------------------------------------------------------
+# RC 4R3C
+# ----------------------------------------------------------------------------------------------
+def _rc_theta(theta, N):
+    theta = _f32c(theta, "theta")
+    if theta.dim() == 1:
+        theta = theta[None]
+    if theta.dim() != 2 or theta.shape[1] != 7:
+        raise ValueError(f"theta must be [N,7] or [7], got {tuple(theta.shape)}")
+    if theta.shape[0] == N and N != 1:
+        return theta, False
+    if theta.shape[0] == 1:
+        return theta, N != 1
+    raise ValueError(f"theta has {theta.shape[0]} systems but x0 has {N}")
+
+
+def rc_forward(theta, x0, u, dt, emit_x=True, emit_y=True, emit_final=False, discrete=False):
+    """Batched ``DifferentiableSimulator(Continuous4R3C, dt).apply`` (simulator.py:22-55, RC.py:137-249).
+
+    theta[N,7]|[7], x0[N,3], u[T,N,5]|[T,1,5]|[T,5]  ->  xsol[T,N,3], ysol[T,N,1], x_final[N,3]
+    (entries not requested are None).
+    """
+    x0, u = _f32c(x0, "x0"), _f32c(u, "u")
+    x0, u, N, T, shared_u = _canon_batch(None, x0, u, 3, 5)
+    theta, shared_th = _rc_theta(theta, N)
+    dev = x0.device
+    xsol = torch.empty((T, N, 3), dtype=torch.float32, device=dev) if emit_x else None
+    ysol = torch.empty((T, N, 1), dtype=torch.float32, device=dev) if emit_y else None
+    xfin = torch.empty((N, 3), dtype=torch.float32, device=dev) if emit_final else None
+    flags = (SHARED_THETA if shared_th else 0) | (SHARED_U if shared_u else 0) | (DISCRETE if discrete else 0)
+    with torch.cuda.device(dev):
+        check(lib().dynax_rc_forward_f32(_ptr(theta), _ptr(x0), _ptr(u), _ptr(xsol), _ptr(ysol), _ptr(xfin),
+                                         N, T, float(dt), flags, _stream()))
+    return xsol, ysol, xfin
+
+
+def rc_loss_grad(theta, x0, u, target, dt, lb=None, ub=None, want_gx0=False, discrete=False):
+    """Fused MSE(+box penalty) loss and its gradient (examples/3-inverse.py:96-112) for N candidates.
+
+    theta[N,7] -> loss[N], grad[N,7];  theta[7] (shared) -> loss[1] (sum over systems), grad[7].
+    target[T,N] or [T] (shared).  Returns (loss, grad, g_x0 or None).
+    """
+    x0, u, target = _f32c(x0, "x0"), _f32c(u, "u"), _f32c(target, "target")
+    x0, u, N, T, shared_u = _canon_batch(None, x0, u, 3, 5)
+    theta, shared_th = _rc_theta(theta, N)
+    if target.dim() == 2 and target.shape == (T, N) and N != 1:
+        shared_tg = False
+    elif target.numel() == T:
+        shared_tg = N != 1
+        target = target.reshape(T)
+    else:
+        raise ValueError(f"target must be [T,N] or [T], got {tuple(target.shape)}")
+    dev = x0.device
+    if (lb is None) != (ub is None):
+        raise ValueError("lb and ub must be given together")
+    if lb is not None:
+        lb = _f32c(torch.as_tensor(lb, dtype=torch.float32, device=dev), "lb").reshape(7)
+        ub = _f32c(torch.as_tensor(ub, dtype=torch.float32, device=dev), "ub").reshape(7)
+    nout = 1 if shared_th else N
+    loss = torch.empty((nout,), dtype=torch.float32, device=dev)
+    grad = torch.empty((nout, 7), dtype=torch.float32, device=dev)
+    gx0 = torch.empty((N, 3), dtype=torch.float32, device=dev) if want_gx0 else None
+    flags = ((SHARED_THETA if shared_th else 0) | (SHARED_U if shared_u else 0) |
+             (SHARED_TARGET if shared_tg else 0) | (DISCRETE if discrete else 0))
+    nbytes = lib().dynax_workspace_bytes(_lib.OP_RC_LOSS_GRAD, N, T, 3, 5, 1, flags)
+    ws = _ws(nbytes, dev)
+    with torch.cuda.device(dev):
+        check(lib().dynax_rc_loss_grad_f32(_ptr(theta), _ptr(x0), _ptr(u), _ptr(target), _ptr(lb), _ptr(ub),
+                                           _ptr(loss), _ptr(grad), _ptr(gx0), N, T, float(dt), flags,
+                                           _ptr(ws), ws.numel(), _stream()))
+    if shared_th:
+        grad = grad.reshape(7)
+    return loss, grad, gx0
+
+
+def rc_vjp(theta, x0, u, dt, g_xsol=None, g_ysol=None, need_theta=True, need_x0=True, need_u=True, discrete=False):
+    """VJP of rc_forward for arbitrary cotangents g_xsol[T,N,3], g_ysol[T,N,1] -> (g_theta, g_x0, g_u)."""
+    x0, u = _f32c(x0, "x0"), _f32c(u, "u")
+    x0, u, N, T, shared_u = _canon_batch(None, x0, u, 3, 5)
+    theta, shared_th = _rc_theta(theta, N)
+    dev = x0.device
+    if g_xsol is not None:
+        g_xsol = _f32c(g_xsol, "g_xsol").reshape(T, N, 3)
+    if g_ysol is not None:
+        g_ysol = _f32c(g_ysol, "g_ysol").reshape(T, N, 1)
+    gth = torch.empty((1 if shared_th else N, 7), dtype=torch.float32, device=dev) if need_theta else None
+    gx0 = torch.empty((N, 3), dtype=torch.float32, device=dev) if need_x0 else None
+    # with a shared input series the per-system g_u is produced against a broadcast view and summed here
+    u_k = u.expand(T, N, 5).contiguous() if (shared_u and need_u) else u
+    gu = torch.empty((T, N, 5), dtype=torch.float32, device=dev) if need_u else None
+    flags = ((SHARED_THETA if shared_th else 0) | (SHARED_U if (shared_u and not need_u) else 0) |
+             (DISCRETE if discrete else 0))
+    nbytes = lib().dynax_workspace_bytes(_lib.OP_RC_VJP, N, T, 3, 5, 1, flags)
+    ws = _ws(nbytes, dev)
+    with torch.cuda.device(dev):
+        check(lib().dynax_rc_vjp_f32(_ptr(theta), _ptr(x0), _ptr(u_k), _ptr(g_xsol), _ptr(g_ysol), _ptr(gth),
+                                     _ptr(gx0), _ptr(gu), N, T, float(dt), flags, _ptr(ws), ws.numel(), _stream()))
+    if gu is not None and shared_u:
+        gu = gu.sum(dim=1, keepdim=True)
+    return gth, gx0, gu
+
+
+class _RCRollout(torch.autograd.Function):
+    """xsol, ysol = rollout(theta, x0, u); backward = one dynax_rc_vjp_f32 launch."""
+
+    @staticmethod
+    def forward(ctx, theta, x0, u, dt, discrete):
+        xsol, ysol, _ = rc_forward(theta, x0, u, dt, discrete=discrete)
+        ctx.save_for_backward(theta, x0, u)
+        ctx.dt, ctx.discrete = dt, discrete
+        return xsol, ysol
+
+    @staticmethod
+    def backward(ctx, g_xsol, g_ysol):
+        theta, x0, u = ctx.saved_tensors
+        nt, nx, nu = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        if g_xsol is None and g_ysol is None:
+            return None, None, None, None, None
+        gth, gx0, gu = rc_vjp(theta, x0, u, ctx.dt, g_xsol, g_ysol, nt, nx, nu, ctx.discrete)
+        if gth is not None:
+            gth = gth.reshape(theta.shape)
+        if gu is not None:
+            gu = gu.reshape(u.shape)
+        return gth, gx0, gu, None, None
+
+
+def rc_rollout(theta, x0, u, dt, discrete=False):
+    """Differentiable (torch autograd) batched RC rollout: returns xsol[T,N,3], ysol[T,N,1]."""
+    return _RCRollout.apply(theta, x0, u, float(dt), bool(discrete))
+
+
+# ----------------------------------------------------------------------------------------------
+# dense LTI
+# ----------------------------------------------------------------------------------------------
+def lti_supported(n, m, p):
+    return bool(lib().dynax_lti_supported(int(n), int(m), int(p)))
+
+
+def _lti_mats(A, B, C, D, N):
+    A, B, C, D = (_f32c(M, nm) for M, nm in ((A, "A"), (B, "B"), (C, "C"), (D, "D")))
+    mats = [M[None] if M.dim() == 2 else M for M in (A, B, C, D)]
+    n, m, p = mats[0].shape[-1], mats[1].shape[-1], mats[2].shape[-2]
+    want = [(n, n), (n, m), (p, n), (p, m)]
+    lead = {M.shape[0] for M in mats}
+    for M, w, nm in zip(mats, want, "ABCD"):
+        if M.dim() != 3 or tuple(M.shape[1:]) != w:
+            raise ValueError(f"{nm} must be [N|1,{w[0]},{w[1]}], got {tuple(M.shape)}")
+    if len(lead) != 1:
+        raise ValueError("A,B,C,D must share their leading (system) dimension")
+    L = lead.pop()
+    if L == N and N != 1:
+        shared = False
+    elif L == 1:
+        shared = N != 1
+    else:
+        raise ValueError(f"matrices have {L} systems but x0 has {N}")
+    if not lti_supported(n, m, p):
+        raise _lib.DynaxError(-2, f"no dense-LTI kernel instantiated for (n,m,p)=({n},{m},{p})")
+    return [M.contiguous() for M in mats], n, m, p, shared
+
+
+def lti_forward(A, B, C, D, x0, u, dt, emit_x=True, emit_y=True, emit_final=False, discrete=False):
+    """Batched rollout of a dense linear block SSM (A,B,C,D are matrices = Flax kernels transposed)."""
+    x0, u = _f32c(x0, "x0"), _f32c(u, "u")
+    if x0.dim() != 2:
+        raise ValueError("x0 must be [N,n]")
+    N = x0.shape[0]
+    (A, B, C, D), n, m, p, shared_th = _lti_mats(A, B, C, D, N)
+    x0, u, N, T, shared_u = _canon_batch(None, x0, u, n, m)
+    dev = x0.device
+    xsol = torch.empty((T, N, n), dtype=torch.float32, device=dev) if emit_x else None
+    ysol = torch.empty((T, N, p), dtype=torch.float32, device=dev) if emit_y else None
+    xfin = torch.empty((N, n), dtype=torch.float32, device=dev) if emit_final else None
+    flags = (SHARED_THETA if shared_th else 0) | (SHARED_U if shared_u else 0) | (DISCRETE if discrete else 0)
+    with torch.cuda.device(dev):
+        check(lib().dynax_lti_forward_f32(_ptr(A), _ptr(B), _ptr(C), _ptr(D), _ptr(x0), _ptr(u), _ptr(xsol),
+                                          _ptr(ysol), _ptr(xfin), N, T, n, m, p, float(dt), flags, _stream()))
+    return xsol, ysol, xfin
+
+
+def lti_vjp(A, B, C, D, x0, u, dt, g_xsol=None, g_ysol=None, need_mats=True, need_x0=True, need_u=True,
+            discrete=False):
+    """VJP of lti_forward -> (gA, gB, gC, gD, g_x0, g_u); matrix grads are summed over systems if shared."""
+    x0, u = _f32c(x0, "x0"), _f32c(u, "u")
+    N = x0.shape[0]
+    (A, B, C, D), n, m, p, shared_th = _lti_mats(A, B, C, D, N)
+    x0, u, N, T, shared_u = _canon_batch(None, x0, u, n, m)
+    dev = x0.device
+    if g_xsol is not None:
+        g_xsol = _f32c(g_xsol, "g_xsol").reshape(T, N, n)
+    if g_ysol is not None:
+        g_ysol = _f32c(g_ysol, "g_ysol").reshape(T, N, p)
+    L = 1 if shared_th else N
+    gm = [torch.empty((L,) + s, dtype=torch.float32, device=dev) if need_mats else None
+          for s in ((n, n), (n, m), (p, n), (p, m))]
+    gx0 = torch.empty((N, n), dtype=torch.float32, device=dev) if need_x0 else None
+    u_k = u.expand(T, N, m).contiguous() if (shared_u and need_u) else u
+    gu = torch.empty((T, N, m), dtype=torch.float32, device=dev) if need_u else None
+    flags = ((SHARED_THETA if shared_th else 0) | (SHARED_U if (shared_u and not need_u) else 0) |
+             (DISCRETE if discrete else 0))
+    nbytes = lib().dynax_workspace_bytes(_lib.OP_LTI_VJP, N, T, n, m, p, flags)
+    ws = _ws(nbytes, dev)
+    with torch.cuda.device(dev):
+        check(lib().dynax_lti_vjp_f32(_ptr(A), _ptr(B), _ptr(C), _ptr(D), _ptr(x0), _ptr(u_k), _ptr(g_xsol),
+                                      _ptr(g_ysol), _ptr(gm[0]), _ptr(gm[1]), _ptr(gm[2]), _ptr(gm[3]), _ptr(gx0),
+                                      _ptr(gu), N, T, n, m, p, float(dt), flags, _ptr(ws), ws.numel(), _stream()))
+    if gu is not None and shared_u:
+        gu = gu.sum(dim=1, keepdim=True)
+    return gm[0], gm[1], gm[2], gm[3], gx0, gu
+
+
+class _LTIRollout(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, A, B, C, D, x0, u, dt, discrete):
+        xsol, ysol, _ = lti_forward(A, B, C, D, x0, u, dt, discrete=discrete)
+        ctx.save_for_backward(A, B, C, D, x0, u)
+        ctx.dt, ctx.discrete = dt, discrete
+        return xsol, ysol
+
+    @staticmethod
+    def backward(ctx, g_xsol, g_ysol):
+        A, B, C, D, x0, u = ctx.saved_tensors
+        need = ctx.needs_input_grad
+        if g_xsol is None and g_ysol is None:
+            return (None,) * 8
+        gA, gB, gC, gD, gx0, gu = lti_vjp(A, B, C, D, x0, u, ctx.dt, g_xsol, g_ysol, any(need[:4]), need[4],
+                                          need[5], ctx.discrete)
+        outs = [g.reshape(M.shape) if (g is not None and nd) else None
+                for g, M, nd in zip((gA, gB, gC, gD), (A, B, C, D), need[:4])]
+        if gu is not None:
+            gu = gu.reshape(u.shape)
+        return outs[0], outs[1], outs[2], outs[3], gx0, gu, None, None
+
+
+def lti_rollout(A, B, C, D, x0, u, dt, discrete=False):
+    """Differentiable batched dense-LTI rollout: returns xsol[T,N,n], ysol[T,N,p]."""
+    return _LTIRollout.apply(A, B, C, D, x0, u, float(dt), bool(discrete))

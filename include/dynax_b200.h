@@ -1,0 +1,135 @@
+/* dynax_b200 -- C ABI of the B200-native batched rollout engine (libdynax_b200.so).
+ *
+ * This is the drop-in boundary for dynax's hot path.  The reference has no FFI of its own;
+ * the boundary it exposes is the Flax call convention
+ *     xsol, ysol = DifferentiableSimulator(model, dt).apply(params, x0, inputs)
+ *         (/root/reference/dynax/simulators/simulator.py:12-55)
+ * over a BaseBlockSSM model (dynax/core/base_block_state_space.py:51-76), differentiated by
+ * jax.value_and_grad (examples/3-inverse.py:96-112).  Each entry point below names the
+ * reference code it replaces; INTEGRATION.md shows the jax.ffi / ctypes stubs that bind it.
+ *
+ * Conventions
+ *  - All arithmetic is fp32 (JAX default dtype); gradient sums are folded in fp64 internally.
+ *  - Unless a name ends in _host, every pointer is a DEVICE pointer owned by the caller, every
+ *    call only enqueues work on `stream` (a cudaStream_t passed as void*) and returns at once.
+ *    No hidden allocation: scratch comes from the caller (`ws`, size from dynax_workspace_bytes).
+ *  - *_host entry points take HOST pointers, allocate device scratch themselves, tile the
+ *    system axis, overlap the H2D/D2H copies with the kernels, and return when results are in
+ *    the host buffers.
+ *  - Layouts are row-major with the system axis in the middle, as north_star prescribes:
+ *      theta[N,7]  x0[N,n]  u[T,N,m]  xsol[T,N,n]  ysol[T,N,p]  target[T,N]
+ *    xsol[k] = x_{k+1} (post-update), ysol[k] = y(x_k,u_k) (pre-update): simulator.py:38-43.
+ *  - Return value: DYNAX_OK or a negative DYNAX_ERR_*; dynax_last_error() gives a thread-local
+ *    message.  Nothing throws.  There is no CPU fallback: without an sm_100 device every compute
+ *    entry point fails with DYNAX_ERR_NO_DEVICE.
+ */
+#ifndef DYNAX_B200_H_
+#define DYNAX_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DYNAX_ABI_VERSION 1
+
+#define DYNAX_OK 0
+#define DYNAX_ERR_INVALID_ARGUMENT (-1)
+#define DYNAX_ERR_UNSUPPORTED_DIMS (-2)
+#define DYNAX_ERR_WORKSPACE (-3)
+#define DYNAX_ERR_CUDA (-4)
+#define DYNAX_ERR_NO_DEVICE (-5)
+
+/* flags (bit-or) */
+#define DYNAX_SHARED_THETA 1u   /* model parameters are one set [1,...] broadcast to all N systems;
+                                   parameter gradients come back SUMMED over the N systems          */
+#define DYNAX_SHARED_U 2u       /* u is [T,1,m]: one input series for all systems                  */
+#define DYNAX_SHARED_TARGET 4u  /* target is [T]: one measured series for all systems              */
+#define DYNAX_DISCRETE 8u       /* x_{k+1} = rhs (stepping a Discrete* model directly,
+                                   tests/test_forward_simulation.py:9-12,33-36) instead of the
+                                   simulator's x += dt*rhs (simulator.py:40)                        */
+
+/* ops for dynax_workspace_bytes */
+#define DYNAX_OP_RC_FORWARD 0
+#define DYNAX_OP_RC_LOSS_GRAD 1
+#define DYNAX_OP_RC_VJP 2
+#define DYNAX_OP_LTI_FORWARD 3
+#define DYNAX_OP_LTI_VJP 4
+
+int dynax_version(void);
+const char *dynax_last_error(void);
+/* 0 if the current CUDA device is compute capability 10.x, else DYNAX_ERR_NO_DEVICE. */
+int dynax_device_check(void);
+/* Bytes of device scratch `ws` the op needs (0 for forward ops). */
+size_t dynax_workspace_bytes(int op, int64_t N, int64_t T, int n, int m, int p, uint32_t flags);
+/* 1 if dense-LTI kernels are instantiated for (n,m,p), else 0. */
+int dynax_lti_supported(int n, int m, int p);
+
+/* ---- 4R3C RC zone model: Continuous4R3C / Discrete4R3C (dynax/models/RC.py:21-249) rolled out
+ *      by DifferentiableSimulator.__call__ (simulators/simulator.py:22-55).  n=3, m=5, p=1.
+ *      theta = [Cai,Cwe,Cwi,Re,Ri,Rw,Rg] (RC.py:176-182); A(theta),B(theta) are built in-kernel
+ *      (RC.py:201-210,222-230), C=[1,0,0], D=0 (RC.py:236-246).
+ *      xsol, ysol, x_final may each be NULL (not emitted). ---------------------------------- */
+int dynax_rc_forward_f32(const float *theta, const float *x0, const float *u,
+                         float *xsol, float *ysol, float *x_final,
+                         int64_t N, int64_t T, float dt, uint32_t flags, void *stream);
+
+/* Fused loss + reverse-mode gradient of examples/3-inverse.py:96-112 for N candidates:
+ *   loss_i = mean_k (ysol_i[k]-target_i[k])^2 + sum_j relu(theta_ij-ub_j)/ub_j + relu(lb_j-theta_ij)/ub_j
+ *   g_theta = d loss / d theta   (checkpointed discrete adjoint; == jax.value_and_grad through the scan)
+ * lb/ub: [7] device arrays or NULL (no penalty).  loss:[N], g_theta:[N,7]; with DYNAX_SHARED_THETA
+ * loss:[1] (mean over systems is NOT taken: it is the SUM over systems of the MSE terms plus one
+ * penalty) and g_theta:[7].  g_x0:[N,3] or NULL. */
+int dynax_rc_loss_grad_f32(const float *theta, const float *x0, const float *u, const float *target,
+                           const float *lb, const float *ub,
+                           float *loss, float *g_theta, float *g_x0,
+                           int64_t N, int64_t T, float dt, uint32_t flags,
+                           void *ws, size_t ws_bytes, void *stream);
+
+/* General-cotangent VJP of dynax_rc_forward_f32 (what jax.vjp/jax.grad of simulator.apply needs
+ * for an arbitrary downstream loss).  g_xsol:[T,N,3] or NULL, g_ysol:[T,N,1] or NULL (at least
+ * one non-NULL).  Outputs (each may be NULL): g_theta:[N,7] ([7] if SHARED_THETA), g_x0:[N,3],
+ * g_u:[T,N,5] (not available with DYNAX_SHARED_U). */
+int dynax_rc_vjp_f32(const float *theta, const float *x0, const float *u,
+                     const float *g_xsol, const float *g_ysol,
+                     float *g_theta, float *g_x0, float *g_u,
+                     int64_t N, int64_t T, float dt, uint32_t flags,
+                     void *ws, size_t ws_bytes, void *stream);
+
+/* ---- Dense linear block SSM: DiscreteLinearSSM / ContinuousLinearSSM
+ *      (dynax/core/discrete_block_state_space.py:5-54, continuous_block_state_space.py:5-54).
+ *      A:[N|1,n,n] B:[N|1,n,m] C:[N|1,p,n] D:[N|1,p,m] are the MATRICES (row-major), i.e. the
+ *      transposes of the Flax nn.Dense kernels.  (n,m,p) must satisfy dynax_lti_supported. ---- */
+int dynax_lti_forward_f32(const float *A, const float *B, const float *C, const float *D,
+                          const float *x0, const float *u,
+                          float *xsol, float *ysol, float *x_final,
+                          int64_t N, int64_t T, int n, int m, int p, float dt, uint32_t flags, void *stream);
+
+int dynax_lti_vjp_f32(const float *A, const float *B, const float *C, const float *D,
+                      const float *x0, const float *u,
+                      const float *g_xsol, const float *g_ysol,
+                      float *g_A, float *g_B, float *g_C, float *g_D, float *g_x0, float *g_u,
+                      int64_t N, int64_t T, int n, int m, int p, float dt, uint32_t flags,
+                      void *ws, size_t ws_bytes, void *stream);
+
+/* ---- Host-buffer entry points (the call a reference user makes with NumPy/JAX-CPU arrays):
+ *      pageable or pinned HOST pointers in, results in HOST buffers on return.  The system axis is
+ *      processed in tiles of `tile_systems` (0 = library default) with copies overlapped. ------ */
+int dynax_rc_forward_host_f32(const float *theta, const float *x0, const float *u,
+                              float *xsol, float *ysol, float *x_final,
+                              int64_t N, int64_t T, float dt, uint32_t flags, int64_t tile_systems);
+
+int dynax_rc_loss_grad_host_f32(const float *theta, const float *x0, const float *u, const float *target,
+                                const float *lb, const float *ub,
+                                float *loss, float *g_theta,
+                                int64_t N, int64_t T, float dt, uint32_t flags, int64_t tile_systems);
+
+/* Frees the device scratch the *_host entry points cache between calls. */
+int dynax_host_release(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DYNAX_B200_H_ */

@@ -1,0 +1,51 @@
+"""GPU: the *_host C-ABI entry points (NumPy buffers in, NumPy buffers out, tiled + overlapped)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle, dynax_oracle as orc
+from tests.util import grad_ok, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def p(a):
+    return None if a is None else a.ctypes.data
+
+
+def test_forward_host_tiled_matches_oracle():
+    from dynax_b200 import host
+    N, Tn = 1000, 300
+    th, x0, u = orc.synth_theta(N, 61), orc.synth_x0(N, 61), orc.synth_u(Tn, N, 61)
+    xr, yr, xfr = c_oracle.rc_forward(th, x0, u, 3600.0)
+    for tile in (0, 256, 384, 1000):
+        xs, ys, xf = host.rc_forward(th, x0, u, 3600.0, tile_systems=tile, emit_final=True)
+        assert rel_err(xs, xr) < 1e-5 and rel_err(ys, yr) < 1e-5 and np.array_equal(xf, xs[-1])
+    xs1, _, _ = host.rc_forward(th[0], x0, u[:, 0], 3600.0, tile_systems=256)     # shared theta + u
+    xr1, _, _ = c_oracle.rc_forward(th[:1], x0, u[:, :1], 3600.0)
+    assert rel_err(xs1, xr1) < 1e-5
+
+
+def test_loss_grad_host_tiled_matches_device_api():
+    import torch
+    from dynax_b200 import host, ops
+    N, Tn = 900, 250
+    th, x0, u = orc.synth_theta(N, 62), orc.synth_x0(N, 62), orc.synth_u(Tn, N, 62)
+    target = (22 + np.random.default_rng(4).normal(size=(Tn, N))).astype(np.float32)
+    th[3, 0] = 5e4
+    l64, g64 = orc.rc_loss_grad(th, x0, u, target, 3600.0, orc.RC_LB, orc.RC_UB)
+    for tile in (0, 256):
+        loss, grad = host.rc_loss_grad(th, x0, u, target, 3600.0, orc.RC_LB, orc.RC_UB, tile_systems=tile)
+        assert np.allclose(loss, l64, rtol=1e-5)
+        assert grad_ok(grad, g64, None, 1e-4)[0] < 1e-4
+    ld, gd, _ = ops.rc_loss_grad(*(torch.tensor(v).cuda() for v in (th, x0, u, target)), 3600.0, orc.RC_LB, orc.RC_UB)
+    assert np.array_equal(ld.cpu().numpy(), loss) and np.array_equal(gd.cpu().numpy(), grad)
+    # shared theta across tiles: sums reduced on the host, penalty once
+    th1 = th[3].copy()
+    loss1, grad1 = host.rc_loss_grad(th1, x0, u, target, 3600.0, orc.RC_LB, orc.RC_UB, tile_systems=256)
+    lr, gr = orc.rc_loss_grad(np.repeat(th1[None], N, 0), x0, u, target, 3600.0)
+    pen = orc.bound_penalty(th1[None], orc.RC_LB, orc.RC_UB)[0]
+    gs = gr.sum(0) + orc.bound_penalty_grad(th1[None], orc.RC_LB, orc.RC_UB)[0]
+    assert np.allclose(loss1[0], lr.sum() + pen, rtol=1e-5)
+    assert np.linalg.norm(grad1 - gs) / np.linalg.norm(gs) < 1e-4

@@ -1,0 +1,95 @@
+"""GPU parity: dense linear block SSMs (Discrete/ContinuousLinearSSM) forward + VJP vs the oracle."""
+import numpy as np
+import pytest
+
+from oracle import dynax_oracle as orc
+from tests.util import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def T():
+    import torch
+    return torch
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from dynax_b200 import ops
+    return ops
+
+
+def cu(T, a):
+    return T.as_tensor(np.ascontiguousarray(a, dtype=np.float32)).cuda()
+
+
+def make(N, Tn, n, m, p, seed, L=None):
+    rng = np.random.default_rng(seed)
+    L = N if L is None else L
+    A = (-np.eye(n)[None] + 0.3 * rng.normal(size=(L, n, n))).astype(np.float32)
+    B = rng.normal(size=(L, n, m)).astype(np.float32)
+    C = rng.normal(size=(L, p, n)).astype(np.float32)
+    D = rng.normal(size=(L, p, m)).astype(np.float32)
+    x0 = rng.normal(size=(N, n)).astype(np.float32)
+    u = rng.normal(size=(Tn, N, m)).astype(np.float32)
+    return A, B, C, D, x0, u
+
+
+DIMS = [(1, 1, 1), (2, 1, 1), (2, 2, 1), (2, 2, 2), (3, 1, 1), (3, 3, 1), (3, 3, 3), (3, 5, 1), (4, 1, 1), (4, 2, 2),
+        (4, 3, 4), (4, 4, 4)]
+
+
+@pytest.mark.parametrize("n,m,p", DIMS)
+def test_forward_all_dims(T, ops, n, m, p):
+    N, Tn, dt = 260, 150, 0.05
+    A, B, C, D, x0, u = make(N, Tn, n, m, p, 41)
+    xs, ys, xf = ops.lti_forward(*(cu(T, v) for v in (A, B, C, D, x0, u)), dt, emit_final=True)
+    xr, yr = orc.lti_rollout(A, B, C, D, x0, u, dt, np.float64)
+    assert rel_err(xs.cpu().numpy(), xr) < 1e-5 and rel_err(ys.cpu().numpy(), yr) < 1e-5
+    assert np.array_equal(xf.cpu().numpy(), xs[-1].cpu().numpy())
+
+
+@pytest.mark.parametrize("discrete", [False, True])
+def test_forward_ragged_shared_discrete(T, ops, discrete):
+    N, Tn, dt = 131, 90, 0.05
+    n, m, p = 4, 3, 4                       # tests/test_forward_simulation.py:17-20
+    A, B, C, D, x0, u = make(N, Tn, n, m, p, 42, L=1)
+    A *= 0.5
+    xs, ys, _ = ops.lti_forward(*(cu(T, v) for v in (A, B, C, D, x0, u[:, :1])), dt, discrete=discrete)
+    xr, yr = orc.lti_rollout(A, B, C, D, x0, u[:, :1], dt, np.float64, discrete=discrete)
+    assert rel_err(xs.cpu().numpy(), xr) < 1e-5 and rel_err(ys.cpu().numpy(), yr) < 1e-5
+
+
+@pytest.mark.parametrize("n,m,p", [(4, 3, 4), (3, 5, 1), (2, 2, 2), (1, 1, 1), (4, 4, 4)])
+@pytest.mark.parametrize("discrete", [False, True])
+def test_vjp(T, ops, n, m, p, discrete):
+    N, Tn, dt = 140, 120, 0.05
+    A, B, C, D, x0, u = make(N, Tn, n, m, p, 43)
+    if discrete:
+        A *= 0.5
+    rng = np.random.default_rng(44)
+    gx = rng.normal(size=(Tn, N, n)).astype(np.float32)
+    gy = rng.normal(size=(Tn, N, p)).astype(np.float32)
+    out = ops.lti_vjp(*(cu(T, v) for v in (A, B, C, D, x0, u)), dt, cu(T, gx), cu(T, gy), discrete=discrete)
+    r = orc.lti_vjp(A, B, C, D, x0, u, dt, gx, gy, np.float64, discrete=discrete)
+    for got, key in zip(out, ("gA", "gB", "gC", "gD", "gx0", "gu")):
+        assert rel_err(got.cpu().numpy(), r[key]) < 1e-4, key
+
+
+def test_vjp_shared_matrices_sums_over_systems(T, ops):
+    N, Tn, dt = 256, 64, 0.05
+    A, B, C, D, x0, u = make(N, Tn, 3, 3, 1, 45, L=1)
+    gy = np.random.default_rng(46).normal(size=(Tn, N, 1)).astype(np.float32)
+    out = ops.lti_vjp(*(cu(T, v) for v in (A, B, C, D, x0, u)), dt, None, cu(T, gy))
+    r = orc.lti_vjp(A, B, C, D, x0, u, dt, None, gy, np.float64)
+    for got, key in zip(out[:4], ("gA", "gB", "gC", "gD")):
+        assert rel_err(got.cpu().numpy()[0], r[key].sum(0)) < 1e-4, key
+
+
+def test_unsupported_dims(T, ops):
+    from dynax_b200._lib import DynaxError
+    A, B, C, D, x0, u = make(4, 5, 5, 2, 1, 47)
+    with pytest.raises(DynaxError) as e:
+        ops.lti_forward(*(cu(T, v) for v in (A, B, C, D, x0, u)), 0.1)
+    assert e.value.code == -2

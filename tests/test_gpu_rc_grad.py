@@ -1,0 +1,180 @@
+"""GPU parity: fused loss+gradient and general VJP of the RC rollout vs the fp64 oracle.
+
+Tolerance (north_star): gradients rel 1e-4 -- applied as SURVEY.md section 7 H2 makes it
+meaningful: norm-wise <= 1e-4 per system, and per element no further from fp64 truth than
+max(1e-4*|g|, error of the all-fp32 reference-order BPTT).  Loss rel 1e-5.
+"""
+import numpy as np
+import pytest
+
+from oracle import c_oracle, dynax_oracle as orc
+from tests.util import grad_ok, rel_err
+
+pytestmark = pytest.mark.gpu
+
+GRAD_RTOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def T():
+    import torch
+    return torch
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from dynax_b200 import ops
+    return ops
+
+
+def cu(T, a):
+    return T.as_tensor(np.ascontiguousarray(a, dtype=np.float32)).cuda()
+
+
+def make_case(N, Tn, seed, noise=0.1):
+    th, x0, u = orc.synth_theta(N, seed), orc.synth_x0(N, seed), orc.synth_u(Tn, N, seed)
+    hidden = orc.synth_theta(N, seed + 100)
+    _, y = orc.rc_rollout(hidden, x0, u, 3600.0, np.float64)
+    target = (y[..., 0] + noise * np.random.default_rng(seed).normal(size=(Tn, N))).astype(np.float32)
+    return th, x0, u, target
+
+
+@pytest.mark.parametrize("N,Tn", [(256, 8760), (130, 1000), (7, 100), (1, 17), (5, 16), (3, 1)])
+def test_loss_grad_vs_fp64(T, ops, N, Tn):
+    th, x0, u, target = make_case(N, Tn, 31)
+    th[0, 0] = 4.0e4            # above ub
+    if N > 1:
+        th[1, 4] = 0.45         # below lb
+    loss, grad, gx0 = ops.rc_loss_grad(cu(T, th), cu(T, x0), cu(T, u), cu(T, target), 3600.0,
+                                       orc.RC_LB, orc.RC_UB, want_gx0=True)
+    l64, g64 = orc.rc_loss_grad(th, x0, u, target, 3600.0, orc.RC_LB, orc.RC_UB, np.float64)
+    l32, g32 = c_oracle.rc_loss_grad(th, x0, u, target, 3600.0, orc.RC_LB, orc.RC_UB)
+    assert np.allclose(loss.cpu().numpy(), l64, rtol=1e-5), np.abs(loss.cpu().numpy() / l64 - 1).max()
+    nrm, elem_ok, worst = grad_ok(grad.cpu().numpy(), g64, g32, GRAD_RTOL)
+    assert nrm < GRAD_RTOL, (nrm, worst)
+    assert elem_ok, worst
+    # d loss / d x0 against the oracle's general VJP
+    gy = (2.0 / Tn) * (orc.rc_rollout(th, x0, u, 3600.0, np.float64)[1][..., 0] - target)
+    _, gx0_64, _ = orc.rc_vjp(th, x0, u, 3600.0, None, gy[..., None])
+    assert rel_err(gx0.cpu().numpy(), gx0_64) < GRAD_RTOL
+
+
+@pytest.mark.parametrize("cfg", ["0", "1", "2", "3", "4"])
+def test_adj_tile_configs(T, ops, monkeypatch, cfg):
+    th, x0, u, target = make_case(300, 777, 32)
+    monkeypatch.setenv("DYNAX_ADJ_CFG", cfg)
+    loss, grad, _ = ops.rc_loss_grad(cu(T, th), cu(T, x0), cu(T, u), cu(T, target), 3600.0)
+    l64, g64 = orc.rc_loss_grad(th, x0, u, target, 3600.0, None, None, np.float64)
+    assert np.allclose(loss.cpu().numpy(), l64, rtol=1e-5)
+    nrm, _, worst = grad_ok(grad.cpu().numpy(), g64, None, GRAD_RTOL)
+    assert nrm < GRAD_RTOL, (nrm, worst)
+
+
+def test_no_tma_path_and_ragged(T, ops, monkeypatch):
+    th, x0, u, target = make_case(261, 300, 33)          # N % 4 != 0 -> plain ld path
+    a = [cu(T, v) for v in (th, x0, u, target)]
+    loss, grad, _ = ops.rc_loss_grad(*a, 3600.0)
+    l64, g64 = orc.rc_loss_grad(th, x0, u, target, 3600.0, None, None, np.float64)
+    assert np.allclose(loss.cpu().numpy(), l64, rtol=1e-5)
+    assert grad_ok(grad.cpu().numpy(), g64, None, GRAD_RTOL)[0] < GRAD_RTOL
+    th, x0, u, target = make_case(256, 300, 34)
+    a = [cu(T, v) for v in (th, x0, u, target)]
+    l1, g1, _ = ops.rc_loss_grad(*a, 3600.0)
+    monkeypatch.setenv("DYNAX_NO_BULK", "1")
+    l2, g2, _ = ops.rc_loss_grad(*a, 3600.0)
+    assert T.equal(l1, l2) and T.equal(g1, g2)
+
+
+def test_shared_modes(T, ops):
+    N, Tn = 384, 500
+    th, x0, u, target = make_case(N, Tn, 35)
+    # shared u + shared target, per-system theta  (config 3 variant ii)
+    loss, grad, _ = ops.rc_loss_grad(cu(T, th), cu(T, x0), cu(T, u[:, :1]), cu(T, target[:, 0]), 3600.0)
+    l64, g64 = orc.rc_loss_grad(th, x0, u[:, :1], target[:, :1], 3600.0, None, None, np.float64)
+    assert np.allclose(loss.cpu().numpy(), l64, rtol=1e-5)
+    assert grad_ok(grad.cpu().numpy(), g64, None, GRAD_RTOL)[0] < GRAD_RTOL
+    # shared theta: gradient summed over systems, penalty counted once
+    th1 = th[:1].copy(); th1[0, 6] = 60.0
+    loss, grad, _ = ops.rc_loss_grad(cu(T, th1[0]), cu(T, x0), cu(T, u), cu(T, target), 3600.0, orc.RC_LB, orc.RC_UB)
+    l64, g64 = orc.rc_loss_grad(np.repeat(th1, N, 0), x0, u, target, 3600.0, None, None, np.float64)
+    pen = orc.bound_penalty(th1, orc.RC_LB, orc.RC_UB)[0]
+    peng = orc.bound_penalty_grad(th1, orc.RC_LB, orc.RC_UB)[0]
+    assert np.allclose(loss.cpu().numpy()[0], l64.sum() + pen, rtol=1e-5)
+    gs = g64.sum(0) + peng
+    assert np.linalg.norm(grad.cpu().numpy() - gs) / np.linalg.norm(gs) < GRAD_RTOL
+    # per-system u, shared target
+    loss, grad, _ = ops.rc_loss_grad(cu(T, th), cu(T, x0), cu(T, u), cu(T, target[:, 0]), 3600.0)
+    l64, g64 = orc.rc_loss_grad(th, x0, u, target[:, :1], 3600.0, None, None, np.float64)
+    assert np.allclose(loss.cpu().numpy(), l64, rtol=1e-5)
+    assert grad_ok(grad.cpu().numpy(), g64, None, GRAD_RTOL)[0] < GRAD_RTOL
+
+
+@pytest.mark.parametrize("N,Tn,use_gx,use_gy", [(200, 400, True, True), (33, 129, True, False), (64, 50, False, True)])
+def test_general_vjp(T, ops, N, Tn, use_gx, use_gy):
+    rng = np.random.default_rng(36)
+    th, x0, u = orc.synth_theta(N, 36), orc.synth_x0(N, 36), orc.synth_u(Tn, N, 36)
+    gx = rng.normal(size=(Tn, N, 3)).astype(np.float32) if use_gx else None
+    gy = rng.normal(size=(Tn, N, 1)).astype(np.float32) if use_gy else None
+    gth, gx0, gu = ops.rc_vjp(cu(T, th), cu(T, x0), cu(T, u), 3600.0,
+                              None if gx is None else cu(T, gx), None if gy is None else cu(T, gy))
+    rth, rx0, ru = orc.rc_vjp(th, x0, u, 3600.0, gx, gy, np.float64)
+    assert grad_ok(gth.cpu().numpy(), rth, None, GRAD_RTOL)[0] < GRAD_RTOL
+    assert rel_err(gx0.cpu().numpy(), rx0) < GRAD_RTOL
+    assert rel_err(gu.cpu().numpy(), ru) < GRAD_RTOL
+
+
+def test_autograd_function_matches_fused(T, ops):
+    """jax.grad-style use: loss built by the caller on top of simulator outputs."""
+    N, Tn = 128, 300
+    th, x0, u, target = make_case(N, Tn, 37)
+    tth = cu(T, th).requires_grad_(True)
+    tx0 = cu(T, x0).requires_grad_(True)
+    tu = cu(T, u).requires_grad_(True)
+    xs, ys = ops.rc_rollout(tth, tx0, tu, 3600.0)
+    loss = ((ys[..., 0] - cu(T, target)) ** 2).mean(0)
+    loss.sum().backward()
+    l64, g64 = orc.rc_loss_grad(th, x0, u, target, 3600.0, None, None, np.float64)
+    assert grad_ok(tth.grad.cpu().numpy(), g64, None, GRAD_RTOL)[0] < GRAD_RTOL
+    lf, gf, gx0f = ops.rc_loss_grad(cu(T, th), cu(T, x0), cu(T, u), cu(T, target), 3600.0, want_gx0=True)
+    assert np.allclose(gf.cpu().numpy(), tth.grad.cpu().numpy(), rtol=2e-4, atol=1e-12)
+    assert np.allclose(gx0f.cpu().numpy(), tx0.grad.cpu().numpy(), rtol=2e-4, atol=1e-12)
+    assert tu.grad is not None and tu.grad.shape == tu.shape
+
+
+def test_grad_property_large(T, ops):
+    """Full-machine tile: shared-theta gradient == sum of per-system gradients (fp64-folded), and
+    64 random systems vs the fp64 oracle."""
+    N, Tn = 148 * 2 * 128, 200
+    g = T.Generator(device="cuda").manual_seed(6)
+    th1 = cu(T, orc.RC_NOMINAL[None])
+    th = th1.expand(N, 7).contiguous()
+    x0 = cu(T, [[20.0, 30.0, 26.0]]) + T.empty((N, 3), device="cuda").uniform_(-1, 1, generator=g)
+    u = T.empty((Tn, N, 5), device="cuda").uniform_(0, 1, generator=g)
+    u[..., 0] = 15 + 10 * u[..., 0]
+    target = 20 + 2 * T.empty((Tn, N), device="cuda").uniform_(-1, 1, generator=g)
+    l_i, g_i, _ = ops.rc_loss_grad(th, x0, u, target, 3600.0)
+    l_s, g_s, _ = ops.rc_loss_grad(th1[0], x0, u, target, 3600.0)
+    assert np.allclose(l_s.item(), l_i.double().sum().item(), rtol=1e-5)
+    gs = g_i.double().sum(0).cpu().numpy()
+    assert np.linalg.norm(g_s.cpu().numpy() - gs) / np.linalg.norm(gs) < 1e-5
+    idx = np.random.default_rng(1).choice(N, 64, replace=False)
+    l64, g64 = orc.rc_loss_grad(th[idx].cpu().numpy(), x0[idx].cpu().numpy(), u[:, idx].cpu().numpy(),
+                                target[:, idx].cpu().numpy(), 3600.0, None, None, np.float64)
+    assert np.allclose(l_i[idx].cpu().numpy(), l64, rtol=1e-5)
+    assert grad_ok(g_i[idx].cpu().numpy(), g64, None, GRAD_RTOL)[0] < GRAD_RTOL
+
+
+def test_workspace_and_errors(T, ops):
+    from dynax_b200 import _lib
+    L = _lib.lib()
+    th, x0, u, target = (cu(T, v) for v in make_case(8, 20, 38))
+    loss = T.empty(8, device="cuda"); grad = T.empty(8, 7, device="cuda")
+    rc = L.dynax_rc_loss_grad_f32(th.data_ptr(), x0.data_ptr(), u.data_ptr(), target.data_ptr(), None, None,
+                                  loss.data_ptr(), grad.data_ptr(), None, 8, 20, 3600.0, 0, None, 0, None)
+    assert rc == -3 and b"workspace" in L.dynax_last_error()
+    rc = L.dynax_rc_loss_grad_f32(th.data_ptr(), x0.data_ptr(), u.data_ptr(), None, None, None,
+                                  loss.data_ptr(), grad.data_ptr(), None, 8, 20, 3600.0, 0, None, 0, None)
+    assert rc == -1
+    rc = L.dynax_rc_loss_grad_f32(th.data_ptr(), x0.data_ptr(), u.data_ptr(), target.data_ptr(), None, None,
+                                  loss.data_ptr(), grad.data_ptr(), None, 8, 0, 3600.0, 0, None, 0, None)
+    assert rc == -1      # T must be >= 1 for a mean over time
