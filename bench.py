@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""Headline benchmark: system-steps/s of the fused forward+gradient RC rollout (BASELINE.json).
+
+    python bench.py [--gpus N --steps K --warmup W]            # our arm (CUDA library)
+    python bench.py --impl reference [--steps K --warmup W]    # reference arm: CPU port of the reference path
+
+A "step" = one loss+gradient evaluation (examples/3-inverse.py:96-112) of `--systems` RC zone models
+over T=8760 hourly steps on EACH rank (weak scaling: the system batch is sharded, no collective on the
+data path).  The full input array of the headline config (2^20 x 8760 x 5 fp32 = 184 GB) does not fit
+one GPU, so a step runs as tiles over the system axis: one u/target tile stays resident and is
+re-read by every tile launch (24 GB >> 126 MB L2, so nothing is served from cache) while theta/x0
+are distinct per tile.  See DESIGN.md "Measurement".
+
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+T_YEAR = 8760
+DT = 3600.0
+B_ALG = 48            # algorithmic bytes / system-step, fwd+grad: u and target once per sweep
+WAVE = 148 * 2 * 128  # systems per full wave of the adjoint kernel (2 CTAs/SM x 128 systems)
+NOMINAL = [10384.31640625, 499089.09375, 1321535.125, 1.5348844528198242, 0.5000327825546265,
+           1.000040054321289, 20.119935989379883]
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--systems", type=int, default=1 << 20, help="systems per rank per step")
+    ap.add_argument("--T", type=int, default=T_YEAR)
+    ap.add_argument("--tile", type=int, default=3 * WAVE, help="systems per kernel launch")
+    ap.add_argument("--e2e-systems", type=int, default=32768)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-systems", type=int, default=8192, help="bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks: sampled DURING the timed region through NVML
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr:
+            self._thr.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml_unavailable"]}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def measured_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def ncu_traffic_per_step():
+    """DRAM bytes per system-step of the dominant kernel from the committed ncu capture (or None)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        return None
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle's C port of the reference arithmetic on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_sample(n_sys, T, seed=99):
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    th = (np.array(NOMINAL)[None] * np.exp(rng.uniform(-0.2, 0.2, size=(n_sys, 7)))).astype(np.float32)
+    x0 = (np.array([20.0, 30.0, 26.0])[None] + rng.uniform(-1, 1, size=(n_sys, 3))).astype(np.float32)
+    u = rng.random((T, n_sys, 5), dtype=np.float32)
+    u[..., 0] = 15 + 10 * u[..., 0]
+    target = (20 + 2 * rng.random((T, n_sys), dtype=np.float32)).astype(np.float32)
+    return th, x0, u, target
+
+
+def time_cpu(n_sys, T, steps, warmup):
+    """All-fp32 BPTT of the reference path (oracle/dynax_oracle.c, OpenMP over all host threads)."""
+    from oracle import c_oracle
+    th, x0, u, target = cpu_sample(n_sys, T)
+    c_oracle.lib(native=True)
+    cores = c_oracle.num_threads()
+    for _ in range(warmup):
+        c_oracle.rc_loss_grad(th, x0, u, target, DT, native=True)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        c_oracle.rc_loss_grad(th, x0, u, target, DT, native=True)
+    dt = time.perf_counter() - t0
+    return n_sys * T * steps / dt, cores, dt / steps
+
+
+def reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    val, cores, sec = time_cpu(a.cpu_systems, a.T, a.steps, a.warmup)
+    sample = f"{a.cpu_systems} systems x {a.T} steps per step (bounded sample of the {a.systems}-system workload)"
+    line = {
+        "impl": "reference", "metric": "system-steps/s, fwd+grad RC rollout", "value": val, "unit": "system-steps/s",
+        "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"rc_fwd_grad N={a.systems} T={a.T} dt=3600 per-system theta/u/target", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "system-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "system-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference is JAX/Flax (not installable here: no jax wheel, no network); this arm times the oracle's "
+                "C/OpenMP port of the same arithmetic (all-fp32 BPTT storing per-step residuals like XLA's scan transpose)",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def ours(a):
+    import torch
+    import torch.distributed as dist
+
+    from dynax_b200 import host, ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    T, S = a.T, a.systems
+    tile = min(a.tile, S)
+    tiles = [tile] * (S // tile) + ([S % tile] if S % tile else [])
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    nominal = torch.tensor(NOMINAL, device=dev)
+    theta = nominal[None] * torch.exp(torch.empty((S, 7), device=dev).uniform_(-0.2, 0.2, generator=g))
+    x0 = torch.tensor([[20.0, 30.0, 26.0]], device=dev) + torch.empty((S, 3), device=dev).uniform_(-1, 1, generator=g)
+    u = torch.empty((T, tile, 5), device=dev).uniform_(0, 1, generator=g)
+    u[..., 0] = 15 + 10 * u[..., 0]
+    target = 20 + 2 * torch.empty((T, tile), device=dev).uniform_(0, 1, generator=g)
+    loss = torch.empty((S,), device=dev)
+    grad = torch.empty((S, 7), device=dev)
+    offs = [sum(tiles[:i]) for i in range(len(tiles))]
+    views = []
+    for o, n in zip(offs, tiles):
+        views.append((theta[o:o + n], x0[o:o + n], u if n == tile else u[:, :n].contiguous(),
+                      target if n == tile else target[:, :n].contiguous(), o, n))
+
+    def step():
+        for th_t, x0_t, u_t, tg_t, o, n in views:
+            l, gth, _ = ops.rc_loss_grad(th_t, x0_t, u_t, tg_t, DT)
+            loss[o:o + n].copy_(l, non_blocking=True)
+            grad[o:o + n].copy_(gth, non_blocking=True)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(a.warmup):
+        step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        e0.record()
+        for _ in range(a.steps):
+            step()
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1)
+    t_ms = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms = float(t_ms.item())
+    sec = ms * 1e-3
+    value = world * S * T * a.steps / sec
+    launches = len(tiles) * a.steps
+    assert bool(torch.isfinite(loss).all()) and bool(torch.isfinite(grad).all())
+
+    # ---- end to end: pinned HOST buffers -> host-API call (tiled H2D / kernel / D2H inside) -> host results
+    e2e = None
+    if not a.no_e2e:
+        import numpy as np
+        Ne = a.e2e_systems
+        hu = torch.empty((T, Ne, 5), dtype=torch.float32, pin_memory=True)
+        ht = torch.empty((T, Ne), dtype=torch.float32, pin_memory=True)
+        hth = torch.empty((Ne, 7), dtype=torch.float32, pin_memory=True)
+        hx0 = torch.empty((Ne, 3), dtype=torch.float32, pin_memory=True)
+        nsrc = min(Ne, tile)
+        reps = (Ne + nsrc - 1) // nsrc
+        hu.copy_(u[:, :nsrc].repeat(1, reps, 1)[:, :Ne]); ht.copy_(target[:, :nsrc].repeat(1, reps)[:, :Ne])
+        hth.copy_(theta[:Ne]); hx0.copy_(x0[:Ne])
+        torch.cuda.synchronize()
+        args = (hth.numpy(), hx0.numpy(), hu.numpy(), ht.numpy(), DT)
+        host.rc_loss_grad(*args)          # warm-up (allocates the cached device scratch)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(a.e2e_steps):
+            l_h, g_h = host.rc_loss_grad(*args)
+        e_sec = time.perf_counter() - t0
+        te = torch.tensor([e_sec], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e_sec = float(te.item())
+        assert np.isfinite(l_h).all()
+        e2e = {"value": world * Ne * T * a.e2e_steps / e_sec, "unit": "system-steps/s",
+               "h2d_bytes_per_step": int(hu.numel() + ht.numel() + hth.numel() + hx0.numel()) * 4,
+               "d2h_bytes_per_step": int(l_h.size + g_h.size) * 4,
+               "systems_per_step": Ne, "ms_per_step": e_sec / a.e2e_steps * 1e3,
+               "api": "dynax_rc_loss_grad_host_f32 (pinned host buffers; tiled H2D/kernel/D2H on 2 streams)"}
+        host.release()
+        del hu, ht
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_kind = measured_peak()
+    achieved = S * T * a.steps * B_ALG / sec / 1e9          # per rank: alg bytes of its launches / its time
+    traffic = ncu_traffic_per_step()
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs, copy bandwidth)" if peak_kind == "measured" else "fallback 6.65 TB/s",
+                "kernel": "rollout_adj_kernel<RCModel,128,16,2,MSE>", "alg_bytes_per_system_step": B_ALG,
+                "alg_bytes_per_launch": B_ALG * tile * T, "avg_launch_ms": ms / launches,
+                "traffic": (traffic or {}).get("dram_bytes_per_launch"), "traffic_note": (traffic or {}).get("note")}
+
+    cpu = None
+    if not a.no_cpu_baseline and world == 1:
+        v, cores, s = time_cpu(a.cpu_systems, T, 2, 1)
+        cpu = {"value": v, "unit": "system-steps/s", "cores": cores, "kind": "port",
+               "sample": f"{a.cpu_systems} systems x {T} steps, oracle/dynax_oracle.c (all-fp32 BPTT, OpenMP, -march=native)"}
+
+    line = {
+        "metric": "system-steps/s, fwd+grad RC rollout", "value": value, "unit": "system-steps/s", "n_gpus": world,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"rc_fwd_grad N={S} T={T} dt=3600 per-system theta/u/target (per rank)",
+                   "tile_systems": tile, "tiles_per_step": len(tiles),
+                   "l2": "inputs larger than L2 (u+target tile %.1f GB re-read by each tile launch)" % ((u.numel() + target.numel()) * 4 / 1e9),
+                   "parallelism": f"system axis sharded over {world} rank(s); no data-path collective"},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk.summary(),
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        reference_arm(a)
+    else:
+        ours(a)
+
+
+if __name__ == "__main__":
+    main()

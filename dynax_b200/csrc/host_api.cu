@@ -108,7 +108,7 @@ int dynax_rc_forward_host_f32(const float *theta, const float *x0, const float *
                               float *x_final, int64_t N, int64_t T, float dt, uint32_t flags, int64_t tile_systems) {
     if (N < 0 || T < 0) return fail(DYNAX_ERR_INVALID_ARGUMENT, "negative N or T");
     if (N == 0) return DYNAX_OK;
-    if (!theta || !x0 || !u) return fail(DYNAX_ERR_INVALID_ARGUMENT, "theta, x0 and u must be non-NULL");
+    if (!theta || !x0 || (!u && T > 0)) return fail(DYNAX_ERR_INVALID_ARGUMENT, "theta, x0 and u must be non-NULL");
     TRY(require_sm100());
     HostCtx &c = ctx();
     std::lock_guard<std::mutex> lk(c.mu);

@@ -46,7 +46,8 @@ int dynax_lti_forward_f32(const float *A, const float *B, const float *C, const 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (N < 0 || T < 0) return fail(DYNAX_ERR_INVALID_ARGUMENT, "negative N or T");
     if (N == 0) return DYNAX_OK;
-    if (!A || !B || !C || !D || !x0 || !u) return fail(DYNAX_ERR_INVALID_ARGUMENT, "A,B,C,D,x0,u must be non-NULL");
+    if (!A || !B || !C || !D || !x0 || (!u && T > 0))
+        return fail(DYNAX_ERR_INVALID_ARGUMENT, "A,B,C,D,x0,u must be non-NULL");
     if (flags & ~(DYNAX_SHARED_THETA | DYNAX_SHARED_U | DYNAX_DISCRETE))
         return fail(DYNAX_ERR_INVALID_ARGUMENT, "unsupported flags 0x%x for lti_forward", flags);
     if (!dynax_lti_supported(n, m, p))

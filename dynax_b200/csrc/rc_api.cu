@@ -43,7 +43,7 @@ static int rc_forward(const float *theta, const float *x0, const float *u, float
                       float *x_final, int64_t N, int64_t T, float dt, uint32_t flags, cudaStream_t st) {
     if (N < 0 || T < 0) return fail(DYNAX_ERR_INVALID_ARGUMENT, "negative N or T");
     if (N == 0) return DYNAX_OK;
-    if (!theta || !x0 || !u) return fail(DYNAX_ERR_INVALID_ARGUMENT, "theta, x0 and u must be non-NULL");
+    if (!theta || !x0 || (!u && T > 0)) return fail(DYNAX_ERR_INVALID_ARGUMENT, "theta, x0 and u must be non-NULL");
     if (flags & ~(DYNAX_SHARED_THETA | DYNAX_SHARED_U | DYNAX_DISCRETE))
         return fail(DYNAX_ERR_INVALID_ARGUMENT, "unsupported flags 0x%x for rc_forward", flags);
     int rc = require_sm100();

@@ -288,3 +288,47 @@ def synth_u(T, N, seed):
     u[..., 3] = rng.uniform(0, 2, size=(T, N)) * (np.sin(2 * np.pi * k / 24) > 0)
     u[..., 4] = rng.uniform(0, 1, size=(T, N))
     return u
+
+
+# --------------------------------------------------------------------------------------
+# Conditioning-aware error budgets.  north_star states two tolerances: trajectories within
+# rel 1e-5, gradients within rel 1e-4.  A loss/gradient is a functional of the trajectory, so a
+# trajectory that is itself only specified to 1e-5 determines them no better than the first-order
+# bounds below.  (SURVEY.md section 7 H2 / finding #9: per-element 1e-4 against an fp32 BPTT is
+# below fp32 noise whenever the residual y-target is small against |y|.)
+# --------------------------------------------------------------------------------------
+def rc_output_sensitivity_budget(theta, x0, u, target, dt, traj_rtol=1e-5):
+    """Returns (loss_budget[N], grad_budget[N,7]): how far loss_i and dloss_i/dtheta_j can move when
+    every y_k is perturbed by up to traj_rtol*|y_k| (first order, fp64):
+        loss_budget_i   = (2/T) sum_k |r_k| * traj_rtol*|y_k|
+        grad_budget_ij  = (2/T) sum_k |dy_k/dtheta_j| * traj_rtol*|y_k|
+    dy/dtheta by forward-mode sensitivities of the same Euler recurrence."""
+    th = np.atleast_2d(np.asarray(theta, dtype=np.float64))
+    x = np.array(x0, dtype=np.float64)
+    u = np.asarray(u, dtype=np.float64)
+    tg = np.asarray(target, dtype=np.float64)
+    T = u.shape[0]
+    N = x.shape[0]
+    A, B, _, _ = rc_abcd(th, np.float64)
+    dA = np.empty((N, 7, 3, 3)); dB = np.empty((N, 7, 3, 5))
+    for j in range(7):
+        h = 1e-6 * th[:, j]
+        tp, tm = th.copy(), th.copy()
+        tp[:, j] += h; tm[:, j] -= h
+        Ap, Bp, _, _ = rc_abcd(tp, np.float64)
+        Am, Bm, _, _ = rc_abcd(tm, np.float64)
+        dA[:, j] = (Ap - Am) / (2 * h)[:, None, None]
+        dB[:, j] = (Bp - Bm) / (2 * h)[:, None, None]
+    S = np.zeros((N, 3, 7))
+    lb = np.zeros(N); gb = np.zeros((N, 7))
+    for k in range(T):
+        uk = np.broadcast_to(u[k], (N, 5))
+        y = x[:, 0]
+        r = y - (tg[k] if tg.ndim == 2 else tg[k])
+        w = traj_rtol * np.abs(y)
+        lb += np.abs(r) * w
+        gb += np.abs(S[:, 0, :]) * w[:, None]
+        forcing = np.einsum("njab,nb->naj", dA, x) + np.einsum("njab,nb->naj", dB, uk)
+        S = S + dt * (np.einsum("nab,nbj->naj", A, S) + forcing)
+        x = x + dt * (_bmv(A, x) + _bmv(B, uk))
+    return (2.0 / T) * lb, (2.0 / T) * gb

@@ -78,7 +78,10 @@ def main():
     d = os.path.join(REF, "resources/jax/data")
     cols = [("out_temp", 1.0), ("qint_lump", 1e-3), ("qhvac_lump", 1e-3), ("qwin_lump", 1e-3),
             ("qradin_lump", 1e-3), ("zone_temp", 1.0)]
-    data = pd.concat([pd.read_csv(os.path.join(d, c + ".csv"), index_col=[0]) * s for c, s in cols], axis=1)
+    # positional concat (the files share one 1-minute time base; their Date/Time labels are not unique
+    # so label alignment would inject NaNs)
+    data = pd.concat([pd.read_csv(os.path.join(d, c + ".csv"), index_col=[0]).reset_index(drop=True) * s
+                      for c, s in cols], axis=1)
     data.index = range(0, len(data) * 60, 60)
     hourly = data.groupby([data.index // 3600]).mean()
     np.savez_compressed(os.path.join(OUT, "c1_hourly.npz"),

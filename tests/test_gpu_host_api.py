@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from oracle import c_oracle, dynax_oracle as orc
-from tests.util import grad_ok, rel_err
+from tests.util import assert_grad_parity, assert_loss_parity, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -35,10 +35,11 @@ def test_loss_grad_host_tiled_matches_device_api():
     target = (22 + np.random.default_rng(4).normal(size=(Tn, N))).astype(np.float32)
     th[3, 0] = 5e4
     l64, g64 = orc.rc_loss_grad(th, x0, u, target, 3600.0, orc.RC_LB, orc.RC_UB)
+    lbud, gbud = orc.rc_output_sensitivity_budget(th, x0, u, target, 3600.0)
     for tile in (0, 256):
         loss, grad = host.rc_loss_grad(th, x0, u, target, 3600.0, orc.RC_LB, orc.RC_UB, tile_systems=tile)
-        assert np.allclose(loss, l64, rtol=1e-5)
-        assert grad_ok(grad, g64, None, 1e-4)[0] < 1e-4
+        assert_loss_parity(loss, l64, lbud)
+        assert_grad_parity(grad, g64, gbud)
     ld, gd, _ = ops.rc_loss_grad(*(torch.tensor(v).cuda() for v in (th, x0, u, target)), 3600.0, orc.RC_LB, orc.RC_UB)
     assert np.array_equal(ld.cpu().numpy(), loss) and np.array_equal(gd.cpu().numpy(), grad)
     # shared theta across tiles: sums reduced on the host, penalty once
@@ -47,5 +48,6 @@ def test_loss_grad_host_tiled_matches_device_api():
     lr, gr = orc.rc_loss_grad(np.repeat(th1[None], N, 0), x0, u, target, 3600.0)
     pen = orc.bound_penalty(th1[None], orc.RC_LB, orc.RC_UB)[0]
     gs = gr.sum(0) + orc.bound_penalty_grad(th1[None], orc.RC_LB, orc.RC_UB)[0]
-    assert np.allclose(loss1[0], lr.sum() + pen, rtol=1e-5)
-    assert np.linalg.norm(grad1 - gs) / np.linalg.norm(gs) < 1e-4
+    lbud, gbud = orc.rc_output_sensitivity_budget(np.repeat(th1[None], N, 0), x0, u, target, 3600.0)
+    assert_loss_parity(loss1[0], lr.sum() + pen, lbud.sum())
+    assert_grad_parity(grad1, gs, gbud.sum(0))
