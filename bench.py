@@ -135,6 +135,7 @@ def time_cpu(n_sys, T, steps, warmup):
     from oracle import c_oracle
     th, x0, u, target = cpu_sample(n_sys, T)
     c_oracle.lib(native=True)
+    c_oracle.use_all_cores()
     cores = c_oracle.num_threads()
     for _ in range(warmup):
         c_oracle.rc_loss_grad(th, x0, u, target, DT, native=True)

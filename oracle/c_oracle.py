@@ -39,6 +39,7 @@ def lib(native=False):
     L.oracle_rc_forward_f32.argtypes = [fp] * 6 + [ctypes.c_long, ctypes.c_long, ctypes.c_float, ctypes.c_int, ctypes.c_int]
     L.oracle_rc_loss_grad_f32.argtypes = [fp] * 8 + [ctypes.c_long, ctypes.c_long, ctypes.c_float] + [ctypes.c_int] * 3
     L.oracle_num_threads.restype = ctypes.c_int
+    L.oracle_set_num_threads.argtypes = [ctypes.c_int]
     _LIB = L
     return L
 
@@ -53,6 +54,13 @@ def _f32(a):
 
 def num_threads():
     return lib().oracle_num_threads()
+
+
+def use_all_cores():
+    """Override OMP_NUM_THREADS (torchrun exports OMP_NUM_THREADS=1) with every host core."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().oracle_set_num_threads(n)
+    return n
 
 
 def rc_forward(theta, x0, u, dt, emit_x=True, emit_y=True, native=False):
