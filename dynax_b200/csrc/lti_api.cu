@@ -16,7 +16,7 @@ template <int n, int m, int p>
 static int lti_forward_t(const FwdParams<DenseModel<n, m, p>> &P, bool shared_u, cudaStream_t st) {
     using M = DenseModel<n, m, p>;
     if (shared_u) return launch_fwd<M, 128, 4, 2, true, 2>(P, st);
-    return launch_fwd<M, 128, 4, 2, false, 2>(P, st);
+    return launch_fwd<M, 256, 4, 4, false, 1>(P, st);  // wide rows: 5 KB+ per bulk copy (see rc_api.cu)
 }
 
 template <int n, int m, int p>

@@ -64,9 +64,11 @@ static int rc_forward(const float *theta, const float *x0, const float *u, float
     P.bulk_out = rows16 && (!xsol || aligned16(xsol)) && (!ysol || aligned16(ysol));
     if (env_int("DYNAX_NO_BULK", 0)) P.bulk_in = P.bulk_out = 0;
     if (flags & DYNAX_SHARED_U) return launch_fwd<RCModel, 128, 4, 4, true, 4>(P, st);
+    // Tile shapes measured on B200 (tools/tune.py, N=132608, T=8760): wide rows win because each
+    // cp.async.bulk then moves 5 KB.  0: 6.45 TB/s (x+y), 1: 5.43, 2: 5.31, 3: 5.80.
     switch (env_int("DYNAX_FWD_CFG", 0)) {
         default:
-        case 0: return launch_fwd<RCModel, 128, 2, 4, false, 6>(P, st);
+        case 0: return launch_fwd<RCModel, 256, 4, 4, false, 1>(P, st);
         case 1: return launch_fwd<RCModel, 128, 4, 4, false, 3>(P, st);
         case 2: return launch_fwd<RCModel, 64, 4, 4, false, 6>(P, st);
         case 3: return launch_fwd<RCModel, 128, 8, 2, false, 3>(P, st);
