@@ -38,6 +38,7 @@ SIGNATURES = {
     "dynax_rc_forward_host_f32": (_int, [_f] * 6 + [_i64, _i64, _flt, _u32, _i64]),
     "dynax_rc_loss_grad_host_f32": (_int, [_f] * 8 + [_i64, _i64, _flt, _u32, _i64]),
     "dynax_host_release": (_int, []),
+    "dynax_rc_mpc_cost_f32": (_int, [_f] * 7 + [_flt] * 4 + [_f] * 3 + [_i64, _i64, _flt, _f, _sz, _f]),
 }
 
 _LIB = None
@@ -48,7 +49,7 @@ def lib():
     if _LIB is None:
         if not os.path.exists(LIB_PATH):
             raise ImportError(
-                f"{LIB_PATH} is missing: build it with `python -m dynax_b200.build` "
+                f"{LIB_PATH} is missing: build it with `python dynax_b200/build.py` "
                 "(dynax_b200 has no CPU or PyTorch fallback)")
         L = ctypes.CDLL(LIB_PATH)
         for name, (res, args) in SIGNATURES.items():

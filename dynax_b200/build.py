@@ -1,6 +1,6 @@
 """Build libdynax_b200.so (sm_100a only) in-tree with nvcc.  No torch, no JIT cache.
 
-    python -m dynax_b200.build [--force] [-v]
+    python dynax_b200/build.py [--force] [-v]
 
 The .so is git-ignored but travels to the GPU box with the repo snapshot.
 """

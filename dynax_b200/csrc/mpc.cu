@@ -1,0 +1,161 @@
+// Sampling-based MPC: cost of N candidate control sequences through ONE shared 4R3C model
+// (BASELINE.json config 4).  Each candidate is the rollout of DifferentiableSimulator
+// (/root/reference/dynax/simulators/simulator.py:36-43) with inputs assembled as in the RC env
+//     inputs_k = [d_k0, d_k1, u_k, d_k2, d_k3]                    (dynax/wrapper/envs/rc.py:131)
+// and the per-step cost is the negated env reward (rc.py:227-252):
+//     cost_k = w0 * price[h] * (-u_k/COP) * dt/3600 + w1 * (relu(y_k - T_high[h]) + relu(T_low[h] - y_k))
+// with y_k = x_k[0] taken from the PRE-update state and the hour index h from the POST-update time
+// (rc.py:135-144,238).
+//
+// One thread == one candidate; theta, x0, the disturbance series and the schedules are shared, so
+// everything that does not depend on the candidate (B d_k, the price/comfort bands per step) is
+// folded into a per-step table in shared memory once per CTA.  HBM traffic is 4 B per
+// candidate-step (u) + 4/H (cost): the kernel sits at the FP32 issue roof, not the HBM roof.
+#include <float.h>
+#include <string.h>
+
+#include "api_common.cuh"
+#include "models.cuh"
+
+namespace dynax {
+
+struct MpcParams {
+    const float *theta;   // [7]
+    const float *x0;      // [3]
+    const float *d;       // [H,4]  disturbances: Tao, qCon_i, qRad_e, qRad_i
+    const float *u;       // [H,N]  candidate HVAC heat flows
+    const float *price, *t_low, *t_high;  // [24] hourly schedules
+    float *cost;          // [N]
+    unsigned long long *best;  // packed (ordered cost bits << 32 | candidate index) or NULL
+    int64_t N, H;
+    float dt, cop, w_energy, w_comfort, start_time;
+};
+
+struct MpcStep {  // per-step shared constants, 32 bytes
+    float bd0, bd1, bd2;  // (B d_k) without the control column
+    float ce;             // w0 * price[h] * (-1/COP) * dt/3600
+    float lo, hi;         // comfort band at hour h
+    float pad0, pad1;
+};
+
+__device__ __forceinline__ unsigned int order_bits(float f) {
+    unsigned int b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);  // monotone map float -> uint
+}
+
+constexpr int kMpcThreads = 256;
+constexpr int kMpcUnroll = 8;
+
+__global__ void __launch_bounds__(kMpcThreads) rc_mpc_cost_kernel(const MpcParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    MpcStep *tab = reinterpret_cast<MpcStep *>(smem_raw);
+    const int64_t H = P.H, N = P.N;
+    RCModel M;
+    RCModel::Ptrs mp{P.theta, 0};
+    M.load(mp, 0);
+    for (int64_t k = threadIdx.x; k < H; k += blockDim.x) {
+        const float *dk = P.d + k * 4;
+        MpcStep s;
+        // B @ [d0, d1, u, d2, d3] without the u column (RC.py:222-230)
+        s.bd0 = M.B00 * dk[0] + M.B01 * dk[1];
+        s.bd1 = M.B10 * dk[0] + M.B13 * dk[2];
+        s.bd2 = M.B24 * dk[3];
+        const float t_next = P.start_time + (float)(k + 1) * P.dt;      // rc.py:137 states.time + dt
+        const int h = (int)((((int)t_next) % 86400) / 3600.0f);        // rc.py:238
+        s.ce = P.w_energy * (__ldg(P.price + h) * (P.dt / 3600.0f)) * (-1.0f / P.cop);
+        s.lo = __ldg(P.t_low + h);
+        s.hi = __ldg(P.t_high + h);
+        s.pad0 = s.pad1 = 0.f;
+        tab[k] = s;
+    }
+    __syncthreads();
+
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = i < N;
+    const int64_t ii = active ? i : (N - 1);
+    float x[3] = {__ldg(P.x0), __ldg(P.x0 + 1), __ldg(P.x0 + 2)};
+    const float dt = P.dt, w1 = P.w_comfort;
+    float cost = 0.f;
+    const float *up = P.u + ii;
+    for (int64_t k0 = 0; k0 < H; k0 += kMpcUnroll) {
+        float uu[kMpcUnroll];
+#pragma unroll
+        for (int j = 0; j < kMpcUnroll; ++j) uu[j] = (k0 + j < H) ? __ldcs(up + (k0 + j) * N) : 0.f;
+#pragma unroll
+        for (int j = 0; j < kMpcUnroll; ++j) {
+            if (k0 + j < H) {
+                const float4 a = *reinterpret_cast<const float4 *>(&tab[k0 + j]);        // bd0 bd1 bd2 ce
+                const float2 b = *reinterpret_cast<const float2 *>(&tab[k0 + j].lo);     // lo hi
+                const float y = x[0];  // pre-update output (simulator.py:38)
+                const float dTz = fmaxf(y - b.y, 0.f) + fmaxf(b.x - y, 0.f);
+                cost = fmaf(a.w, uu[j], cost);   // energy: w0*price*(-u/COP)*dt/3600
+                cost = fmaf(w1, dTz, cost);
+                const float r0 = (M.A00 * x[0] + M.A02 * x[2]) + (a.x + M.B02 * uu[j]);
+                const float r1 = (M.A11 * x[1] + M.A12 * x[2]) + a.y;
+                const float r2 = (M.A20 * x[0] + M.A21 * x[1] + M.A22 * x[2]) + a.z;
+                x[0] = fmaf(dt, r0, x[0]);
+                x[1] = fmaf(dt, r1, x[1]);
+                x[2] = fmaf(dt, r2, x[2]);
+            }
+        }
+    }
+    if (active) P.cost[i] = cost;
+    if (P.best != nullptr) {
+        unsigned long long key = active ? (((unsigned long long)order_bits(cost) << 32) | (unsigned long long)(uint32_t)i)
+                                        : ~0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+            key = other < key ? other : key;
+        }
+        if ((threadIdx.x & 31) == 0) atomicMin(P.best, key);
+    }
+}
+
+__global__ void rc_mpc_decode_kernel(const unsigned long long *best, const float *cost, long long *argmin,
+                                     float *min_cost) {
+    const unsigned long long key = *best;
+    const long long idx = (long long)(key & 0xffffffffull);
+    if (argmin) *argmin = idx;
+    if (min_cost) *min_cost = cost[idx];
+}
+
+}  // namespace dynax
+
+using namespace dynax;
+
+extern "C" int dynax_rc_mpc_cost_f32(const float *theta, const float *x0, const float *d, const float *u,
+                                     const float *price, const float *t_low, const float *t_high, float cop,
+                                     float w_energy, float w_comfort, float start_time, float *cost,
+                                     long long *argmin, float *min_cost, int64_t N, int64_t H, float dt, void *ws,
+                                     size_t ws_bytes, void *stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (N < 0 || H < 1) return fail(DYNAX_ERR_INVALID_ARGUMENT, "need N >= 0 and H >= 1");
+    if (N == 0) return DYNAX_OK;
+    if (!theta || !x0 || !d || !u || !price || !t_low || !t_high || !cost)
+        return fail(DYNAX_ERR_INVALID_ARGUMENT, "theta,x0,d,u,price,t_low,t_high,cost must be non-NULL");
+    if (N > 0xffffffffLL) return fail(DYNAX_ERR_INVALID_ARGUMENT, "N must fit 32 bits (argmin packing)");
+    if (cop == 0.f) return fail(DYNAX_ERR_INVALID_ARGUMENT, "COP must be non-zero");
+    const size_t smem = sizeof(MpcStep) * (size_t)H;
+    if (smem > 200 * 1024) return fail(DYNAX_ERR_INVALID_ARGUMENT, "horizon too long for the shared-memory step table (H <= 6400)");
+    const bool want_min = argmin != nullptr || min_cost != nullptr;
+    if (want_min && (!ws || ws_bytes < 16 || !aligned16(ws)))
+        return fail(DYNAX_ERR_WORKSPACE, "argmin needs a 16-byte aligned workspace of >= 16 bytes");
+    int rc = require_sm100();
+    if (rc != DYNAX_OK) return rc;
+    MpcParams P;
+    P.theta = theta; P.x0 = x0; P.d = d; P.u = u; P.price = price; P.t_low = t_low; P.t_high = t_high;
+    P.cost = cost; P.best = want_min ? reinterpret_cast<unsigned long long *>(ws) : nullptr;
+    P.N = N; P.H = H; P.dt = dt; P.cop = cop; P.w_energy = w_energy; P.w_comfort = w_comfort; P.start_time = start_time;
+    if (want_min) DYNAX_CUDA_TRY(cudaMemsetAsync(ws, 0xff, 8, st));
+    rc = set_smem(rc_mpc_cost_kernel, smem);
+    if (rc != DYNAX_OK) return rc;
+    const int64_t grid = (N + kMpcThreads - 1) / kMpcThreads;
+    rc_mpc_cost_kernel<<<(unsigned)grid, kMpcThreads, smem, st>>>(P);
+    DYNAX_CUDA_TRY(cudaGetLastError());
+    if (want_min) {
+        rc_mpc_decode_kernel<<<1, 1, 0, st>>>(P.best, cost, argmin, min_cost);
+        DYNAX_CUDA_TRY(cudaGetLastError());
+    }
+    return DYNAX_OK;
+}

@@ -296,3 +296,35 @@ class _LTIRollout(torch.autograd.Function):
 def lti_rollout(A, B, C, D, x0, u, dt, discrete=False):
     """Differentiable batched dense-LTI rollout: returns xsol[T,N,n], ysol[T,N,p]."""
     return _LTIRollout.apply(A, B, C, D, x0, u, float(dt), bool(discrete))
+
+
+# ----------------------------------------------------------------------------------------------
+# sampling-based MPC (config 4)
+# ----------------------------------------------------------------------------------------------
+def rc_mpc_cost(theta, x0, d, u, price, t_low, t_high, dt, cop=2.5, w_energy=100.0, w_comfort=1.0,
+                start_time=0.0, want_argmin=True):
+    """Cost of N candidate control sequences through one shared 4R3C model (rc.py:131,227-252).
+
+    theta[7], x0[3], d[H,4] (Tao,qCon_i,qRad_e,qRad_i), u[H,N], price/t_low/t_high[24].
+    Returns (cost[N], argmin (0-d int64 tensor) or None, min_cost (0-d) or None).
+    """
+    theta, x0, d, u = (_f32c(t, nm) for t, nm in ((theta, "theta"), (x0, "x0"), (d, "d"), (u, "u")))
+    price, t_low, t_high = (_f32c(t, nm) for t, nm in ((price, "price"), (t_low, "t_low"), (t_high, "t_high")))
+    if theta.numel() != 7 or x0.numel() != 3:
+        raise ValueError("theta must be [7] and x0 [3] (one shared model)")
+    if u.dim() != 2 or d.dim() != 2 or d.shape != (u.shape[0], 4):
+        raise ValueError(f"u must be [H,N] and d [H,4], got {tuple(u.shape)} and {tuple(d.shape)}")
+    if price.numel() != 24 or t_low.numel() != 24 or t_high.numel() != 24:
+        raise ValueError("price, t_low, t_high must be hourly tables of 24 entries")
+    H, N = u.shape
+    dev = u.device
+    cost = torch.empty((N,), dtype=torch.float32, device=dev)
+    amin = torch.empty((), dtype=torch.int64, device=dev) if want_argmin else None
+    cmin = torch.empty((), dtype=torch.float32, device=dev) if want_argmin else None
+    ws = _ws(16, dev)
+    with torch.cuda.device(dev):
+        check(lib().dynax_rc_mpc_cost_f32(_ptr(theta), _ptr(x0), _ptr(d), _ptr(u), _ptr(price), _ptr(t_low),
+                                          _ptr(t_high), float(cop), float(w_energy), float(w_comfort),
+                                          float(start_time), _ptr(cost), _ptr(amin), _ptr(cmin), N, H, float(dt),
+                                          _ptr(ws), ws.numel(), _stream()))
+    return cost, amin, cmin

@@ -114,6 +114,19 @@ int dynax_lti_vjp_f32(const float *A, const float *B, const float *C, const floa
                       int64_t N, int64_t T, int n, int m, int p, float dt, uint32_t flags,
                       void *ws, size_t ws_bytes, void *stream);
 
+/* ---- Sampling-based MPC (BASELINE.json config 4): cost of N candidate control sequences u[H,N] through
+ *      ONE shared 4R3C model.  Inputs per step are assembled as the RC env does,
+ *      [d_k0, d_k1, u_k, d_k2, d_k3] (dynax/wrapper/envs/rc.py:131), rolled out by simulator.py:36-43, and
+ *      cost_i = sum_k  w_energy*price[h]*(-u_k/COP)*dt/3600 + w_comfort*(relu(y_k-t_high[h]) + relu(t_low[h]-y_k))
+ *      i.e. the negated env reward (rc.py:227-252): y_k from the pre-update state, hour h from the
+ *      post-update time start_time+(k+1)*dt.  theta:[7] x0:[3] d:[H,4] u:[H,N] price/t_low/t_high:[24]
+ *      cost:[N]; argmin (int64) / min_cost (float) may be NULL, else ws must hold >= 16 bytes. ---- */
+int dynax_rc_mpc_cost_f32(const float *theta, const float *x0, const float *d, const float *u,
+                          const float *price, const float *t_low, const float *t_high,
+                          float cop, float w_energy, float w_comfort, float start_time,
+                          float *cost, long long *argmin, float *min_cost,
+                          int64_t N, int64_t H, float dt, void *ws, size_t ws_bytes, void *stream);
+
 /* ---- Host-buffer entry points (the call a reference user makes with NumPy/JAX-CPU arrays):
  *      pageable or pinned HOST pointers in, results in HOST buffers on return.  The system axis is
  *      processed in tiles of `tile_systems` (0 = library default) with copies overlapped. ------ */

@@ -332,3 +332,39 @@ def rc_output_sensitivity_budget(theta, x0, u, target, dt, traj_rtol=1e-5):
         S = S + dt * (np.einsum("nab,nbj->naj", A, S) + forcing)
         x = x + dt * (_bmv(A, x) + _bmv(B, uk))
     return (2.0 / T) * lb, (2.0 / T) * gb
+
+
+# --------------------------------------------------------------------------------------
+# Config 4: sampling-based MPC cost = negated RC-env reward summed over the horizon.
+#   dynax/wrapper/envs/rc.py:125-147 (step), :200-222 (obs), :227-252 (reward), :32-42 (schedules)
+# Pinned for H=1 by golden #2 (REWARD=-0.05974, tests/test_gymwrapper_basics.py:8).
+# --------------------------------------------------------------------------------------
+RC_T_LOW = np.array([12.0] * 8 + [22.0] * 10 + [12.0] * 6)          # rc.py:32-33
+RC_T_HIGH = np.array([30.0] * 8 + [26.0] * 10 + [30.0] * 6)         # rc.py:34-35
+RC_PRICE = np.array([0.02987] * 6 + [0.04667] * 6 + [0.15877] * 7 + [0.04667] * 3 + [0.02987] * 2)  # rc.py:37-42
+
+
+def mpc_cost(theta, x0, d, u, dt, price=RC_PRICE, t_low=RC_T_LOW, t_high=RC_T_HIGH, cop=2.5,
+             w_energy=100.0, w_comfort=1.0, start_time=0.0, dtype=np.float32):
+    """theta[7], x0[3], d[H,4], u[H,N] -> cost[N] (sum over the horizon of -reward)."""
+    u = np.asarray(u, dtype=dtype)
+    d = np.asarray(d, dtype=dtype)
+    H, N = u.shape
+    A, B, _, _ = rc_abcd(np.asarray(theta)[None], dtype)
+    x = np.repeat(np.asarray(x0, dtype=dtype)[None], N, 0)
+    price, t_low, t_high = (np.asarray(v, dtype=dtype) for v in (price, t_low, t_high))
+    dtf = dtype(dt)
+    cost = np.zeros(N, dtype=dtype)
+    t = dtype(start_time)
+    for k in range(H):
+        inp = np.empty((N, 5), dtype=dtype)                      # rc.py:131
+        inp[:, 0], inp[:, 1], inp[:, 2], inp[:, 3], inp[:, 4] = d[k, 0], d[k, 1], u[k], d[k, 2], d[k, 3]
+        y = x[:, 0].copy()                                       # pre-update output
+        x = x + dtf * (_bmv(A, x) + _bmv(B, inp))                # simulator.py:38-40
+        t = t + dtf                                              # rc.py:137
+        h = int((int(t) % 86400) / 3600)                         # rc.py:238
+        energy = (-u[k] / dtype(cop)) * dtf / dtype(3600.0)      # rc.py:221,241
+        c = price[h] * energy                                    # rc.py:244
+        dTz = np.maximum(y - t_high[h], 0) + np.maximum(t_low[h] - y, 0)   # rc.py:247
+        cost += dtype(w_energy) * c + dtype(w_comfort) * dTz     # -(reward) rc.py:250
+    return cost

@@ -21,8 +21,12 @@ def header_functions():
 
 @pytest.fixture(scope="module")
 def built():
-    from dynax_b200 import build
-    return build.build()
+    # load build.py by path: importing the package would (rightly) refuse a stale or missing library
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("dynax_b200_build", os.path.join(ROOT, "dynax_b200", "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.build()
 
 
 def test_header_declares_expected_entry_points():

@@ -1,0 +1,67 @@
+"""GPU parity: sampling-based MPC cost kernel (config 4) vs the oracle and the env golden."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import dynax_oracle as orc
+from tests.util import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def T():
+    import torch
+    return torch
+
+
+def cu(T, a):
+    return T.as_tensor(np.ascontiguousarray(a, dtype=np.float32)).cuda()
+
+
+def sched(T):
+    return cu(T, orc.RC_PRICE), cu(T, orc.RC_T_LOW), cu(T, orc.RC_T_HIGH)
+
+
+def test_one_step_matches_env_golden(T, golden_dir):
+    from dynax_b200 import ops
+    g = json.load(open(os.path.join(golden_dir, "golden2.json")))
+    r0 = g["disturbance_row0"]
+    d = np.array([[r0["out_temp"], r0["qint_lump"], r0["qwin_lump"], r0["qradin_lump"]]], np.float32)
+    cost, amin, cmin = ops.rc_mpc_cost(cu(T, g["theta"]), cu(T, g["x0"]), cu(T, d), cu(T, [[-3.0, -1.0, 0.0]]),
+                                       *sched(T), g["dt"], g["COP"], g["weights"][0], g["weights"][1])
+    assert abs(cost[0].item() + g["REWARD"]) < 1e-6          # tests/test_gymwrapper_basics.py:8
+    assert amin.item() == 2 and cmin.item() == cost[2].item()
+
+
+@pytest.mark.parametrize("N,H,start", [(5000, 96, 0.0), (257, 96, 8 * 3600.0), (1, 7, 0.0), (100000, 24, 6.5 * 3600)])
+def test_matches_oracle(T, N, H, start):
+    from dynax_b200 import ops
+    rng = np.random.default_rng(91)
+    d = np.stack([10 + 15 * rng.random(H), rng.random(H), 2 * rng.random(H), rng.random(H)], 1).astype(np.float32)
+    u = (-10 * rng.random((H, N))).astype(np.float32)
+    x0 = np.array([20.0, 35.8, 26.0], np.float32)
+    cost, amin, cmin = ops.rc_mpc_cost(cu(T, orc.RC_NOMINAL), cu(T, x0), cu(T, d), cu(T, u), *sched(T), 900.0,
+                                       start_time=start)
+    ref = orc.mpc_cost(orc.RC_NOMINAL, x0, d, u, 900.0, start_time=start, dtype=np.float64)
+    assert rel_err(cost.cpu().numpy(), ref, floor=1.0) < 1e-5
+    c = cost.cpu().numpy()
+    assert amin.item() == int(np.argmin(c)) and cmin.item() == c.min()      # ties -> lowest index
+
+
+def test_argmin_large_and_errors(T):
+    from dynax_b200 import ops
+    from dynax_b200._lib import DynaxError
+    N, H = 1 << 20, 96
+    g = T.Generator(device="cuda").manual_seed(3)
+    u = -10 * T.rand((H, N), device="cuda", generator=g)
+    d = cu(T, np.stack([20 + np.zeros(H), 0.5 + np.zeros(H), np.zeros(H), np.zeros(H)], 1))
+    cost, amin, cmin = ops.rc_mpc_cost(cu(T, orc.RC_NOMINAL), cu(T, [20.0, 35.8, 26.0]), d, u, *sched(T), 900.0)
+    assert amin.item() == int(T.argmin(cost).item()) and cmin.item() == cost.min().item()
+    idx = np.random.default_rng(2).choice(N, 32, replace=False)
+    ref = orc.mpc_cost(orc.RC_NOMINAL, [20.0, 35.8, 26.0], d.cpu().numpy(), u[:, idx].cpu().numpy(), 900.0, dtype=np.float64)
+    assert rel_err(cost[idx].cpu().numpy(), ref, floor=1.0) < 1e-5
+    with pytest.raises(ValueError):
+        ops.rc_mpc_cost(cu(T, orc.RC_NOMINAL), cu(T, [20.0, 35.8, 26.0]), d[:5], u, *sched(T), 900.0)

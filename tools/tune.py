@@ -38,6 +38,19 @@ def main():
     a = ap.parse_args()
     N, T = a.N, a.T
     g = torch.Generator(device="cuda").manual_seed(0)
+    if "mpc" in a.what:
+        Nm, H = 1 << 22, 96
+        um = -10 * torch.rand((H, Nm), device="cuda", generator=g)
+        d = torch.rand((H, 4), device="cuda", generator=g)
+        d[:, 0] = 15 + 10 * d[:, 0]
+        price = torch.full((24,), 0.05, device="cuda"); lo = torch.full((24,), 22.0, device="cuda"); hi = torch.full((24,), 26.0, device="cuda")
+        th1 = torch.tensor(NOMINAL, device="cuda"); x01 = torch.tensor([20.0, 35.8, 26.0], device="cuda")
+        best, avg = timeit(lambda: ops.rc_mpc_cost(th1, x01, d, um, price, lo, hi, 900.0), iters=5)
+        st = Nm * H
+        print(f"mpc N={Nm} H={H} best {best*1e3:8.3f} ms avg {avg*1e3:8.3f} ms  {st/best:.3e} cand-steps/s  {st*4/best/1e9:7.1f} GB/s", flush=True)
+        del um
+        if a.what == "mpc":
+            return
     th = torch.tensor(NOMINAL, device="cuda")[None] * torch.exp(torch.empty((N, 7), device="cuda").uniform_(-0.2, 0.2, generator=g))
     x0 = torch.tensor([[20.0, 30.0, 26.0]], device="cuda") + torch.empty((N, 3), device="cuda").uniform_(-1, 1, generator=g)
     u = torch.empty((T, N, 5), device="cuda").uniform_(0, 1, generator=g)
