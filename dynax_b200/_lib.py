@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdynax_b200.so")
 
 # flags / ops (include/dynax_b200.h)
-SHARED_THETA, SHARED_U, SHARED_TARGET, DISCRETE = 1, 2, 4, 8
+SHARED_THETA, SHARED_U, SHARED_TARGET, DISCRETE, SOLVER_EULER = 1, 2, 4, 8, 16
 OP_RC_FORWARD, OP_RC_LOSS_GRAD, OP_RC_VJP, OP_LTI_FORWARD, OP_LTI_VJP = 0, 1, 2, 3, 4
 
 _f = ctypes.c_void_p       # device or host float* passed as an integer address
@@ -38,6 +38,7 @@ SIGNATURES = {
     "dynax_rc_forward_host_f32": (_int, [_f] * 6 + [_i64, _i64, _flt, _u32, _i64]),
     "dynax_rc_loss_grad_host_f32": (_int, [_f] * 8 + [_i64, _i64, _flt, _u32, _i64]),
     "dynax_host_release": (_int, []),
+    "dynax_node_rk4_forward_f32": (_int, [_f] * 11 + [_i64, _i64, _int, _int, _int, _int, _flt, _u32, _f]),
     "dynax_rc_mpc_cost_f32": (_int, [_f] * 7 + [_flt] * 4 + [_f] * 3 + [_i64, _i64, _flt, _f, _sz, _f]),
 }
 

@@ -63,6 +63,19 @@ struct RCModel {
         r[2] = ax2 + bu2;
     }
 
+
+    // ---- hooks used by the rollout kernels ----
+    static constexpr int SMEM_FLOATS = 0;  // no block-shared model data
+    __device__ __forceinline__ static void block_init(float *, const Ptrs &, int, int) {}
+    __device__ __forceinline__ void load(const Ptrs &P, int64_t i, const float *) { load(P, i); }
+    // explicit Euler in residual form (simulator.py:40); `discrete` steps x_{k+1} = rhs instead
+    __device__ __forceinline__ void step(float *x, const float *u, float dt, bool discrete) const {
+        float r[n];
+        rhs(x, u, r);
+#pragma unroll
+        for (int d = 0; d < n; ++d) x[d] = discrete ? r[d] : fmaf(dt, r[d], x[d]);
+    }
+
     // y = C x + D u with C=[1,0,0], D=0  (RC.py:236-249)
     __device__ __forceinline__ void out(const float *x, const float *, float *y) const { y[0] = x[0]; }
 
@@ -162,6 +175,19 @@ struct DenseModel {
             for (int j = 1; j < m; ++j) bu = fmaf(B[i * m + j], u[j], bu);
             r[i] = ax + bu;  // fxx(x) + fxu(u)   base_block_state_space.py:61
         }
+    }
+
+
+    // ---- hooks used by the rollout kernels ----
+    static constexpr int SMEM_FLOATS = 0;  // no block-shared model data
+    __device__ __forceinline__ static void block_init(float *, const Ptrs &, int, int) {}
+    __device__ __forceinline__ void load(const Ptrs &P, int64_t i, const float *) { load(P, i); }
+    // explicit Euler in residual form (simulator.py:40); `discrete` steps x_{k+1} = rhs instead
+    __device__ __forceinline__ void step(float *x, const float *u, float dt, bool discrete) const {
+        float r[n];
+        rhs(x, u, r);
+#pragma unroll
+        for (int d = 0; d < n; ++d) x[d] = discrete ? r[d] : fmaf(dt, r[d], x[d]);
     }
 
     __device__ __forceinline__ void out(const float *x, const float *u, float *y) const {

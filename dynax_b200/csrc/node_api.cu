@@ -1,0 +1,40 @@
+// C-ABI entry point for the general fx/fy path with MLP dynamics + RK4 (config 5, row A7).
+// CUDA-core implementation (mlp_model.cuh) on the shared forward pipeline (TMA-staged u, smem
+// out-tiles).  See include/dynax_b200.h.
+#include "launch.cuh"
+#include "mlp_model.cuh"
+
+using namespace dynax;
+
+extern "C" int dynax_node_rk4_forward_f32(const float *W1, const float *b1, const float *W2, const float *b2,
+                                          const float *W3, const float *b3, const float *x0, const float *u,
+                                          float *xsol, float *ysol, float *x_final, int64_t N, int64_t T, int n,
+                                          int m, int p, int hidden, float dt, uint32_t flags, void *stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (N < 0 || T < 0) return fail(DYNAX_ERR_INVALID_ARGUMENT, "negative N or T");
+    if (N == 0) return DYNAX_OK;
+    if (!W1 || !b1 || !W2 || !b2 || !W3 || !b3 || !x0 || (!u && T > 0))
+        return fail(DYNAX_ERR_INVALID_ARGUMENT, "weights, x0 and u must be non-NULL");
+    if (flags & ~(DYNAX_SHARED_U | DYNAX_SOLVER_EULER))
+        return fail(DYNAX_ERR_INVALID_ARGUMENT, "unsupported flags 0x%x for node_rk4_forward", flags);
+    if (!(n == 3 && m == 5 && p == 1 && hidden == 64))
+        return fail(DYNAX_ERR_UNSUPPORTED_DIMS, "MLP kernel is instantiated for (n,m,p,hidden)=(3,5,1,64), got (%d,%d,%d,%d)", n, m, p, hidden);
+    int rc = require_sm100();
+    if (rc != DYNAX_OK) return rc;
+    if (T == 0) {
+        if (x_final) DYNAX_CUDA_TRY(cudaMemcpyAsync(x_final, x0, sizeof(float) * n * N, cudaMemcpyDeviceToDevice, st));
+        return DYNAX_OK;
+    }
+    using M = MlpModel<3, 5, 1, 64>;
+    FwdParams<M> P;
+    P.mp.W1 = W1; P.mp.b1 = b1; P.mp.W2 = W2; P.mp.b2 = b2; P.mp.W3 = W3; P.mp.b3 = b3;
+    P.mp.rk4 = (flags & DYNAX_SOLVER_EULER) ? 0 : 1;
+    P.x0 = x0; P.u = u; P.xsol = xsol; P.ysol = ysol; P.x_final = x_final;
+    P.N = N; P.T = T; P.dt = dt; P.discrete = 0;
+    const bool rows16 = (N % 4) == 0;
+    P.bulk_in = rows16 && aligned16(u);
+    P.bulk_out = rows16 && (!xsol || aligned16(xsol)) && (!ysol || aligned16(ysol));
+    // KF=1: the step body (64 inlined tanhf + the fused layer-2/3 loop) is large; one copy per CTA loop
+    if (flags & DYNAX_SHARED_U) return launch_fwd<M, 128, 1, 4, true, 1>(P, st);
+    return launch_fwd<M, 128, 1, 4, false, 1>(P, st);
+}

@@ -42,8 +42,9 @@ struct FwdCfg {
     static constexpr int XO_STAGE = KF * TN * n;
     static constexpr int YO_STAGE = KF * TN * p;
     static constexpr int NBAR = 2 * S + 4;
+    static constexpr int MODEL_FLOATS = align4i(Model::SMEM_FLOATS);  // block-shared model data (MLP weights)
     static constexpr size_t SMEM_BYTES =
-        sizeof(float) * (size_t)(S * IN_STAGE + 2 * XO_STAGE + 2 * YO_STAGE) + sizeof(uint64_t) * NBAR;
+        sizeof(float) * (size_t)(S * IN_STAGE + 2 * XO_STAGE + 2 * YO_STAGE + MODEL_FLOATS) + sizeof(uint64_t) * NBAR;
     static constexpr int THREADS = TN + 32;
 };
 
@@ -59,7 +60,8 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_fwd_kernel(const FwdPar
     float *s_in = reinterpret_cast<float *>(smem_raw);
     float *s_xo = s_in + S * IN_STAGE;
     float *s_yo = s_xo + 2 * XO_STAGE;
-    uint64_t *full = reinterpret_cast<uint64_t *>(s_yo + 2 * YO_STAGE);
+    float *s_model = s_yo + 2 * YO_STAGE;
+    uint64_t *full = reinterpret_cast<uint64_t *>(s_model + Cfg::MODEL_FLOATS);
     uint64_t *empty = full + S;
     uint64_t *ofull = empty + S;
     uint64_t *ofree = ofull + 2;
@@ -84,6 +86,7 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_fwd_kernel(const FwdPar
         ptx::mbar_init(&ofree[1], 1);
         ptx::fence_mbar_init();
     }
+    Model::block_init(s_model, P.mp, tid, TN + 32);  // no-op unless the model keeps shared data
     __syncthreads();
 
     if (tid >= TN) {
@@ -171,7 +174,7 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_fwd_kernel(const FwdPar
     const bool active = tid < valid;
     const int64_t i = active ? (n0 + tid) : (N - 1);  // idle lanes shadow the last system; never stored
     Model M;
-    M.load(P.mp, i);
+    M.load(P.mp, i, s_model);
     float x[n];
 #pragma unroll
     for (int d = 0; d < n; ++d) x[d] = __ldg(P.x0 + i * n + d);
@@ -191,7 +194,7 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_fwd_kernel(const FwdPar
 #pragma unroll
         for (int j = 0; j < KF; ++j) {
             if (j < rows) {
-                float u[m], r[n];
+                float u[m];
 #pragma unroll
                 for (int d = 0; d < m; ++d) u[d] = in[j * IN_ROW + d];
                 if (emit_y) {
@@ -200,9 +203,7 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_fwd_kernel(const FwdPar
 #pragma unroll
                     for (int d = 0; d < p; ++d) yo[j * TN * p + d] = y[d];
                 }
-                M.rhs(x, u, r);
-#pragma unroll
-                for (int d = 0; d < n; ++d) x[d] = discrete ? r[d] : fmaf(dt, r[d], x[d]);  // simulator.py:40
+                M.step(x, u, dt, discrete);  // explicit Euler x += dt*rhs (simulator.py:40) unless the model says otherwise
                 if (emit_x) {
 #pragma unroll
                     for (int d = 0; d < n; ++d) xo[j * TN * n + d] = x[d];  // x_{k+1} (simulator.py:43)

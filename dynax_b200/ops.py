@@ -328,3 +328,31 @@ def rc_mpc_cost(theta, x0, d, u, price, t_low, t_high, dt, cop=2.5, w_energy=100
                                           float(start_time), _ptr(cost), _ptr(amin), _ptr(cmin), N, H, float(dt),
                                           _ptr(ws), ws.numel(), _stream()))
     return cost, amin, cmin
+
+
+# ----------------------------------------------------------------------------------------------
+# general fx/fy: MLP dynamics + RK4 (config 5)
+# ----------------------------------------------------------------------------------------------
+def node_rk4_forward(W1, b1, W2, b2, W3, b3, x0, u, dt, emit_x=True, emit_y=True, emit_final=False, euler=False):
+    """Rollout of rhs = W3 tanh(W2 tanh(W1 [x;u] + b1) + b2) + b3, y = x[0] with RK4 (or Euler).
+
+    Weights are row-major [out,in] matrices shared by all systems; x0[N,3], u[T,N,5]|[T,5].
+    """
+    ws = [_f32c(t, nm) for t, nm in ((W1, "W1"), (b1, "b1"), (W2, "W2"), (b2, "b2"), (W3, "W3"), (b3, "b3"))]
+    x0, u = _f32c(x0, "x0"), _f32c(u, "u")
+    hidden = ws[1].numel()
+    n = ws[5].numel()
+    m = ws[0].shape[1] - n
+    if ws[0].shape != (hidden, n + m) or ws[2].shape != (hidden, hidden) or ws[3].numel() != hidden or ws[4].shape != (n, hidden):
+        raise ValueError("weight shapes must be W1[h,n+m] b1[h] W2[h,h] b2[h] W3[n,h] b3[n]")
+    x0, u, N, T, shared_u = _canon_batch(None, x0, u, n, m)
+    dev = x0.device
+    p = 1
+    xsol = torch.empty((T, N, n), dtype=torch.float32, device=dev) if emit_x else None
+    ysol = torch.empty((T, N, p), dtype=torch.float32, device=dev) if emit_y else None
+    xfin = torch.empty((N, n), dtype=torch.float32, device=dev) if emit_final else None
+    flags = (SHARED_U if shared_u else 0) | (_lib.SOLVER_EULER if euler else 0)
+    with torch.cuda.device(dev):
+        check(lib().dynax_node_rk4_forward_f32(*[_ptr(t) for t in ws], _ptr(x0), _ptr(u), _ptr(xsol), _ptr(ysol),
+                                               _ptr(xfin), N, T, n, m, p, hidden, float(dt), flags, _stream()))
+    return xsol, ysol, xfin

@@ -51,6 +51,8 @@ extern "C" {
                                    tests/test_forward_simulation.py:9-12,33-36) instead of the
                                    simulator's x += dt*rhs (simulator.py:40)                        */
 
+#define DYNAX_SOLVER_EULER 16u  /* node_rk4_forward: explicit Euler instead of classical RK4            */
+
 /* ops for dynax_workspace_bytes */
 #define DYNAX_OP_RC_FORWARD 0
 #define DYNAX_OP_RC_LOSS_GRAD 1
@@ -113,6 +115,20 @@ int dynax_lti_vjp_f32(const float *A, const float *B, const float *C, const floa
                       float *g_A, float *g_B, float *g_C, float *g_D, float *g_x0, float *g_u,
                       int64_t N, int64_t T, int n, int m, int p, float dt, uint32_t flags,
                       void *ws, size_t ws_bytes, void *stream);
+
+/* ---- General fx/fy block SSM (dynax/core/base_block_state_space.py:62-63,72-73) with MLP dynamics,
+ *      BASELINE.json config 5.  The reference has only the dispatch for this form (its example
+ *      examples/4-neural-ode.py does not run), so the model is the restated
+ *          rhs = W3 tanh(W2 tanh(W1 [x;u] + b1) + b2) + b3,   y = x[0:p]
+ *      stepped with classical RK4 (u held constant over a step) or Euler (DYNAX_SOLVER_EULER).
+ *      Weights are row-major [out,in] matrices shared by all systems: W1:[hidden,n+m] b1:[hidden]
+ *      W2:[hidden,hidden] b2:[hidden] W3:[n,hidden] b3:[n].  Instantiated for (n,m,p,hidden)=(3,5,1,64).
+ *      Output convention as dynax_rc_forward_f32.  PARITY UNPINNED BY THE REFERENCE. ---- */
+int dynax_node_rk4_forward_f32(const float *W1, const float *b1, const float *W2, const float *b2,
+                               const float *W3, const float *b3, const float *x0, const float *u,
+                               float *xsol, float *ysol, float *x_final,
+                               int64_t N, int64_t T, int n, int m, int p, int hidden, float dt,
+                               uint32_t flags, void *stream);
 
 /* ---- Sampling-based MPC (BASELINE.json config 4): cost of N candidate control sequences u[H,N] through
  *      ONE shared 4R3C model.  Inputs per step are assembled as the RC env does,

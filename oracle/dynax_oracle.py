@@ -368,3 +368,48 @@ def mpc_cost(theta, x0, d, u, dt, price=RC_PRICE, t_low=RC_T_LOW, t_high=RC_T_HI
         dTz = np.maximum(y - t_high[h], 0) + np.maximum(t_low[h] - y, 0)   # rc.py:247
         cost += dtype(w_energy) * c + dtype(w_comfort) * dTz     # -(reward) rc.py:250
     return cost
+
+
+# --------------------------------------------------------------------------------------
+# A7 / config 5: general fx/fy block SSM with MLP dynamics, classical RK4 (u held over the step).
+# The reference has only the dispatch (base_block_state_space.py:62-63,72-73); its example
+# (examples/4-neural-ode.py) does not run.  PARITY UNPINNED BY THE REFERENCE: this restatement is
+# the oracle.  Weights are row-major [out,in].
+# --------------------------------------------------------------------------------------
+def node_mlp_rhs(W, x, u, dtype):
+    W1, b1, W2, b2, W3, b3 = W
+    z = np.concatenate([x, u], axis=-1)
+    h1 = np.tanh(z @ W1.T + b1, dtype=dtype)
+    h2 = np.tanh(h1 @ W2.T + b2, dtype=dtype)
+    return (h2 @ W3.T + b3).astype(dtype)
+
+
+def node_rk4_rollout(W1, b1, W2, b2, W3, b3, x0, u, dt, dtype=np.float32, euler=False, p=1):
+    """x0[N,n], u[T,N|1,m] -> xsol[T,N,n] (x_{k+1}), ysol[T,N,p] (y_k = x_k[0:p], pre-update)."""
+    W = tuple(np.asarray(w, dtype=dtype) for w in (W1, b1, W2, b2, W3, b3))
+    x = np.array(x0, dtype=dtype, copy=True)
+    u = np.asarray(u, dtype=dtype)
+    T, N, n = u.shape[0], x.shape[0], x.shape[1]
+    dt = dtype(dt)
+    xsol = np.empty((T, N, n), dtype=dtype); ysol = np.empty((T, N, p), dtype=dtype)
+    for k in range(T):
+        uk = np.broadcast_to(u[k], (N, u.shape[-1]))
+        ysol[k] = x[:, :p]
+        k1 = node_mlp_rhs(W, x, uk, dtype)
+        if euler:
+            x = x + dt * k1
+        else:
+            k2 = node_mlp_rhs(W, x + dtype(0.5) * dt * k1, uk, dtype)
+            k3 = node_mlp_rhs(W, x + dtype(0.5) * dt * k2, uk, dtype)
+            k4 = node_mlp_rhs(W, x + dt * k3, uk, dtype)
+            x = x + (dt / dtype(6)) * (k1 + dtype(2) * k2 + dtype(2) * k3 + k4)
+        xsol[k] = x
+    return xsol, ysol
+
+
+def synth_mlp(seed, n=3, m=5, hidden=64, scale=0.1):
+    """LeCun-normal x scale weights as row-major [out,in] matrices."""
+    rng = np.random.default_rng(seed)
+    mk = lambda o, i: (scale * rng.normal(size=(o, i)) / np.sqrt(i)).astype(np.float32)
+    return (mk(hidden, n + m), (0.01 * rng.normal(size=hidden)).astype(np.float32), mk(hidden, hidden),
+            (0.01 * rng.normal(size=hidden)).astype(np.float32), mk(n, hidden), np.zeros(n, np.float32))

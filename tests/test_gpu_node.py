@@ -1,0 +1,57 @@
+"""GPU parity: MLP-dynamics RK4 rollout (config 5, row A7) vs the restated oracle.
+PARITY UNPINNED BY THE REFERENCE (it has no runnable neural ODE): the oracle is our restatement."""
+import numpy as np
+import pytest
+
+from oracle import dynax_oracle as orc
+from tests.util import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def T():
+    import torch
+    return torch
+
+
+def cu(T, a):
+    return T.as_tensor(np.ascontiguousarray(a, dtype=np.float32)).cuda()
+
+
+def inputs(N, Tn, seed):
+    rng = np.random.default_rng(seed)
+    x0 = rng.normal(size=(N, 3)).astype(np.float32)
+    u = rng.normal(size=(Tn, N, 5)).astype(np.float32)        # normalised channels (cf. examples/4-pinn.py:63-69)
+    return x0, u
+
+
+@pytest.mark.parametrize("N,Tn,euler", [(300, 64, False), (129, 33, True), (4, 7, False), (1024, 256, False)])
+def test_matches_oracle(T, N, Tn, euler):
+    from dynax_b200 import ops
+    W = orc.synth_mlp(101)
+    x0, u = inputs(N, Tn, 102)
+    xs, ys, xf = ops.node_rk4_forward(*(cu(T, w) for w in W), cu(T, x0), cu(T, u), 0.25, emit_final=True, euler=euler)
+    xr, yr = orc.node_rk4_rollout(*W, x0, u, 0.25, np.float64, euler=euler)
+    assert rel_err(xs.cpu().numpy(), xr, floor=1.0) < 1e-5
+    assert rel_err(ys.cpu().numpy(), yr, floor=1.0) < 1e-5
+    assert np.array_equal(xf.cpu().numpy(), xs[-1].cpu().numpy())
+
+
+def test_strong_nonlinearity_and_shared_u(T):
+    from dynax_b200 import ops
+    W = orc.synth_mlp(103, scale=1.0)                          # saturating tanh
+    x0, u = inputs(200, 40, 104)
+    xs, _, _ = ops.node_rk4_forward(*(cu(T, w) for w in W), cu(T, x0), cu(T, u[:, 0]), 0.1)
+    xr, _ = orc.node_rk4_rollout(*W, x0, u[:, :1], 0.1, np.float64)
+    assert rel_err(xs.cpu().numpy(), xr, floor=1.0) < 1e-5
+
+
+def test_unsupported_dims(T):
+    from dynax_b200 import ops
+    from dynax_b200._lib import DynaxError
+    W = orc.synth_mlp(105, hidden=32)
+    x0, u = inputs(8, 4, 106)
+    with pytest.raises(DynaxError) as e:
+        ops.node_rk4_forward(*(cu(T, w) for w in W), cu(T, x0), cu(T, u), 0.1)
+    assert e.value.code == -2
