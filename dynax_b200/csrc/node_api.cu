@@ -2,7 +2,10 @@
 // CUDA-core implementation (mlp_model.cuh) on the shared forward pipeline (TMA-staged u, smem
 // out-tiles).  See include/dynax_b200.h.
 #include "launch.cuh"
+#include <stdlib.h>
+
 #include "mlp_model.cuh"
+#include "node_tc.cuh"
 
 using namespace dynax;
 
@@ -23,6 +26,24 @@ extern "C" int dynax_node_rk4_forward_f32(const float *W1, const float *b1, cons
     if (rc != DYNAX_OK) return rc;
     if (T == 0) {
         if (x_final) DYNAX_CUDA_TRY(cudaMemcpyAsync(x_final, x0, sizeof(float) * n * N, cudaMemcpyDeviceToDevice, st));
+        return DYNAX_OK;
+    }
+    // Default: tensor-core kernel (tcgen05 + TMEM, node_tc.cuh).  DYNAX_NODE_IMPL=0 selects the CUDA-core
+    // policy kernel (mlp_model.cuh), which is also what a shared input series uses.
+    const char *impl = getenv("DYNAX_NODE_IMPL");
+    if (!(flags & DYNAX_SHARED_U) && !(impl && impl[0] == '0')) {
+        NodeTcParams Q;
+        Q.W1 = W1; Q.b1 = b1; Q.W2 = W2; Q.b2 = b2; Q.W3 = W3; Q.b3 = b3;
+        Q.x0 = x0; Q.u = u; Q.xsol = xsol; Q.ysol = ysol; Q.x_final = x_final;
+        Q.N = N; Q.T = T; Q.dt = dt; Q.rk4 = (flags & DYNAX_SOLVER_EULER) ? 0 : 1;
+        const bool r16 = (N % 4) == 0;
+        Q.bulk_in = r16 && aligned16(u);
+        Q.bulk_out = r16 && (!xsol || aligned16(xsol)) && (!ysol || aligned16(ysol));
+        rc = set_smem(node_tc_kernel, tc::SMEM_BYTES);
+        if (rc != DYNAX_OK) return rc;
+        const int64_t grid = (N + tc::TN - 1) / tc::TN;
+        node_tc_kernel<<<(unsigned)grid, tc::TN + 32, tc::SMEM_BYTES, st>>>(Q);
+        DYNAX_CUDA_TRY(cudaGetLastError());
         return DYNAX_OK;
     }
     using M = MlpModel<3, 5, 1, 64>;

@@ -26,9 +26,11 @@ def inputs(N, Tn, seed):
     return x0, u
 
 
+@pytest.mark.parametrize("impl", ["1", "0"])        # 1: tcgen05/TMEM kernel (default), 0: CUDA-core kernel
 @pytest.mark.parametrize("N,Tn,euler", [(300, 64, False), (129, 33, True), (4, 7, False), (1024, 256, False)])
-def test_matches_oracle(T, N, Tn, euler):
+def test_matches_oracle(T, monkeypatch, N, Tn, euler, impl):
     from dynax_b200 import ops
+    monkeypatch.setenv("DYNAX_NODE_IMPL", impl)
     W = orc.synth_mlp(101)
     x0, u = inputs(N, Tn, 102)
     xs, ys, xf = ops.node_rk4_forward(*(cu(T, w) for w in W), cu(T, x0), cu(T, u), 0.25, emit_final=True, euler=euler)
@@ -36,6 +38,21 @@ def test_matches_oracle(T, N, Tn, euler):
     assert rel_err(xs.cpu().numpy(), xr, floor=1.0) < 1e-5
     assert rel_err(ys.cpu().numpy(), yr, floor=1.0) < 1e-5
     assert np.array_equal(xf.cpu().numpy(), xs[-1].cpu().numpy())
+
+
+def test_tensor_core_kernel_saturating_tanh_and_chaining(T):
+    """tcgen05 kernel with O(1) weights (saturating tanh), ragged N, and T steps == T1 + (T-T1) steps."""
+    from dynax_b200 import ops
+    W = [cu(T, w) for w in orc.synth_mlp(107, scale=1.0)]
+    x0, u = inputs(1000, 48, 108)
+    xs, ys, xf = ops.node_rk4_forward(*W, cu(T, x0), cu(T, u), 0.1, emit_final=True)
+    xr, yr = orc.node_rk4_rollout(*[w.cpu().numpy() for w in W], x0, u, 0.1, np.float64)
+    assert rel_err(xs.cpu().numpy(), xr, floor=1.0) < 1e-5 and rel_err(ys.cpu().numpy(), yr, floor=1.0) < 1e-5
+    xa, _, xfa = ops.node_rk4_forward(*W, cu(T, x0), cu(T, u[:20]), 0.1, emit_final=True)
+    xb, _, xfb = ops.node_rk4_forward(*W, xfa, cu(T, u[20:]), 0.1, emit_final=True)
+    assert T.equal(T.cat([xa, xb]), xs) and T.equal(xfb, xf)
+    x3, _, _ = ops.node_rk4_forward(*W, cu(T, x0[:999]), cu(T, u[:, :999]), 0.1)       # N % 4 != 0: no-TMA producer
+    assert T.equal(x3, xs[:, :999])
 
 
 def test_strong_nonlinearity_and_shared_u(T):
