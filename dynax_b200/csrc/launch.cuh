@@ -23,7 +23,9 @@ int launch_fwd(const FwdParams<Model> &P, cudaStream_t st) {
     if (rc != DYNAX_OK) return rc;
     const int64_t grid = (P.N + TN - 1) / TN;
     if (grid > 0x7fffffffLL) return fail(DYNAX_ERR_INVALID_ARGUMENT, "N too large for one launch");
-    kern<<<(unsigned)grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(P);
+    const int64_t chunks = P.chunk_len > 0 ? (P.T + P.chunk_len - 1) / P.chunk_len : 1;
+    if (chunks > 65535) return fail(DYNAX_ERR_INVALID_ARGUMENT, "too many time chunks");
+    kern<<<dim3((unsigned)grid, (unsigned)chunks), Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(P);
     DYNAX_CUDA_TRY(cudaGetLastError());
     return DYNAX_OK;
 }

@@ -30,6 +30,12 @@ struct FwdParams {
     float dt;
     int discrete;
     int bulk_in, bulk_out;
+    // Time-chunked launches (gridDim.y = number of chunks; lti_chunked.cu): chunk c rolls steps
+    // [c*chunk_len, min(T,(c+1)*chunk_len)) from x0 + c*x0_chunk_stride (or from zero) and writes its
+    // final state to x_final + c*N*n.  chunk_len == 0: one chunk, the whole horizon.
+    int64_t chunk_len = 0;
+    int64_t x0_chunk_stride = 0;
+    int x0_zero = 0;
 };
 
 __host__ __device__ constexpr int align4i(int x) { return (x + 3) & ~3; }
@@ -67,9 +73,15 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_fwd_kernel(const FwdPar
     uint64_t *ofree = ofull + 2;
 
     const int tid = threadIdx.x;
-    const int64_t N = P.N, T = P.T;
+    const int64_t N = P.N;
     const int64_t n0 = (int64_t)blockIdx.x * TN;
     const int valid = (int)((N - n0) < TN ? (N - n0) : TN);
+    // this CTA's slice of the time axis (the whole horizon unless the launch is time-chunked)
+    const int64_t t_begin = P.chunk_len > 0 ? (int64_t)blockIdx.y * P.chunk_len : 0;
+    const int64_t T = P.chunk_len > 0 ? ((P.T - t_begin) < P.chunk_len ? (P.T - t_begin) : P.chunk_len) : P.T;
+    const float *const u_base = P.u + t_begin * (SHARED_U ? m : N * m);
+    float *const xsol_base = P.xsol ? P.xsol + t_begin * N * n : nullptr;
+    float *const ysol_base = P.ysol ? P.ysol + t_begin * N * p : nullptr;
     const bool emit_x = P.xsol != nullptr, emit_y = P.ysol != nullptr;
     const bool emit = emit_x || emit_y;
     const int64_t C = (T + KF - 1) / KF;
@@ -100,7 +112,7 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_fwd_kernel(const FwdPar
             const int rows = (int)((T - k0) < KF ? (T - k0) : KF);
             float *dst = s_in + s * IN_STAGE;
             if (SHARED_U) {
-                const float *src = P.u + k0 * m;  // [T,1,m] is contiguous in k
+                const float *src = u_base + k0 * m;  // [T,1,m] is contiguous in k
                 for (int i = lane; i < rows * m; i += 32) dst[i] = __ldg(src + i);
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(&full[s]);
@@ -109,11 +121,11 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_fwd_kernel(const FwdPar
                     const uint32_t row_bytes = (uint32_t)valid * m * 4u;
                     ptx::mbar_arrive_expect_tx(&full[s], row_bytes * (uint32_t)rows);
                     for (int r = 0; r < rows; ++r)
-                        ptx::bulk_g2s(dst + r * IN_ROW, P.u + ((k0 + r) * N + n0) * m, row_bytes, &full[s], pol);
+                        ptx::bulk_g2s(dst + r * IN_ROW, u_base + ((k0 + r) * N + n0) * m, row_bytes, &full[s], pol);
                 }
             } else {
                 for (int r = 0; r < rows; ++r) {
-                    const float *src = P.u + ((k0 + r) * N + n0) * m;
+                    const float *src = u_base + ((k0 + r) * N + n0) * m;
                     for (int i = lane; i < valid * m; i += 32) dst[r * IN_ROW + i] = __ldg(src + i);
                 }
                 __syncwarp();
@@ -131,9 +143,9 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_fwd_kernel(const FwdPar
                 if (lane == 0) {
                     for (int r = 0; r < rows; ++r) {
                         if (emit_x)
-                            ptx::bulk_s2g(P.xsol + ((k0 + r) * N + n0) * n, sx + r * TN * n, (uint32_t)valid * n * 4u);
+                            ptx::bulk_s2g(xsol_base + ((k0 + r) * N + n0) * n, sx + r * TN * n, (uint32_t)valid * n * 4u);
                         if (emit_y)
-                            ptx::bulk_s2g(P.ysol + ((k0 + r) * N + n0) * p, sy + r * TN * p, (uint32_t)valid * p * 4u);
+                            ptx::bulk_s2g(ysol_base + ((k0 + r) * N + n0) * p, sy + r * TN * p, (uint32_t)valid * p * 4u);
                     }
                     ptx::bulk_commit();
                     ptx::bulk_wait_read<0>();  // out-tile may be overwritten once TMA has read it
@@ -142,11 +154,11 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_fwd_kernel(const FwdPar
             } else {
                 for (int r = 0; r < rows; ++r) {
                     if (emit_x) {
-                        float *dst = P.xsol + ((k0 + r) * N + n0) * n;
+                        float *dst = xsol_base + ((k0 + r) * N + n0) * n;
                         for (int i = lane; i < valid * n; i += 32) dst[i] = sx[r * TN * n + i];
                     }
                     if (emit_y) {
-                        float *dst = P.ysol + ((k0 + r) * N + n0) * p;
+                        float *dst = ysol_base + ((k0 + r) * N + n0) * p;
                         for (int i = lane; i < valid * p; i += 32) dst[i] = sy[r * TN * p + i];
                     }
                 }
@@ -177,7 +189,7 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_fwd_kernel(const FwdPar
     M.load(P.mp, i, s_model);
     float x[n];
 #pragma unroll
-    for (int d = 0; d < n; ++d) x[d] = __ldg(P.x0 + i * n + d);
+    for (int d = 0; d < n; ++d) x[d] = P.x0_zero ? 0.f : __ldg(P.x0 + (int64_t)blockIdx.y * P.x0_chunk_stride + i * n + d);
     const float dt = P.dt;
     const bool discrete = P.discrete != 0;
 
@@ -219,7 +231,7 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_fwd_kernel(const FwdPar
     }
     if (P.x_final != nullptr && active) {
 #pragma unroll
-        for (int d = 0; d < n; ++d) P.x_final[i * n + d] = x[d];
+        for (int d = 0; d < n; ++d) P.x_final[(P.chunk_len > 0 ? (int64_t)blockIdx.y * N * n : 0) + i * n + d] = x[d];
     }
 }
 

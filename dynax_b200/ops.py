@@ -75,11 +75,15 @@ def _rc_theta(theta, N):
     raise ValueError(f"theta has {theta.shape[0]} systems but x0 has {N}")
 
 
-def rc_forward(theta, x0, u, dt, emit_x=True, emit_y=True, emit_final=False, discrete=False):
+def rc_forward(theta, x0, u, dt, emit_x=True, emit_y=True, emit_final=False, discrete=False, time_chunks=None):
     """Batched ``DifferentiableSimulator(Continuous4R3C, dt).apply`` (simulator.py:22-55, RC.py:137-249).
 
     theta[N,7]|[7], x0[N,3], u[T,N,5]|[T,1,5]|[T,5]  ->  xsol[T,N,3], ysol[T,N,1], x_final[N,3]
     (entries not requested are None).
+
+    ``time_chunks``: None = serial-in-time kernel unless the launch is small and long (N <= 8192 and
+    T >= 2048), where the time-parallel chunked kernel is used with an automatic chunk length;
+    0 = always serial; k > 0 = k chunks.
     """
     x0, u = _f32c(x0, "x0"), _f32c(u, "u")
     x0, u, N, T, shared_u = _canon_batch(None, x0, u, 3, 5)
@@ -89,9 +93,17 @@ def rc_forward(theta, x0, u, dt, emit_x=True, emit_y=True, emit_final=False, dis
     ysol = torch.empty((T, N, 1), dtype=torch.float32, device=dev) if emit_y else None
     xfin = torch.empty((N, 3), dtype=torch.float32, device=dev) if emit_final else None
     flags = (SHARED_THETA if shared_th else 0) | (SHARED_U if shared_u else 0) | (DISCRETE if discrete else 0)
+    if time_chunks is None:
+        time_chunks = -1 if (not discrete and 0 < N <= 8192 and T >= 2048) else 0
     with torch.cuda.device(dev):
-        check(lib().dynax_rc_forward_f32(_ptr(theta), _ptr(x0), _ptr(u), _ptr(xsol), _ptr(ysol), _ptr(xfin),
-                                         N, T, float(dt), flags, _stream()))
+        if time_chunks != 0 and not discrete and N > 0 and T > 0:
+            chunk_len = 0 if time_chunks < 0 else -(-T // int(time_chunks))
+            ws = _ws(lib().dynax_rc_forward_chunked_workspace(N, T, chunk_len), dev)
+            check(lib().dynax_rc_forward_chunked_f32(_ptr(theta), _ptr(x0), _ptr(u), _ptr(xsol), _ptr(ysol), _ptr(xfin),
+                                                     N, T, float(dt), flags, chunk_len, _ptr(ws), ws.numel(), _stream()))
+        else:
+            check(lib().dynax_rc_forward_f32(_ptr(theta), _ptr(x0), _ptr(u), _ptr(xsol), _ptr(ysol), _ptr(xfin),
+                                             N, T, float(dt), flags, _stream()))
     return xsol, ysol, xfin
 
 

@@ -78,6 +78,18 @@ int dynax_rc_forward_f32(const float *theta, const float *x0, const float *u,
                          float *xsol, float *ysol, float *x_final,
                          int64_t N, int64_t T, float dt, uint32_t flags, void *stream);
 
+/* Time-parallel variant of dynax_rc_forward_f32 for launches with too few systems to fill the GPU
+ * (long-horizon LTI, north_star "chunked associative-scan variant"): the horizon is cut into chunks
+ * of `chunk_len` steps (0 = choose automatically) that are rolled in parallel from zero state, stitched
+ * with Psi = (I+dt A)^L - I, and rolled again from their true boundary states.
+ * Same outputs as dynax_rc_forward_f32 within the trajectory tolerance (not bit-identical).  Euler
+ * residual form only (no DYNAX_DISCRETE).  ws: dynax_rc_forward_chunked_workspace(N,T,chunk_len) bytes. */
+size_t dynax_rc_forward_chunked_workspace(int64_t N, int64_t T, int64_t chunk_len);
+int dynax_rc_forward_chunked_f32(const float *theta, const float *x0, const float *u,
+                                 float *xsol, float *ysol, float *x_final,
+                                 int64_t N, int64_t T, float dt, uint32_t flags, int64_t chunk_len,
+                                 void *ws, size_t ws_bytes, void *stream);
+
 /* Fused loss + reverse-mode gradient of examples/3-inverse.py:96-112 for N candidates:
  *   loss_i = mean_k (ysol_i[k]-target_i[k])^2 + sum_j relu(theta_ij-ub_j)/ub_j + relu(lb_j-theta_ij)/ub_j
  *   g_theta = d loss / d theta   (checkpointed discrete adjoint; == jax.value_and_grad through the scan)
