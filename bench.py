@@ -263,8 +263,27 @@ def ours(a):
                "d2h_bytes_per_step": int(l_h.size + g_h.size) * 4,
                "systems_per_step": Ne, "ms_per_step": e_sec / a.e2e_steps * 1e3,
                "api": "dynax_rc_loss_grad_host_f32 (pinned host buffers; tiled H2D/kernel/D2H on 2 streams)"}
+        # informational: the same loss+gradient when the disturbances are ONE shared series and only the
+        # control channel is per system: 8 instead of 24 B/step over PCIe
+        hc = torch.empty((T, Ne), dtype=torch.float32, pin_memory=True)
+        hc.copy_(hu[:, :, 2])
+        hd = hu[:, 0, :].contiguous()
+        cargs = (hth.numpy(), hx0.numpy(), hd.numpy(), hc.numpy(), ht.numpy(), DT)
+        host.rc_loss_grad_ctrl(*cargs)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(a.e2e_steps):
+            host.rc_loss_grad_ctrl(*cargs)
+        c_sec = time.perf_counter() - t0
+        tc_ = torch.tensor([c_sec], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tc_, op=dist.ReduceOp.MAX)
+        e2e["shared_disturbance_variant"] = {
+            "value": world * Ne * T * a.e2e_steps / float(tc_.item()), "unit": "system-steps/s",
+            "h2d_bytes_per_step": int(hc.numel() + ht.numel() + hd.numel() + hth.numel() + hx0.numel()) * 4,
+            "api": "dynax_rc_loss_grad_ctrl_host_f32 (shared u[T,5] + per-system ctrl[T,N]; not the headline workload)"}
         host.release()
-        del hu, ht
+        del hu, ht, hc
 
     if rank != 0:
         if world > 1:

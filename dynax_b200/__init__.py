@@ -15,7 +15,7 @@ from . import _lib
 
 _lib.lib()  # fail loudly at import time if the CUDA library has not been built
 
-from . import core, estimators, models, ops, simulators  # noqa: E402
+from . import agents, core, estimators, models, ops, simulators, utils  # noqa: E402
 from .simulators import DifferentiableSimulator  # noqa: E402
 
-__all__ = ["core", "models", "simulators", "estimators", "ops", "DifferentiableSimulator"]
+__all__ = ["agents", "core", "models", "simulators", "estimators", "ops", "utils", "DifferentiableSimulator"]

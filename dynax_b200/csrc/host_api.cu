@@ -149,9 +149,10 @@ int dynax_rc_forward_host_f32(const float *theta, const float *x0, const float *
     return DYNAX_OK;
 }
 
-int dynax_rc_loss_grad_host_f32(const float *theta, const float *x0, const float *u, const float *target,
-                                const float *lb, const float *ub, float *loss, float *g_theta, int64_t N,
-                                int64_t T, float dt, uint32_t flags, int64_t tile_systems) {
+static int loss_grad_host_impl(const float *theta, const float *x0, const float *u, const float *ctrl, int ctrl_col,
+                               const float *target, const float *lb, const float *ub, float *loss, float *g_theta,
+                               int64_t N, int64_t T, float dt, uint32_t flags, int64_t tile_systems) {
+    if (ctrl) flags |= DYNAX_SHARED_U;  // u is the shared [T,5] series, ctrl the per-system channel [T,N]
     if (N < 0 || T < 1) return fail(DYNAX_ERR_INVALID_ARGUMENT, "need N >= 0 and T >= 1");
     if (N == 0) return DYNAX_OK;
     if (!theta || !x0 || !u || !target || !loss || !g_theta)
@@ -162,7 +163,7 @@ int dynax_rc_loss_grad_host_f32(const float *theta, const float *x0, const float
     std::lock_guard<std::mutex> lk(c.mu);
     TRY(ensure_ctx(c));
     const bool sth = flags & DYNAX_SHARED_THETA, su = flags & DYNAX_SHARED_U, stg = flags & DYNAX_SHARED_TARGET;
-    const int64_t nt = pick_tile(N, T, tile_systems, 24);
+    const int64_t nt = pick_tile(N, T, tile_systems, ctrl ? 8 : 24);
     const int64_t ntiles = (N + nt - 1) / nt;
     // shared-theta partial sums per tile land here and are reduced on the host in fp64
     float(*part)[8] = sth ? new float[ntiles][8] : nullptr;
@@ -174,7 +175,7 @@ int dynax_rc_loss_grad_host_f32(const float *theta, const float *x0, const float
         cudaStream_t st = c.streams[b];
         auto body = [&]() -> int {
             DYNAX_CUDA_TRY(cudaEventSynchronize(c.done[b]));
-            float *d_th, *d_x0, *d_u, *d_tg, *d_out, *d_bounds = nullptr;
+            float *d_th, *d_x0, *d_u, *d_tg, *d_out, *d_bounds = nullptr, *d_ctrl = nullptr;
             void *d_ws;
             const size_t ws_bytes = dynax_workspace_bytes(DYNAX_OP_RC_LOSS_GRAD, cur, T, 3, 5, 1, flags);
             TRY(reserve(c.slots[b][0], sizeof(float) * 7 * (sth ? 1 : cur), (void **)&d_th));
@@ -196,8 +197,16 @@ int dynax_rc_loss_grad_host_f32(const float *theta, const float *x0, const float
             if (stg) DYNAX_CUDA_TRY(cudaMemcpyAsync(d_tg, target, sizeof(float) * T, cudaMemcpyHostToDevice, st));
             else TRY(copy_tile(d_tg, (size_t)cur, target + n0, (size_t)N, cur, 1, T, cudaMemcpyHostToDevice, st));
             float *d_loss = d_out, *d_g = d_out + cur;
-            TRY(dynax_rc_loss_grad_f32(d_th, d_x0, d_u, d_tg, d_bounds, d_bounds ? d_bounds + 8 : nullptr, d_loss, d_g,
-                                       nullptr, cur, T, dt, flags, d_ws, ws_bytes, st));
+            if (ctrl) {
+                TRY(reserve(c.slots[b][7], sizeof(float) * (size_t)T * cur + 16, (void **)&d_ctrl));
+                TRY(copy_tile(d_ctrl, (size_t)cur, ctrl + n0, (size_t)N, cur, 1, T, cudaMemcpyHostToDevice, st));
+                TRY(dynax_rc_loss_grad_ctrl_f32(d_th, d_x0, d_u, d_ctrl, ctrl_col, d_tg, d_bounds,
+                                                d_bounds ? d_bounds + 8 : nullptr, d_loss, d_g, nullptr, cur, T, dt,
+                                                flags, d_ws, ws_bytes, st));
+            } else {
+                TRY(dynax_rc_loss_grad_f32(d_th, d_x0, d_u, d_tg, d_bounds, d_bounds ? d_bounds + 8 : nullptr, d_loss,
+                                           d_g, nullptr, cur, T, dt, flags, d_ws, ws_bytes, st));
+            }
             if (sth) {
                 DYNAX_CUDA_TRY(cudaMemcpyAsync(&part[tile][0], d_loss, sizeof(float), cudaMemcpyDeviceToHost, st));
                 DYNAX_CUDA_TRY(cudaMemcpyAsync(&part[tile][1], d_g, sizeof(float) * 7, cudaMemcpyDeviceToHost, st));
@@ -231,6 +240,21 @@ int dynax_rc_loss_grad_host_f32(const float *theta, const float *x0, const float
     }
     delete[] part;
     return rc;
+}
+
+int dynax_rc_loss_grad_host_f32(const float *theta, const float *x0, const float *u, const float *target,
+                                const float *lb, const float *ub, float *loss, float *g_theta, int64_t N,
+                                int64_t T, float dt, uint32_t flags, int64_t tile_systems) {
+    return loss_grad_host_impl(theta, x0, u, nullptr, 0, target, lb, ub, loss, g_theta, N, T, dt, flags, tile_systems);
+}
+
+int dynax_rc_loss_grad_ctrl_host_f32(const float *theta, const float *x0, const float *u_shared, const float *ctrl,
+                                     int ctrl_col, const float *target, const float *lb, const float *ub, float *loss,
+                                     float *g_theta, int64_t N, int64_t T, float dt, uint32_t flags,
+                                     int64_t tile_systems) {
+    if (!ctrl && N > 0) return fail(DYNAX_ERR_INVALID_ARGUMENT, "ctrl must be non-NULL");
+    return loss_grad_host_impl(theta, x0, u_shared, ctrl, ctrl_col, target, lb, ub, loss, g_theta, N, T, dt, flags,
+                               tile_systems);
 }
 
 }  // extern "C"

@@ -40,7 +40,8 @@ static int env_int(const char *name, int dflt) {
 
 // ------------------------------------------------------------------------------------------
 static int rc_forward(const float *theta, const float *x0, const float *u, float *xsol, float *ysol,
-                      float *x_final, int64_t N, int64_t T, float dt, uint32_t flags, cudaStream_t st) {
+                      float *x_final, int64_t N, int64_t T, float dt, uint32_t flags, cudaStream_t st,
+                      const float *ctrl = nullptr, int ctrl_col = 0) {
     if (N < 0 || T < 0) return fail(DYNAX_ERR_INVALID_ARGUMENT, "negative N or T");
     if (N == 0) return DYNAX_OK;
     if (!theta || !x0 || (!u && T > 0)) return fail(DYNAX_ERR_INVALID_ARGUMENT, "theta, x0 and u must be non-NULL");
@@ -60,9 +61,15 @@ static int rc_forward(const float *theta, const float *x0, const float *u, float
     P.N = N; P.T = T; P.dt = dt;
     P.discrete = (flags & DYNAX_DISCRETE) ? 1 : 0;
     const bool rows16 = (N % 4) == 0;  // every [*,N,w] row starts and ends on a 16-byte boundary
-    P.bulk_in = rows16 && aligned16(u);
+    P.bulk_in = rows16 && aligned16(u) && (!ctrl || aligned16(ctrl));
     P.bulk_out = rows16 && (!xsol || aligned16(xsol)) && (!ysol || aligned16(ysol));
     if (env_int("DYNAX_NO_BULK", 0)) P.bulk_in = P.bulk_out = 0;
+    if (ctrl) {
+        if (!(flags & DYNAX_SHARED_U)) return fail(DYNAX_ERR_INVALID_ARGUMENT, "a control channel needs a shared input series");
+        if (ctrl_col < 0 || ctrl_col >= 5) return fail(DYNAX_ERR_INVALID_ARGUMENT, "ctrl_col must be in [0,5)");
+        P.ctrl = ctrl;
+        P.ctrl_col = ctrl_col;
+    }
     if (flags & DYNAX_SHARED_U) return launch_fwd<RCModel, 128, 4, 4, true, 4>(P, st);
     // Tile shapes measured on B200 (tools/tune.py, N=132608, T=8760): wide rows win because each
     // cp.async.bulk then moves 5 KB.  0: 6.45 TB/s (x+y), 1: 5.43, 2: 5.31, 3: 5.80.
@@ -79,7 +86,7 @@ template <int MODE>
 static int rc_adjoint(const float *theta, const float *x0, const float *u, const float *target, const float *lb,
                       const float *ub, const float *g_xsol, const float *g_ysol, float *loss, float *g_theta,
                       float *g_x0, float *g_u, int64_t N, int64_t T, float dt, uint32_t flags, void *ws,
-                      size_t ws_bytes, cudaStream_t st) {
+                      size_t ws_bytes, cudaStream_t st, const float *ctrl = nullptr, int ctrl_col = 0) {
     if (N < 0 || T < 1) return fail(DYNAX_ERR_INVALID_ARGUMENT, "need N >= 0 and T >= 1");
     if (N == 0) return DYNAX_OK;
     if (!theta || !x0 || !u) return fail(DYNAX_ERR_INVALID_ARGUMENT, "theta, x0 and u must be non-NULL");
@@ -112,15 +119,22 @@ static int rc_adjoint(const float *theta, const float *x0, const float *u, const
     P.discrete = (flags & DYNAX_DISCRETE) ? 1 : 0;
     P.shared_theta = (flags & DYNAX_SHARED_THETA) ? 1 : 0;
     P.bulk = (N % 4) == 0 && aligned16(u) && (!target || aligned16(target)) && (!g_xsol || aligned16(g_xsol)) &&
-             (!g_ysol || aligned16(g_ysol));
+             (!g_ysol || aligned16(g_ysol)) && (!ctrl || aligned16(ctrl));
+    if (ctrl) {
+        if (!(flags & DYNAX_SHARED_U)) return fail(DYNAX_ERR_INVALID_ARGUMENT, "a control channel needs a shared input series");
+        if (ctrl_col < 0 || ctrl_col >= 5) return fail(DYNAX_ERR_INVALID_ARGUMENT, "ctrl_col must be in [0,5)");
+        P.ctrl = ctrl;
+        P.ctrl_col = ctrl_col;
+    }
     if (env_int("DYNAX_NO_BULK", 0)) P.bulk = 0;
     const bool su = flags & DYNAX_SHARED_U, stg = flags & DYNAX_SHARED_TARGET;
     if constexpr (MODE == ADJ_VJP) {
         if (su) return launch_adj<RCModel, 128, 8, 2, ADJ_VJP, true, false, 2>(P, st);
         return launch_adj<RCModel, 128, 8, 2, ADJ_VJP, false, false, 2>(P, st);
     } else {
-        if (su && stg) return launch_adj<RCModel, 128, 16, 2, ADJ_MSE, true, true, 2>(P, st);
-        if (su) return launch_adj<RCModel, 128, 16, 2, ADJ_MSE, true, false, 2>(P, st);
+        // shared-u stages are small (<= 17 KB): a 4-deep ring keeps the producer ahead of the consumers
+        if (su && stg) return launch_adj<RCModel, 128, 16, 4, ADJ_MSE, true, true, 2>(P, st);
+        if (su) return launch_adj<RCModel, 128, 16, 4, ADJ_MSE, true, false, 2>(P, st);
         if (stg) return launch_adj<RCModel, 128, 16, 2, ADJ_MSE, false, true, 2>(P, st);
         switch (env_int("DYNAX_ADJ_CFG", 0)) {
             default:
@@ -165,6 +179,23 @@ int dynax_rc_loss_grad_f32(const float *theta, const float *x0, const float *u, 
                            int64_t T, float dt, uint32_t flags, void *ws, size_t ws_bytes, void *stream) {
     return rc_adjoint<ADJ_MSE>(theta, x0, u, target, lb, ub, nullptr, nullptr, loss, g_theta, g_x0, nullptr, N, T, dt,
                                flags, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int dynax_rc_forward_ctrl_f32(const float *theta, const float *x0, const float *u_shared, const float *ctrl,
+                              int ctrl_col, float *xsol, float *ysol, float *x_final, int64_t N, int64_t T, float dt,
+                              uint32_t flags, void *stream) {
+    if (!ctrl && N > 0 && T > 0) return fail(DYNAX_ERR_INVALID_ARGUMENT, "ctrl must be non-NULL");
+    return rc_forward(theta, x0, u_shared, xsol, ysol, x_final, N, T, dt, flags | DYNAX_SHARED_U,
+                      static_cast<cudaStream_t>(stream), ctrl, ctrl_col);
+}
+
+int dynax_rc_loss_grad_ctrl_f32(const float *theta, const float *x0, const float *u_shared, const float *ctrl,
+                                int ctrl_col, const float *target, const float *lb, const float *ub, float *loss,
+                                float *g_theta, float *g_x0, int64_t N, int64_t T, float dt, uint32_t flags, void *ws,
+                                size_t ws_bytes, void *stream) {
+    if (!ctrl && N > 0) return fail(DYNAX_ERR_INVALID_ARGUMENT, "ctrl must be non-NULL");
+    return rc_adjoint<ADJ_MSE>(theta, x0, u_shared, target, lb, ub, nullptr, nullptr, loss, g_theta, g_x0, nullptr, N, T,
+                               dt, flags | DYNAX_SHARED_U, ws, ws_bytes, static_cast<cudaStream_t>(stream), ctrl, ctrl_col);
 }
 
 int dynax_rc_vjp_f32(const float *theta, const float *x0, const float *u, const float *g_xsol, const float *g_ysol,

@@ -44,6 +44,8 @@ struct AdjParams {
     int64_t N, T;
     float dt;
     int discrete, bulk, shared_theta;
+    const float *ctrl;    // SHARED_U only: per-system channel [T,N] replacing column ctrl_col of the shared u, or NULL
+    int ctrl_col;
 };
 
 template <class Model, int TN, int KC, int S, int MODE, bool SHARED_U, bool SHARED_TGT>
@@ -55,7 +57,8 @@ struct AdjCfg {
     static constexpr int U_OFF = 0;
     static constexpr int A1_OFF = align4i(KC * U_ROW);
     static constexpr int A2_OFF = A1_OFF + align4i(KC * A1_ROW);
-    static constexpr int STAGE = A2_OFF + align4i(KC * A2_ROW);
+    static constexpr int A3_OFF = A2_OFF + align4i(KC * A2_ROW);                       // per-system channel (ctrl)
+    static constexpr int STAGE = A3_OFF + (SHARED_U ? KC * TN : 0);
     static constexpr int NBAR = 2 * S;
     static constexpr size_t SMEM_BYTES = sizeof(float) * (size_t)(S * STAGE) + sizeof(uint64_t) * NBAR;
     static constexpr int THREADS = TN + 32;
@@ -109,10 +112,9 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_adj_kernel(const AdjPar
                           int rows, uint64_t *bar) -> uint32_t {
             if (g == nullptr) return 0;
             if (shared) {
-                if (pass == 0) {
+                if (pass == 0) {  // [T,1,w] is contiguous in k and the smem rows are packed (row_stride == w)
                     const float *src = g + k0 * w;
-                    for (int r = 0; r < rows; ++r)
-                        for (int i = lane; i < w; i += 32) dst[r * row_stride + i] = __ldg(src + r * w + i);
+                    for (int i = lane; i < rows * w; i += 32) dst[i] = __ldg(src + i);
                 }
                 return 0;
             }
@@ -142,6 +144,7 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_adj_kernel(const AdjPar
 #pragma unroll
             for (int pass = 0; pass < 2; ++pass) {
                 uint32_t b = stream(pass, st + Cfg::U_OFF, U_ROW, P.u, m, SHARED_U, k0, rows, &full[s]);
+                if (SHARED_U) b += stream(pass, st + Cfg::A3_OFF, TN, P.ctrl, 1, false, k0, rows, &full[s]);
                 if (!fwd) {
                     if (MODE == ADJ_MSE) {
                         b += stream(pass, st + Cfg::A1_OFF, A1_ROW, P.target, 1, SHARED_TGT, k0, rows, &full[s]);
@@ -181,6 +184,14 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_adj_kernel(const AdjPar
     const float dt = P.dt;
     const bool discrete = P.discrete != 0;
     float *ck = P.ckpt + (n0 + tid);  // ckpt[(seg*n + d)*N + system]; only touched when active
+    // shared input series + one per-system channel (rc.py:128-131): replace column ctrl_col
+    auto override_ctrl = [&](float *u, const float *stage, int j) {
+        if (SHARED_U && P.ctrl != nullptr) {
+            const float cv = stage[Cfg::A3_OFF + j * TN + tid];
+#pragma unroll
+            for (int d = 0; d < m; ++d) u[d] = (d == P.ctrl_col) ? cv : u[d];
+        }
+    };
 
     int64_t q = 0;
     // ---- phase 1: forward sweep over segments 0..C-2, checkpointing the state at each start
@@ -197,6 +208,7 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_adj_kernel(const AdjPar
             float u[m], r[n];
 #pragma unroll
             for (int d = 0; d < m; ++d) u[d] = in[j * U_ROW + d];
+            override_ctrl(u, s_in + s * Cfg::STAGE, j);
             M.rhs(xc, u, r);
 #pragma unroll
             for (int d = 0; d < n; ++d) xc[d] = discrete ? r[d] : fmaf(dt, r[d], xc[d]);
@@ -242,6 +254,7 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_adj_kernel(const AdjPar
                 float u[m], r[n];
 #pragma unroll
                 for (int d = 0; d < m; ++d) u[d] = in[j * U_ROW + d];
+                override_ctrl(u, st, j);
                 M.rhs(xs[j], u, r);
 #pragma unroll
                 for (int d = 0; d < n; ++d) xs[j + 1][d] = discrete ? r[d] : fmaf(dt, r[d], xs[j][d]);
@@ -254,6 +267,7 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_adj_kernel(const AdjPar
                 float u[m], gy[p], sv[n], ax[n];
 #pragma unroll
                 for (int d = 0; d < m; ++d) u[d] = in[j * U_ROW + d];
+                override_ctrl(u, st, j);
                 if (MODE == ADJ_MSE) {
                     float y[p];
                     M.out(xs[j], u, y);

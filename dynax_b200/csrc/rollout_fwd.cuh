@@ -36,6 +36,12 @@ struct FwdParams {
     int64_t chunk_len = 0;
     int64_t x0_chunk_stride = 0;
     int x0_zero = 0;
+    // Shared input series + ONE per-system channel (SHARED_U kernels only): u_k = u_shared[k] with column
+    // ctrl_col replaced by ctrl[k, system].  This is how the RC env assembles its inputs
+    // (dynax/wrapper/envs/rc.py:128-131: shared disturbance table + per-env control) and what
+    // sampling-based control needs; it cuts the streamed input from 4m to 4 bytes per system-step.
+    const float *ctrl = nullptr;  // [T,N] or NULL
+    int ctrl_col = 0;
 };
 
 __host__ __device__ constexpr int align4i(int x) { return (x + 3) & ~3; }
@@ -44,7 +50,8 @@ template <class Model, int TN, int KF, int S, bool SHARED_U>
 struct FwdCfg {
     static constexpr int n = Model::n, m = Model::m, p = Model::p;
     static constexpr int IN_ROW = SHARED_U ? m : TN * m;
-    static constexpr int IN_STAGE = align4i(KF * IN_ROW);
+    static constexpr int CTRL_OFF = align4i(KF * IN_ROW);               // per-system channel rows [KF][TN]
+    static constexpr int IN_STAGE = CTRL_OFF + (SHARED_U ? KF * TN : 0);
     static constexpr int XO_STAGE = KF * TN * n;
     static constexpr int YO_STAGE = KF * TN * p;
     static constexpr int NBAR = 2 * S + 4;
@@ -114,8 +121,21 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_fwd_kernel(const FwdPar
             if (SHARED_U) {
                 const float *src = u_base + k0 * m;  // [T,1,m] is contiguous in k
                 for (int i = lane; i < rows * m; i += 32) dst[i] = __ldg(src + i);
+                const float *csrc = P.ctrl ? P.ctrl + (t_begin + k0) * N + n0 : nullptr;
+                float *cdst = dst + Cfg::CTRL_OFF;
+                if (csrc && !P.bulk_in)
+                    for (int r = 0; r < rows; ++r)
+                        for (int i = lane; i < valid; i += 32) cdst[r * TN + i] = __ldg(csrc + r * N + i);
                 __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&full[s]);
+                if (lane == 0) {
+                    if (csrc && P.bulk_in) {
+                        const uint32_t row_bytes = (uint32_t)valid * 4u;
+                        ptx::mbar_arrive_expect_tx(&full[s], row_bytes * (uint32_t)rows);
+                        for (int r = 0; r < rows; ++r) ptx::bulk_g2s(cdst + r * TN, csrc + r * N, row_bytes, &full[s], pol);
+                    } else {
+                        ptx::mbar_arrive(&full[s]);
+                    }
+                }
             } else if (P.bulk_in) {
                 if (lane == 0) {
                     const uint32_t row_bytes = (uint32_t)valid * m * 4u;
@@ -209,6 +229,11 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_fwd_kernel(const FwdPar
                 float u[m];
 #pragma unroll
                 for (int d = 0; d < m; ++d) u[d] = in[j * IN_ROW + d];
+                if (SHARED_U && P.ctrl != nullptr) {
+                    const float cv = s_in[s * IN_STAGE + Cfg::CTRL_OFF + j * TN + tid];
+#pragma unroll
+                    for (int d = 0; d < m; ++d) u[d] = (d == P.ctrl_col) ? cv : u[d];
+                }
                 if (emit_y) {
                     float y[p];
                     M.out(x, u, y);  // y_k from the PRE-update state (simulator.py:38)

@@ -80,3 +80,32 @@ def rc_loss_grad(theta, x0, u, target, dt, lb=None, ub=None, discrete=False, til
 
 def release():
     check(lib().dynax_host_release())
+
+
+def rc_loss_grad_ctrl(theta, x0, u_shared, ctrl, target, dt, ctrl_col=2, lb=None, ub=None, tile_systems=0):
+    """Host-buffer loss + gradient with a shared input series u_shared[T,5] and a per-system channel
+    ctrl[T,N] (rc.py:128-131): only 4 B (+ target) per system-step cross PCIe instead of 24."""
+    theta, x0 = _f32(theta), _f32(x0)
+    u_shared, ctrl, target = _f32(u_shared).reshape(-1, 5), _f32(ctrl), _f32(target)
+    N, T = x0.shape[0], u_shared.shape[0]
+    if theta.ndim == 1:
+        theta = theta[None]
+    if ctrl.shape != (T, N):
+        raise ValueError(f"ctrl must be [T,N]=({T},{N}), got {ctrl.shape}")
+    flags = SHARED_THETA if (theta.shape[0] == 1 and N != 1) else 0
+    if target.shape == (T, N) and N != 1:
+        pass
+    elif target.size == T:
+        target = target.reshape(T)
+        flags |= SHARED_TARGET if N != 1 else 0
+    else:
+        raise ValueError(f"target must be [T,N] or [T], got {target.shape}")
+    lb = None if lb is None else _f32(lb).reshape(7)
+    ub = None if ub is None else _f32(ub).reshape(7)
+    shared = bool(flags & SHARED_THETA)
+    loss = np.empty((1 if shared else N,), np.float32)
+    grad = np.empty((7,) if shared else (N, 7), np.float32)
+    check(lib().dynax_rc_loss_grad_ctrl_host_f32(_p(theta), _p(x0), _p(u_shared), _p(ctrl), int(ctrl_col), _p(target),
+                                                 _p(lb), _p(ub), _p(loss), _p(grad), N, T, float(dt), flags,
+                                                 int(tile_systems)))
+    return loss, grad

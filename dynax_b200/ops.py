@@ -368,3 +368,85 @@ def node_rk4_forward(W1, b1, W2, b2, W3, b3, x0, u, dt, emit_x=True, emit_y=True
         check(lib().dynax_node_rk4_forward_f32(*[_ptr(t) for t in ws], _ptr(x0), _ptr(u), _ptr(xsol), _ptr(ysol),
                                                _ptr(xfin), N, T, n, m, p, hidden, float(dt), flags, _stream()))
     return xsol, ysol, xfin
+
+
+# ----------------------------------------------------------------------------------------------
+# shared input series + per-system control channel; tabular interpolation (row f-1)
+# ----------------------------------------------------------------------------------------------
+def _ctrl_args(theta, x0, u_shared, ctrl, ctrl_col):
+    x0, u_shared, ctrl = _f32c(x0, "x0"), _f32c(u_shared, "u_shared"), _f32c(ctrl, "ctrl")
+    if x0.dim() != 2 or x0.shape[1] != 3:
+        raise ValueError(f"x0 must be [N,3], got {tuple(x0.shape)}")
+    N = x0.shape[0]
+    u_shared = u_shared.reshape(-1, 5)
+    T = u_shared.shape[0]
+    if ctrl.shape != (T, N):
+        raise ValueError(f"ctrl must be [T,N]=({T},{N}), got {tuple(ctrl.shape)}")
+    if not 0 <= int(ctrl_col) < 5:
+        raise ValueError("ctrl_col must be in [0,5)")
+    theta, shared_th = _rc_theta(theta, N)
+    return theta, shared_th, x0, u_shared, ctrl, N, T
+
+
+def rc_forward_ctrl(theta, x0, u_shared, ctrl, dt, ctrl_col=2, emit_x=True, emit_y=True, emit_final=False):
+    """RC rollout with inputs u_k = u_shared[k] except column ``ctrl_col`` = ctrl[k, system]
+    (dynax/wrapper/envs/rc.py:128-131: shared disturbances + per-system HVAC control)."""
+    theta, shared_th, x0, u_shared, ctrl, N, T = _ctrl_args(theta, x0, u_shared, ctrl, ctrl_col)
+    dev = x0.device
+    xsol = torch.empty((T, N, 3), dtype=torch.float32, device=dev) if emit_x else None
+    ysol = torch.empty((T, N, 1), dtype=torch.float32, device=dev) if emit_y else None
+    xfin = torch.empty((N, 3), dtype=torch.float32, device=dev) if emit_final else None
+    flags = SHARED_THETA if shared_th else 0
+    with torch.cuda.device(dev):
+        check(lib().dynax_rc_forward_ctrl_f32(_ptr(theta), _ptr(x0), _ptr(u_shared), _ptr(ctrl), int(ctrl_col),
+                                              _ptr(xsol), _ptr(ysol), _ptr(xfin), N, T, float(dt), flags, _stream()))
+    return xsol, ysol, xfin
+
+
+def rc_loss_grad_ctrl(theta, x0, u_shared, ctrl, target, dt, ctrl_col=2, lb=None, ub=None, want_gx0=False):
+    """Fused MSE loss + gradient with shared disturbances and a per-system control channel."""
+    theta, shared_th, x0, u_shared, ctrl, N, T = _ctrl_args(theta, x0, u_shared, ctrl, ctrl_col)
+    target = _f32c(target, "target")
+    if target.dim() == 2 and target.shape == (T, N) and N != 1:
+        shared_tg = False
+    elif target.numel() == T:
+        shared_tg, target = N != 1, target.reshape(T)
+    else:
+        raise ValueError(f"target must be [T,N] or [T], got {tuple(target.shape)}")
+    dev = x0.device
+    if (lb is None) != (ub is None):
+        raise ValueError("lb and ub must be given together")
+    if lb is not None:
+        lb = torch.as_tensor(lb, dtype=torch.float32, device=dev).reshape(7).contiguous()
+        ub = torch.as_tensor(ub, dtype=torch.float32, device=dev).reshape(7).contiguous()
+    nout = 1 if shared_th else N
+    loss = torch.empty((nout,), dtype=torch.float32, device=dev)
+    grad = torch.empty((nout, 7), dtype=torch.float32, device=dev)
+    gx0 = torch.empty((N, 3), dtype=torch.float32, device=dev) if want_gx0 else None
+    flags = (SHARED_THETA if shared_th else 0) | (SHARED_TARGET if shared_tg else 0)
+    ws = _ws(lib().dynax_workspace_bytes(_lib.OP_RC_LOSS_GRAD, N, T, 3, 5, 1, flags), dev)
+    with torch.cuda.device(dev):
+        check(lib().dynax_rc_loss_grad_ctrl_f32(_ptr(theta), _ptr(x0), _ptr(u_shared), _ptr(ctrl), int(ctrl_col),
+                                                _ptr(target), _ptr(lb), _ptr(ub), _ptr(loss), _ptr(grad), _ptr(gx0),
+                                                N, T, float(dt), flags, _ptr(ws), ws.numel(), _stream()))
+    return loss, (grad.reshape(7) if shared_th else grad), gx0
+
+
+def tabular_interp(ts, xs, at, mode="linear"):
+    """``Tabular(ts, xs, mode)(at)`` (dynax/agents/tabular.py:33-44): rows xs[n_rows,n_cols] at times ts,
+    evaluated at at[...] -> out[..., n_cols].  mode 'linear' or 'constant' (= nearest row)."""
+    ts, xs, at = _f32c(ts, "ts"), _f32c(xs, "xs"), _f32c(at, "at")
+    if ts.dim() != 1:
+        raise AssertionError("rank of ts has to be 1 !!!")          # interpolate.py:15
+    if xs.dim() != 2:
+        raise AssertionError("rank of xs has to be 2 !!!")          # interpolate.py:16
+    if xs.shape[0] != ts.shape[0]:
+        raise ValueError("ts and xs must have the same number of rows")
+    if mode not in ("linear", "constant"):
+        raise ValueError("Interpolation mode in Tabular has to be either 'linear' or 'constant' !!!")   # tabular.py:39
+    flat = at.reshape(-1)
+    out = torch.empty((flat.numel(), xs.shape[1]), dtype=torch.float32, device=xs.device)
+    with torch.cuda.device(xs.device):
+        check(lib().dynax_tabular_interp_f32(_ptr(ts), _ptr(xs), xs.shape[0], xs.shape[1], _ptr(flat), flat.numel(),
+                                             1 if mode == "linear" else 0, _ptr(out), _stream()))
+    return out.reshape(tuple(at.shape) + (xs.shape[1],)) if at.dim() != 2 or at.shape[-1] != 1 else out

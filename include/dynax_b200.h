@@ -102,6 +102,27 @@ int dynax_rc_loss_grad_f32(const float *theta, const float *x0, const float *u, 
                            int64_t N, int64_t T, float dt, uint32_t flags,
                            void *ws, size_t ws_bytes, void *stream);
 
+/* Shared input series + one per-system channel: u_k(system) = u_shared[k] with column `ctrl_col`
+ * replaced by ctrl[k, system].  This is how the RC env assembles its inputs from the shared
+ * disturbance table and the per-env control (dynax/wrapper/envs/rc.py:128-131); the streamed input
+ * drops from 20 to 4 bytes per system-step.  u_shared:[T,5], ctrl:[T,N].  DYNAX_SHARED_U is implied. */
+int dynax_rc_forward_ctrl_f32(const float *theta, const float *x0, const float *u_shared, const float *ctrl,
+                              int ctrl_col, float *xsol, float *ysol, float *x_final,
+                              int64_t N, int64_t T, float dt, uint32_t flags, void *stream);
+int dynax_rc_loss_grad_ctrl_f32(const float *theta, const float *x0, const float *u_shared, const float *ctrl,
+                                int ctrl_col, const float *target, const float *lb, const float *ub,
+                                float *loss, float *g_theta, float *g_x0,
+                                int64_t N, int64_t T, float dt, uint32_t flags,
+                                void *ws, size_t ws_bytes, void *stream);
+
+/* Tabular time-table lookup (dynax/agents/tabular.py:33-44 over dynax/utils/interpolate.py:26-68):
+ * out[i,:] = interpolation of the rows xs[n_rows,n_cols] sampled at times ts[n_rows] evaluated at at[i].
+ * mode 1 = 'linear' (jnp.interp to a fractional row index, then order-1 map_coordinates),
+ * mode 0 = 'constant' (order-0 map_coordinates = NEAREST row, halves round away from zero; it is not a
+ * zero-order hold).  Queries outside [ts[0], ts[-1]] clamp to the end rows.  out:[n_at,n_cols]. */
+int dynax_tabular_interp_f32(const float *ts, const float *xs, int64_t n_rows, int n_cols,
+                             const float *at, int64_t n_at, int mode, float *out, void *stream);
+
 /* General-cotangent VJP of dynax_rc_forward_f32 (what jax.vjp/jax.grad of simulator.apply needs
  * for an arbitrary downstream loss).  g_xsol:[T,N,3] or NULL, g_ysol:[T,N,1] or NULL (at least
  * one non-NULL).  Outputs (each may be NULL): g_theta:[N,7] ([7] if SHARED_THETA), g_x0:[N,3],
@@ -166,6 +187,12 @@ int dynax_rc_loss_grad_host_f32(const float *theta, const float *x0, const float
                                 const float *lb, const float *ub,
                                 float *loss, float *g_theta,
                                 int64_t N, int64_t T, float dt, uint32_t flags, int64_t tile_systems);
+
+/* Host-buffer flavour of dynax_rc_loss_grad_ctrl_f32: only ctrl[T,N] (+ target) cross PCIe per system. */
+int dynax_rc_loss_grad_ctrl_host_f32(const float *theta, const float *x0, const float *u_shared, const float *ctrl,
+                                     int ctrl_col, const float *target, const float *lb, const float *ub,
+                                     float *loss, float *g_theta,
+                                     int64_t N, int64_t T, float dt, uint32_t flags, int64_t tile_systems);
 
 /* Frees the device scratch the *_host entry points cache between calls. */
 int dynax_host_release(void);

@@ -413,3 +413,19 @@ def synth_mlp(seed, n=3, m=5, hidden=64, scale=0.1):
     mk = lambda o, i: (scale * rng.normal(size=(o, i)) / np.sqrt(i)).astype(np.float32)
     return (mk(hidden, n + m), (0.01 * rng.normal(size=hidden)).astype(np.float32), mk(hidden, hidden),
             (0.01 * rng.normal(size=hidden)).astype(np.float32), mk(n, hidden), np.zeros(n, np.float32))
+
+
+# --------------------------------------------------------------------------------------
+# f-1: Tabular time-table lookup      dynax/agents/tabular.py:33-44, dynax/utils/interpolate.py:26-68
+# Pinned by tests/test_agents.py:13-25 (tests/golden/golden_tabular.json).
+# --------------------------------------------------------------------------------------
+def tabular_interp(ts, xs, at, mode="linear", dtype=np.float64):
+    ts = np.asarray(ts, dtype=dtype); xs = np.asarray(xs, dtype=dtype); at = np.asarray(at, dtype=dtype).reshape(-1)
+    idx = np.interp(at, ts, np.arange(len(ts), dtype=dtype))               # interpolate.py:42 / :63
+    if mode == "linear":                                                    # map_coordinates(order=1)
+        lo = np.minimum(np.floor(idx).astype(int), len(ts) - 1)
+        hi = np.minimum(lo + 1, len(ts) - 1)
+        w = (idx - np.floor(idx))[:, None]
+        return xs[lo] * (1 - w) + xs[hi] * w
+    r = np.floor(np.abs(idx) + 0.5) * np.sign(idx)                          # order=0: nearest, half away from zero
+    return xs[np.clip(r.astype(int), 0, len(ts) - 1)]

@@ -51,3 +51,16 @@ def test_loss_grad_host_tiled_matches_device_api():
     lbud, gbud = orc.rc_output_sensitivity_budget(np.repeat(th1[None], N, 0), x0, u, target, 3600.0)
     assert_loss_parity(loss1[0], lr.sum() + pen, lbud.sum())
     assert_grad_parity(grad1, gs, gbud.sum(0))
+
+
+def test_loss_grad_ctrl_host_matches_device_api():
+    import torch
+    from dynax_b200 import host, ops
+    N, Tn = 700, 200
+    th, x0, u = orc.synth_theta(N, 63), orc.synth_x0(N, 63), orc.synth_u(Tn, N, 63)
+    d, ctrl = u[:, 0].copy(), u[:, :, 2].copy()
+    target = (22 + np.random.default_rng(8).normal(size=(Tn, N))).astype(np.float32)
+    loss, grad = host.rc_loss_grad_ctrl(th, x0, d, ctrl, target, 3600.0, lb=orc.RC_LB, ub=orc.RC_UB, tile_systems=256)
+    c = lambda a: torch.tensor(np.ascontiguousarray(a)).cuda()
+    ld, gd, _ = ops.rc_loss_grad_ctrl(c(th), c(x0), c(d), c(ctrl), c(target), 3600.0, lb=orc.RC_LB, ub=orc.RC_UB)
+    assert np.array_equal(ld.cpu().numpy(), loss) and np.array_equal(gd.cpu().numpy(), grad)
