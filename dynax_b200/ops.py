@@ -450,3 +450,37 @@ def tabular_interp(ts, xs, at, mode="linear"):
         check(lib().dynax_tabular_interp_f32(_ptr(ts), _ptr(xs), xs.shape[0], xs.shape[1], _ptr(flat), flat.numel(),
                                              1 if mode == "linear" else 0, _ptr(out), _stream()))
     return out.reshape(tuple(at.shape) + (xs.shape[1],)) if at.dim() != 2 or at.shape[-1] != 1 else out
+
+
+# ----------------------------------------------------------------------------------------------
+# batched RC-env step (row f-2)
+# ----------------------------------------------------------------------------------------------
+def rc_env_step(theta, x, t, action, ts, dist, price, t_low, t_high, dt, cop=2.5, w_energy=100.0, w_comfort=1.0,
+                u_low=-10.0, u_high=0.0, num_actions=101):
+    """K consecutive ``RC.step`` calls (dynax/wrapper/envs/rc.py:103-158) for N environments.
+
+    theta[7]|[N,7], x[N,3], t[N], action[K,N]|[N] (int), ts[R], dist[R,4], price/t_low/t_high[24].
+    Returns dict(x_next[N,3], t_next[N], obs[K,N,5], reward[K,N], terminated[K,N], cost[K,N], dTz[K,N]).
+    """
+    x, t, ts, dist = _f32c(x, "x"), _f32c(t, "t"), _f32c(ts, "ts"), _f32c(dist, "dist")
+    price, t_low, t_high = _f32c(price, "price"), _f32c(t_low, "t_low"), _f32c(t_high, "t_high")
+    N = x.shape[0]
+    theta, shared_th = _rc_theta(theta, N)
+    action = action.to(torch.int32)
+    if action.dim() == 1:
+        action = action[None]
+    action = action.contiguous()
+    if not action.is_cuda or action.shape[1] != N or t.numel() != N or dist.shape != (ts.numel(), 4):
+        raise ValueError("action must be CUDA [K,N], t [N], dist [R,4] with R = len(ts)")
+    K = action.shape[0]
+    dev = x.device
+    mk = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+    out = dict(x_next=mk(N, 3), t_next=mk(N), obs=mk(K, N, 5), reward=mk(K, N), terminated=mk(K, N), cost=mk(K, N), dTz=mk(K, N))
+    with torch.cuda.device(dev):
+        check(lib().dynax_rc_env_step_f32(_ptr(theta), _ptr(x), _ptr(t), _ptr(action), _ptr(ts), _ptr(dist), ts.numel(),
+                                          _ptr(price), _ptr(t_low), _ptr(t_high), float(cop), float(w_energy),
+                                          float(w_comfort), float(u_low), float(u_high), int(num_actions),
+                                          _ptr(out["x_next"]), _ptr(out["t_next"]), _ptr(out["obs"]), _ptr(out["reward"]),
+                                          _ptr(out["terminated"]), _ptr(out["cost"]), _ptr(out["dTz"]), N, K, float(dt),
+                                          SHARED_THETA if shared_th else 0, _stream()))
+    return out

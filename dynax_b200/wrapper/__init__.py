@@ -1,0 +1,3 @@
+from .envs.rc import RC, EnvStates
+
+__all__ = ["RC", "EnvStates"]

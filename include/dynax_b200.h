@@ -176,6 +176,21 @@ int dynax_rc_mpc_cost_f32(const float *theta, const float *x0, const float *d, c
                           float *cost, long long *argmin, float *min_cost,
                           int64_t N, int64_t H, float dt, void *ws, size_t ws_bytes, void *stream);
 
+/* ---- Batched RC-env step: K consecutive RC.step calls
+ *      (dynax/wrapper/envs/rc.py:103-158) for N independent environments in one launch: action ->
+ *      control (rc.py:166), linear Tabular lookup of the 4 disturbances at each env's own time (rc.py:128),
+ *      one Euler step (rc.py:131-132), observation (rc.py:200-222), reward (rc.py:227-252) and
+ *      termination flag (rc.py:255-264).  theta:[7]|[N,7] x:[N,3] t:[N] action:[K,N] int32
+ *      ts:[R] dist:[R,4] price/t_low/t_high:[24];  outputs x_next:[N,3] t_next:[N] obs:[K,N,5]
+ *      reward:[K,N] terminated:[K,N] (1.0/0.0), cost/dTz:[K,N] or NULL. ---- */
+int dynax_rc_env_step_f32(const float *theta, const float *x, const float *t, const int32_t *action,
+                          const float *ts, const float *dist, int64_t R,
+                          const float *price, const float *t_low, const float *t_high,
+                          float cop, float w_energy, float w_comfort, float u_low, float u_high, int num_actions,
+                          float *x_next, float *t_next, float *obs, float *reward, float *terminated,
+                          float *cost, float *dTz,
+                          int64_t N, int64_t K, float dt, uint32_t flags, void *stream);
+
 /* ---- Host-buffer entry points (the call a reference user makes with NumPy/JAX-CPU arrays):
  *      pageable or pinned HOST pointers in, results in HOST buffers on return.  The system axis is
  *      processed in tiles of `tile_systems` (0 = library default) with copies overlapped. ------ */

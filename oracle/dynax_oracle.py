@@ -429,3 +429,28 @@ def tabular_interp(ts, xs, at, mode="linear", dtype=np.float64):
         return xs[lo] * (1 - w) + xs[hi] * w
     r = np.floor(np.abs(idx) + 0.5) * np.sign(idx)                          # order=0: nearest, half away from zero
     return xs[np.clip(r.astype(int), 0, len(ts) - 1)]
+
+
+# --------------------------------------------------------------------------------------
+# f-2: one RC-env step for N environments          dynax/wrapper/envs/rc.py:103-158, 200-264
+# Pinned by tests/test_gymwrapper_basics.py:7-12 (golden #2).
+# --------------------------------------------------------------------------------------
+def rc_env_step(theta, x, t, action, ts, dist, dt, price=RC_PRICE, t_low=RC_T_LOW, t_high=RC_T_HIGH, cop=2.5,
+                weights=(100.0, 1.0), u_low=-10.0, u_high=0.0, num_actions=101, dtype=np.float32):
+    """theta[N|1,7], x[N,3], t[N], action[N] -> dict(x_next, t_next, obs[N,5], reward, terminated, cost, dTz)."""
+    x = np.asarray(x, dtype=dtype); t = np.asarray(t, dtype=dtype); N = x.shape[0]
+    control = (np.asarray(action) * dtype((u_high - u_low) / (num_actions - 1)) + dtype(u_low)).astype(dtype)   # rc.py:166
+    d = tabular_interp(ts, dist, t, "linear", dtype).astype(dtype)                                             # rc.py:128
+    inputs = np.stack([d[:, 0], d[:, 1], control, d[:, 2], d[:, 3]], -1).astype(dtype)                         # rc.py:131
+    xs, ys = rc_rollout(np.atleast_2d(theta), x, inputs[None], dt, dtype)                                      # rc.py:132
+    x_next, y = xs[0], ys[0, :, 0]
+    t_next = (t + dtype(dt)).astype(dtype)                                                                     # rc.py:137
+    power = (-control / dtype(cop)).astype(dtype)
+    obs = np.stack([t_next, y, d[:, 0], d[:, 3], power], -1).astype(dtype)                                     # rc.py:218-222
+    h = ((t_next.astype(np.int64) % 86400) / 3600).astype(np.int64)                                            # rc.py:238
+    energy = power * dtype(dt) / dtype(3600.0)                                                                 # rc.py:241
+    cost = np.asarray(price, dtype)[h] * energy                                                                # rc.py:244
+    dTz = np.maximum(y - np.asarray(t_high, dtype)[h], 0) + np.maximum(np.asarray(t_low, dtype)[h] - y, 0)     # rc.py:247
+    reward = -dtype(weights[0]) * cost - dtype(weights[1]) * dTz                                               # rc.py:250
+    viol = np.maximum(x_next - 40.0, 0).sum(-1) + np.maximum(12.0 - x_next, 0).sum(-1)                         # rc.py:258
+    return dict(x_next=x_next, t_next=t_next, obs=obs, reward=reward, terminated=(viol > 0).astype(dtype), cost=cost, dTz=dTz)
