@@ -48,3 +48,39 @@ def mse_loss_and_grad(simulator, variables, x0, u, target, params_lb=None, param
                                      _bounds(params_ub, dev))
     grads = {"params": {"model": unstack_theta(grad.reshape(-1, 7), leaves)}}
     return loss, grads
+
+
+def calibrate(simulator, variables, x0, u, target, params_lb=None, params_ub=None, n_epochs=5000, lr=1e-3,
+              log_every=0):
+    """The training loop of examples/3-inverse.py:117-138 kept entirely on the device (row f-3):
+    every epoch = one fused loss+gradient launch + one LAMB update launch, no host round trip.
+
+    ``variables`` holds [N] leaves (N candidates calibrated independently) or scalar leaves (one
+    candidate).  Returns (variables_fitted, loss[N] of the last epoch).
+    """
+    model = simulator.model
+    if not isinstance(model, _RC4R3C):
+        raise NotImplementedError("calibrate is implemented for the 4R3C model")
+    x0 = torch.as_tensor(x0, dtype=torch.float32)
+    x0 = x0.cuda() if not x0.is_cuda else x0
+    dev = x0.device
+    u = torch.as_tensor(u, dtype=torch.float32).to(dev)
+    target = torch.as_tensor(target, dtype=torch.float32).to(dev)
+    leaves = variables["params"]["model"]
+    theta = stack_theta(leaves, dev).detach().clone().contiguous()
+    if x0.dim() == 1:
+        x0 = x0.reshape(1, 3)
+        u = u[:, None, :] if u.dim() == 2 else u
+        target = target.reshape(u.shape[0], -1)
+    if theta.shape[0] == 1 and x0.shape[0] > 1:
+        raise NotImplementedError("calibrate updates per-candidate parameters; pass [N] leaves")
+    lb, ub = _bounds(params_lb, dev), _bounds(params_ub, dev)
+    m, v = torch.zeros_like(theta), torch.zeros_like(theta)
+    loss = None
+    for epoch in range(1, int(n_epochs) + 1):
+        loss, grad, _ = ops.rc_loss_grad(theta, x0, u, target, float(simulator.dt), lb, ub)
+        ops.lamb_update_(theta, grad.contiguous(), m, v, epoch, lr)
+        if log_every and epoch % log_every == 0:
+            print("loss at epoch %d: %.4f, grad norm %.4f" % (epoch, float(loss.mean()), float(grad.norm())))
+    fitted = {"params": {"model": unstack_theta(theta, leaves)}}
+    return fitted, loss

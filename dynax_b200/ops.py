@@ -484,3 +484,31 @@ def rc_env_step(theta, x, t, action, ts, dist, price, t_low, t_high, dt, cop=2.5
                                           _ptr(out["terminated"]), _ptr(out["cost"]), _ptr(out["dTz"]), N, K, float(dt),
                                           SHARED_THETA if shared_th else 0, _stream()))
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# on-device calibration loop pieces (rows f-3 / f-4)
+# ----------------------------------------------------------------------------------------------
+def lamb_update_(theta, grad, m, v, step, lr=1e-3, b1=0.9, b2=0.999, eps=1e-6):
+    """In-place optax.lamb(lr) update (examples/3-inverse.py:113-122) of every scalar in ``theta``."""
+    for t, nm in ((theta, "theta"), (grad, "grad"), (m, "m"), (v, "v")):
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise ValueError(f"{nm} must be a contiguous float32 CUDA tensor")
+        if t.numel() != theta.numel():
+            raise ValueError("theta, grad, m, v must have the same number of elements")
+    with torch.cuda.device(theta.device):
+        check(lib().dynax_lamb_update_f32(_ptr(theta), _ptr(grad), _ptr(m), _ptr(v), theta.numel(), int(step), float(lr),
+                                          float(b1), float(b2), float(eps), _stream()))
+    return theta
+
+
+def resample_mean(x, factor):
+    """``data.groupby(index // factor).mean()`` (examples/1-forward.py:26-27) for x[rows, cols] on the device."""
+    x = _f32c(x, "x")
+    if x.dim() != 2:
+        raise ValueError("x must be [rows, cols]")
+    rows, cols = x.shape
+    out = torch.empty((-(-rows // int(factor)), cols), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib().dynax_resample_mean_f32(_ptr(x), _ptr(out), rows, cols, int(factor), _stream()))
+    return out

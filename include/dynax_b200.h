@@ -191,6 +191,17 @@ int dynax_rc_env_step_f32(const float *theta, const float *x, const float *t, co
                           float *cost, float *dTz,
                           int64_t N, int64_t K, float dt, uint32_t flags, void *stream);
 
+/* ---- On-device calibration loop pieces.
+ *      dynax_lamb_update_f32: the optax.lamb(lr) update that examples/3-inverse.py:113-122 applies after
+ *      value_and_grad, element-wise over n = N*7 scalar parameters (every Flax leaf there is a scalar, so
+ *      the LAMB trust ratio is per element).  m, v: Adam moments (zero-initialised by the caller),
+ *      step: 1-based epoch.  PARITY UNPINNED BY THE REFERENCE (optax is an absent, unpinned dependency).
+ *      dynax_resample_mean_f32: data.groupby(index // dt).mean() of examples/1-forward.py:26-27:
+ *      out[r,:] = mean(in[r*factor : (r+1)*factor, :]), out rows = ceil(rows/factor). ---- */
+int dynax_lamb_update_f32(float *theta, const float *grad, float *m, float *v, int64_t n, int64_t step,
+                          float lr, float b1, float b2, float eps, void *stream);
+int dynax_resample_mean_f32(const float *in, float *out, int64_t rows, int cols, int64_t factor, void *stream);
+
 /* ---- Host-buffer entry points (the call a reference user makes with NumPy/JAX-CPU arrays):
  *      pageable or pinned HOST pointers in, results in HOST buffers on return.  The system axis is
  *      processed in tiles of `tile_systems` (0 = library default) with copies overlapped. ------ */

@@ -454,3 +454,25 @@ def rc_env_step(theta, x, t, action, ts, dist, dt, price=RC_PRICE, t_low=RC_T_LO
     reward = -dtype(weights[0]) * cost - dtype(weights[1]) * dTz                                               # rc.py:250
     viol = np.maximum(x_next - 40.0, 0).sum(-1) + np.maximum(12.0 - x_next, 0).sum(-1)                         # rc.py:258
     return dict(x_next=x_next, t_next=t_next, obs=obs, reward=reward, terminated=(viol > 0).astype(dtype), cost=cost, dTz=dTz)
+
+
+# --------------------------------------------------------------------------------------
+# f-3: optax.lamb(lr) update for scalar leaves (examples/3-inverse.py:113-122).  optax is an absent,
+# unpinned third-party dependency: this restates its published chain scale_by_adam(b1=.9,b2=.999,
+# eps=1e-6) -> add_decayed_weights(0) -> scale_by_trust_ratio() -> scale(-lr).  PARITY UNPINNED.
+# f-4: data.groupby(index // factor).mean()  (examples/1-forward.py:26-27)
+# --------------------------------------------------------------------------------------
+def lamb_update(theta, grad, m, v, step, lr=1e-3, b1=0.9, b2=0.999, eps=1e-6):
+    theta, grad, m, v = (np.asarray(a, dtype=np.float64) for a in (theta, grad, m, v))
+    m = b1 * m + (1 - b1) * grad
+    v = b2 * v + (1 - b2) * grad * grad
+    upd = (m / (1 - b1 ** step)) / (np.sqrt(v / (1 - b2 ** step)) + eps)
+    pn, un = np.abs(theta), np.abs(upd)
+    trust = np.where((pn == 0) | (un == 0), 1.0, pn / np.where(un == 0, 1.0, un))
+    return theta - lr * trust * upd, m, v
+
+
+def resample_mean(x, factor):
+    x = np.asarray(x, dtype=np.float64)
+    rows = x.shape[0]
+    return np.stack([x[r:r + factor].mean(0) for r in range(0, rows, factor)])
