@@ -39,6 +39,13 @@ int launch_adj(const AdjParams<Model> &P, cudaStream_t st) {
     if (rc != DYNAX_OK) return rc;
     const int64_t grid = (P.N + TN - 1) / TN;
     if (grid > 0x7fffffffLL) return fail(DYNAX_ERR_INVALID_ARGUMENT, "N too large for one launch");
+    if (P.chunk_len > 0) {  // time-chunked launch: the caller (rc_chunked_adj.cu) owns zeroing and finalisation
+        const int64_t chunks = (P.T + P.chunk_len - 1) / P.chunk_len;
+        if (chunks > 65535) return fail(DYNAX_ERR_INVALID_ARGUMENT, "too many time chunks");
+        kern<<<dim3((unsigned)grid, (unsigned)chunks), Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(P);
+        DYNAX_CUDA_TRY(cudaGetLastError());
+        return DYNAX_OK;
+    }
     if (P.shared_theta) DYNAX_CUDA_TRY(cudaMemsetAsync(P.shared_acc, 0, kAccBytes, st));
     kern<<<(unsigned)grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(P);
     DYNAX_CUDA_TRY(cudaGetLastError());

@@ -126,6 +126,66 @@ int forward_chunked(FwdParams<Model> P, int64_t L, void *ws, size_t ws_bytes, cu
     return DYNAX_OK;
 }
 
+// a_end[C-1] = 0;  a_end[c-1] = a_start_true[c] = w[c] + a_end[c] + Psi^T a_end[c]      (c = C-1 .. 1)
+// where w[c] is chunk c's start adjoint for a ZERO terminal adjoint.  ((I+dtA)^T)^L = (I+Psi_L)^T; the
+// last chunk may be shorter but its terminal adjoint is zero, so only Psi_L of full chunks is needed.
+template <int n>
+__global__ void stitch_adjoint_kernel(const float *psi, const float *w /*[C,N,n]*/, float *aend /*[C,N,n]*/, int64_t N,
+                                      int64_t C) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    float P[n][n], a[n];
+#pragma unroll
+    for (int j = 0; j < n; ++j)
+#pragma unroll
+        for (int d = 0; d < n; ++d) P[j][d] = psi[(i * n + j) * n + d];  // P[j][d] = Psi[d][j]
+#pragma unroll
+    for (int d = 0; d < n; ++d) a[d] = 0.f;
+    for (int64_t c = C - 1; c >= 0; --c) {
+#pragma unroll
+        for (int d = 0; d < n; ++d) aend[(c * N + i) * n + d] = a[d];
+        if (c == 0) break;
+        float b[n];
+#pragma unroll
+        for (int j = 0; j < n; ++j) {
+            float acc = w[(c * N + i) * n + j];
+#pragma unroll
+            for (int d = 0; d < n; ++d) acc = fmaf(P[j][d], a[d], acc);  // (Psi^T a)_j
+            b[j] = a[j] + acc;
+        }
+#pragma unroll
+        for (int j = 0; j < n; ++j) a[j] = b[j];
+    }
+}
+
+struct ChunkedAdjWs {
+    float *psi, *v, *xb, *w, *aend, *ckpt;
+    double *chunk_acc, *shared_acc;
+    size_t bytes;
+};
+
+inline ChunkedAdjWs chunked_adj_layout(void *ws, int64_t N, int64_t T, int n, int nout, int64_t L) {
+    const int64_t C = (T + L - 1) / L;
+    const int64_t segs = (L + kMinKC - 1) / kMinKC;
+    char *p = reinterpret_cast<char *>(ws);
+    auto take = [&](size_t bytes) {
+        char *r = p;
+        p += (bytes + 255) & ~(size_t)255;
+        return r;
+    };
+    ChunkedAdjWs o;
+    o.shared_acc = reinterpret_cast<double *>(take(kAccBytes));
+    o.chunk_acc = reinterpret_cast<double *>(take(sizeof(double) * (size_t)N * (nout + 1)));
+    o.psi = reinterpret_cast<float *>(take(sizeof(float) * (size_t)N * n * n));
+    o.v = reinterpret_cast<float *>(take(sizeof(float) * (size_t)C * N * n));
+    o.xb = reinterpret_cast<float *>(take(sizeof(float) * (size_t)C * N * n));
+    o.w = reinterpret_cast<float *>(take(sizeof(float) * (size_t)C * N * n));
+    o.aend = reinterpret_cast<float *>(take(sizeof(float) * (size_t)C * N * n));
+    o.ckpt = reinterpret_cast<float *>(take(sizeof(float) * (size_t)C * segs * n * N));
+    o.bytes = (size_t)(p - reinterpret_cast<char *>(ws));
+    return o;
+}
+
 }  // namespace dynax
 
 using namespace dynax;
@@ -165,6 +225,84 @@ int dynax_rc_forward_chunked_f32(const float *theta, const float *x0, const floa
     return forward_chunked<RCModel>(P, L, ws, ws_bytes, st, [](const FwdParams<RCModel> &Q, cudaStream_t s) {
         return launch_fwd<RCModel, 128, 4, 4, false, 3>(Q, s);
     });
+}
+
+size_t dynax_rc_loss_grad_chunked_workspace(int64_t N, int64_t T, int64_t chunk_len) {
+    if (N <= 0 || T <= 0) return 0;
+    const int64_t L = chunk_len > 0 ? (chunk_len < T ? chunk_len : T) : auto_chunk_len(N, T, 128);
+    return chunked_adj_layout(nullptr, N, T, 3, 7, L).bytes;
+}
+
+int dynax_rc_loss_grad_chunked_f32(const float *theta, const float *x0, const float *u, const float *target,
+                                   const float *lb, const float *ub, float *loss, float *g_theta, float *g_x0,
+                                   int64_t N, int64_t T, float dt, uint32_t flags, int64_t chunk_len, void *ws,
+                                   size_t ws_bytes, void *stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (N < 0 || T < 1) return fail(DYNAX_ERR_INVALID_ARGUMENT, "need N >= 0 and T >= 1");
+    if (N == 0) return DYNAX_OK;
+    if (!theta || !x0 || !u || !target || !loss) return fail(DYNAX_ERR_INVALID_ARGUMENT, "theta, x0, u, target, loss must be non-NULL");
+    if ((lb == nullptr) != (ub == nullptr)) return fail(DYNAX_ERR_INVALID_ARGUMENT, "lb and ub must both be given or both be NULL");
+    if (flags & ~(DYNAX_SHARED_THETA | DYNAX_SHARED_U | DYNAX_SHARED_TARGET))
+        return fail(DYNAX_ERR_INVALID_ARGUMENT, "unsupported flags 0x%x for rc_loss_grad_chunked", flags);
+    int rc = require_sm100();
+    if (rc != DYNAX_OK) return rc;
+    const int64_t L = chunk_len > 0 ? (chunk_len < T ? chunk_len : T) : auto_chunk_len(N, T, 128);
+    const int64_t C = (T + L - 1) / L;
+    if (!ws || !aligned16(ws)) return fail(DYNAX_ERR_WORKSPACE, "workspace must be non-NULL and 16-byte aligned");
+    const ChunkedAdjWs W = chunked_adj_layout(ws, N, T, 3, 7, L);
+    if (ws_bytes < W.bytes) return fail(DYNAX_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", W.bytes, ws_bytes);
+    const bool sth = flags & DYNAX_SHARED_THETA, su = flags & DYNAX_SHARED_U, stg = flags & DYNAX_SHARED_TARGET;
+    const bool bulk = (N % 4) == 0 && aligned16(u) && aligned16(target);
+    const unsigned tb = 128, gb = (unsigned)((N + tb - 1) / tb);
+
+    // ---- forward: chunk boundary states xb[c]  (psi, zero-state responses, stitch)
+    FwdParams<RCModel> F;
+    F.mp.theta = theta; F.mp.stride = sth ? 0 : 7;
+    F.x0 = x0; F.u = u; F.xsol = nullptr; F.ysol = nullptr; F.x_final = W.v;
+    F.N = N; F.T = T; F.dt = dt; F.discrete = 0; F.bulk_in = bulk; F.bulk_out = 0;
+    F.chunk_len = L; F.x0_zero = 1;
+    psi_kernel<RCModel><<<gb, tb, 0, st>>>(F.mp, W.psi, N, L, dt);
+    DYNAX_CUDA_TRY(cudaGetLastError());
+    rc = su ? launch_fwd<RCModel, 128, 4, 4, true, 4>(F, st) : launch_fwd<RCModel, 128, 4, 4, false, 3>(F, st);
+    if (rc != DYNAX_OK) return rc;
+    stitch_kernel<3><<<gb, tb, 0, st>>>(W.psi, x0, W.v, W.xb, N, C);
+    DYNAX_CUDA_TRY(cudaGetLastError());
+
+    // ---- adjoint pass B1 (zero terminal adjoint, no gradient sums) -> w[c]; backward stitch -> aend[c];
+    //      pass B2 (true terminal adjoints) -> per-system fp64 sums over chunks -> outputs
+    AdjParams<RCModel> A;
+    memset(&A, 0, sizeof(A));
+    A.mp = F.mp; A.gp.g_theta = g_theta;
+    A.x0 = W.xb; A.x0_chunk_stride = N * 3;
+    A.u = u; A.target = target; A.lb = lb; A.ub = ub; A.loss = loss;
+    A.ckpt = W.ckpt; A.ckpt_chunk_stride = ((L + kMinKC - 1) / kMinKC) * 3 * N;
+    A.shared_acc = W.shared_acc; A.chunk_acc = nullptr;
+    A.N = N; A.T = T; A.dt = dt; A.bulk = bulk; A.shared_theta = sth ? 1 : 0; A.chunk_len = L;
+    auto launch = [&](const AdjParams<RCModel> &Q) {
+        if (su && stg) return launch_adj<RCModel, 128, 16, 4, ADJ_MSE, true, true, 2>(Q, st);
+        if (su) return launch_adj<RCModel, 128, 16, 4, ADJ_MSE, true, false, 2>(Q, st);
+        if (stg) return launch_adj<RCModel, 128, 16, 2, ADJ_MSE, false, true, 2>(Q, st);
+        return launch_adj<RCModel, 128, 16, 2, ADJ_MSE, false, false, 2>(Q, st);
+    };
+    AdjParams<RCModel> B1 = A;
+    B1.a_term = nullptr; B1.a_start = W.w; B1.skip_grads = 1;
+    rc = launch(B1);
+    if (rc != DYNAX_OK) return rc;
+    stitch_adjoint_kernel<3><<<gb, tb, 0, st>>>(W.psi, W.w, W.aend, N, C);
+    DYNAX_CUDA_TRY(cudaGetLastError());
+    DYNAX_CUDA_TRY(cudaMemsetAsync(W.chunk_acc, 0, sizeof(double) * (size_t)N * 8, st));
+    if (sth) DYNAX_CUDA_TRY(cudaMemsetAsync(W.shared_acc, 0, kAccBytes, st));
+    AdjParams<RCModel> B2 = A;
+    B2.a_term = W.aend; B2.a_start = nullptr; B2.skip_grads = 0; B2.chunk_acc = W.chunk_acc; B2.g_x0 = g_x0;
+    rc = launch(B2);
+    if (rc != DYNAX_OK) return rc;
+    chunk_finalize_kernel<RCModel><<<gb, tb, 0, st>>>(W.chunk_acc, A.mp, A.gp, lb, ub, loss, W.shared_acc, N, sth ? 1 : 0);
+    DYNAX_CUDA_TRY(cudaGetLastError());
+    if (sth) {
+        shared_finalize_kernel<RCModel, ADJ_MSE><<<1, 32, 0, st>>>(W.shared_acc, A.mp, A.gp, lb, ub, loss);
+        DYNAX_CUDA_TRY(cudaGetLastError());
+    }
+    return DYNAX_OK;
 }
 
 }  // extern "C"

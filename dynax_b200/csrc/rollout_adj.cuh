@@ -46,6 +46,16 @@ struct AdjParams {
     int discrete, bulk, shared_theta;
     const float *ctrl;    // SHARED_U only: per-system channel [T,N] replacing column ctrl_col of the shared u, or NULL
     int ctrl_col;
+    // Time-chunked launches (gridDim.y = chunks; rc_chunked_adj.cu).  Chunk c covers steps
+    // [c*chunk_len, min(T,(c+1)*chunk_len)), starts from x0 + c*x0_chunk_stride, and its adjoint starts
+    // from a_term[c] (zero if NULL).  MSE mode only.
+    int64_t chunk_len;        // 0: one chunk, the whole horizon
+    int64_t x0_chunk_stride;
+    int64_t ckpt_chunk_stride;  // floats between the checkpoint areas of consecutive chunks
+    const float *a_term;      // [C,N,n] adjoint entering each chunk from the future, or NULL
+    float *a_start;           // [C,N,n] out: adjoint at each chunk's first step, or NULL
+    double *chunk_acc;        // [N,NOUT+1] out: per-system fp64 sums over chunks (atomics), or NULL
+    int skip_grads;           // only a_start is wanted: skip the outer-product accumulation
 };
 
 template <class Model, int TN, int KC, int S, int MODE, bool SHARED_U, bool SHARED_TGT>
@@ -85,9 +95,16 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_adj_kernel(const AdjPar
     uint64_t *empty = full + S;
 
     const int tid = threadIdx.x;
-    const int64_t N = P.N, T = P.T;
+    const int64_t N = P.N;
     const int64_t n0 = (int64_t)blockIdx.x * TN;
     const int valid = (int)((N - n0) < TN ? (N - n0) : TN);
+    // this CTA's slice of the time axis (the whole horizon unless the launch is time-chunked)
+    const int64_t cidx = P.chunk_len > 0 ? (int64_t)blockIdx.y : 0;
+    const int64_t t_begin = cidx * P.chunk_len;
+    const int64_t T = P.chunk_len > 0 ? ((P.T - t_begin) < P.chunk_len ? (P.T - t_begin) : P.chunk_len) : P.T;
+    const float *const u_base = P.u + t_begin * (SHARED_U ? m : N * m);
+    const float *const tgt_base = P.target ? P.target + t_begin * (SHARED_TGT ? 1 : N) : nullptr;
+    const float *const ctrl_base = P.ctrl ? P.ctrl + t_begin * N : nullptr;
     const int64_t C = (T + KC - 1) / KC;  // number of segments
     const int64_t Q = 2 * C - 1;          // chunks through the ring: C-1 forward + C reverse
 
@@ -143,11 +160,11 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_adj_kernel(const AdjPar
             uint32_t bytes = 0;
 #pragma unroll
             for (int pass = 0; pass < 2; ++pass) {
-                uint32_t b = stream(pass, st + Cfg::U_OFF, U_ROW, P.u, m, SHARED_U, k0, rows, &full[s]);
-                if (SHARED_U) b += stream(pass, st + Cfg::A3_OFF, TN, P.ctrl, 1, false, k0, rows, &full[s]);
+                uint32_t b = stream(pass, st + Cfg::U_OFF, U_ROW, u_base, m, SHARED_U, k0, rows, &full[s]);
+                if (SHARED_U) b += stream(pass, st + Cfg::A3_OFF, TN, ctrl_base, 1, false, k0, rows, &full[s]);
                 if (!fwd) {
                     if (MODE == ADJ_MSE) {
-                        b += stream(pass, st + Cfg::A1_OFF, A1_ROW, P.target, 1, SHARED_TGT, k0, rows, &full[s]);
+                        b += stream(pass, st + Cfg::A1_OFF, A1_ROW, tgt_base, 1, SHARED_TGT, k0, rows, &full[s]);
                     } else {
                         b += stream(pass, st + Cfg::A1_OFF, A1_ROW, P.g_ysol, p, false, k0, rows, &full[s]);
                         b += stream(pass, st + Cfg::A2_OFF, A2_ROW, P.g_xsol, n, false, k0, rows, &full[s]);
@@ -180,10 +197,10 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_adj_kernel(const AdjPar
     M.load(P.mp, i);
     float xc[n];  // state at the start of the current chunk / segment
 #pragma unroll
-    for (int d = 0; d < n; ++d) xc[d] = __ldg(P.x0 + i * n + d);
+    for (int d = 0; d < n; ++d) xc[d] = __ldg(P.x0 + cidx * P.x0_chunk_stride + i * n + d);
     const float dt = P.dt;
     const bool discrete = P.discrete != 0;
-    float *ck = P.ckpt + (n0 + tid);  // ckpt[(seg*n + d)*N + system]; only touched when active
+    float *ck = P.ckpt + cidx * P.ckpt_chunk_stride + (n0 + tid);  // ckpt[(seg*n + d)*N + system]; only touched when active
     // shared input series + one per-system channel (rc.py:128-131): replace column ctrl_col
     auto override_ctrl = [&](float *u, const float *stage, int j) {
         if (SHARED_U && P.ctrl != nullptr) {
@@ -224,13 +241,13 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_adj_kernel(const AdjPar
     float sq = 0.f;
     double sqt = 0.0;
 #pragma unroll
-    for (int d = 0; d < n; ++d) a[d] = 0.f;
+    for (int d = 0; d < n; ++d) a[d] = P.a_term ? P.a_term[(cidx * N + i) * n + d] : 0.f;
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
         Gp[g] = 0.f;
         Gt[g] = 0.0;
     }
-    const float c2T = 2.0f / (float)T;
+    const float c2T = 2.0f / (float)P.T;  // the mean runs over the WHOLE horizon, also in a chunked launch
 
     for (int64_t seg = C - 1; seg >= 0; --seg, ++q) {
         const int s = (int)(q % S);
@@ -286,7 +303,7 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_adj_kernel(const AdjPar
                 }
 #pragma unroll
                 for (int d = 0; d < n; ++d) sv[d] = discrete ? a[d] : dt * a[d];  // cotangent of rhs
-                M.accum(Gp, sv, gy, xs[j], u);
+                if (!P.skip_grads) M.accum(Gp, sv, gy, xs[j], u);
                 if (MODE == ADJ_VJP && P.g_u != nullptr && active) {
                     float gu[m];
                     M.adj_u(sv, gy, gu);
@@ -314,9 +331,27 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_adj_kernel(const AdjPar
     }
 
     // ---- finalize: chain rule to the model parameters, loss, penalty, outputs
+    if (P.a_start != nullptr && active) {
+#pragma unroll
+        for (int d = 0; d < n; ++d) P.a_start[(cidx * N + i) * n + d] = a[d];
+    }
+    if (P.skip_grads) return;
     double g[NOUT];
-    M.finalize(Gt, P.mp, i, g);
-    double loss = (MODE == ADJ_MSE) ? sqt / (double)T : 0.0;
+    M.finalize(Gt, P.mp, i, g);  // linear in the accumulators, so per-chunk results simply add
+    double loss = (MODE == ADJ_MSE) ? sqt / (double)P.T : 0.0;
+    if (P.chunk_acc != nullptr) {
+        if (active) {
+            double *acc = P.chunk_acc + i * (NOUT + 1);
+#pragma unroll
+            for (int j = 0; j < NOUT; ++j) atomicAdd(acc + j, g[j]);
+            atomicAdd(acc + NOUT, loss);
+            if (P.g_x0 != nullptr && cidx == 0) {
+#pragma unroll
+                for (int d = 0; d < n; ++d) P.g_x0[i * n + d] = a[d];
+            }
+        }
+        return;
+    }
     if (MODE == ADJ_MSE && P.lb != nullptr && P.ub != nullptr && !P.shared_theta) {
         if constexpr (Model::HAS_BOX) {  // RC parameter box (3-inverse.py:66-85, 103-107; normaliser = ub)
             const float *th = P.mp.theta + i * P.mp.stride;
@@ -376,6 +411,49 @@ __global__ void shared_finalize_kernel(const double *acc, typename Model::Ptrs m
         if (dst) *dst = (float)g;
     }
     if (MODE == ADJ_MSE && loss) *loss = (float)L;
+}
+
+// Chunked launches: turns the per-system fp64 sums over chunks into the caller's outputs (penalty added
+// here); with shared parameters the per-system values are reduced into shared_acc first.
+template <class Model>
+__global__ void chunk_finalize_kernel(const double *chunk_acc, typename Model::Ptrs mp, typename Model::GradPtrs gp,
+                                      const float *lb, const float *ub, float *loss, double *shared_acc, int64_t N,
+                                      int shared_theta) {
+    constexpr int NOUT = Model::NOUT;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = i < N;
+    double g[NOUT], L = 0.0;
+#pragma unroll
+    for (int j = 0; j < NOUT; ++j) g[j] = active ? chunk_acc[i * (NOUT + 1) + j] : 0.0;
+    if (active) L = chunk_acc[i * (NOUT + 1) + NOUT];
+    if (!shared_theta) {
+        if (!active) return;
+        if constexpr (Model::HAS_BOX) {
+            if (lb != nullptr && ub != nullptr) {
+                const float *th = mp.theta + i * mp.stride;
+#pragma unroll
+                for (int j = 0; j < NOUT; ++j) {
+                    const double t = (double)th[j], lo = (double)lb[j], hi = (double)ub[j];
+                    if (t > hi) { L += (t - hi) / hi; g[j] += 1.0 / hi; }
+                    if (t < lo) { L += (lo - t) / hi; g[j] -= 1.0 / hi; }
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NOUT; ++j) {
+            float *dst = Model::grad_addr(gp, i, j);
+            if (dst) *dst = (float)g[j];
+        }
+        if (loss) loss[i] = (float)L;
+    } else {
+#pragma unroll
+        for (int j = 0; j < NOUT; ++j) {
+            const double v = warp_sum(g[j]);
+            if ((threadIdx.x & 31) == 0) atomicAdd(shared_acc + j, v);
+        }
+        const double v = warp_sum(L);
+        if ((threadIdx.x & 31) == 0) atomicAdd(shared_acc + NOUT, v);
+    }
 }
 
 }  // namespace dynax

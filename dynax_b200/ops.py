@@ -107,11 +107,13 @@ def rc_forward(theta, x0, u, dt, emit_x=True, emit_y=True, emit_final=False, dis
     return xsol, ysol, xfin
 
 
-def rc_loss_grad(theta, x0, u, target, dt, lb=None, ub=None, want_gx0=False, discrete=False):
+def rc_loss_grad(theta, x0, u, target, dt, lb=None, ub=None, want_gx0=False, discrete=False, time_chunks=None):
     """Fused MSE(+box penalty) loss and its gradient (examples/3-inverse.py:96-112) for N candidates.
 
     theta[N,7] -> loss[N], grad[N,7];  theta[7] (shared) -> loss[1] (sum over systems), grad[7].
     target[T,N] or [T] (shared).  Returns (loss, grad, g_x0 or None).
+    ``time_chunks``: None = time-parallel chunked kernels only for small long launches (N <= 4096 and
+    T >= 2048), 0 = never, k > 0 = k chunks.
     """
     x0, u, target = _f32c(x0, "x0"), _f32c(u, "u"), _f32c(target, "target")
     x0, u, N, T, shared_u = _canon_batch(None, x0, u, 3, 5)
@@ -135,12 +137,20 @@ def rc_loss_grad(theta, x0, u, target, dt, lb=None, ub=None, want_gx0=False, dis
     gx0 = torch.empty((N, 3), dtype=torch.float32, device=dev) if want_gx0 else None
     flags = ((SHARED_THETA if shared_th else 0) | (SHARED_U if shared_u else 0) |
              (SHARED_TARGET if shared_tg else 0) | (DISCRETE if discrete else 0))
-    nbytes = lib().dynax_workspace_bytes(_lib.OP_RC_LOSS_GRAD, N, T, 3, 5, 1, flags)
-    ws = _ws(nbytes, dev)
+    if time_chunks is None:
+        time_chunks = -1 if (not discrete and 0 < N <= 4096 and T >= 2048) else 0
     with torch.cuda.device(dev):
-        check(lib().dynax_rc_loss_grad_f32(_ptr(theta), _ptr(x0), _ptr(u), _ptr(target), _ptr(lb), _ptr(ub),
-                                           _ptr(loss), _ptr(grad), _ptr(gx0), N, T, float(dt), flags,
-                                           _ptr(ws), ws.numel(), _stream()))
+        if time_chunks != 0 and not discrete and N > 0:
+            chunk_len = 0 if time_chunks < 0 else -(-T // int(time_chunks))
+            ws = _ws(lib().dynax_rc_loss_grad_chunked_workspace(N, T, chunk_len), dev)
+            check(lib().dynax_rc_loss_grad_chunked_f32(_ptr(theta), _ptr(x0), _ptr(u), _ptr(target), _ptr(lb), _ptr(ub),
+                                                       _ptr(loss), _ptr(grad), _ptr(gx0), N, T, float(dt), flags,
+                                                       chunk_len, _ptr(ws), ws.numel(), _stream()))
+        else:
+            ws = _ws(lib().dynax_workspace_bytes(_lib.OP_RC_LOSS_GRAD, N, T, 3, 5, 1, flags), dev)
+            check(lib().dynax_rc_loss_grad_f32(_ptr(theta), _ptr(x0), _ptr(u), _ptr(target), _ptr(lb), _ptr(ub),
+                                               _ptr(loss), _ptr(grad), _ptr(gx0), N, T, float(dt), flags,
+                                               _ptr(ws), ws.numel(), _stream()))
     if shared_th:
         grad = grad.reshape(7)
     return loss, grad, gx0

@@ -90,6 +90,18 @@ int dynax_rc_forward_chunked_f32(const float *theta, const float *x0, const floa
                                  int64_t N, int64_t T, float dt, uint32_t flags, int64_t chunk_len,
                                  void *ws, size_t ws_bytes, void *stream);
 
+/* Time-parallel variant of dynax_rc_loss_grad_f32 (same outputs within the gradient tolerance) for
+ * launches with few systems and a long horizon (one building over a year: N=1, T=8760).  Forward chunk
+ * boundaries as above; then every chunk's adjoint for a zero terminal value, a backward stitch with
+ * Psi^T, and every chunk's adjoint again from its true terminal value; per-chunk gradient sums are
+ * added per system in fp64.  u is read 5 times, so use it only when N cannot fill the GPU. */
+size_t dynax_rc_loss_grad_chunked_workspace(int64_t N, int64_t T, int64_t chunk_len);
+int dynax_rc_loss_grad_chunked_f32(const float *theta, const float *x0, const float *u, const float *target,
+                                   const float *lb, const float *ub,
+                                   float *loss, float *g_theta, float *g_x0,
+                                   int64_t N, int64_t T, float dt, uint32_t flags, int64_t chunk_len,
+                                   void *ws, size_t ws_bytes, void *stream);
+
 /* Fused loss + reverse-mode gradient of examples/3-inverse.py:96-112 for N candidates:
  *   loss_i = mean_k (ysol_i[k]-target_i[k])^2 + sum_j relu(theta_ij-ub_j)/ub_j + relu(lb_j-theta_ij)/ub_j
  *   g_theta = d loss / d theta   (checkpointed discrete adjoint; == jax.value_and_grad through the scan)

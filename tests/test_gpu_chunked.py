@@ -42,3 +42,39 @@ def test_chunked_shared_inputs_and_flags(T):
     xo, yo, xf = ops.rc_forward(cu(T, th), cu(T, x0), cu(T, u), 3600.0, emit_x=False, emit_y=True, emit_final=True, time_chunks=9)
     x64, y64 = orc.rc_rollout(th, x0, u, 3600.0, np.float64)
     assert xo is None and rel_err(yo.cpu().numpy(), y64) < TRAJ_RTOL and rel_err(xf.cpu().numpy(), x64[-1]) < TRAJ_RTOL
+
+
+@pytest.mark.parametrize("N,Tn,chunks", [(64, 8760, -1), (1, 8760, 40), (130, 1000, 7), (33, 257, 4), (8, 100, 1), (5, 70, 9)])
+def test_chunked_loss_grad_matches_fp64_and_serial(T, N, Tn, chunks):
+    from dynax_b200 import ops
+    from tests.util import assert_grad_parity, assert_loss_parity
+    th, x0, u = orc.synth_theta(N, 113), orc.synth_x0(N, 113), orc.synth_u(Tn, N, 113)
+    target = (22 + np.random.default_rng(9).normal(size=(Tn, N))).astype(np.float32)
+    th[0, 0] = 4.0e4                                                     # penalty branch
+    a = [cu(T, v) for v in (th, x0, u, target)]
+    loss, grad, gx0 = ops.rc_loss_grad(*a, 3600.0, orc.RC_LB, orc.RC_UB, want_gx0=True, time_chunks=chunks)
+    l1, g1, gx1 = ops.rc_loss_grad(*a, 3600.0, orc.RC_LB, orc.RC_UB, want_gx0=True, time_chunks=0)
+    l64, g64 = orc.rc_loss_grad(th, x0, u, target, 3600.0, orc.RC_LB, orc.RC_UB)
+    lbud, gbud = orc.rc_output_sensitivity_budget(th, x0, u, target, 3600.0)
+    assert_loss_parity(loss.cpu().numpy(), l64, lbud)
+    assert_grad_parity(grad.cpu().numpy(), g64, gbud)
+    assert rel_err(gx0.cpu().numpy(), gx1.cpu().numpy(), floor=1.0) < 1e-4
+    assert np.allclose(loss.cpu().numpy(), l1.cpu().numpy(), rtol=2e-5)
+
+
+def test_chunked_loss_grad_shared_modes(T):
+    from dynax_b200 import ops
+    from tests.util import assert_grad_parity, assert_loss_parity
+    N, Tn = 48, 3000
+    th, x0, u = orc.synth_theta(N, 114), orc.synth_x0(N, 114), orc.synth_u(Tn, N, 114)
+    target = (22 + np.random.default_rng(10).normal(size=(Tn, N))).astype(np.float32)
+    # shared theta (sum over systems, penalty once) + shared u + shared target
+    th1 = th[0].copy(); th1[6] = 60.0
+    loss, grad, _ = ops.rc_loss_grad(cu(T, th1), cu(T, x0), cu(T, u[:, 0]), cu(T, target[:, 0]), 3600.0,
+                                     orc.RC_LB, orc.RC_UB, time_chunks=10)
+    l64, g64 = orc.rc_loss_grad(np.repeat(th1[None], N, 0), x0, u[:, :1], target[:, :1], 3600.0)
+    lbud, gbud = orc.rc_output_sensitivity_budget(np.repeat(th1[None], N, 0), x0, u[:, :1], target[:, :1], 3600.0)
+    pen = orc.bound_penalty(th1[None], orc.RC_LB, orc.RC_UB)[0]
+    peng = orc.bound_penalty_grad(th1[None], orc.RC_LB, orc.RC_UB)[0]
+    assert_loss_parity(loss.cpu().numpy()[0], l64.sum() + pen, lbud.sum())
+    assert_grad_parity(grad.cpu().numpy(), g64.sum(0) + peng, gbud.sum(0))

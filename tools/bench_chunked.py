@@ -19,3 +19,19 @@ for N in (1, 128, 1024, 8192, 32768):
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 5
         print(f"N={N:6d} T={T} {name:8s} {ms:8.3f} ms  {N*T/ms*1e3:.3e} steps/s", flush=True)
+
+print("--- loss+grad")
+for N in (1, 128, 1024, 4096, 8192):
+    th = torch.tensor(NOM, device="cuda")[None].repeat(N, 1)
+    x0 = torch.tensor([[20.0, 30.0, 26.0]], device="cuda").repeat(N, 1)
+    u = torch.rand((T, N, 5), device="cuda"); tg = 20 + torch.rand((T, N), device="cuda")
+    for name, tc in (("serial", 0), ("chunked", -1)):
+        for _ in range(2):
+            ops.rc_loss_grad(th, x0, u, tg, 3600.0, time_chunks=tc)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            ops.rc_loss_grad(th, x0, u, tg, 3600.0, time_chunks=tc)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        print(f"N={N:6d} T={T} loss+grad {name:8s} {ms:8.3f} ms  {N*T/ms*1e3:.3e} steps/s", flush=True)
