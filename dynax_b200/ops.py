@@ -522,3 +522,55 @@ def resample_mean(x, factor):
     with torch.cuda.device(x.device):
         check(lib().dynax_resample_mean_f32(_ptr(x), _ptr(out), rows, cols, int(factor), _stream()))
     return out
+
+
+def node_rk4_vjp(W1, b1, W2, b2, W3, b3, x0, u, xsol, dt, g_xsol=None, g_ysol=None, need_u=True, euler=False):
+    """VJP of node_rk4_forward: returns (gW1, gb1, gW2, gb2, gW3, gb3, g_x0, g_u)."""
+    ws_ = [_f32c(t, nm) for t, nm in ((W1, "W1"), (b1, "b1"), (W2, "W2"), (b2, "b2"), (W3, "W3"), (b3, "b3"))]
+    x0, u, xsol = _f32c(x0, "x0"), _f32c(u, "u"), _f32c(xsol, "xsol")
+    hidden, n = ws_[1].numel(), ws_[5].numel()
+    m = ws_[0].shape[1] - n
+    N = x0.shape[0]
+    if u.dim() == 2:
+        u = u[:, None, :].expand(u.shape[0], N, m).contiguous()
+    T = u.shape[0]
+    dev = x0.device
+    if g_xsol is not None:
+        g_xsol = _f32c(g_xsol, "g_xsol").reshape(T, N, n)
+    if g_ysol is not None:
+        g_ysol = _f32c(g_ysol, "g_ysol").reshape(T, N, 1)
+    gw = [torch.empty_like(t) for t in ws_]
+    gx0 = torch.empty((N, n), dtype=torch.float32, device=dev)
+    gu = torch.empty((T, N, m), dtype=torch.float32, device=dev) if need_u else None
+    wsb = _ws(lib().dynax_node_rk4_vjp_workspace(), dev)
+    with torch.cuda.device(dev):
+        check(lib().dynax_node_rk4_vjp_f32(*[_ptr(t) for t in ws_], _ptr(x0), _ptr(u), _ptr(xsol), _ptr(g_xsol),
+                                           _ptr(g_ysol), *[_ptr(t) for t in gw], _ptr(gx0), _ptr(gu), N, T, n, m, 1,
+                                           hidden, float(dt), _lib.SOLVER_EULER if euler else 0, _ptr(wsb), wsb.numel(),
+                                           _stream()))
+    return (*gw, gx0, gu)
+
+
+class _NodeRollout(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, W1, b1, W2, b2, W3, b3, x0, u, dt, euler):
+        xsol, ysol, _ = node_rk4_forward(W1, b1, W2, b2, W3, b3, x0, u, dt, euler=euler)
+        ctx.save_for_backward(W1, b1, W2, b2, W3, b3, x0, u, xsol)
+        ctx.dt, ctx.euler = dt, euler
+        return xsol, ysol
+
+    @staticmethod
+    def backward(ctx, g_xsol, g_ysol):
+        *W, x0, u, xsol = ctx.saved_tensors
+        if g_xsol is None and g_ysol is None:
+            return (None,) * 10
+        out = node_rk4_vjp(*W, x0, u, xsol, ctx.dt, g_xsol, g_ysol, need_u=ctx.needs_input_grad[7], euler=ctx.euler)
+        gu = out[7]
+        if gu is not None and u.dim() == 2:
+            gu = gu.sum(1)
+        return (*out[:6], out[6], gu, None, None)
+
+
+def node_rollout(W1, b1, W2, b2, W3, b3, x0, u, dt, euler=False):
+    """Differentiable MLP-dynamics rollout (RK4 or Euler): xsol[T,N,3], ysol[T,N,1]."""
+    return _NodeRollout.apply(W1, b1, W2, b2, W3, b3, x0, u, float(dt), bool(euler))

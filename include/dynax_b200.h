@@ -175,6 +175,19 @@ int dynax_node_rk4_forward_f32(const float *W1, const float *b1, const float *W2
                                int64_t N, int64_t T, int n, int m, int p, int hidden, float dt,
                                uint32_t flags, void *stream);
 
+/* Reverse-mode gradient of dynax_node_rk4_forward_f32 (exact discrete adjoint of RK4 / Euler): cotangents
+ * g_xsol:[T,N,3] and/or g_ysol:[T,N,1] in; weight gradients (summed over systems, each may be NULL),
+ * g_x0:[N,3], g_u:[T,N,5] out.  xsol is the forward trajectory (x_{k+1} at row k).  CUDA-core kernel.
+ * ws: dynax_node_rk4_vjp_workspace() bytes.  PARITY UNPINNED BY THE REFERENCE. */
+size_t dynax_node_rk4_vjp_workspace(void);
+int dynax_node_rk4_vjp_f32(const float *W1, const float *b1, const float *W2, const float *b2,
+                           const float *W3, const float *b3, const float *x0, const float *u, const float *xsol,
+                           const float *g_xsol, const float *g_ysol,
+                           float *gW1, float *gb1, float *gW2, float *gb2, float *gW3, float *gb3,
+                           float *g_x0, float *g_u,
+                           int64_t N, int64_t T, int n, int m, int p, int hidden, float dt, uint32_t flags,
+                           void *ws, size_t ws_bytes, void *stream);
+
 /* ---- Sampling-based MPC (BASELINE.json config 4): cost of N candidate control sequences u[H,N] through
  *      ONE shared 4R3C model.  Inputs per step are assembled as the RC env does,
  *      [d_k0, d_k1, u_k, d_k2, d_k3] (dynax/wrapper/envs/rc.py:131), rolled out by simulator.py:36-43, and

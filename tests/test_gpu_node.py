@@ -72,3 +72,39 @@ def test_unsupported_dims(T):
     with pytest.raises(DynaxError) as e:
         ops.node_rk4_forward(*(cu(T, w) for w in W), cu(T, x0), cu(T, u), 0.1)
     assert e.value.code == -2
+
+
+def _torch_node_rollout(T, W, x0, u, dt, euler):
+    W1, b1, W2, b2, W3, b3 = W
+    f = lambda x, uk: T.tanh(T.tanh(T.cat([x, uk], -1) @ W1.T + b1) @ W2.T + b2) @ W3.T + b3
+    x = x0; xs, ys = [], []
+    for k in range(u.shape[0]):
+        ys.append(x[:, :1])
+        k1 = f(x, u[k])
+        if euler:
+            x = x + dt * k1
+        else:
+            k2 = f(x + 0.5 * dt * k1, u[k]); k3 = f(x + 0.5 * dt * k2, u[k]); k4 = f(x + dt * k3, u[k])
+            x = x + dt / 6 * (k1 + 2 * k2 + 2 * k3 + k4)
+        xs.append(x)
+    return T.stack(xs), T.stack(ys)
+
+
+@pytest.mark.parametrize("N,Tn,euler,scale", [(200, 24, False, 0.5), (130, 17, True, 1.0), (3, 5, False, 0.3), (256, 40, False, 0.1)])
+def test_vjp_matches_torch_autograd_fp64(T, N, Tn, euler, scale):
+    """Oracle = torch autograd (fp64, CPU) over the restated RK4-MLP rollout (the reference has neither)."""
+    from dynax_b200 import ops
+    Wnp = orc.synth_mlp(109, scale=scale)
+    x0, u = inputs(N, Tn, 110)
+    rng = np.random.default_rng(111)
+    gx = rng.normal(size=(Tn, N, 3)).astype(np.float32); gy = rng.normal(size=(Tn, N, 1)).astype(np.float32)
+    Wd = [T.tensor(w, dtype=T.float64, requires_grad=True) for w in Wnp]
+    x0d = T.tensor(x0, dtype=T.float64, requires_grad=True); ud = T.tensor(u, dtype=T.float64, requires_grad=True)
+    xs, ys = _torch_node_rollout(T, Wd, x0d, ud, 0.25, euler)
+    ((xs * T.tensor(gx, dtype=T.float64)).sum() + (ys * T.tensor(gy, dtype=T.float64)).sum()).backward()
+    Wc = [cu(T, w).requires_grad_(True) for w in Wnp]
+    x0c = cu(T, x0).requires_grad_(True); uc = cu(T, u).requires_grad_(True)
+    xs_c, ys_c = ops.node_rollout(*Wc, x0c, uc, 0.25, euler=euler)
+    ((xs_c * cu(T, gx)).sum() + (ys_c * cu(T, gy)).sum()).backward()
+    for got, ref, nm in zip(Wc + [x0c, uc], Wd + [x0d, ud], ["W1", "b1", "W2", "b2", "W3", "b3", "x0", "u"]):
+        assert rel_err(got.grad.cpu().numpy(), ref.grad.numpy(), floor=1.0) < 1e-4, nm
