@@ -101,6 +101,24 @@ class ClockSampler:
         return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this rank to the CPUs NVML reports as local to its GPU, so first-touch places the pinned
+    host buffers of the e2e leg on the GPU's NUMA node (8 ranks otherwise share one node's memory)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, mask in enumerate(words) for b in range(64) if (mask >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"bound to {len(cpus)} GPU-local cpus"
+    except Exception as e:  # not fatal: only a placement hint
+        return f"no numa binding ({type(e).__name__})"
+    return "no numa binding (empty intersection)"
+
+
 def measured_peak():
     try:
         return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured"
@@ -179,6 +197,7 @@ def ours(a):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_note = bind_to_gpu_numa_node(local) if world > 1 else None   # pinned e2e buffers land next to the GPU
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -262,7 +281,8 @@ def ours(a):
                "h2d_bytes_per_step": int(hu.numel() + ht.numel() + hth.numel() + hx0.numel()) * 4,
                "d2h_bytes_per_step": int(l_h.size + g_h.size) * 4,
                "systems_per_step": Ne, "ms_per_step": e_sec / a.e2e_steps * 1e3,
-               "api": "dynax_rc_loss_grad_host_f32 (pinned host buffers; tiled H2D/kernel/D2H on 2 streams)"}
+               "api": "dynax_rc_loss_grad_host_f32 (pinned host buffers; tiled H2D/kernel/D2H on 2 streams)",
+               "numa": numa_note}
         # informational: the same loss+gradient when the disturbances are ONE shared series and only the
         # control channel is per system: 8 instead of 24 B/step over PCIe
         hc = torch.empty((T, Ne), dtype=torch.float32, pin_memory=True)

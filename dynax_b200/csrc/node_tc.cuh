@@ -12,7 +12,8 @@
 //
 // fp32-grade accuracy from TF32 tensor cores: every operand is split a = a_hi + a_lo (a_hi = top 19
 // bits), and a.b ~= a_hi.b_hi + a_lo.b_hi + a_hi.b_lo (3 MMAs, error ~2^-21 relative); accumulation
-// is fp32 in TMEM.  tanh = 1 - 2/(2^(2x log2 e) + 1) with ex2.approx/rcp.approx (abs error ~4e-7):
+// is fp32 in TMEM.  tanh = 1 - 2/(2^(2x log2 e) + 1) with ex2.approx/rcp.approx (abs error ~5e-7),
+// evaluated in pairs that share one reciprocal (3 MUFU ops per 2 tanh):
 // MUFU.TANH's 2^-11 would break the 1e-5 trajectory tolerance.
 //
 // u rows / x,y rows stream through the same TMA (cp.async.bulk) + mbarrier rings as rollout_fwd_kernel.
@@ -101,11 +102,17 @@ __device__ __forceinline__ void split_tf32(float a, uint32_t &hi, uint32_t &lo) 
     lo = __float_as_uint(a - __uint_as_float(hi));
 }
 
-__device__ __forceinline__ float fast_tanh(float x) {
-    float e, r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.885390081777927f));  // 2^(2x log2 e) = e^(2x)
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
-    return fmaf(-2.0f, r, 1.0f);
+// Two tanh for THREE MUFU ops (the kernel is bound by the MUFU pipe): tanh(x) = 1 - 2/(e^{2x}+1) and the two
+// reciprocals share one rcp:  r = 1/(a b),  1/a = r b,  1/b = r a.  The exponent is clamped at 2^60 so
+// a*b stays finite (tanh is 1 to fp32 precision far below that).
+__device__ __forceinline__ void fast_tanh2(float x0, float x1, float &t0, float &t1) {
+    float e0, e1, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fminf(x0 * 2.885390081777927f, 60.f)));  // e^(2x)
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fminf(x1 * 2.885390081777927f, 60.f)));
+    const float a = e0 + 1.0f, b = e1 + 1.0f;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a * b));
+    t0 = fmaf(-2.0f, r * b, 1.0f);
+    t1 = fmaf(-2.0f, r * a, 1.0f);
 }
 
 // shared-memory map (floats unless noted)
@@ -267,7 +274,12 @@ __global__ void __launch_bounds__(tc::TN + 32, 2) node_tc_kernel(const NodeTcPar
             float v[16];
             tmem_ld16(lane_base + COL_D + c, v);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) split_tf32(fast_tanh(v[j] + sm[F_B1 + c + j]), hi[j], lo[j]);
+            for (int j = 0; j < 16; j += 2) {
+                float t0, t1;
+                fast_tanh2(v[j] + sm[F_B1 + c + j], v[j + 1] + sm[F_B1 + c + j + 1], t0, t1);
+                split_tf32(t0, hi[j], lo[j]);
+                split_tf32(t1, hi[j + 1], lo[j + 1]);
+            }
             tmem_st16(lane_base + COL_AHI + c, hi);
             tmem_st16(lane_base + COL_ALO + c, lo);
         }
@@ -299,10 +311,14 @@ __global__ void __launch_bounds__(tc::TN + 32, 2) node_tc_kernel(const NodeTcPar
             float v[16];
             tmem_ld16(lane_base + COL_D + c, v);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const float h = fast_tanh(v[j] + sm[F_B2 + c + j]);
+            for (int j = 0; j < 16; j += 2) {
+                float h0, h1;
+                fast_tanh2(v[j] + sm[F_B2 + c + j], v[j + 1] + sm[F_B2 + c + j + 1], h0, h1);
 #pragma unroll
-                for (int d = 0; d < NX; ++d) r[d] = fmaf(sm[F_W3 + d * HID + c + j], h, r[d]);
+                for (int d = 0; d < NX; ++d) {
+                    r[d] = fmaf(sm[F_W3 + d * HID + c + j], h0, r[d]);
+                    r[d] = fmaf(sm[F_W3 + d * HID + c + j + 1], h1, r[d]);
+                }
             }
         }
     };
