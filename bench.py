@@ -28,7 +28,7 @@ sys.path.insert(0, ROOT)
 T_YEAR = 8760
 DT = 3600.0
 B_ALG = 48            # algorithmic bytes / system-step, fwd+grad: u and target once per sweep
-WAVE = 148 * 2 * 128  # systems per full wave of the adjoint kernel (2 CTAs/SM x 128 systems)
+WAVE = 148 * 3 * 128  # systems per full wave of the adjoint kernel (3 CTAs/SM x 128 systems)
 NOMINAL = [10384.31640625, 499089.09375, 1321535.125, 1.5348844528198242, 0.5000327825546265,
            1.000040054321289, 20.119935989379883]
 
@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--systems", type=int, default=1 << 20, help="systems per rank per step")
     ap.add_argument("--T", type=int, default=T_YEAR)
-    ap.add_argument("--tile", type=int, default=3 * WAVE, help="systems per kernel launch")
+    ap.add_argument("--tile", type=int, default=4 * WAVE, help="systems per kernel launch")
     ap.add_argument("--e2e-systems", type=int, default=32768)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-systems", type=int, default=8192, help="bounded CPU-baseline sample")
@@ -315,7 +315,7 @@ def ours(a):
     traffic = ncu_traffic_per_step()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs, copy bandwidth)" if peak_kind == "measured" else "fallback 6.65 TB/s",
-                "kernel": "rollout_adj_kernel<RCModel,128,16,2,MSE>", "alg_bytes_per_system_step": B_ALG,
+                "kernel": "rollout_adj_kernel<RCModel,128,12,2,MSE>", "alg_bytes_per_system_step": B_ALG,
                 "alg_bytes_per_launch": B_ALG * tile * T, "avg_launch_ms": ms / launches,
                 "traffic": (traffic or {}).get("dram_bytes_per_launch"), "traffic_note": (traffic or {}).get("note")}
 

@@ -281,8 +281,8 @@ int dynax_rc_loss_grad_chunked_f32(const float *theta, const float *x0, const fl
     auto launch = [&](const AdjParams<RCModel> &Q) {
         if (su && stg) return launch_adj<RCModel, 128, 16, 4, ADJ_MSE, true, true, 2>(Q, st);
         if (su) return launch_adj<RCModel, 128, 16, 4, ADJ_MSE, true, false, 2>(Q, st);
-        if (stg) return launch_adj<RCModel, 128, 16, 2, ADJ_MSE, false, true, 2>(Q, st);
-        return launch_adj<RCModel, 128, 16, 2, ADJ_MSE, false, false, 2>(Q, st);
+        if (stg) return launch_adj<RCModel, 128, 12, 2, ADJ_MSE, false, true, 3>(Q, st);
+        return launch_adj<RCModel, 128, 12, 2, ADJ_MSE, false, false, 3>(Q, st);
     };
     AdjParams<RCModel> B1 = A;
     B1.a_term = nullptr; B1.a_start = W.w; B1.skip_grads = 1;

@@ -54,7 +54,7 @@ def main():
     u3 = torch.empty((T, N3, 5), device=dev).uniform_(0, 1, generator=g); u3[..., 0] = 15 + 10 * u3[..., 0]
     tg3 = 20 + 2 * torch.empty((T, N3), device=dev).uniform_(0, 1, generator=g)
     s = timeit(lambda: ops.rc_loss_grad(th[:N3], x0[:N3], u3, tg3, 3600.0), a.iters)
-    emit("config3 inverse loss+grad, per-system u/target", N3 * T, s, 48, N=N3, T=T, kernel="rollout_adj_kernel<RCModel,128,16,2,MSE>")
+    emit("config3 inverse loss+grad, per-system u/target", N3 * T, s, 48, N=N3, T=T, kernel="rollout_adj_kernel<RCModel,128,12,2,MSE>")
     us, ts_ = u3[:, 0].contiguous(), tg3[:, 0].contiguous()
     s = timeit(lambda: ops.rc_loss_grad(th[:N3], x0[:N3], us, ts_, 3600.0), a.iters)
     emit("config3 inverse loss+grad, shared u/target (compute-bound)", N3 * T, s, None, N=N3, T=T)
