@@ -18,11 +18,17 @@ from ..core.base_block_state_space import BaseBlockSSM
 
 
 class DifferentiableSimulator:
-    def __init__(self, model: BaseBlockSSM, dt: float = 1.0, mode_interp: str = "linear", start_time: float = 0.0):
+    def __init__(self, model: BaseBlockSSM, dt: float = 1.0, mode_interp: str = "linear", start_time: float = 0.0,
+                 solver: str = "euler"):
         self.model = model
         self.dt = dt
         self.mode_interp = mode_interp      # dead field in the reference too (simulator.py:15)
         self.start_time = start_time
+        # The reference integrates with explicit Euler only (simulator.py:40).  "rk4" is an extension for
+        # models on the general fx/fy path (NeuralODE, BASELINE.json config 5).
+        if solver not in ("euler", "rk4"):
+            raise ValueError("solver must be 'euler' or 'rk4'")
+        self.solver = solver
 
     # Flax: simulator.init(key, x0, inputs) -> {'params': {'model': ...}}
     def init(self, key, states_init, inputs):
@@ -44,7 +50,10 @@ class DifferentiableSimulator:
                 raise ValueError(f"unbatched call expects inputs[T,{model.input_dim}], got {tuple(u.shape)}")
             u = u[:, None, :]
         params = variables["params"]["model"]
-        xsol, ysol = model._rollout(params, x0, u, float(self.dt), False)   # simulator.py:40 always Euler
+        if self.solver == "rk4":
+            xsol, ysol = model._rollout(params, x0, u, float(self.dt), False, solver="rk4")
+        else:
+            xsol, ysol = model._rollout(params, x0, u, float(self.dt), False)   # simulator.py:40 always Euler
         if not batched:
             xsol, ysol = xsol[:, 0], ysol[:, 0]
         return xsol, ysol
