@@ -44,6 +44,7 @@ SIGNATURES = {
     "dynax_rc_loss_grad_chunked_f32": (_int, [_f] * 9 + [_i64, _i64, _flt, _u32, _i64, _f, _sz, _f]),
     "dynax_lamb_update_f32": (_int, [_f] * 4 + [_i64, _i64, _flt, _flt, _flt, _flt, _f]),
     "dynax_resample_mean_f32": (_int, [_f, _f, _i64, _int, _i64, _f]),
+    "dynax_lamb_update_dev_f32": (_int, [_f] * 4 + [_i64, _f, _flt, _flt, _flt, _flt, _f]),
     "dynax_rc_env_step_f32": (_int, [_f] * 6 + [_i64] + [_f] * 3 + [_flt] * 5 + [_int] + [_f] * 7 + [_i64, _i64, _flt, _u32, _f]),
     "dynax_rc_loss_grad_ctrl_host_f32": (_int, [_f] * 4 + [_int] + [_f] * 5 + [_i64, _i64, _flt, _u32, _i64]),
     "dynax_rc_forward_ctrl_f32": (_int, [_f] * 4 + [_int] + [_f] * 3 + [_i64, _i64, _flt, _u32, _f]),

@@ -31,6 +31,29 @@ __global__ void lamb_update_kernel(float *theta, const float *grad, float *m, fl
     theta[i] = th - lr * trust * u;
 }
 
+// Same update with the epoch number kept ON THE DEVICE (incremented by the kernel), so that a captured
+// CUDA graph of {loss+grad, update} can be replayed without any host-side parameter changing.
+__global__ void lamb_update_dev_kernel(float *theta, const float *grad, float *m, float *v, int64_t n, int64_t *step,
+                                       float lr, float b1, float b2, float eps) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t t = *step + 1;  // 1-based epoch of this update
+    if (i < n) {
+        const float bc1 = 1.f - powf(b1, (float)t), bc2 = 1.f - powf(b2, (float)t);
+        const float g = grad[i];
+        const float mi = b1 * m[i] + (1.f - b1) * g;
+        const float vi = b2 * v[i] + (1.f - b2) * g * g;
+        m[i] = mi;
+        v[i] = vi;
+        const float u = (mi / bc1) / (sqrtf(vi / bc2) + eps);
+        const float th = theta[i];
+        const float pn = fabsf(th), un = fabsf(u);
+        const float trust = (pn == 0.f || un == 0.f) ? 1.f : pn / un;
+        theta[i] = th - lr * trust * u;
+    }
+}
+
+__global__ void bump_step_kernel(int64_t *step) { *step += 1; }
+
 __global__ void resample_mean_kernel(const float *in, float *out, int64_t rows, int cols, int64_t factor,
                                      int64_t out_rows) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -60,6 +83,22 @@ int dynax_lamb_update_f32(float *theta, const float *grad, float *m, float *v, i
     const int tb = 256;
     lamb_update_kernel<<<(unsigned)((n + tb - 1) / tb), tb, 0, static_cast<cudaStream_t>(stream)>>>(
         theta, grad, m, v, n, lr, b1, b2, eps, bc1, bc2);
+    DYNAX_CUDA_TRY(cudaGetLastError());
+    return DYNAX_OK;
+}
+
+int dynax_lamb_update_dev_f32(float *theta, const float *grad, float *m, float *v, int64_t n, int64_t *step_counter,
+                              float lr, float b1, float b2, float eps, void *stream) {
+    if (n < 0) return fail(DYNAX_ERR_INVALID_ARGUMENT, "need n >= 0");
+    if (n == 0) return DYNAX_OK;
+    if (!theta || !grad || !m || !v || !step_counter) return fail(DYNAX_ERR_INVALID_ARGUMENT, "NULL argument");
+    int rc = require_sm100();
+    if (rc != DYNAX_OK) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int tb = 256;
+    lamb_update_dev_kernel<<<(unsigned)((n + tb - 1) / tb), tb, 0, st>>>(theta, grad, m, v, n, step_counter, lr, b1, b2, eps);
+    DYNAX_CUDA_TRY(cudaGetLastError());
+    bump_step_kernel<<<1, 1, 0, st>>>(step_counter);
     DYNAX_CUDA_TRY(cudaGetLastError());
     return DYNAX_OK;
 }

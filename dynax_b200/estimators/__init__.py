@@ -51,12 +51,15 @@ def mse_loss_and_grad(simulator, variables, x0, u, target, params_lb=None, param
 
 
 def calibrate(simulator, variables, x0, u, target, params_lb=None, params_ub=None, n_epochs=5000, lr=1e-3,
-              log_every=0):
+              log_every=0, cuda_graph=False):
     """The training loop of examples/3-inverse.py:117-138 kept entirely on the device (row f-3):
     every epoch = one fused loss+gradient launch + one LAMB update launch, no host round trip.
 
     ``variables`` holds [N] leaves (N candidates calibrated independently) or scalar leaves (one
     candidate).  Returns (variables_fitted, loss[N] of the last epoch).
+    ``cuda_graph=True`` captures one epoch (all kernels of the loss/gradient + the update, epoch counter on
+    the device) into a CUDA graph and replays it: for small batches the epoch is launch-bound and the graph
+    removes the per-launch host cost.
     """
     model = simulator.model
     if not isinstance(model, _RC4R3C):
@@ -77,6 +80,27 @@ def calibrate(simulator, variables, x0, u, target, params_lb=None, params_ub=Non
     lb, ub = _bounds(params_lb, dev), _bounds(params_ub, dev)
     m, v = torch.zeros_like(theta), torch.zeros_like(theta)
     loss = None
+    if cuda_graph and int(n_epochs) > 3:
+        counter = torch.zeros((), dtype=torch.int64, device=dev)
+
+        def epoch_fn():
+            l, g, _ = ops.rc_loss_grad(theta, x0, u, target, float(simulator.dt), lb, ub)
+            ops.lamb_update_dev_(theta, g.contiguous(), m, v, counter, lr)
+            return l
+
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):          # warm-up outside capture (lazy module loads, attribute calls)
+            for _ in range(2):
+                loss = epoch_fn()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            loss = epoch_fn()
+        for _ in range(int(n_epochs) - 3):
+            graph.replay()
+        fitted = {"params": {"model": unstack_theta(theta, leaves)}}
+        return fitted, loss
     for epoch in range(1, int(n_epochs) + 1):
         loss, grad, _ = ops.rc_loss_grad(theta, x0, u, target, float(simulator.dt), lb, ub)
         ops.lamb_update_(theta, grad.contiguous(), m, v, epoch, lr)

@@ -512,6 +512,20 @@ def lamb_update_(theta, grad, m, v, step, lr=1e-3, b1=0.9, b2=0.999, eps=1e-6):
     return theta
 
 
+def lamb_update_dev_(theta, grad, m, v, step_counter, lr=1e-3, b1=0.9, b2=0.999, eps=1e-6):
+    """LAMB update whose epoch number lives in ``step_counter`` (int64 CUDA tensor, incremented by the
+    call) -- the graph-capturable form of :func:`lamb_update_`."""
+    if not (step_counter.is_cuda and step_counter.dtype == torch.int64 and step_counter.numel() == 1):
+        raise ValueError("step_counter must be a 1-element int64 CUDA tensor")
+    for t, nm in ((theta, "theta"), (grad, "grad"), (m, "m"), (v, "v")):
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise ValueError(f"{nm} must be a contiguous float32 CUDA tensor")
+    with torch.cuda.device(theta.device):
+        check(lib().dynax_lamb_update_dev_f32(_ptr(theta), _ptr(grad), _ptr(m), _ptr(v), theta.numel(),
+                                              _ptr(step_counter), float(lr), float(b1), float(b2), float(eps), _stream()))
+    return theta
+
+
 def resample_mean(x, factor):
     """``data.groupby(index // factor).mean()`` (examples/1-forward.py:26-27) for x[rows, cols] on the device."""
     x = _f32c(x, "x")

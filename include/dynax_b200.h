@@ -225,6 +225,10 @@ int dynax_rc_env_step_f32(const float *theta, const float *x, const float *t, co
  *      out[r,:] = mean(in[r*factor : (r+1)*factor, :]), out rows = ceil(rows/factor). ---- */
 int dynax_lamb_update_f32(float *theta, const float *grad, float *m, float *v, int64_t n, int64_t step,
                           float lr, float b1, float b2, float eps, void *stream);
+/* Same update with the epoch number in DEVICE memory (*step_counter = epochs done so far; incremented by
+ * the call), so a CUDA graph capturing {dynax_rc_loss_grad_f32, dynax_lamb_update_dev_f32} replays as is. */
+int dynax_lamb_update_dev_f32(float *theta, const float *grad, float *m, float *v, int64_t n, int64_t *step_counter,
+                              float lr, float b1, float b2, float eps, void *stream);
 int dynax_resample_mean_f32(const float *in, float *out, int64_t rows, int cols, int64_t factor, void *stream);
 
 /* ---- Host-buffer entry points (the call a reference user makes with NumPy/JAX-CPU arrays):
