@@ -97,7 +97,7 @@ def calibrate(simulator, variables, x0, u, target, params_lb=None, params_ub=Non
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             loss = epoch_fn()
-        for _ in range(int(n_epochs) - 3):
+        for _ in range(int(n_epochs) - 2):      # capture records without executing: 2 warm-up epochs ran so far
             graph.replay()
         fitted = {"params": {"model": unstack_theta(theta, leaves)}}
         return fitted, loss
