@@ -77,28 +77,32 @@ __global__ void __launch_bounds__(kMpcThreads) rc_mpc_cost_kernel(const MpcParam
     const float dt = P.dt, w1 = P.w_comfort;
     float cost = 0.f;
     const float *up = P.u + ii;
-    for (int64_t k0 = 0; k0 < H; k0 += kMpcUnroll) {
+    // one candidate-step; `s` = this step's shared constants
+    auto step = [&](const MpcStep *s, float uk) {
+        const float4 a = *reinterpret_cast<const float4 *>(s);        // bd0 bd1 bd2 ce
+        const float2 b = *reinterpret_cast<const float2 *>(&s->lo);   // lo hi
+        const float y = x[0];  // pre-update output (simulator.py:38)
+        const float dTz = fmaxf(y - b.y, 0.f) + fmaxf(b.x - y, 0.f);
+        cost = fmaf(a.w, uk, cost);   // energy: w0*price*(-u/COP)*dt/3600
+        cost = fmaf(w1, dTz, cost);
+        const float r0 = (M.A00 * x[0] + M.A02 * x[2]) + (a.x + M.B02 * uk);
+        const float r1 = (M.A11 * x[1] + M.A12 * x[2]) + a.y;
+        const float r2 = (M.A20 * x[0] + M.A21 * x[1] + M.A22 * x[2]) + a.z;
+        x[0] = fmaf(dt, r0, x[0]);
+        x[1] = fmaf(dt, r1, x[1]);
+        x[2] = fmaf(dt, r2, x[2]);
+    };
+    // full blocks of kMpcUnroll steps carry no per-step predicate (8 loads in flight, then 8 steps) ...
+    const int64_t Hfull = H - (H % kMpcUnroll);
+    for (int64_t k0 = 0; k0 < Hfull; k0 += kMpcUnroll) {
         float uu[kMpcUnroll];
 #pragma unroll
-        for (int j = 0; j < kMpcUnroll; ++j) uu[j] = (k0 + j < H) ? __ldcs(up + (k0 + j) * N) : 0.f;
+        for (int j = 0; j < kMpcUnroll; ++j) uu[j] = __ldcs(up + (k0 + j) * N);
 #pragma unroll
-        for (int j = 0; j < kMpcUnroll; ++j) {
-            if (k0 + j < H) {
-                const float4 a = *reinterpret_cast<const float4 *>(&tab[k0 + j]);        // bd0 bd1 bd2 ce
-                const float2 b = *reinterpret_cast<const float2 *>(&tab[k0 + j].lo);     // lo hi
-                const float y = x[0];  // pre-update output (simulator.py:38)
-                const float dTz = fmaxf(y - b.y, 0.f) + fmaxf(b.x - y, 0.f);
-                cost = fmaf(a.w, uu[j], cost);   // energy: w0*price*(-u/COP)*dt/3600
-                cost = fmaf(w1, dTz, cost);
-                const float r0 = (M.A00 * x[0] + M.A02 * x[2]) + (a.x + M.B02 * uu[j]);
-                const float r1 = (M.A11 * x[1] + M.A12 * x[2]) + a.y;
-                const float r2 = (M.A20 * x[0] + M.A21 * x[1] + M.A22 * x[2]) + a.z;
-                x[0] = fmaf(dt, r0, x[0]);
-                x[1] = fmaf(dt, r1, x[1]);
-                x[2] = fmaf(dt, r2, x[2]);
-            }
-        }
+        for (int j = 0; j < kMpcUnroll; ++j) step(&tab[k0 + j], uu[j]);
     }
+    // ... and the ragged tail goes step by step
+    for (int64_t k = Hfull; k < H; ++k) step(&tab[k], __ldcs(up + k * N));
     if (active) P.cost[i] = cost;
     if (P.best != nullptr) {
         unsigned long long key = active ? (((unsigned long long)order_bits(cost) << 32) | (unsigned long long)(uint32_t)i)
