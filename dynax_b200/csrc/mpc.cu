@@ -85,9 +85,12 @@ __global__ void __launch_bounds__(kMpcThreads) rc_mpc_cost_kernel(const MpcParam
         const float dTz = fmaxf(y - b.y, 0.f) + fmaxf(b.x - y, 0.f);
         cost = fmaf(a.w, uk, cost);   // energy: w0*price*(-u/COP)*dt/3600
         cost = fmaf(w1, dTz, cost);
-        const float r0 = (M.A00 * x[0] + M.A02 * x[2]) + (a.x + M.B02 * uk);
-        const float r1 = (M.A11 * x[1] + M.A12 * x[2]) + a.y;
-        const float r2 = (M.A20 * x[0] + M.A21 * x[1] + M.A22 * x[2]) + a.z;
+        // rhs = A x + B u as single FMA chains seeded with the shared (B d_k) term: 8 FMAs instead of 11 ops
+        // (this kernel is bound by FP32 issue slots; the summation order differs from fxx(x)+fxu(u) by
+        // rounding only, far inside the 1e-5 tolerance)
+        const float r0 = fmaf(M.A02, x[2], fmaf(M.A00, x[0], fmaf(M.B02, uk, a.x)));
+        const float r1 = fmaf(M.A12, x[2], fmaf(M.A11, x[1], a.y));
+        const float r2 = fmaf(M.A22, x[2], fmaf(M.A21, x[1], fmaf(M.A20, x[0], a.z)));
         x[0] = fmaf(dt, r0, x[0]);
         x[1] = fmaf(dt, r1, x[1]);
         x[2] = fmaf(dt, r2, x[2]);
