@@ -137,8 +137,20 @@ static int rc_adjoint(const float *theta, const float *x0, const float *u, const
         if (su) return launch_adj<RCModel, 128, 16, 4, ADJ_MSE, true, false, 2>(P, st);
         if (stg) return launch_adj<RCModel, 128, 12, 2, ADJ_MSE, false, true, 3>(P, st);
         // Tile shapes measured on B200 (bench.py, N=2^20, T=8760, same box): KC=12 keeps 3 CTAs per SM
-        // (74 KB smem, 128 regs) and is ~4 % faster than KC=16 with 2 CTAs per SM.
-        switch (env_int("DYNAX_ADJ_CFG", 0)) {
+        // (74 KB smem, 128 regs) and is ~4 % faster than KC=16 with 2 CTAs per SM when the grid fills whole
+        // waves -- but every CTA runs for the whole horizon, so a launch costs ceil(CTAs/slots) full waves.
+        // Pick the shape whose wave quantisation wastes less (N=65536: 512 CTAs = 1.15 waves of 444 slots
+        // but 1.73 waves of 296; measured 5.6 ms vs 4.7 ms).  DYNAX_ADJ_CFG >= 0 forces a shape.
+        int cfg = env_int("DYNAX_ADJ_CFG", -1);
+        if (cfg < 0) {
+            DeviceInfo di;
+            rc = device_info(&di);
+            if (rc != DYNAX_OK) return rc;
+            const int64_t ctas = (N + 127) / 128, s3 = 3ll * di.sm_count, s2 = 2ll * di.sm_count;
+            const double cost3 = (double)((ctas + s3 - 1) / s3 * s3) / 1.04, cost2 = (double)((ctas + s2 - 1) / s2 * s2);
+            cfg = (ctas <= s3 || cost3 <= cost2) ? 0 : 1;
+        }
+        switch (cfg) {
             default:
             case 0: return launch_adj<RCModel, 128, 12, 2, ADJ_MSE, false, false, 3>(P, st);
             case 1: return launch_adj<RCModel, 128, 16, 2, ADJ_MSE, false, false, 2>(P, st);
