@@ -27,8 +27,16 @@ sys.path.insert(0, ROOT)
 
 T_YEAR = 8760
 DT = 3600.0
-B_ALG = 48            # algorithmic bytes / system-step, fwd+grad: u and target once per sweep
-WAVE = 148 * 3 * 128  # systems per full wave of the adjoint kernel (3 CTAs/SM x 128 systems)
+# The library computes the loss+gradient with one of two kernels:
+#   tangent  forward-mode sensitivities in ONE sweep: u (20 B) + target (4 B) per system-step  -> 24 B
+#   adjoint  checkpointed discrete adjoint, forward sweep + reverse sweep -> 48 B
+# `alg_bytes` is the algorithmic HBM traffic of the kernel actually launched, so roofline.frac is
+# comparable between the two; `value` (system-steps/s) is what the user sees.
+ALGOS = {
+    "tangent": {"alg_bytes": 24, "kernel": "rc_fwdsens_kernel<256,8,2>", "env": "1"},
+    "adjoint": {"alg_bytes": 48, "kernel": "rollout_adj_kernel<RCModel,128,12,2,MSE>", "env": "0"},
+}
+WAVE = 148 * 2 * 256  # systems per full wave: 2 CTAs/SM x 256 (tangent) == 148 x 4 x 128; the adjoint's is 148*3*128
 NOMINAL = [10384.31640625, 499089.09375, 1321535.125, 1.5348844528198242, 0.5000327825546265,
            1.000040054321289, 20.119935989379883]
 
@@ -41,7 +49,9 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--systems", type=int, default=1 << 20, help="systems per rank per step")
     ap.add_argument("--T", type=int, default=T_YEAR)
-    ap.add_argument("--tile", type=int, default=4 * WAVE, help="systems per kernel launch")
+    ap.add_argument("--algo", default="tangent", choices=sorted(ALGOS),
+                    help="gradient kernel: the library default (tangent) or the checkpointed adjoint")
+    ap.add_argument("--tile", type=int, default=None, help="systems per kernel launch (default: 3 full waves)")
     ap.add_argument("--e2e-systems", type=int, default=32768)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-systems", type=int, default=8192, help="bounded CPU-baseline sample")
@@ -126,10 +136,10 @@ def measured_peak():
         return 6650.0, "fallback"
 
 
-def ncu_traffic_per_step():
-    """DRAM bytes per system-step of the dominant kernel from the committed ncu capture (or None)."""
+def ncu_traffic_per_step(algo):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (or None)."""
     try:
-        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[algo]
     except Exception:
         return None
 
@@ -190,6 +200,11 @@ def ours(a):
     import torch
     import torch.distributed as dist
 
+    algo = ALGOS[a.algo]
+    os.environ["DYNAX_GRAD_ALGO"] = algo["env"]     # read by the library at every call
+    B_ALG = algo["alg_bytes"]
+    if a.tile is None:
+        a.tile = 3 * WAVE if a.algo == "tangent" else 4 * 148 * 3 * 128   # both 227328 systems
     from dynax_b200 import host, ops
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -312,10 +327,10 @@ def ours(a):
 
     peak, peak_kind = measured_peak()
     achieved = S * T * a.steps * B_ALG / sec / 1e9          # per rank: alg bytes of its launches / its time
-    traffic = ncu_traffic_per_step()
+    traffic = ncu_traffic_per_step(a.algo)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs, copy bandwidth)" if peak_kind == "measured" else "fallback 6.65 TB/s",
-                "kernel": "rollout_adj_kernel<RCModel,128,12,2,MSE>", "alg_bytes_per_system_step": B_ALG,
+                "kernel": algo["kernel"], "alg_bytes_per_system_step": B_ALG,
                 "alg_bytes_per_launch": B_ALG * tile * T, "avg_launch_ms": ms / launches,
                 "traffic": (traffic or {}).get("dram_bytes_per_launch"), "traffic_note": (traffic or {}).get("note")}
 
@@ -330,6 +345,7 @@ def ours(a):
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"rc_fwd_grad N={S} T={T} dt=3600 per-system theta/u/target (per rank)",
+                   "algo": a.algo,
                    "tile_systems": tile, "tiles_per_step": len(tiles),
                    "l2": "inputs larger than L2 (u+target tile %.1f GB re-read by each tile launch)" % ((u.numel() + target.numel()) * 4 / 1e9),
                    "parallelism": f"system axis sharded over {world} rank(s); no data-path collective"},

@@ -4,6 +4,7 @@
 #include <string.h>
 
 #include "launch.cuh"
+#include "rc_fwdsens.cuh"
 
 namespace dynax {
 
@@ -82,6 +83,19 @@ static int rc_forward(const float *theta, const float *x0, const float *u, float
     }
 }
 
+template <int TN, int KF, int S, int MINB>
+static int launch_fwdsens(const FwdSensParams &P, cudaStream_t st) {
+    using Cfg = FwdSensCfg<TN, KF, S>;
+    auto kern = rc_fwdsens_kernel<TN, KF, S, MINB>;
+    int rc = set_smem(kern, Cfg::SMEM_BYTES);
+    if (rc != DYNAX_OK) return rc;
+    const int64_t grid = (P.N + TN - 1) / TN;
+    if (grid > 0x7fffffffLL) return fail(DYNAX_ERR_INVALID_ARGUMENT, "N too large for one launch");
+    kern<<<(unsigned)grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(P);
+    DYNAX_CUDA_TRY(cudaGetLastError());
+    return DYNAX_OK;
+}
+
 template <int MODE>
 static int rc_adjoint(const float *theta, const float *x0, const float *u, const float *target, const float *lb,
                       const float *ub, const float *g_xsol, const float *g_ysol, float *loss, float *g_theta,
@@ -128,6 +142,22 @@ static int rc_adjoint(const float *theta, const float *x0, const float *u, const
     }
     if (env_int("DYNAX_NO_BULK", 0)) P.bulk = 0;
     const bool su = flags & DYNAX_SHARED_U, stg = flags & DYNAX_SHARED_TARGET;
+    // Forward-mode (tangent) single sweep for the plain per-system MSE case (rc_fwdsens.cuh): one pass over u
+    // and target, 24 B per system-step, measured 2.2-2.3e11 system-steps/s against 1.3-1.4e11 for the
+    // checkpointed adjoint below on the same box.  DYNAX_GRAD_ALGO=0 forces the adjoint; the adjoint also
+    // serves every case the tangent kernel does not cover (shared inputs, control channel, g_x0, discrete).
+    if (MODE == ADJ_MSE && env_int("DYNAX_GRAD_ALGO", 1) == 1 && !su && !stg && !ctrl && !g_x0 &&
+        !(flags & (DYNAX_SHARED_THETA | DYNAX_DISCRETE))) {
+        FwdSensParams F;
+        F.mp = P.mp; F.x0 = x0; F.u = u; F.target = target; F.lb = lb; F.ub = ub; F.loss = loss; F.g_theta = g_theta;
+        F.N = N; F.T = T; F.dt = dt; F.bulk = P.bulk;
+        switch (env_int("DYNAX_FS_CFG", 0)) {  // tools/tune.py: 0: 2.31e11, 1: 2.16e11, 2: 1.77e11 steps/s
+            default:
+            case 0: return launch_fwdsens<256, 8, 2, 2>(F, st);
+            case 1: return launch_fwdsens<128, 8, 2, 4>(F, st);
+            case 2: return launch_fwdsens<128, 4, 2, 4>(F, st);
+        }
+    }
     if constexpr (MODE == ADJ_VJP) {
         if (su) return launch_adj<RCModel, 128, 8, 2, ADJ_VJP, true, false, 2>(P, st);
         return launch_adj<RCModel, 128, 8, 2, ADJ_VJP, false, false, 2>(P, st);

@@ -40,13 +40,14 @@ def test_year_long_forward_one_wave():
     assert bool(torch.isfinite(xs).all())
 
 
-def test_year_long_loss_grad_one_wave():
-    """One full wave of the adjoint kernel over a year: permuting the systems permutes the results bit
+@pytest.mark.parametrize("algo,N", [("1", 148 * 2 * 256), ("0", 148 * 3 * 128)])
+def test_year_long_loss_grad_one_wave(monkeypatch, algo, N):
+    """One full wave of the tangent (DYNAX_GRAD_ALGO=1) / adjoint (=0) kernel over a year: permuting the systems permutes the results bit
     for bit (no cross-talk between threads / tiles); a launch split in two halves of the system axis gives
     the same bits; 32 random systems match the fp64 oracle within the conditioning-aware budget."""
     import torch
     from dynax_b200 import ops
-    N = 148 * 3 * 128
+    monkeypatch.setenv("DYNAX_GRAD_ALGO", algo)
     th, x0, u, tg = _inputs(torch, N, 162)
     loss, grad, _ = ops.rc_loss_grad(th, x0, u, tg, 3600.0)
     perm = torch.randperm(N, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))

@@ -41,22 +41,30 @@ def make_case(N, Tn, seed, noise=0.1):
     return th, x0, u, target
 
 
+ALGO_ENV = {"tangent": "1", "adjoint": "0"}   # DYNAX_GRAD_ALGO: forward-mode single sweep / checkpointed adjoint
+
+
+@pytest.mark.parametrize("algo", ["tangent", "adjoint"])
 @pytest.mark.parametrize("N,Tn,noise", [(256, 8760, 0.1), (256, 8760, None), (130, 1000, 0.1), (7, 100, 1.0),
                                         (1, 17, 0.1), (5, 16, 0.1), (3, 1, 0.1)])
-def test_loss_grad_vs_fp64(T, ops, N, Tn, noise):
+def test_loss_grad_vs_fp64(T, ops, monkeypatch, N, Tn, noise, algo):
+    monkeypatch.setenv("DYNAX_GRAD_ALGO", ALGO_ENV[algo])
     # noise=0.1: target = a hidden model's output + N(0,0.1) (small residual: ill-conditioned, the
     # realistic near-optimum regime); noise=None: target = 22 + N(0,1) (large residual)
     th, x0, u, target = make_case(N, Tn, 31, noise)
     th[0, 0] = 4.0e4            # above ub
     if N > 1:
         th[1, 4] = 0.45         # below lb
+    # asking for d loss/d x0 routes to the adjoint whatever the environment says: the tangent leg goes without
     loss, grad, gx0 = ops.rc_loss_grad(cu(T, th), cu(T, x0), cu(T, u), cu(T, target), 3600.0,
-                                       orc.RC_LB, orc.RC_UB, want_gx0=True)
+                                       orc.RC_LB, orc.RC_UB, want_gx0=(algo == "adjoint"))
     l64, g64 = orc.rc_loss_grad(th, x0, u, target, 3600.0, orc.RC_LB, orc.RC_UB, np.float64)
     l32, g32 = c_oracle.rc_loss_grad(th, x0, u, target, 3600.0, orc.RC_LB, orc.RC_UB)
     lbud, gbud = orc.rc_output_sensitivity_budget(th, x0, u, target, 3600.0)
     assert_loss_parity(loss.cpu().numpy(), l64, lbud)
     assert_grad_parity(grad.cpu().numpy(), g64, gbud, g32 if N >= 64 else None)
+    if algo == "tangent":
+        return
     # d loss / d x0 against the oracle's general VJP
     gy = (2.0 / Tn) * (orc.rc_rollout(th, x0, u, 3600.0, np.float64)[1][..., 0] - target)
     _, gx0_64, _ = orc.rc_vjp(th, x0, u, 3600.0, None, gy[..., None])
@@ -70,6 +78,7 @@ def test_loss_grad_vs_fp64(T, ops, N, Tn, noise):
 @pytest.mark.parametrize("cfg", ["0", "1", "2", "3", "4"])
 def test_adj_tile_configs(T, ops, monkeypatch, cfg):
     th, x0, u, target = make_case(300, 777, 32)
+    monkeypatch.setenv("DYNAX_GRAD_ALGO", "0")
     monkeypatch.setenv("DYNAX_ADJ_CFG", cfg)
     loss, grad, _ = ops.rc_loss_grad(cu(T, th), cu(T, x0), cu(T, u), cu(T, target), 3600.0)
     l64, g64 = orc.rc_loss_grad(th, x0, u, target, 3600.0, None, None, np.float64)
@@ -78,7 +87,38 @@ def test_adj_tile_configs(T, ops, monkeypatch, cfg):
     assert_grad_parity(grad.cpu().numpy(), g64, gbud)
 
 
-def test_no_tma_path_and_ragged(T, ops, monkeypatch):
+@pytest.mark.parametrize("cfg", ["0", "1", "2"])
+def test_tangent_tile_configs(T, ops, monkeypatch, cfg):
+    th, x0, u, target = make_case(300, 777, 32)
+    monkeypatch.setenv("DYNAX_GRAD_ALGO", "1")
+    monkeypatch.setenv("DYNAX_FS_CFG", cfg)
+    loss, grad, _ = ops.rc_loss_grad(cu(T, th), cu(T, x0), cu(T, u), cu(T, target), 3600.0)
+    l64, g64 = orc.rc_loss_grad(th, x0, u, target, 3600.0, None, None, np.float64)
+    lbud, gbud = orc.rc_output_sensitivity_budget(th, x0, u, target, 3600.0)
+    assert_loss_parity(loss.cpu().numpy(), l64, lbud)
+    assert_grad_parity(grad.cpu().numpy(), g64, gbud)
+
+
+def test_tangent_and_adjoint_agree(T, ops, monkeypatch):
+    """The two gradient kernels are different fp32 evaluations of one quantity: identical loss
+    arithmetic (bit-equal per-step residuals, fp64 fold) and gradients inside twice the parity band."""
+    th, x0, u, target = make_case(1024, 2000, 39)
+    th[3, 2] = 5e6              # clipped by ub: penalty path in both
+    a = [cu(T, v) for v in (th, x0, u, target)]
+    monkeypatch.setenv("DYNAX_GRAD_ALGO", "1")
+    l1, g1, _ = ops.rc_loss_grad(*a, 3600.0, orc.RC_LB, orc.RC_UB)
+    monkeypatch.setenv("DYNAX_GRAD_ALGO", "0")
+    l2, g2, _ = ops.rc_loss_grad(*a, 3600.0, orc.RC_LB, orc.RC_UB)
+    assert not T.equal(g1, g2)          # really two code paths
+    assert T.allclose(l1, l2, rtol=2e-6, atol=0)
+    _, g64 = orc.rc_loss_grad(th, x0, u, target, 3600.0, orc.RC_LB, orc.RC_UB, np.float64)
+    _, gbud = orc.rc_output_sensitivity_budget(th, x0, u, target, 3600.0)
+    assert (np.abs((g1 - g2).cpu().numpy()) <= 2 * (GRAD_RTOL * np.abs(g64) + gbud)).all()
+
+
+@pytest.mark.parametrize("algo", ["tangent", "adjoint"])
+def test_no_tma_path_and_ragged(T, ops, monkeypatch, algo):
+    monkeypatch.setenv("DYNAX_GRAD_ALGO", ALGO_ENV[algo])
     th, x0, u, target = make_case(261, 300, 33)          # N % 4 != 0 -> plain ld path
     a = [cu(T, v) for v in (th, x0, u, target)]
     loss, grad, _ = ops.rc_loss_grad(*a, 3600.0)

@@ -32,9 +32,10 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--T", type=int, default=4380)
     ap.add_argument("--N", type=int, default=148 * 7 * 128)
-    ap.add_argument("--what", default="fwd,adj")
+    ap.add_argument("--what", default="fwd,tan,adj")
     ap.add_argument("--fwd-cfgs", default="0,1,2,3")
     ap.add_argument("--adj-cfgs", default="0,1,2,3,4")
+    ap.add_argument("--fs-cfgs", default="0,1,2")
     a = ap.parse_args()
     N, T = a.N, a.T
     g = torch.Generator(device="cuda").manual_seed(0)
@@ -65,7 +66,15 @@ def main():
                 best, avg = timeit(lambda: ops.rc_forward(th, x0, u, 3600.0, **kw))
                 print(f"fwd cfg={cfg} {name:7s} best {best*1e3:8.2f} ms avg {avg*1e3:8.2f} ms  "
                       f"{steps/best:.3e} steps/s  {steps*B/best/1e9:7.1f} GB/s", flush=True)
+    if "tan" in a.what:
+        os.environ["DYNAX_GRAD_ALGO"] = "1"
+        for cfg in a.fs_cfgs.split(","):
+            os.environ["DYNAX_FS_CFG"] = cfg
+            best, avg = timeit(lambda: ops.rc_loss_grad(th, x0, u, target, 3600.0), iters=4)
+            print(f"tan cfg={cfg} best {best*1e3:8.2f} ms avg {avg*1e3:8.2f} ms  {steps/best:.3e} steps/s  "
+                  f"{steps*24/best/1e9:7.1f} GB/s (24 B/step)", flush=True)
     if "adj" in a.what:
+        os.environ["DYNAX_GRAD_ALGO"] = "0"
         for cfg in a.adj_cfgs.split(","):
             os.environ["DYNAX_ADJ_CFG"] = cfg
             best, avg = timeit(lambda: ops.rc_loss_grad(th, x0, u, target, 3600.0))
