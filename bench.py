@@ -33,7 +33,7 @@ DT = 3600.0
 # `alg_bytes` is the algorithmic HBM traffic of the kernel actually launched, so roofline.frac is
 # comparable between the two; `value` (system-steps/s) is what the user sees.
 ALGOS = {
-    "tangent": {"alg_bytes": 24, "kernel": "rc_fwdsens_kernel<256,8,2>", "env": "1"},
+    "tangent": {"alg_bytes": 24, "kernel": "rc_fwdsens_kernel<256,8,2,2,packed>", "env": "1"},
     "adjoint": {"alg_bytes": 48, "kernel": "rollout_adj_kernel<RCModel,128,12,2,MSE>", "env": "0"},
 }
 WAVE = 148 * 2 * 256  # systems per full wave: 2 CTAs/SM x 256 (tangent) == 148 x 4 x 128; the adjoint's is 148*3*128

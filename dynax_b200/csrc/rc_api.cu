@@ -83,10 +83,10 @@ static int rc_forward(const float *theta, const float *x0, const float *u, float
     }
 }
 
-template <int TN, int KF, int S, int MINB>
+template <int TN, int KF, int S, int MINB, bool PACKED = false>
 static int launch_fwdsens(const FwdSensParams &P, cudaStream_t st) {
     using Cfg = FwdSensCfg<TN, KF, S>;
-    auto kern = rc_fwdsens_kernel<TN, KF, S, MINB>;
+    auto kern = rc_fwdsens_kernel<TN, KF, S, MINB, PACKED>;
     int rc = set_smem(kern, Cfg::SMEM_BYTES);
     if (rc != DYNAX_OK) return rc;
     const int64_t grid = (P.N + TN - 1) / TN;
@@ -151,11 +151,14 @@ static int rc_adjoint(const float *theta, const float *x0, const float *u, const
         FwdSensParams F;
         F.mp = P.mp; F.x0 = x0; F.u = u; F.target = target; F.lb = lb; F.ub = ub; F.loss = loss; F.g_theta = g_theta;
         F.N = N; F.T = T; F.dt = dt; F.bulk = P.bulk;
-        switch (env_int("DYNAX_FS_CFG", 0)) {  // tools/tune.py: 0: 2.31e11, 1: 2.16e11, 2: 1.77e11 steps/s
+        // tools/tune.py, N=227328 x T=8760, same box, interleaved, power-capped steady state:
+        //   0 packed fp32x2 <256,8,2,2>: 8.7 ms (2.28e11 steps/s; 7.8 ms = 2.55e11 on a cool GPU)
+        //   1 scalar        <256,8,2,2>: 9.9 ms (2.01e11)        2 packed <128,8,2,4>: 9.7 ms
+        switch (env_int("DYNAX_FS_CFG", 0)) {
             default:
-            case 0: return launch_fwdsens<256, 8, 2, 2>(F, st);
-            case 1: return launch_fwdsens<128, 8, 2, 4>(F, st);
-            case 2: return launch_fwdsens<128, 4, 2, 4>(F, st);
+            case 0: return launch_fwdsens<256, 8, 2, 2, true>(F, st);
+            case 1: return launch_fwdsens<256, 8, 2, 2, false>(F, st);
+            case 2: return launch_fwdsens<128, 8, 2, 4, true>(F, st);
         }
     }
     if constexpr (MODE == ADJ_VJP) {

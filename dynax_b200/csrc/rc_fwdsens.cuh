@@ -7,8 +7,9 @@
 //     loss    = mean_k (x_k[0] - target_k)^2,     dloss/dtheta_j = sum_k (2/T)(x_k[0] - target_k) S_k[0,j]
 // This is mathematically the same gradient jax.value_and_grad returns (examples/3-inverse.py:96-112); it
 // reads u and target ONCE (24 B per system-step instead of the adjoint's 46 B, no checkpoints, no
-// workspace) at the price of ~110 FMAs per step, which moves the kernel from the HBM roof to the FP32
-// issue roof.  Same thread-per-system / TMA-ring structure as the other rollout kernels.
+// workspace) at the price of ~90 FMAs per step, which moves the kernel from the HBM roof towards the FP32
+// issue / power roof -- hence the packed-fp32 (FFMA2) form below: 78 instead of 108 issue slots per step.
+// Same thread-per-system / TMA-ring structure as the other rollout kernels.
 //
 // Writing rhs_i = (1/C_i) q_i with q0 = (u0-x0)/Rg + (x2-x0)/Ri + u1 + u2, q1 = (u0-x1)/Re + (x2-x1)/Rw + u3,
 // q2 = (x0-x2)/Ri + (x1-x2)/Rw + u4, the direct partials are
@@ -39,11 +40,13 @@ constexpr int kFsFoldSteps = 32;  // fp32 partial sums are folded into the fp64 
 template <int TN, int KF, int S>
 struct FwdSensCfg {
     static constexpr int U_STAGE = KF * TN * 5, T_STAGE = KF * TN, STAGE = U_STAGE + T_STAGE;
-    static constexpr size_t SMEM_BYTES = sizeof(float) * (size_t)(S * STAGE) + sizeof(uint64_t) * 2 * S;
+    static constexpr size_t RING_BYTES = sizeof(float) * (size_t)(S * STAGE) + sizeof(uint64_t) * 2 * S;
+    static constexpr size_t ACC_OFF = (RING_BYTES + 15) / 16 * 16;                 // fp64 totals [8][TN] (packed path)
+    static constexpr size_t SMEM_BYTES = ACC_OFF + sizeof(double) * 8 * (size_t)TN;
     static constexpr int THREADS = TN + 32;
 };
 
-template <int TN, int KF, int S, int MINB>
+template <int TN, int KF, int S, int MINB, bool PACKED = false>
 __global__ void __launch_bounds__(TN + 32, MINB) rc_fwdsens_kernel(const FwdSensParams P) {
     using Cfg = FwdSensCfg<TN, KF, S>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -118,17 +121,105 @@ __global__ void __launch_bounds__(TN + 32, MINB) rc_fwdsens_kernel(const FwdSens
     const float tRi0 = -dt * iCai * iRi * iRi, tRi2 = -dt * iCwi * iRi * iRi, tRw1 = -dt * iCwe * iRw * iRw,
                 tRw2 = -dt * iCwi * iRw * iRw;
     float x0 = __ldg(P.x0 + i * 3), x1 = __ldg(P.x0 + i * 3 + 1), x2 = __ldg(P.x0 + i * 3 + 2);
-    float s0[7], s1[7], s2[7];  // rows of S = dx/dtheta
-    float gp[7];
     double gt[7], sqt = 0.0;
     float sq = 0.f;
+#pragma unroll
+    for (int j = 0; j < 7; ++j) gt[j] = 0.0;
+    const float c2T = 2.0f / (float)T;
+
+    if constexpr (PACKED) {
+        // Packed-fp32 form (FFMA2/FMUL2/FADD2, sm_100: two IEEE fp32 operations per issue slot).
+        //   * the columns of S travel in pairs (Cai,Cwe) (Cwi,Re) (Ri,Rw) (Rg,0): the homogeneous part
+        //     S + dt A S and the gradient accumulation take 32 issue slots instead of 56;
+        //   * rows 0 and 1 of the rhs, the differences u0 - x, x2 - x and the update of (x0,x1) are pairs too.
+        // Every lane performs the same operations in the same order as the scalar path (RCModel::rhs as nvcc
+        // contracts it), so x, the loss and S are bit-identical to it; ~70 instead of ~108 instructions per step.
+        float2 X01 = make_float2(x0, x1);
+        // fp64 totals live in shared memory ([j][tid]: conflict-free 8-byte accesses), touched once per
+        // kFsFoldSteps steps: 16 registers the loop needs for its coefficients
+        double *acc = reinterpret_cast<double *>(smem_raw + Cfg::ACC_OFF) + tid;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j * TN] = 0.0;
+        float2 s0[4], s1[4], s2[4], gp[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) s0[q] = s1[q] = s2[q] = gp[q] = make_float2(0.f, 0.f);
+        const float2 pA00 = make_float2(tA00, tA00), pA02 = make_float2(tA02, tA02), pA11 = make_float2(tA11, tA11),
+                     pA12 = make_float2(tA12, tA12), pA20 = make_float2(tA20, tA20), pA21 = make_float2(tA21, tA21),
+                     pA22 = make_float2(tA22, tA22);
+        const float2 rAd = make_float2(M.A00, M.A11), rAx2 = make_float2(M.A02, M.A12);   // rhs rows 0,1
+        const float2 rB0 = make_float2(M.B00, M.B10), rB1 = make_float2(M.B01, M.B13);
+        const float2 neg1 = make_float2(-1.f, -1.f), dt2 = make_float2(dt, dt), pR2 = make_float2(-tRi2, -tRw2);
+        for (int64_t c = 0; c < C; ++c) {
+            const int s = (int)(c % S);
+            const int64_t k0 = c * KF;
+            const int rows = (int)((T - k0) < KF ? (T - k0) : KF);
+            ptx::mbar_wait(&full[s], (uint32_t)((c / S) & 1));
+            const float *in = s_in + s * Cfg::STAGE + tid * 5;
+            const float *tg = s_in + s * Cfg::STAGE + Cfg::U_STAGE + tid;
+#pragma unroll
+            for (int jj = 0; jj < KF; ++jj) {
+                if (jj < rows) {
+                    const float u0 = in[jj * TN * 5], u1 = in[jj * TN * 5 + 1], u2 = in[jj * TN * 5 + 2],
+                                u3 = in[jj * TN * 5 + 3], u4 = in[jj * TN * 5 + 4];
+                    const float res = X01.x - tg[jj * TN];   // PRE-update state (simulator.py:38)
+                    sq = fmaf(res, res, sq);
+                    const float gy = c2T * res;
+                    const float2 gy2 = make_float2(gy, gy);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) gp[q] = __ffma2_rn(gy2, s0[q], gp[q]);
+                    // rhs = (A x) + (B u), rows 0 and 1 as a pair, row 2 scalar
+                    const float2 U0 = make_float2(u0, u0), X2 = make_float2(x2, x2);
+                    const float2 AX = __ffma2_rn(rAd, X01, __fmul2_rn(rAx2, X2));
+                    float2 BU = __ffma2_rn(rB0, U0, __fmul2_rn(rB1, make_float2(u1, u3)));
+                    BU.x = fmaf(M.B02, u2, BU.x);
+                    const float2 R01 = __fadd2_rn(AX, BU);
+                    const float r2 = fmaf(M.A22, x2, fmaf(M.A20, X01.x, M.A21 * X01.y)) + M.B24 * u4;
+                    const float2 DU = __ffma2_rn(neg1, X01, U0);   // (u0 - x0, u0 - x1), exact as a subtraction
+                    const float2 DX = __ffma2_rn(neg1, X01, X2);   // (x2 - x0, x2 - x1)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float2 a0 = s0[q], a1 = s1[q], a2 = s2[q];
+                        s0[q] = __ffma2_rn(pA02, a2, __ffma2_rn(pA00, a0, a0));
+                        s1[q] = __ffma2_rn(pA12, a2, __ffma2_rn(pA11, a1, a1));
+                        s2[q] = __ffma2_rn(pA22, a2, __ffma2_rn(pA21, a1, __ffma2_rn(pA20, a0, a2)));
+                    }
+                    s0[0].x = fmaf(tCai, R01.x, s0[0].x);      // d/dCai   (column 0)
+                    s1[0].y = fmaf(tCwe, R01.y, s1[0].y);      // d/dCwe   (column 1)
+                    s2[1].x = fmaf(tCwi, r2, s2[1].x);         // d/dCwi   (column 2)
+                    s1[1].y = fmaf(tRe, DU.y, s1[1].y);        // d/dRe    (column 3)
+                    s0[2].x = fmaf(tRi0, DX.x, s0[2].x);       // d/dRi    (column 4), row 0
+                    s1[2].y = fmaf(tRw1, DX.y, s1[2].y);       // d/dRw    (column 5), row 1
+                    s2[2] = __ffma2_rn(pR2, DX, s2[2]);        // d/dRi, d/dRw, row 2
+                    s0[3].x = fmaf(tRg, DU.x, s0[3].x);        // d/dRg    (column 6)
+                    X01 = __ffma2_rn(dt2, R01, X01);
+                    x2 = fmaf(dt, r2, x2);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&empty[s]);
+            constexpr int FOLDC = kFsFoldSteps / KF > 0 ? kFsFoldSteps / KF : 1;
+            if ((c + 1) % FOLDC == 0 || c + 1 == C) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    acc[(2 * q) * TN] += (double)gp[q].x;
+                    if (q < 3) acc[(2 * q + 1) * TN] += (double)gp[q].y;
+                    gp[q] = make_float2(0.f, 0.f);
+                }
+                acc[7 * TN] += (double)sq;
+                sq = 0.f;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 7; ++j) gt[j] = acc[j * TN];
+        sqt = acc[7 * TN];
+    } else {
+    float s0[7], s1[7], s2[7];  // rows of S = dx/dtheta
+    float gp[7];
 #pragma unroll
     for (int j = 0; j < 7; ++j) {
         s0[j] = s1[j] = s2[j] = 0.f;
         gp[j] = 0.f;
-        gt[j] = 0.0;
     }
-    const float c2T = 2.0f / (float)T;
 
     for (int64_t c = 0; c < C; ++c) {
         const int s = (int)(c % S);
@@ -137,6 +228,8 @@ __global__ void __launch_bounds__(TN + 32, MINB) rc_fwdsens_kernel(const FwdSens
         ptx::mbar_wait(&full[s], (uint32_t)((c / S) & 1));
         const float *in = s_in + s * Cfg::STAGE + tid * 5;
         const float *tg = s_in + s * Cfg::STAGE + Cfg::U_STAGE + tid;
+        // (one predicated, fully unrolled loop: a separate unpredicated body for full chunks executes 3 % fewer
+        // instructions but makes ptxas spill at 96 registers and measured 3 % slower)
 #pragma unroll
         for (int jj = 0; jj < KF; ++jj) {
             if (jj < rows) {
@@ -190,6 +283,7 @@ __global__ void __launch_bounds__(TN + 32, MINB) rc_fwdsens_kernel(const FwdSens
             sqt += (double)sq;
             sq = 0.f;
         }
+    }
     }
     if (!active) return;
     double loss = sqt / (double)T;

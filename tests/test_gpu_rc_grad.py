@@ -100,8 +100,8 @@ def test_tangent_tile_configs(T, ops, monkeypatch, cfg):
 
 
 def test_tangent_and_adjoint_agree(T, ops, monkeypatch):
-    """The two gradient kernels are different fp32 evaluations of one quantity: identical loss
-    arithmetic (bit-equal per-step residuals, fp64 fold) and gradients inside twice the parity band."""
+    """The two gradient kernels are different fp32 evaluations of one quantity: both sit inside the
+    parity band around the fp64 oracle, so they differ by at most twice that band."""
     th, x0, u, target = make_case(1024, 2000, 39)
     th[3, 2] = 5e6              # clipped by ub: penalty path in both
     a = [cu(T, v) for v in (th, x0, u, target)]
@@ -110,10 +110,12 @@ def test_tangent_and_adjoint_agree(T, ops, monkeypatch):
     monkeypatch.setenv("DYNAX_GRAD_ALGO", "0")
     l2, g2, _ = ops.rc_loss_grad(*a, 3600.0, orc.RC_LB, orc.RC_UB)
     assert not T.equal(g1, g2)          # really two code paths
-    assert T.allclose(l1, l2, rtol=2e-6, atol=0)
-    _, g64 = orc.rc_loss_grad(th, x0, u, target, 3600.0, orc.RC_LB, orc.RC_UB, np.float64)
-    _, gbud = orc.rc_output_sensitivity_budget(th, x0, u, target, 3600.0)
-    assert (np.abs((g1 - g2).cpu().numpy()) <= 2 * (GRAD_RTOL * np.abs(g64) + gbud)).all()
+    l64, g64 = orc.rc_loss_grad(th, x0, u, target, 3600.0, orc.RC_LB, orc.RC_UB, np.float64)
+    lbud, gbud = orc.rc_output_sensitivity_budget(th, x0, u, target, 3600.0)
+    dl = np.abs((l1 - l2).double().cpu().numpy())
+    assert (dl <= 2 * (1e-5 * np.abs(l64) + lbud)).all(), (dl / (1e-5 * np.abs(l64) + lbud)).max()
+    dg = np.abs((g1 - g2).double().cpu().numpy())
+    assert (dg <= 2 * (GRAD_RTOL * np.abs(g64) + gbud)).all(), (dg / (GRAD_RTOL * np.abs(g64) + gbud)).max()
 
 
 @pytest.mark.parametrize("algo", ["tangent", "adjoint"])
