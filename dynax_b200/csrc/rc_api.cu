@@ -83,10 +83,10 @@ static int rc_forward(const float *theta, const float *x0, const float *u, float
     }
 }
 
-template <int TN, int KF, int S, int MINB, bool PACKED = false>
+template <int TN, int KF, int S, int MINB, bool PACKED = false, bool SU = false, bool STG = false>
 static int launch_fwdsens(const FwdSensParams &P, cudaStream_t st) {
-    using Cfg = FwdSensCfg<TN, KF, S>;
-    auto kern = rc_fwdsens_kernel<TN, KF, S, MINB, PACKED>;
+    using Cfg = FwdSensCfg<TN, KF, S, SU, STG>;
+    auto kern = rc_fwdsens_kernel<TN, KF, S, MINB, PACKED, SU, STG>;
     int rc = set_smem(kern, Cfg::SMEM_BYTES);
     if (rc != DYNAX_OK) return rc;
     const int64_t grid = (P.N + TN - 1) / TN;
@@ -142,15 +142,32 @@ static int rc_adjoint(const float *theta, const float *x0, const float *u, const
     }
     if (env_int("DYNAX_NO_BULK", 0)) P.bulk = 0;
     const bool su = flags & DYNAX_SHARED_U, stg = flags & DYNAX_SHARED_TARGET;
-    // Forward-mode (tangent) single sweep for the plain per-system MSE case (rc_fwdsens.cuh): one pass over u
-    // and target, 24 B per system-step, measured 2.2-2.3e11 system-steps/s against 1.3-1.4e11 for the
-    // checkpointed adjoint below on the same box.  DYNAX_GRAD_ALGO=0 forces the adjoint; the adjoint also
-    // serves every case the tangent kernel does not cover (shared inputs, control channel, g_x0, discrete).
-    if (MODE == ADJ_MSE && env_int("DYNAX_GRAD_ALGO", 1) == 1 && !su && !stg && !ctrl && !g_x0 &&
+    // Forward-mode (tangent) single sweep for the fused 4R3C loss+gradient with per-system theta (rc_fwdsens.cuh):
+    // one pass over u and target (24 B per system-step; nothing at all when both are shared series), measured
+    // 2.2-2.3e11 system-steps/s against 1.3-1.4e11 for the checkpointed adjoint below on the same box.
+    // DYNAX_GRAD_ALGO=0 forces the adjoint; the adjoint also serves every case the tangent kernel does not cover
+    // (shared theta, control channel, g_x0, discrete stepping, general cotangents).
+    if (MODE == ADJ_MSE && env_int("DYNAX_GRAD_ALGO", 1) == 1 && !ctrl && !g_x0 &&
         !(flags & (DYNAX_SHARED_THETA | DYNAX_DISCRETE))) {
         FwdSensParams F;
         F.mp = P.mp; F.x0 = x0; F.u = u; F.target = target; F.lb = lb; F.ub = ub; F.loss = loss; F.g_theta = g_theta;
-        F.N = N; F.T = T; F.dt = dt; F.bulk = P.bulk;
+        F.N = N; F.T = T; F.dt = dt;
+        F.bulk = (N % 4) == 0 && (su || aligned16(u)) && (stg || aligned16(target)) && !env_int("DYNAX_NO_BULK", 0);
+        // Every CTA runs the whole horizon, so a launch costs (waves x systems per CTA): 224-system CTAs win when they
+        // save a wave (N = 65536: 293 CTAs fill the 296 slots once, 256 CTAs of 256 leave 40 SMs half empty).
+        DeviceInfo di;
+        rc = device_info(&di);
+        if (rc != DYNAX_OK) return rc;
+        const int64_t slots = 2 * (int64_t)di.sm_count;
+        auto cost = [&](int64_t tn) { return ((N + tn - 1) / tn + slots - 1) / slots * tn; };
+        const bool narrow = cost(224) < cost(256) && env_int("DYNAX_FS_CFG", 0) == 0;
+        if (su && stg) return narrow ? launch_fwdsens<224, 8, 2, 2, true, true, true>(F, st)
+                                     : launch_fwdsens<256, 8, 2, 2, true, true, true>(F, st);
+        if (su) return narrow ? launch_fwdsens<224, 8, 2, 2, true, true, false>(F, st)
+                              : launch_fwdsens<256, 8, 2, 2, true, true, false>(F, st);
+        if (stg) return narrow ? launch_fwdsens<224, 8, 2, 2, true, false, true>(F, st)
+                               : launch_fwdsens<256, 8, 2, 2, true, false, true>(F, st);
+        if (narrow) return launch_fwdsens<224, 8, 2, 2, true>(F, st);
         // tools/tune.py, N=227328 x T=8760, same box, interleaved, power-capped steady state:
         //   0 packed fp32x2 <256,8,2,2>: 8.7 ms (2.28e11 steps/s; 7.8 ms = 2.55e11 on a cool GPU)
         //   1 scalar        <256,8,2,2>: 9.9 ms (2.01e11)        2 packed <128,8,2,4>: 9.7 ms

@@ -27,7 +27,7 @@ namespace dynax {
 
 struct FwdSensParams {
     RCModel::Ptrs mp;
-    const float *x0, *u, *target;  // [N,3], [T,N,5], [T,N]
+    const float *x0, *u, *target;  // [N,3], [T,N,5] (SHARED_U: [T,5]), [T,N] (SHARED_TGT: [T])
     const float *lb, *ub;          // [7] or NULL
     float *loss, *g_theta;         // [N], [N,7]
     int64_t N, T;
@@ -37,18 +37,20 @@ struct FwdSensParams {
 
 constexpr int kFsFoldSteps = 32;  // fp32 partial sums are folded into the fp64 totals every this many steps
 
-template <int TN, int KF, int S>
+template <int TN, int KF, int S, bool SHARED_U = false, bool SHARED_TGT = false>
 struct FwdSensCfg {
-    static constexpr int U_STAGE = KF * TN * 5, T_STAGE = KF * TN, STAGE = U_STAGE + T_STAGE;
+    // a shared series occupies KF rows of 5 (or 1) floats per stage instead of KF x TN of them
+    static constexpr int U_ROW = SHARED_U ? 5 : TN * 5, T_ROW = SHARED_TGT ? 1 : TN;
+    static constexpr int U_STAGE = (KF * U_ROW + 3) / 4 * 4, T_STAGE = (KF * T_ROW + 3) / 4 * 4, STAGE = U_STAGE + T_STAGE;
     static constexpr size_t RING_BYTES = sizeof(float) * (size_t)(S * STAGE) + sizeof(uint64_t) * 2 * S;
     static constexpr size_t ACC_OFF = (RING_BYTES + 15) / 16 * 16;                 // fp64 totals [8][TN] (packed path)
     static constexpr size_t SMEM_BYTES = ACC_OFF + sizeof(double) * 8 * (size_t)TN;
     static constexpr int THREADS = TN + 32;
 };
 
-template <int TN, int KF, int S, int MINB, bool PACKED = false>
+template <int TN, int KF, int S, int MINB, bool PACKED = false, bool SHARED_U = false, bool SHARED_TGT = false>
 __global__ void __launch_bounds__(TN + 32, MINB) rc_fwdsens_kernel(const FwdSensParams P) {
-    using Cfg = FwdSensCfg<TN, KF, S>;
+    using Cfg = FwdSensCfg<TN, KF, S, SHARED_U, SHARED_TGT>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *s_in = reinterpret_cast<float *>(smem_raw);
     uint64_t *full = reinterpret_cast<uint64_t *>(s_in + S * Cfg::STAGE);
@@ -76,20 +78,37 @@ __global__ void __launch_bounds__(TN + 32, MINB) rc_fwdsens_kernel(const FwdSens
             const int64_t k0 = c * KF;
             const int rows = (int)((T - k0) < KF ? (T - k0) : KF);
             float *du = s_in + s * Cfg::STAGE, *dtg = du + Cfg::U_STAGE;
-            if (P.bulk) {
+            // shared series: a few floats per stage, copied by the producer lanes; per-system rows: TMA (or plain
+            // loads when rows are not 16-byte aligned).  The arrive that publishes the stage comes last.
+            if constexpr (SHARED_U) {
+                const float *su = P.u + k0 * 5;
+                for (int i = lane; i < rows * 5; i += 32) du[i] = __ldg(su + i);
+            }
+            if constexpr (SHARED_TGT) {
+                const float *st = P.target + k0;
+                for (int i = lane; i < rows; i += 32) dtg[i] = __ldg(st + i);
+            }
+            constexpr bool ANY_ROWS = !SHARED_U || !SHARED_TGT;
+            if (ANY_ROWS && P.bulk) {
+                __syncwarp();
                 if (lane == 0) {
-                    const uint32_t ub = (uint32_t)valid * 20u, tb = (uint32_t)valid * 4u;
+                    const uint32_t ub = SHARED_U ? 0u : (uint32_t)valid * 20u, tb = SHARED_TGT ? 0u : (uint32_t)valid * 4u;
                     ptx::mbar_arrive_expect_tx(&full[s], (ub + tb) * (uint32_t)rows);
                     for (int r = 0; r < rows; ++r) {
-                        ptx::bulk_g2s(du + r * TN * 5, P.u + ((k0 + r) * N + n0) * 5, ub, &full[s], pol);
-                        ptx::bulk_g2s(dtg + r * TN, P.target + (k0 + r) * N + n0, tb, &full[s], pol);
+                        if constexpr (!SHARED_U) ptx::bulk_g2s(du + r * TN * 5, P.u + ((k0 + r) * N + n0) * 5, ub, &full[s], pol);
+                        if constexpr (!SHARED_TGT) ptx::bulk_g2s(dtg + r * TN, P.target + (k0 + r) * N + n0, tb, &full[s], pol);
                     }
                 }
             } else {
                 for (int r = 0; r < rows; ++r) {
-                    const float *su = P.u + ((k0 + r) * N + n0) * 5, *st = P.target + (k0 + r) * N + n0;
-                    for (int i = lane; i < valid * 5; i += 32) du[r * TN * 5 + i] = __ldg(su + i);
-                    for (int i = lane; i < valid; i += 32) dtg[r * TN + i] = __ldg(st + i);
+                    if constexpr (!SHARED_U) {
+                        const float *su = P.u + ((k0 + r) * N + n0) * 5;
+                        for (int i = lane; i < valid * 5; i += 32) du[r * TN * 5 + i] = __ldg(su + i);
+                    }
+                    if constexpr (!SHARED_TGT) {
+                        const float *st = P.target + (k0 + r) * N + n0;
+                        for (int i = lane; i < valid; i += 32) dtg[r * TN + i] = __ldg(st + i);
+                    }
                 }
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(&full[s]);
@@ -154,14 +173,14 @@ __global__ void __launch_bounds__(TN + 32, MINB) rc_fwdsens_kernel(const FwdSens
             const int64_t k0 = c * KF;
             const int rows = (int)((T - k0) < KF ? (T - k0) : KF);
             ptx::mbar_wait(&full[s], (uint32_t)((c / S) & 1));
-            const float *in = s_in + s * Cfg::STAGE + tid * 5;
-            const float *tg = s_in + s * Cfg::STAGE + Cfg::U_STAGE + tid;
+            const float *in = s_in + s * Cfg::STAGE + (SHARED_U ? 0 : tid * 5);
+            const float *tg = s_in + s * Cfg::STAGE + Cfg::U_STAGE + (SHARED_TGT ? 0 : tid);
 #pragma unroll
             for (int jj = 0; jj < KF; ++jj) {
                 if (jj < rows) {
-                    const float u0 = in[jj * TN * 5], u1 = in[jj * TN * 5 + 1], u2 = in[jj * TN * 5 + 2],
-                                u3 = in[jj * TN * 5 + 3], u4 = in[jj * TN * 5 + 4];
-                    const float res = X01.x - tg[jj * TN];   // PRE-update state (simulator.py:38)
+                    const float u0 = in[jj * Cfg::U_ROW], u1 = in[jj * Cfg::U_ROW + 1], u2 = in[jj * Cfg::U_ROW + 2],
+                                u3 = in[jj * Cfg::U_ROW + 3], u4 = in[jj * Cfg::U_ROW + 4];
+                    const float res = X01.x - tg[jj * Cfg::T_ROW];   // PRE-update state (simulator.py:38)
                     sq = fmaf(res, res, sq);
                     const float gy = c2T * res;
                     const float2 gy2 = make_float2(gy, gy);
@@ -226,17 +245,17 @@ __global__ void __launch_bounds__(TN + 32, MINB) rc_fwdsens_kernel(const FwdSens
         const int64_t k0 = c * KF;
         const int rows = (int)((T - k0) < KF ? (T - k0) : KF);
         ptx::mbar_wait(&full[s], (uint32_t)((c / S) & 1));
-        const float *in = s_in + s * Cfg::STAGE + tid * 5;
-        const float *tg = s_in + s * Cfg::STAGE + Cfg::U_STAGE + tid;
+        const float *in = s_in + s * Cfg::STAGE + (SHARED_U ? 0 : tid * 5);
+        const float *tg = s_in + s * Cfg::STAGE + Cfg::U_STAGE + (SHARED_TGT ? 0 : tid);
         // (one predicated, fully unrolled loop: a separate unpredicated body for full chunks executes 3 % fewer
         // instructions but makes ptxas spill at 96 registers and measured 3 % slower)
 #pragma unroll
         for (int jj = 0; jj < KF; ++jj) {
             if (jj < rows) {
-                const float u0 = in[jj * TN * 5], u1 = in[jj * TN * 5 + 1], u2 = in[jj * TN * 5 + 2],
-                            u3 = in[jj * TN * 5 + 3], u4 = in[jj * TN * 5 + 4];
+                const float u0 = in[jj * Cfg::U_ROW], u1 = in[jj * Cfg::U_ROW + 1], u2 = in[jj * Cfg::U_ROW + 2],
+                            u3 = in[jj * Cfg::U_ROW + 3], u4 = in[jj * Cfg::U_ROW + 4];
                 // loss and gradient use the PRE-update state (ysol[k] = x_k[0], simulator.py:38)
-                const float res = x0 - tg[jj * TN];
+                const float res = x0 - tg[jj * Cfg::T_ROW];
                 sq = fmaf(res, res, sq);
                 const float gy = c2T * res;
 #pragma unroll

@@ -136,8 +136,10 @@ def test_no_tma_path_and_ragged(T, ops, monkeypatch, algo):
     assert T.equal(l1, l2) and T.equal(g1, g2)
 
 
-def test_shared_modes(T, ops):
-    N, Tn = 384, 500
+@pytest.mark.parametrize("algo", ["tangent", "adjoint"])
+def test_shared_modes(T, ops, monkeypatch, algo):
+    monkeypatch.setenv("DYNAX_GRAD_ALGO", ALGO_ENV[algo])
+    N, Tn = 384, 501            # ragged last chunk
     th, x0, u, target = make_case(N, Tn, 35, None)
     # shared u + shared target, per-system theta  (config 3 variant ii)
     loss, grad, _ = ops.rc_loss_grad(cu(T, th), cu(T, x0), cu(T, u[:, :1]), cu(T, target[:, 0]), 3600.0)
@@ -158,6 +160,13 @@ def test_shared_modes(T, ops):
     loss, grad, _ = ops.rc_loss_grad(cu(T, th), cu(T, x0), cu(T, u), cu(T, target[:, 0]), 3600.0)
     l64, g64 = orc.rc_loss_grad(th, x0, u, target[:, :1], 3600.0, None, None, np.float64)
     lbud, gbud = orc.rc_output_sensitivity_budget(th, x0, u, target[:, :1], 3600.0)
+    assert_loss_parity(loss.cpu().numpy(), l64, lbud)
+    assert_grad_parity(grad.cpu().numpy(), g64, gbud)
+    # shared u, per-system target, box penalty on
+    th2 = th.copy(); th2[5, 3] = 50.0
+    loss, grad, _ = ops.rc_loss_grad(cu(T, th2), cu(T, x0), cu(T, u[:, :1]), cu(T, target), 3600.0, orc.RC_LB, orc.RC_UB)
+    l64, g64 = orc.rc_loss_grad(th2, x0, u[:, :1], target, 3600.0, orc.RC_LB, orc.RC_UB, np.float64)
+    lbud, gbud = orc.rc_output_sensitivity_budget(th2, x0, u[:, :1], target, 3600.0)
     assert_loss_parity(loss.cpu().numpy(), l64, lbud)
     assert_grad_parity(grad.cpu().numpy(), g64, gbud)
 

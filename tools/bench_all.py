@@ -53,11 +53,15 @@ def main():
     N3 = 65536
     u3 = torch.empty((T, N3, 5), device=dev).uniform_(0, 1, generator=g); u3[..., 0] = 15 + 10 * u3[..., 0]
     tg3 = 20 + 2 * torch.empty((T, N3), device=dev).uniform_(0, 1, generator=g)
-    s = timeit(lambda: ops.rc_loss_grad(th[:N3], x0[:N3], u3, tg3, 3600.0), a.iters)
-    emit("config3 inverse loss+grad, per-system u/target", N3 * T, s, 48, N=N3, T=T, kernel="rollout_adj_kernel<RCModel,128,12,2,MSE>")
     us, ts_ = u3[:, 0].contiguous(), tg3[:, 0].contiguous()
-    s = timeit(lambda: ops.rc_loss_grad(th[:N3], x0[:N3], us, ts_, 3600.0), a.iters)
-    emit("config3 inverse loss+grad, shared u/target (compute-bound)", N3 * T, s, None, N=N3, T=T)
+    for algo, env, B, kern in (("tangent", "1", 24, "rc_fwdsens_kernel<256,8,2,2,packed>"),
+                               ("adjoint", "0", 48, "rollout_adj_kernel<RCModel,128,12|16,2,MSE>")):
+        os.environ["DYNAX_GRAD_ALGO"] = env
+        s = timeit(lambda: ops.rc_loss_grad(th[:N3], x0[:N3], u3, tg3, 3600.0), a.iters)
+        emit(f"config3 inverse loss+grad, per-system u/target [{algo}]", N3 * T, s, B, N=N3, T=T, kernel=kern)
+        s = timeit(lambda: ops.rc_loss_grad(th[:N3], x0[:N3], us, ts_, 3600.0), a.iters)
+        emit(f"config3 inverse loss+grad, shared u/target (compute-bound) [{algo}]", N3 * T, s, None, N=N3, T=T)
+    os.environ["DYNAX_GRAD_ALGO"] = "1"
     s = timeit(lambda: ops.rc_loss_grad(nom, x0[:N3], u3, tg3, 3600.0), a.iters)
     emit("config3 shared-theta loss+grad (fp64 block sums + atomics)", N3 * T, s, 48, N=N3, T=T)
     del u3, tg3
@@ -68,7 +72,7 @@ def main():
     sch = [torch.tensor(v, dtype=torch.float32, device=dev) for v in (orc.RC_PRICE, orc.RC_T_LOW, orc.RC_T_HIGH)]
     xm = torch.tensor([20.0, 35.8, 26.0], device=dev)
     s = timeit(lambda: ops.rc_mpc_cost(nom, xm, d, um, *sch, 900.0), a.iters)
-    emit("config4 MPC cost + argmin", Nm * H, s, 4, N=Nm, H=H, kernel="rc_mpc_cost_kernel", bound="fp32 issue (ncu: 85% issue slots)")
+    emit("config4 MPC cost + argmin", Nm * H, s, 4, N=Nm, H=H, kernel="rc_mpc_cost_kernel", bound="fp32 issue slots")
     del um
     # --- config 5: neural ODE
     Nn, Tn = 262144, 2048
