@@ -64,7 +64,10 @@ int reserve(Slot &s, size_t bytes, void **out) {
 int64_t pick_tile(int64_t N, int64_t T, int64_t tile_systems, int bytes_per_system_step) {
     int64_t nt = tile_systems;
     if (nt <= 0) {
-        const int64_t budget = 512ll << 20;  // ~512 MB of streamed input per tile
+        // ~2 GB of streamed input per tile: the strided 2-D copies approach the contiguous PCIe rate only with
+        // long rows (probe on one B200, 32768 systems x 8760: 4096-system tiles 51.0 GB/s, 8192: 53.2, 16384: 54.3,
+        // one contiguous copy 55.5), and the kernels are ~100x faster than the link, so little overlap is lost
+        const int64_t budget = 2048ll << 20;
         nt = budget / (T > 0 ? T * bytes_per_system_step : 1);
         if (nt < 4096) nt = 4096;
     }
