@@ -54,6 +54,13 @@ __device__ __forceinline__ uint64_t policy_evict_first() {
     return pol;
 }
 
+// L2 policy for data every CTA re-reads (a shared input series).
+__device__ __forceinline__ uint64_t policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+
 // global -> shared bulk copy, completion signalled on an mbarrier (complete_tx::bytes).
 // dst/src 16-byte aligned, bytes a multiple of 16.
 __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar,

@@ -83,10 +83,10 @@ static int rc_forward(const float *theta, const float *x0, const float *u, float
     }
 }
 
-template <int TN, int KF, int S, int MINB, bool PACKED = false, bool SU = false, bool STG = false>
+template <int TN, int KF, int S, int MINB, bool PACKED = false, bool SU = false, bool STG = false, bool CTRL = false>
 static int launch_fwdsens(const FwdSensParams &P, cudaStream_t st) {
-    using Cfg = FwdSensCfg<TN, KF, S, SU, STG>;
-    auto kern = rc_fwdsens_kernel<TN, KF, S, MINB, PACKED, SU, STG>;
+    using Cfg = FwdSensCfg<TN, KF, S, SU, STG, CTRL>;
+    auto kern = rc_fwdsens_kernel<TN, KF, S, MINB, PACKED, SU, STG, CTRL>;
     int rc = set_smem(kern, Cfg::SMEM_BYTES);
     if (rc != DYNAX_OK) return rc;
     const int64_t grid = (P.N + TN - 1) / TN;
@@ -146,13 +146,15 @@ static int rc_adjoint(const float *theta, const float *x0, const float *u, const
     // one pass over u and target (24 B per system-step; nothing at all when both are shared series), measured
     // 2.2-2.3e11 system-steps/s against 1.3-1.4e11 for the checkpointed adjoint below on the same box.
     // DYNAX_GRAD_ALGO=0 forces the adjoint; the adjoint also serves every case the tangent kernel does not cover
-    // (shared theta, control channel, g_x0, discrete stepping, general cotangents).
-    if (MODE == ADJ_MSE && env_int("DYNAX_GRAD_ALGO", 1) == 1 && !ctrl && !g_x0 &&
+    // (shared theta, g_x0, discrete stepping, general cotangents).
+    if (MODE == ADJ_MSE && env_int("DYNAX_GRAD_ALGO", 1) == 1 && !g_x0 &&
         !(flags & (DYNAX_SHARED_THETA | DYNAX_DISCRETE))) {
         FwdSensParams F;
         F.mp = P.mp; F.x0 = x0; F.u = u; F.target = target; F.lb = lb; F.ub = ub; F.loss = loss; F.g_theta = g_theta;
+        F.ctrl = ctrl; F.ctrl_col = ctrl_col;
         F.N = N; F.T = T; F.dt = dt;
-        F.bulk = (N % 4) == 0 && (su || aligned16(u)) && (stg || aligned16(target)) && !env_int("DYNAX_NO_BULK", 0);
+        F.bulk = (N % 4) == 0 && (su || aligned16(u)) && (stg || aligned16(target)) && (!ctrl || aligned16(ctrl)) &&
+                 !env_int("DYNAX_NO_BULK", 0);
         // Every CTA runs the whole horizon, so a launch costs (waves x systems per CTA): 224-system CTAs win when they
         // save a wave (N = 65536: 293 CTAs fill the 296 slots once, 256 CTAs of 256 leave 40 SMs half empty).
         DeviceInfo di;
@@ -161,6 +163,10 @@ static int rc_adjoint(const float *theta, const float *x0, const float *u, const
         const int64_t slots = 2 * (int64_t)di.sm_count;
         auto cost = [&](int64_t tn) { return ((N + tn - 1) / tn + slots - 1) / slots * tn; };
         const bool narrow = cost(224) < cost(256) && env_int("DYNAX_FS_CFG", 0) == 0;
+        if (ctrl && stg) return narrow ? launch_fwdsens<224, 8, 2, 2, true, true, true, true>(F, st)
+                                       : launch_fwdsens<256, 8, 2, 2, true, true, true, true>(F, st);
+        if (ctrl) return narrow ? launch_fwdsens<224, 8, 2, 2, true, true, false, true>(F, st)
+                                : launch_fwdsens<256, 8, 2, 2, true, true, false, true>(F, st);
         if (su && stg) return narrow ? launch_fwdsens<224, 8, 2, 2, true, true, true>(F, st)
                                      : launch_fwdsens<256, 8, 2, 2, true, true, true>(F, st);
         if (su) return narrow ? launch_fwdsens<224, 8, 2, 2, true, true, false>(F, st)

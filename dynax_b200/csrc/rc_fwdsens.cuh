@@ -28,6 +28,8 @@ namespace dynax {
 struct FwdSensParams {
     RCModel::Ptrs mp;
     const float *x0, *u, *target;  // [N,3], [T,N,5] (SHARED_U: [T,5]), [T,N] (SHARED_TGT: [T])
+    const float *ctrl;             // CTRL mode (with SHARED_U): per-system channel [T,N] replacing column ctrl_col of u
+    int ctrl_col;
     const float *lb, *ub;          // [7] or NULL
     float *loss, *g_theta;         // [N], [N,7]
     int64_t N, T;
@@ -37,20 +39,23 @@ struct FwdSensParams {
 
 constexpr int kFsFoldSteps = 32;  // fp32 partial sums are folded into the fp64 totals every this many steps
 
-template <int TN, int KF, int S, bool SHARED_U = false, bool SHARED_TGT = false>
+template <int TN, int KF, int S, bool SHARED_U = false, bool SHARED_TGT = false, bool CTRL = false>
 struct FwdSensCfg {
     // a shared series occupies KF rows of 5 (or 1) floats per stage instead of KF x TN of them
     static constexpr int U_ROW = SHARED_U ? 5 : TN * 5, T_ROW = SHARED_TGT ? 1 : TN;
-    static constexpr int U_STAGE = (KF * U_ROW + 3) / 4 * 4, T_STAGE = (KF * T_ROW + 3) / 4 * 4, STAGE = U_STAGE + T_STAGE;
+    static constexpr int U_STAGE = (KF * U_ROW + 3) / 4 * 4, T_STAGE = (KF * T_ROW + 3) / 4 * 4;
+    static constexpr int C_STAGE = CTRL ? KF * TN : 0, STAGE = U_STAGE + T_STAGE + C_STAGE;
     static constexpr size_t RING_BYTES = sizeof(float) * (size_t)(S * STAGE) + sizeof(uint64_t) * 2 * S;
     static constexpr size_t ACC_OFF = (RING_BYTES + 15) / 16 * 16;                 // fp64 totals [8][TN] (packed path)
     static constexpr size_t SMEM_BYTES = ACC_OFF + sizeof(double) * 8 * (size_t)TN;
     static constexpr int THREADS = TN + 32;
 };
 
-template <int TN, int KF, int S, int MINB, bool PACKED = false, bool SHARED_U = false, bool SHARED_TGT = false>
+template <int TN, int KF, int S, int MINB, bool PACKED = false, bool SHARED_U = false, bool SHARED_TGT = false,
+          bool CTRL = false>
 __global__ void __launch_bounds__(TN + 32, MINB) rc_fwdsens_kernel(const FwdSensParams P) {
-    using Cfg = FwdSensCfg<TN, KF, S, SHARED_U, SHARED_TGT>;
+    static_assert(!CTRL || (SHARED_U && PACKED), "the control channel replaces a column of a SHARED input series");
+    using Cfg = FwdSensCfg<TN, KF, S, SHARED_U, SHARED_TGT, CTRL>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *s_in = reinterpret_cast<float *>(smem_raw);
     uint64_t *full = reinterpret_cast<uint64_t *>(s_in + S * Cfg::STAGE);
@@ -72,34 +77,33 @@ __global__ void __launch_bounds__(TN + 32, MINB) rc_fwdsens_kernel(const FwdSens
 
     if (tid >= TN) {  // ------------------------------- producer warp -------------------------------
         const int lane = tid - TN;
-        const uint64_t pol = ptx::policy_evict_first();
+        const uint64_t pol = ptx::policy_evict_first(), pol_keep = ptx::policy_evict_last();
         auto load_chunk = [&](int64_t c) {
             const int s = (int)(c % S);
             const int64_t k0 = c * KF;
             const int rows = (int)((T - k0) < KF ? (T - k0) : KF);
             float *du = s_in + s * Cfg::STAGE, *dtg = du + Cfg::U_STAGE;
-            // shared series: a few floats per stage, copied by the producer lanes; per-system rows: TMA (or plain
-            // loads when rows are not 16-byte aligned).  The arrive that publishes the stage comes last.
+            // Shared series: one bulk copy per block of rows when it is 16-byte aligned and sized (asynchronous, so the
+            // producer does not pay an L2 round trip per chunk), else plain loads by the producer lanes.  Per-system
+            // rows: one bulk copy per row, or plain loads.  The arrive that publishes the stage comes last.
+            uint32_t sh_tx = 0;
+            bool su_bulk = false, st_bulk = false;
             if constexpr (SHARED_U) {
                 const float *su = P.u + k0 * 5;
-                for (int i = lane; i < rows * 5; i += 32) du[i] = __ldg(su + i);
+                su_bulk = (reinterpret_cast<uintptr_t>(su) & 15) == 0 && ((rows * 20) & 15) == 0;
+                if (su_bulk) sh_tx += (uint32_t)rows * 20u;
+                else for (int i = lane; i < rows * 5; i += 32) du[i] = __ldg(su + i);
             }
             if constexpr (SHARED_TGT) {
                 const float *st = P.target + k0;
-                for (int i = lane; i < rows; i += 32) dtg[i] = __ldg(st + i);
+                st_bulk = (reinterpret_cast<uintptr_t>(st) & 15) == 0 && ((rows * 4) & 15) == 0;
+                if (st_bulk) sh_tx += (uint32_t)rows * 4u;
+                else for (int i = lane; i < rows; i += 32) dtg[i] = __ldg(st + i);
             }
-            constexpr bool ANY_ROWS = !SHARED_U || !SHARED_TGT;
-            if (ANY_ROWS && P.bulk) {
-                __syncwarp();
-                if (lane == 0) {
-                    const uint32_t ub = SHARED_U ? 0u : (uint32_t)valid * 20u, tb = SHARED_TGT ? 0u : (uint32_t)valid * 4u;
-                    ptx::mbar_arrive_expect_tx(&full[s], (ub + tb) * (uint32_t)rows);
-                    for (int r = 0; r < rows; ++r) {
-                        if constexpr (!SHARED_U) ptx::bulk_g2s(du + r * TN * 5, P.u + ((k0 + r) * N + n0) * 5, ub, &full[s], pol);
-                        if constexpr (!SHARED_TGT) ptx::bulk_g2s(dtg + r * TN, P.target + (k0 + r) * N + n0, tb, &full[s], pol);
-                    }
-                }
-            } else {
+            constexpr bool ANY_ROWS = !SHARED_U || !SHARED_TGT || CTRL;
+            float *dc = dtg + Cfg::T_STAGE;
+            const bool rows_bulk = ANY_ROWS && P.bulk;
+            if (ANY_ROWS && !rows_bulk) {  // per-system rows by plain coalesced loads (N % 4 != 0 or unaligned arrays)
                 for (int r = 0; r < rows; ++r) {
                     if constexpr (!SHARED_U) {
                         const float *su = P.u + ((k0 + r) * N + n0) * 5;
@@ -109,9 +113,29 @@ __global__ void __launch_bounds__(TN + 32, MINB) rc_fwdsens_kernel(const FwdSens
                         const float *st = P.target + (k0 + r) * N + n0;
                         for (int i = lane; i < valid; i += 32) dtg[r * TN + i] = __ldg(st + i);
                     }
+                    if constexpr (CTRL) {
+                        const float *sc = P.ctrl + (k0 + r) * N + n0;
+                        for (int i = lane; i < valid; i += 32) dc[r * TN + i] = __ldg(sc + i);
+                    }
                 }
-                __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&full[s]);
+            }
+            __syncwarp();
+            if (lane == 0) {
+                const uint32_t ub = SHARED_U ? 0u : (uint32_t)valid * 20u, tb = SHARED_TGT ? 0u : (uint32_t)valid * 4u,
+                               cb = CTRL ? (uint32_t)valid * 4u : 0u;
+                const uint32_t tx = sh_tx + (rows_bulk ? (ub + tb + cb) * (uint32_t)rows : 0u);
+                if (tx == 0) {
+                    ptx::mbar_arrive(&full[s]);  // everything was staged with plain stores
+                } else {
+                    ptx::mbar_arrive_expect_tx(&full[s], tx);
+                    if (SHARED_U && su_bulk) ptx::bulk_g2s(du, P.u + k0 * 5, (uint32_t)rows * 20u, &full[s], pol_keep);
+                    if (SHARED_TGT && st_bulk) ptx::bulk_g2s(dtg, P.target + k0, (uint32_t)rows * 4u, &full[s], pol_keep);
+                    for (int r = 0; rows_bulk && r < rows; ++r) {
+                        if constexpr (!SHARED_U) ptx::bulk_g2s(du + r * TN * 5, P.u + ((k0 + r) * N + n0) * 5, ub, &full[s], pol);
+                        if constexpr (!SHARED_TGT) ptx::bulk_g2s(dtg + r * TN, P.target + (k0 + r) * N + n0, tb, &full[s], pol);
+                        if constexpr (CTRL) ptx::bulk_g2s(dc + r * TN, P.ctrl + (k0 + r) * N + n0, cb, &full[s], pol);
+                    }
+                }
             }
         };
         for (int64_t c = 0; c < C && c < S; ++c) load_chunk(c);
@@ -154,6 +178,7 @@ __global__ void __launch_bounds__(TN + 32, MINB) rc_fwdsens_kernel(const FwdSens
         // Every lane performs the same operations in the same order as the scalar path (RCModel::rhs as nvcc
         // contracts it), so x, the loss and S are bit-identical to it; ~70 instead of ~108 instructions per step.
         float2 X01 = make_float2(x0, x1);
+        const int ccol = CTRL ? P.ctrl_col : -1;
         // fp64 totals live in shared memory ([j][tid]: conflict-free 8-byte accesses), touched once per
         // kFsFoldSteps steps: 16 registers the loop needs for its coefficients
         double *acc = reinterpret_cast<double *>(smem_raw + Cfg::ACC_OFF) + tid;
@@ -178,8 +203,13 @@ __global__ void __launch_bounds__(TN + 32, MINB) rc_fwdsens_kernel(const FwdSens
 #pragma unroll
             for (int jj = 0; jj < KF; ++jj) {
                 if (jj < rows) {
-                    const float u0 = in[jj * Cfg::U_ROW], u1 = in[jj * Cfg::U_ROW + 1], u2 = in[jj * Cfg::U_ROW + 2],
-                                u3 = in[jj * Cfg::U_ROW + 3], u4 = in[jj * Cfg::U_ROW + 4];
+                    float u0 = in[jj * Cfg::U_ROW], u1 = in[jj * Cfg::U_ROW + 1], u2 = in[jj * Cfg::U_ROW + 2],
+                          u3 = in[jj * Cfg::U_ROW + 3], u4 = in[jj * Cfg::U_ROW + 4];
+                    if constexpr (CTRL) {  // inputs assembled as in wrapper/envs/rc.py:128-131
+                        const float cv = tg[Cfg::T_STAGE + (SHARED_TGT ? tid : 0) + jj * TN];
+                        u0 = ccol == 0 ? cv : u0; u1 = ccol == 1 ? cv : u1; u2 = ccol == 2 ? cv : u2;
+                        u3 = ccol == 3 ? cv : u3; u4 = ccol == 4 ? cv : u4;
+                    }
                     const float res = X01.x - tg[jj * Cfg::T_ROW];   // PRE-update state (simulator.py:38)
                     sq = fmaf(res, res, sq);
                     const float gy = c2T * res;

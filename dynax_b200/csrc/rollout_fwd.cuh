@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_fwd_kernel(const FwdPar
     if (tid >= TN) {
         // ------------------------------- producer warp -------------------------------
         const int lane = tid - TN;
-        const uint64_t pol = ptx::policy_evict_first();
+        const uint64_t pol = ptx::policy_evict_first(), pol_keep = ptx::policy_evict_last();
 
         auto load_chunk = [&](int64_t c) {
             const int s = (int)(c % S);
@@ -120,18 +120,27 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_fwd_kernel(const FwdPar
             float *dst = s_in + s * IN_STAGE;
             if (SHARED_U) {
                 const float *src = u_base + k0 * m;  // [T,1,m] is contiguous in k
-                for (int i = lane; i < rows * m; i += 32) dst[i] = __ldg(src + i);
+                // the shared rows of a chunk are one contiguous block: a single bulk copy when it is 16-byte
+                // aligned and sized (asynchronous, so the producer runs S chunks ahead instead of paying an L2
+                // round trip per chunk), plain loads otherwise (ragged last chunk, odd offsets)
+                const uint32_t sh_bytes = (uint32_t)(rows * m) * 4u;
+                const bool sh_bulk = (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (sh_bytes & 15u) == 0;
+                if (!sh_bulk)
+                    for (int i = lane; i < rows * m; i += 32) dst[i] = __ldg(src + i);
                 const float *csrc = P.ctrl ? P.ctrl + (t_begin + k0) * N + n0 : nullptr;
                 float *cdst = dst + Cfg::CTRL_OFF;
-                if (csrc && !P.bulk_in)
+                const bool c_bulk = csrc && P.bulk_in;
+                if (csrc && !c_bulk)
                     for (int r = 0; r < rows; ++r)
                         for (int i = lane; i < valid; i += 32) cdst[r * TN + i] = __ldg(csrc + r * N + i);
                 __syncwarp();
                 if (lane == 0) {
-                    if (csrc && P.bulk_in) {
+                    if (sh_bulk || c_bulk) {
                         const uint32_t row_bytes = (uint32_t)valid * 4u;
-                        ptx::mbar_arrive_expect_tx(&full[s], row_bytes * (uint32_t)rows);
-                        for (int r = 0; r < rows; ++r) ptx::bulk_g2s(cdst + r * TN, csrc + r * N, row_bytes, &full[s], pol);
+                        ptx::mbar_arrive_expect_tx(&full[s], (sh_bulk ? sh_bytes : 0u) + (c_bulk ? row_bytes * (uint32_t)rows : 0u));
+                        if (sh_bulk) ptx::bulk_g2s(dst, src, sh_bytes, &full[s], pol_keep);
+                        if (c_bulk)
+                            for (int r = 0; r < rows; ++r) ptx::bulk_g2s(cdst + r * TN, csrc + r * N, row_bytes, &full[s], pol);
                     } else {
                         ptx::mbar_arrive(&full[s]);
                     }

@@ -53,9 +53,11 @@ def test_tabular_random_vs_oracle(T):
             assert (np.abs(got - ref).max(1) < 1e-6).mean() > 0.999   # ties at exact halves may differ in fp32
 
 
+@pytest.mark.parametrize("algo", ["1", "0"])     # DYNAX_GRAD_ALGO: tangent / adjoint kernel
 @pytest.mark.parametrize("N,Tn", [(512, 700), (130, 96), (3, 10)])
-def test_forward_and_grad_with_control_channel(T, N, Tn):
+def test_forward_and_grad_with_control_channel(T, monkeypatch, N, Tn, algo):
     from dynax_b200 import ops
+    monkeypatch.setenv("DYNAX_GRAD_ALGO", algo)
     th, x0, u = orc.synth_theta(N, 122), orc.synth_x0(N, 122), orc.synth_u(Tn, N, 122)
     d = u[:, 0].copy()                      # one shared disturbance series [T,5] ...
     ctrl = u[:, :, 2].copy()                # ... and a per-system HVAC channel [T,N]
@@ -77,3 +79,14 @@ def test_forward_and_grad_with_control_channel(T, N, Tn):
     l2, g2, _ = ops.rc_loss_grad(cu(T, th), cu(T, x0), cu(T, u_full), cu(T, target), 3600.0, orc.RC_LB, orc.RC_UB)
     assert np.allclose(loss.cpu().numpy(), l2.cpu().numpy(), rtol=1e-5)
     assert (np.abs(grad.cpu().numpy() - g2.cpu().numpy()) <= 2 * (1e-4 * np.abs(g64) + gbud)).all()
+    if algo == "1":     # the tangent kernel performs identical arithmetic whichever way the inputs are staged
+        assert T.equal(loss, l2) and T.equal(grad, g2)
+    # another column, ONE shared target series
+    col = 0
+    u_full0 = np.repeat(d[:, None, :], N, 1); u_full0[:, :, col] = 15 + ctrl
+    loss, grad, _ = ops.rc_loss_grad_ctrl(cu(T, th), cu(T, x0), cu(T, d), cu(T, 15 + ctrl), cu(T, target[:, 0]), 3600.0,
+                                          ctrl_col=col)
+    l64, g64 = orc.rc_loss_grad(th, x0, u_full0, target[:, :1], 3600.0, None, None)
+    lbud, gbud = orc.rc_output_sensitivity_budget(th, x0, u_full0, target[:, :1], 3600.0)
+    assert_loss_parity(loss.cpu().numpy(), l64, lbud)
+    assert_grad_parity(grad.cpu().numpy(), g64, gbud)
