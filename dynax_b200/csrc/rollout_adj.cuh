@@ -70,7 +70,14 @@ struct AdjCfg {
     static constexpr int A3_OFF = A2_OFF + align4i(KC * A2_ROW);                       // per-system channel (ctrl)
     static constexpr int STAGE = A3_OFF + (SHARED_U ? KC * TN : 0);
     static constexpr int NBAR = 2 * S;
-    static constexpr size_t SMEM_BYTES = sizeof(float) * (size_t)(S * STAGE) + sizeof(uint64_t) * NBAR;
+    // Models with many gradient accumulators (dense LTI: n*n + n*m + p*n + p*m) keep the fp64 totals in shared
+    // memory ([NG][TN] doubles, conflict-free 8-byte accesses) and fold into them every GT_FOLD segments: as 2*NG
+    // registers they push the kernel to 255 registers plus spills and one CTA per SM.
+    static constexpr bool GT_SMEM = Model::NG > 16;
+    static constexpr int GT_FOLD = GT_SMEM ? 4 : 1;
+    static constexpr size_t RING_BYTES = sizeof(float) * (size_t)(S * STAGE) + sizeof(uint64_t) * NBAR;
+    static constexpr size_t GT_OFF = (RING_BYTES + 15) / 16 * 16;
+    static constexpr size_t SMEM_BYTES = GT_SMEM ? GT_OFF + sizeof(double) * Model::NG * (size_t)TN : RING_BYTES;
     static constexpr int THREADS = TN + 32;
 };
 
@@ -237,7 +244,9 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_adj_kernel(const AdjPar
     // ---- phase 2: reverse sweep
     float a[n];  // adjoint of x_{k+1}
     float Gp[NG];
-    double Gt[NG];
+    constexpr bool GT_SMEM = Cfg::GT_SMEM;
+    double Gt[GT_SMEM ? 1 : NG];
+    double *const gt_s = reinterpret_cast<double *>(smem_raw + Cfg::GT_OFF) + tid;  // used only if GT_SMEM
     float sq = 0.f;
     double sqt = 0.0;
 #pragma unroll
@@ -245,7 +254,8 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_adj_kernel(const AdjPar
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
         Gp[g] = 0.f;
-        Gt[g] = 0.0;
+        if constexpr (GT_SMEM) gt_s[g * TN] = 0.0;
+        else Gt[g] = 0.0;
     }
     const float c2T = 2.0f / (float)P.T;  // the mean runs over the WHOLE horizon, also in a chunked launch
 
@@ -318,15 +328,18 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_adj_kernel(const AdjPar
         }
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&empty[s]);
-        // fold the segment's fp32 partial sums into the fp64 totals
+        // fold the fp32 partial sums into the fp64 totals (every segment; every GT_FOLD segments if they live in smem)
+        if (Cfg::GT_FOLD == 1 || seg == 0 || (C - seg) % Cfg::GT_FOLD == 0) {
 #pragma unroll
-        for (int g = 0; g < NG; ++g) {
-            Gt[g] += (double)Gp[g];
-            Gp[g] = 0.f;
-        }
-        if (MODE == ADJ_MSE) {
-            sqt += (double)sq;
-            sq = 0.f;
+            for (int g = 0; g < NG; ++g) {
+                if constexpr (GT_SMEM) gt_s[g * TN] += (double)Gp[g];
+                else Gt[g] += (double)Gp[g];
+                Gp[g] = 0.f;
+            }
+            if (MODE == ADJ_MSE) {
+                sqt += (double)sq;
+                sq = 0.f;
+            }
         }
     }
 
@@ -337,7 +350,14 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_adj_kernel(const AdjPar
     }
     if (P.skip_grads) return;
     double g[NOUT];
-    M.finalize(Gt, P.mp, i, g);  // linear in the accumulators, so per-chunk results simply add
+    if constexpr (GT_SMEM) {
+        double Gl[NG];
+#pragma unroll
+        for (int q = 0; q < NG; ++q) Gl[q] = gt_s[q * TN];
+        M.finalize(Gl, P.mp, i, g);
+    } else {
+        M.finalize(Gt, P.mp, i, g);  // linear in the accumulators, so per-chunk results simply add
+    }
     double loss = (MODE == ADJ_MSE) ? sqt / (double)P.T : 0.0;
     if (P.chunk_acc != nullptr) {
         if (active) {
