@@ -127,6 +127,7 @@ constexpr size_t SMEM_BYTES = SMEM_USED > 100 * 1024 ? SMEM_USED : 100 * 1024;
 
 }  // namespace tc
 
+#ifndef DYNAX_NODE_TC_HELPERS_ONLY  // node_vjp_tc.cuh reuses the tc:: helpers above without this kernel
 __global__ void __launch_bounds__(tc::TN + 32, 2) node_tc_kernel(const NodeTcParams P) {
     using namespace tc;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -374,5 +375,6 @@ __global__ void __launch_bounds__(tc::TN + 32, 2) node_tc_kernel(const NodeTcPar
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
     }
 }
+#endif  // DYNAX_NODE_TC_HELPERS_ONLY
 
 }  // namespace dynax

@@ -16,8 +16,11 @@
 // PARITY UNPINNED BY THE REFERENCE; the test oracle is torch autograd (fp64) over the restated rollout.
 #include <string.h>
 
+#include <stdlib.h>
+
 #include "api_common.cuh"
 #include "mlp_model.cuh"
+#include "node_vjp_tc.cuh"
 
 namespace dynax {
 
@@ -69,16 +72,18 @@ __global__ void __launch_bounds__(nv::TN, 1) node_vjp_kernel(const NodeVjpParams
         for (int b = 0; b < 8; ++b) aW2[a][b] = 0.f;
     }
     aW3[0] = aW3[1] = 0.f;
-    const int j0 = (tid >> 3) * 4, i0 = (tid & 7) * 8;          // dW2 patch rows j0..j0+3, cols i0..i0+7
+    // dW2 patch: rows j0..j0+3, cols i0 + 8b (interleaved: the 8 lanes of a quarter-warp then read 8 CONSECUTIVE tile
+    // rows, which LD = 132 spreads over all 32 banks; 8 rows apart they would all hit the same banks)
+    const int j0 = (tid >> 3) * 4, i0 = tid & 7;
     const int w1i = tid >> 1, w1c = (tid & 1) * 4;              // dW1[w1i][w1c..w1c+3]
-    const int w3d = tid >> 5, w3j = (tid & 31) * 2;             // dW3[w3d][w3j..w3j+1]   (tid < 96)
+    const int w3d = tid >> 5, w3j = tid & 31;                   // dW3[w3d][w3j], dW3[w3d][w3j + 32]   (tid < 96)
 
     auto flush = [&]() {
 #pragma unroll
         for (int a = 0; a < 4; ++a)
 #pragma unroll
             for (int b = 0; b < 8; ++b) {
-                atomicAdd(P.acc + A_W2 + (j0 + a) * HID + i0 + b, (double)aW2[a][b]);
+                atomicAdd(P.acc + A_W2 + (j0 + a) * HID + i0 + 8 * b, (double)aW2[a][b]);
                 aW2[a][b] = 0.f;
             }
 #pragma unroll
@@ -88,7 +93,7 @@ __global__ void __launch_bounds__(nv::TN, 1) node_vjp_kernel(const NodeVjpParams
         }
         if (tid < 96) {
             atomicAdd(P.acc + A_W3 + w3d * HID + w3j, (double)aW3[0]);
-            atomicAdd(P.acc + A_W3 + w3d * HID + w3j + 1, (double)aW3[1]);
+            atomicAdd(P.acc + A_W3 + w3d * HID + w3j + 32, (double)aW3[1]);
         }
         aW3[0] = aW3[1] = 0.f;
         atomicAdd(P.acc + (tid < 64 ? A_B2 + tid : A_B1 + tid - 64), (double)aB);
@@ -161,7 +166,7 @@ __global__ void __launch_bounds__(nv::TN, 1) node_vjp_kernel(const NodeVjpParams
 #pragma unroll
             for (int a = 0; a < 4; ++a) dj[a] = *reinterpret_cast<const float4 *>(D2 + (j0 + a) * LD + r);
 #pragma unroll
-            for (int b = 0; b < 8; ++b) hi[b] = *reinterpret_cast<const float4 *>(H1 + (i0 + b) * LD + r);
+            for (int b = 0; b < 8; ++b) hi[b] = *reinterpret_cast<const float4 *>(H1 + (i0 + 8 * b) * LD + r);
 #pragma unroll
             for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -180,7 +185,7 @@ __global__ void __launch_bounds__(nv::TN, 1) node_vjp_kernel(const NodeVjpParams
                 const float4 d3r = *reinterpret_cast<const float4 *>(D3 + w3d * LD + r);
 #pragma unroll
                 for (int a = 0; a < 2; ++a) {
-                    const float4 hr = *reinterpret_cast<const float4 *>(H2 + (w3j + a) * LD + r);
+                    const float4 hr = *reinterpret_cast<const float4 *>(H2 + (w3j + 32 * a) * LD + r);
                     aW3[a] = fmaf(d3r.x, hr.x, aW3[a]); aW3[a] = fmaf(d3r.y, hr.y, aW3[a]);
                     aW3[a] = fmaf(d3r.z, hr.z, aW3[a]); aW3[a] = fmaf(d3r.w, hr.w, aW3[a]);
                 }
@@ -308,9 +313,21 @@ int dynax_node_rk4_vjp_f32(const float *W1, const float *b1, const float *W2, co
     P.x0 = x0; P.u = u; P.xsol = xsol; P.g_xsol = g_xsol; P.g_ysol = g_ysol; P.g_x0 = g_x0; P.g_u = g_u;
     P.acc = reinterpret_cast<double *>(ws); P.N = N; P.T = T; P.dt = dt;
     DYNAX_CUDA_TRY(cudaMemsetAsync(ws, 0, need, st));
-    rc = set_smem(node_vjp_kernel, nv::SMEM_BYTES);
-    if (rc != DYNAX_OK) return rc;
-    node_vjp_kernel<<<(unsigned)((N + nv::TN - 1) / nv::TN), nv::TN, nv::SMEM_BYTES, st>>>(P);
+    static_assert(vtc::A_END == nv::A_END, "both kernels share the accumulator layout");
+    const char *impl = getenv("DYNAX_NODE_VJP_IMPL");  // "0": CUDA-core kernel; default: tcgen05 kernel
+    if (impl && impl[0] == '0') {
+        rc = set_smem(node_vjp_kernel, nv::SMEM_BYTES);
+        if (rc != DYNAX_OK) return rc;
+        node_vjp_kernel<<<(unsigned)((N + nv::TN - 1) / nv::TN), nv::TN, nv::SMEM_BYTES, st>>>(P);
+    } else {
+        NodeVjpTcParams Q;
+        Q.W1 = W1; Q.b1 = b1; Q.W2 = W2; Q.b2 = b2; Q.W3 = W3; Q.b3 = b3;
+        Q.x0 = x0; Q.u = u; Q.xsol = xsol; Q.g_xsol = g_xsol; Q.g_ysol = g_ysol; Q.g_x0 = g_x0; Q.g_u = g_u;
+        Q.acc = P.acc; Q.N = N; Q.T = T; Q.dt = dt; Q.rk4 = P.mp.rk4;
+        rc = set_smem(node_vjp_tc_kernel, vtc::SMEM_BYTES);
+        if (rc != DYNAX_OK) return rc;
+        node_vjp_tc_kernel<<<(unsigned)((N + vtc::TN - 1) / vtc::TN), vtc::TN, vtc::SMEM_BYTES, st>>>(Q);
+    }
     DYNAX_CUDA_TRY(cudaGetLastError());
     node_vjp_finalize_kernel<<<(nv::A_END + 255) / 256, 256, 0, st>>>(P.acc, gW1, gb1, gW2, gb2, gW3, gb3);
     DYNAX_CUDA_TRY(cudaGetLastError());

@@ -90,10 +90,14 @@ def _torch_node_rollout(T, W, x0, u, dt, euler):
     return T.stack(xs), T.stack(ys)
 
 
+@pytest.mark.parametrize("impl", ["tc", "cuda_core"])
 @pytest.mark.parametrize("N,Tn,euler,scale", [(200, 24, False, 0.5), (130, 17, True, 1.0), (3, 5, False, 0.3), (256, 40, False, 0.1)])
-def test_vjp_matches_torch_autograd_fp64(T, N, Tn, euler, scale):
-    """Oracle = torch autograd (fp64, CPU) over the restated RK4-MLP rollout (the reference has neither)."""
+def test_vjp_matches_torch_autograd_fp64(T, monkeypatch, N, Tn, euler, scale, impl):
+    """Oracle = torch autograd (fp64, CPU) over the restated RK4-MLP rollout (the reference has neither).
+    Both VJP kernels: tcgen05 (default) and CUDA cores (DYNAX_NODE_VJP_IMPL=0)."""
     from dynax_b200 import ops
+    if impl == "cuda_core":
+        monkeypatch.setenv("DYNAX_NODE_VJP_IMPL", "0")
     Wnp = orc.synth_mlp(109, scale=scale)
     x0, u = inputs(N, Tn, 110)
     rng = np.random.default_rng(111)
