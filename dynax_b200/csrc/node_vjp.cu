@@ -326,7 +326,7 @@ int dynax_node_rk4_vjp_f32(const float *W1, const float *b1, const float *W2, co
         Q.acc = P.acc; Q.N = N; Q.T = T; Q.dt = dt; Q.rk4 = P.mp.rk4;
         rc = set_smem(node_vjp_tc_kernel, vtc::SMEM_BYTES);
         if (rc != DYNAX_OK) return rc;
-        node_vjp_tc_kernel<<<(unsigned)((N + vtc::TN - 1) / vtc::TN), vtc::TN, vtc::SMEM_BYTES, st>>>(Q);
+        node_vjp_tc_kernel<<<(unsigned)((N + vtc::TN - 1) / vtc::TN), vtc::NTHR, vtc::SMEM_BYTES, st>>>(Q);
     }
     DYNAX_CUDA_TRY(cudaGetLastError());
     node_vjp_finalize_kernel<<<(nv::A_END + 255) / 256, 256, 0, st>>>(P.acc, gW1, gb1, gW2, gb2, gW3, gb3);

@@ -18,7 +18,10 @@
 //   window 1 of the NEXT stage (z W1^T in flight): dW1, db1 of the previous stage (Z tile double-buffered)
 // fp32 register accumulators, flushed to fp64 global accumulators every 16 steps (as node_vjp.cu).
 // Stage points are recomputed from the saved forward trajectory with three forward evaluations per step.
-// One CTA per SM (225 KB of shared memory: weights + transposed copies, hi and lo, 79 KB; tiles 146 KB).
+// One CTA per SM (225 KB of shared memory: weights + transposed copies, hi and lo, 79 KB; tiles 146 KB), so the CTA
+// runs TWO threads per trajectory (256 threads; thread t and t+128 share row t & 127 and TMEM lane quadrant
+// (t/32) % 4): each owns 32 of the 64 hidden columns in the tanh / split / tile phases and 64 of the 128 rows in
+// the weight-gradient contractions, which gives every SM sub-partition two warps to interleave.
 // PARITY UNPINNED BY THE REFERENCE; pinned to torch-autograd fp64 and to the CUDA-core kernel by the tests.
 #pragma once
 #define DYNAX_NODE_TC_HELPERS_ONLY
@@ -40,6 +43,7 @@ namespace vtc {
 using namespace tc;
 
 constexpr int LD = 132;  // padded tile row: conflict-free float4 rows
+constexpr int NTHR = 2 * TN, HC = HID / 2;  // two threads per row, HC hidden columns each
 constexpr uint32_t IDESC16 = (1u << 4) | (2u << 7) | (2u << 10) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
 constexpr uint32_t LBO16 = 256;  // N = 16: two 8-row groups of 128 B per 16-byte K chunk
 __device__ __forceinline__ int wofs16(int n, int k) { return (k >> 2) * 64 + (n >> 3) * 32 + (n & 7) * 4 + (k & 3); }
@@ -61,7 +65,8 @@ constexpr int G_W2HI = 0, G_W2LO = G_W2HI + HID * HID, G_W2THI = G_W2LO + HID * 
               G_W1HI = G_W2TLO + HID * HID, G_W1LO = G_W1HI + HID * NIN, G_W1THI = G_W1LO + HID * NIN,
               G_W1TLO = G_W1THI + 16 * HID, G_B1 = G_W1TLO + 16 * HID, G_B2 = G_B1 + HID, G_W3 = G_B2 + HID,
               G_B3 = G_W3 + NX * HID, T_H1 = G_B3 + 4, T_H2 = T_H1 + HID * LD, T_D2 = T_H2 + HID * LD,
-              T_D1 = T_D2 + HID * LD, T_Z = T_D1 + HID * LD, T_D3 = T_Z + 2 * NIN * LD, G_END = T_D3 + 4 * LD;
+              T_D1 = T_D2 + HID * LD, T_Z = T_D1 + HID * LD, T_D3 = T_Z + 2 * NIN * LD, T_R = T_D3 + 4 * LD,
+              G_END = T_R + 2 * 4 * TN;  // T_R: the two column halves' partial sums of the 64 -> 3 output layer
 constexpr size_t SMEM_BYTES = sizeof(float) * G_END + sizeof(uint64_t) + 16;
 // fp64 accumulator layout (identical to nv:: in node_vjp.cu)
 constexpr int A_W1 = 0, A_B1 = A_W1 + HID * NIN, A_W2 = A_B1 + HID, A_B2 = A_W2 + HID * HID, A_W3 = A_B2 + HID,
@@ -69,17 +74,20 @@ constexpr int A_W1 = 0, A_B1 = A_W1 + HID * NIN, A_W2 = A_B1 + HID, A_B2 = A_W2 
 constexpr int FLUSH = 16;
 }  // namespace vtc
 
-__global__ void __launch_bounds__(vtc::TN, 1) node_vjp_tc_kernel(const NodeVjpTcParams P) {
+__global__ void __launch_bounds__(vtc::NTHR, 1) node_vjp_tc_kernel(const NodeVjpTcParams P) {
     using namespace vtc;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *sm = reinterpret_cast<float *>(smem_raw);
-    float *H1 = sm + T_H1, *H2 = sm + T_H2, *D2 = sm + T_D2, *D1 = sm + T_D1, *Zt = sm + T_Z, *D3 = sm + T_D3;
+    float *H1 = sm + T_H1, *H2 = sm + T_H2, *D2 = sm + T_D2, *D1 = sm + T_D1, *Zt = sm + T_Z, *D3 = sm + T_D3, *R = sm + T_R;
     uint64_t *mma_bar = reinterpret_cast<uint64_t *>(sm + G_END);
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(mma_bar + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5;
+    const int row = tid & (TN - 1), half = tid >> 7;  // this thread's trajectory / column half (and row half)
+    const int c_lo = half * HC;                       // hidden columns c_lo .. c_lo + HC - 1
+    const int r_lo = half * (TN / 2);                 // tile rows r_lo .. r_lo + TN/2 - 1 in the contractions
     const int64_t N = P.N, T = P.T;
-    const int64_t i = (int64_t)blockIdx.x * TN + tid;
+    const int64_t i = (int64_t)blockIdx.x * TN + row;
     const bool active = i < N;
     const int64_t iu = active ? i : 0;
 
@@ -88,7 +96,7 @@ __global__ void __launch_bounds__(vtc::TN, 1) node_vjp_tc_kernel(const NodeVjpTc
         ptx::mbar_init(mma_bar, 1);
         ptx::fence_mbar_init();
     }
-    for (int e = tid; e < HID * HID; e += TN) {
+    for (int e = tid; e < HID * HID; e += NTHR) {
         const int j = e / HID, c = e % HID;  // W2[j][c]: output j, input c
         uint32_t hi, lo;
         split_tf32(__ldg(P.W2 + e), hi, lo);
@@ -97,12 +105,12 @@ __global__ void __launch_bounds__(vtc::TN, 1) node_vjp_tc_kernel(const NodeVjpTc
         sm[G_W2THI + wofs(c, j)] = __uint_as_float(hi);  // backward: B[n = c][k = j]
         sm[G_W2TLO + wofs(c, j)] = __uint_as_float(lo);
     }
-    for (int e = tid; e < 16 * HID; e += TN) {  // zero the padded rows 8..15 of the W1^T tile
+    for (int e = tid; e < 16 * HID; e += NTHR) {  // zero the padded rows 8..15 of the W1^T tile
         sm[G_W1THI + e] = 0.f;
         sm[G_W1TLO + e] = 0.f;
     }
     __syncthreads();
-    for (int e = tid; e < HID * NIN; e += TN) {
+    for (int e = tid; e < HID * NIN; e += NTHR) {
         const int a = e / NIN, c = e % NIN;  // W1[a][c]: hidden a, input c
         uint32_t hi, lo;
         split_tf32(__ldg(P.W1 + e), hi, lo);
@@ -111,11 +119,11 @@ __global__ void __launch_bounds__(vtc::TN, 1) node_vjp_tc_kernel(const NodeVjpTc
         sm[G_W1THI + wofs16(c, a)] = __uint_as_float(hi);
         sm[G_W1TLO + wofs16(c, a)] = __uint_as_float(lo);
     }
-    for (int e = tid; e < HID; e += TN) {
+    for (int e = tid; e < HID; e += NTHR) {
         sm[G_B1 + e] = __ldg(P.b1 + e);
         sm[G_B2 + e] = __ldg(P.b2 + e);
     }
-    for (int e = tid; e < NX * HID; e += TN) sm[G_W3 + e] = __ldg(P.W3 + e);
+    for (int e = tid; e < NX * HID; e += NTHR) sm[G_W3 + e] = __ldg(P.W3 + e);
     if (tid < NX) sm[G_B3 + tid] = __ldg(P.b3 + tid);
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ptx::smem_u32(s_tmem)),
@@ -128,7 +136,7 @@ __global__ void __launch_bounds__(vtc::TN, 1) node_vjp_tc_kernel(const NodeVjpTc
     __syncthreads();
     fence_after();
     const uint32_t tmem = *s_tmem;
-    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);  // a warp reaches TMEM lanes 32 (w % 4) ..
     const uint64_t dW1hi = smem_desc(sm + G_W1HI), dW1lo = smem_desc(sm + G_W1LO);
     const uint64_t dW2hi = smem_desc(sm + G_W2HI), dW2lo = smem_desc(sm + G_W2LO);
     const uint64_t dW2Thi = smem_desc(sm + G_W2THI), dW2Tlo = smem_desc(sm + G_W2TLO);
@@ -148,9 +156,9 @@ __global__ void __launch_bounds__(vtc::TN, 1) node_vjp_tc_kernel(const NodeVjpTc
     aW3[0] = aW3[1] = 0.f;
     // dW2 patch: rows j0..j0+3, cols i0 + 8b (interleaved: the 8 lanes of a quarter-warp then read 8 CONSECUTIVE tile
     // rows, which LD = 132 spreads over all 32 banks; 8 rows apart they would all hit the same banks)
-    const int j0 = (tid >> 3) * 4, i0 = tid & 7;
-    const int w1i = tid >> 1, w1c = (tid & 1) * 4;      // dW1[w1i][w1c..w1c+3]
-    const int w3d = tid >> 5, w3j = tid & 31;           // dW3[w3d][w3j], dW3[w3d][w3j + 32]   (tid < 96)
+    const int j0 = (row >> 3) * 4, i0 = row & 7;
+    const int w1i = row >> 1, w1c = (row & 1) * 4;      // dW1[w1i][w1c..w1c+3]
+    const int w3d = row >> 5, w3j = row & 31;           // dW3[w3d][w3j], dW3[w3d][w3j + 32]   (row < 96)
 
     auto flush = [&]() {
 #pragma unroll
@@ -165,18 +173,18 @@ __global__ void __launch_bounds__(vtc::TN, 1) node_vjp_tc_kernel(const NodeVjpTc
             atomicAdd(P.acc + A_W1 + w1i * NIN + w1c + a, (double)aW1[a]);
             aW1[a] = 0.f;
         }
-        if (tid < 96) {
+        if (row < 96) {
             atomicAdd(P.acc + A_W3 + w3d * HID + w3j, (double)aW3[0]);
             atomicAdd(P.acc + A_W3 + w3d * HID + w3j + 32, (double)aW3[1]);
         }
         aW3[0] = aW3[1] = 0.f;
-        atomicAdd(P.acc + (tid < 64 ? A_B2 + tid : A_B1 + tid - 64), (double)aB);
+        atomicAdd(P.acc + (row < 64 ? A_B2 + row : A_B1 + row - 64), (double)aB);
         aB = 0.f;
-        if (tid < NX) atomicAdd(P.acc + A_B3 + tid, (double)aB3);
+        if (row < NX) atomicAdd(P.acc + A_B3 + row, (double)aB3);
         aB3 = 0.f;
     };
 
-    // ---- tile contractions over the CTA's 128 rows (run inside the MMA windows)
+    // ---- tile contractions (run inside the MMA windows); this thread covers tile rows r_lo .. r_lo + 63
     auto contract_w2 = [&](int r_begin, int r_end) {
         for (int r = r_begin; r < r_end; r += 4) {
             float4 dj[4], hi[8];
@@ -194,8 +202,8 @@ __global__ void __launch_bounds__(vtc::TN, 1) node_vjp_tc_kernel(const NodeVjpTc
         }
     };
     auto contract_w3_b3_b2 = [&]() {
-        for (int r = 0; r < TN; r += 4) {
-            if (tid < 96) {
+        for (int r = r_lo; r < r_lo + TN / 2; r += 4) {
+            if (row < 96) {
                 const float4 d3r = *reinterpret_cast<const float4 *>(D3 + w3d * LD + r);
 #pragma unroll
                 for (int a = 0; a < 2; ++a) {
@@ -204,19 +212,19 @@ __global__ void __launch_bounds__(vtc::TN, 1) node_vjp_tc_kernel(const NodeVjpTc
                     aW3[a] = fmaf(d3r.z, hr.z, aW3[a]); aW3[a] = fmaf(d3r.w, hr.w, aW3[a]);
                 }
             }
-            if (tid < 64) {
-                const float4 br = *reinterpret_cast<const float4 *>(D2 + tid * LD + r);
+            if (row < 64) {
+                const float4 br = *reinterpret_cast<const float4 *>(D2 + row * LD + r);
                 aB += (br.x + br.y) + (br.z + br.w);
             }
-            if (tid < NX) {
-                const float4 b3 = *reinterpret_cast<const float4 *>(D3 + tid * LD + r);
+            if (row < NX) {
+                const float4 b3 = *reinterpret_cast<const float4 *>(D3 + row * LD + r);
                 aB3 += (b3.x + b3.y) + (b3.z + b3.w);
             }
         }
     };
     auto contract_w1_b1 = [&](int zbuf) {
         const float *Z = Zt + zbuf * NIN * LD;
-        for (int r = 0; r < TN; r += 4) {
+        for (int r = r_lo; r < r_lo + TN / 2; r += 4) {
             const float4 d1r = *reinterpret_cast<const float4 *>(D1 + w1i * LD + r);
 #pragma unroll
             for (int a = 0; a < 4; ++a) {
@@ -224,8 +232,8 @@ __global__ void __launch_bounds__(vtc::TN, 1) node_vjp_tc_kernel(const NodeVjpTc
                 aW1[a] = fmaf(d1r.x, zr.x, aW1[a]); aW1[a] = fmaf(d1r.y, zr.y, aW1[a]);
                 aW1[a] = fmaf(d1r.z, zr.z, aW1[a]); aW1[a] = fmaf(d1r.w, zr.w, aW1[a]);
             }
-            if (tid >= 64) {
-                const float4 br = *reinterpret_cast<const float4 *>(D1 + (tid - 64) * LD + r);
+            if (row >= 64) {
+                const float4 br = *reinterpret_cast<const float4 *>(D1 + (row - 64) * LD + r);
                 aB += (br.x + br.y) + (br.z + br.w);
             }
         }
@@ -266,15 +274,17 @@ __global__ void __launch_bounds__(vtc::TN, 1) node_vjp_tc_kernel(const NodeVjpTc
             mma_commit(mma_bar);
         }
     };
-    auto store_z = [&](const float *z) {
-        uint32_t hi[NIN], lo[NIN];
+    auto store_z = [&](const float *z) {  // the 8 input columns: written by the row's first thread
+        if (half == 0) {
+            uint32_t hi[NIN], lo[NIN];
 #pragma unroll
-        for (int c = 0; c < NIN; ++c) split_tf32(z[c], hi[c], lo[c]);
-        tmem_st8(lane_base + COL_AHI, hi);
-        tmem_st8(lane_base + COL_ALO, lo);
+            for (int c = 0; c < NIN; ++c) split_tf32(z[c], hi[c], lo[c]);
+            tmem_st8(lane_base + COL_AHI, hi);
+            tmem_st8(lane_base + COL_ALO, lo);
+        }
     };
 
-    // forward evaluation only (stage points): r = MLP(z)
+    // forward evaluation only (stage points): r = MLP(z).  Both threads of a row return the same r.
     auto mlp_forward = [&](const float *z, float *r) {
         uint32_t hi[16], lo[16];
         store_z(z);
@@ -282,7 +292,8 @@ __global__ void __launch_bounds__(vtc::TN, 1) node_vjp_tc_kernel(const NodeVjpTc
         issue_l1();
         mma_wait();
 #pragma unroll
-        for (int c = 0; c < HID; c += 16) {
+        for (int cc = 0; cc < HC; cc += 16) {
+            const int c = c_lo + cc;
             float v[16];
             tmem_ld16(lane_base + COL_D + c, v);
 #pragma unroll
@@ -298,10 +309,12 @@ __global__ void __launch_bounds__(vtc::TN, 1) node_vjp_tc_kernel(const NodeVjpTc
         a_ready();
         issue_k64(dW2hi, dW2lo, IDESC, LBO);
         mma_wait();
+        float pr[NX];
 #pragma unroll
-        for (int d = 0; d < NX; ++d) r[d] = sm[G_B3 + d];
+        for (int d = 0; d < NX; ++d) pr[d] = 0.f;
 #pragma unroll
-        for (int c = 0; c < HID; c += 16) {
+        for (int cc = 0; cc < HC; cc += 16) {
+            const int c = c_lo + cc;
             float v[16];
             tmem_ld16(lane_base + COL_D + c, v);
 #pragma unroll
@@ -310,25 +323,33 @@ __global__ void __launch_bounds__(vtc::TN, 1) node_vjp_tc_kernel(const NodeVjpTc
                 fast_tanh2(v[j] + sm[G_B2 + c + j], v[j + 1] + sm[G_B2 + c + j + 1], h0, h1);
 #pragma unroll
                 for (int d = 0; d < NX; ++d) {
-                    r[d] = fmaf(sm[G_W3 + d * HID + c + j], h0, r[d]);
-                    r[d] = fmaf(sm[G_W3 + d * HID + c + j + 1], h1, r[d]);
+                    pr[d] = fmaf(sm[G_W3 + d * HID + c + j], h0, pr[d]);
+                    pr[d] = fmaf(sm[G_W3 + d * HID + c + j + 1], h1, pr[d]);
                 }
             }
         }
+        // exchange the two halves' partial sums of the output layer (same order in both threads)
+#pragma unroll
+        for (int d = 0; d < NX; ++d) R[(half * 4 + d) * TN + row] = pr[d];
+        __syncthreads();
+#pragma unroll
+        for (int d = 0; d < NX; ++d) r[d] = sm[G_B3 + d] + (R[d * TN + row] + R[(4 + d) * TN + row]);
     };
 
     int zbuf = 0;             // Z tile buffer the NEXT backward stage writes
     bool pending_w1 = false;  // dW1/db1 of the previous backward stage still to be contracted (its D1, Z[zbuf^1])
 
-    // backward pass of the MLP at stage point z with output cotangent d3 -> zbar (8 values)
+    // backward pass of the MLP at stage point z with output cotangent d3 -> zbar (8 values, both threads of a row)
     auto mlp_backward = [&](const float *z, const float *d3, float *zb) {
         uint32_t hi[16], lo[16];
-        float h1[HID];
+        float h1[HC];
         float *Z = Zt + zbuf * NIN * LD;
+        if (half == 0) {
 #pragma unroll
-        for (int c = 0; c < NIN; ++c) Z[c * LD + tid] = z[c];
+            for (int c = 0; c < NIN; ++c) Z[c * LD + row] = z[c];
 #pragma unroll
-        for (int d = 0; d < NX; ++d) D3[d * LD + tid] = d3[d];
+            for (int d = 0; d < NX; ++d) D3[d * LD + row] = d3[d];
+        }
         store_z(z);
         a_ready();
         issue_l1();
@@ -336,17 +357,18 @@ __global__ void __launch_bounds__(vtc::TN, 1) node_vjp_tc_kernel(const NodeVjpTc
         mma_wait();
         // h1 = tanh(D + b1): kept in registers for delta1, tile for dW2, A operand for layer 2
 #pragma unroll
-        for (int c = 0; c < HID; c += 16) {
+        for (int cc = 0; cc < HC; cc += 16) {
+            const int c = c_lo + cc;
             float v[16];
             tmem_ld16(lane_base + COL_D + c, v);
 #pragma unroll
             for (int j = 0; j < 16; j += 2) {
                 float t0, t1;
                 fast_tanh2(v[j] + sm[G_B1 + c + j], v[j + 1] + sm[G_B1 + c + j + 1], t0, t1);
-                h1[c + j] = t0;
-                h1[c + j + 1] = t1;
-                H1[(c + j) * LD + tid] = t0;
-                H1[(c + j + 1) * LD + tid] = t1;
+                h1[cc + j] = t0;
+                h1[cc + j + 1] = t1;
+                H1[(c + j) * LD + row] = t0;
+                H1[(c + j + 1) * LD + row] = t1;
                 split_tf32(t0, hi[j], lo[j]);
                 split_tf32(t1, hi[j + 1], lo[j + 1]);
             }
@@ -358,7 +380,8 @@ __global__ void __launch_bounds__(vtc::TN, 1) node_vjp_tc_kernel(const NodeVjpTc
         mma_wait();
         // h2 = tanh(D + b2);  delta2 = (W3^T d3) o (1 - h2^2)  -> tiles, A operand
 #pragma unroll
-        for (int c = 0; c < HID; c += 16) {
+        for (int cc = 0; cc < HC; cc += 16) {
+            const int c = c_lo + cc;
             float v[16];
             tmem_ld16(lane_base + COL_D + c, v);
 #pragma unroll
@@ -372,10 +395,10 @@ __global__ void __launch_bounds__(vtc::TN, 1) node_vjp_tc_kernel(const NodeVjpTc
                     g1 = fmaf(sm[G_W3 + d * HID + c + j + 1], d3[d], g1);
                 }
                 const float e0 = g0 * (1.f - t0 * t0), e1 = g1 * (1.f - t1 * t1);
-                H2[(c + j) * LD + tid] = t0;
-                H2[(c + j + 1) * LD + tid] = t1;
-                D2[(c + j) * LD + tid] = e0;
-                D2[(c + j + 1) * LD + tid] = e1;
+                H2[(c + j) * LD + row] = t0;
+                H2[(c + j + 1) * LD + row] = t1;
+                D2[(c + j) * LD + row] = e0;
+                D2[(c + j + 1) * LD + row] = e1;
                 split_tf32(e0, hi[j], lo[j]);
                 split_tf32(e1, hi[j + 1], lo[j + 1]);
             }
@@ -385,17 +408,18 @@ __global__ void __launch_bounds__(vtc::TN, 1) node_vjp_tc_kernel(const NodeVjpTc
         a_ready();
         issue_k64(dW2Thi, dW2Tlo, IDESC, LBO);  // D = delta2 W2
         contract_w3_b3_b2();                    // window 3
-        contract_w2(0, TN / 2);
+        contract_w2(r_lo, r_lo + TN / 4);
         mma_wait();
         // delta1 = D o (1 - h1^2) -> tile, A operand
 #pragma unroll
-        for (int c = 0; c < HID; c += 16) {
+        for (int cc = 0; cc < HC; cc += 16) {
+            const int c = c_lo + cc;
             float v[16];
             tmem_ld16(lane_base + COL_D + c, v);
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                const float e = v[j] * (1.f - h1[c + j] * h1[c + j]);
-                D1[(c + j) * LD + tid] = e;
+                const float e = v[j] * (1.f - h1[cc + j] * h1[cc + j]);
+                D1[(c + j) * LD + row] = e;
                 split_tf32(e, hi[j], lo[j]);
             }
             tmem_st16(lane_base + COL_AHI + c, hi);
@@ -403,7 +427,7 @@ __global__ void __launch_bounds__(vtc::TN, 1) node_vjp_tc_kernel(const NodeVjpTc
         }
         a_ready();
         issue_k64(dW1Thi, dW1Tlo, IDESC16, LBO16);  // D = delta1 W1  (16 columns, 8 used)
-        contract_w2(TN / 2, TN);                    // window 4
+        contract_w2(r_lo + TN / 4, r_lo + TN / 2);  // window 4
         mma_wait();
         {
             float v[16];
@@ -470,7 +494,7 @@ __global__ void __launch_bounds__(vtc::TN, 1) node_vjp_tc_kernel(const NodeVjpTc
 #pragma unroll
         for (int d = 0; d < NX; ++d) lam[d] += xbar[d];
         if (active && P.g_ysol) lam[0] += __ldg(P.g_ysol + k * N + iu);  // y_k = x_k[0]
-        if (active && P.g_u) {
+        if (active && P.g_u && half == 0) {
 #pragma unroll
             for (int d = 0; d < NU; ++d) P.g_u[(k * N + iu) * NU + d] = ubar[d];
         }
@@ -488,7 +512,7 @@ __global__ void __launch_bounds__(vtc::TN, 1) node_vjp_tc_kernel(const NodeVjpTc
         contract_w1_b1(zbuf ^ 1);
     }
     flush();
-    if (active && P.g_x0) {
+    if (active && P.g_x0 && half == 0) {
 #pragma unroll
         for (int d = 0; d < NX; ++d) P.g_x0[iu * NX + d] = lam[d];
     }
