@@ -14,8 +14,8 @@
 // to be staged through shared memory as hi/lo pairs in UMMA layout (544 shared stores per row and stage), so
 // they stay on the FMA pipe as fp32 tile GEMMs over [feature][row] tiles (every thread owns a 4x8 patch of
 // dW2) -- and run INSIDE the windows in which the row threads would otherwise wait for an MMA to complete:
-//   window 3 (delta2 W2 in flight):  dW3, db3, first half of dW2        window 4 (delta1 W1): rest of dW2, db2
-//   window 1 of the NEXT stage (z W1^T in flight): dW1, db1 of the previous stage (Z tile double-buffered)
+//   window 3 (delta2 W2 in flight):  dW3, db3, db2, dW2 part 1          window 4 (delta1 W1): dW2 part 2
+//   windows 1 and 2 of the NEXT stage or forward evaluation: dW2 part 3; dW1, db1 (Z tile double-buffered)
 // fp32 register accumulators, flushed to fp64 global accumulators every 16 steps (as node_vjp.cu).
 // Stage points are recomputed from the saved forward trajectory with three forward evaluations per step.
 // One CTA per SM (225 KB of shared memory: weights + transposed copies, hi and lo, 79 KB; tiles 146 KB), so the CTA
@@ -146,12 +146,14 @@ __global__ void __launch_bounds__(vtc::NTHR, 1) node_vjp_tc_kernel(const NodeVjp
     const bool rk4 = P.rk4 != 0;
 
     // ---- this thread's share of the weight gradients (fp32, flushed to fp64 every FLUSH steps)
-    float aW2[4][8], aW1[4], aW3[2], aB = 0.f, aB3 = 0.f;
+    // (dW2: two partial sums per entry -- even / odd tile rows -- so the inner product runs as packed FFMA2)
+    float2 aW2[4][8];
+    float aW1[4], aW3[2], aB = 0.f, aB3 = 0.f;
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
         aW1[a] = 0.f;
 #pragma unroll
-        for (int b = 0; b < 8; ++b) aW2[a][b] = 0.f;
+        for (int b = 0; b < 8; ++b) aW2[a][b] = make_float2(0.f, 0.f);
     }
     aW3[0] = aW3[1] = 0.f;
     // dW2 patch: rows j0..j0+3, cols i0 + 8b (interleaved: the 8 lanes of a quarter-warp then read 8 CONSECUTIVE tile
@@ -165,8 +167,8 @@ __global__ void __launch_bounds__(vtc::NTHR, 1) node_vjp_tc_kernel(const NodeVjp
         for (int a = 0; a < 4; ++a)
 #pragma unroll
             for (int b = 0; b < 8; ++b) {
-                atomicAdd(P.acc + A_W2 + (j0 + a) * HID + i0 + 8 * b, (double)aW2[a][b]);
-                aW2[a][b] = 0.f;
+                atomicAdd(P.acc + A_W2 + (j0 + a) * HID + i0 + 8 * b, (double)aW2[a][b].x + (double)aW2[a][b].y);
+                aW2[a][b] = make_float2(0.f, 0.f);
             }
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
@@ -196,8 +198,8 @@ __global__ void __launch_bounds__(vtc::NTHR, 1) node_vjp_tc_kernel(const NodeVjp
             for (int a = 0; a < 4; ++a)
 #pragma unroll
                 for (int b = 0; b < 8; ++b) {
-                    aW2[a][b] = fmaf(dj[a].x, hi[b].x, aW2[a][b]); aW2[a][b] = fmaf(dj[a].y, hi[b].y, aW2[a][b]);
-                    aW2[a][b] = fmaf(dj[a].z, hi[b].z, aW2[a][b]); aW2[a][b] = fmaf(dj[a].w, hi[b].w, aW2[a][b]);
+                    aW2[a][b] = __ffma2_rn(make_float2(dj[a].x, dj[a].y), make_float2(hi[b].x, hi[b].y), aW2[a][b]);
+                    aW2[a][b] = __ffma2_rn(make_float2(dj[a].z, dj[a].w), make_float2(hi[b].z, hi[b].w), aW2[a][b]);
                 }
         }
     };
@@ -284,12 +286,29 @@ __global__ void __launch_bounds__(vtc::NTHR, 1) node_vjp_tc_kernel(const NodeVjp
         }
     };
 
+    // Weight-gradient work left over from the previous backward stage, drained in the next windows:
+    //   dW2 iterations W2_SPLIT..15 (tiles H1, D2 stay intact until the next backward stage's h1 phase) -> next window 1
+    //   dW1 / db1               (tiles D1, Z[zbuf^1] stay intact until the next stage's delta1 phase) -> next window 2
+    // A forward evaluation touches no tile, so its two windows serve as well.
+    constexpr int ITERS = TN / 2 / 4, W2_A = 6, W2_B = 11;  // dW2 iterations: [0,W2_A) window 3, [W2_A,W2_B) window 4, rest later
+    int zbuf = 0;             // Z tile buffer the NEXT backward stage writes
+    bool pending_w2 = false, pending_w1 = false;
+    auto drain_w2 = [&]() {
+        if (pending_w2) contract_w2(r_lo + 4 * W2_B, r_lo + 4 * ITERS);
+        pending_w2 = false;
+    };
+    auto drain_w1 = [&]() {
+        if (pending_w1) contract_w1_b1(zbuf ^ 1);
+        pending_w1 = false;
+    };
+
     // forward evaluation only (stage points): r = MLP(z).  Both threads of a row return the same r.
     auto mlp_forward = [&](const float *z, float *r) {
         uint32_t hi[16], lo[16];
         store_z(z);
         a_ready();
         issue_l1();
+        drain_w2();  // window 1
         mma_wait();
 #pragma unroll
         for (int cc = 0; cc < HC; cc += 16) {
@@ -308,6 +327,7 @@ __global__ void __launch_bounds__(vtc::NTHR, 1) node_vjp_tc_kernel(const NodeVjp
         }
         a_ready();
         issue_k64(dW2hi, dW2lo, IDESC, LBO);
+        drain_w1();  // window 2
         mma_wait();
         float pr[NX];
 #pragma unroll
@@ -336,9 +356,6 @@ __global__ void __launch_bounds__(vtc::NTHR, 1) node_vjp_tc_kernel(const NodeVjp
         for (int d = 0; d < NX; ++d) r[d] = sm[G_B3 + d] + (R[d * TN + row] + R[(4 + d) * TN + row]);
     };
 
-    int zbuf = 0;             // Z tile buffer the NEXT backward stage writes
-    bool pending_w1 = false;  // dW1/db1 of the previous backward stage still to be contracted (its D1, Z[zbuf^1])
-
     // backward pass of the MLP at stage point z with output cotangent d3 -> zbar (8 values, both threads of a row)
     auto mlp_backward = [&](const float *z, const float *d3, float *zb) {
         uint32_t hi[16], lo[16];
@@ -353,7 +370,7 @@ __global__ void __launch_bounds__(vtc::NTHR, 1) node_vjp_tc_kernel(const NodeVjp
         store_z(z);
         a_ready();
         issue_l1();
-        if (pending_w1) contract_w1_b1(zbuf ^ 1);  // window 1
+        drain_w2();  // window 1
         mma_wait();
         // h1 = tanh(D + b1): kept in registers for delta1, tile for dW2, A operand for layer 2
 #pragma unroll
@@ -377,6 +394,7 @@ __global__ void __launch_bounds__(vtc::NTHR, 1) node_vjp_tc_kernel(const NodeVjp
         }
         a_ready();
         issue_k64(dW2hi, dW2lo, IDESC, LBO);
+        drain_w1();  // window 2
         mma_wait();
         // h2 = tanh(D + b2);  delta2 = (W3^T d3) o (1 - h2^2)  -> tiles, A operand
 #pragma unroll
@@ -408,7 +426,7 @@ __global__ void __launch_bounds__(vtc::NTHR, 1) node_vjp_tc_kernel(const NodeVjp
         a_ready();
         issue_k64(dW2Thi, dW2Tlo, IDESC, LBO);  // D = delta2 W2
         contract_w3_b3_b2();                    // window 3
-        contract_w2(r_lo, r_lo + TN / 4);
+        contract_w2(r_lo, r_lo + 4 * W2_A);
         mma_wait();
         // delta1 = D o (1 - h1^2) -> tile, A operand
 #pragma unroll
@@ -427,7 +445,7 @@ __global__ void __launch_bounds__(vtc::NTHR, 1) node_vjp_tc_kernel(const NodeVjp
         }
         a_ready();
         issue_k64(dW1Thi, dW1Tlo, IDESC16, LBO16);  // D = delta1 W1  (16 columns, 8 used)
-        contract_w2(r_lo + TN / 4, r_lo + TN / 2);  // window 4
+        contract_w2(r_lo + 4 * W2_A, r_lo + 4 * W2_B);  // window 4
         mma_wait();
         {
             float v[16];
@@ -435,7 +453,7 @@ __global__ void __launch_bounds__(vtc::NTHR, 1) node_vjp_tc_kernel(const NodeVjp
 #pragma unroll
             for (int c = 0; c < NIN; ++c) zb[c] = v[c];
         }
-        pending_w1 = true;
+        pending_w2 = pending_w1 = true;
         zbuf ^= 1;
     };
 
@@ -498,19 +516,11 @@ __global__ void __launch_bounds__(vtc::NTHR, 1) node_vjp_tc_kernel(const NodeVjp
 #pragma unroll
             for (int d = 0; d < NU; ++d) P.g_u[(k * N + iu) * NU + d] = ubar[d];
         }
-        if (((T - 1 - k) % FLUSH) == FLUSH - 1) {
-            if (pending_w1) {  // D1/Z of the last stage are complete once every row thread has passed this point
-                __syncthreads();
-                contract_w1_b1(zbuf ^ 1);
-                pending_w1 = false;
-            }
-            flush();
-        }
+        if (((T - 1 - k) % FLUSH) == FLUSH - 1) flush();  // (pending tile work lands in a later flush)
     }
-    if (pending_w1) {
-        __syncthreads();
-        contract_w1_b1(zbuf ^ 1);
-    }
+    __syncthreads();  // the last stage's tiles are complete
+    drain_w2();
+    drain_w1();
     flush();
     if (active && P.g_x0 && half == 0) {
 #pragma unroll
