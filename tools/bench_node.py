@@ -23,13 +23,4 @@ idx = np.random.default_rng(0).choice(a.N, 64, replace=False)
 xr, _ = orc.node_rk4_rollout(*[w.cpu().numpy() for w in W], x0[idx].cpu().numpy(), u[:, idx].cpu().numpy(), 0.25, np.float64)
 err = np.abs(xs[:, idx].cpu().numpy() - xr).max() / np.abs(xr).max()
 print("max inf-norm rel err vs fp64 oracle on 64 trajectories:", err)
-# --- VJP timing (CUDA-core kernel)
-Nv, Tv = 32768, 64
-xs, ys, _ = ops.node_rk4_forward(*W, x0[:Nv], u[:Tv, :Nv].contiguous(), 0.25)
-gx, gy = torch.ones_like(xs), torch.ones_like(ys)
-uv = u[:Tv, :Nv].contiguous()
-for it in range(2):
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(); out = ops.node_rk4_vjp(*W, x0[:Nv], uv, xs, 0.25, gx, gy); e1.record(); torch.cuda.synchronize()
-    s = e0.elapsed_time(e1) * 1e-3
-    print(f"node rk4 VJP N={Nv} T={Tv}: {s*1e3:.2f} ms  {Nv*Tv/s:.3e} steps/s", flush=True)
+# --- VJP timing: see tools/bench_node_vjp.py (tcgen05 kernel vs CUDA-core kernel)
