@@ -91,8 +91,15 @@ static int launch_fwdsens(const FwdSensParams &P, cudaStream_t st) {
     if (rc != DYNAX_OK) return rc;
     const int64_t grid = (P.N + TN - 1) / TN;
     if (grid > 0x7fffffffLL) return fail(DYNAX_ERR_INVALID_ARGUMENT, "N too large for one launch");
+    if (P.shared_acc) DYNAX_CUDA_TRY(cudaMemsetAsync(P.shared_acc, 0, kAccBytes, st));
     kern<<<(unsigned)grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(P);
     DYNAX_CUDA_TRY(cudaGetLastError());
+    if (P.shared_acc) {
+        RCModel::GradPtrs gp;
+        gp.g_theta = P.g_theta;
+        shared_finalize_kernel<RCModel, ADJ_MSE><<<1, 32, 0, st>>>(P.shared_acc, P.mp, gp, P.lb, P.ub, P.loss);
+        DYNAX_CUDA_TRY(cudaGetLastError());
+    }
     return DYNAX_OK;
 }
 
@@ -146,12 +153,12 @@ static int rc_adjoint(const float *theta, const float *x0, const float *u, const
     // one pass over u and target (24 B per system-step; nothing at all when both are shared series), measured
     // 2.2-2.3e11 system-steps/s against 1.3-1.4e11 for the checkpointed adjoint below on the same box.
     // DYNAX_GRAD_ALGO=0 forces the adjoint; the adjoint also serves every case the tangent kernel does not cover
-    // (shared theta, g_x0, discrete stepping, general cotangents).
-    if (MODE == ADJ_MSE && env_int("DYNAX_GRAD_ALGO", 1) == 1 && !g_x0 &&
-        !(flags & (DYNAX_SHARED_THETA | DYNAX_DISCRETE))) {
+    // (g_x0, discrete stepping, general cotangents).
+    if (MODE == ADJ_MSE && env_int("DYNAX_GRAD_ALGO", 1) == 1 && !g_x0 && !(flags & DYNAX_DISCRETE)) {
         FwdSensParams F;
         F.mp = P.mp; F.x0 = x0; F.u = u; F.target = target; F.lb = lb; F.ub = ub; F.loss = loss; F.g_theta = g_theta;
         F.ctrl = ctrl; F.ctrl_col = ctrl_col;
+        F.shared_acc = P.shared_theta ? P.shared_acc : nullptr;
         F.N = N; F.T = T; F.dt = dt;
         F.bulk = (N % 4) == 0 && (su || aligned16(u)) && (stg || aligned16(target)) && (!ctrl || aligned16(ctrl)) &&
                  !env_int("DYNAX_NO_BULK", 0);

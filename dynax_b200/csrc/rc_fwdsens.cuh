@@ -21,6 +21,7 @@
 #pragma once
 #include "models.cuh"
 #include "ptx.cuh"
+#include "rollout_adj.cuh"  // warp_sum
 #include "rollout_fwd.cuh"  // align4i
 
 namespace dynax {
@@ -32,6 +33,7 @@ struct FwdSensParams {
     int ctrl_col;
     const float *lb, *ub;          // [7] or NULL
     float *loss, *g_theta;         // [N], [N,7]
+    double *shared_acc;            // shared theta (mp.stride == 0): fp64 sums over systems [7 grads, loss], zeroed by the caller
     int64_t N, T;
     float dt;
     int bulk;
@@ -334,8 +336,20 @@ __global__ void __launch_bounds__(TN + 32, MINB) rc_fwdsens_kernel(const FwdSens
         }
     }
     }
-    if (!active) return;
     double loss = sqt / (double)T;
+    if (P.shared_acc != nullptr) {
+        // ONE parameter vector for all systems: sum the per-system gradients (warp shuffle in fp64 -> one atomic
+        // per warp and output); the penalty is added once by shared_finalize_kernel
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+            const double v = warp_sum(active ? gt[j] : 0.0);
+            if (lane == 0) atomicAdd(P.shared_acc + j, v);
+        }
+        const double v = warp_sum(active ? loss : 0.0);
+        if (lane == 0) atomicAdd(P.shared_acc + 7, v);
+        return;
+    }
+    if (!active) return;
     if (P.lb != nullptr && P.ub != nullptr) {
 #pragma unroll
         for (int j = 0; j < 7; ++j) {  // 3-inverse.py:103-107, normaliser = ub

@@ -63,7 +63,7 @@ def main():
         emit(f"config3 inverse loss+grad, shared u/target (compute-bound) [{algo}]", N3 * T, s, None, N=N3, T=T)
     os.environ["DYNAX_GRAD_ALGO"] = "1"
     s = timeit(lambda: ops.rc_loss_grad(nom, x0[:N3], u3, tg3, 3600.0), a.iters)
-    emit("config3 shared-theta loss+grad (fp64 block sums + atomics)", N3 * T, s, 48, N=N3, T=T)
+    emit("config3 shared-theta loss+grad (tangent kernel, fp64 warp sums + atomics)", N3 * T, s, 24, N=N3, T=T)
     del u3, tg3
     # --- config 4: MPC
     Nm, H = 1 << 22, 96
