@@ -99,6 +99,24 @@ def test_tangent_tile_configs(T, ops, monkeypatch, cfg):
     assert_grad_parity(grad.cpu().numpy(), g64, gbud)
 
 
+def test_tangent_packed_equals_scalar(T, ops, monkeypatch):
+    """The packed-fp32 (FFMA2) tangent kernel performs, lane by lane, the scalar kernel's IEEE operations in
+    the same order: loss and gradient are bit-identical (DYNAX_FS_CFG=1 selects the scalar variant)."""
+    th, x0, u, target = make_case(1000, 1237, 40)
+    a = [cu(T, v) for v in (th, x0, u, target)]
+    monkeypatch.setenv("DYNAX_GRAD_ALGO", "1")
+    monkeypatch.setenv("DYNAX_FS_CFG", "0")
+    l0, g0, _ = ops.rc_loss_grad(*a, 3600.0, orc.RC_LB, orc.RC_UB)
+    monkeypatch.setenv("DYNAX_FS_CFG", "1")
+    l1, g1, _ = ops.rc_loss_grad(*a, 3600.0, orc.RC_LB, orc.RC_UB)
+    assert T.equal(l0, l1) and T.equal(g0, g1)
+    # ... and the loss is the forward kernel's trajectory evaluated in fp64
+    _, ys, _ = ops.rc_forward(a[0], a[1], a[2], 3600.0)
+    mse = ((ys[..., 0].double() - a[3].double()) ** 2).mean(0)
+    pen = T.as_tensor(orc.bound_penalty(th, orc.RC_LB, orc.RC_UB), device="cuda")
+    assert T.allclose(l0.double(), mse + pen, rtol=1e-5, atol=0)   # fp32 partial sums over 32 steps, fp32 output
+
+
 def test_tangent_and_adjoint_agree(T, ops, monkeypatch):
     """The two gradient kernels are different fp32 evaluations of one quantity: both sit inside the
     parity band around the fp64 oracle, so they differ by at most twice that band."""
