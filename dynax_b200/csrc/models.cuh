@@ -50,17 +50,21 @@ struct RCModel {
         B24 = 1.0f / Cwi;
     }
 
-    // rhs = A x + B u  (structural zeros of A and B skipped: x + 0*y == x exactly for finite y)
+    // rhs = A x + B u  (structural zeros of A and B skipped: x + 0*y == x exactly for finite y).
+    // The order of operations is spelled out with intrinsics (nvcc contracts a*b + c*d differently from one
+    // inlining context to the next): every kernel that steps this model -- forward, adjoint, tangent (scalar and
+    // packed) -- then produces bit-identical trajectories.  Each dot product = one product, then FMAs; the two
+    // dot products are added last (fxx(x) + fxu(u), base_block_state_space.py:61).
     __device__ __forceinline__ void rhs(const float *x, const float *u, float *r) const {
-        const float bu0 = B00 * u[0] + B01 * u[1] + B02 * u[2];
-        const float bu1 = B10 * u[0] + B13 * u[3];
-        const float bu2 = B24 * u[4];
-        const float ax0 = A00 * x[0] + A02 * x[2];
-        const float ax1 = A11 * x[1] + A12 * x[2];
-        const float ax2 = A20 * x[0] + A21 * x[1] + A22 * x[2];
-        r[0] = ax0 + bu0;
-        r[1] = ax1 + bu1;
-        r[2] = ax2 + bu2;
+        const float bu0 = fmaf(B02, u[2], fmaf(B00, u[0], __fmul_rn(B01, u[1])));
+        const float bu1 = fmaf(B10, u[0], __fmul_rn(B13, u[3]));
+        const float bu2 = __fmul_rn(B24, u[4]);
+        const float ax0 = fmaf(A00, x[0], __fmul_rn(A02, x[2]));
+        const float ax1 = fmaf(A11, x[1], __fmul_rn(A12, x[2]));
+        const float ax2 = fmaf(A22, x[2], fmaf(A20, x[0], __fmul_rn(A21, x[1])));
+        r[0] = __fadd_rn(ax0, bu0);
+        r[1] = __fadd_rn(ax1, bu1);
+        r[2] = __fadd_rn(ax2, bu2);
     }
 
 
@@ -167,13 +171,13 @@ struct DenseModel {
     __device__ __forceinline__ void rhs(const float *x, const float *u, float *r) const {
 #pragma unroll
         for (int i = 0; i < n; ++i) {
-            float ax = A[i * n] * x[0];
+            float ax = __fmul_rn(A[i * n], x[0]);  // (intrinsics: no context-dependent contraction, see RCModel::rhs)
 #pragma unroll
             for (int j = 1; j < n; ++j) ax = fmaf(A[i * n + j], x[j], ax);
-            float bu = B[i * m] * u[0];
+            float bu = __fmul_rn(B[i * m], u[0]);
 #pragma unroll
             for (int j = 1; j < m; ++j) bu = fmaf(B[i * m + j], u[j], bu);
-            r[i] = ax + bu;  // fxx(x) + fxu(u)   base_block_state_space.py:61
+            r[i] = __fadd_rn(ax, bu);  // fxx(x) + fxu(u)   base_block_state_space.py:61
         }
     }
 
@@ -193,13 +197,13 @@ struct DenseModel {
     __device__ __forceinline__ void out(const float *x, const float *u, float *y) const {
 #pragma unroll
         for (int i = 0; i < p; ++i) {
-            float cx = C[i * n] * x[0];
+            float cx = __fmul_rn(C[i * n], x[0]);
 #pragma unroll
             for (int j = 1; j < n; ++j) cx = fmaf(C[i * n + j], x[j], cx);
-            float du = D[i * m] * u[0];
+            float du = __fmul_rn(D[i * m], u[0]);
 #pragma unroll
             for (int j = 1; j < m; ++j) du = fmaf(D[i * m + j], u[j], du);
-            y[i] = cx + du;  // fyx(x) + fyu(u)   base_block_state_space.py:69
+            y[i] = __fadd_rn(cx, du);  // fyx(x) + fyu(u)   base_block_state_space.py:69
         }
     }
 

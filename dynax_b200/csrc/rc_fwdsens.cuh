@@ -177,8 +177,9 @@ __global__ void __launch_bounds__(TN + 32, MINB) rc_fwdsens_kernel(const FwdSens
         //   * the columns of S travel in pairs (Cai,Cwe) (Cwi,Re) (Ri,Rw) (Rg,0): the homogeneous part
         //     S + dt A S and the gradient accumulation take 32 issue slots instead of 56;
         //   * rows 0 and 1 of the rhs, the differences u0 - x, x2 - x and the update of (x0,x1) are pairs too.
-        // Every lane performs the same operations in the same order as the scalar path (RCModel::rhs as nvcc
-        // contracts it), so x, the loss and S are bit-identical to it; ~70 instead of ~108 instructions per step.
+        // Every lane performs the operations of the scalar path in the same order (RCModel::rhs spells its order
+        // out with intrinsics), so x, the loss and S are bit-identical to it -- and x to every other kernel that
+        // steps the model; 78 instead of 108 instructions per step.
         float2 X01 = make_float2(x0, x1);
         const int ccol = CTRL ? P.ctrl_col : -1;
         // fp64 totals live in shared memory ([j][tid]: conflict-free 8-byte accesses), touched once per
@@ -224,7 +225,7 @@ __global__ void __launch_bounds__(TN + 32, MINB) rc_fwdsens_kernel(const FwdSens
                     float2 BU = __ffma2_rn(rB0, U0, __fmul2_rn(rB1, make_float2(u1, u3)));
                     BU.x = fmaf(M.B02, u2, BU.x);
                     const float2 R01 = __fadd2_rn(AX, BU);
-                    const float r2 = fmaf(M.A22, x2, fmaf(M.A20, X01.x, M.A21 * X01.y)) + M.B24 * u4;
+                    const float r2 = __fadd_rn(fmaf(M.A22, x2, fmaf(M.A20, X01.x, __fmul_rn(M.A21, X01.y))), __fmul_rn(M.B24, u4));
                     const float2 DU = __ffma2_rn(neg1, X01, U0);   // (u0 - x0, u0 - x1), exact as a subtraction
                     const float2 DX = __ffma2_rn(neg1, X01, X2);   // (x2 - x0, x2 - x1)
 #pragma unroll
