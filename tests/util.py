@@ -2,10 +2,18 @@
 
 north_star: trajectories within rel 1e-5, gradients within rel 1e-4 (fp32).
 """
+import os
+
 import numpy as np
 
 TRAJ_RTOL = 1e-5
 GRAD_RTOL = 1e-4
+_MARGINS = os.environ.get("DYNAX_TEST_MARGINS")   # print how much of each tolerance a check used (pytest -s)
+
+
+def _margin(name, frac):
+    if _MARGINS:
+        print(f"[margin] {name}: {frac:.3f} of tolerance", flush=True)
 
 
 def rel_err(a, ref, floor=1e-3):
@@ -16,7 +24,9 @@ def rel_err(a, ref, floor=1e-3):
     if ref.size == 0:
         return 0.0
     den = np.maximum(np.abs(ref), floor * np.abs(ref).max() + 1e-300)
-    return float((np.abs(a - ref) / den).max())
+    e = float((np.abs(a - ref) / den).max())
+    _margin("rel_err/1e-5", e / TRAJ_RTOL)
+    return e
 
 
 def normwise(g, g64):
@@ -30,6 +40,7 @@ def assert_loss_parity(loss, l64, loss_budget, what=""):
     loss = np.asarray(loss, np.float64); l64 = np.asarray(l64, np.float64)
     tol = TRAJ_RTOL * np.abs(l64) + loss_budget
     bad = np.abs(loss - l64) > tol
+    _margin("loss", float((np.abs(loss - l64) / tol).max()))
     assert not bad.any(), (what, float((np.abs(loss - l64) / tol).max()))
 
 
@@ -46,9 +57,12 @@ def assert_grad_parity(g, g64, grad_budget, g32=None, what=""):
     g = np.asarray(g, np.float64); g64 = np.asarray(g64, np.float64)
     tol = GRAD_RTOL * np.abs(g64) + grad_budget
     ratio = np.abs(g - g64) / (tol + 1e-300)
+    _margin("grad", float(ratio.max()))
     assert ratio.max() <= 1.0, (what, "worst element at %.2f of its tolerance" % ratio.max())
     if g32 is not None:
         no, nr = normwise(g, g64), normwise(g32, g64)
+        _margin("grad median vs fp32 reference", float(np.median(no) / max(GRAD_RTOL, np.median(nr))))
+        _margin("grad worst vs fp32 reference", float(no.max() / max(GRAD_RTOL, 2.0 * nr.max())))
         assert np.median(no) <= max(GRAD_RTOL, np.median(nr)), (what, np.median(no), np.median(nr))
         assert no.max() <= max(GRAD_RTOL, 2.0 * nr.max()), (what, no.max(), nr.max())
     return float(ratio.max())
