@@ -162,34 +162,33 @@ static int rc_adjoint(const float *theta, const float *x0, const float *u, const
         F.N = N; F.T = T; F.dt = dt;
         F.bulk = (N % 4) == 0 && (su || aligned16(u)) && (stg || aligned16(target)) && (!ctrl || aligned16(ctrl)) &&
                  !env_int("DYNAX_NO_BULK", 0);
-        // Every CTA runs the whole horizon, so a launch costs (waves x systems per CTA): 224-system CTAs win when they
-        // save a wave (N = 65536: 293 CTAs fill the 296 slots once, 256 CTAs of 256 leave 40 SMs half empty).
+        // Tile width.  Every CTA runs the whole horizon, so a launch costs (waves x systems per CTA):
+        //   * up to sm_count x 128 systems: 128-system CTAs, one per SM -- each warp then has an SM sub-partition to
+        //     itself, and the serial chain of 8760 steps is what bounds the launch (N <= 16384: 1.08 vs 1.37 ms);
+        //   * 224-system CTAs when they save a wave (N = 65536: 293 CTAs fill the 296 slots once, 256 CTAs of 256
+        //     leave 40 SMs half empty);   * else 256-system CTAs, 2 per SM (5 KB per TMA row copy).
+        // DYNAX_FS_CFG: 1 = scalar (unpacked) 256-wide kernel, 2 = always 128-wide, 3 = always 256-wide.
         DeviceInfo di;
         rc = device_info(&di);
         if (rc != DYNAX_OK) return rc;
         const int64_t slots = 2 * (int64_t)di.sm_count;
         auto cost = [&](int64_t tn) { return ((N + tn - 1) / tn + slots - 1) / slots * tn; };
-        const bool narrow = cost(224) < cost(256) && env_int("DYNAX_FS_CFG", 0) == 0;
-        if (ctrl && stg) return narrow ? launch_fwdsens<224, 8, 2, 2, true, true, true, true>(F, st)
-                                       : launch_fwdsens<256, 8, 2, 2, true, true, true, true>(F, st);
-        if (ctrl) return narrow ? launch_fwdsens<224, 8, 2, 2, true, true, false, true>(F, st)
-                                : launch_fwdsens<256, 8, 2, 2, true, true, false, true>(F, st);
-        if (su && stg) return narrow ? launch_fwdsens<224, 8, 2, 2, true, true, true>(F, st)
-                                     : launch_fwdsens<256, 8, 2, 2, true, true, true>(F, st);
-        if (su) return narrow ? launch_fwdsens<224, 8, 2, 2, true, true, false>(F, st)
-                              : launch_fwdsens<256, 8, 2, 2, true, true, false>(F, st);
-        if (stg) return narrow ? launch_fwdsens<224, 8, 2, 2, true, false, true>(F, st)
-                               : launch_fwdsens<256, 8, 2, 2, true, false, true>(F, st);
-        if (narrow) return launch_fwdsens<224, 8, 2, 2, true>(F, st);
-        // tools/tune.py, N=227328 x T=8760, same box, interleaved, power-capped steady state:
-        //   0 packed fp32x2 <256,8,2,2>: 8.7 ms (2.28e11 steps/s; 7.8 ms = 2.55e11 on a cool GPU)
-        //   1 scalar        <256,8,2,2>: 9.9 ms (2.01e11)        2 packed <128,8,2,4>: 9.7 ms
-        switch (env_int("DYNAX_FS_CFG", 0)) {
-            default:
-            case 0: return launch_fwdsens<256, 8, 2, 2, true>(F, st);
-            case 1: return launch_fwdsens<256, 8, 2, 2, false>(F, st);
-            case 2: return launch_fwdsens<128, 8, 2, 4, true>(F, st);
-        }
+        const int cfg = env_int("DYNAX_FS_CFG", 0);
+        int tn = 256;
+        if (cfg == 2 || (cfg == 0 && (N + 127) / 128 <= di.sm_count)) tn = 128;
+        else if (cfg == 0 && cost(224) < cost(256)) tn = 224;
+#define DYNAX_FS_LAUNCH(SU, STG, CTRL)                                                             \
+    (tn == 128 ? launch_fwdsens<128, 8, 2, 4, true, SU, STG, CTRL>(F, st)                            \
+               : tn == 224 ? launch_fwdsens<224, 8, 2, 2, true, SU, STG, CTRL>(F, st)                \
+                           : launch_fwdsens<256, 8, 2, 2, true, SU, STG, CTRL>(F, st))
+        if (ctrl && stg) return DYNAX_FS_LAUNCH(true, true, true);
+        if (ctrl) return DYNAX_FS_LAUNCH(true, false, true);
+        if (su && stg) return DYNAX_FS_LAUNCH(true, true, false);
+        if (su) return DYNAX_FS_LAUNCH(true, false, false);
+        if (stg) return DYNAX_FS_LAUNCH(false, true, false);
+        if (cfg == 1) return launch_fwdsens<256, 8, 2, 2, false>(F, st);
+        return DYNAX_FS_LAUNCH(false, false, false);
+#undef DYNAX_FS_LAUNCH
     }
     if constexpr (MODE == ADJ_VJP) {
         if (su) return launch_adj<RCModel, 128, 8, 2, ADJ_VJP, true, false, 2>(P, st);

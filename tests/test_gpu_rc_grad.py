@@ -87,7 +87,7 @@ def test_adj_tile_configs(T, ops, monkeypatch, cfg):
     assert_grad_parity(grad.cpu().numpy(), g64, gbud)
 
 
-@pytest.mark.parametrize("cfg", ["0", "1", "2"])
+@pytest.mark.parametrize("cfg", ["0", "1", "2", "3"])
 def test_tangent_tile_configs(T, ops, monkeypatch, cfg):
     th, x0, u, target = make_case(300, 777, 32)
     monkeypatch.setenv("DYNAX_GRAD_ALGO", "1")

@@ -21,7 +21,7 @@ for N in (1, 128, 1024, 8192, 32768):
         print(f"N={N:6d} T={T} {name:8s} {ms:8.3f} ms  {N*T/ms*1e3:.3e} steps/s", flush=True)
 
 print("--- loss+grad")
-for N in (1, 128, 1024, 4096, 8192):
+for N in (1, 128, 512, 1024, 2048, 4096, 8192):
     th = torch.tensor(NOM, device="cuda")[None].repeat(N, 1)
     x0 = torch.tensor([[20.0, 30.0, 26.0]], device="cuda").repeat(N, 1)
     u = torch.rand((T, N, 5), device="cuda"); tg = 20 + torch.rand((T, N), device="cuda")
