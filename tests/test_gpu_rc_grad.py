@@ -56,8 +56,9 @@ def test_loss_grad_vs_fp64(T, ops, monkeypatch, N, Tn, noise, algo):
     if N > 1:
         th[1, 4] = 0.45         # below lb
     # asking for d loss/d x0 routes to the adjoint whatever the environment says: the tangent leg goes without
+    # (time_chunks=0: the serial-in-time kernels are what this file tests; the chunked ones have test_gpu_chunked.py)
     loss, grad, gx0 = ops.rc_loss_grad(cu(T, th), cu(T, x0), cu(T, u), cu(T, target), 3600.0,
-                                       orc.RC_LB, orc.RC_UB, want_gx0=(algo == "adjoint"))
+                                       orc.RC_LB, orc.RC_UB, want_gx0=(algo == "adjoint"), time_chunks=0)
     l64, g64 = orc.rc_loss_grad(th, x0, u, target, 3600.0, orc.RC_LB, orc.RC_UB, np.float64)
     l32, g32 = c_oracle.rc_loss_grad(th, x0, u, target, 3600.0, orc.RC_LB, orc.RC_UB)
     lbud, gbud = orc.rc_output_sensitivity_budget(th, x0, u, target, 3600.0)
@@ -106,18 +107,18 @@ def test_tangent_packed_equals_scalar(T, ops, monkeypatch):
     a = [cu(T, v) for v in (th, x0, u, target)]
     monkeypatch.setenv("DYNAX_GRAD_ALGO", "1")
     monkeypatch.setenv("DYNAX_FS_CFG", "0")
-    l0, g0, _ = ops.rc_loss_grad(*a, 3600.0, orc.RC_LB, orc.RC_UB)
+    l0, g0, _ = ops.rc_loss_grad(*a, 3600.0, orc.RC_LB, orc.RC_UB, time_chunks=0)
     monkeypatch.setenv("DYNAX_FS_CFG", "1")
-    l1, g1, _ = ops.rc_loss_grad(*a, 3600.0, orc.RC_LB, orc.RC_UB)
+    l1, g1, _ = ops.rc_loss_grad(*a, 3600.0, orc.RC_LB, orc.RC_UB, time_chunks=0)
     assert T.equal(l0, l1) and T.equal(g0, g1)
     # ... and the trajectory inside the loss kernels is the forward kernel's, bit for bit (RCModel::rhs fixes the
     # order of operations), so the loss equals the MSE of the emitted ysol up to the rounding of the sum
-    _, ys, _ = ops.rc_forward(a[0], a[1], a[2], 3600.0)
+    _, ys, _ = ops.rc_forward(a[0], a[1], a[2], 3600.0, time_chunks=0)
     mse = ((ys[..., 0].double() - a[3].double()) ** 2).mean(0)
     pen = T.as_tensor(orc.bound_penalty(th, orc.RC_LB, orc.RC_UB), device="cuda")
     assert T.allclose(l0.double(), mse + pen, rtol=2e-6, atol=0)   # fp32 partial sums over 32 steps, fp32 output
     monkeypatch.setenv("DYNAX_GRAD_ALGO", "0")
-    l2, _, _ = ops.rc_loss_grad(*a, 3600.0, orc.RC_LB, orc.RC_UB)
+    l2, _, _ = ops.rc_loss_grad(*a, 3600.0, orc.RC_LB, orc.RC_UB, time_chunks=0)
     assert T.allclose(l2.double(), mse + pen, rtol=2e-6, atol=0)   # the adjoint kernel steps the same trajectory
 
 
@@ -128,9 +129,9 @@ def test_tangent_and_adjoint_agree(T, ops, monkeypatch):
     th[3, 2] = 5e6              # clipped by ub: penalty path in both
     a = [cu(T, v) for v in (th, x0, u, target)]
     monkeypatch.setenv("DYNAX_GRAD_ALGO", "1")
-    l1, g1, _ = ops.rc_loss_grad(*a, 3600.0, orc.RC_LB, orc.RC_UB)
+    l1, g1, _ = ops.rc_loss_grad(*a, 3600.0, orc.RC_LB, orc.RC_UB, time_chunks=0)
     monkeypatch.setenv("DYNAX_GRAD_ALGO", "0")
-    l2, g2, _ = ops.rc_loss_grad(*a, 3600.0, orc.RC_LB, orc.RC_UB)
+    l2, g2, _ = ops.rc_loss_grad(*a, 3600.0, orc.RC_LB, orc.RC_UB, time_chunks=0)
     assert not T.equal(g1, g2)          # really two code paths
     l64, g64 = orc.rc_loss_grad(th, x0, u, target, 3600.0, orc.RC_LB, orc.RC_UB, np.float64)
     lbud, gbud = orc.rc_output_sensitivity_budget(th, x0, u, target, 3600.0)
