@@ -54,6 +54,55 @@ __device__ __forceinline__ uint64_t policy_evict_first() {
     return pol;
 }
 
+// Producer-warp fallback for rows that TMA cannot move (not 16-byte aligned / sized): `rows` rows of `count`
+// floats, global row stride `src_stride`, shared row stride `dst_stride`.  Narrow rows (a handful of systems:
+// the reference's own single-building examples) are flattened over the lanes so that the loads of ALL rows are
+// in flight together instead of one dependent round trip per row.
+__device__ __forceinline__ void copy_rows_plain(float *dst, int dst_stride, const float *src, int64_t src_stride,
+                                                int rows, int count, int lane) {
+    if (count < 32) {
+        const int total = rows * count;
+#pragma unroll 4
+        for (int e = lane; e < total; e += 32) {
+            const int r = e / count, i = e - r * count;
+            dst[r * dst_stride + i] = __ldg(src + r * src_stride + i);
+        }
+    } else {
+        for (int r = 0; r < rows; ++r) {
+#pragma unroll 4
+            for (int i = lane; i < count; i += 32) dst[r * dst_stride + i] = __ldg(src + r * src_stride + i);
+        }
+    }
+}
+
+// Asynchronous flavour of copy_rows_plain: 4-byte cp.async (LDGSTS) per element, so the producer warp only ISSUES
+// the copies (no load round trips on its critical path); completion is reported to an mbarrier by
+// cp_async_arrive() from every lane (barrier count 32).  Used when rows are not TMA-able (N % 4 != 0).
+__device__ __forceinline__ void cp_async4(float *smem_dst, const float *gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive(uint64_t *bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void copy_rows_async(float *dst, int dst_stride, const float *src, int64_t src_stride,
+                                                int rows, int count, int lane) {
+    if (count < 32) {
+        const int total = rows * count;
+        for (int e = lane; e < total; e += 32) {
+            const int r = e / count, i = e - r * count;
+            cp_async4(dst + r * dst_stride + i, src + r * src_stride + i);
+        }
+    } else {
+        for (int r = 0; r < rows; ++r) {
+#pragma unroll 4
+            for (int i = lane; i < count; i += 32) cp_async4(dst + r * dst_stride + i, src + r * src_stride + i);
+        }
+    }
+}
+
 // L2 policy for data every CTA re-reads (a shared input series).
 __device__ __forceinline__ uint64_t policy_evict_last() {
     uint64_t pol;

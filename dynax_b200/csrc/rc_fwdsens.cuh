@@ -67,10 +67,14 @@ __global__ void __launch_bounds__(TN + 32, MINB) rc_fwdsens_kernel(const FwdSens
     const int64_t n0 = (int64_t)blockIdx.x * TN;
     const int valid = (int)((N - n0) < TN ? (N - n0) : TN);
     const int64_t C = (T + KF - 1) / KF;
+    // per-system rows that TMA cannot move (N % 4 != 0) go through 4-byte cp.async from all producer lanes: every
+    // lane then arrives on the stage's barrier (count 32) instead of the one elected lane of the TMA path
+    constexpr bool ANY_ROWS = !SHARED_U || !SHARED_TGT || CTRL;
+    const bool async_rows = ANY_ROWS && !P.bulk;
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < S; ++s) {
-            ptx::mbar_init(&full[s], 1);
+            ptx::mbar_init(&full[s], async_rows ? 32 : 1);
             ptx::mbar_init(&empty[s], TN / 32);
         }
         ptx::fence_mbar_init();
@@ -94,45 +98,41 @@ __global__ void __launch_bounds__(TN + 32, MINB) rc_fwdsens_kernel(const FwdSens
                 const float *su = P.u + k0 * 5;
                 su_bulk = (reinterpret_cast<uintptr_t>(su) & 15) == 0 && ((rows * 20) & 15) == 0;
                 if (su_bulk) sh_tx += (uint32_t)rows * 20u;
+                else if (async_rows) ptx::copy_rows_async(du, 0, su, 0, 1, rows * 5, lane);
                 else for (int i = lane; i < rows * 5; i += 32) du[i] = __ldg(su + i);
             }
             if constexpr (SHARED_TGT) {
                 const float *st = P.target + k0;
                 st_bulk = (reinterpret_cast<uintptr_t>(st) & 15) == 0 && ((rows * 4) & 15) == 0;
                 if (st_bulk) sh_tx += (uint32_t)rows * 4u;
+                else if (async_rows) ptx::copy_rows_async(dtg, 0, st, 0, 1, rows, lane);
                 else for (int i = lane; i < rows; i += 32) dtg[i] = __ldg(st + i);
             }
-            constexpr bool ANY_ROWS = !SHARED_U || !SHARED_TGT || CTRL;
             float *dc = dtg + Cfg::T_STAGE;
-            const bool rows_bulk = ANY_ROWS && P.bulk;
-            if (ANY_ROWS && !rows_bulk) {  // per-system rows by plain coalesced loads (N % 4 != 0 or unaligned arrays)
-                for (int r = 0; r < rows; ++r) {
-                    if constexpr (!SHARED_U) {
-                        const float *su = P.u + ((k0 + r) * N + n0) * 5;
-                        for (int i = lane; i < valid * 5; i += 32) du[r * TN * 5 + i] = __ldg(su + i);
-                    }
-                    if constexpr (!SHARED_TGT) {
-                        const float *st = P.target + (k0 + r) * N + n0;
-                        for (int i = lane; i < valid; i += 32) dtg[r * TN + i] = __ldg(st + i);
-                    }
-                    if constexpr (CTRL) {
-                        const float *sc = P.ctrl + (k0 + r) * N + n0;
-                        for (int i = lane; i < valid; i += 32) dc[r * TN + i] = __ldg(sc + i);
-                    }
+            if (async_rows) {
+                if (lane == 0 && sh_tx != 0) {
+                    ptx::mbar_expect_tx(&full[s], sh_tx);
+                    if (SHARED_U && su_bulk) ptx::bulk_g2s(du, P.u + k0 * 5, (uint32_t)rows * 20u, &full[s], pol_keep);
+                    if (SHARED_TGT && st_bulk) ptx::bulk_g2s(dtg, P.target + k0, (uint32_t)rows * 4u, &full[s], pol_keep);
                 }
+                if constexpr (!SHARED_U) ptx::copy_rows_async(du, TN * 5, P.u + (k0 * N + n0) * 5, N * 5, rows, valid * 5, lane);
+                if constexpr (!SHARED_TGT) ptx::copy_rows_async(dtg, TN, P.target + k0 * N + n0, N, rows, valid, lane);
+                if constexpr (CTRL) ptx::copy_rows_async(dc, TN, P.ctrl + k0 * N + n0, N, rows, valid, lane);
+                ptx::cp_async_arrive(&full[s]);  // every lane: arrives once its own copies have landed
+                return;
             }
             __syncwarp();
             if (lane == 0) {
                 const uint32_t ub = SHARED_U ? 0u : (uint32_t)valid * 20u, tb = SHARED_TGT ? 0u : (uint32_t)valid * 4u,
                                cb = CTRL ? (uint32_t)valid * 4u : 0u;
-                const uint32_t tx = sh_tx + (rows_bulk ? (ub + tb + cb) * (uint32_t)rows : 0u);
+                const uint32_t tx = sh_tx + (ANY_ROWS ? (ub + tb + cb) * (uint32_t)rows : 0u);
                 if (tx == 0) {
                     ptx::mbar_arrive(&full[s]);  // everything was staged with plain stores
                 } else {
                     ptx::mbar_arrive_expect_tx(&full[s], tx);
                     if (SHARED_U && su_bulk) ptx::bulk_g2s(du, P.u + k0 * 5, (uint32_t)rows * 20u, &full[s], pol_keep);
                     if (SHARED_TGT && st_bulk) ptx::bulk_g2s(dtg, P.target + k0, (uint32_t)rows * 4u, &full[s], pol_keep);
-                    for (int r = 0; rows_bulk && r < rows; ++r) {
+                    for (int r = 0; ANY_ROWS && r < rows; ++r) {
                         if constexpr (!SHARED_U) ptx::bulk_g2s(du + r * TN * 5, P.u + ((k0 + r) * N + n0) * 5, ub, &full[s], pol);
                         if constexpr (!SHARED_TGT) ptx::bulk_g2s(dtg + r * TN, P.target + (k0 + r) * N + n0, tb, &full[s], pol);
                         if constexpr (CTRL) ptx::bulk_g2s(dc + r * TN, P.ctrl + (k0 + r) * N + n0, cb, &full[s], pol);

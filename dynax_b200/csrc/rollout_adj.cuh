@@ -115,10 +115,13 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_adj_kernel(const AdjPar
     const int64_t C = (T + KC - 1) / KC;  // number of segments
     const int64_t Q = 2 * C - 1;          // chunks through the ring: C-1 forward + C reverse
 
+    // Per-system rows that TMA cannot move (N % 4 != 0 or unaligned arrays) go through 4-byte cp.async from all
+    // producer lanes: every lane then arrives on the stage's barrier (count 32) instead of one elected lane.
+    const bool async_rows = !P.bulk && (!SHARED_U || P.ctrl != nullptr || MODE != ADJ_MSE || !SHARED_TGT);
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < S; ++s) {
-            ptx::mbar_init(&full[s], 1);
+            ptx::mbar_init(&full[s], async_rows ? 32 : 1);
             ptx::mbar_init(&empty[s], TN / 32);
         }
         ptx::fence_mbar_init();
@@ -130,24 +133,22 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_adj_kernel(const AdjPar
         const int lane = tid - TN;
         const uint64_t pol = ptx::policy_evict_first();
 
-        // Copy `rows` rows of one stream into the stage.  pass 0: plain loads by all lanes (shared
-        // streams, or everything when !bulk); pass 1: TMA bulk copies by lane 0.
+        // Copy `rows` rows of one stream into the stage.  pass 0: copies issued by all lanes (shared streams, or
+        // everything when !bulk: cp.async if the launch is in async_rows mode, plain loads otherwise); pass 1: TMA
+        // bulk copies by lane 0.
         auto stream = [&](int pass, float *dst, int row_stride, const float *g, int w, bool shared, int64_t k0,
                           int rows, uint64_t *bar) -> uint32_t {
             if (g == nullptr) return 0;
             if (shared) {
                 if (pass == 0) {  // [T,1,w] is contiguous in k and the smem rows are packed (row_stride == w)
                     const float *src = g + k0 * w;
-                    for (int i = lane; i < rows * w; i += 32) dst[i] = __ldg(src + i);
+                    if (async_rows) ptx::copy_rows_async(dst, 0, src, 0, 1, rows * w, lane);
+                    else for (int i = lane; i < rows * w; i += 32) dst[i] = __ldg(src + i);
                 }
                 return 0;
             }
             if (!P.bulk) {
-                if (pass == 0)
-                    for (int r = 0; r < rows; ++r) {
-                        const float *src = g + ((k0 + r) * N + n0) * w;
-                        for (int i = lane; i < valid * w; i += 32) dst[r * row_stride + i] = __ldg(src + i);
-                    }
+                if (pass == 0) ptx::copy_rows_async(dst, row_stride, g + (k0 * N + n0) * w, N * w, rows, valid * w, lane);
                 return 0;
             }
             const uint32_t row_bytes = (uint32_t)valid * w * 4u;
@@ -178,6 +179,10 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_adj_kernel(const AdjPar
                     }
                 }
                 if (pass == 0) {
+                    if (async_rows) {  // every lane: arrives once its own copies have landed; nothing left for pass 1
+                        ptx::cp_async_arrive(&full[s]);
+                        break;
+                    }
                     bytes = b;
                     __syncwarp();
                     if (lane == 0) {

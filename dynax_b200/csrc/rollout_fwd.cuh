@@ -93,10 +93,13 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_fwd_kernel(const FwdPar
     const bool emit = emit_x || emit_y;
     const int64_t C = (T + KF - 1) / KF;
 
+    // per-system input rows that TMA cannot move (N % 4 != 0) go through 4-byte cp.async from all producer lanes:
+    // every lane then arrives on the stage's barrier (count 32) instead of one elected lane
+    const bool async_rows = !P.bulk_in && (!SHARED_U || P.ctrl != nullptr);
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < S; ++s) {
-            ptx::mbar_init(&full[s], 1);
+            ptx::mbar_init(&full[s], async_rows ? 32 : 1);
             ptx::mbar_init(&empty[s], TN / 32);
         }
         ptx::mbar_init(&ofull[0], TN / 32);
@@ -125,14 +128,21 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_fwd_kernel(const FwdPar
                 // round trip per chunk), plain loads otherwise (ragged last chunk, odd offsets)
                 const uint32_t sh_bytes = (uint32_t)(rows * m) * 4u;
                 const bool sh_bulk = (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (sh_bytes & 15u) == 0;
-                if (!sh_bulk)
-                    for (int i = lane; i < rows * m; i += 32) dst[i] = __ldg(src + i);
                 const float *csrc = P.ctrl ? P.ctrl + (t_begin + k0) * N + n0 : nullptr;
                 float *cdst = dst + Cfg::CTRL_OFF;
-                const bool c_bulk = csrc && P.bulk_in;
-                if (csrc && !c_bulk)
-                    for (int r = 0; r < rows; ++r)
-                        for (int i = lane; i < valid; i += 32) cdst[r * TN + i] = __ldg(csrc + r * N + i);
+                if (async_rows) {  // ctrl rows are not TMA-able: everything the lanes move goes through cp.async
+                    if (!sh_bulk) ptx::copy_rows_async(dst, 0, src, 0, 1, rows * m, lane);
+                    else if (lane == 0) {
+                        ptx::mbar_expect_tx(&full[s], sh_bytes);
+                        ptx::bulk_g2s(dst, src, sh_bytes, &full[s], pol_keep);
+                    }
+                    ptx::copy_rows_async(cdst, TN, csrc, N, rows, valid, lane);
+                    ptx::cp_async_arrive(&full[s]);
+                    return;
+                }
+                if (!sh_bulk)
+                    for (int i = lane; i < rows * m; i += 32) dst[i] = __ldg(src + i);
+                const bool c_bulk = csrc != nullptr;  // (not async_rows => bulk_in whenever there is a ctrl channel)
                 __syncwarp();
                 if (lane == 0) {
                     if (sh_bulk || c_bulk) {
@@ -153,12 +163,8 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_fwd_kernel(const FwdPar
                         ptx::bulk_g2s(dst + r * IN_ROW, u_base + ((k0 + r) * N + n0) * m, row_bytes, &full[s], pol);
                 }
             } else {
-                for (int r = 0; r < rows; ++r) {
-                    const float *src = u_base + ((k0 + r) * N + n0) * m;
-                    for (int i = lane; i < valid * m; i += 32) dst[r * IN_ROW + i] = __ldg(src + i);
-                }
-                __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&full[s]);
+                ptx::copy_rows_async(dst, IN_ROW, u_base + (k0 * N + n0) * m, N * m, rows, valid * m, lane);
+                ptx::cp_async_arrive(&full[s]);
             }
         };
 
