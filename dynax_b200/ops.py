@@ -114,8 +114,7 @@ def rc_loss_grad(theta, x0, u, target, dt, lb=None, ub=None, want_gx0=False, dis
     theta[N,7] -> loss[N], grad[N,7];  theta[7] (shared) -> loss[1] (sum over systems), grad[7].
     target[T,N] or [T] (shared).  Returns (loss, grad, g_x0 or None).
     ``time_chunks``: None = time-parallel chunked kernels only for small long launches (N <= 4096 and
-    T >= 2048; N <= 1024 and T >= 1024; N < 4 and T >= 512 -- measured break-evens against the serial
-    tangent kernel), 0 = never, k > 0 = k chunks.
+    T >= 2048; N <= 1024 and T >= 1024 -- measured break-evens against the serial tangent kernel), 0 = never, k > 0 = k chunks.
     """
     x0, u, target = _f32c(x0, "x0"), _f32c(u, "u"), _f32c(target, "target")
     x0, u, N, T, shared_u = _canon_batch(None, x0, u, 3, 5)
@@ -140,7 +139,7 @@ def rc_loss_grad(theta, x0, u, target, dt, lb=None, ub=None, want_gx0=False, dis
     flags = ((SHARED_THETA if shared_th else 0) | (SHARED_U if shared_u else 0) |
              (SHARED_TARGET if shared_tg else 0) | (DISCRETE if discrete else 0))
     if time_chunks is None:
-        small_long = (N <= 4096 and T >= 2048) or (N <= 1024 and T >= 1024) or (N < 4 and T >= 512)
+        small_long = (N <= 4096 and T >= 2048) or (N <= 1024 and T >= 1024)
         time_chunks = -1 if (not discrete and N > 0 and small_long) else 0
     with torch.cuda.device(dev):
         if time_chunks != 0 and not discrete and N > 0:
