@@ -40,6 +40,7 @@ SIGNATURES = {
     "dynax_host_release": (_int, []),
     "dynax_node_rk4_vjp_workspace": (_sz, []),
     "dynax_node_rk4_vjp_f32": (_int, [_f] * 19 + [_i64, _i64, _int, _int, _int, _int, _flt, _u32, _f, _sz, _f]),
+    "dynax_node_rk4_vjp_stages_f32": (_int, [_f] * 20 + [_i64, _i64, _int, _int, _int, _int, _flt, _u32, _f, _sz, _f]),
     "dynax_rc_loss_grad_chunked_workspace": (_sz, [_i64, _i64, _i64]),
     "dynax_rc_loss_grad_chunked_f32": (_int, [_f] * 9 + [_i64, _i64, _flt, _u32, _i64, _f, _sz, _f]),
     "dynax_lamb_update_f32": (_int, [_f] * 4 + [_i64, _i64, _flt, _flt, _flt, _flt, _f]),
@@ -53,6 +54,7 @@ SIGNATURES = {
     "dynax_rc_forward_chunked_workspace": (_sz, [_i64, _i64, _i64]),
     "dynax_rc_forward_chunked_f32": (_int, [_f] * 6 + [_i64, _i64, _flt, _u32, _i64, _f, _sz, _f]),
     "dynax_node_rk4_forward_f32": (_int, [_f] * 11 + [_i64, _i64, _int, _int, _int, _int, _flt, _u32, _f]),
+    "dynax_node_rk4_forward_stages_f32": (_int, [_f] * 12 + [_i64, _i64, _int, _int, _int, _int, _flt, _u32, _f]),
     "dynax_rc_mpc_cost_f32": (_int, [_f] * 7 + [_flt] * 4 + [_f] * 3 + [_i64, _i64, _flt, _f, _sz, _f]),
 }
 

@@ -13,6 +13,15 @@ extern "C" int dynax_node_rk4_forward_f32(const float *W1, const float *b1, cons
                                           const float *W3, const float *b3, const float *x0, const float *u,
                                           float *xsol, float *ysol, float *x_final, int64_t N, int64_t T, int n,
                                           int m, int p, int hidden, float dt, uint32_t flags, void *stream) {
+    return dynax_node_rk4_forward_stages_f32(W1, b1, W2, b2, W3, b3, x0, u, xsol, ysol, x_final, nullptr, N, T, n, m, p,
+                                             hidden, dt, flags, stream);
+}
+
+extern "C" int dynax_node_rk4_forward_stages_f32(const float *W1, const float *b1, const float *W2, const float *b2,
+                                                 const float *W3, const float *b3, const float *x0, const float *u,
+                                                 float *xsol, float *ysol, float *x_final, float *stage_x, int64_t N,
+                                                 int64_t T, int n, int m, int p, int hidden, float dt, uint32_t flags,
+                                                 void *stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (N < 0 || T < 0) return fail(DYNAX_ERR_INVALID_ARGUMENT, "negative N or T");
     if (N == 0) return DYNAX_OK;
@@ -34,11 +43,11 @@ extern "C" int dynax_node_rk4_forward_f32(const float *W1, const float *b1, cons
     if (!(flags & DYNAX_SHARED_U) && !(impl && impl[0] == '0')) {
         NodeTcParams Q;
         Q.W1 = W1; Q.b1 = b1; Q.W2 = W2; Q.b2 = b2; Q.W3 = W3; Q.b3 = b3;
-        Q.x0 = x0; Q.u = u; Q.xsol = xsol; Q.ysol = ysol; Q.x_final = x_final;
+        Q.x0 = x0; Q.u = u; Q.xsol = xsol; Q.ysol = ysol; Q.x_final = x_final; Q.stage_x = stage_x;
         Q.N = N; Q.T = T; Q.dt = dt; Q.rk4 = (flags & DYNAX_SOLVER_EULER) ? 0 : 1;
         const bool r16 = (N % 4) == 0;
         Q.bulk_in = r16 && aligned16(u);
-        Q.bulk_out = r16 && (!xsol || aligned16(xsol)) && (!ysol || aligned16(ysol));
+        Q.bulk_out = r16 && (!xsol || aligned16(xsol)) && (!ysol || aligned16(ysol)) && (!stage_x || aligned16(stage_x));
         rc = set_smem(node_tc_kernel, tc::SMEM_BYTES);
         if (rc != DYNAX_OK) return rc;
         const int64_t grid = (N + tc::TN - 1) / tc::TN;
@@ -46,6 +55,8 @@ extern "C" int dynax_node_rk4_forward_f32(const float *W1, const float *b1, cons
         DYNAX_CUDA_TRY(cudaGetLastError());
         return DYNAX_OK;
     }
+    if (stage_x != nullptr && !(flags & DYNAX_SOLVER_EULER))
+        return fail(DYNAX_ERR_INVALID_ARGUMENT, "stage points are emitted by the tcgen05 kernel only (per-system u, DYNAX_NODE_IMPL != 0)");
     using M = MlpModel<3, 5, 1, 64>;
     FwdParams<M> P;
     P.mp.W1 = W1; P.mp.b1 = b1; P.mp.W2 = W2; P.mp.b2 = b2; P.mp.W3 = W3; P.mp.b3 = b3;

@@ -27,6 +27,7 @@ struct NodeTcParams {
     const float *W1, *b1, *W2, *b2, *W3, *b3;
     const float *x0, *u;
     float *xsol, *ysol, *x_final;
+    float *stage_x;  // [T,N,9] or NULL: x parts of the RK4 stage points z2, z3, z4 of every step (saved for the VJP)
     int64_t N, T;
     float dt;
     int rk4, bulk_in, bulk_out;
@@ -118,7 +119,8 @@ __device__ __forceinline__ void fast_tanh2(float x0, float x1, float &t0, float 
 // shared-memory map (floats unless noted)
 constexpr int F_W2HI = 0, F_W2LO = F_W2HI + HID * HID, F_W1HI = F_W2LO + HID * HID, F_W1LO = F_W1HI + HID * NIN,
               F_B1 = F_W1LO + HID * NIN, F_B2 = F_B1 + HID, F_W3 = F_B2 + HID, F_B3 = F_W3 + NX * HID,
-              F_IN = F_B3 + 4, F_XO = F_IN + S * TN * NU, F_YO = F_XO + 2 * TN * NX, F_END = F_YO + 2 * TN;
+              F_IN = F_B3 + 4, F_XO = F_IN + S * TN * NU, F_YO = F_XO + 2 * TN * NX, F_ZO = F_YO + 2 * TN,
+              F_END = F_ZO + 2 * TN * 3 * NX;
 constexpr int NBAR = 2 * S + 4 + 1;
 constexpr size_t SMEM_USED = sizeof(float) * F_END + sizeof(uint64_t) * NBAR + 16;
 // TMEM holds 512 columns per SM and each CTA allocates 256: pad the request so at most 2 CTAs are
@@ -132,7 +134,7 @@ __global__ void __launch_bounds__(tc::TN + 32, 2) node_tc_kernel(const NodeTcPar
     using namespace tc;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *sm = reinterpret_cast<float *>(smem_raw);
-    float *s_in = sm + F_IN, *s_xo = sm + F_XO, *s_yo = sm + F_YO;
+    float *s_in = sm + F_IN, *s_xo = sm + F_XO, *s_yo = sm + F_YO, *s_zo = sm + F_ZO;
     uint64_t *full = reinterpret_cast<uint64_t *>(sm + F_END);
     uint64_t *empty = full + S, *ofull = empty + S, *ofree = ofull + 2, *mma_bar = ofree + 2;
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(mma_bar + 1);
@@ -141,7 +143,8 @@ __global__ void __launch_bounds__(tc::TN + 32, 2) node_tc_kernel(const NodeTcPar
     const int64_t N = P.N, T = P.T;
     const int64_t n0 = (int64_t)blockIdx.x * TN;
     const int valid = (int)((N - n0) < TN ? (N - n0) : TN);
-    const bool emit_x = P.xsol != nullptr, emit_y = P.ysol != nullptr, emit = emit_x || emit_y;
+    const bool emit_x = P.xsol != nullptr, emit_y = P.ysol != nullptr, emit_z = P.stage_x != nullptr && P.rk4;
+    const bool emit = emit_x || emit_y || emit_z;
 
     // ---- one-time setup: barriers, weights split hi/lo into the canonical UMMA layout, TMEM ----
     if (tid == 0) {
@@ -207,11 +210,12 @@ __global__ void __launch_bounds__(tc::TN + 32, 2) node_tc_kernel(const NodeTcPar
         };
         auto store_step = [&](int64_t c) {
             const int o = (int)(c & 1);
-            const float *sx = s_xo + o * TN * NX, *sy = s_yo + o * TN;
+            const float *sx = s_xo + o * TN * NX, *sy = s_yo + o * TN, *sz = s_zo + o * TN * 3 * NX;
             if (P.bulk_out) {
                 if (lane == 0) {
                     if (emit_x) ptx::bulk_s2g(P.xsol + (c * N + n0) * NX, sx, (uint32_t)valid * NX * 4u);
                     if (emit_y) ptx::bulk_s2g(P.ysol + (c * N + n0), sy, (uint32_t)valid * 4u);
+                    if (emit_z) ptx::bulk_s2g(P.stage_x + (c * N + n0) * 3 * NX, sz, (uint32_t)valid * 3 * NX * 4u);
                     ptx::bulk_commit();
                     ptx::bulk_wait_read<0>();
                     ptx::mbar_arrive(&ofree[o]);
@@ -219,6 +223,7 @@ __global__ void __launch_bounds__(tc::TN + 32, 2) node_tc_kernel(const NodeTcPar
             } else {
                 if (emit_x) for (int i = lane; i < valid * NX; i += 32) P.xsol[(c * N + n0) * NX + i] = sx[i];
                 if (emit_y) for (int i = lane; i < valid; i += 32) P.ysol[(c * N + n0) + i] = sy[i];
+                if (emit_z) for (int i = lane; i < valid * 3 * NX; i += 32) P.stage_x[(c * N + n0) * 3 * NX + i] = sz[i];
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(&ofree[o]);
             }
@@ -348,6 +353,10 @@ __global__ void __launch_bounds__(tc::TN + 32, 2) node_tc_kernel(const NodeTcPar
             for (int d = 0; d < NX; ++d) {
                 acc[d] = fmaf(wk, k[d], acc[d]);
                 z[d] = fmaf(cs, k[d], x[d]);
+            }
+            if (emit_z && st < 3) {  // the next stage point (z2, z3, z4): what the VJP would otherwise recompute
+#pragma unroll
+                for (int d = 0; d < NX; ++d) s_zo[o * TN * 3 * NX + tid * 3 * NX + st * NX + d] = z[d];
             }
         }
 #pragma unroll

@@ -40,6 +40,7 @@ constexpr int FLUSH = 16;
 struct NodeVjpParams {
     nv::M::Ptrs mp;
     const float *x0, *u, *xsol, *g_xsol, *g_ysol;
+    const float *stage_x;  // [T,N,9] stage points saved by the forward kernel, or NULL (recomputed)
     float *g_x0, *g_u;
     double *acc;
     int64_t N, T;
@@ -219,7 +220,12 @@ __global__ void __launch_bounds__(nv::TN, 1) node_vjp_kernel(const NodeVjpParams
             for (int d = 0; d < NU; ++d) z[s][NX + d] = u[d];
 #pragma unroll
         for (int d = 0; d < NX; ++d) z[0][d] = x[d];
-        if (rk4) {
+        if (rk4 && P.stage_x != nullptr) {
+#pragma unroll
+            for (int s = 0; s < 3; ++s)
+#pragma unroll
+                for (int d = 0; d < NX; ++d) z[s + 1][d] = active ? P.stage_x[(k * N + iu) * 3 * NX + s * NX + d] : 0.f;
+        } else if (rk4) {
 #pragma unroll 1
             for (int s = 0; s < 3; ++s) {
                 model.rhs(z[s], u, kk);
@@ -294,6 +300,16 @@ int dynax_node_rk4_vjp_f32(const float *W1, const float *b1, const float *W2, co
                            const float *g_ysol, float *gW1, float *gb1, float *gW2, float *gb2, float *gW3, float *gb3,
                            float *g_x0, float *g_u, int64_t N, int64_t T, int n, int m, int p, int hidden, float dt,
                            uint32_t flags, void *ws, size_t ws_bytes, void *stream) {
+    return dynax_node_rk4_vjp_stages_f32(W1, b1, W2, b2, W3, b3, x0, u, xsol, nullptr, g_xsol, g_ysol, gW1, gb1, gW2, gb2,
+                                         gW3, gb3, g_x0, g_u, N, T, n, m, p, hidden, dt, flags, ws, ws_bytes, stream);
+}
+
+int dynax_node_rk4_vjp_stages_f32(const float *W1, const float *b1, const float *W2, const float *b2, const float *W3,
+                                  const float *b3, const float *x0, const float *u, const float *xsol,
+                                  const float *stage_x, const float *g_xsol, const float *g_ysol, float *gW1, float *gb1,
+                                  float *gW2, float *gb2, float *gW3, float *gb3, float *g_x0, float *g_u, int64_t N,
+                                  int64_t T, int n, int m, int p, int hidden, float dt, uint32_t flags, void *ws,
+                                  size_t ws_bytes, void *stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (N < 0 || T < 1) return fail(DYNAX_ERR_INVALID_ARGUMENT, "need N >= 0 and T >= 1");
     if (N == 0) return DYNAX_OK;
@@ -310,7 +326,7 @@ int dynax_node_rk4_vjp_f32(const float *W1, const float *b1, const float *W2, co
     NodeVjpParams P;
     P.mp.W1 = W1; P.mp.b1 = b1; P.mp.W2 = W2; P.mp.b2 = b2; P.mp.W3 = W3; P.mp.b3 = b3;
     P.mp.rk4 = (flags & DYNAX_SOLVER_EULER) ? 0 : 1;
-    P.x0 = x0; P.u = u; P.xsol = xsol; P.g_xsol = g_xsol; P.g_ysol = g_ysol; P.g_x0 = g_x0; P.g_u = g_u;
+    P.x0 = x0; P.u = u; P.xsol = xsol; P.stage_x = stage_x; P.g_xsol = g_xsol; P.g_ysol = g_ysol; P.g_x0 = g_x0; P.g_u = g_u;
     P.acc = reinterpret_cast<double *>(ws); P.N = N; P.T = T; P.dt = dt;
     DYNAX_CUDA_TRY(cudaMemsetAsync(ws, 0, need, st));
     static_assert(vtc::A_END == nv::A_END, "both kernels share the accumulator layout");
@@ -322,7 +338,7 @@ int dynax_node_rk4_vjp_f32(const float *W1, const float *b1, const float *W2, co
     } else {
         NodeVjpTcParams Q;
         Q.W1 = W1; Q.b1 = b1; Q.W2 = W2; Q.b2 = b2; Q.W3 = W3; Q.b3 = b3;
-        Q.x0 = x0; Q.u = u; Q.xsol = xsol; Q.g_xsol = g_xsol; Q.g_ysol = g_ysol; Q.g_x0 = g_x0; Q.g_u = g_u;
+        Q.x0 = x0; Q.u = u; Q.xsol = xsol; Q.stage_x = stage_x; Q.g_xsol = g_xsol; Q.g_ysol = g_ysol; Q.g_x0 = g_x0; Q.g_u = g_u;
         Q.acc = P.acc; Q.N = N; Q.T = T; Q.dt = dt; Q.rk4 = P.mp.rk4;
         rc = set_smem(node_vjp_tc_kernel, vtc::SMEM_BYTES);
         if (rc != DYNAX_OK) return rc;

@@ -32,6 +32,7 @@ namespace dynax {
 struct NodeVjpTcParams {
     const float *W1, *b1, *W2, *b2, *W3, *b3;
     const float *x0, *u, *xsol, *g_xsol, *g_ysol;
+    const float *stage_x;  // [T,N,9] stage points saved by the forward kernel, or NULL (recomputed: 3 more evaluations per step)
     float *g_x0, *g_u;
     double *acc;  // fp64 accumulators, layout of node_vjp.cu (A_W1 .. A_B3), zeroed by the caller
     int64_t N, T;
@@ -471,7 +472,12 @@ __global__ void __launch_bounds__(vtc::NTHR, 1) node_vjp_tc_kernel(const NodeVjp
         // stage points (x parts; the u part is the same for all four)
 #pragma unroll
         for (int d = 0; d < NX; ++d) zx[0][d] = x[d];
-        if (rk4) {
+        if (rk4 && P.stage_x != nullptr) {
+#pragma unroll
+            for (int s = 0; s < 3; ++s)
+#pragma unroll
+                for (int d = 0; d < NX; ++d) zx[s + 1][d] = active ? __ldg(P.stage_x + (k * N + iu) * 3 * NX + s * NX + d) : 0.f;
+        } else if (rk4) {
 #pragma unroll 1
             for (int s = 0; s < 3; ++s) {
                 float z[NIN];

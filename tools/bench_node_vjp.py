@@ -12,18 +12,19 @@ W = [torch.tensor(w).cuda() for w in orc.synth_mlp(7)]
 g = torch.Generator(device="cuda").manual_seed(0)
 x0 = torch.randn((a.N, 3), device="cuda", generator=g)
 u = torch.randn((a.T, a.N, 5), device="cuda", generator=g)
-xs, ys, _ = ops.node_rk4_forward(*W, x0, u, 0.25)
+xs, ys, _, stages = ops.node_rk4_forward(*W, x0, u, 0.25, emit_stages=True)
 gx, gy = torch.randn(xs.shape, device="cuda", generator=g), torch.randn(ys.shape, device="cuda", generator=g)
 outs = {}
 for impl in a.impls.split(","):
     os.environ["DYNAX_NODE_VJP_IMPL"] = impl
-    for it in range(3):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); out = ops.node_rk4_vjp(*W, x0, u, xs, 0.25, gx, gy); e1.record(); torch.cuda.synchronize()
-        s = e0.elapsed_time(e1) * 1e-3
+    for st, label in ((None, "stage points recomputed"), (stages, "stage points saved by the forward kernel")):
+        for it in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); out = ops.node_rk4_vjp(*W, x0, u, xs, 0.25, gx, gy, stage_x=st); e1.record(); torch.cuda.synchronize()
+            s = e0.elapsed_time(e1) * 1e-3
+        print(f"node rk4 VJP impl={'tcgen05' if impl != '0' else 'cuda-core'} N={a.N} T={a.T} ({label}): {s*1e3:.2f} ms  "
+              f"{a.N*a.T/s:.3e} steps/s", flush=True)
     outs[impl] = out
-    print(f"node rk4 VJP impl={'tcgen05' if impl != '0' else 'cuda-core'} N={a.N} T={a.T}: {s*1e3:.2f} ms  {a.N*a.T/s:.3e} steps/s  "
-          f"{a.N*a.T*115200/s/1e12:.1f} TFLOP/s (fwd+bwd+wgrad of the 4 stages)", flush=True)
 if len(outs) == 2:
     for nm, p, q in zip(["gW1", "gb1", "gW2", "gb2", "gW3", "gb3", "g_x0", "g_u"], outs["1"], outs["0"]):
         print(f"  {nm}: max|tc - cuda_core| / max|cuda_core| = {(p - q).abs().max().item() / q.abs().max().item():.2e}")
