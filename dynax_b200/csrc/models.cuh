@@ -14,7 +14,7 @@ namespace dynax {
 
 struct RCModel {
     static constexpr int n = 3, m = 5, p = 1;
-    static constexpr int NG = 13;   // accumulators: the 7 non-zeros of A and 6 of B
+    static constexpr int NG = 7;    // accumulators: one per parameter (see accum)
     static constexpr int NOUT = 7;  // d/d[Cai,Cwe,Cwi,Re,Ri,Rw,Rg]
     static constexpr bool HAS_BOX = true;  // parameter box penalty of examples/3-inverse.py:66-85,103-107
 
@@ -28,6 +28,7 @@ struct RCModel {
 
     float A00, A02, A11, A12, A20, A21, A22;
     float B00, B01, B02, B10, B13, B24;
+    float iRe, iRi, iRw, iRg;  // reciprocals of the resistances (gradient accumulation only)
 
     // theta -> A, B with the reference's expression shapes so coefficient rounding matches
     // (RC.py:203-209, 224-229).  IEEE division: the library is built without fast-math.
@@ -48,6 +49,7 @@ struct RCModel {
         B10 = 1.0f / (Cwe * Re);
         B13 = 1.0f / Cwe;
         B24 = 1.0f / Cwi;
+        iRe = 1.0f / Re; iRi = 1.0f / Ri; iRw = 1.0f / Rw; iRg = 1.0f / Rg;
     }
 
     // rhs = A x + B u  (structural zeros of A and B skipped: x + 0*y == x exactly for finite y).
@@ -83,22 +85,29 @@ struct RCModel {
     // y = C x + D u with C=[1,0,0], D=0  (RC.py:236-249)
     __device__ __forceinline__ void out(const float *x, const float *, float *y) const { y[0] = x[0]; }
 
-    // G_A += s x^T, G_B += s u^T on the sparsity pattern (s = cotangent of rhs).  C, D are constants.
+    // Gradient accumulators (s = cotangent of rhs), one per parameter:
+    //   capacities   d rhs_i / d C_i = -rhs_i / C_i            ->  S s0 rhs0,  S s1 rhs1,  S s2 rhs2   with rhs AS COMPUTED
+    //                by rhs() -- the increments the stored trajectory actually took; a more accurate re-evaluation
+    //                of rhs is LESS accurate here (2.8e-4 vs 2e-5 on a year-long case: these sums cancel over time
+    //                and must stay consistent with the trajectory they are evaluated on);
+    //   resistances  in DIFFERENCE form:  S s1 (u0-x1) [Re],  S (s0/Cai - s2/Cwi)(x2-x0) [Ri],
+    //                S (s1/Cwe - s2/Cwi)(x2-x1) [Rw],  S s0 (u0-x0) [Rg].
+    // Accumulating dL/dA = S s x^T and dL/dB = S s u^T entry by entry and combining them afterwards (what XLA's
+    // transpose of the scan does) subtracts two large fp32 sums -- dL/dRg ~ dL/dA00 - dL/dB00 = S s0 x0 - S s0 u0 --
+    // and loses |x0| / |x0 - u0| in relative accuracy (7e-4 on a case with outdoor ~ zone temperature).
     __device__ __forceinline__ void accum(float *G, const float *s, const float *, const float *x,
                                           const float *u) const {
-        G[0] = fmaf(s[0], x[0], G[0]);    // A00
-        G[1] = fmaf(s[0], x[2], G[1]);    // A02
-        G[2] = fmaf(s[1], x[1], G[2]);    // A11
-        G[3] = fmaf(s[1], x[2], G[3]);    // A12
-        G[4] = fmaf(s[2], x[0], G[4]);    // A20
-        G[5] = fmaf(s[2], x[1], G[5]);    // A21
-        G[6] = fmaf(s[2], x[2], G[6]);    // A22
-        G[7] = fmaf(s[0], u[0], G[7]);    // B00
-        G[8] = fmaf(s[0], u[1], G[8]);    // B01
-        G[9] = fmaf(s[0], u[2], G[9]);    // B02
-        G[10] = fmaf(s[1], u[0], G[10]);  // B10
-        G[11] = fmaf(s[1], u[3], G[11]);  // B13
-        G[12] = fmaf(s[2], u[4], G[12]);  // B24
+        float r[3];
+        rhs(x, u, r);
+        const float dg = u[0] - x[0], de = u[0] - x[1], di = x[2] - x[0], dw = x[2] - x[1];
+        const float t0 = s[0] * B01, t1 = s[1] * B13, t2 = s[2] * B24;  // s_i / C_i
+        G[0] = fmaf(s[0], r[0], G[0]);
+        G[1] = fmaf(s[1], r[1], G[1]);
+        G[2] = fmaf(s[2], r[2], G[2]);
+        G[3] = fmaf(s[1], de, G[3]);
+        G[4] = fmaf(t0 - t2, di, G[4]);
+        G[5] = fmaf(t1 - t2, dw, G[5]);
+        G[6] = fmaf(s[0], dg, G[6]);
     }
 
     // ax = A^T s + C^T gy
@@ -117,21 +126,18 @@ struct RCModel {
         gu[4] = B24 * s[2];
     }
 
-    // Chain rule dL/dtheta from dL/dA, dL/dB (derivatives of RC.py:203-209,224-229), in fp64.
+    // dL/dtheta from the seven sums above (derivatives of RC.py:203-209,224-229), in fp64.
     __device__ __forceinline__ void finalize(const double *G, const Ptrs &P, int64_t i, double *g) const {
         const float *th = P.theta + i * P.stride;
-        const double iCai = 1.0 / (double)th[0], iCwe = 1.0 / (double)th[1], iCwi = 1.0 / (double)th[2];
-        const double iRe = 1.0 / (double)th[3], iRi = 1.0 / (double)th[4], iRw = 1.0 / (double)th[5],
-                     iRg = 1.0 / (double)th[6];
-        const double gA00 = G[0], gA02 = G[1], gA11 = G[2], gA12 = G[3], gA20 = G[4], gA21 = G[5], gA22 = G[6];
-        const double gB00 = G[7], gB01 = G[8], gB02 = G[9], gB10 = G[10], gB13 = G[11], gB24 = G[12];
-        g[0] = -iCai * (gA00 * (double)A00 + gA02 * (double)A02 + gB00 * (double)B00 + (gB01 + gB02) * (double)B01);
-        g[1] = -iCwe * (gA11 * (double)A11 + gA12 * (double)A12 + gB10 * (double)B10 + gB13 * (double)B13);
-        g[2] = -iCwi * (gA20 * (double)A20 + gA21 * (double)A21 + gA22 * (double)A22 + gB24 * (double)B24);
-        g[3] = iCwe * iRe * iRe * (gA11 - gB10);
-        g[4] = iRi * iRi * (iCai * (gA00 - gA02) + iCwi * (gA22 - gA20));
-        g[5] = iRw * iRw * (iCwe * (gA11 - gA12) + iCwi * (gA22 - gA21));
-        g[6] = iCai * iRg * iRg * (gA00 - gB00);
+        const double cai = 1.0 / (double)th[0], cwe = 1.0 / (double)th[1], cwi = 1.0 / (double)th[2];
+        const double re = 1.0 / (double)th[3], ri = 1.0 / (double)th[4], rw = 1.0 / (double)th[5], rg = 1.0 / (double)th[6];
+        g[0] = -cai * G[0];
+        g[1] = -cwe * G[1];
+        g[2] = -cwi * G[2];
+        g[3] = -cwe * re * re * G[3];
+        g[4] = -ri * ri * G[4];
+        g[5] = -rw * rw * G[5];
+        g[6] = -cai * rg * rg * G[6];
     }
 
     __device__ __forceinline__ static float *grad_addr(const GradPtrs &Gp, int64_t i, int j) {
