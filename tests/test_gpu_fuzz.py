@@ -12,8 +12,8 @@ from tests.util import TRAJ_RTOL, assert_grad_parity, assert_loss_parity, rel_er
 
 pytestmark = pytest.mark.gpu
 
-NS = [1, 2, 3, 4, 5, 31, 33, 127, 129, 224, 255, 257, 300]
-TS = [1, 2, 7, 8, 9, 15, 16, 17, 31, 33, 100]
+NS = [1, 2, 3, 4, 5, 31, 33, 127, 129, 224, 255, 257, 300, 449, 512, 515]
+TS = [1, 2, 7, 8, 9, 15, 16, 17, 31, 33, 100, 257]
 
 
 def cu(T, a):
@@ -28,7 +28,7 @@ def _cases(seed, count):
 
 
 @pytest.mark.parametrize("algo", ["1", "0"])
-@pytest.mark.parametrize("N,Tn", _cases(7, 14))
+@pytest.mark.parametrize("N,Tn", _cases(7, 32))
 def test_loss_grad_modes(monkeypatch, N, Tn, algo):
     import torch as T
     from dynax_b200 import ops
@@ -58,7 +58,7 @@ def test_loss_grad_modes(monkeypatch, N, Tn, algo):
         assert_grad_parity(grad.cpu().numpy(), g64.sum(0), gbud.sum(0), what=(N, Tn, "shared theta"))
 
 
-@pytest.mark.parametrize("N,Tn", _cases(8, 14))
+@pytest.mark.parametrize("N,Tn", _cases(8, 32))
 def test_forward_and_vjp_shapes(N, Tn):
     import torch as T
     from dynax_b200 import ops
@@ -82,3 +82,69 @@ def test_forward_and_vjp_shapes(N, Tn):
     assert nrm(gth.cpu().numpy(), rth) <= max(1e-4, 2.0 * nrm(fth, rth))
     assert rel_err(gx0.cpu().numpy(), rx0, floor=1.0) <= max(1e-4, 2.0 * rel_err(fx0, rx0, floor=1.0))
     assert rel_err(gu.cpu().numpy(), ru, floor=1.0) <= max(1e-4, 2.0 * rel_err(fu, ru, floor=1.0))
+
+
+@pytest.mark.parametrize("N,Tn", _cases(9, 24))
+def test_chunked_and_ctrl_shapes(N, Tn):
+    """Time-parallel kernels with automatic and forced chunk counts, and the shared-series + control-channel
+    rollouts, on ragged shapes."""
+    import torch as T
+    from dynax_b200 import ops
+    seed = 3000 + 11 * N + Tn
+    th, x0, u = orc.synth_theta(N, seed), orc.synth_x0(N, seed), orc.synth_u(Tn, N, seed)
+    target = (22 + np.random.default_rng(seed).normal(size=(Tn, N))).astype(np.float32)
+    x64, y64 = orc.rc_rollout(th, x0, u, 3600.0, np.float64)
+    l64, g64 = orc.rc_loss_grad(th, x0, u, target, 3600.0, None, None, np.float64)
+    lbud, gbud = orc.rc_output_sensitivity_budget(th, x0, u, target, 3600.0)
+    for chunks in (-1, 1, 3, Tn):
+        xs, ys, _ = ops.rc_forward(cu(T, th), cu(T, x0), cu(T, u), 3600.0, time_chunks=chunks)
+        assert rel_err(xs.cpu().numpy(), x64) < TRAJ_RTOL and rel_err(ys.cpu().numpy(), y64) < TRAJ_RTOL, chunks
+        loss, grad, _ = ops.rc_loss_grad(cu(T, th), cu(T, x0), cu(T, u), cu(T, target), 3600.0, time_chunks=chunks)
+        assert_loss_parity(loss.cpu().numpy(), l64, lbud, what=(N, Tn, chunks))
+        assert_grad_parity(grad.cpu().numpy(), g64, gbud, what=(N, Tn, chunks))
+    # shared disturbances + one per-system channel in column `col`
+    for col in (0, 2, 4):
+        d = u[:, 0].copy()
+        ctrl = u[:, :, col].copy()
+        u_full = np.repeat(d[:, None, :], N, 1); u_full[:, :, col] = ctrl
+        xr, yr = orc.rc_rollout(th, x0, u_full, 3600.0, np.float64)
+        xs, ys, _ = ops.rc_forward_ctrl(cu(T, th), cu(T, x0), cu(T, d), cu(T, ctrl), 3600.0, ctrl_col=col)
+        assert rel_err(xs.cpu().numpy(), xr) < TRAJ_RTOL and rel_err(ys.cpu().numpy(), yr) < TRAJ_RTOL
+        lr, gr = orc.rc_loss_grad(th, x0, u_full, target, 3600.0, None, None, np.float64)
+        lb_, gb_ = orc.rc_output_sensitivity_budget(th, x0, u_full, target, 3600.0)
+        loss, grad, _ = ops.rc_loss_grad_ctrl(cu(T, th), cu(T, x0), cu(T, d), cu(T, ctrl), cu(T, target), 3600.0, ctrl_col=col)
+        assert_loss_parity(loss.cpu().numpy(), lr, lb_, what=(N, Tn, "ctrl", col))
+        assert_grad_parity(grad.cpu().numpy(), gr, gb_, what=(N, Tn, "ctrl", col))
+
+
+LTI_DIMS = [(1, 1, 1), (2, 1, 1), (2, 2, 1), (2, 2, 2), (3, 1, 1), (3, 3, 1), (3, 3, 3), (3, 5, 1), (4, 1, 1), (4, 2, 2),
+            (4, 3, 4), (4, 4, 4)]
+
+
+@pytest.mark.parametrize("k", range(12))
+def test_lti_shapes(k):
+    """Dense LTI forward + VJP: every instantiated (n,m,p) on a ragged shape drawn from the same grid."""
+    import torch as T
+    from dynax_b200 import ops
+    n, m, p = LTI_DIMS[k]
+    N, Tn = _cases(10, 12)[k]
+    rng = np.random.default_rng(4000 + k)
+    shared = k % 3 == 0                                  # one set of matrices for all systems
+    L = 1 if shared else N
+    A = (-np.eye(n)[None] + 0.3 * rng.normal(size=(L, n, n))).astype(np.float32)
+    B = rng.normal(size=(L, n, m)).astype(np.float32)
+    C = rng.normal(size=(L, p, n)).astype(np.float32)
+    D = rng.normal(size=(L, p, m)).astype(np.float32)
+    x0 = rng.normal(size=(N, n)).astype(np.float32)
+    u = rng.normal(size=(Tn, N, m)).astype(np.float32)
+    dt = 0.05
+    xs, ys, _ = ops.lti_forward(*(cu(T, v) for v in (A, B, C, D, x0, u)), dt)
+    xr, yr = orc.lti_rollout(A, B, C, D, x0, u, dt, np.float64)
+    assert rel_err(xs.cpu().numpy(), xr, floor=1.0) < 1e-5 and rel_err(ys.cpu().numpy(), yr, floor=1.0) < 1e-5
+    gx = rng.normal(size=(Tn, N, n)).astype(np.float32)
+    gy = rng.normal(size=(Tn, N, p)).astype(np.float32)
+    out = ops.lti_vjp(*(cu(T, v) for v in (A, B, C, D, x0, u)), dt, cu(T, gx), cu(T, gy))
+    r = orc.lti_vjp(A, B, C, D, x0, u, dt, gx, gy, np.float64)
+    for got, key in zip(out, ("gA", "gB", "gC", "gD", "gx0", "gu")):
+        ref = r[key].sum(0, keepdims=True) if (shared and key in ("gA", "gB", "gC", "gD")) else r[key]
+        assert rel_err(got.cpu().numpy().reshape(ref.shape), ref, floor=1.0) < 1e-4, (key, n, m, p, N, Tn, shared)
