@@ -148,3 +148,53 @@ def test_lti_shapes(k):
     for got, key in zip(out, ("gA", "gB", "gC", "gD", "gx0", "gu")):
         ref = r[key].sum(0, keepdims=True) if (shared and key in ("gA", "gB", "gC", "gD")) else r[key]
         assert rel_err(got.cpu().numpy().reshape(ref.shape), ref, floor=1.0) < 1e-4, (key, n, m, p, N, Tn, shared)
+
+
+@pytest.mark.parametrize("N,Tn,euler", [(1, 1, False), (5, 9, False), (127, 2, True), (129, 9, False), (260, 5, False),
+                                        (131, 17, True), (2, 33, False)])
+def test_node_shapes(monkeypatch, N, Tn, euler):
+    """MLP-dynamics rollout and its VJP on ragged shapes: tcgen05 and CUDA-core kernels, stage points saved and
+    recomputed, against the fp64 oracle (forward) and each other (gradient)."""
+    import torch as T
+    from dynax_b200 import ops
+    seed = 5000 + 7 * N + Tn
+    W = orc.synth_mlp(seed, scale=0.5)
+    rng = np.random.default_rng(seed)
+    x0 = rng.normal(size=(N, 3)).astype(np.float32)
+    u = rng.normal(size=(Tn, N, 5)).astype(np.float32)
+    Wc = [cu(T, w) for w in W]
+    xr, yr = orc.node_rk4_rollout(*W, x0, u, 0.25, np.float64, euler=euler)
+    outs = {}
+    for impl in ("1", "0"):
+        monkeypatch.setenv("DYNAX_NODE_IMPL", impl)
+        xs, ys, _, st = ops.node_rk4_forward(*Wc, cu(T, x0), cu(T, u), 0.25, euler=euler, emit_stages=True)
+        assert rel_err(xs.cpu().numpy(), xr, floor=1.0) < 1e-5 and rel_err(ys.cpu().numpy(), yr, floor=1.0) < 1e-5
+        outs[impl] = (xs, st)
+    xs, st = outs["1"]
+    assert (st is None) == euler
+    gx = cu(T, rng.normal(size=(Tn, N, 3))); gy = cu(T, rng.normal(size=(Tn, N, 1)))
+    grads = []
+    for vimpl in ("1", "0"):
+        monkeypatch.setenv("DYNAX_NODE_VJP_IMPL", vimpl)
+        for stage in ((None, st) if st is not None else (None,)):
+            grads.append(ops.node_rk4_vjp(*Wc, cu(T, x0), cu(T, u), xs, 0.25, gx, gy, euler=euler, stage_x=stage))
+    for g in grads[1:]:
+        for a, b, nm in zip(g, grads[0], ["W1", "b1", "W2", "b2", "W3", "b3", "x0", "u"]):
+            assert rel_err(a.cpu().numpy(), b.cpu().numpy(), floor=1.0) < 3e-5, (nm, N, Tn, euler)
+
+
+@pytest.mark.parametrize("N,H", [(1, 1), (3, 7), (31, 8), (257, 9), (1000, 96), (4099, 17)])
+def test_mpc_shapes(N, H):
+    import torch as T
+    from dynax_b200 import ops
+    rng = np.random.default_rng(6000 + N + H)
+    d = np.stack([10 + 15 * rng.random(H), rng.random(H), 2 * rng.random(H), rng.random(H)], 1).astype(np.float32)
+    u = (-10 * rng.random((H, N))).astype(np.float32)
+    x0 = np.array([20.0, 35.8, 26.0], np.float32)
+    sched = [cu(T, v) for v in (orc.RC_PRICE, orc.RC_T_LOW, orc.RC_T_HIGH)]
+    start = float(rng.integers(0, 24)) * 3600.0
+    cost, amin, cmin = ops.rc_mpc_cost(cu(T, orc.RC_NOMINAL), cu(T, x0), cu(T, d), cu(T, u), *sched, 900.0, start_time=start)
+    ref = orc.mpc_cost(orc.RC_NOMINAL, x0, d, u, 900.0, start_time=start, dtype=np.float64)
+    assert rel_err(cost.cpu().numpy(), ref, floor=1.0) < 1e-5
+    c = cost.cpu().numpy()
+    assert amin.item() == int(np.argmin(c)) and cmin.item() == c.min()
