@@ -198,3 +198,22 @@ def test_mpc_shapes(N, H):
     assert rel_err(cost.cpu().numpy(), ref, floor=1.0) < 1e-5
     c = cost.cpu().numpy()
     assert amin.item() == int(np.argmin(c)) and cmin.item() == c.min()
+
+
+@pytest.mark.parametrize("N,Tn,tile", [(261, 40, 128), (5, 17, 0), (1, 9, 0), (515, 33, 128), (300, 8, 256)])
+def test_host_api_shapes(N, Tn, tile):
+    """Host-buffer entry points with ragged system counts: tiles of the system axis, strided 2-D copies, the last
+    tile narrower than the rest (and not a multiple of 4: cp.async staging on the device)."""
+    from dynax_b200 import host
+    seed = 7000 + N + Tn
+    th, x0, u = orc.synth_theta(N, seed), orc.synth_x0(N, seed), orc.synth_u(Tn, N, seed)
+    target = (22 + np.random.default_rng(seed).normal(size=(Tn, N))).astype(np.float32)
+    xs, ys, xf = host.rc_forward(th, x0, u, 3600.0, tile_systems=tile, emit_final=True)
+    xr, yr = orc.rc_rollout(th, x0, u, 3600.0, np.float64)
+    assert rel_err(xs, xr) < TRAJ_RTOL and rel_err(ys, yr) < TRAJ_RTOL and np.array_equal(xf, xs[-1])
+    loss, grad = host.rc_loss_grad(th, x0, u, target, 3600.0, orc.RC_LB, orc.RC_UB, tile_systems=tile)
+    l64, g64 = orc.rc_loss_grad(th, x0, u, target, 3600.0, orc.RC_LB, orc.RC_UB, np.float64)
+    lbud, gbud = orc.rc_output_sensitivity_budget(th, x0, u, target, 3600.0)
+    assert_loss_parity(loss, l64, lbud, what=(N, Tn, tile))
+    assert_grad_parity(grad, g64, gbud, what=(N, Tn, tile))
+    host.release()
