@@ -83,10 +83,11 @@ static int rc_forward(const float *theta, const float *x0, const float *u, float
     }
 }
 
-template <int TN, int KF, int S, int MINB, bool PACKED = false, bool SU = false, bool STG = false, bool CTRL = false>
+template <int TN, int KF, int S, int MINB, bool PACKED = false, bool SU = false, bool STG = false, bool CTRL = false,
+          bool GX0 = false>
 static int launch_fwdsens(const FwdSensParams &P, cudaStream_t st) {
-    using Cfg = FwdSensCfg<TN, KF, S, SU, STG, CTRL>;
-    auto kern = rc_fwdsens_kernel<TN, KF, S, MINB, PACKED, SU, STG, CTRL>;
+    using Cfg = FwdSensCfg<TN, KF, S, SU, STG, CTRL, GX0>;
+    auto kern = rc_fwdsens_kernel<TN, KF, S, MINB, PACKED, SU, STG, CTRL, GX0>;
     int rc = set_smem(kern, Cfg::SMEM_BYTES);
     if (rc != DYNAX_OK) return rc;
     const int64_t grid = (P.N + TN - 1) / TN;
@@ -153,11 +154,11 @@ static int rc_adjoint(const float *theta, const float *x0, const float *u, const
     // one pass over u and target (24 B per system-step; nothing at all when both are shared series), measured
     // 2.2-2.3e11 system-steps/s against 1.3-1.4e11 for the checkpointed adjoint below on the same box.
     // DYNAX_GRAD_ALGO=0 forces the adjoint; the adjoint also serves every case the tangent kernel does not cover
-    // (g_x0, discrete stepping, general cotangents).
-    if (MODE == ADJ_MSE && env_int("DYNAX_GRAD_ALGO", 1) == 1 && !g_x0 && !(flags & DYNAX_DISCRETE)) {
+    // (discrete stepping, general cotangents).  d loss / d x0 rides along as three more sensitivity columns.
+    if (MODE == ADJ_MSE && env_int("DYNAX_GRAD_ALGO", 1) == 1 && !(flags & DYNAX_DISCRETE)) {
         FwdSensParams F;
         F.mp = P.mp; F.x0 = x0; F.u = u; F.target = target; F.lb = lb; F.ub = ub; F.loss = loss; F.g_theta = g_theta;
-        F.ctrl = ctrl; F.ctrl_col = ctrl_col;
+        F.ctrl = ctrl; F.ctrl_col = ctrl_col; F.g_x0 = g_x0;
         F.shared_acc = P.shared_theta ? P.shared_acc : nullptr;
         F.N = N; F.T = T; F.dt = dt;
         F.bulk = (N % 4) == 0 && (su || aligned16(u)) && (stg || aligned16(target)) && (!ctrl || aligned16(ctrl)) &&
@@ -177,16 +178,19 @@ static int rc_adjoint(const float *theta, const float *x0, const float *u, const
         int tn = 256;
         if (cfg == 2 || (cfg == 0 && (N + 127) / 128 <= di.sm_count)) tn = 128;
         else if (cfg == 0 && cost(224) < cost(256)) tn = 224;
+        // (with g_x0: 11 fp64 totals per system in shared memory -> 128-system CTAs x3 or 224-system CTAs x2 per SM)
 #define DYNAX_FS_LAUNCH(SU, STG, CTRL)                                                             \
-    (tn == 128 ? launch_fwdsens<128, 8, 2, 4, true, SU, STG, CTRL>(F, st)                            \
-               : tn == 224 ? launch_fwdsens<224, 8, 2, 2, true, SU, STG, CTRL>(F, st)                \
-                           : launch_fwdsens<256, 8, 2, 2, true, SU, STG, CTRL>(F, st))
+    (g_x0 ? (tn == 128 ? launch_fwdsens<128, 8, 2, 3, true, SU, STG, CTRL, true>(F, st)              \
+                       : launch_fwdsens<224, 8, 2, 2, true, SU, STG, CTRL, true>(F, st))             \
+          : tn == 128 ? launch_fwdsens<128, 8, 2, 4, true, SU, STG, CTRL>(F, st)                     \
+                      : tn == 224 ? launch_fwdsens<224, 8, 2, 2, true, SU, STG, CTRL>(F, st)         \
+                                  : launch_fwdsens<256, 8, 2, 2, true, SU, STG, CTRL>(F, st))
         if (ctrl && stg) return DYNAX_FS_LAUNCH(true, true, true);
         if (ctrl) return DYNAX_FS_LAUNCH(true, false, true);
         if (su && stg) return DYNAX_FS_LAUNCH(true, true, false);
         if (su) return DYNAX_FS_LAUNCH(true, false, false);
         if (stg) return DYNAX_FS_LAUNCH(false, true, false);
-        if (cfg == 1) return launch_fwdsens<256, 8, 2, 2, false>(F, st);
+        if (cfg == 1 && !g_x0) return launch_fwdsens<256, 8, 2, 2, false>(F, st);
         return DYNAX_FS_LAUNCH(false, false, false);
 #undef DYNAX_FS_LAUNCH
     }

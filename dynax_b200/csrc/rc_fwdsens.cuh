@@ -33,6 +33,7 @@ struct FwdSensParams {
     int ctrl_col;
     const float *lb, *ub;          // [7] or NULL
     float *loss, *g_theta;         // [N], [N,7]
+    float *g_x0;                   // [N,3] d loss / d x0 (GX0 kernels only), or NULL
     double *shared_acc;            // shared theta (mp.stride == 0): fp64 sums over systems [7 grads, loss], zeroed by the caller
     int64_t N, T;
     float dt;
@@ -41,23 +42,25 @@ struct FwdSensParams {
 
 constexpr int kFsFoldSteps = 32;  // fp32 partial sums are folded into the fp64 totals every this many steps
 
-template <int TN, int KF, int S, bool SHARED_U = false, bool SHARED_TGT = false, bool CTRL = false>
+template <int TN, int KF, int S, bool SHARED_U = false, bool SHARED_TGT = false, bool CTRL = false, bool GX0 = false>
 struct FwdSensCfg {
+    static constexpr int NACC = GX0 ? 11 : 8;  // fp64 totals per system: 7 gradient entries (+3 for x0) + squared residual
     // a shared series occupies KF rows of 5 (or 1) floats per stage instead of KF x TN of them
     static constexpr int U_ROW = SHARED_U ? 5 : TN * 5, T_ROW = SHARED_TGT ? 1 : TN;
     static constexpr int U_STAGE = (KF * U_ROW + 3) / 4 * 4, T_STAGE = (KF * T_ROW + 3) / 4 * 4;
     static constexpr int C_STAGE = CTRL ? KF * TN : 0, STAGE = U_STAGE + T_STAGE + C_STAGE;
     static constexpr size_t RING_BYTES = sizeof(float) * (size_t)(S * STAGE) + sizeof(uint64_t) * 2 * S;
-    static constexpr size_t ACC_OFF = (RING_BYTES + 15) / 16 * 16;                 // fp64 totals [8][TN] (packed path)
-    static constexpr size_t SMEM_BYTES = ACC_OFF + sizeof(double) * 8 * (size_t)TN;
+    static constexpr size_t ACC_OFF = (RING_BYTES + 15) / 16 * 16;                 // fp64 totals [NACC][TN] (packed path)
+    static constexpr size_t SMEM_BYTES = ACC_OFF + sizeof(double) * NACC * (size_t)TN;
     static constexpr int THREADS = TN + 32;
 };
 
 template <int TN, int KF, int S, int MINB, bool PACKED = false, bool SHARED_U = false, bool SHARED_TGT = false,
-          bool CTRL = false>
+          bool CTRL = false, bool GX0 = false>
 __global__ void __launch_bounds__(TN + 32, MINB) rc_fwdsens_kernel(const FwdSensParams P) {
     static_assert(!CTRL || (SHARED_U && PACKED), "the control channel replaces a column of a SHARED input series");
-    using Cfg = FwdSensCfg<TN, KF, S, SHARED_U, SHARED_TGT, CTRL>;
+    static_assert(!GX0 || PACKED, "d loss / d x0 rides in the packed kernel");
+    using Cfg = FwdSensCfg<TN, KF, S, SHARED_U, SHARED_TGT, CTRL, GX0>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *s_in = reinterpret_cast<float *>(smem_raw);
     uint64_t *full = reinterpret_cast<uint64_t *>(s_in + S * Cfg::STAGE);
@@ -186,10 +189,17 @@ __global__ void __launch_bounds__(TN + 32, MINB) rc_fwdsens_kernel(const FwdSens
         // kFsFoldSteps steps: 16 registers the loop needs for its coefficients
         double *acc = reinterpret_cast<double *>(smem_raw + Cfg::ACC_OFF) + tid;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j * TN] = 0.0;
-        float2 s0[4], s1[4], s2[4], gp[4];
+        for (int j = 0; j < Cfg::NACC; ++j) acc[j * TN] = 0.0;
+        // GX0: three more columns, d x / d x0 (identity at k = 0, no forcing): (Rg, x0_0) share pair 3, (x0_1, x0_2) pair 4
+        constexpr int NP = GX0 ? 5 : 4;
+        float2 s0[NP], s1[NP], s2[NP], gp[NP];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) s0[q] = s1[q] = s2[q] = gp[q] = make_float2(0.f, 0.f);
+        for (int q = 0; q < NP; ++q) s0[q] = s1[q] = s2[q] = gp[q] = make_float2(0.f, 0.f);
+        if constexpr (GX0) {
+            s0[3].y = 1.f;
+            s1[4].x = 1.f;
+            s2[4].y = 1.f;
+        }
         const float2 pA00 = make_float2(tA00, tA00), pA02 = make_float2(tA02, tA02), pA11 = make_float2(tA11, tA11),
                      pA12 = make_float2(tA12, tA12), pA20 = make_float2(tA20, tA20), pA21 = make_float2(tA21, tA21),
                      pA22 = make_float2(tA22, tA22);
@@ -218,7 +228,7 @@ __global__ void __launch_bounds__(TN + 32, MINB) rc_fwdsens_kernel(const FwdSens
                     const float gy = c2T * res;
                     const float2 gy2 = make_float2(gy, gy);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) gp[q] = __ffma2_rn(gy2, s0[q], gp[q]);
+                    for (int q = 0; q < NP; ++q) gp[q] = __ffma2_rn(gy2, s0[q], gp[q]);
                     // rhs = (A x) + (B u), rows 0 and 1 as a pair, row 2 scalar
                     const float2 U0 = make_float2(u0, u0), X2 = make_float2(x2, x2);
                     const float2 AX = __ffma2_rn(rAd, X01, __fmul2_rn(rAx2, X2));
@@ -229,7 +239,7 @@ __global__ void __launch_bounds__(TN + 32, MINB) rc_fwdsens_kernel(const FwdSens
                     const float2 DU = __ffma2_rn(neg1, X01, U0);   // (u0 - x0, u0 - x1), exact as a subtraction
                     const float2 DX = __ffma2_rn(neg1, X01, X2);   // (x2 - x0, x2 - x1)
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
+                    for (int q = 0; q < NP; ++q) {
                         const float2 a0 = s0[q], a1 = s1[q], a2 = s2[q];
                         s0[q] = __ffma2_rn(pA02, a2, __ffma2_rn(pA00, a0, a0));
                         s1[q] = __ffma2_rn(pA12, a2, __ffma2_rn(pA11, a1, a1));
@@ -252,9 +262,10 @@ __global__ void __launch_bounds__(TN + 32, MINB) rc_fwdsens_kernel(const FwdSens
             constexpr int FOLDC = kFsFoldSteps / KF > 0 ? kFsFoldSteps / KF : 1;
             if ((c + 1) % FOLDC == 0 || c + 1 == C) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
+                for (int q = 0; q < NP; ++q) {  // columns 2q, 2q+1; column 7 is the empty lane unless GX0 (then x0_0)
                     acc[(2 * q) * TN] += (double)gp[q].x;
-                    if (q < 3) acc[(2 * q + 1) * TN] += (double)gp[q].y;
+                    if (2 * q + 1 != 7) acc[(2 * q + 1) * TN] += (double)gp[q].y;
+                    else if constexpr (GX0) acc[10 * TN] += (double)gp[q].y;   // x0_0 parks in slot 10 (7 holds sq)
                     gp[q] = make_float2(0.f, 0.f);
                 }
                 acc[7 * TN] += (double)sq;
@@ -264,6 +275,13 @@ __global__ void __launch_bounds__(TN + 32, MINB) rc_fwdsens_kernel(const FwdSens
 #pragma unroll
         for (int j = 0; j < 7; ++j) gt[j] = acc[j * TN];
         sqt = acc[7 * TN];
+        if constexpr (GX0) {  // slots 8, 9 = columns 8, 9 (x0_1, x0_2); slot 10 = x0_0
+            if (active && P.g_x0 != nullptr) {
+                P.g_x0[i * 3 + 0] = (float)acc[10 * TN];
+                P.g_x0[i * 3 + 1] = (float)acc[8 * TN];
+                P.g_x0[i * 3 + 2] = (float)acc[9 * TN];
+            }
+        }
     } else {
     float s0[7], s1[7], s2[7];  // rows of S = dx/dtheta
     float gp[7];

@@ -104,11 +104,12 @@ int dynax_rc_loss_grad_chunked_f32(const float *theta, const float *x0, const fl
 
 /* Fused loss + reverse-mode gradient of examples/3-inverse.py:96-112 for N candidates:
  *   loss_i = mean_k (ysol_i[k]-target_i[k])^2 + sum_j relu(theta_ij-ub_j)/ub_j + relu(lb_j-theta_ij)/ub_j
- *   g_theta = d loss / d theta   (== jax.value_and_grad through the scan).  With per-system theta, u and
- *   target and g_x0 == NULL the gradient is evaluated in forward mode (3x7 sensitivities beside the state, one
- *   sweep, 24 B per system-step: csrc/rc_fwdsens.cuh); every other case -- and all cases when the environment
- *   holds DYNAX_GRAD_ALGO=0 -- runs the checkpointed discrete adjoint (csrc/rollout_adj.cuh).  The two agree
- *   within the gradient tolerance, not bit for bit.  The workspace is required either way.
+ *   g_theta = d loss / d theta   (== jax.value_and_grad through the scan).  The gradient is evaluated in forward
+ *   mode (3x7 sensitivities beside the state, +3 columns for g_x0; one sweep, 24 B per system-step:
+ *   csrc/rc_fwdsens.cuh) for every combination of shared / per-system theta, u and target; DYNAX_DISCRETE -- and
+ *   every call when the environment holds DYNAX_GRAD_ALGO=0 -- runs the checkpointed discrete adjoint
+ *   (csrc/rollout_adj.cuh).  The two agree within the gradient tolerance, not bit for bit.  The workspace is
+ *   required either way.
  * lb/ub: [7] device arrays or NULL (no penalty).  loss:[N], g_theta:[N,7]; with DYNAX_SHARED_THETA
  * loss:[1] (mean over systems is NOT taken: it is the SUM over systems of the MSE terms plus one
  * penalty) and g_theta:[7].  g_x0:[N,3] or NULL. */

@@ -42,12 +42,21 @@ def test_loss_grad_modes(monkeypatch, N, Tn, algo):
             continue                                  # a batch of one has nothing to share
         uu = u[:, :1] if su else u
         tt = target[:, :1] if stg else target
-        loss, grad, _ = ops.rc_loss_grad(cu(T, th), cu(T, x0), cu(T, uu), cu(T, tt[:, 0] if stg else tt), 3600.0,
-                                         orc.RC_LB, orc.RC_UB, time_chunks=0)
+        want_gx0 = (N + Tn) % 2 == 0                  # half of the cases also ask for d loss / d x0
+        loss, grad, gx0 = ops.rc_loss_grad(cu(T, th), cu(T, x0), cu(T, uu), cu(T, tt[:, 0] if stg else tt), 3600.0,
+                                           orc.RC_LB, orc.RC_UB, want_gx0=want_gx0, time_chunks=0)
         l64, g64 = orc.rc_loss_grad(th, x0, uu, tt, 3600.0, orc.RC_LB, orc.RC_UB, np.float64)
         lbud, gbud = orc.rc_output_sensitivity_budget(th, x0, uu, tt, 3600.0)
         assert_loss_parity(loss.cpu().numpy(), l64, lbud, what=(N, Tn, su, stg))
         assert_grad_parity(grad.cpu().numpy(), g64, gbud, what=(N, Tn, su, stg))
+        if want_gx0:
+            y64 = orc.rc_rollout(th, x0, uu, 3600.0, np.float64)[1][..., 0]
+            gy = ((2.0 / Tn) * (y64 - tt))[..., None]
+            _, gx0_64, _ = orc.rc_vjp(th, x0, uu, 3600.0, None, gy, np.float64)
+            y32 = orc.rc_rollout(th, x0, uu, 3600.0, np.float32)[1][..., 0]
+            _, gx0_32, _ = orc.rc_vjp(th, x0, uu, 3600.0, None, ((2.0 / Tn) * (y32 - tt))[..., None].astype(np.float32), np.float32)
+            e, e32 = rel_err(gx0.cpu().numpy(), gx0_64, floor=1.0), rel_err(gx0_32, gx0_64, floor=1.0)
+            assert e <= max(1e-4, 2.0 * e32), (N, Tn, su, stg, e, e32)
     # shared theta: the sum over systems
     if N > 1:
         th1 = th[1:2]

@@ -55,18 +55,15 @@ def test_loss_grad_vs_fp64(T, ops, monkeypatch, N, Tn, noise, algo):
     th[0, 0] = 4.0e4            # above ub
     if N > 1:
         th[1, 4] = 0.45         # below lb
-    # asking for d loss/d x0 routes to the adjoint whatever the environment says: the tangent leg goes without
     # (time_chunks=0: the serial-in-time kernels are what this file tests; the chunked ones have test_gpu_chunked.py)
     loss, grad, gx0 = ops.rc_loss_grad(cu(T, th), cu(T, x0), cu(T, u), cu(T, target), 3600.0,
-                                       orc.RC_LB, orc.RC_UB, want_gx0=(algo == "adjoint"), time_chunks=0)
+                                       orc.RC_LB, orc.RC_UB, want_gx0=True, time_chunks=0)
     l64, g64 = orc.rc_loss_grad(th, x0, u, target, 3600.0, orc.RC_LB, orc.RC_UB, np.float64)
     l32, g32 = c_oracle.rc_loss_grad(th, x0, u, target, 3600.0, orc.RC_LB, orc.RC_UB)
     lbud, gbud = orc.rc_output_sensitivity_budget(th, x0, u, target, 3600.0)
     assert_loss_parity(loss.cpu().numpy(), l64, lbud)
     assert_grad_parity(grad.cpu().numpy(), g64, gbud, g32 if N >= 64 else None)
-    if algo == "tangent":
-        return
-    # d loss / d x0 against the oracle's general VJP
+    # d loss / d x0 against the oracle's general VJP (tangent kernel: three more sensitivity columns)
     gy = (2.0 / Tn) * (orc.rc_rollout(th, x0, u, 3600.0, np.float64)[1][..., 0] - target)
     _, gx0_64, _ = orc.rc_vjp(th, x0, u, 3600.0, None, gy[..., None])
     # yardstick for d loss/d x0: the same adjoint in fp32 reference order (NumPy oracle)
