@@ -214,7 +214,19 @@ def ours(a):
     dev = torch.device("cuda", local)
     numa_note = bind_to_gpu_numa_node(local) if world > 1 else None   # pinned e2e buffers land next to the GPU
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # the "NCCL version ..." banner goes to stdout when the first communicator is created: point fd 1 at stderr
+        # while that happens, so that stdout carries the ONE JSON line and nothing else
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     T, S = a.T, a.systems
     tile = min(a.tile, S)
