@@ -2,6 +2,7 @@
 #pragma once
 #include "api_common.cuh"
 #include "rollout_adj.cuh"
+#include "rc_fwdsens.cuh"
 #include "rollout_fwd.cuh"
 
 namespace dynax {
@@ -55,5 +56,35 @@ int launch_adj(const AdjParams<Model> &P, cudaStream_t st) {
     }
     return DYNAX_OK;
 }
+
+// Forward-mode (tangent) fused loss + gradient of the 4R3C model (rc_fwdsens.cuh).
+template <int TN, int KF, int S, int MINB, bool PACKED = false, bool SU = false, bool STG = false, bool CTRL = false,
+          bool GX0 = false, bool CHUNK = false>
+int launch_fwdsens(const FwdSensParams &P, cudaStream_t st) {
+    using Cfg = FwdSensCfg<TN, KF, S, SU, STG, CTRL, GX0>;
+    auto kern = rc_fwdsens_kernel<TN, KF, S, MINB, PACKED, SU, STG, CTRL, GX0, CHUNK>;
+    int rc = set_smem(kern, Cfg::SMEM_BYTES);
+    if (rc != DYNAX_OK) return rc;
+    const int64_t grid = (P.N + TN - 1) / TN;
+    if (grid > 0x7fffffffLL) return fail(DYNAX_ERR_INVALID_ARGUMENT, "N too large for one launch");
+    if (P.shared_acc) DYNAX_CUDA_TRY(cudaMemsetAsync(P.shared_acc, 0, kAccBytes, st));
+    if constexpr (CHUNK) {  // time-chunked launch: the caller (lti_chunked.cu) owns the stitch and the outputs
+        const int64_t chunks = (P.T + P.chunk_len - 1) / P.chunk_len;
+        if (chunks > 65535) return fail(DYNAX_ERR_INVALID_ARGUMENT, "too many time chunks");
+        kern<<<dim3((unsigned)grid, (unsigned)chunks), Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(P);
+        DYNAX_CUDA_TRY(cudaGetLastError());
+        return DYNAX_OK;
+    }
+    kern<<<(unsigned)grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(P);
+    DYNAX_CUDA_TRY(cudaGetLastError());
+    if (P.shared_acc) {
+        RCModel::GradPtrs gp;
+        gp.g_theta = P.g_theta;
+        shared_finalize_kernel<RCModel, ADJ_MSE><<<1, 32, 0, st>>>(P.shared_acc, P.mp, gp, P.lb, P.ub, P.loss);
+        DYNAX_CUDA_TRY(cudaGetLastError());
+    }
+    return DYNAX_OK;
+}
+
 
 }  // namespace dynax

@@ -12,6 +12,7 @@
 //
 // u is read twice, so this is for launches that cannot fill the machine with systems alone
 // (N per GPU below ~one wave: e.g. config 3 sharded over 8 GPUs, or a single building over a year).
+#include <stdlib.h>
 #include <string.h>
 
 #include "launch.cuh"
@@ -64,20 +65,33 @@ __global__ void stitch_kernel(const float *psi, const float *x0, const float *v 
         for (int d = 0; d < n; ++d) P[j][d] = psi[(i * n + j) * n + d];
 #pragma unroll
     for (int d = 0; d < n; ++d) x[d] = x0[i * n + d];
-    for (int64_t c = 0; c < C; ++c) {
+    // the serial recurrence is short; what costs is one dependent global round trip per chunk, so the zero-state
+    // responses are fetched kStitchGroup chunks at a time
+    constexpr int G = 8;
+    for (int64_t c0 = 0; c0 < C; c0 += G) {
+        float vv[G][n];
 #pragma unroll
-        for (int d = 0; d < n; ++d) xb[(c * N + i) * n + d] = x[d];
-        if (c + 1 == C) break;
-        float y[n];
+        for (int g = 0; g < G; ++g)
 #pragma unroll
-        for (int d = 0; d < n; ++d) {
-            float acc = v[(c * N + i) * n + d];
+            for (int d = 0; d < n; ++d) vv[g][d] = (c0 + g + 1 < C) ? __ldg(v + ((c0 + g) * N + i) * n + d) : 0.f;
 #pragma unroll
-            for (int j = 0; j < n; ++j) acc = fmaf(P[j][d], x[j], acc);
-            y[d] = x[d] + acc;
+        for (int g = 0; g < G; ++g) {
+            const int64_t c = c0 + g;
+            if (c >= C) break;
+#pragma unroll
+            for (int d = 0; d < n; ++d) xb[(c * N + i) * n + d] = x[d];
+            if (c + 1 == C) break;
+            float y[n];
+#pragma unroll
+            for (int d = 0; d < n; ++d) {
+                float acc = vv[g][d];
+#pragma unroll
+                for (int j = 0; j < n; ++j) acc = fmaf(P[j][d], x[j], acc);
+                y[d] = x[d] + acc;
+            }
+#pragma unroll
+            for (int d = 0; d < n; ++d) x[d] = y[d];
         }
-#pragma unroll
-        for (int d = 0; d < n; ++d) x[d] = y[d];
     }
 }
 
@@ -158,9 +172,100 @@ __global__ void stitch_adjoint_kernel(const float *psi, const float *w /*[C,N,n]
     }
 }
 
+// Tangent path: assemble loss and gradient from the chunks' local results.  With S_c = dx/dtheta at the start of
+// chunk c (S_0 = 0) and X_c = dx/dx0 there (X_0 = I):
+//     grad  += g_loc[c] + w[c]^T S_c          g_x0 += w[c]^T X_c
+//     S_c+1  = S_c + Psi S_c + s_end[c]       X_c+1 = X_c + Psi X_c           (Psi = (I + dt A)^L - I, full chunks)
+// The ten columns (7 of S, 3 of X) evolve independently: one thread per (column, system), columns outermost so that a
+// warp holds 32 systems of one column (coalesced records, warp-level sums for shared theta).  Columns in fp32 like
+// the serial kernel's S, sums in fp64; records fetched G chunks at a time (the recurrence is short, the dependent
+// global round trips are what cost).  Thread (column 0) also owns the loss.
+__global__ void tangent_stitch_kernel(const float *psi, const float *s_end, const double *g_loc, const float *w,
+                                      RCModel::Ptrs mp, const float *lb, const float *ub, float *loss, float *g_theta,
+                                      float *g_x0, double *shared_acc, int64_t N, int64_t C, int64_t T) {
+    const int64_t N32 = (N + 31) / 32 * 32;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = (int)(t / N32);  // column: 0..6 = theta, 7..9 = x0
+    const int64_t i = t % N32;
+    const bool active = i < N && j < 10;
+    const int64_t ii = i < N ? i : N - 1;
+    const int jj = j < 10 ? j : 9;
+    float Ps[3][3];  // Ps[d][e] = Psi[d][e]   (psi is stored column-major per system: psi[(i*3 + e)*3 + d])
+#pragma unroll
+    for (int e = 0; e < 3; ++e)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) Ps[d][e] = __ldg(psi + (ii * 3 + e) * 3 + d);
+    float v[3] = {jj == 7 ? 1.f : 0.f, jj == 8 ? 1.f : 0.f, jj == 9 ? 1.f : 0.f};
+    double g = 0.0, sq = 0.0;
+    constexpr int G = 8;
+    for (int64_t c0 = 0; c0 < C; c0 += G) {
+        float wv[G][3], se[G][3];
+        double gl[G], sl[G];
+#pragma unroll
+        for (int q = 0; q < G; ++q) {
+            const int64_t o = ((c0 + q < C) ? (c0 + q) : (C - 1)) * N + ii;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                wv[q][d] = __ldg(w + o * 3 + d);
+                se[q][d] = jj < 7 ? __ldg(s_end + o * 21 + d * 7 + jj) : 0.f;
+            }
+            gl[q] = jj < 7 ? __ldg(g_loc + o * 8 + jj) : 0.0;
+            sl[q] = jj == 0 ? __ldg(g_loc + o * 8 + 7) : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < G; ++q) {
+            if (c0 + q >= C) break;
+            g += gl[q] + ((double)wv[q][0] * (double)v[0] + (double)wv[q][1] * (double)v[1] + (double)wv[q][2] * (double)v[2]);
+            sq += sl[q];
+            float vn[3];
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+                vn[d] = v[d] + (fmaf(Ps[d][2], v[2], fmaf(Ps[d][1], v[1], Ps[d][0] * v[0])) + se[q][d]);
+#pragma unroll
+            for (int d = 0; d < 3; ++d) v[d] = vn[d];
+        }
+    }
+    if (jj >= 7) {  // d loss / d x0
+        if (active && g_x0 != nullptr) g_x0[i * 3 + (jj - 7)] = (float)g;
+        return;
+    }
+    double L = sq / (double)T;  // meaningful in column 0 only
+    if (shared_acc != nullptr) {  // ONE parameter vector: sum over systems; penalty added once by shared_finalize_kernel
+        const int lane = threadIdx.x & 31;
+        const double vs = warp_sum(active ? g : 0.0);
+        if (lane == 0) atomicAdd(shared_acc + jj, vs);
+        if (jj == 0) {
+            const double ls = warp_sum(active ? L : 0.0);
+            if (lane == 0) atomicAdd(shared_acc + 7, ls);
+        }
+        return;
+    }
+    if (!active) return;
+    if (lb != nullptr && ub != nullptr) {
+        const float *th = mp.theta + i * mp.stride;
+        {  // 3-inverse.py:103-107, normaliser = ub
+            const double tv = (double)th[jj], lo = (double)lb[jj], hi = (double)ub[jj];
+            if (tv > hi) g += 1.0 / hi;
+            if (tv < lo) g -= 1.0 / hi;
+        }
+        if (jj == 0) {
+#pragma unroll
+            for (int q = 0; q < 7; ++q) {
+                const double tv = (double)th[q], lo = (double)lb[q], hi = (double)ub[q];
+                if (tv > hi) L += (tv - hi) / hi;
+                if (tv < lo) L += (lo - tv) / hi;
+            }
+        }
+    }
+    if (jj == 0) loss[i] = (float)L;
+    g_theta[i * 7 + jj] = (float)g;
+}
+
 struct ChunkedAdjWs {
     float *psi, *v, *xb, *w, *aend, *ckpt;
     double *chunk_acc, *shared_acc;
+    float *s_end;   // tangent path: [C,N,21]
+    double *g_loc;  // tangent path: [C,N,8]
     size_t bytes;
 };
 
@@ -182,6 +287,8 @@ inline ChunkedAdjWs chunked_adj_layout(void *ws, int64_t N, int64_t T, int n, in
     o.w = reinterpret_cast<float *>(take(sizeof(float) * (size_t)C * N * n));
     o.aend = reinterpret_cast<float *>(take(sizeof(float) * (size_t)C * N * n));
     o.ckpt = reinterpret_cast<float *>(take(sizeof(float) * (size_t)C * segs * n * N));
+    o.s_end = reinterpret_cast<float *>(take(sizeof(float) * (size_t)C * N * n * nout));
+    o.g_loc = reinterpret_cast<double *>(take(sizeof(double) * (size_t)C * N * (nout + 1)));
     o.bytes = (size_t)(p - reinterpret_cast<char *>(ws));
     return o;
 }
@@ -267,6 +374,37 @@ int dynax_rc_loss_grad_chunked_f32(const float *theta, const float *x0, const fl
     if (rc != DYNAX_OK) return rc;
     stitch_kernel<3><<<gb, tb, 0, st>>>(W.psi, x0, W.v, W.xb, N, C);
     DYNAX_CUDA_TRY(cudaGetLastError());
+
+    // ---- gradient, default: ONE forward-mode (tangent) pass over the chunks from their true boundary states with
+    //      S = 0, then a stitch over chunks (tangent_stitch_kernel).  u is read twice in total (adjoint path below: 5x).
+    {
+        const char *algo = getenv("DYNAX_GRAD_ALGO");
+        if (!(algo && algo[0] == '0')) {
+            FwdSensParams Q;
+            memset(&Q, 0, sizeof(Q));
+            Q.mp = F.mp; Q.x0 = W.xb; Q.x0_chunk_stride = N * 3; Q.u = u; Q.target = target;
+            Q.N = N; Q.T = T; Q.dt = dt; Q.chunk_len = L;
+            Q.bulk = (N % 4) == 0 && (su || aligned16(u)) && (stg || aligned16(target));
+            Q.s_end = W.s_end; Q.g_loc = W.g_loc; Q.w_out = W.w;
+            if (su && stg) rc = launch_fwdsens<128, 8, 2, 4, true, true, true, false, false, true>(Q, st);
+            else if (su) rc = launch_fwdsens<128, 8, 2, 4, true, true, false, false, false, true>(Q, st);
+            else if (stg) rc = launch_fwdsens<128, 8, 2, 4, true, false, true, false, false, true>(Q, st);
+            else rc = launch_fwdsens<128, 8, 2, 4, true, false, false, false, false, true>(Q, st);
+            if (rc != DYNAX_OK) return rc;
+            if (sth) DYNAX_CUDA_TRY(cudaMemsetAsync(W.shared_acc, 0, kAccBytes, st));
+            const int64_t threads = 10 * ((N + 31) / 32 * 32);
+            tangent_stitch_kernel<<<(unsigned)((threads + tb - 1) / tb), tb, 0, st>>>(
+                W.psi, W.s_end, W.g_loc, W.w, F.mp, lb, ub, loss, g_theta, g_x0, sth ? W.shared_acc : nullptr, N, C, T);
+            DYNAX_CUDA_TRY(cudaGetLastError());
+            if (sth) {
+                RCModel::GradPtrs gp;
+                gp.g_theta = g_theta;
+                shared_finalize_kernel<RCModel, ADJ_MSE><<<1, 32, 0, st>>>(W.shared_acc, F.mp, gp, lb, ub, loss);
+                DYNAX_CUDA_TRY(cudaGetLastError());
+            }
+            return DYNAX_OK;
+        }
+    }
 
     // ---- adjoint pass B1 (zero terminal adjoint, no gradient sums) -> w[c]; backward stitch -> aend[c];
     //      pass B2 (true terminal adjoints) -> per-system fp64 sums over chunks -> outputs

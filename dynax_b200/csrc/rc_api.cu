@@ -4,7 +4,6 @@
 #include <string.h>
 
 #include "launch.cuh"
-#include "rc_fwdsens.cuh"
 
 namespace dynax {
 
@@ -81,27 +80,6 @@ static int rc_forward(const float *theta, const float *x0, const float *u, float
         case 2: return launch_fwd<RCModel, 64, 4, 4, false, 6>(P, st);
         case 3: return launch_fwd<RCModel, 128, 8, 2, false, 3>(P, st);
     }
-}
-
-template <int TN, int KF, int S, int MINB, bool PACKED = false, bool SU = false, bool STG = false, bool CTRL = false,
-          bool GX0 = false>
-static int launch_fwdsens(const FwdSensParams &P, cudaStream_t st) {
-    using Cfg = FwdSensCfg<TN, KF, S, SU, STG, CTRL, GX0>;
-    auto kern = rc_fwdsens_kernel<TN, KF, S, MINB, PACKED, SU, STG, CTRL, GX0>;
-    int rc = set_smem(kern, Cfg::SMEM_BYTES);
-    if (rc != DYNAX_OK) return rc;
-    const int64_t grid = (P.N + TN - 1) / TN;
-    if (grid > 0x7fffffffLL) return fail(DYNAX_ERR_INVALID_ARGUMENT, "N too large for one launch");
-    if (P.shared_acc) DYNAX_CUDA_TRY(cudaMemsetAsync(P.shared_acc, 0, kAccBytes, st));
-    kern<<<(unsigned)grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(P);
-    DYNAX_CUDA_TRY(cudaGetLastError());
-    if (P.shared_acc) {
-        RCModel::GradPtrs gp;
-        gp.g_theta = P.g_theta;
-        shared_finalize_kernel<RCModel, ADJ_MSE><<<1, 32, 0, st>>>(P.shared_acc, P.mp, gp, P.lb, P.ub, P.loss);
-        DYNAX_CUDA_TRY(cudaGetLastError());
-    }
-    return DYNAX_OK;
 }
 
 template <int MODE>

@@ -38,6 +38,12 @@ struct FwdSensParams {
     int64_t N, T;
     float dt;
     int bulk;
+    // time-chunked launch (CHUNK kernels, gridDim.y = chunks; lti_chunked.cu): chunk c covers steps [c*chunk_len, ...),
+    // starts from x0 + c*x0_chunk_stride with S = 0 and reports its LOCAL results for the stitch over chunks
+    int64_t chunk_len, x0_chunk_stride;
+    float *s_end;   // [C,N,21]  S at the end of the chunk (row-major 3x7)
+    double *g_loc;  // [C,N,8]   sum_k gy_k e0^T S_k (7) and sum_k res_k^2
+    float *w_out;   // [C,N,3]   sum_k gy_k ((I + dt A)^T)^(k-k0) e0: what the chunk's loss sees of S at its start
 };
 
 constexpr int kFsFoldSteps = 32;  // fp32 partial sums are folded into the fp64 totals every this many steps
@@ -56,19 +62,26 @@ struct FwdSensCfg {
 };
 
 template <int TN, int KF, int S, int MINB, bool PACKED = false, bool SHARED_U = false, bool SHARED_TGT = false,
-          bool CTRL = false, bool GX0 = false>
+          bool CTRL = false, bool GX0 = false, bool CHUNK = false>
 __global__ void __launch_bounds__(TN + 32, MINB) rc_fwdsens_kernel(const FwdSensParams P) {
     static_assert(!CTRL || (SHARED_U && PACKED), "the control channel replaces a column of a SHARED input series");
     static_assert(!GX0 || PACKED, "d loss / d x0 rides in the packed kernel");
+    static_assert(!CHUNK || (PACKED && !GX0 && !CTRL), "time-chunked launches use the plain packed kernel");
     using Cfg = FwdSensCfg<TN, KF, S, SHARED_U, SHARED_TGT, CTRL, GX0>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *s_in = reinterpret_cast<float *>(smem_raw);
     uint64_t *full = reinterpret_cast<uint64_t *>(s_in + S * Cfg::STAGE);
     uint64_t *empty = full + S;
     const int tid = threadIdx.x;
-    const int64_t N = P.N, T = P.T;
+    const int64_t N = P.N;
     const int64_t n0 = (int64_t)blockIdx.x * TN;
     const int valid = (int)((N - n0) < TN ? (N - n0) : TN);
+    // this CTA's slice of the time axis (the whole horizon unless the launch is time-chunked)
+    const int64_t cidx = CHUNK ? (int64_t)blockIdx.y : 0;
+    const int64_t t_begin = CHUNK ? cidx * P.chunk_len : 0;
+    const int64_t T = CHUNK ? ((P.T - t_begin) < P.chunk_len ? (P.T - t_begin) : P.chunk_len) : P.T;
+    const float *const u_base = P.u + t_begin * (SHARED_U ? 5 : N * 5);
+    const float *const tgt_base = P.target + t_begin * (SHARED_TGT ? 1 : N);
     const int64_t C = (T + KF - 1) / KF;
     // per-system rows that TMA cannot move (N % 4 != 0) go through 4-byte cp.async from all producer lanes: every
     // lane then arrives on the stage's barrier (count 32) instead of the one elected lane of the TMA path
@@ -98,14 +111,14 @@ __global__ void __launch_bounds__(TN + 32, MINB) rc_fwdsens_kernel(const FwdSens
             uint32_t sh_tx = 0;
             bool su_bulk = false, st_bulk = false;
             if constexpr (SHARED_U) {
-                const float *su = P.u + k0 * 5;
+                const float *su = u_base + k0 * 5;
                 su_bulk = (reinterpret_cast<uintptr_t>(su) & 15) == 0 && ((rows * 20) & 15) == 0;
                 if (su_bulk) sh_tx += (uint32_t)rows * 20u;
                 else if (async_rows) ptx::copy_rows_async(du, 0, su, 0, 1, rows * 5, lane);
                 else for (int i = lane; i < rows * 5; i += 32) du[i] = __ldg(su + i);
             }
             if constexpr (SHARED_TGT) {
-                const float *st = P.target + k0;
+                const float *st = tgt_base + k0;
                 st_bulk = (reinterpret_cast<uintptr_t>(st) & 15) == 0 && ((rows * 4) & 15) == 0;
                 if (st_bulk) sh_tx += (uint32_t)rows * 4u;
                 else if (async_rows) ptx::copy_rows_async(dtg, 0, st, 0, 1, rows, lane);
@@ -115,11 +128,11 @@ __global__ void __launch_bounds__(TN + 32, MINB) rc_fwdsens_kernel(const FwdSens
             if (async_rows) {
                 if (lane == 0 && sh_tx != 0) {
                     ptx::mbar_expect_tx(&full[s], sh_tx);
-                    if (SHARED_U && su_bulk) ptx::bulk_g2s(du, P.u + k0 * 5, (uint32_t)rows * 20u, &full[s], pol_keep);
-                    if (SHARED_TGT && st_bulk) ptx::bulk_g2s(dtg, P.target + k0, (uint32_t)rows * 4u, &full[s], pol_keep);
+                    if (SHARED_U && su_bulk) ptx::bulk_g2s(du, u_base + k0 * 5, (uint32_t)rows * 20u, &full[s], pol_keep);
+                    if (SHARED_TGT && st_bulk) ptx::bulk_g2s(dtg, tgt_base + k0, (uint32_t)rows * 4u, &full[s], pol_keep);
                 }
-                if constexpr (!SHARED_U) ptx::copy_rows_async(du, TN * 5, P.u + (k0 * N + n0) * 5, N * 5, rows, valid * 5, lane);
-                if constexpr (!SHARED_TGT) ptx::copy_rows_async(dtg, TN, P.target + k0 * N + n0, N, rows, valid, lane);
+                if constexpr (!SHARED_U) ptx::copy_rows_async(du, TN * 5, u_base + (k0 * N + n0) * 5, N * 5, rows, valid * 5, lane);
+                if constexpr (!SHARED_TGT) ptx::copy_rows_async(dtg, TN, tgt_base + k0 * N + n0, N, rows, valid, lane);
                 if constexpr (CTRL) ptx::copy_rows_async(dc, TN, P.ctrl + k0 * N + n0, N, rows, valid, lane);
                 ptx::cp_async_arrive(&full[s]);  // every lane: arrives once its own copies have landed
                 return;
@@ -133,11 +146,11 @@ __global__ void __launch_bounds__(TN + 32, MINB) rc_fwdsens_kernel(const FwdSens
                     ptx::mbar_arrive(&full[s]);  // everything was staged with plain stores
                 } else {
                     ptx::mbar_arrive_expect_tx(&full[s], tx);
-                    if (SHARED_U && su_bulk) ptx::bulk_g2s(du, P.u + k0 * 5, (uint32_t)rows * 20u, &full[s], pol_keep);
-                    if (SHARED_TGT && st_bulk) ptx::bulk_g2s(dtg, P.target + k0, (uint32_t)rows * 4u, &full[s], pol_keep);
+                    if (SHARED_U && su_bulk) ptx::bulk_g2s(du, u_base + k0 * 5, (uint32_t)rows * 20u, &full[s], pol_keep);
+                    if (SHARED_TGT && st_bulk) ptx::bulk_g2s(dtg, tgt_base + k0, (uint32_t)rows * 4u, &full[s], pol_keep);
                     for (int r = 0; ANY_ROWS && r < rows; ++r) {
-                        if constexpr (!SHARED_U) ptx::bulk_g2s(du + r * TN * 5, P.u + ((k0 + r) * N + n0) * 5, ub, &full[s], pol);
-                        if constexpr (!SHARED_TGT) ptx::bulk_g2s(dtg + r * TN, P.target + (k0 + r) * N + n0, tb, &full[s], pol);
+                        if constexpr (!SHARED_U) ptx::bulk_g2s(du + r * TN * 5, u_base + ((k0 + r) * N + n0) * 5, ub, &full[s], pol);
+                        if constexpr (!SHARED_TGT) ptx::bulk_g2s(dtg + r * TN, tgt_base + (k0 + r) * N + n0, tb, &full[s], pol);
                         if constexpr (CTRL) ptx::bulk_g2s(dc + r * TN, P.ctrl + (k0 + r) * N + n0, cb, &full[s], pol);
                     }
                 }
@@ -168,12 +181,13 @@ __global__ void __launch_bounds__(TN + 32, MINB) rc_fwdsens_kernel(const FwdSens
     const float tRe = -dt * iCwe * iRe * iRe, tRg = -dt * iCai * iRg * iRg;
     const float tRi0 = -dt * iCai * iRi * iRi, tRi2 = -dt * iCwi * iRi * iRi, tRw1 = -dt * iCwe * iRw * iRw,
                 tRw2 = -dt * iCwi * iRw * iRw;
-    float x0 = __ldg(P.x0 + i * 3), x1 = __ldg(P.x0 + i * 3 + 1), x2 = __ldg(P.x0 + i * 3 + 2);
+    const float *xs0 = P.x0 + (CHUNK ? cidx * P.x0_chunk_stride : 0) + i * 3;
+    float x0 = __ldg(xs0), x1 = __ldg(xs0 + 1), x2 = __ldg(xs0 + 2);
     double gt[7], sqt = 0.0;
     float sq = 0.f;
 #pragma unroll
     for (int j = 0; j < 7; ++j) gt[j] = 0.0;
-    const float c2T = 2.0f / (float)T;
+    const float c2T = 2.0f / (float)P.T;  // the mean runs over the WHOLE horizon, also in a chunked launch
 
     if constexpr (PACKED) {
         // Packed-fp32 form (FFMA2/FMUL2/FADD2, sm_100: two IEEE fp32 operations per issue slot).
@@ -206,6 +220,9 @@ __global__ void __launch_bounds__(TN + 32, MINB) rc_fwdsens_kernel(const FwdSens
         const float2 rAd = make_float2(M.A00, M.A11), rAx2 = make_float2(M.A02, M.A12);   // rhs rows 0,1
         const float2 rB0 = make_float2(M.B00, M.B10), rB1 = make_float2(M.B01, M.B13);
         const float2 neg1 = make_float2(-1.f, -1.f), dt2 = make_float2(dt, dt), pR2 = make_float2(-tRi2, -tRw2);
+        // CHUNK: p_j = ((I + dt A)^T)^j e0 and w = sum_k gy_k p_(k-k0), so that the part of this chunk's gradient that
+        // comes from S at the chunk start is w^T S_start (added by the stitch over chunks)
+        float p0 = 1.f, p1 = 0.f, p2 = 0.f, w0 = 0.f, w1 = 0.f, w2 = 0.f;
         for (int64_t c = 0; c < C; ++c) {
             const int s = (int)(c % S);
             const int64_t k0 = c * KF;
@@ -229,6 +246,13 @@ __global__ void __launch_bounds__(TN + 32, MINB) rc_fwdsens_kernel(const FwdSens
                     const float2 gy2 = make_float2(gy, gy);
 #pragma unroll
                     for (int q = 0; q < NP; ++q) gp[q] = __ffma2_rn(gy2, s0[q], gp[q]);
+                    if constexpr (CHUNK) {
+                        w0 = fmaf(gy, p0, w0); w1 = fmaf(gy, p1, w1); w2 = fmaf(gy, p2, w2);
+                        const float q0 = fmaf(tA20, p2, fmaf(tA00, p0, p0));                     // p + dt A^T p
+                        const float q1 = fmaf(tA21, p2, fmaf(tA11, p1, p1));
+                        const float q2 = fmaf(tA22, p2, fmaf(tA12, p1, fmaf(tA02, p0, p2)));
+                        p0 = q0; p1 = q1; p2 = q2;
+                    }
                     // rhs = (A x) + (B u), rows 0 and 1 as a pair, row 2 scalar
                     const float2 U0 = make_float2(u0, u0), X2 = make_float2(x2, x2);
                     const float2 AX = __ffma2_rn(rAd, X01, __fmul2_rn(rAx2, X2));
@@ -275,6 +299,27 @@ __global__ void __launch_bounds__(TN + 32, MINB) rc_fwdsens_kernel(const FwdSens
 #pragma unroll
         for (int j = 0; j < 7; ++j) gt[j] = acc[j * TN];
         sqt = acc[7 * TN];
+        if constexpr (CHUNK) {  // local results of this chunk; the stitch kernel assembles loss and gradient
+            if (active) {
+                const int64_t o = cidx * N + i;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    P.s_end[o * 21 + 2 * q] = s0[q].x;
+                    P.s_end[o * 21 + 7 + 2 * q] = s1[q].x;
+                    P.s_end[o * 21 + 14 + 2 * q] = s2[q].x;
+                    if (q < 3) {
+                        P.s_end[o * 21 + 2 * q + 1] = s0[q].y;
+                        P.s_end[o * 21 + 7 + 2 * q + 1] = s1[q].y;
+                        P.s_end[o * 21 + 14 + 2 * q + 1] = s2[q].y;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 7; ++j) P.g_loc[o * 8 + j] = gt[j];
+                P.g_loc[o * 8 + 7] = sqt;
+                P.w_out[o * 3 + 0] = w0; P.w_out[o * 3 + 1] = w1; P.w_out[o * 3 + 2] = w2;
+            }
+            return;
+        }
         if constexpr (GX0) {  // slots 8, 9 = columns 8, 9 (x0_1, x0_2); slot 10 = x0_0
             if (active && P.g_x0 != nullptr) {
                 P.g_x0[i * 3 + 0] = (float)acc[10 * TN];
