@@ -92,9 +92,10 @@ int dynax_rc_forward_chunked_f32(const float *theta, const float *x0, const floa
 
 /* Time-parallel variant of dynax_rc_loss_grad_f32 (same outputs within the gradient tolerance) for
  * launches with few systems and a long horizon (one building over a year: N=1, T=8760).  Forward chunk
- * boundaries as above; then every chunk's adjoint for a zero terminal value, a backward stitch with
- * Psi^T, and every chunk's adjoint again from its true terminal value; per-chunk gradient sums are
- * added per system in fp64.  u is read 5 times, so use it only when N cannot fill the GPU. */
+ * boundaries as above; then every chunk runs the forward-mode (tangent) kernel from its true boundary state with
+ * zero sensitivities, and a stitch over the chunks assembles loss, g_theta and g_x0 (u is read twice in total).
+ * With DYNAX_GRAD_ALGO=0 in the environment: the adjoint-based scheme (zero-terminal adjoint pass, backward
+ * stitch with Psi^T, true-terminal pass; u read 5 times).  Use it only when N cannot fill the GPU. */
 size_t dynax_rc_loss_grad_chunked_workspace(int64_t N, int64_t T, int64_t chunk_len);
 int dynax_rc_loss_grad_chunked_f32(const float *theta, const float *x0, const float *u, const float *target,
                                    const float *lb, const float *ub,
