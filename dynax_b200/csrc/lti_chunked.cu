@@ -330,7 +330,7 @@ int dynax_rc_forward_chunked_f32(const float *theta, const float *x0, const floa
             return launch_fwd<RCModel, 128, 4, 4, true, 4>(Q, s);
         });
     return forward_chunked<RCModel>(P, L, ws, ws_bytes, st, [](const FwdParams<RCModel> &Q, cudaStream_t s) {
-        return launch_fwd<RCModel, 128, 4, 4, false, 3>(Q, s);
+        return launch_fwd<RCModel, 128, 8, 2, false, 3>(Q, s);  // 8-row chunks: fewer hand-shakes on the serial chain
     });
 }
 
@@ -370,7 +370,7 @@ int dynax_rc_loss_grad_chunked_f32(const float *theta, const float *x0, const fl
     F.chunk_len = L; F.x0_zero = 1;
     psi_kernel<RCModel><<<gb, tb, 0, st>>>(F.mp, W.psi, N, L, dt);
     DYNAX_CUDA_TRY(cudaGetLastError());
-    rc = su ? launch_fwd<RCModel, 128, 4, 4, true, 4>(F, st) : launch_fwd<RCModel, 128, 4, 4, false, 3>(F, st);
+    rc = su ? launch_fwd<RCModel, 128, 4, 4, true, 4>(F, st) : launch_fwd<RCModel, 128, 8, 2, false, 3>(F, st);
     if (rc != DYNAX_OK) return rc;
     stitch_kernel<3><<<gb, tb, 0, st>>>(W.psi, x0, W.v, W.xb, N, C);
     DYNAX_CUDA_TRY(cudaGetLastError());

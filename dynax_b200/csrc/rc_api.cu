@@ -73,7 +73,16 @@ static int rc_forward(const float *theta, const float *x0, const float *u, float
     if (flags & DYNAX_SHARED_U) return launch_fwd<RCModel, 128, 4, 4, true, 4>(P, st);
     // Tile shapes measured on B200 (tools/tune.py, N=132608, T=8760): wide rows win because each
     // cp.async.bulk then moves 5 KB.  0: 6.45 TB/s (x+y), 1: 5.43, 2: 5.31, 3: 5.80.
-    switch (env_int("DYNAX_FWD_CFG", 0)) {
+    // Launches that leave at most one 256-system CTA per SM are bound by the per-chunk hand-shakes of the serial
+    // chain, not by HBM: 8-row chunks (shape 3) halve them (N=16384: 1.37 vs 1.91 ms, N=32768: 1.65 vs 1.91 ms).
+    int cfg = env_int("DYNAX_FWD_CFG", -1);
+    if (cfg < 0) {
+        DeviceInfo di;
+        rc = device_info(&di);
+        if (rc != DYNAX_OK) return rc;
+        cfg = ((N + 255) / 256 <= di.sm_count) ? 3 : 0;
+    }
+    switch (cfg) {
         default:
         case 0: return launch_fwd<RCModel, 256, 4, 4, false, 1>(P, st);
         case 1: return launch_fwd<RCModel, 128, 4, 4, false, 3>(P, st);
