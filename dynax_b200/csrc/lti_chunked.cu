@@ -330,7 +330,7 @@ int dynax_rc_forward_chunked_f32(const float *theta, const float *x0, const floa
             return launch_fwd<RCModel, 128, 4, 4, true, 4>(Q, s);
         });
     return forward_chunked<RCModel>(P, L, ws, ws_bytes, st, [](const FwdParams<RCModel> &Q, cudaStream_t s) {
-        return launch_fwd<RCModel, 128, 8, 2, false, 3>(Q, s);  // 8-row chunks: fewer hand-shakes on the serial chain
+        return launch_fwd<RCModel, 128, 8, 2, false, 3>(Q, s);  // 8-row chunks: fewer hand-shakes on the serial chain (16 rows: 2 CTAs/SM, slower here)
     });
 }
 

@@ -74,13 +74,14 @@ static int rc_forward(const float *theta, const float *x0, const float *u, float
     // Tile shapes measured on B200 (tools/tune.py, N=132608, T=8760): wide rows win because each
     // cp.async.bulk then moves 5 KB.  0: 6.45 TB/s (x+y), 1: 5.43, 2: 5.31, 3: 5.80.
     // Launches that leave at most one 256-system CTA per SM are bound by the per-chunk hand-shakes of the serial
-    // chain, not by HBM: 8-row chunks (shape 3) halve them (N=16384: 1.37 vs 1.91 ms, N=32768: 1.65 vs 1.91 ms).
+    // chain, not by HBM: longer chunks amortise them -- 16 rows while one 128-system CTA per SM suffices (N=16384:
+    // 1.18 ms; 8 rows 1.37, 4 rows 1.91), 8 rows up to one 256-system CTA per SM (N=32768: 1.65 vs 1.91 ms).
     int cfg = env_int("DYNAX_FWD_CFG", -1);
     if (cfg < 0) {
         DeviceInfo di;
         rc = device_info(&di);
         if (rc != DYNAX_OK) return rc;
-        cfg = ((N + 255) / 256 <= di.sm_count) ? 3 : 0;
+        cfg = ((N + 127) / 128 <= di.sm_count) ? 4 : ((N + 255) / 256 <= di.sm_count) ? 3 : 0;
     }
     switch (cfg) {
         default:
@@ -88,6 +89,7 @@ static int rc_forward(const float *theta, const float *x0, const float *u, float
         case 1: return launch_fwd<RCModel, 128, 4, 4, false, 3>(P, st);
         case 2: return launch_fwd<RCModel, 64, 4, 4, false, 6>(P, st);
         case 3: return launch_fwd<RCModel, 128, 8, 2, false, 3>(P, st);
+        case 4: return launch_fwd<RCModel, 128, 16, 2, false, 2>(P, st);
     }
 }
 
@@ -151,8 +153,9 @@ static int rc_adjoint(const float *theta, const float *x0, const float *u, const
         F.bulk = (N % 4) == 0 && (su || aligned16(u)) && (stg || aligned16(target)) && (!ctrl || aligned16(ctrl)) &&
                  !env_int("DYNAX_NO_BULK", 0);
         // Tile width.  Every CTA runs the whole horizon, so a launch costs (waves x systems per CTA):
-        //   * up to sm_count x 128 systems: 128-system CTAs, one per SM -- each warp then has an SM sub-partition to
-        //     itself, and the serial chain of 8760 steps is what bounds the launch (N <= 16384: 1.08 vs 1.37 ms);
+        //   * up to sm_count x 128 systems: 128-system CTAs, one per SM, 16-row chunks -- each warp then has an SM
+        //     sub-partition to itself, and the serial chain of 8760 steps is what bounds the launch (N <= 16384:
+        //     0.88 ms; 8-row chunks 1.08, 256-system CTAs 1.37);
         //   * 224-system CTAs when they save a wave (N = 65536: 293 CTAs fill the 296 slots once, 256 CTAs of 256
         //     leave 40 SMs half empty);   * else 256-system CTAs, 2 per SM (5 KB per TMA row copy).
         // DYNAX_FS_CFG: 1 = scalar (unpacked) 256-wide kernel, 2 = always 128-wide, 3 = always 256-wide.
@@ -167,9 +170,9 @@ static int rc_adjoint(const float *theta, const float *x0, const float *u, const
         else if (cfg == 0 && cost(224) < cost(256)) tn = 224;
         // (with g_x0: 11 fp64 totals per system in shared memory -> 128-system CTAs x3 or 224-system CTAs x2 per SM)
 #define DYNAX_FS_LAUNCH(SU, STG, CTRL)                                                             \
-    (g_x0 ? (tn == 128 ? launch_fwdsens<128, 8, 2, 3, true, SU, STG, CTRL, true>(F, st)              \
+    (g_x0 ? (tn == 128 ? launch_fwdsens<128, 16, 2, 2, true, SU, STG, CTRL, true>(F, st)             \
                        : launch_fwdsens<224, 8, 2, 2, true, SU, STG, CTRL, true>(F, st))             \
-          : tn == 128 ? launch_fwdsens<128, 8, 2, 4, true, SU, STG, CTRL>(F, st)                     \
+          : tn == 128 ? launch_fwdsens<128, 16, 2, 2, true, SU, STG, CTRL>(F, st)                    \
                       : tn == 224 ? launch_fwdsens<224, 8, 2, 2, true, SU, STG, CTRL>(F, st)         \
                                   : launch_fwdsens<256, 8, 2, 2, true, SU, STG, CTRL>(F, st))
         if (ctrl && stg) return DYNAX_FS_LAUNCH(true, true, true);

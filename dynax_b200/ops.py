@@ -84,7 +84,7 @@ def rc_forward(theta, x0, u, dt, emit_x=True, emit_y=True, emit_final=False, dis
     (entries not requested are None).
 
     ``time_chunks``: None = serial-in-time kernel unless the launch cannot fill the GPU with systems alone
-    (N <= 16384 and T >= 256: measured break-evens; a single building over four weeks, examples/1-forward.py,
+    (N <= 8192 and T >= 256: measured break-evens; a single building over four weeks, examples/1-forward.py,
     is 0.045 ms instead of 0.24 ms), where the time-parallel chunked kernel is used with an automatic chunk
     length; 0 = always serial; k > 0 = k chunks.
     """
@@ -97,7 +97,7 @@ def rc_forward(theta, x0, u, dt, emit_x=True, emit_y=True, emit_final=False, dis
     xfin = torch.empty((N, 3), dtype=torch.float32, device=dev) if emit_final else None
     flags = (SHARED_THETA if shared_th else 0) | (SHARED_U if shared_u else 0) | (DISCRETE if discrete else 0)
     if time_chunks is None:
-        time_chunks = -1 if (not discrete and 0 < N <= 16384 and T >= 256) else 0
+        time_chunks = -1 if (not discrete and 0 < N <= 8192 and T >= 256) else 0
     with torch.cuda.device(dev):
         if time_chunks != 0 and not discrete and N > 0 and T > 0:
             chunk_len = 0 if time_chunks < 0 else -(-T // int(time_chunks))
@@ -115,9 +115,8 @@ def rc_loss_grad(theta, x0, u, target, dt, lb=None, ub=None, want_gx0=False, dis
 
     theta[N,7] -> loss[N], grad[N,7];  theta[7] (shared) -> loss[1] (sum over systems), grad[7].
     target[T,N] or [T] (shared).  Returns (loss, grad, g_x0 or None).
-    ``time_chunks``: None = time-parallel chunked kernels only for small long launches (N <= 8192 and
-    T >= 2048; N <= 4096 and T >= 512 -- measured break-evens against the serial tangent kernel), 0 = never,
-    k > 0 = k chunks.
+    ``time_chunks``: None = time-parallel chunked kernels only for small long launches (N <= 4096 and
+    T >= 512 -- measured break-evens against the serial tangent kernel), 0 = never, k > 0 = k chunks.
     """
     x0, u, target = _f32c(x0, "x0"), _f32c(u, "u"), _f32c(target, "target")
     x0, u, N, T, shared_u = _canon_batch(None, x0, u, 3, 5)
@@ -142,7 +141,7 @@ def rc_loss_grad(theta, x0, u, target, dt, lb=None, ub=None, want_gx0=False, dis
     flags = ((SHARED_THETA if shared_th else 0) | (SHARED_U if shared_u else 0) |
              (SHARED_TARGET if shared_tg else 0) | (DISCRETE if discrete else 0))
     if time_chunks is None:
-        small_long = (N <= 8192 and T >= 2048) or (N <= 4096 and T >= 512)
+        small_long = N <= 4096 and T >= 512
         time_chunks = -1 if (not discrete and N > 0 and small_long) else 0
     with torch.cuda.device(dev):
         if time_chunks != 0 and not discrete and N > 0:
