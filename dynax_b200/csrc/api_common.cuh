@@ -34,6 +34,10 @@ int require_sm100();
 
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// (n, m, p) of the dense-LTI kernels that are instantiated (lti_api.cu, lti_chunked.cu)
+#define DYNAX_LTI_DIMS(X) \
+    X(1, 1, 1) X(2, 1, 1) X(2, 2, 1) X(2, 2, 2) X(3, 1, 1) X(3, 3, 1) X(3, 3, 3) X(3, 5, 1) X(4, 1, 1) X(4, 2, 2) X(4, 3, 4) X(4, 4, 4)
+
 struct DeviceInfo {
     int sm_count;
     int smem_optin;

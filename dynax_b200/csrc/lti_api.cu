@@ -7,8 +7,6 @@
 
 // X(n, m, p): (4,3,4) is the shape of the reference's own test
 // (tests/test_forward_simulation.py:17-20); (3,5,1) is the 4R3C shape with free matrices.
-#define DYNAX_LTI_DIMS(X) \
-    X(1, 1, 1) X(2, 1, 1) X(2, 2, 1) X(2, 2, 2) X(3, 1, 1) X(3, 3, 1) X(3, 3, 3) X(3, 5, 1) X(4, 1, 1) X(4, 2, 2) X(4, 3, 4) X(4, 4, 4)
 
 namespace dynax {
 

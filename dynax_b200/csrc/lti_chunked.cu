@@ -334,6 +334,57 @@ int dynax_rc_forward_chunked_f32(const float *theta, const float *x0, const floa
     });
 }
 
+// Dense linear block SSMs (Discrete/ContinuousLinearSSM stepped by the simulator): the same time-parallel forward.
+size_t dynax_lti_forward_chunked_workspace(int64_t N, int64_t T, int n, int64_t chunk_len) {
+    if (N <= 0 || T <= 0 || n <= 0) return 0;
+    const int64_t L = chunk_len > 0 ? chunk_len : auto_chunk_len(N, T, 128);
+    return chunked_ws_bytes(N, T, n, L);
+}
+
+int dynax_lti_forward_chunked_f32(const float *A, const float *B, const float *C, const float *D, const float *x0,
+                                  const float *u, float *xsol, float *ysol, float *x_final, int64_t N, int64_t T, int n,
+                                  int m, int p, float dt, uint32_t flags, int64_t chunk_len, void *ws, size_t ws_bytes,
+                                  void *stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (N < 0 || T < 0) return fail(DYNAX_ERR_INVALID_ARGUMENT, "negative N or T");
+    if (N == 0) return DYNAX_OK;
+    if (!A || !B || !C || !D || !x0 || (!u && T > 0)) return fail(DYNAX_ERR_INVALID_ARGUMENT, "A,B,C,D,x0,u must be non-NULL");
+    if (flags & ~(DYNAX_SHARED_THETA | DYNAX_SHARED_U))
+        return fail(DYNAX_ERR_INVALID_ARGUMENT, "unsupported flags 0x%x for lti_forward_chunked (Euler residual form only)", flags);
+    if (!dynax_lti_supported(n, m, p))
+        return fail(DYNAX_ERR_UNSUPPORTED_DIMS, "no dense-LTI kernel instantiated for (n,m,p)=(%d,%d,%d)", n, m, p);
+    int rc = require_sm100();
+    if (rc != DYNAX_OK) return rc;
+    if (T == 0) {
+        if (x_final) DYNAX_CUDA_TRY(cudaMemcpyAsync(x_final, x0, sizeof(float) * n * N, cudaMemcpyDeviceToDevice, st));
+        return DYNAX_OK;
+    }
+    if (!ws || !aligned16(ws)) return fail(DYNAX_ERR_WORKSPACE, "workspace must be non-NULL and 16-byte aligned");
+    const int64_t L = chunk_len > 0 ? (chunk_len < T ? chunk_len : T) : auto_chunk_len(N, T, 128);
+    const bool rows16 = (N % 4) == 0;
+    const int bulk_in = rows16 && aligned16(u);
+    const int bulk_out = rows16 && (!xsol || aligned16(xsol)) && (!ysol || aligned16(ysol));
+#define X(a, b, c)                                                                                          \
+    if (n == a && m == b && p == c) {                                                                       \
+        using M = DenseModel<a, b, c>;                                                                      \
+        FwdParams<M> P;                                                                                     \
+        P.mp.A = A; P.mp.B = B; P.mp.C = C; P.mp.D = D;                                                     \
+        P.mp.shared = (flags & DYNAX_SHARED_THETA) ? 1 : 0;                                                 \
+        P.x0 = x0; P.u = u; P.xsol = xsol; P.ysol = ysol; P.x_final = x_final;                              \
+        P.N = N; P.T = T; P.dt = dt; P.discrete = 0; P.bulk_in = bulk_in; P.bulk_out = bulk_out;            \
+        if (flags & DYNAX_SHARED_U)                                                                         \
+            return forward_chunked<M>(P, L, ws, ws_bytes, st, [](const FwdParams<M> &Q, cudaStream_t s) {   \
+                return launch_fwd<M, 128, 4, 2, true, 2>(Q, s);                                             \
+            });                                                                                             \
+        return forward_chunked<M>(P, L, ws, ws_bytes, st, [](const FwdParams<M> &Q, cudaStream_t s) {       \
+            return launch_fwd<M, 128, 8, 2, false, 2>(Q, s);                                                \
+        });                                                                                                 \
+    }
+    DYNAX_LTI_DIMS(X)
+#undef X
+    return fail(DYNAX_ERR_UNSUPPORTED_DIMS, "unreachable");
+}
+
 size_t dynax_rc_loss_grad_chunked_workspace(int64_t N, int64_t T, int64_t chunk_len) {
     if (N <= 0 || T <= 0) return 0;
     const int64_t L = chunk_len > 0 ? (chunk_len < T ? chunk_len : T) : auto_chunk_len(N, T, 128);

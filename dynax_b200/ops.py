@@ -246,8 +246,11 @@ def _lti_mats(A, B, C, D, N):
     return [M.contiguous() for M in mats], n, m, p, shared
 
 
-def lti_forward(A, B, C, D, x0, u, dt, emit_x=True, emit_y=True, emit_final=False, discrete=False):
-    """Batched rollout of a dense linear block SSM (A,B,C,D are matrices = Flax kernels transposed)."""
+def lti_forward(A, B, C, D, x0, u, dt, emit_x=True, emit_y=True, emit_final=False, discrete=False, time_chunks=None):
+    """Batched rollout of a dense linear block SSM (A,B,C,D are matrices = Flax kernels transposed).
+
+    ``time_chunks``: as in ``rc_forward`` -- None = the time-parallel chunked kernels for launches that cannot fill
+    the GPU with systems alone (N <= 4096 and T >= 256, continuous stepping), 0 = serial, k > 0 = k chunks."""
     x0, u = _f32c(x0, "x0"), _f32c(u, "u")
     if x0.dim() != 2:
         raise ValueError("x0 must be [N,n]")
@@ -259,9 +262,18 @@ def lti_forward(A, B, C, D, x0, u, dt, emit_x=True, emit_y=True, emit_final=Fals
     ysol = torch.empty((T, N, p), dtype=torch.float32, device=dev) if emit_y else None
     xfin = torch.empty((N, n), dtype=torch.float32, device=dev) if emit_final else None
     flags = (SHARED_THETA if shared_th else 0) | (SHARED_U if shared_u else 0) | (DISCRETE if discrete else 0)
+    if time_chunks is None:
+        time_chunks = -1 if (not discrete and 0 < N <= 4096 and T >= 256) else 0
     with torch.cuda.device(dev):
-        check(lib().dynax_lti_forward_f32(_ptr(A), _ptr(B), _ptr(C), _ptr(D), _ptr(x0), _ptr(u), _ptr(xsol),
-                                          _ptr(ysol), _ptr(xfin), N, T, n, m, p, float(dt), flags, _stream()))
+        if time_chunks != 0 and not discrete and N > 0 and T > 0:
+            chunk_len = 0 if time_chunks < 0 else -(-T // int(time_chunks))
+            ws = _ws(lib().dynax_lti_forward_chunked_workspace(N, T, n, chunk_len), dev)
+            check(lib().dynax_lti_forward_chunked_f32(_ptr(A), _ptr(B), _ptr(C), _ptr(D), _ptr(x0), _ptr(u), _ptr(xsol),
+                                                      _ptr(ysol), _ptr(xfin), N, T, n, m, p, float(dt), flags, chunk_len,
+                                                      _ptr(ws), ws.numel(), _stream()))
+        else:
+            check(lib().dynax_lti_forward_f32(_ptr(A), _ptr(B), _ptr(C), _ptr(D), _ptr(x0), _ptr(u), _ptr(xsol),
+                                              _ptr(ysol), _ptr(xfin), N, T, n, m, p, float(dt), flags, _stream()))
     return xsol, ysol, xfin
 
 

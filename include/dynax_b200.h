@@ -167,6 +167,16 @@ int dynax_lti_vjp_f32(const float *A, const float *B, const float *C, const floa
                       int64_t N, int64_t T, int n, int m, int p, float dt, uint32_t flags,
                       void *ws, size_t ws_bytes, void *stream);
 
+/* Time-parallel variant of dynax_lti_forward_f32 (same scheme as dynax_rc_forward_chunked_f32: Psi = (I+dt A)^L - I,
+ * zero-state pass, stitch, second pass) for launches with few systems and a long horizon.  Euler residual form only
+ * (no DYNAX_DISCRETE).  ws: dynax_lti_forward_chunked_workspace(N,T,n,chunk_len) bytes; chunk_len 0 = automatic. */
+size_t dynax_lti_forward_chunked_workspace(int64_t N, int64_t T, int n, int64_t chunk_len);
+int dynax_lti_forward_chunked_f32(const float *A, const float *B, const float *C, const float *D,
+                                  const float *x0, const float *u,
+                                  float *xsol, float *ysol, float *x_final,
+                                  int64_t N, int64_t T, int n, int m, int p, float dt, uint32_t flags,
+                                  int64_t chunk_len, void *ws, size_t ws_bytes, void *stream);
+
 /* ---- General fx/fy block SSM (dynax/core/base_block_state_space.py:62-63,72-73) with MLP dynamics,
  *      BASELINE.json config 5.  The reference has only the dispatch for this form (its example
  *      examples/4-neural-ode.py does not run), so the model is the restated

@@ -94,3 +94,23 @@ def test_unsupported_dims(T, ops):
     with pytest.raises(DynaxError) as e:
         ops.lti_forward(*(cu(T, v) for v in (A, B, C, D, x0, u)), 0.1)
     assert e.value.code == -2
+
+
+@pytest.mark.parametrize("n,m,p,N,Tn,chunks", [(4, 3, 4, 1, 2000, -1), (3, 5, 1, 130, 700, 7), (2, 1, 1, 33, 257, 4),
+                                               (4, 4, 4, 64, 900, -1), (1, 1, 1, 5, 300, 3), (3, 3, 3, 260, 512, 16)])
+def test_forward_time_parallel(T, ops, n, m, p, N, Tn, chunks):
+    """Time-parallel (chunked) dense-LTI forward: same outputs as the serial kernel within the trajectory tolerance."""
+    dt = 0.02
+    A, B, C, D, x0, u = make(N, Tn, n, m, p, 47)
+    a = [cu(T, v) for v in (A, B, C, D, x0, u)]
+    xs, ys, xf = ops.lti_forward(*a, dt, emit_final=True, time_chunks=chunks)
+    x1, y1, _ = ops.lti_forward(*a, dt, emit_final=True, time_chunks=0)
+    xr, yr = orc.lti_rollout(A, B, C, D, x0, u, dt, np.float64)
+    assert rel_err(xs.cpu().numpy(), xr, floor=1.0) < 1e-5 and rel_err(ys.cpu().numpy(), yr, floor=1.0) < 1e-5
+    assert rel_err(xs.cpu().numpy(), x1.cpu().numpy(), floor=1.0) < 1e-5
+    assert T.equal(xf, xs[-1])
+    # one set of matrices, one shared input series
+    A1, B1, C1, D1 = A[:1], B[:1], C[:1], D[:1]
+    xs, ys, _ = ops.lti_forward(*(cu(T, v) for v in (A1, B1, C1, D1, x0, u[:, :1])), dt, time_chunks=chunks)
+    xr, yr = orc.lti_rollout(A1, B1, C1, D1, x0, u[:, :1], dt, np.float64)
+    assert rel_err(xs.cpu().numpy(), xr, floor=1.0) < 1e-5 and rel_err(ys.cpu().numpy(), yr, floor=1.0) < 1e-5
