@@ -54,6 +54,8 @@ SIGNATURES = {
     "dynax_rc_loss_grad_ctrl_f32": (_int, [_f] * 4 + [_int] + [_f] * 6 + [_i64, _i64, _flt, _u32, _f, _sz, _f]),
     "dynax_tabular_interp_f32": (_int, [_f, _f, _i64, _int, _f, _i64, _int, _f, _f]),
     "dynax_rc_forward_chunked_workspace": (_sz, [_i64, _i64, _i64]),
+    "dynax_rc_vjp_chunked_workspace": (_sz, [_i64, _i64, _i64]),
+    "dynax_rc_vjp_chunked_f32": (_int, [_f] * 8 + [_i64, _i64, _flt, _u32, _i64, _f, _sz, _f]),
     "dynax_rc_forward_chunked_f32": (_int, [_f] * 6 + [_i64, _i64, _flt, _u32, _i64, _f, _sz, _f]),
     "dynax_node_rk4_forward_f32": (_int, [_f] * 11 + [_i64, _i64, _int, _int, _int, _int, _flt, _u32, _f]),
     "dynax_node_rk4_forward_stages_f32": (_int, [_f] * 12 + [_i64, _i64, _int, _int, _int, _int, _flt, _u32, _f]),

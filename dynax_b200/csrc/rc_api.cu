@@ -186,6 +186,13 @@ static int rc_adjoint(const float *theta, const float *x0, const float *u, const
     }
     if constexpr (MODE == ADJ_VJP) {
         if (su) return launch_adj<RCModel, 128, 8, 2, ADJ_VJP, true, false, 2>(P, st);
+        // launches that fit one CTA per SM are bound by the per-segment hand-shakes of the serial chain: 16-step segments
+        if (env_int("DYNAX_VJP_CFG", 0) == 0) {
+            DeviceInfo di;
+            rc = device_info(&di);
+            if (rc != DYNAX_OK) return rc;
+            if ((N + 127) / 128 <= di.sm_count) return launch_adj<RCModel, 128, 16, 2, ADJ_VJP, false, false, 1>(P, st);
+        }
         return launch_adj<RCModel, 128, 8, 2, ADJ_VJP, false, false, 2>(P, st);
     } else {
         // shared-u stages are small (<= 17 KB): a 4-deep ring keeps the producer ahead of the consumers

@@ -112,6 +112,9 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_adj_kernel(const AdjPar
     const float *const u_base = P.u + t_begin * (SHARED_U ? m : N * m);
     const float *const tgt_base = P.target ? P.target + t_begin * (SHARED_TGT ? 1 : N) : nullptr;
     const float *const ctrl_base = P.ctrl ? P.ctrl + t_begin * N : nullptr;
+    const float *const gy_base = P.g_ysol ? P.g_ysol + t_begin * N * p : nullptr;
+    const float *const gx_base = P.g_xsol ? P.g_xsol + t_begin * N * n : nullptr;
+    float *const gu_base = P.g_u ? P.g_u + t_begin * N * m : nullptr;
     const int64_t C = (T + KC - 1) / KC;  // number of segments
     const int64_t Q = 2 * C - 1;          // chunks through the ring: C-1 forward + C reverse
 
@@ -174,8 +177,8 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_adj_kernel(const AdjPar
                     if (MODE == ADJ_MSE) {
                         b += stream(pass, st + Cfg::A1_OFF, A1_ROW, tgt_base, 1, SHARED_TGT, k0, rows, &full[s]);
                     } else {
-                        b += stream(pass, st + Cfg::A1_OFF, A1_ROW, P.g_ysol, p, false, k0, rows, &full[s]);
-                        b += stream(pass, st + Cfg::A2_OFF, A2_ROW, P.g_xsol, n, false, k0, rows, &full[s]);
+                        b += stream(pass, st + Cfg::A1_OFF, A1_ROW, gy_base, p, false, k0, rows, &full[s]);
+                        b += stream(pass, st + Cfg::A2_OFF, A2_ROW, gx_base, n, false, k0, rows, &full[s]);
                     }
                 }
                 if (pass == 0) {
@@ -319,10 +322,10 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_adj_kernel(const AdjPar
 #pragma unroll
                 for (int d = 0; d < n; ++d) sv[d] = discrete ? a[d] : dt * a[d];  // cotangent of rhs
                 if (!P.skip_grads) M.accum(Gp, sv, gy, xs[j], u);
-                if (MODE == ADJ_VJP && P.g_u != nullptr && active) {
+                if (MODE == ADJ_VJP && gu_base != nullptr && active && !P.skip_grads) {
                     float gu[m];
                     M.adj_u(sv, gy, gu);
-                    float *dst = P.g_u + ((k0 + j) * N + i) * m;
+                    float *dst = gu_base + ((k0 + j) * N + i) * m;
 #pragma unroll
                     for (int d = 0; d < m; ++d) dst[d] = gu[d];
                 }

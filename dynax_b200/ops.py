@@ -160,8 +160,12 @@ def rc_loss_grad(theta, x0, u, target, dt, lb=None, ub=None, want_gx0=False, dis
     return loss, grad, gx0
 
 
-def rc_vjp(theta, x0, u, dt, g_xsol=None, g_ysol=None, need_theta=True, need_x0=True, need_u=True, discrete=False):
-    """VJP of rc_forward for arbitrary cotangents g_xsol[T,N,3], g_ysol[T,N,1] -> (g_theta, g_x0, g_u)."""
+def rc_vjp(theta, x0, u, dt, g_xsol=None, g_ysol=None, need_theta=True, need_x0=True, need_u=True, discrete=False,
+           time_chunks=None):
+    """VJP of rc_forward for arbitrary cotangents g_xsol[T,N,3], g_ysol[T,N,1] -> (g_theta, g_x0, g_u).
+
+    ``time_chunks``: None = the time-parallel chunked adjoint for launches that cannot fill the GPU with systems alone
+    (N <= 8192 and T >= 512: measured break-evens; continuous stepping), 0 = serial, k > 0 = k chunks."""
     x0, u = _f32c(x0, "x0"), _f32c(u, "u")
     x0, u, N, T, shared_u = _canon_batch(None, x0, u, 3, 5)
     theta, shared_th = _rc_theta(theta, N)
@@ -177,11 +181,20 @@ def rc_vjp(theta, x0, u, dt, g_xsol=None, g_ysol=None, need_theta=True, need_x0=
     gu = torch.empty((T, N, 5), dtype=torch.float32, device=dev) if need_u else None
     flags = ((SHARED_THETA if shared_th else 0) | (SHARED_U if (shared_u and not need_u) else 0) |
              (DISCRETE if discrete else 0))
-    nbytes = lib().dynax_workspace_bytes(_lib.OP_RC_VJP, N, T, 3, 5, 1, flags)
-    ws = _ws(nbytes, dev)
+    if time_chunks is None:
+        time_chunks = -1 if (not discrete and 0 < N <= 8192 and T >= 512) else 0
+    chunked = time_chunks != 0 and not discrete and not (flags & SHARED_U) and N > 0
     with torch.cuda.device(dev):
-        check(lib().dynax_rc_vjp_f32(_ptr(theta), _ptr(x0), _ptr(u_k), _ptr(g_xsol), _ptr(g_ysol), _ptr(gth),
-                                     _ptr(gx0), _ptr(gu), N, T, float(dt), flags, _ptr(ws), ws.numel(), _stream()))
+        if chunked:
+            chunk_len = 0 if time_chunks < 0 else -(-T // int(time_chunks))
+            ws = _ws(lib().dynax_rc_vjp_chunked_workspace(N, T, chunk_len), dev)
+            check(lib().dynax_rc_vjp_chunked_f32(_ptr(theta), _ptr(x0), _ptr(u_k), _ptr(g_xsol), _ptr(g_ysol), _ptr(gth),
+                                                 _ptr(gx0), _ptr(gu), N, T, float(dt), flags & SHARED_THETA, chunk_len,
+                                                 _ptr(ws), ws.numel(), _stream()))
+        else:
+            ws = _ws(lib().dynax_workspace_bytes(_lib.OP_RC_VJP, N, T, 3, 5, 1, flags), dev)
+            check(lib().dynax_rc_vjp_f32(_ptr(theta), _ptr(x0), _ptr(u_k), _ptr(g_xsol), _ptr(g_ysol), _ptr(gth),
+                                         _ptr(gx0), _ptr(gu), N, T, float(dt), flags, _ptr(ws), ws.numel(), _stream()))
     if gu is not None and shared_u:
         gu = gu.sum(dim=1, keepdim=True)
     return gth, gx0, gu

@@ -151,6 +151,17 @@ int dynax_rc_vjp_f32(const float *theta, const float *x0, const float *u,
                      int64_t N, int64_t T, float dt, uint32_t flags,
                      void *ws, size_t ws_bytes, void *stream);
 
+/* Time-parallel variant of dynax_rc_vjp_f32 (same outputs within the gradient tolerance) for launches with few
+ * systems and a long horizon: forward chunk boundaries, every chunk's adjoint for a zero terminal adjoint, a backward
+ * stitch with Psi^T, every chunk's adjoint again from its true terminal adjoint.  Per-system u, Euler residual form;
+ * flags: DYNAX_SHARED_THETA only.  ws: dynax_rc_vjp_chunked_workspace(N,T,chunk_len) bytes; chunk_len 0 = automatic. */
+size_t dynax_rc_vjp_chunked_workspace(int64_t N, int64_t T, int64_t chunk_len);
+int dynax_rc_vjp_chunked_f32(const float *theta, const float *x0, const float *u,
+                             const float *g_xsol, const float *g_ysol,
+                             float *g_theta, float *g_x0, float *g_u,
+                             int64_t N, int64_t T, float dt, uint32_t flags, int64_t chunk_len,
+                             void *ws, size_t ws_bytes, void *stream);
+
 /* ---- Dense linear block SSM: DiscreteLinearSSM / ContinuousLinearSSM
  *      (dynax/core/discrete_block_state_space.py:5-54, continuous_block_state_space.py:5-54).
  *      A:[N|1,n,n] B:[N|1,n,m] C:[N|1,p,n] D:[N|1,p,m] are the MATRICES (row-major), i.e. the

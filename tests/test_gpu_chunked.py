@@ -78,3 +78,30 @@ def test_chunked_loss_grad_shared_modes(T):
     peng = orc.bound_penalty_grad(th1[None], orc.RC_LB, orc.RC_UB)[0]
     assert_loss_parity(loss.cpu().numpy()[0], l64.sum() + pen, lbud.sum())
     assert_grad_parity(grad.cpu().numpy(), g64.sum(0) + peng, gbud.sum(0))
+
+
+@pytest.mark.parametrize("N,Tn,chunks,use_gx", [(64, 4000, -1, True), (1, 8760, 40, False), (130, 1000, 7, True),
+                                                (33, 257, 4, True), (8, 100, 1, False), (5, 70, 9, True)])
+def test_chunked_vjp_matches_fp64_and_serial(T, N, Tn, chunks, use_gx):
+    """Time-parallel general-cotangent VJP (what autograd through rc_rollout calls for few systems, long horizons)."""
+    from dynax_b200 import ops
+    rng = np.random.default_rng(115)
+    th, x0, u = orc.synth_theta(N, 115), orc.synth_x0(N, 115), orc.synth_u(Tn, N, 115)
+    gx = rng.normal(size=(Tn, N, 3)).astype(np.float32) if use_gx else None
+    gy = rng.normal(size=(Tn, N, 1)).astype(np.float32)
+    a = [cu(T, v) for v in (th, x0, u)]
+    args = (None if gx is None else cu(T, gx), cu(T, gy))
+    gth, gx0, gu = ops.rc_vjp(*a, 3600.0, *args, time_chunks=chunks)
+    sth, sx0, su_ = ops.rc_vjp(*a, 3600.0, *args, time_chunks=0)
+    rth, rx0, ru = orc.rc_vjp(th, x0, u, 3600.0, gx, gy, np.float64)
+    fth, fx0, fu = orc.rc_vjp(th, x0, u, 3600.0, gx, gy, np.float32)       # yardstick: the same adjoint in fp32
+    nrm = lambda p_, q_: np.linalg.norm(p_ - q_) / (np.linalg.norm(q_) + 1e-30)
+    assert nrm(gth.cpu().numpy(), rth) <= max(1e-4, 2.0 * nrm(fth, rth))
+    assert rel_err(gx0.cpu().numpy(), rx0, floor=1.0) <= max(1e-4, 2.0 * rel_err(fx0, rx0, floor=1.0))
+    assert rel_err(gu.cpu().numpy(), ru, floor=1.0) <= max(1e-4, 2.0 * rel_err(fu, ru, floor=1.0))
+    assert nrm(gth.cpu().numpy(), sth.cpu().numpy()) <= max(2e-4, 4.0 * nrm(fth, rth))
+    # one shared parameter vector: gradient summed over systems
+    g1, _, _ = ops.rc_vjp(cu(T, th[0]), a[1], a[2], 3600.0, *args, need_u=False, time_chunks=chunks)
+    r1, _, _ = orc.rc_vjp(np.repeat(th[:1], N, 0), x0, u, 3600.0, gx, gy, np.float64)
+    f1, _, _ = orc.rc_vjp(np.repeat(th[:1], N, 0), x0, u, 3600.0, gx, gy, np.float32)
+    assert nrm(g1.cpu().numpy().reshape(-1), r1.sum(0)) <= max(1e-4, 2.0 * nrm(f1.sum(0), r1.sum(0)))
