@@ -111,6 +111,18 @@ def test_chunked_and_ctrl_shapes(N, Tn):
         loss, grad, _ = ops.rc_loss_grad(cu(T, th), cu(T, x0), cu(T, u), cu(T, target), 3600.0, time_chunks=chunks)
         assert_loss_parity(loss.cpu().numpy(), l64, lbud, what=(N, Tn, chunks))
         assert_grad_parity(grad.cpu().numpy(), g64, gbud, what=(N, Tn, chunks))
+    # general-cotangent VJP, time-parallel vs serial (both against the fp64 hand adjoint, fp32 adjoint as yardstick)
+    rng = np.random.default_rng(seed)
+    gx = rng.normal(size=(Tn, N, 3)).astype(np.float32)
+    gy = rng.normal(size=(Tn, N, 1)).astype(np.float32)
+    rth, rx0, ru = orc.rc_vjp(th, x0, u, 3600.0, gx, gy, np.float64)
+    fth, fx0, fu = orc.rc_vjp(th, x0, u, 3600.0, gx, gy, np.float32)
+    nrm = lambda a, b: np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30)
+    for chunks in (-1, 2, Tn):
+        gth, gx0, gu = ops.rc_vjp(cu(T, th), cu(T, x0), cu(T, u), 3600.0, cu(T, gx), cu(T, gy), time_chunks=chunks)
+        assert nrm(gth.cpu().numpy(), rth) <= max(1e-4, 2.0 * nrm(fth, rth)), (N, Tn, chunks)
+        assert rel_err(gx0.cpu().numpy(), rx0, floor=1.0) <= max(1e-4, 2.0 * rel_err(fx0, rx0, floor=1.0)), (N, Tn, chunks)
+        assert rel_err(gu.cpu().numpy(), ru, floor=1.0) <= max(1e-4, 2.0 * rel_err(fu, ru, floor=1.0)), (N, Tn, chunks)
     # shared disturbances + one per-system channel in column `col`
     for col in (0, 2, 4):
         d = u[:, 0].copy()
