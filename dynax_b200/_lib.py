@@ -35,6 +35,8 @@ SIGNATURES = {
     "dynax_rc_vjp_f32": (_int, [_f] * 8 + [_i64, _i64, _flt, _u32, _f, _sz, _f]),
     "dynax_lti_forward_f32": (_int, [_f] * 9 + [_i64, _i64, _int, _int, _int, _flt, _u32, _f]),
     "dynax_lti_forward_chunked_workspace": (_sz, [_i64, _i64, _int, _i64]),
+    "dynax_lti_vjp_chunked_workspace": (_sz, [_i64, _i64, _int, _int, _int, _i64]),
+    "dynax_lti_vjp_chunked_f32": (_int, [_f] * 14 + [_i64, _i64, _int, _int, _int, _flt, _u32, _i64, _f, _sz, _f]),
     "dynax_lti_forward_chunked_f32": (_int, [_f] * 9 + [_i64, _i64, _int, _int, _int, _flt, _u32, _i64, _f, _sz, _f]),
     "dynax_lti_vjp_f32": (_int, [_f] * 14 + [_i64, _i64, _int, _int, _int, _flt, _u32, _f, _sz, _f]),
     "dynax_rc_forward_host_f32": (_int, [_f] * 6 + [_i64, _i64, _flt, _u32, _i64]),

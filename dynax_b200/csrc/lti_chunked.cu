@@ -269,7 +269,8 @@ struct ChunkedAdjWs {
     size_t bytes;
 };
 
-inline ChunkedAdjWs chunked_adj_layout(void *ws, int64_t N, int64_t T, int n, int nout, int64_t L) {
+inline ChunkedAdjWs chunked_adj_layout(void *ws, int64_t N, int64_t T, int n, int nout, int64_t L,
+                                       bool tangent_bufs = false) {
     const int64_t C = (T + L - 1) / L;
     const int64_t segs = (L + kMinKC - 1) / kMinKC;
     char *p = reinterpret_cast<char *>(ws);
@@ -287,10 +288,70 @@ inline ChunkedAdjWs chunked_adj_layout(void *ws, int64_t N, int64_t T, int n, in
     o.w = reinterpret_cast<float *>(take(sizeof(float) * (size_t)C * N * n));
     o.aend = reinterpret_cast<float *>(take(sizeof(float) * (size_t)C * N * n));
     o.ckpt = reinterpret_cast<float *>(take(sizeof(float) * (size_t)C * segs * n * N));
-    o.s_end = reinterpret_cast<float *>(take(sizeof(float) * (size_t)C * N * n * nout));
-    o.g_loc = reinterpret_cast<double *>(take(sizeof(double) * (size_t)C * N * (nout + 1)));
+    o.s_end = tangent_bufs ? reinterpret_cast<float *>(take(sizeof(float) * (size_t)C * N * n * nout)) : nullptr;
+    o.g_loc = tangent_bufs ? reinterpret_cast<double *>(take(sizeof(double) * (size_t)C * N * (nout + 1))) : nullptr;
     o.bytes = (size_t)(p - reinterpret_cast<char *>(ws));
     return o;
+}
+
+// Time-parallel general-cotangent VJP, any linear block model (see dynax_rc_vjp_chunked_f32 below).
+template <class Model, int MINB>
+int vjp_chunked(typename Model::Ptrs mp, typename Model::GradPtrs gp, const float *x0, const float *u,
+                const float *g_xsol, const float *g_ysol, float *g_x0, float *g_u, int64_t N, int64_t T, float dt,
+                bool sth, int64_t chunk_len, void *ws, size_t ws_bytes, cudaStream_t st) {
+    constexpr int n = Model::n, NOUT = Model::NOUT;
+    int rc = require_sm100();
+    if (rc != DYNAX_OK) return rc;
+    const int64_t L = chunk_len > 0 ? (chunk_len < T ? chunk_len : T) : auto_chunk_len(N, T, 128);
+    const int64_t C = (T + L - 1) / L;
+    if (!ws || !aligned16(ws)) return fail(DYNAX_ERR_WORKSPACE, "workspace must be non-NULL and 16-byte aligned");
+    const ChunkedAdjWs W = chunked_adj_layout(ws, N, T, n, NOUT, L);
+    if (ws_bytes < W.bytes) return fail(DYNAX_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", W.bytes, ws_bytes);
+    const bool bulk = (N % 4) == 0 && aligned16(u) && (!g_xsol || aligned16(g_xsol)) && (!g_ysol || aligned16(g_ysol));
+    const unsigned tb = 128, gb = (unsigned)((N + tb - 1) / tb);
+
+    // ---- forward: chunk boundary states xb[c]  (psi, zero-state responses, stitch)
+    FwdParams<Model> F;
+    F.mp = mp;
+    F.x0 = x0; F.u = u; F.xsol = nullptr; F.ysol = nullptr; F.x_final = W.v;
+    F.N = N; F.T = T; F.dt = dt; F.discrete = 0; F.bulk_in = (N % 4) == 0 && aligned16(u); F.bulk_out = 0;
+    F.chunk_len = L; F.x0_zero = 1;
+    psi_kernel<Model><<<gb, tb, 0, st>>>(mp, W.psi, N, L, dt);
+    DYNAX_CUDA_TRY(cudaGetLastError());
+    rc = launch_fwd<Model, 128, 8, 2, false, 2>(F, st);
+    if (rc != DYNAX_OK) return rc;
+    stitch_kernel<n><<<gb, tb, 0, st>>>(W.psi, x0, W.v, W.xb, N, C);
+    DYNAX_CUDA_TRY(cudaGetLastError());
+
+    // ---- adjoint pass B1 (zero terminal adjoint, no sums) -> w[c]; backward stitch -> aend[c]; pass B2 (true terminal
+    //      adjoints): gradient sums per system in fp64 over the chunks, g_u in place
+    AdjParams<Model> A;
+    memset(&A, 0, sizeof(A));
+    A.mp = mp; A.gp = gp;
+    A.x0 = W.xb; A.x0_chunk_stride = N * n;
+    A.u = u; A.g_xsol = g_xsol; A.g_ysol = g_ysol; A.g_u = g_u;
+    A.ckpt = W.ckpt; A.ckpt_chunk_stride = ((L + kMinKC - 1) / kMinKC) * n * N;
+    A.shared_acc = W.shared_acc;
+    A.N = N; A.T = T; A.dt = dt; A.bulk = bulk; A.shared_theta = sth ? 1 : 0; A.chunk_len = L;
+    AdjParams<Model> B1 = A;
+    B1.a_start = W.w; B1.skip_grads = 1;
+    rc = launch_adj<Model, 128, 8, 2, ADJ_VJP, false, false, MINB>(B1, st);
+    if (rc != DYNAX_OK) return rc;
+    stitch_adjoint_kernel<n><<<gb, tb, 0, st>>>(W.psi, W.w, W.aend, N, C);
+    DYNAX_CUDA_TRY(cudaGetLastError());
+    DYNAX_CUDA_TRY(cudaMemsetAsync(W.chunk_acc, 0, sizeof(double) * (size_t)N * (NOUT + 1), st));
+    if (sth) DYNAX_CUDA_TRY(cudaMemsetAsync(W.shared_acc, 0, kAccBytes, st));
+    AdjParams<Model> B2 = A;
+    B2.a_term = W.aend; B2.chunk_acc = W.chunk_acc; B2.g_x0 = g_x0;
+    rc = launch_adj<Model, 128, 8, 2, ADJ_VJP, false, false, MINB>(B2, st);
+    if (rc != DYNAX_OK) return rc;
+    chunk_finalize_kernel<Model><<<gb, tb, 0, st>>>(W.chunk_acc, mp, gp, nullptr, nullptr, nullptr, W.shared_acc, N, sth ? 1 : 0);
+    DYNAX_CUDA_TRY(cudaGetLastError());
+    if (sth) {
+        shared_finalize_kernel<Model, ADJ_VJP><<<1, 32, 0, st>>>(W.shared_acc, mp, gp, nullptr, nullptr, nullptr);
+        DYNAX_CUDA_TRY(cudaGetLastError());
+    }
+    return DYNAX_OK;
 }
 
 }  // namespace dynax
@@ -398,69 +459,59 @@ size_t dynax_rc_vjp_chunked_workspace(int64_t N, int64_t T, int64_t chunk_len) {
 int dynax_rc_vjp_chunked_f32(const float *theta, const float *x0, const float *u, const float *g_xsol,
                              const float *g_ysol, float *g_theta, float *g_x0, float *g_u, int64_t N, int64_t T,
                              float dt, uint32_t flags, int64_t chunk_len, void *ws, size_t ws_bytes, void *stream) {
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (N < 0 || T < 1) return fail(DYNAX_ERR_INVALID_ARGUMENT, "need N >= 0 and T >= 1");
     if (N == 0) return DYNAX_OK;
     if (!theta || !x0 || !u) return fail(DYNAX_ERR_INVALID_ARGUMENT, "theta, x0 and u must be non-NULL");
     if (!g_xsol && !g_ysol) return fail(DYNAX_ERR_INVALID_ARGUMENT, "need g_xsol or g_ysol");
     if (flags & ~DYNAX_SHARED_THETA)
         return fail(DYNAX_ERR_INVALID_ARGUMENT, "unsupported flags 0x%x for rc_vjp_chunked (per-system u, Euler residual form)", flags);
-    int rc = require_sm100();
-    if (rc != DYNAX_OK) return rc;
+    RCModel::Ptrs mp;
+    mp.theta = theta; mp.stride = (flags & DYNAX_SHARED_THETA) ? 0 : 7;
+    RCModel::GradPtrs gp;
+    gp.g_theta = g_theta;
+    return vjp_chunked<RCModel, 2>(mp, gp, x0, u, g_xsol, g_ysol, g_x0, g_u, N, T, dt, (flags & DYNAX_SHARED_THETA) != 0,
+                                   chunk_len, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+size_t dynax_lti_vjp_chunked_workspace(int64_t N, int64_t T, int n, int m, int p, int64_t chunk_len) {
+    if (N <= 0 || T <= 0 || n <= 0) return 0;
     const int64_t L = chunk_len > 0 ? (chunk_len < T ? chunk_len : T) : auto_chunk_len(N, T, 128);
-    const int64_t C = (T + L - 1) / L;
-    if (!ws || !aligned16(ws)) return fail(DYNAX_ERR_WORKSPACE, "workspace must be non-NULL and 16-byte aligned");
-    const ChunkedAdjWs W = chunked_adj_layout(ws, N, T, 3, 7, L);
-    if (ws_bytes < W.bytes) return fail(DYNAX_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", W.bytes, ws_bytes);
-    const bool sth = flags & DYNAX_SHARED_THETA;
-    const bool bulk = (N % 4) == 0 && aligned16(u) && (!g_xsol || aligned16(g_xsol)) && (!g_ysol || aligned16(g_ysol));
-    const unsigned tb = 128, gb = (unsigned)((N + tb - 1) / tb);
+    return chunked_adj_layout(nullptr, N, T, n, n * n + n * m + p * n + p * m, L).bytes;
+}
 
-    FwdParams<RCModel> F;
-    F.mp.theta = theta; F.mp.stride = sth ? 0 : 7;
-    F.x0 = x0; F.u = u; F.xsol = nullptr; F.ysol = nullptr; F.x_final = W.v;
-    F.N = N; F.T = T; F.dt = dt; F.discrete = 0; F.bulk_in = (N % 4) == 0 && aligned16(u); F.bulk_out = 0;
-    F.chunk_len = L; F.x0_zero = 1;
-    psi_kernel<RCModel><<<gb, tb, 0, st>>>(F.mp, W.psi, N, L, dt);
-    DYNAX_CUDA_TRY(cudaGetLastError());
-    rc = launch_fwd<RCModel, 128, 8, 2, false, 3>(F, st);
-    if (rc != DYNAX_OK) return rc;
-    stitch_kernel<3><<<gb, tb, 0, st>>>(W.psi, x0, W.v, W.xb, N, C);
-    DYNAX_CUDA_TRY(cudaGetLastError());
-
-    AdjParams<RCModel> A;
-    memset(&A, 0, sizeof(A));
-    A.mp = F.mp; A.gp.g_theta = g_theta;
-    A.x0 = W.xb; A.x0_chunk_stride = N * 3;
-    A.u = u; A.g_xsol = g_xsol; A.g_ysol = g_ysol; A.g_u = g_u;
-    A.ckpt = W.ckpt; A.ckpt_chunk_stride = ((L + kMinKC - 1) / kMinKC) * 3 * N;
-    A.shared_acc = W.shared_acc;
-    A.N = N; A.T = T; A.dt = dt; A.bulk = bulk; A.shared_theta = sth ? 1 : 0; A.chunk_len = L;
-    AdjParams<RCModel> B1 = A;
-    B1.a_start = W.w; B1.skip_grads = 1;
-    rc = launch_adj<RCModel, 128, 8, 2, ADJ_VJP, false, false, 2>(B1, st);
-    if (rc != DYNAX_OK) return rc;
-    stitch_adjoint_kernel<3><<<gb, tb, 0, st>>>(W.psi, W.w, W.aend, N, C);
-    DYNAX_CUDA_TRY(cudaGetLastError());
-    DYNAX_CUDA_TRY(cudaMemsetAsync(W.chunk_acc, 0, sizeof(double) * (size_t)N * 8, st));
-    if (sth) DYNAX_CUDA_TRY(cudaMemsetAsync(W.shared_acc, 0, kAccBytes, st));
-    AdjParams<RCModel> B2 = A;
-    B2.a_term = W.aend; B2.chunk_acc = W.chunk_acc; B2.g_x0 = g_x0;
-    rc = launch_adj<RCModel, 128, 8, 2, ADJ_VJP, false, false, 2>(B2, st);
-    if (rc != DYNAX_OK) return rc;
-    chunk_finalize_kernel<RCModel><<<gb, tb, 0, st>>>(W.chunk_acc, A.mp, A.gp, nullptr, nullptr, nullptr, W.shared_acc, N, sth ? 1 : 0);
-    DYNAX_CUDA_TRY(cudaGetLastError());
-    if (sth) {
-        shared_finalize_kernel<RCModel, ADJ_VJP><<<1, 32, 0, st>>>(W.shared_acc, A.mp, A.gp, nullptr, nullptr, nullptr);
-        DYNAX_CUDA_TRY(cudaGetLastError());
+int dynax_lti_vjp_chunked_f32(const float *A, const float *B, const float *C, const float *D, const float *x0,
+                              const float *u, const float *g_xsol, const float *g_ysol, float *g_A, float *g_B,
+                              float *g_C, float *g_D, float *g_x0, float *g_u, int64_t N, int64_t T, int n, int m,
+                              int p, float dt, uint32_t flags, int64_t chunk_len, void *ws, size_t ws_bytes,
+                              void *stream) {
+    if (N < 0 || T < 1) return fail(DYNAX_ERR_INVALID_ARGUMENT, "need N >= 0 and T >= 1");
+    if (N == 0) return DYNAX_OK;
+    if (!A || !B || !C || !D || !x0 || !u) return fail(DYNAX_ERR_INVALID_ARGUMENT, "A,B,C,D,x0,u must be non-NULL");
+    if (!g_xsol && !g_ysol) return fail(DYNAX_ERR_INVALID_ARGUMENT, "need g_xsol or g_ysol");
+    if (flags & ~DYNAX_SHARED_THETA)
+        return fail(DYNAX_ERR_INVALID_ARGUMENT, "unsupported flags 0x%x for lti_vjp_chunked (per-system u, Euler residual form)", flags);
+    if (!dynax_lti_supported(n, m, p))
+        return fail(DYNAX_ERR_UNSUPPORTED_DIMS, "no dense-LTI kernel instantiated for (n,m,p)=(%d,%d,%d)", n, m, p);
+#define X(a, b, c)                                                                                              \
+    if (n == a && m == b && p == c) {                                                                           \
+        using M = DenseModel<a, b, c>;                                                                          \
+        M::Ptrs mp;                                                                                             \
+        mp.A = A; mp.B = B; mp.C = C; mp.D = D; mp.shared = (flags & DYNAX_SHARED_THETA) ? 1 : 0;               \
+        M::GradPtrs gp;                                                                                         \
+        gp.gA = g_A; gp.gB = g_B; gp.gC = g_C; gp.gD = g_D;                                                     \
+        return vjp_chunked<M, 1>(mp, gp, x0, u, g_xsol, g_ysol, g_x0, g_u, N, T, dt,                            \
+                                 (flags & DYNAX_SHARED_THETA) != 0, chunk_len, ws, ws_bytes,                    \
+                                 static_cast<cudaStream_t>(stream));                                            \
     }
-    return DYNAX_OK;
+    DYNAX_LTI_DIMS(X)
+#undef X
+    return fail(DYNAX_ERR_UNSUPPORTED_DIMS, "unreachable");
 }
 
 size_t dynax_rc_loss_grad_chunked_workspace(int64_t N, int64_t T, int64_t chunk_len) {
     if (N <= 0 || T <= 0) return 0;
     const int64_t L = chunk_len > 0 ? (chunk_len < T ? chunk_len : T) : auto_chunk_len(N, T, 128);
-    return chunked_adj_layout(nullptr, N, T, 3, 7, L).bytes;
+    return chunked_adj_layout(nullptr, N, T, 3, 7, L, true).bytes;
 }
 
 int dynax_rc_loss_grad_chunked_f32(const float *theta, const float *x0, const float *u, const float *target,
@@ -479,7 +530,7 @@ int dynax_rc_loss_grad_chunked_f32(const float *theta, const float *x0, const fl
     const int64_t L = chunk_len > 0 ? (chunk_len < T ? chunk_len : T) : auto_chunk_len(N, T, 128);
     const int64_t C = (T + L - 1) / L;
     if (!ws || !aligned16(ws)) return fail(DYNAX_ERR_WORKSPACE, "workspace must be non-NULL and 16-byte aligned");
-    const ChunkedAdjWs W = chunked_adj_layout(ws, N, T, 3, 7, L);
+    const ChunkedAdjWs W = chunked_adj_layout(ws, N, T, 3, 7, L, true);
     if (ws_bytes < W.bytes) return fail(DYNAX_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", W.bytes, ws_bytes);
     const bool sth = flags & DYNAX_SHARED_THETA, su = flags & DYNAX_SHARED_U, stg = flags & DYNAX_SHARED_TARGET;
     const bool bulk = (N % 4) == 0 && aligned16(u) && aligned16(target);

@@ -291,8 +291,11 @@ def lti_forward(A, B, C, D, x0, u, dt, emit_x=True, emit_y=True, emit_final=Fals
 
 
 def lti_vjp(A, B, C, D, x0, u, dt, g_xsol=None, g_ysol=None, need_mats=True, need_x0=True, need_u=True,
-            discrete=False):
-    """VJP of lti_forward -> (gA, gB, gC, gD, g_x0, g_u); matrix grads are summed over systems if shared."""
+            discrete=False, time_chunks=None):
+    """VJP of lti_forward -> (gA, gB, gC, gD, g_x0, g_u); matrix grads are summed over systems if shared.
+
+    ``time_chunks``: None = the time-parallel chunked adjoint for launches that cannot fill the GPU with systems alone
+    (N <= 4096 and T >= 512: measured break-evens; continuous stepping), 0 = serial, k > 0 = k chunks."""
     x0, u = _f32c(x0, "x0"), _f32c(u, "u")
     N = x0.shape[0]
     (A, B, C, D), n, m, p, shared_th = _lti_mats(A, B, C, D, N)
@@ -310,12 +313,22 @@ def lti_vjp(A, B, C, D, x0, u, dt, g_xsol=None, g_ysol=None, need_mats=True, nee
     gu = torch.empty((T, N, m), dtype=torch.float32, device=dev) if need_u else None
     flags = ((SHARED_THETA if shared_th else 0) | (SHARED_U if (shared_u and not need_u) else 0) |
              (DISCRETE if discrete else 0))
-    nbytes = lib().dynax_workspace_bytes(_lib.OP_LTI_VJP, N, T, n, m, p, flags)
-    ws = _ws(nbytes, dev)
+    if time_chunks is None:
+        time_chunks = -1 if (not discrete and 0 < N <= 4096 and T >= 512) else 0
+    chunked = time_chunks != 0 and not discrete and not (flags & SHARED_U) and N > 0
     with torch.cuda.device(dev):
-        check(lib().dynax_lti_vjp_f32(_ptr(A), _ptr(B), _ptr(C), _ptr(D), _ptr(x0), _ptr(u_k), _ptr(g_xsol),
-                                      _ptr(g_ysol), _ptr(gm[0]), _ptr(gm[1]), _ptr(gm[2]), _ptr(gm[3]), _ptr(gx0),
-                                      _ptr(gu), N, T, n, m, p, float(dt), flags, _ptr(ws), ws.numel(), _stream()))
+        if chunked:
+            chunk_len = 0 if time_chunks < 0 else -(-T // int(time_chunks))
+            ws = _ws(lib().dynax_lti_vjp_chunked_workspace(N, T, n, m, p, chunk_len), dev)
+            check(lib().dynax_lti_vjp_chunked_f32(_ptr(A), _ptr(B), _ptr(C), _ptr(D), _ptr(x0), _ptr(u_k), _ptr(g_xsol),
+                                                  _ptr(g_ysol), _ptr(gm[0]), _ptr(gm[1]), _ptr(gm[2]), _ptr(gm[3]),
+                                                  _ptr(gx0), _ptr(gu), N, T, n, m, p, float(dt), flags & SHARED_THETA,
+                                                  chunk_len, _ptr(ws), ws.numel(), _stream()))
+        else:
+            ws = _ws(lib().dynax_workspace_bytes(_lib.OP_LTI_VJP, N, T, n, m, p, flags), dev)
+            check(lib().dynax_lti_vjp_f32(_ptr(A), _ptr(B), _ptr(C), _ptr(D), _ptr(x0), _ptr(u_k), _ptr(g_xsol),
+                                          _ptr(g_ysol), _ptr(gm[0]), _ptr(gm[1]), _ptr(gm[2]), _ptr(gm[3]), _ptr(gx0),
+                                          _ptr(gu), N, T, n, m, p, float(dt), flags, _ptr(ws), ws.numel(), _stream()))
     if gu is not None and shared_u:
         gu = gu.sum(dim=1, keepdim=True)
     return gm[0], gm[1], gm[2], gm[3], gx0, gu

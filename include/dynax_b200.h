@@ -188,6 +188,16 @@ int dynax_lti_forward_chunked_f32(const float *A, const float *B, const float *C
                                   int64_t N, int64_t T, int n, int m, int p, float dt, uint32_t flags,
                                   int64_t chunk_len, void *ws, size_t ws_bytes, void *stream);
 
+/* Time-parallel variant of dynax_lti_vjp_f32 (same scheme as dynax_rc_vjp_chunked_f32) for launches with few systems
+ * and a long horizon -- fitting A,B,C,D to one measured trajectory.  Per-system u, Euler residual form; flags:
+ * DYNAX_SHARED_THETA only.  ws: dynax_lti_vjp_chunked_workspace(N,T,n,m,p,chunk_len) bytes. */
+size_t dynax_lti_vjp_chunked_workspace(int64_t N, int64_t T, int n, int m, int p, int64_t chunk_len);
+int dynax_lti_vjp_chunked_f32(const float *A, const float *B, const float *C, const float *D,
+                              const float *x0, const float *u, const float *g_xsol, const float *g_ysol,
+                              float *g_A, float *g_B, float *g_C, float *g_D, float *g_x0, float *g_u,
+                              int64_t N, int64_t T, int n, int m, int p, float dt, uint32_t flags,
+                              int64_t chunk_len, void *ws, size_t ws_bytes, void *stream);
+
 /* ---- General fx/fy block SSM (dynax/core/base_block_state_space.py:62-63,72-73) with MLP dynamics,
  *      BASELINE.json config 5.  The reference has only the dispatch for this form (its example
  *      examples/4-neural-ode.py does not run), so the model is the restated

@@ -114,3 +114,23 @@ def test_forward_time_parallel(T, ops, n, m, p, N, Tn, chunks):
     xs, ys, _ = ops.lti_forward(*(cu(T, v) for v in (A1, B1, C1, D1, x0, u[:, :1])), dt, time_chunks=chunks)
     xr, yr = orc.lti_rollout(A1, B1, C1, D1, x0, u[:, :1], dt, np.float64)
     assert rel_err(xs.cpu().numpy(), xr, floor=1.0) < 1e-5 and rel_err(ys.cpu().numpy(), yr, floor=1.0) < 1e-5
+
+
+@pytest.mark.parametrize("n,m,p,N,Tn,chunks,shared", [(4, 3, 4, 1, 1500, -1, False), (3, 5, 1, 130, 600, 7, False),
+                                                      (2, 2, 2, 33, 257, 4, True), (4, 4, 4, 8, 640, -1, True),
+                                                      (1, 1, 1, 5, 300, 3, False)])
+def test_vjp_time_parallel(T, ops, n, m, p, N, Tn, chunks, shared):
+    """Time-parallel (chunked) dense-LTI VJP vs the fp64 hand adjoint and the serial kernel."""
+    dt = 0.02
+    A, B, C, D, x0, u = make(N, Tn, n, m, p, 48, L=1 if shared else None)
+    rng = np.random.default_rng(49)
+    gx = rng.normal(size=(Tn, N, n)).astype(np.float32)
+    gy = rng.normal(size=(Tn, N, p)).astype(np.float32)
+    a = [cu(T, v) for v in (A, B, C, D, x0, u)]
+    out = ops.lti_vjp(*a, dt, cu(T, gx), cu(T, gy), time_chunks=chunks)
+    ser = ops.lti_vjp(*a, dt, cu(T, gx), cu(T, gy), time_chunks=0)
+    r = orc.lti_vjp(A, B, C, D, x0, u, dt, gx, gy, np.float64)
+    for got, s_, key in zip(out, ser, ("gA", "gB", "gC", "gD", "gx0", "gu")):
+        ref = r[key].sum(0, keepdims=True) if (shared and key in ("gA", "gB", "gC", "gD")) else r[key]
+        assert rel_err(got.cpu().numpy().reshape(ref.shape), ref, floor=1.0) < 1e-4, key
+        assert rel_err(got.cpu().numpy(), s_.cpu().numpy(), floor=1.0) < 1e-4, key
