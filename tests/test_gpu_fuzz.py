@@ -169,6 +169,14 @@ def test_lti_shapes(k):
     for got, key in zip(out, ("gA", "gB", "gC", "gD", "gx0", "gu")):
         ref = r[key].sum(0, keepdims=True) if (shared and key in ("gA", "gB", "gC", "gD")) else r[key]
         assert rel_err(got.cpu().numpy().reshape(ref.shape), ref, floor=1.0) < 1e-4, (key, n, m, p, N, Tn, shared)
+    # the time-parallel variants with forced chunk counts
+    for chunks in (2, Tn):
+        xs, ys, _ = ops.lti_forward(*(cu(T, v) for v in (A, B, C, D, x0, u)), dt, time_chunks=chunks)
+        assert rel_err(xs.cpu().numpy(), xr, floor=1.0) < 1e-5 and rel_err(ys.cpu().numpy(), yr, floor=1.0) < 1e-5
+        out = ops.lti_vjp(*(cu(T, v) for v in (A, B, C, D, x0, u)), dt, cu(T, gx), cu(T, gy), time_chunks=chunks)
+        for got, key in zip(out, ("gA", "gB", "gC", "gD", "gx0", "gu")):
+            ref = r[key].sum(0, keepdims=True) if (shared and key in ("gA", "gB", "gC", "gD")) else r[key]
+            assert rel_err(got.cpu().numpy().reshape(ref.shape), ref, floor=1.0) < 1e-4, (key, n, m, p, N, Tn, shared, chunks)
 
 
 @pytest.mark.parametrize("N,Tn,euler", [(1, 1, False), (5, 9, False), (127, 2, True), (129, 9, False), (260, 5, False),
