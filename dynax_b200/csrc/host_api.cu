@@ -80,8 +80,13 @@ int64_t pick_tile(int64_t N, int64_t T, int64_t tile_systems, int bytes_per_syst
 // strided [T, nt, w] block out of a [T, N, w] host array (or back)
 int copy_tile(float *dst, size_t dpitch_f, const float *src, size_t spitch_f, int64_t nt, int w, int64_t T,
               cudaMemcpyKind kind, cudaStream_t st) {
-    DYNAX_CUDA_TRY(cudaMemcpy2DAsync(dst, dpitch_f * sizeof(float), src, spitch_f * sizeof(float),
-                                     (size_t)nt * w * sizeof(float), (size_t)T, kind, st));
+    const size_t width = (size_t)nt * w;
+    if (dpitch_f == width && spitch_f == width) {  // the tile is the whole system axis: one contiguous block, not T rows
+        DYNAX_CUDA_TRY(cudaMemcpyAsync(dst, src, width * (size_t)T * sizeof(float), kind, st));
+        return DYNAX_OK;
+    }
+    DYNAX_CUDA_TRY(cudaMemcpy2DAsync(dst, dpitch_f * sizeof(float), src, spitch_f * sizeof(float), width * sizeof(float),
+                                     (size_t)T, kind, st));
     return DYNAX_OK;
 }
 
@@ -138,7 +143,15 @@ int dynax_rc_forward_host_f32(const float *theta, const float *x0, const float *
             if (su) DYNAX_CUDA_TRY(cudaMemcpyAsync(d_u, u, sizeof(float) * 5 * T, cudaMemcpyHostToDevice, st));
             else TRY(copy_tile(d_u, (size_t)cur * 5, u + n0 * 5, (size_t)N * 5, cur, 5, T, cudaMemcpyHostToDevice, st));
         }
-        TRY(dynax_rc_forward_f32(d_th, d_x0, d_u, d_xs, d_ys, d_xf, cur, T, dt, flags, st));
+        // tiles that cannot fill the GPU with systems alone take the time-parallel kernels (break-evens of ops.py)
+        if (!(flags & DYNAX_DISCRETE) && cur <= 8192 && T >= 256) {
+            void *d_ws;
+            const size_t wsb = dynax_rc_forward_chunked_workspace(cur, T, 0);
+            TRY(reserve(c.slots[b][6], wsb, &d_ws));
+            TRY(dynax_rc_forward_chunked_f32(d_th, d_x0, d_u, d_xs, d_ys, d_xf, cur, T, dt, flags, 0, d_ws, wsb, st));
+        } else {
+            TRY(dynax_rc_forward_f32(d_th, d_x0, d_u, d_xs, d_ys, d_xf, cur, T, dt, flags, st));
+        }
         if (T > 0 && xsol)
             TRY(copy_tile(xsol + n0 * 3, (size_t)N * 3, d_xs, (size_t)cur * 3, cur, 3, T, cudaMemcpyDeviceToHost, st));
         if (T > 0 && ysol)
@@ -180,7 +193,10 @@ static int loss_grad_host_impl(const float *theta, const float *x0, const float 
             DYNAX_CUDA_TRY(cudaEventSynchronize(c.done[b]));
             float *d_th, *d_x0, *d_u, *d_tg, *d_out, *d_bounds = nullptr, *d_ctrl = nullptr;
             void *d_ws;
-            const size_t ws_bytes = dynax_workspace_bytes(DYNAX_OP_RC_LOSS_GRAD, cur, T, 3, 5, 1, flags);
+            // tiles that cannot fill the GPU with systems alone take the time-parallel kernels (break-evens of ops.py)
+            const bool chunked = !ctrl && !(flags & DYNAX_DISCRETE) && cur <= 4096 && T >= 512;
+            const size_t ws_bytes = chunked ? dynax_rc_loss_grad_chunked_workspace(cur, T, 0)
+                                            : dynax_workspace_bytes(DYNAX_OP_RC_LOSS_GRAD, cur, T, 3, 5, 1, flags);
             TRY(reserve(c.slots[b][0], sizeof(float) * 7 * (sth ? 1 : cur), (void **)&d_th));
             TRY(reserve(c.slots[b][1], sizeof(float) * 3 * cur, (void **)&d_x0));
             TRY(reserve(c.slots[b][2], sizeof(float) * 5 * (size_t)T * (su ? 1 : cur) + 16, (void **)&d_u));
@@ -206,6 +222,9 @@ static int loss_grad_host_impl(const float *theta, const float *x0, const float 
                 TRY(dynax_rc_loss_grad_ctrl_f32(d_th, d_x0, d_u, d_ctrl, ctrl_col, d_tg, d_bounds,
                                                 d_bounds ? d_bounds + 8 : nullptr, d_loss, d_g, nullptr, cur, T, dt,
                                                 flags, d_ws, ws_bytes, st));
+            } else if (chunked) {
+                TRY(dynax_rc_loss_grad_chunked_f32(d_th, d_x0, d_u, d_tg, d_bounds, d_bounds ? d_bounds + 8 : nullptr, d_loss,
+                                                   d_g, nullptr, cur, T, dt, flags, 0, d_ws, ws_bytes, st));
             } else {
                 TRY(dynax_rc_loss_grad_f32(d_th, d_x0, d_u, d_tg, d_bounds, d_bounds ? d_bounds + 8 : nullptr, d_loss,
                                            d_g, nullptr, cur, T, dt, flags, d_ws, ws_bytes, st));
