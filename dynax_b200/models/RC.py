@@ -18,6 +18,9 @@ PARAM_NAMES = ("Cai", "Cwe", "Cwi", "Re", "Ri", "Rw", "Rg")
 
 def stack_theta(params, device=None):
     """Flax-style dict of 7 leaves -> theta[N,7] (or [1,7] when every leaf is a scalar)."""
+    if not any(isinstance(params[k], torch.Tensor) for k in PARAM_NAMES):
+        # plain Python / NumPy scalars (how the reference's examples pass a fitted model): ONE host-to-device copy
+        return torch.tensor([[float(params[k]) for k in PARAM_NAMES]], dtype=torch.float32).to(device or "cuda")
     leaves = []
     for k in PARAM_NAMES:
         v = params[k]
