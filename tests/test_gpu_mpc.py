@@ -65,3 +65,20 @@ def test_argmin_large_and_errors(T):
     assert rel_err(cost[idx].cpu().numpy(), ref, floor=1.0) < 1e-5
     with pytest.raises(ValueError):
         ops.rc_mpc_cost(cu(T, orc.RC_NOMINAL), cu(T, [20.0, 35.8, 26.0]), d[:5], u, *sched(T), 900.0)
+
+
+def test_crossed_comfort_band(T):
+    """Schedules with t_low > t_high (both violations positive at once) give relu(y - hi) + relu(lo - y), not the
+    larger of the two."""
+    from dynax_b200 import ops
+    rng = np.random.default_rng(93)
+    N, H = 3000, 50
+    d = np.stack([10 + 15 * rng.random(H), rng.random(H), 2 * rng.random(H), rng.random(H)], 1).astype(np.float32)
+    u = (-10 * rng.random((H, N))).astype(np.float32)
+    x0 = np.array([20.0, 35.8, 26.0], np.float32)
+    lo, hi = orc.RC_T_LOW.copy(), orc.RC_T_HIGH.copy()
+    lo[:] = 24.0; hi[:] = 21.0                          # crossed everywhere
+    cost, _, _ = ops.rc_mpc_cost(cu(T, orc.RC_NOMINAL), cu(T, x0), cu(T, d), cu(T, u), cu(T, orc.RC_PRICE), cu(T, lo),
+                                 cu(T, hi), 900.0)
+    ref = orc.mpc_cost(orc.RC_NOMINAL, x0, d, u, 900.0, t_low=lo, t_high=hi, dtype=np.float64)
+    assert rel_err(cost.cpu().numpy(), ref, floor=1.0) < 1e-5
