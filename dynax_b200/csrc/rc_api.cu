@@ -193,6 +193,9 @@ static int rc_adjoint(const float *theta, const float *x0, const float *u, const
             if (rc != DYNAX_OK) return rc;
             if ((N + 127) / 128 <= di.sm_count) return launch_adj<RCModel, 128, 16, 2, ADJ_VJP, false, false, 1>(P, st);
         }
+        // full cotangents in and g_u out (79 B per system-step): 12-step segments, 6.24 vs 6.00 TB/s; with g_ysol only
+        // (47 B) 8-step segments are faster (5.66 vs 4.99 TB/s)
+        if (g_xsol && g_u) return launch_adj<RCModel, 128, 12, 2, ADJ_VJP, false, false, 2>(P, st);
         return launch_adj<RCModel, 128, 8, 2, ADJ_VJP, false, false, 2>(P, st);
     } else {
         // shared-u stages are small (<= 17 KB): a 4-deep ring keeps the producer ahead of the consumers
