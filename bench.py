@@ -184,7 +184,7 @@ def reference_arm(a):
         "impl": "reference", "metric": "system-steps/s, fwd+grad RC rollout", "value": val, "unit": "system-steps/s",
         "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"rc_fwd_grad N={a.systems} T={a.T} dt=3600 per-system theta/u/target", "sample": sample},
+        "config": {"workload": f"rc_fwd_grad N={a.systems} T={a.T} dt=3600 per-system theta/u/target (per rank)", "sample": sample},
         "cpu_baseline": {"value": val, "unit": "system-steps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "system-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference is JAX/Flax (not installable here: no jax wheel, no network); this arm times the oracle's "
