@@ -61,7 +61,6 @@ int dynax_lti_forward_f32(const float *A, const float *B, const float *C, const 
         return fail(DYNAX_ERR_UNSUPPORTED_DIMS, "no dense-LTI kernel instantiated for (n,m,p)=(%d,%d,%d)", n, m, p);
     int rc = require_sm100();
     if (rc != DYNAX_OK) return rc;
-    if (N == 0) return DYNAX_OK;
     if (T == 0) {
         if (x_final) DYNAX_CUDA_TRY(cudaMemcpyAsync(x_final, x0, sizeof(float) * n * N, cudaMemcpyDeviceToDevice, st));
         return DYNAX_OK;
@@ -101,7 +100,6 @@ int dynax_lti_vjp_f32(const float *A, const float *B, const float *C, const floa
         return fail(DYNAX_ERR_UNSUPPORTED_DIMS, "no dense-LTI kernel instantiated for (n,m,p)=(%d,%d,%d)", n, m, p);
     int rc = require_sm100();
     if (rc != DYNAX_OK) return rc;
-    if (N == 0) return DYNAX_OK;
     const size_t need = adj_workspace_bytes(N, T, n);
     if (!ws || ws_bytes < need)
         return fail(DYNAX_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", need, ws ? ws_bytes : (size_t)0);

@@ -49,7 +49,6 @@ static int rc_forward(const float *theta, const float *x0, const float *u, float
         return fail(DYNAX_ERR_INVALID_ARGUMENT, "unsupported flags 0x%x for rc_forward", flags);
     int rc = require_sm100();
     if (rc != DYNAX_OK) return rc;
-    if (N == 0) return DYNAX_OK;
     if (T == 0) {  // empty scan: nothing to emit, final state is the initial state
         if (x_final) DYNAX_CUDA_TRY(cudaMemcpyAsync(x_final, x0, sizeof(float) * 3 * N, cudaMemcpyDeviceToDevice, st));
         return DYNAX_OK;
@@ -111,7 +110,6 @@ static int rc_adjoint(const float *theta, const float *x0, const float *u, const
         return fail(DYNAX_ERR_INVALID_ARGUMENT, "g_u is not available with DYNAX_SHARED_U (sum it on the caller side)");
     int rc = require_sm100();
     if (rc != DYNAX_OK) return rc;
-    if (N == 0) return DYNAX_OK;
     const size_t need = adj_workspace_bytes(N, T, 3);
     if (!ws || ws_bytes < need)
         return fail(DYNAX_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", need, ws ? ws_bytes : (size_t)0);
