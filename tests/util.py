@@ -13,7 +13,7 @@ _MARGINS = os.environ.get("DYNAX_TEST_MARGINS")   # print how much of each toler
 
 def _margin(name, frac):
     if _MARGINS:
-        print(f"[margin] {name}: {frac:.3f} of tolerance", flush=True)
+        print(f"[margin] {name}: {frac:.3f} of tolerance  ({os.environ.get('PYTEST_CURRENT_TEST', '')})", flush=True)
 
 
 def rel_err(a, ref, floor=1e-3):
