@@ -10,7 +10,7 @@ from __future__ import annotations
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_range", "allreduce_sum_", "sharded_shared_loss_grad", "box_penalty"]
+__all__ = ["shard_range", "allreduce_sum_", "sharded_shared_loss_grad", "sharded_argmin", "box_penalty"]
 
 
 def shard_range(N, rank, world):
@@ -56,3 +56,25 @@ def sharded_shared_loss_grad(local_fn, theta, lb=None, ub=None, group=None, devi
         loss = loss + pen.to(buf.dtype).to(buf.device)
         grad = grad + g.to(buf.dtype).to(buf.device)
     return loss, grad
+
+
+def sharded_argmin(local_min, local_argmin, offset, group=None):
+    """Best candidate over a candidate axis sharded across ranks (config 4).
+
+    ``local_min`` / ``local_argmin``: what ``ops.rc_mpc_cost`` returns for this rank's candidates
+    (0-d tensors); ``offset``: global index of the rank's first candidate (``shard_range(...)[0]``).
+    One all-gather of two 8-byte values per rank; ties go to the lowest global index, like ``argmin``
+    over the unsharded axis.  Returns (min_cost, global_index) as 0-d tensors, identical on every rank.
+    """
+    pair = torch.stack([local_min.reshape(()).to(torch.float64),
+                        (local_argmin.reshape(()) + int(offset)).to(torch.float64)])   # indices < 2^53 are exact
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        allp = [torch.empty_like(pair) for _ in range(dist.get_world_size(group))]
+        dist.all_gather(allp, pair, group=group)
+        allp = torch.stack(allp)
+    else:
+        allp = pair[None]
+    cost, idx = allp[:, 0], allp[:, 1]
+    best = cost.min()
+    winner = torch.where(cost == best, idx, torch.full_like(idx, float("inf"))).min()
+    return best.to(local_min.dtype), winner.to(torch.int64)

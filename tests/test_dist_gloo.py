@@ -80,3 +80,45 @@ def test_two_rank_shared_theta_allreduce():
     for r in range(world):
         assert np.isclose(ret[r][0], want_l, rtol=1e-12)
         assert np.allclose(ret[r][1], want_g, rtol=1e-10)
+
+
+def _argmin_worker(rank, world, port, N, H, ret):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from dynax_b200.distributed import shard_range, sharded_argmin
+    cost = _mpc_costs(N, H)
+    lo, hi = shard_range(N, rank, world)
+    local = torch.tensor(cost[lo:hi])
+    best, idx = sharded_argmin(local.min(), local.argmin(), lo)
+    ret[rank] = (float(best), int(idx))
+    dist.destroy_process_group()
+
+
+def _mpc_costs(N, H):
+    from oracle import dynax_oracle as orc
+    rng = np.random.default_rng(9)
+    d = np.stack([rng.uniform(10, 30, H), rng.uniform(0, 2, H), rng.uniform(0, 2, H), rng.uniform(0, 2, H)], 1).astype(np.float32)
+    u = rng.uniform(-5, 0, (H, N)).astype(np.float32)
+    cost = np.asarray(orc.mpc_cost(orc.RC_NOMINAL, np.array([20, 30, 26], np.float32), d, u, 900.0), np.float32)
+    cost[1] = cost[N - 2] = cost.min() - 1  # the best cost twice, once per shard: the lower global index must win
+    return cost
+
+
+@pytest.mark.timeout(120)
+def test_two_rank_mpc_argmin():
+    """Config 4 on two ranks: every rank ends with the global best candidate (cost, index)."""
+    N, H, world = 13, 24, 2
+    cost = _mpc_costs(N, H)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_argmin_worker, args=(world, _free_port(), N, H, ret), nprocs=world, join=True)
+    for r in range(world):
+        assert ret[r] == (float(cost.min()), 1)
+
+
+def test_sharded_argmin_tie_goes_to_lowest_index():
+    from dynax_b200.distributed import sharded_argmin
+    best, idx = sharded_argmin(torch.tensor(1.5), torch.tensor(3), 10)
+    assert float(best) == 1.5 and int(idx) == 13
