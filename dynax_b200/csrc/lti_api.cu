@@ -1,6 +1,7 @@
 // C-ABI entry points for dense linear block SSMs (DiscreteLinearSSM / ContinuousLinearSSM,
 // /root/reference/dynax/core/{discrete,continuous}_block_state_space.py:5-54).
 // Kernels are instantiated for a fixed list of (n,m,p); dynax_lti_supported() reports it.
+#include <stdlib.h>
 #include <string.h>
 
 #include "launch.cuh"
@@ -23,6 +24,14 @@ static int lti_forward_t(const FwdParams<DenseModel<n, m, p>> &P, bool shared_u,
     return launch_fwd<M, 256, 4, 4, false, 1>(P, st);  // wide rows: 5 KB+ per bulk copy (see rc_api.cu)
 }
 
+template <class M>
+constexpr int dense_vjp_tn() {
+    constexpr size_t lim = 227 * 1024;
+    if (AdjCfg<M, 192, 8, 2, ADJ_VJP, false, false>::SMEM_BYTES <= lim) return 192;
+    if (AdjCfg<M, 160, 8, 2, ADJ_VJP, false, false>::SMEM_BYTES <= lim) return 160;
+    return 128;
+}
+
 template <int n, int m, int p>
 static int lti_vjp_t(const AdjParams<DenseModel<n, m, p>> &P, bool shared_u, cudaStream_t st) {
     using M = DenseModel<n, m, p>;
@@ -30,6 +39,17 @@ static int lti_vjp_t(const AdjParams<DenseModel<n, m, p>> &P, bool shared_u, cud
     // Mid-size models (17..40 accumulators, e.g. (3,5,1)): 64-system CTAs, three per SM -- 1.25 vs 1.83 ms on
     // N=113664 x T=1024.  Larger ones ((4,3,4): 56) would spill at the 168 registers that leaves: 128-system CTAs.
     if constexpr (M::NG > 16 && M::NG <= 40) return launch_adj<M, 64, 8, 2, ADJ_VJP, false, false, 3>(P, st);
+    // Large models ((4,3,4): 56 accumulators, ~250 registers) run one CTA per SM whatever the tile: the widest tile whose
+    // ring + fp64 totals still fit in shared memory gives the most warps per SM (192 systems: 1.88 vs 2.61 ms on
+    // N=113664 x T=1024).  Launches of at most one 128-system CTA per SM keep the narrow tile (more SMs busy).
+    if constexpr (M::NG > 40 && dense_vjp_tn<M>() > 128) {
+        DeviceInfo di;
+        const int rc = device_info(&di);
+        if (rc != DYNAX_OK) return rc;
+        const char *e = getenv("DYNAX_LTI_VJP_CFG");  // 0 forces the 128-system tile
+        if ((P.N + 127) / 128 > di.sm_count && !(e && atoi(e) == 0))
+            return launch_adj<M, dense_vjp_tn<M>(), 8, 2, ADJ_VJP, false, false, 1>(P, st);
+    }
     return launch_adj<M, 128, 8, 2, ADJ_VJP, false, false, 1>(P, st);
 }
 

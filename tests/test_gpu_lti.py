@@ -78,6 +78,35 @@ def test_vjp(T, ops, n, m, p, discrete):
         assert rel_err(got.cpu().numpy(), r[key], floor=1.0) < 1e-4, key
 
 
+@pytest.mark.parametrize("n,m,p,N", [(4, 3, 4, 19201), (4, 3, 4, 19392), (4, 4, 4, 19203), (4, 4, 4, 19360)])
+def test_vjp_wide_tile(T, ops, n, m, p, N, monkeypatch):
+    """Large dense models on launches of more than one 128-system CTA per SM take 192-/160-system tiles
+    (lti_api.cu): parity with the fp64 oracle, ragged and 16-byte-aligned N, and the same numbers as the
+    128-system tile (per-system outputs bit for bit: the per-thread arithmetic does not depend on the tile)."""
+    Tn, dt = 37, 0.05
+    A, B, C, D, x0, u = make(N, Tn, n, m, p, 48)
+    rng = np.random.default_rng(49)
+    gx = rng.normal(size=(Tn, N, n)).astype(np.float32)
+    gy = rng.normal(size=(Tn, N, p)).astype(np.float32)
+    a = [cu(T, v) for v in (A, B, C, D, x0, u)]
+    out = ops.lti_vjp(*a, dt, cu(T, gx), cu(T, gy), time_chunks=0)
+    r = orc.lti_vjp(A, B, C, D, x0, u, dt, gx, gy, np.float64)
+    for got, key in zip(out, ("gA", "gB", "gC", "gD", "gx0", "gu")):
+        assert rel_err(got.cpu().numpy(), r[key], floor=1.0) < 1e-4, key
+    monkeypatch.setenv("DYNAX_LTI_VJP_CFG", "0")
+    ref = ops.lti_vjp(*a, dt, cu(T, gx), cu(T, gy), time_chunks=0)
+    for got, want in zip(out, ref):
+        assert T.equal(got, want)
+    monkeypatch.delenv("DYNAX_LTI_VJP_CFG")
+    # one shared set of matrices: gradients summed over the systems (fp64 warp sums + atomics)
+    sh = [cu(T, v[:1]) for v in (A, B, C, D)] + a[4:]
+    A1, B1, C1, D1 = (np.repeat(v[:1], N, 0) for v in (A, B, C, D))
+    outs = ops.lti_vjp(*sh, dt, cu(T, gx), cu(T, gy), time_chunks=0)
+    rs = orc.lti_vjp(A1, B1, C1, D1, x0, u, dt, gx, gy, np.float64)
+    for got, key in zip(outs[:4], ("gA", "gB", "gC", "gD")):
+        assert rel_err(got.cpu().numpy()[0], rs[key].sum(0), floor=1.0) < 1e-4, key
+
+
 def test_vjp_shared_matrices_sums_over_systems(T, ops):
     N, Tn, dt = 256, 64, 0.05
     A, B, C, D, x0, u = make(N, Tn, 3, 3, 1, 45, L=1)
