@@ -12,6 +12,7 @@
 // folded into a per-step table in shared memory once per CTA.  HBM traffic is 4 B per
 // candidate-step (u) + 4/H (cost): the kernel sits at the FP32 issue roof, not the HBM roof.
 #include <float.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "api_common.cuh"
@@ -46,7 +47,27 @@ __device__ __forceinline__ unsigned int order_bits(float f) {
 constexpr int kMpcThreads = 256;
 constexpr int kMpcUnroll = 8;
 
+// V candidates per thread.  V=4: one 16-byte load per thread and step (4 KB contiguous per CTA row instead of 1 KB)
+// and one read of the step table per four candidates; needs N % 4 == 0 and 16-byte aligned u and cost.  Every candidate
+// sees the same arithmetic as with V=1 (bit-identical costs).
+template <int V>
+struct MpcVec;
+template <>
+struct MpcVec<1> {
+    using T = float;
+    __device__ static void get(const T &v, float *o) { o[0] = v; }
+    __device__ static T put(const float *o) { return o[0]; }
+};
+template <>
+struct MpcVec<4> {
+    using T = float4;
+    __device__ static void get(const T &v, float *o) { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+    __device__ static T put(const float *o) { return make_float4(o[0], o[1], o[2], o[3]); }
+};
+
+template <int V>
 __global__ void __launch_bounds__(kMpcThreads) rc_mpc_cost_kernel(const MpcParams P) {
+    using VT = typename MpcVec<V>::T;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     MpcStep *tab = reinterpret_cast<MpcStep *>(smem_raw);
     const int64_t H = P.H, N = P.N;
@@ -70,46 +91,61 @@ __global__ void __launch_bounds__(kMpcThreads) rc_mpc_cost_kernel(const MpcParam
     }
     __syncthreads();
 
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // first candidate of this thread; with V=4 the host guarantees N % 4 == 0, so a thread is all in or all out
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * V;
     const bool active = i < N;
-    const int64_t ii = active ? i : (N - 1);
-    float x[3] = {__ldg(P.x0), __ldg(P.x0 + 1), __ldg(P.x0 + 2)};
+    const int64_t ii = active ? i : (N - V);
+    float x[V][3], cost[V];
+#pragma unroll
+    for (int c = 0; c < V; ++c) {
+        x[c][0] = __ldg(P.x0); x[c][1] = __ldg(P.x0 + 1); x[c][2] = __ldg(P.x0 + 2);
+        cost[c] = 0.f;
+    }
     const float dt = P.dt, w1 = P.w_comfort;
-    float cost = 0.f;
     const float *up = P.u + ii;
-    // one candidate-step; `s` = this step's shared constants
-    auto step = [&](const MpcStep *s, float uk) {
+    // one step of this thread's candidates; `s` = this step's shared constants
+    auto step = [&](const MpcStep *s, const VT &uv) {
         const float4 a = *reinterpret_cast<const float4 *>(s);        // bd0 bd1 bd2 ce
         const float2 b = *reinterpret_cast<const float2 *>(&s->lo);   // lo hi
-        const float y = x[0];  // pre-update output (simulator.py:38)
-        const float dTz = fmaxf(y - b.y, 0.f) + fmaxf(b.x - y, 0.f);
-        cost = fmaf(a.w, uk, cost);   // energy: w0*price*(-u/COP)*dt/3600
-        cost = fmaf(w1, dTz, cost);
-        // rhs = A x + B u as single FMA chains seeded with the shared (B d_k) term: 8 FMAs instead of 11 ops
-        // (this kernel is bound by FP32 issue slots; the summation order differs from fxx(x)+fxu(u) by
-        // rounding only, far inside the 1e-5 tolerance)
-        const float r0 = fmaf(M.A02, x[2], fmaf(M.A00, x[0], fmaf(M.B02, uk, a.x)));
-        const float r1 = fmaf(M.A12, x[2], fmaf(M.A11, x[1], a.y));
-        const float r2 = fmaf(M.A22, x[2], fmaf(M.A21, x[1], fmaf(M.A20, x[0], a.z)));
-        x[0] = fmaf(dt, r0, x[0]);
-        x[1] = fmaf(dt, r1, x[1]);
-        x[2] = fmaf(dt, r2, x[2]);
+        float uk[V];
+        MpcVec<V>::get(uv, uk);
+#pragma unroll
+        for (int c = 0; c < V; ++c) {
+            float *xc = x[c];
+            const float y = xc[0];  // pre-update output (simulator.py:38)
+            const float dTz = fmaxf(y - b.y, 0.f) + fmaxf(b.x - y, 0.f);
+            cost[c] = fmaf(a.w, uk[c], cost[c]);   // energy: w0*price*(-u/COP)*dt/3600
+            cost[c] = fmaf(w1, dTz, cost[c]);
+            // rhs = A x + B u as single FMA chains seeded with the shared (B d_k) term: 8 FMAs instead of 11 ops
+            // (this kernel is bound by FP32 issue slots; the summation order differs from fxx(x)+fxu(u) by
+            // rounding only, far inside the 1e-5 tolerance)
+            const float r0 = fmaf(M.A02, xc[2], fmaf(M.A00, xc[0], fmaf(M.B02, uk[c], a.x)));
+            const float r1 = fmaf(M.A12, xc[2], fmaf(M.A11, xc[1], a.y));
+            const float r2 = fmaf(M.A22, xc[2], fmaf(M.A21, xc[1], fmaf(M.A20, xc[0], a.z)));
+            xc[0] = fmaf(dt, r0, xc[0]);
+            xc[1] = fmaf(dt, r1, xc[1]);
+            xc[2] = fmaf(dt, r2, xc[2]);
+        }
     };
     // full blocks of kMpcUnroll steps carry no per-step predicate (8 loads in flight, then 8 steps) ...
     const int64_t Hfull = H - (H % kMpcUnroll);
     for (int64_t k0 = 0; k0 < Hfull; k0 += kMpcUnroll) {
-        float uu[kMpcUnroll];
+        VT uu[kMpcUnroll];
 #pragma unroll
-        for (int j = 0; j < kMpcUnroll; ++j) uu[j] = __ldcs(up + (k0 + j) * N);
+        for (int j = 0; j < kMpcUnroll; ++j) uu[j] = __ldcs(reinterpret_cast<const VT *>(up + (k0 + j) * N));
 #pragma unroll
         for (int j = 0; j < kMpcUnroll; ++j) step(&tab[k0 + j], uu[j]);
     }
     // ... and the ragged tail goes step by step
-    for (int64_t k = Hfull; k < H; ++k) step(&tab[k], __ldcs(up + k * N));
-    if (active) P.cost[i] = cost;
+    for (int64_t k = Hfull; k < H; ++k) step(&tab[k], __ldcs(reinterpret_cast<const VT *>(up + k * N)));
+    if (active) *reinterpret_cast<VT *>(P.cost + i) = MpcVec<V>::put(cost);
     if (P.best != nullptr) {
-        unsigned long long key = active ? (((unsigned long long)order_bits(cost) << 32) | (unsigned long long)(uint32_t)i)
-                                        : ~0ull;
+        unsigned long long key = ~0ull;
+#pragma unroll
+        for (int c = 0; c < V; ++c) {
+            const unsigned long long kc = ((unsigned long long)order_bits(cost[c]) << 32) | (unsigned long long)(uint32_t)(i + c);
+            key = (active && kc < key) ? kc : key;
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
@@ -155,10 +191,25 @@ extern "C" int dynax_rc_mpc_cost_f32(const float *theta, const float *x0, const 
     P.cost = cost; P.best = want_min ? reinterpret_cast<unsigned long long *>(ws) : nullptr;
     P.N = N; P.H = H; P.dt = dt; P.cop = cop; P.w_energy = w_energy; P.w_comfort = w_comfort; P.start_time = start_time;
     if (want_min) DYNAX_CUDA_TRY(cudaMemsetAsync(ws, 0xff, 8, st));
-    rc = set_smem(rc_mpc_cost_kernel, smem);
+    // four candidates per thread when the layout allows 16-byte accesses and there are enough candidates to keep
+    // every SM busy with the wider CTAs (1024 candidates each); DYNAX_MPC_VEC=1 forces one candidate per thread
+    DeviceInfo di;
+    rc = device_info(&di);
     if (rc != DYNAX_OK) return rc;
-    const int64_t grid = (N + kMpcThreads - 1) / kMpcThreads;
-    rc_mpc_cost_kernel<<<(unsigned)grid, kMpcThreads, smem, st>>>(P);
+    const char *e = getenv("DYNAX_MPC_VEC");
+    const bool vec4 = (N % 4) == 0 && aligned16(u) && aligned16(cost) && N >= (int64_t)di.sm_count * 2 * 4 * kMpcThreads &&
+                      !(e && atoi(e) == 1);
+    if (vec4) {
+        rc = set_smem(rc_mpc_cost_kernel<4>, smem);
+        if (rc != DYNAX_OK) return rc;
+        const int64_t grid = (N / 4 + kMpcThreads - 1) / kMpcThreads;
+        rc_mpc_cost_kernel<4><<<(unsigned)grid, kMpcThreads, smem, st>>>(P);
+    } else {
+        rc = set_smem(rc_mpc_cost_kernel<1>, smem);
+        if (rc != DYNAX_OK) return rc;
+        const int64_t grid = (N + kMpcThreads - 1) / kMpcThreads;
+        rc_mpc_cost_kernel<1><<<(unsigned)grid, kMpcThreads, smem, st>>>(P);
+    }
     DYNAX_CUDA_TRY(cudaGetLastError());
     if (want_min) {
         rc_mpc_decode_kernel<<<1, 1, 0, st>>>(P.best, cost, argmin, min_cost);

@@ -82,3 +82,31 @@ def test_crossed_comfort_band(T):
                                  cu(T, hi), 900.0)
     ref = orc.mpc_cost(orc.RC_NOMINAL, x0, d, u, 900.0, t_low=lo, t_high=hi, dtype=np.float64)
     assert rel_err(cost.cpu().numpy(), ref, floor=1.0) < 1e-5
+
+
+def test_four_candidates_per_thread_matches_one(T, monkeypatch):
+    """Large, 16-byte-aligned candidate sets take the kernel with four candidates per thread (one float4 load per step,
+    mpc.cu): same arithmetic per candidate, so costs and argmin are bit-identical to the one-per-thread kernel; a
+    candidate count that is not a multiple of 4 falls back by itself."""
+    from dynax_b200 import ops
+    H = 29                                                     # 3 full blocks of 8 steps + a ragged tail
+    N = 148 * 2 * 4 * 256 + 4 * 77                             # above the switch, last CTA partly filled
+    g = T.Generator(device="cuda").manual_seed(5)
+    u = -10 * T.rand((H, N + 3), device="cuda", generator=g)
+    rng = np.random.default_rng(94)
+    d = cu(T, np.stack([10 + 15 * rng.random(H), rng.random(H), 2 * rng.random(H), rng.random(H)], 1))
+    args = (cu(T, orc.RC_NOMINAL), cu(T, [20.0, 35.8, 26.0]), d)
+    uv = u[:, :N].contiguous()
+    c4, a4, m4 = ops.rc_mpc_cost(*args, uv, *sched(T), 900.0, start_time=5 * 3600.0)
+    monkeypatch.setenv("DYNAX_MPC_VEC", "1")
+    c1, a1, m1 = ops.rc_mpc_cost(*args, uv, *sched(T), 900.0, start_time=5 * 3600.0)
+    monkeypatch.delenv("DYNAX_MPC_VEC")
+    assert T.equal(c4, c1) and a4.item() == a1.item() and m4.item() == m1.item()
+    assert a4.item() == int(T.argmin(c4).item())
+    idx = np.concatenate([np.random.default_rng(3).choice(N, 64, replace=False), [0, 1, 2, 3, N - 4, N - 3, N - 2, N - 1]])
+    ref = orc.mpc_cost(orc.RC_NOMINAL, [20.0, 35.8, 26.0], d.cpu().numpy(), uv[:, idx].cpu().numpy(), 900.0,
+                       start_time=5 * 3600.0, dtype=np.float64)
+    assert rel_err(c4[idx].cpu().numpy(), ref, floor=1.0) < 1e-5
+    ur = u[:, :N + 3].contiguous()                             # N % 4 == 3: one candidate per thread
+    cr, ar, _ = ops.rc_mpc_cost(*args, ur, *sched(T), 900.0, start_time=5 * 3600.0)
+    assert T.equal(cr[:N], c4) and ar.item() == int(T.argmin(cr).item())
