@@ -90,7 +90,11 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_fwd_kernel(const FwdPar
     float *const xsol_base = P.xsol ? P.xsol + t_begin * N * n : nullptr;
     float *const ysol_base = P.ysol ? P.ysol + t_begin * N * p : nullptr;
     const bool emit_x = P.xsol != nullptr, emit_y = P.ysol != nullptr;
-    const bool emit = emit_x || emit_y;
+    // outputs that TMA cannot move (N % 4 != 0 or unaligned bases) are stored by the computing threads themselves,
+    // straight from registers: no out-tile, no hand-shake with the producer warp (which would otherwise copy every row
+    // with its 32 lanes)
+    const bool emit = (emit_x || emit_y) && P.bulk_out;
+    const bool direct = (emit_x || emit_y) && !P.bulk_out;
     const int64_t C = (T + KF - 1) / KF;
 
     // per-system input rows that TMA cannot move (N % 4 != 0) go through 4-byte cp.async from all producer lanes:
@@ -174,31 +178,16 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_fwd_kernel(const FwdPar
             const int rows = (int)((T - k0) < KF ? (T - k0) : KF);
             const float *sx = s_xo + o * XO_STAGE;
             const float *sy = s_yo + o * YO_STAGE;
-            if (P.bulk_out) {
-                if (lane == 0) {
-                    for (int r = 0; r < rows; ++r) {
-                        if (emit_x)
-                            ptx::bulk_s2g(xsol_base + ((k0 + r) * N + n0) * n, sx + r * TN * n, (uint32_t)valid * n * 4u);
-                        if (emit_y)
-                            ptx::bulk_s2g(ysol_base + ((k0 + r) * N + n0) * p, sy + r * TN * p, (uint32_t)valid * p * 4u);
-                    }
-                    ptx::bulk_commit();
-                    ptx::bulk_wait_read<0>();  // out-tile may be overwritten once TMA has read it
-                    ptx::mbar_arrive(&ofree[o]);
-                }
-            } else {
+            if (lane == 0) {
                 for (int r = 0; r < rows; ++r) {
-                    if (emit_x) {
-                        float *dst = xsol_base + ((k0 + r) * N + n0) * n;
-                        for (int i = lane; i < valid * n; i += 32) dst[i] = sx[r * TN * n + i];
-                    }
-                    if (emit_y) {
-                        float *dst = ysol_base + ((k0 + r) * N + n0) * p;
-                        for (int i = lane; i < valid * p; i += 32) dst[i] = sy[r * TN * p + i];
-                    }
+                    if (emit_x)
+                        ptx::bulk_s2g(xsol_base + ((k0 + r) * N + n0) * n, sx + r * TN * n, (uint32_t)valid * n * 4u);
+                    if (emit_y)
+                        ptx::bulk_s2g(ysol_base + ((k0 + r) * N + n0) * p, sy + r * TN * p, (uint32_t)valid * p * 4u);
                 }
-                __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&ofree[o]);
+                ptx::bulk_commit();
+                ptx::bulk_wait_read<0>();  // out-tile may be overwritten once TMA has read it
+                ptx::mbar_arrive(&ofree[o]);
             }
         };
 
@@ -252,13 +241,27 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_fwd_kernel(const FwdPar
                 if (emit_y) {
                     float y[p];
                     M.out(x, u, y);  // y_k from the PRE-update state (simulator.py:38)
+                    if (direct) {
+                        if (active) {
 #pragma unroll
-                    for (int d = 0; d < p; ++d) yo[j * TN * p + d] = y[d];
+                            for (int d = 0; d < p; ++d) ysol_base[((k0 + j) * N + i) * p + d] = y[d];
+                        }
+                    } else {
+#pragma unroll
+                        for (int d = 0; d < p; ++d) yo[j * TN * p + d] = y[d];
+                    }
                 }
                 M.step(x, u, dt, discrete);  // explicit Euler x += dt*rhs (simulator.py:40) unless the model says otherwise
                 if (emit_x) {
+                    if (direct) {
+                        if (active) {
 #pragma unroll
-                    for (int d = 0; d < n; ++d) xo[j * TN * n + d] = x[d];  // x_{k+1} (simulator.py:43)
+                            for (int d = 0; d < n; ++d) xsol_base[((k0 + j) * N + i) * n + d] = x[d];
+                        }
+                    } else {
+#pragma unroll
+                        for (int d = 0; d < n; ++d) xo[j * TN * n + d] = x[d];  // x_{k+1} (simulator.py:43)
+                    }
                 }
             }
         }

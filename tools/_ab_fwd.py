@@ -1,0 +1,27 @@
+import os, sys, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from dynax_b200 import ops, _lib
+NOM = [10384.31640625, 499089.09375, 1321535.125, 1.5348844528198242, 0.5000327825546265, 1.000040054321289, 20.119935989379883]
+def t(fn, it=10):
+    for _ in range(3): fn()
+    torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(it):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return best
+libs = {"new": _lib.LIB_PATH, "old": os.path.join(os.path.dirname(_lib.LIB_PATH), "_old", "libdynax_old.so")}
+g = torch.Generator(device="cuda").manual_seed(0)
+for N, T, tc in ((1, 8760, -1), (1, 8760, 0), (129, 8760, -1), (1023, 8760, 0), (75777, 2000, 0), (151553, 2000, 0), (151552, 2000, 0), (16384, 8760, 0)):
+    th = torch.tensor(NOM, device="cuda")[None].repeat(N, 1)
+    x0 = torch.tensor([[20.0, 30.0, 26.0]], device="cuda").repeat(N, 1)
+    u = torch.rand((T, N, 5), device="cuda", generator=g)
+    for rep in range(2):
+        for name, path in libs.items():
+            _lib._LIB = None; _lib.LIB_PATH = path; _lib.lib()
+            a = t(lambda: ops.rc_forward(th, x0, u, 3600.0, time_chunks=tc))
+            b = t(lambda: ops.rc_forward(th, x0, u, 3600.0, emit_x=False, time_chunks=tc))
+            xs, ys, _ = ops.rc_forward(th, x0, u, 3600.0, time_chunks=tc)
+            print(f"N={N:6d} T={T} chunks={tc:2d} {name}: x+y {a:8.4f} ms | y only {b:8.4f} ms  chk {float(xs.double().sum()):.10e} {float(ys.double().sum()):.10e}", flush=True)
+    del u
