@@ -1,3 +1,5 @@
+"""Diagnostic (not collected by pytest): element-wise gradient error of the CUDA path and of the fp32 C oracle against the
+fp64 oracle, per case of tests/test_gpu_rc_grad.py.  Run on a GPU box: python tests/diag_grad.py"""
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

@@ -1,3 +1,9 @@
+"""A/B timing of the forward kernel between two builds of the library, same process, same inputs.
+
+    git stash; python -m dynax_b200.build; mkdir -p dynax_b200/_old; cp dynax_b200/libdynax_b200.so dynax_b200/_old/libdynax_old.so
+    git stash pop; python -m dynax_b200.build; gpurun -- python tools/_ab_fwd.py
+
+Prints ms for x+y and y-only per shape and the fp64 sums of both outputs (equal sums = same results)."""
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from dynax_b200 import ops, _lib

@@ -2,18 +2,21 @@
 import os, sys, time
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from dynax_b200 import ops
 from dynax_b200.estimators import calibrate
 from dynax_b200.models.RC import Continuous4R3C
 from dynax_b200.simulators.simulator import DifferentiableSimulator
-from oracle import dynax_oracle as orc
+from tools import _synth as orc
 
 T = 672                                       # the bundled four weeks of hourly data (examples/3-inverse.py)
 for N in (1, 1024, 65536):
     rng = np.random.default_rng(0)
     u = orc.synth_u(T, 1, 3)[:, 0]            # one measured building: shared series
     hidden = orc.synth_theta(1, 5)
-    _, y = orc.rc_rollout(hidden, orc.synth_x0(1, 3), u[:, None, :], 3600.0, np.float64)
-    target = y[:, 0, 0].astype(np.float32)
+    # the "measured" zone temperature: a rollout of the hidden building by the product path itself
+    _, y, _ = ops.rc_forward(torch.tensor(hidden).cuda(), torch.tensor(orc.synth_x0(1, 3)).cuda(),
+                             torch.tensor(u[:, None, :]).cuda(), 3600.0)
+    target = y[:, 0, 0].cpu().numpy()
     th0 = orc.synth_theta(N, 7)
     sim = DifferentiableSimulator(Continuous4R3C(), dt=3600.0)
     names = ["Cai", "Cwe", "Cwi", "Re", "Ri", "Rw", "Rg"]

@@ -3,7 +3,7 @@ import argparse, os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from dynax_b200 import ops
-from oracle import dynax_oracle as orc
+from tools import _synth as orc
 
 ap = argparse.ArgumentParser(); ap.add_argument("--N", type=int, default=148 * 128 * 2); ap.add_argument("--T", type=int, default=64)
 ap.add_argument("--impls", default="1,0")

@@ -4,7 +4,7 @@ import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from dynax_b200 import ops
-from oracle import dynax_oracle as orc
+from tools import _synth as orc
 
 c = lambda a: torch.tensor(np.ascontiguousarray(a, dtype=np.float32)).cuda()
 for N, T in ((132, 37), (131, 20)):      # TMA path with a ragged tail tile / plain-load path
