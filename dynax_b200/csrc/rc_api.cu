@@ -63,6 +63,7 @@ static int rc_forward(const float *theta, const float *x0, const float *u, float
     P.bulk_in = rows16 && aligned16(u) && (!ctrl || aligned16(ctrl));
     P.bulk_out = rows16 && (!xsol || aligned16(xsol)) && (!ysol || aligned16(ysol));
     if (env_int("DYNAX_NO_BULK", 0)) P.bulk_in = P.bulk_out = 0;
+    if (env_int("DYNAX_FWD_DIRECT", 0)) P.bulk_out = 0;  // tuning knob: per-thread stores even where TMA could move the rows
     if (ctrl) {
         if (!(flags & DYNAX_SHARED_U)) return fail(DYNAX_ERR_INVALID_ARGUMENT, "a control channel needs a shared input series");
         if (ctrl_col < 0 || ctrl_col >= 5) return fail(DYNAX_ERR_INVALID_ARGUMENT, "ctrl_col must be in [0,5)");
