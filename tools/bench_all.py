@@ -54,7 +54,7 @@ def main():
     u3 = torch.empty((T, N3, 5), device=dev).uniform_(0, 1, generator=g); u3[..., 0] = 15 + 10 * u3[..., 0]
     tg3 = 20 + 2 * torch.empty((T, N3), device=dev).uniform_(0, 1, generator=g)
     us, ts_ = u3[:, 0].contiguous(), tg3[:, 0].contiguous()
-    for algo, env, B, kern in (("tangent", "1", 24, "rc_fwdsens_kernel<256,8,2,2,packed>"),
+    for algo, env, B, kern in (("tangent", "1", 24, "rc_fwdsens_kernel<224,8,2,2,packed>"),
                                ("adjoint", "0", 48, "rollout_adj_kernel<RCModel,128,12|16,2,MSE>")):
         os.environ["DYNAX_GRAD_ALGO"] = env
         s = timeit(lambda: ops.rc_loss_grad(th[:N3], x0[:N3], u3, tg3, 3600.0), a.iters)
