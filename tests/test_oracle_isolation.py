@@ -1,0 +1,30 @@
+"""The oracle is test infrastructure: only tests/, __graft_entry__.smoke() and bench.py's CPU arm may use it."""
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PAT = re.compile(r"^\s*(from\s+oracle\b|import\s+oracle\b|from\s+\.+oracle\b)|libdynax_oracle", re.M)
+
+
+def _sources(*dirs):
+    for d in dirs:
+        for base, _, files in os.walk(os.path.join(ROOT, d)):
+            if "__pycache__" in base or os.sep + "_build" in base:
+                continue
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".cc", ".cpp")):
+                    yield os.path.join(base, f)
+
+
+def test_product_examples_and_tools_never_touch_the_oracle():
+    bad = [p for p in _sources("dynax_b200", "examples", "tools", "ffi", "include") if PAT.search(open(p).read())]
+    assert not bad, f"oracle used outside tests/bench/smoke: {bad}"
+
+
+def test_bench_uses_the_oracle_only_in_the_cpu_arm():
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    hits = [m.start() for m in re.finditer(r"from oracle import", src)]
+    assert hits, "bench.py's CPU arm is expected to time the oracle port"
+    for h in hits:  # every import sits inside the function that times the CPU port
+        fn = re.findall(r"^def (\w+)\(", src[:h], re.M)[-1]
+        assert "cpu" in fn or "reference" in fn, fn
