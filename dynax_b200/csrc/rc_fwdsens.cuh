@@ -204,9 +204,13 @@ __global__ void __launch_bounds__(TN + 32, MINB) rc_fwdsens_kernel(const FwdSens
         double *acc = reinterpret_cast<double *>(smem_raw + Cfg::ACC_OFF) + tid;
 #pragma unroll
         for (int j = 0; j < Cfg::NACC; ++j) acc[j * TN] = 0.0;
-        // GX0: three more columns, d x / d x0 (identity at k = 0, no forcing): (Rg, x0_0) share pair 3, (x0_1, x0_2) pair 4
-        constexpr int NP = GX0 ? 5 : 4;
+        // GX0: three more columns, d x / d x0 (identity at k = 0, no forcing): (Rg, x0_0) share pair 3, (x0_1, x0_2) pair 4.
+        // Without them the seventh column (Rg) has no partner: it travels as scalars (c0, c1, c2, gc) -- the same
+        // number of issue slots as a half-empty pair, but 8 plain FFMAs (either FMA pipe, half the arithmetic) in
+        // place of 8 FFMA2 on the heavy pipe, and four registers fewer.
+        constexpr int NP = GX0 ? 5 : 3;
         float2 s0[NP], s1[NP], s2[NP], gp[NP];
+        float c0 = 0.f, c1 = 0.f, c2 = 0.f, gc = 0.f;
 #pragma unroll
         for (int q = 0; q < NP; ++q) s0[q] = s1[q] = s2[q] = gp[q] = make_float2(0.f, 0.f);
         if constexpr (GX0) {
@@ -246,6 +250,7 @@ __global__ void __launch_bounds__(TN + 32, MINB) rc_fwdsens_kernel(const FwdSens
                     const float2 gy2 = make_float2(gy, gy);
 #pragma unroll
                     for (int q = 0; q < NP; ++q) gp[q] = __ffma2_rn(gy2, s0[q], gp[q]);
+                    if constexpr (!GX0) gc = fmaf(gy, c0, gc);
                     if constexpr (CHUNK) {
                         w0 = fmaf(gy, p0, w0); w1 = fmaf(gy, p1, w1); w2 = fmaf(gy, p2, w2);
                         const float q0 = fmaf(tA20, p2, fmaf(tA00, p0, p0));                     // p + dt A^T p
@@ -269,6 +274,12 @@ __global__ void __launch_bounds__(TN + 32, MINB) rc_fwdsens_kernel(const FwdSens
                         s1[q] = __ffma2_rn(pA12, a2, __ffma2_rn(pA11, a1, a1));
                         s2[q] = __ffma2_rn(pA22, a2, __ffma2_rn(pA21, a1, __ffma2_rn(pA20, a0, a2)));
                     }
+                    if constexpr (!GX0) {  // the same three expressions, one lane
+                        const float a0 = c0, a1 = c1, a2 = c2;
+                        c0 = fmaf(tA02, a2, fmaf(tA00, a0, a0));
+                        c1 = fmaf(tA12, a2, fmaf(tA11, a1, a1));
+                        c2 = fmaf(tA22, a2, fmaf(tA21, a1, fmaf(tA20, a0, a2)));
+                    }
                     s0[0].x = fmaf(tCai, R01.x, s0[0].x);      // d/dCai   (column 0)
                     s1[0].y = fmaf(tCwe, R01.y, s1[0].y);      // d/dCwe   (column 1)
                     s2[1].x = fmaf(tCwi, r2, s2[1].x);         // d/dCwi   (column 2)
@@ -276,7 +287,8 @@ __global__ void __launch_bounds__(TN + 32, MINB) rc_fwdsens_kernel(const FwdSens
                     s0[2].x = fmaf(tRi0, DX.x, s0[2].x);       // d/dRi    (column 4), row 0
                     s1[2].y = fmaf(tRw1, DX.y, s1[2].y);       // d/dRw    (column 5), row 1
                     s2[2] = __ffma2_rn(pR2, DX, s2[2]);        // d/dRi, d/dRw, row 2
-                    s0[3].x = fmaf(tRg, DU.x, s0[3].x);        // d/dRg    (column 6)
+                    if constexpr (GX0) s0[3].x = fmaf(tRg, DU.x, s0[3].x);   // d/dRg    (column 6)
+                    else c0 = fmaf(tRg, DU.x, c0);
                     X01 = __ffma2_rn(dt2, R01, X01);
                     x2 = fmaf(dt, r2, x2);
                 }
@@ -292,6 +304,10 @@ __global__ void __launch_bounds__(TN + 32, MINB) rc_fwdsens_kernel(const FwdSens
                     else if constexpr (GX0) acc[10 * TN] += (double)gp[q].y;   // x0_0 parks in slot 10 (7 holds sq)
                     gp[q] = make_float2(0.f, 0.f);
                 }
+                if constexpr (!GX0) {
+                    acc[6 * TN] += (double)gc;
+                    gc = 0.f;
+                }
                 acc[7 * TN] += (double)sq;
                 sq = 0.f;
             }
@@ -303,16 +319,17 @@ __global__ void __launch_bounds__(TN + 32, MINB) rc_fwdsens_kernel(const FwdSens
             if (active) {
                 const int64_t o = cidx * N + i;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
+                for (int q = 0; q < 3; ++q) {
                     P.s_end[o * 21 + 2 * q] = s0[q].x;
                     P.s_end[o * 21 + 7 + 2 * q] = s1[q].x;
                     P.s_end[o * 21 + 14 + 2 * q] = s2[q].x;
-                    if (q < 3) {
-                        P.s_end[o * 21 + 2 * q + 1] = s0[q].y;
-                        P.s_end[o * 21 + 7 + 2 * q + 1] = s1[q].y;
-                        P.s_end[o * 21 + 14 + 2 * q + 1] = s2[q].y;
-                    }
+                    P.s_end[o * 21 + 2 * q + 1] = s0[q].y;
+                    P.s_end[o * 21 + 7 + 2 * q + 1] = s1[q].y;
+                    P.s_end[o * 21 + 14 + 2 * q + 1] = s2[q].y;
                 }
+                P.s_end[o * 21 + 6] = c0;
+                P.s_end[o * 21 + 13] = c1;
+                P.s_end[o * 21 + 20] = c2;
 #pragma unroll
                 for (int j = 0; j < 7; ++j) P.g_loc[o * 8 + j] = gt[j];
                 P.g_loc[o * 8 + 7] = sqt;
