@@ -28,3 +28,19 @@ def test_bench_uses_the_oracle_only_in_the_cpu_arm():
     for h in hits:  # every import sits inside the function that times the CPU port
         fn = re.findall(r"^def (\w+)\(", src[:h], re.M)[-1]
         assert "cpu" in fn or "reference" in fn, fn
+
+
+def test_tools_synthetic_inputs_match_the_test_generators():
+    """tools/_synth.py restates the generators the parity tests use, so timings and tests see the same inputs."""
+    import sys
+
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    from oracle import dynax_oracle as orc
+    from tools import _synth as syn
+    assert np.array_equal(syn.synth_theta(9, 3), orc.synth_theta(9, 3))
+    assert np.array_equal(syn.synth_x0(9, 3), orc.synth_x0(9, 3))
+    assert np.array_equal(syn.synth_u(50, 6, 3), orc.synth_u(50, 6, 3))
+    assert all(np.array_equal(a, b) for a, b in zip(syn.synth_mlp(7), orc.synth_mlp(7)))
+    for name in ("RC_NOMINAL", "RC_LB", "RC_UB", "RC_PRICE", "RC_T_LOW", "RC_T_HIGH"):
+        assert np.array_equal(getattr(syn, name), getattr(orc, name)), name
