@@ -28,6 +28,10 @@ SIGNATURES = {
     "dynax_version": (_int, []),
     "dynax_last_error": (ctypes.c_char_p, []),
     "dynax_device_check": (_int, []),
+    "dynax_debug_kernel_count": (_int, []),
+    "dynax_debug_kernel_tag": (ctypes.c_char_p, [_int]),
+    "dynax_debug_kernel_launches": (ctypes.c_longlong, [_int]),
+    "dynax_debug_last_kernel": (ctypes.c_char_p, []),
     "dynax_workspace_bytes": (_sz, [_int, _i64, _i64, _int, _int, _int, _u32]),
     "dynax_lti_supported": (_int, [_int, _int, _int]),
     "dynax_rc_forward_f32": (_int, [_f] * 6 + [_i64, _i64, _flt, _u32, _f]),

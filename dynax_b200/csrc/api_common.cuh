@@ -44,6 +44,27 @@ struct DeviceInfo {
 };
 int device_info(DeviceInfo *out);
 
+// ---- launch registry (debug hook; tests/test_gpu_variants.py) -------------------------------------------------
+// Every call site that launches a rollout kernel carries DYNAX_NOTE_LAUNCH(): the enclosing (template) function
+// registers its signature -- template arguments included -- when the library is loaded, and counts its launches.
+// dynax_debug_kernel_count/_tag/_launches enumerate them, so a test can prove that every kernel variant the
+// library instantiates is selected (and checked against the oracle) by some test case.
+int registry_add(const char *tag);   // defined in rc_api.cu
+void registry_note(int id);
+template <class Here>
+struct LaunchTag {
+    static const int id;
+};
+template <class Here>
+const int LaunchTag<Here>::id = registry_add(Here::tag());
+#define DYNAX_NOTE_LAUNCH()                                                      \
+    do {                                                                         \
+        struct Here_ {                                                           \
+            static const char *tag() { return __PRETTY_FUNCTION__; }             \
+        };                                                                       \
+        ::dynax::registry_note(::dynax::LaunchTag<Here_>::id);                   \
+    } while (0)
+
 template <class Kernel>
 inline int set_smem(Kernel k, size_t bytes) {
     DYNAX_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));

@@ -20,6 +20,7 @@ template <class Model, int TN, int KF, int S, bool SHARED_U, int MINB>
 int launch_fwd(const FwdParams<Model> &P, cudaStream_t st) {
     using Cfg = FwdCfg<Model, TN, KF, S, SHARED_U>;
     auto kern = rollout_fwd_kernel<Model, TN, KF, S, SHARED_U, MINB>;
+    DYNAX_NOTE_LAUNCH();
     int rc = set_smem(kern, Cfg::SMEM_BYTES);
     if (rc != DYNAX_OK) return rc;
     const int64_t grid = (P.N + TN - 1) / TN;
@@ -36,6 +37,7 @@ int launch_adj(const AdjParams<Model> &P, cudaStream_t st) {
     using Cfg = AdjCfg<Model, TN, KC, S, MODE, SHARED_U, SHARED_TGT>;
     static_assert(KC >= kMinKC, "workspace sizing assumes KC >= kMinKC");
     auto kern = rollout_adj_kernel<Model, TN, KC, S, MODE, SHARED_U, SHARED_TGT, MINB>;
+    DYNAX_NOTE_LAUNCH();
     int rc = set_smem(kern, Cfg::SMEM_BYTES);
     if (rc != DYNAX_OK) return rc;
     const int64_t grid = (P.N + TN - 1) / TN;
@@ -58,15 +60,17 @@ int launch_adj(const AdjParams<Model> &P, cudaStream_t st) {
 }
 
 // Forward-mode (tangent) fused loss + gradient of the 4R3C model (rc_fwdsens.cuh).
-template <int TN, int KF, int S, int MINB, bool PACKED = false, bool SU = false, bool STG = false, bool CTRL = false,
+template <int TN, int KF, int S, int MINB, int SPLIT = 1, bool SU = false, bool STG = false, bool CTRL = false,
           bool GX0 = false, bool CHUNK = false>
 int launch_fwdsens(const FwdSensParams &P, cudaStream_t st) {
-    using Cfg = FwdSensCfg<TN, KF, S, SU, STG, CTRL, GX0>;
-    auto kern = rc_fwdsens_kernel<TN, KF, S, MINB, PACKED, SU, STG, CTRL, GX0, CHUNK>;
+    using Cfg = FwdSensCfg<TN, KF, S, SPLIT, SU, STG, CTRL, GX0>;
+    auto kern = rc_fwdsens_kernel<TN, KF, S, MINB, SPLIT, SU, STG, CTRL, GX0, CHUNK>;
+    DYNAX_NOTE_LAUNCH();
     int rc = set_smem(kern, Cfg::SMEM_BYTES);
     if (rc != DYNAX_OK) return rc;
     const int64_t grid = (P.N + TN - 1) / TN;
     if (grid > 0x7fffffffLL) return fail(DYNAX_ERR_INVALID_ARGUMENT, "N too large for one launch");
+    if (P.T > 0x7fffffffLL) return fail(DYNAX_ERR_INVALID_ARGUMENT, "T too large");
     if (P.shared_acc) DYNAX_CUDA_TRY(cudaMemsetAsync(P.shared_acc, 0, kAccBytes, st));
     if constexpr (CHUNK) {  // time-chunked launch: the caller (lti_chunked.cu) owns the stitch and the outputs
         const int64_t chunks = (P.T + P.chunk_len - 1) / P.chunk_len;

@@ -572,10 +572,10 @@ int dynax_rc_loss_grad_chunked_f32(const float *theta, const float *x0, const fl
             Q.N = N; Q.T = T; Q.dt = dt; Q.chunk_len = L;
             Q.bulk = (N % 4) == 0 && (su || aligned16(u)) && (stg || aligned16(target));
             Q.s_end = W.s_end; Q.g_loc = W.g_loc; Q.w_out = W.w;
-            if (su && stg) rc = launch_fwdsens<128, 8, 2, 4, true, true, true, false, false, true>(Q, st);
-            else if (su) rc = launch_fwdsens<128, 8, 2, 4, true, true, false, false, false, true>(Q, st);
-            else if (stg) rc = launch_fwdsens<128, 8, 2, 4, true, false, true, false, false, true>(Q, st);
-            else rc = launch_fwdsens<128, 8, 2, 4, true, false, false, false, false, true>(Q, st);
+            if (su && stg) rc = launch_fwdsens<128, 8, 2, 4, 1, true, true, false, false, true>(Q, st);
+            else if (su) rc = launch_fwdsens<128, 8, 2, 4, 1, true, false, false, false, true>(Q, st);
+            else if (stg) rc = launch_fwdsens<128, 8, 2, 4, 1, false, true, false, false, true>(Q, st);
+            else rc = launch_fwdsens<128, 8, 2, 4, 1, false, false, false, false, true>(Q, st);
             if (rc != DYNAX_OK) return rc;
             if (sth) DYNAX_CUDA_TRY(cudaMemsetAsync(W.shared_acc, 0, kAccBytes, st));
             const int64_t threads = 10 * ((N + 31) / 32 * 32);

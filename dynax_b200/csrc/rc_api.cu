@@ -3,6 +3,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
+#include <string>
+#include <vector>
+
 #include "launch.cuh"
 
 namespace dynax {
@@ -10,6 +14,35 @@ namespace dynax {
 char *last_error_buf() {
     static thread_local char buf[kErrBufLen] = {0};
     return buf;
+}
+
+// ---- launch registry (api_common.cuh) ----
+namespace {
+struct Registry {
+    std::mutex mu;
+    std::vector<std::string> tags;
+    std::vector<long long> launches;
+};
+Registry &registry() {
+    static Registry *r = new Registry;  // never destroyed: registrations run during static initialisation
+    return *r;
+}
+thread_local int last_launch_id = -1;
+}  // namespace
+
+int registry_add(const char *tag) {
+    Registry &r = registry();
+    std::lock_guard<std::mutex> lk(r.mu);
+    r.tags.emplace_back(tag);
+    r.launches.push_back(0);
+    return (int)r.tags.size() - 1;
+}
+
+void registry_note(int id) {
+    Registry &r = registry();
+    std::lock_guard<std::mutex> lk(r.mu);
+    r.launches[id] += 1;
+    last_launch_id = id;
 }
 
 int require_sm100() {
@@ -36,6 +69,15 @@ int device_info(DeviceInfo *out) {
 static int env_int(const char *name, int dflt) {
     const char *v = getenv(name);
     return v ? atoi(v) : dflt;
+}
+
+// The fused loss+gradient runs the forward-mode (tangent) kernel unless the caller steps a discrete model or the
+// environment holds DYNAX_GRAD_ALGO=0 (then, and for general cotangents: the checkpointed adjoint).
+static bool rc_uses_tangent(uint32_t flags) { return env_int("DYNAX_GRAD_ALGO", 1) == 1 && !(flags & DYNAX_DISCRETE); }
+
+static size_t rc_workspace_bytes(int op, int64_t N, int64_t T, uint32_t flags) {
+    if (op == DYNAX_OP_RC_LOSS_GRAD && rc_uses_tangent(flags)) return (flags & DYNAX_SHARED_THETA) ? kAccBytes : 0;
+    return adj_workspace_bytes(N, T, 3);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -72,7 +114,7 @@ static int rc_forward(const float *theta, const float *x0, const float *u, float
     }
     if (flags & DYNAX_SHARED_U) return launch_fwd<RCModel, 128, 4, 4, true, 4>(P, st);
     // Tile shapes measured on B200 (tools/tune.py, N=132608, T=8760): wide rows win because each
-    // cp.async.bulk then moves 5 KB.  0: 6.45 TB/s (x+y), 1: 5.43, 2: 5.31, 3: 5.80.
+    // cp.async.bulk then moves 5 KB: 256-system CTAs 6.45 TB/s (x+y), 128-system 5.43, 64-system 5.31.
     // Launches that leave at most one 256-system CTA per SM are bound by the per-chunk hand-shakes of the serial
     // chain, not by HBM: longer chunks amortise them -- 16 rows while one 128-system CTA per SM suffices (N=16384:
     // 1.18 ms; 8 rows 1.37, 4 rows 1.91), 8 rows up to one 256-system CTA per SM (N=32768: 1.65 vs 1.91 ms).
@@ -86,8 +128,6 @@ static int rc_forward(const float *theta, const float *x0, const float *u, float
     switch (cfg) {
         default:
         case 0: return launch_fwd<RCModel, 256, 4, 4, false, 1>(P, st);
-        case 1: return launch_fwd<RCModel, 128, 4, 4, false, 3>(P, st);
-        case 2: return launch_fwd<RCModel, 64, 4, 4, false, 6>(P, st);
         case 3: return launch_fwd<RCModel, 128, 8, 2, false, 3>(P, st);
         case 4: return launch_fwd<RCModel, 128, 16, 2, false, 2>(P, st);
     }
@@ -111,10 +151,12 @@ static int rc_adjoint(const float *theta, const float *x0, const float *u, const
         return fail(DYNAX_ERR_INVALID_ARGUMENT, "g_u is not available with DYNAX_SHARED_U (sum it on the caller side)");
     int rc = require_sm100();
     if (rc != DYNAX_OK) return rc;
-    const size_t need = adj_workspace_bytes(N, T, 3);
-    if (!ws || ws_bytes < need)
+    // the forward-mode kernel needs no scratch beyond the 1 KB of fp64 sums of a shared parameter vector; the
+    // checkpointed adjoint needs its checkpoints (rc_workspace_bytes is what dynax_workspace_bytes reports)
+    const size_t need = rc_workspace_bytes(MODE == ADJ_MSE ? DYNAX_OP_RC_LOSS_GRAD : DYNAX_OP_RC_VJP, N, T, flags);
+    if (need > 0 && (!ws || ws_bytes < need))
         return fail(DYNAX_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", need, ws ? ws_bytes : (size_t)0);
-    if (!aligned16(ws)) return fail(DYNAX_ERR_WORKSPACE, "workspace must be 16-byte aligned");
+    if (need > 0 && !aligned16(ws)) return fail(DYNAX_ERR_WORKSPACE, "workspace must be 16-byte aligned");
 
     AdjParams<RCModel> P;
     memset(&P, 0, sizeof(P));
@@ -124,7 +166,7 @@ static int rc_adjoint(const float *theta, const float *x0, const float *u, const
     P.x0 = x0; P.u = u; P.target = target; P.lb = lb; P.ub = ub; P.loss = loss;
     P.g_xsol = g_xsol; P.g_ysol = g_ysol; P.g_x0 = g_x0; P.g_u = g_u;
     P.shared_acc = reinterpret_cast<double *>(ws);
-    P.ckpt = reinterpret_cast<float *>(reinterpret_cast<char *>(ws) + kAccBytes);
+    P.ckpt = ws ? reinterpret_cast<float *>(reinterpret_cast<char *>(ws) + kAccBytes) : nullptr;
     P.N = N; P.T = T; P.dt = dt;
     P.discrete = (flags & DYNAX_DISCRETE) ? 1 : 0;
     P.shared_theta = (flags & DYNAX_SHARED_THETA) ? 1 : 0;
@@ -143,45 +185,53 @@ static int rc_adjoint(const float *theta, const float *x0, const float *u, const
     // 2.2-2.3e11 system-steps/s against 1.3-1.4e11 for the checkpointed adjoint below on the same box.
     // DYNAX_GRAD_ALGO=0 forces the adjoint; the adjoint also serves every case the tangent kernel does not cover
     // (discrete stepping, general cotangents).  d loss / d x0 rides along as three more sensitivity columns.
-    if (MODE == ADJ_MSE && env_int("DYNAX_GRAD_ALGO", 1) == 1 && !(flags & DYNAX_DISCRETE)) {
+    if (MODE == ADJ_MSE && rc_uses_tangent(flags)) {
         FwdSensParams F;
+        memset(&F, 0, sizeof(F));
         F.mp = P.mp; F.x0 = x0; F.u = u; F.target = target; F.lb = lb; F.ub = ub; F.loss = loss; F.g_theta = g_theta;
         F.ctrl = ctrl; F.ctrl_col = ctrl_col; F.g_x0 = g_x0;
         F.shared_acc = P.shared_theta ? P.shared_acc : nullptr;
         F.N = N; F.T = T; F.dt = dt;
         F.bulk = (N % 4) == 0 && (su || aligned16(u)) && (stg || aligned16(target)) && (!ctrl || aligned16(ctrl)) &&
                  !env_int("DYNAX_NO_BULK", 0);
-        // Tile width.  Every CTA runs the whole horizon, so a launch costs (waves x systems per CTA):
-        //   * up to sm_count x 128 systems: 128-system CTAs, one per SM, 16-row chunks -- each warp then has an SM
-        //     sub-partition to itself, and the serial chain of 8760 steps is what bounds the launch (N <= 16384:
-        //     0.88 ms; 8-row chunks 1.08, 256-system CTAs 1.37);
+        // Tile shape.  Every CTA runs the whole horizon, so a launch costs (waves x systems per CTA):
+        //   * launches that cannot fill the GPU with one thread per system give every system 4 (<= 2 x 32-system CTAs
+        //     per SM) or 2 (<= 2 x 64-system CTAs per SM) threads, each owning a subset of the sensitivity columns
+        //     (SPLIT, rc_fwdsens.cuh): the serial chain of 8760 steps per thread is what bounds such a launch;
+        //   * up to sm_count x 128 systems with a control channel or d loss / d x0: 128-system CTAs, 16-row chunks;
         //   * 224-system CTAs when they save a wave (N = 65536: 293 CTAs fill the 296 slots once, 256 CTAs of 256
         //     leave 40 SMs half empty);   * else 256-system CTAs, 2 per SM (5 KB per TMA row copy).
-        // DYNAX_FS_CFG: 1 = scalar (unpacked) 256-wide kernel, 2 = always 128-wide, 3 = always 256-wide.
+        // DYNAX_FS_CFG: 2 = always 128-wide, 3 = always 256-wide; DYNAX_FS_SPLIT: 1, 2 or 4 forces the threads per system.
         DeviceInfo di;
         rc = device_info(&di);
         if (rc != DYNAX_OK) return rc;
         const int64_t slots = 2 * (int64_t)di.sm_count;
         auto cost = [&](int64_t tn) { return ((N + tn - 1) / tn + slots - 1) / slots * tn; };
         const int cfg = env_int("DYNAX_FS_CFG", 0);
+        int split = env_int("DYNAX_FS_SPLIT", 0);
+        if (ctrl || g_x0) split = 1;
+        else if (split != 1 && split != 2 && split != 4) split = (cfg != 0) ? 1 : (N <= slots * 32) ? 4 : (N <= slots * 64) ? 2 : 1;
         int tn = 256;
         if (cfg == 2 || (cfg == 0 && (N + 127) / 128 <= di.sm_count)) tn = 128;
         else if (cfg == 0 && cost(224) < cost(256)) tn = 224;
         // (with g_x0: 11 fp64 totals per system in shared memory -> 128-system CTAs x3 or 224-system CTAs x2 per SM)
-#define DYNAX_FS_LAUNCH(SU, STG, CTRL)                                                             \
-    (g_x0 ? (tn == 128 ? launch_fwdsens<128, 16, 2, 2, true, SU, STG, CTRL, true>(F, st)             \
-                       : launch_fwdsens<224, 8, 2, 2, true, SU, STG, CTRL, true>(F, st))             \
-          : tn == 128 ? launch_fwdsens<128, 16, 2, 2, true, SU, STG, CTRL>(F, st)                    \
-                      : tn == 224 ? launch_fwdsens<224, 8, 2, 2, true, SU, STG, CTRL>(F, st)         \
-                                  : launch_fwdsens<256, 8, 2, 2, true, SU, STG, CTRL>(F, st))
+#define DYNAX_FS_LAUNCH(SU, STG, CTRL)                                                                \
+    (g_x0 ? (tn == 128 ? launch_fwdsens<128, 16, 2, 2, 1, SU, STG, CTRL, true>(F, st)                   \
+                       : launch_fwdsens<224, 8, 2, 2, 1, SU, STG, CTRL, true>(F, st))                   \
+          : tn == 128 ? launch_fwdsens<128, 16, 2, 2, 1, SU, STG, CTRL>(F, st)                          \
+                      : tn == 224 ? launch_fwdsens<224, 8, 2, 2, 1, SU, STG, CTRL>(F, st)               \
+                                  : launch_fwdsens<256, 8, 2, 2, 1, SU, STG, CTRL>(F, st))
+#define DYNAX_FS_LAUNCH_SPLIT(SU, STG)                                                                \
+    (split == 4 ? launch_fwdsens<32, 16, 3, 4, 4, SU, STG>(F, st)                                       \
+                : split == 2 ? launch_fwdsens<64, 16, 3, 4, 2, SU, STG>(F, st) : DYNAX_FS_LAUNCH(SU, STG, false))
         if (ctrl && stg) return DYNAX_FS_LAUNCH(true, true, true);
         if (ctrl) return DYNAX_FS_LAUNCH(true, false, true);
-        if (su && stg) return DYNAX_FS_LAUNCH(true, true, false);
-        if (su) return DYNAX_FS_LAUNCH(true, false, false);
-        if (stg) return DYNAX_FS_LAUNCH(false, true, false);
-        if (cfg == 1 && !g_x0) return launch_fwdsens<256, 8, 2, 2, false>(F, st);
-        return DYNAX_FS_LAUNCH(false, false, false);
+        if (su && stg) return DYNAX_FS_LAUNCH_SPLIT(true, true);
+        if (su) return DYNAX_FS_LAUNCH_SPLIT(true, false);
+        if (stg) return DYNAX_FS_LAUNCH_SPLIT(false, true);
+        return DYNAX_FS_LAUNCH_SPLIT(false, false);
 #undef DYNAX_FS_LAUNCH
+#undef DYNAX_FS_LAUNCH_SPLIT
     }
     if constexpr (MODE == ADJ_VJP) {
         if (su) return launch_adj<RCModel, 128, 8, 2, ADJ_VJP, true, false, 2>(P, st);
@@ -219,9 +269,6 @@ static int rc_adjoint(const float *theta, const float *x0, const float *u, const
             default:
             case 0: return launch_adj<RCModel, 128, 12, 2, ADJ_MSE, false, false, 3>(P, st);
             case 1: return launch_adj<RCModel, 128, 16, 2, ADJ_MSE, false, false, 2>(P, st);
-            case 2: return launch_adj<RCModel, 64, 16, 2, ADJ_MSE, false, false, 4>(P, st);
-            case 3: return launch_adj<RCModel, 128, 8, 4, ADJ_MSE, false, false, 2>(P, st);
-            case 4: return launch_adj<RCModel, 128, 8, 2, ADJ_MSE, false, false, 4>(P, st);
         }
     }
 }
@@ -238,11 +285,28 @@ const char *dynax_last_error(void) { return last_error_buf(); }
 
 int dynax_device_check(void) { return require_sm100(); }
 
+int dynax_debug_kernel_count(void) {
+    std::lock_guard<std::mutex> lk(registry().mu);
+    return (int)registry().tags.size();
+}
+
+const char *dynax_debug_kernel_tag(int i) {
+    std::lock_guard<std::mutex> lk(registry().mu);
+    return (i >= 0 && i < (int)registry().tags.size()) ? registry().tags[i].c_str() : "";
+}
+
+long long dynax_debug_kernel_launches(int i) {
+    std::lock_guard<std::mutex> lk(registry().mu);
+    return (i >= 0 && i < (int)registry().launches.size()) ? registry().launches[i] : -1;
+}
+
+const char *dynax_debug_last_kernel(void) { return dynax_debug_kernel_tag(last_launch_id); }
+
 size_t dynax_workspace_bytes(int op, int64_t N, int64_t T, int n, int m, int p, uint32_t flags) {
-    (void)m; (void)p; (void)flags;
+    (void)m; (void)p;
     switch (op) {
         case DYNAX_OP_RC_LOSS_GRAD:
-        case DYNAX_OP_RC_VJP: return adj_workspace_bytes(N, T, 3);
+        case DYNAX_OP_RC_VJP: return rc_workspace_bytes(op, N, T, flags);
         case DYNAX_OP_LTI_VJP: return adj_workspace_bytes(N, T, n);
         default: return 0;
     }

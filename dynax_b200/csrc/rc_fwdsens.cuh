@@ -8,7 +8,7 @@
 // This is mathematically the same gradient jax.value_and_grad returns (examples/3-inverse.py:96-112); it
 // reads u and target ONCE (24 B per system-step instead of the adjoint's 46 B, no checkpoints, no
 // workspace) at the price of ~90 FMAs per step, which moves the kernel from the HBM roof towards the FP32
-// issue / power roof -- hence the packed-fp32 (FFMA2) form below: 78 instead of 108 issue slots per step.
+// issue / power roof -- hence the packed-fp32 (FFMA2) form below.
 // Same thread-per-system / TMA-ring structure as the other rollout kernels.
 //
 // Writing rhs_i = (1/C_i) q_i with q0 = (u0-x0)/Rg + (x2-x0)/Ri + u1 + u2, q1 = (u0-x1)/Re + (x2-x1)/Rw + u3,
@@ -18,6 +18,19 @@
 //     d rhs0/dRi  = -(x2-x0)/(Cai Ri^2)        d rhs2/dRi = -(x0-x2)/(Cwi Ri^2)
 //     d rhs1/dRw  = -(x2-x1)/(Cwe Rw^2)        d rhs2/dRw = -(x1-x2)/(Cwi Rw^2)
 // Gradient sums: fp32 over kFsFoldSteps steps, then folded into fp64 totals (as in the adjoint kernel).
+//
+// Packed fp32 (FFMA2/FMUL2/FADD2, sm_100: two IEEE fp32 operations per issue slot):
+//   * the columns of S travel in pairs (Cai,Cwe) (Cwi,Re) (Ri,Rw); the seventh column (Rg) travels as scalars
+//     (GX0: (Rg, x0_0) (x0_1, x0_2) are two more pairs: d x / d x0, identity at k = 0, no forcing);
+//   * rows 0 and 1 of the rhs, the differences u0 - x, x2 - x and the update of (x0,x1) are pairs too.
+// Every lane performs the operations of RCModel::rhs in the same order (intrinsics), so x and the loss are
+// bit-identical to every other kernel that steps the model.
+//
+// SPLIT (threads per system): the sensitivity columns are independent of each other given x, so a launch with too
+// few systems to fill the GPU (BASELINE.json config 3 sharded over 8 GPUs: 8192 systems per rank) gives every system
+// SPLIT threads -- "roles", one warp-uniform role per warp -- that each step x redundantly (bit-identical) and own
+// a subset of the columns: the serial chain per thread drops from ~70 to ~35 instructions per step and four times
+// as many warps share the 8760-step critical path.  No cross-thread reduction: a role writes its own columns.
 #pragma once
 #include "models.cuh"
 #include "ptx.cuh"
@@ -46,9 +59,20 @@ struct FwdSensParams {
     float *w_out;   // [C,N,3]   sum_k gy_k ((I + dt A)^T)^(k-k0) e0: what the chunk's loss sees of S at its start
 };
 
+#ifndef DYNAX_FS_FENCE
+#define DYNAX_FS_FENCE 1
+#endif
+#ifndef DYNAX_FS_PACKF
+#define DYNAX_FS_PACKF 0
+#endif
+#ifndef DYNAX_FS_ORDER
+#define DYNAX_FS_ORDER 0
+#endif
+
 constexpr int kFsFoldSteps = 32;  // fp32 partial sums are folded into the fp64 totals every this many steps
 
-template <int TN, int KF, int S, bool SHARED_U = false, bool SHARED_TGT = false, bool CTRL = false, bool GX0 = false>
+template <int TN, int KF, int S, int SPLIT = 1, bool SHARED_U = false, bool SHARED_TGT = false, bool CTRL = false,
+          bool GX0 = false>
 struct FwdSensCfg {
     static constexpr int NACC = GX0 ? 11 : 8;  // fp64 totals per system: 7 gradient entries (+3 for x0) + squared residual
     // a shared series occupies KF rows of 5 (or 1) floats per stage instead of KF x TN of them
@@ -56,18 +80,340 @@ struct FwdSensCfg {
     static constexpr int U_STAGE = (KF * U_ROW + 3) / 4 * 4, T_STAGE = (KF * T_ROW + 3) / 4 * 4;
     static constexpr int C_STAGE = CTRL ? KF * TN : 0, STAGE = U_STAGE + T_STAGE + C_STAGE;
     static constexpr size_t RING_BYTES = sizeof(float) * (size_t)(S * STAGE) + sizeof(uint64_t) * 2 * S;
-    static constexpr size_t ACC_OFF = (RING_BYTES + 15) / 16 * 16;                 // fp64 totals [NACC][TN] (packed path)
+    static constexpr size_t ACC_OFF = (RING_BYTES + 15) / 16 * 16;                 // fp64 totals [NACC][TN]
     static constexpr size_t SMEM_BYTES = ACC_OFF + sizeof(double) * NACC * (size_t)TN;
-    static constexpr int THREADS = TN + 32;
+    static constexpr int CONSUMERS = TN * SPLIT, THREADS = CONSUMERS + 32;
 };
 
-template <int TN, int KF, int S, int MINB, bool PACKED = false, bool SHARED_U = false, bool SHARED_TGT = false,
+// which column pairs (bit q = pair q) and whether the scalar seventh column a role owns
+__host__ __device__ constexpr unsigned fs_pair_mask(int split, int role, bool gx0) {
+    return split == 1   ? (gx0 ? 0x1fu : 0x07u)
+           : split == 2 ? (role == 0 ? 0x03u : (gx0 ? 0x1cu : 0x04u))
+                        : (role < 3 ? (1u << role) : (gx0 ? 0x18u : 0u));
+}
+__host__ __device__ constexpr bool fs_has_c(int split, int role, bool gx0) { return !gx0 && role == split - 1; }
+
+template <int TN, int KF, int S, int SPLIT, int ROLE, bool SHARED_U, bool SHARED_TGT, bool CTRL, bool GX0, bool CHUNK>
+__device__ __forceinline__ void fs_consumer(const FwdSensParams &P, unsigned char *smem_raw, float *s_in, uint64_t *full,
+                                            uint64_t *empty, const int sys, const int64_t n0, const int valid,
+                                            const int64_t cidx, const int T, const int C) {
+    using Cfg = FwdSensCfg<TN, KF, S, SPLIT, SHARED_U, SHARED_TGT, CTRL, GX0>;
+    constexpr unsigned PM = fs_pair_mask(SPLIT, ROLE, GX0);
+    constexpr bool HAS_C = fs_has_c(SPLIT, ROLE, GX0);
+    constexpr bool LOSS_ROLE = ROLE == SPLIT - 1;   // squared residual, chunk weights, the loss output
+    constexpr int NP = GX0 ? 5 : 3;
+    constexpr bool NEED_DU = (PM & 0x2u) || (PM & 0x8u) || HAS_C, NEED_DX = (PM & 0x4u) != 0;
+    const int lane = threadIdx.x & 31;
+    const int64_t N = P.N;
+    const bool active = sys < valid;
+    const int64_t i = active ? (n0 + sys) : (N - 1);
+    RCModel M;
+    M.load(P.mp, i);
+    const float *th = P.mp.theta + i * P.mp.stride;
+    const float iCai = 1.0f / th[0], iCwe = 1.0f / th[1], iCwi = 1.0f / th[2];
+    const float iRe = 1.0f / th[3], iRi = 1.0f / th[4], iRw = 1.0f / th[5], iRg = 1.0f / th[6];
+    const float dt = P.dt;
+    // dt-scaled coefficients of the sensitivity recurrence
+    const float tA00 = dt * M.A00, tA02 = dt * M.A02, tA11 = dt * M.A11, tA12 = dt * M.A12, tA20 = dt * M.A20,
+                tA21 = dt * M.A21, tA22 = dt * M.A22;
+    const float tCai = -dt * iCai, tCwe = -dt * iCwe, tCwi = -dt * iCwi;
+    const float tRe = -dt * iCwe * iRe * iRe, tRg = -dt * iCai * iRg * iRg;
+    const float tRi0 = -dt * iCai * iRi * iRi, tRi2 = -dt * iCwi * iRi * iRi, tRw1 = -dt * iCwe * iRw * iRw,
+                tRw2 = -dt * iCwi * iRw * iRw;
+    const float *xs0 = P.x0 + (CHUNK ? cidx * P.x0_chunk_stride : 0) + i * 3;
+    float x2 = __ldg(xs0 + 2);
+    float2 X01 = make_float2(__ldg(xs0), __ldg(xs0 + 1));
+    float sq = 0.f;
+    const float c2T = 2.0f / (float)P.T;  // the mean runs over the WHOLE horizon, also in a chunked launch
+    const int ccol = CTRL ? P.ctrl_col : -1;
+    // fp64 totals live in shared memory ([j][sys]: conflict-free 8-byte accesses), touched once per kFsFoldSteps
+    // steps: registers the loop needs for its coefficients.  A role touches the slots of its own columns only.
+    double *acc = reinterpret_cast<double *>(smem_raw + Cfg::ACC_OFF) + sys;
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+        if (PM >> q & 1u) {
+            acc[(2 * q) * TN] = 0.0;
+            acc[(2 * q + 1 != 7 ? 2 * q + 1 : 10) * TN] = 0.0;   // x0_0 (column 7) parks in slot 10: 7 holds sq
+        }
+    }
+    if constexpr (HAS_C) acc[6 * TN] = 0.0;
+    if constexpr (LOSS_ROLE) acc[7 * TN] = 0.0;
+    float2 s0[NP], s1[NP], s2[NP], gp[NP];
+    float c0 = 0.f, c1 = 0.f, c2 = 0.f, gc = 0.f;
+#pragma unroll
+    for (int q = 0; q < NP; ++q) s0[q] = s1[q] = s2[q] = gp[q] = make_float2(0.f, 0.f);
+    if constexpr (GX0) {
+        s0[3].y = 1.f;
+        s1[4].x = 1.f;
+        s2[4].y = 1.f;
+    }
+    const float2 pA00 = make_float2(tA00, tA00), pA02 = make_float2(tA02, tA02), pA11 = make_float2(tA11, tA11),
+                 pA12 = make_float2(tA12, tA12), pA20 = make_float2(tA20, tA20), pA21 = make_float2(tA21, tA21),
+                 pA22 = make_float2(tA22, tA22);
+    const float2 rAd = make_float2(M.A00, M.A11), rAx2 = make_float2(M.A02, M.A12);   // rhs rows 0,1
+    const float2 rB0 = make_float2(M.B00, M.B10), rB1 = make_float2(M.B01, M.B13);
+    const float2 fCai = make_float2(tCai, 0.f), fCwe = make_float2(0.f, tCwe), fCwi = make_float2(tCwi, 0.f),
+                 fRe = make_float2(0.f, tRe), fRi0 = make_float2(tRi0, 0.f), fRw1 = make_float2(0.f, tRw1);
+    const float2 neg1 = make_float2(-1.f, -1.f), dt2 = make_float2(dt, dt), pR2 = make_float2(-tRi2, -tRw2);
+    // CHUNK: p_j = ((I + dt A)^T)^j e0 and w = sum_k gy_k p_(k-k0), so that the part of this chunk's gradient that
+    // comes from S at the chunk start is w^T S_start (added by the stitch over chunks)
+    float p0 = 1.f, p1 = 0.f, p2 = 0.f, w0 = 0.f, w1 = 0.f, w2 = 0.f;
+
+    const float *in = nullptr, *tg = nullptr;
+    auto step = [&](const int jj) {
+        float u0 = in[jj * Cfg::U_ROW], u1 = in[jj * Cfg::U_ROW + 1], u2 = in[jj * Cfg::U_ROW + 2],
+              u3 = in[jj * Cfg::U_ROW + 3], u4 = in[jj * Cfg::U_ROW + 4];
+        if constexpr (CTRL) {  // inputs assembled as in wrapper/envs/rc.py:128-131
+            const float cv = tg[Cfg::T_STAGE + (SHARED_TGT ? sys : 0) + jj * TN];
+            u0 = ccol == 0 ? cv : u0; u1 = ccol == 1 ? cv : u1; u2 = ccol == 2 ? cv : u2;
+            u3 = ccol == 3 ? cv : u3; u4 = ccol == 4 ? cv : u4;
+        }
+        const float res = X01.x - tg[jj * Cfg::T_ROW];   // PRE-update state (simulator.py:38)
+        if constexpr (LOSS_ROLE) sq = fmaf(res, res, sq);
+        const float gy = c2T * res;
+        const float2 gy2 = make_float2(gy, gy);
+#pragma unroll
+        for (int q = 0; q < NP; ++q)
+            if (PM >> q & 1u) gp[q] = __ffma2_rn(gy2, s0[q], gp[q]);
+        if constexpr (HAS_C) gc = fmaf(gy, c0, gc);
+        if constexpr (CHUNK && LOSS_ROLE) {
+            w0 = fmaf(gy, p0, w0); w1 = fmaf(gy, p1, w1); w2 = fmaf(gy, p2, w2);
+            const float q0 = fmaf(tA20, p2, fmaf(tA00, p0, p0));                     // p + dt A^T p
+            const float q1 = fmaf(tA21, p2, fmaf(tA11, p1, p1));
+            const float q2 = fmaf(tA22, p2, fmaf(tA12, p1, fmaf(tA02, p0, p2)));
+            p0 = q0; p1 = q1; p2 = q2;
+        }
+        // rhs = (A x) + (B u), rows 0 and 1 as a pair, row 2 scalar
+        const float2 U0 = make_float2(u0, u0), X2 = make_float2(x2, x2);
+        const float2 AX = __ffma2_rn(rAd, X01, __fmul2_rn(rAx2, X2));
+        float2 BU = __ffma2_rn(rB0, U0, __fmul2_rn(rB1, make_float2(u1, u3)));
+        BU.x = fmaf(M.B02, u2, BU.x);
+        const float2 R01 = __fadd2_rn(AX, BU);
+        const float r2 = __fadd_rn(fmaf(M.A22, x2, fmaf(M.A20, X01.x, __fmul_rn(M.A21, X01.y))), __fmul_rn(M.B24, u4));
+        float2 DU = make_float2(0.f, 0.f), DX = make_float2(0.f, 0.f);
+        if constexpr (NEED_DU) DU = __ffma2_rn(neg1, X01, U0);   // (u0 - x0, u0 - x1), exact as a subtraction
+        if constexpr (NEED_DX) DX = __ffma2_rn(neg1, X01, X2);   // (x2 - x0, x2 - x1)
+#if DYNAX_FS_ORDER == 1
+        // S <- S + dt A S, coefficient by coefficient: consecutive FFMA2s share their scalar operand, which the
+        // operand-reuse cache then serves (the loop is bound by register-file reads, not by issue slots)
+        float2 t0[NP], t1[NP], t2[NP];
+#pragma unroll
+        for (int q = 0; q < NP; ++q)
+            if (PM >> q & 1u) t0[q] = __ffma2_rn(pA00, s0[q], s0[q]);
+        const float d0 = fmaf(tA00, c0, c0);
+#pragma unroll
+        for (int q = 0; q < NP; ++q)
+            if (PM >> q & 1u) t1[q] = __ffma2_rn(pA11, s1[q], s1[q]);
+        const float d1 = fmaf(tA11, c1, c1);
+#pragma unroll
+        for (int q = 0; q < NP; ++q)
+            if (PM >> q & 1u) t2[q] = __ffma2_rn(pA20, s0[q], s2[q]);
+        float d2 = fmaf(tA20, c0, c2);
+#pragma unroll
+        for (int q = 0; q < NP; ++q)
+            if (PM >> q & 1u) t2[q] = __ffma2_rn(pA21, s1[q], t2[q]);
+        d2 = fmaf(tA21, c1, d2);
+#pragma unroll
+        for (int q = 0; q < NP; ++q)
+            if (PM >> q & 1u) s0[q] = __ffma2_rn(pA02, s2[q], t0[q]);
+        if constexpr (HAS_C) c0 = fmaf(tA02, c2, d0);
+#pragma unroll
+        for (int q = 0; q < NP; ++q)
+            if (PM >> q & 1u) s1[q] = __ffma2_rn(pA12, s2[q], t1[q]);
+        if constexpr (HAS_C) c1 = fmaf(tA12, c2, d1);
+#pragma unroll
+        for (int q = 0; q < NP; ++q)
+            if (PM >> q & 1u) s2[q] = __ffma2_rn(pA22, s2[q], t2[q]);
+        if constexpr (HAS_C) c2 = fmaf(tA22, c2, d2);
+#else
+        // S <- S + dt A S
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+            if (PM >> q & 1u) {
+                const float2 a0 = s0[q], a1 = s1[q], a2 = s2[q];
+                // (the diagonal term goes LAST: fma(c, a, a) reads one register pair through two operand slots, which
+                // ptxas resolves with a pair copy in straight-line code)
+                s0[q] = __ffma2_rn(pA00, a0, __ffma2_rn(pA02, a2, a0));
+                s1[q] = __ffma2_rn(pA11, a1, __ffma2_rn(pA12, a2, a1));
+                s2[q] = __ffma2_rn(pA22, a2, __ffma2_rn(pA21, a1, __ffma2_rn(pA20, a0, a2)));
+            }
+        }
+        if constexpr (HAS_C) {  // the same three expressions, one lane
+            const float a0 = c0, a1 = c1, a2 = c2;
+            c0 = fmaf(tA00, a0, fmaf(tA02, a2, a0));
+            c1 = fmaf(tA11, a1, fmaf(tA12, a2, a1));
+            c2 = fmaf(tA22, a2, fmaf(tA21, a1, fmaf(tA20, a0, a2)));
+        }
+#endif
+#if DYNAX_FS_PACKF
+        // direct partials as packed FMAs with a zero coefficient in the lane that is not forced (x + 0*y == x exactly
+        // for finite y): a scalar update of one half of a register pair costs ptxas a pair copy
+        if constexpr ((PM & 0x1u) != 0) {
+            s0[0] = __ffma2_rn(fCai, R01, s0[0]);      // d/dCai   (column 0), row 0
+            s1[0] = __ffma2_rn(fCwe, R01, s1[0]);      // d/dCwe   (column 1), row 1
+        }
+        if constexpr ((PM & 0x2u) != 0) {
+            s2[1] = __ffma2_rn(fCwi, make_float2(r2, r2), s2[1]);   // d/dCwi   (column 2), row 2
+            s1[1] = __ffma2_rn(fRe, DU, s1[1]);                     // d/dRe    (column 3), row 1
+        }
+        if constexpr ((PM & 0x4u) != 0) {
+            s0[2] = __ffma2_rn(fRi0, DX, s0[2]);       // d/dRi    (column 4), row 0
+            s1[2] = __ffma2_rn(fRw1, DX, s1[2]);       // d/dRw    (column 5), row 1
+            s2[2] = __ffma2_rn(pR2, DX, s2[2]);        // d/dRi, d/dRw, row 2
+        }
+#else
+        if constexpr ((PM & 0x1u) != 0) {
+            s0[0].x = fmaf(tCai, R01.x, s0[0].x);      // d/dCai   (column 0)
+            s1[0].y = fmaf(tCwe, R01.y, s1[0].y);      // d/dCwe   (column 1)
+        }
+        if constexpr ((PM & 0x2u) != 0) {
+            s2[1].x = fmaf(tCwi, r2, s2[1].x);         // d/dCwi   (column 2)
+            s1[1].y = fmaf(tRe, DU.y, s1[1].y);        // d/dRe    (column 3)
+        }
+        if constexpr ((PM & 0x4u) != 0) {
+            s0[2].x = fmaf(tRi0, DX.x, s0[2].x);       // d/dRi    (column 4), row 0
+            s1[2].y = fmaf(tRw1, DX.y, s1[2].y);       // d/dRw    (column 5), row 1
+            s2[2] = __ffma2_rn(pR2, DX, s2[2]);        // d/dRi, d/dRw, row 2
+        }
+#endif
+        if constexpr ((PM & 0x8u) != 0) s0[3].x = fmaf(tRg, DU.x, s0[3].x);   // d/dRg    (column 6)
+        if constexpr (HAS_C) c0 = fmaf(tRg, DU.x, c0);
+        X01 = __ffma2_rn(dt2, R01, X01);
+        x2 = fmaf(dt, r2, x2);
+    };
+
+    // Chunk 0 holds the ragged part of the horizon (r0 = T - (C-1) KF rows, 1..KF) and runs as a rolled loop; every
+    // other chunk is full and runs the unrolled body without per-row predicates.
+    const int r0 = T - (C - 1) * KF;
+    constexpr int FOLDC = kFsFoldSteps / KF > 0 ? kFsFoldSteps / KF : 1;
+    auto fold = [&]() {
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+            if (PM >> q & 1u) {
+                acc[(2 * q) * TN] += (double)gp[q].x;
+                acc[(2 * q + 1 != 7 ? 2 * q + 1 : 10) * TN] += (double)gp[q].y;
+                gp[q] = make_float2(0.f, 0.f);
+            }
+        }
+        if constexpr (HAS_C) {
+            acc[6 * TN] += (double)gc;
+            gc = 0.f;
+        }
+        if constexpr (LOSS_ROLE) {
+            acc[7 * TN] += (double)sq;
+            sq = 0.f;
+        }
+    };
+    {
+        ptx::mbar_wait(&full[0], 0u);
+        in = s_in + (SHARED_U ? 0 : sys * 5);
+        tg = s_in + Cfg::U_STAGE + (SHARED_TGT ? 0 : sys);
+#pragma unroll 1
+        for (int jj = 0; jj < r0; ++jj) step(jj);
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&empty[0]);
+    }
+    for (int c = 1; c < C; ++c) {
+        const int s = c % S;
+        ptx::mbar_wait(&full[s], (uint32_t)((c / S) & 1));
+        in = s_in + s * Cfg::STAGE + (SHARED_U ? 0 : sys * 5);
+        tg = s_in + s * Cfg::STAGE + Cfg::U_STAGE + (SHARED_TGT ? 0 : sys);
+#pragma unroll
+        for (int jj = 0; jj < KF; ++jj) {
+            step(jj);
+#if DYNAX_FS_FENCE
+            asm volatile("" ::: "memory");  // keeps the loads of step jj+1 behind step jj: short live ranges (96 registers)
+#endif
+        }
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&empty[s]);
+        if (c % FOLDC == 0) fold();
+    }
+    fold();
+
+    // ---- outputs: every role reports the columns it owns ----
+    // column j of the gradient lives in slot j (j < 7); x0 columns: x0_0 -> slot 10, x0_1 -> 8, x0_2 -> 9
+    constexpr unsigned COLS = (PM & 1u ? 0x03u : 0u) | (PM & 2u ? 0x0cu : 0u) | (PM & 4u ? 0x30u : 0u) |
+                              ((PM & 8u) || HAS_C ? 0x40u : 0u);
+    if constexpr (CHUNK) {  // local results of this chunk; the stitch kernel assembles loss and gradient
+        if (active) {
+            const int64_t o = cidx * N + i;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                if (PM >> q & 1u) {
+                    P.s_end[o * 21 + 2 * q] = s0[q].x;
+                    P.s_end[o * 21 + 7 + 2 * q] = s1[q].x;
+                    P.s_end[o * 21 + 14 + 2 * q] = s2[q].x;
+                    P.s_end[o * 21 + 2 * q + 1] = s0[q].y;
+                    P.s_end[o * 21 + 7 + 2 * q + 1] = s1[q].y;
+                    P.s_end[o * 21 + 14 + 2 * q + 1] = s2[q].y;
+                }
+            }
+            if constexpr (HAS_C) {
+                P.s_end[o * 21 + 6] = c0;
+                P.s_end[o * 21 + 13] = c1;
+                P.s_end[o * 21 + 20] = c2;
+            }
+#pragma unroll
+            for (int j = 0; j < 7; ++j)
+                if (COLS >> j & 1u) P.g_loc[o * 8 + j] = acc[j * TN];
+            if constexpr (LOSS_ROLE) {
+                P.g_loc[o * 8 + 7] = acc[7 * TN];
+                P.w_out[o * 3 + 0] = w0; P.w_out[o * 3 + 1] = w1; P.w_out[o * 3 + 2] = w2;
+            }
+        }
+        return;
+    }
+    if constexpr (GX0) {
+        if (active && P.g_x0 != nullptr) {
+            if constexpr ((PM & 0x8u) != 0) P.g_x0[i * 3 + 0] = (float)acc[10 * TN];
+            if constexpr ((PM & 0x10u) != 0) {
+                P.g_x0[i * 3 + 1] = (float)acc[8 * TN];
+                P.g_x0[i * 3 + 2] = (float)acc[9 * TN];
+            }
+        }
+    }
+    double loss = LOSS_ROLE ? acc[7 * TN] / (double)T : 0.0;
+    if (P.shared_acc != nullptr) {
+        // ONE parameter vector for all systems: sum the per-system gradients (warp shuffle in fp64 -> one atomic
+        // per warp and output); the penalty is added once by shared_finalize_kernel
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+            if (COLS >> j & 1u) {
+                const double v = warp_sum(active ? acc[j * TN] : 0.0);
+                if (lane == 0) atomicAdd(P.shared_acc + j, v);
+            }
+        }
+        if constexpr (LOSS_ROLE) {
+            const double v = warp_sum(active ? loss : 0.0);
+            if (lane == 0) atomicAdd(P.shared_acc + 7, v);
+        }
+        return;
+    }
+    if (!active) return;
+    const bool box = P.lb != nullptr && P.ub != nullptr;
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {  // 3-inverse.py:103-107, normaliser = ub
+        double g = (COLS >> j & 1u) ? acc[j * TN] : 0.0;
+        if (box) {
+            const double t = (double)th[j], lo = (double)P.lb[j], hi = (double)P.ub[j];
+            if (t > hi) { loss += (t - hi) / hi; g += 1.0 / hi; }
+            if (t < lo) { loss += (lo - t) / hi; g -= 1.0 / hi; }
+        }
+        if ((COLS >> j & 1u) && P.g_theta != nullptr) P.g_theta[i * 7 + j] = (float)g;
+    }
+    if constexpr (LOSS_ROLE)
+        if (P.loss != nullptr) P.loss[i] = (float)loss;
+}
+
+template <int TN, int KF, int S, int MINB, int SPLIT = 1, bool SHARED_U = false, bool SHARED_TGT = false,
           bool CTRL = false, bool GX0 = false, bool CHUNK = false>
-__global__ void __launch_bounds__(TN + 32, MINB) rc_fwdsens_kernel(const FwdSensParams P) {
-    static_assert(!CTRL || (SHARED_U && PACKED), "the control channel replaces a column of a SHARED input series");
-    static_assert(!GX0 || PACKED, "d loss / d x0 rides in the packed kernel");
-    static_assert(!CHUNK || (PACKED && !GX0 && !CTRL), "time-chunked launches use the plain packed kernel");
-    using Cfg = FwdSensCfg<TN, KF, S, SHARED_U, SHARED_TGT, CTRL, GX0>;
+__global__ void __launch_bounds__(TN * SPLIT + 32, MINB) rc_fwdsens_kernel(const FwdSensParams P) {
+    static_assert(!CTRL || SHARED_U, "the control channel replaces a column of a SHARED input series");
+    static_assert(!CHUNK || (!GX0 && !CTRL), "time-chunked launches use the plain kernel");
+    static_assert(SPLIT == 1 || SPLIT == 2 || SPLIT == 4, "1, 2 or 4 threads per system");
+    static_assert(TN % 32 == 0, "a warp holds one role");
+    using Cfg = FwdSensCfg<TN, KF, S, SPLIT, SHARED_U, SHARED_TGT, CTRL, GX0>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *s_in = reinterpret_cast<float *>(smem_raw);
     uint64_t *full = reinterpret_cast<uint64_t *>(s_in + S * Cfg::STAGE);
@@ -79,10 +425,10 @@ __global__ void __launch_bounds__(TN + 32, MINB) rc_fwdsens_kernel(const FwdSens
     // this CTA's slice of the time axis (the whole horizon unless the launch is time-chunked)
     const int64_t cidx = CHUNK ? (int64_t)blockIdx.y : 0;
     const int64_t t_begin = CHUNK ? cidx * P.chunk_len : 0;
-    const int64_t T = CHUNK ? ((P.T - t_begin) < P.chunk_len ? (P.T - t_begin) : P.chunk_len) : P.T;
+    const int T = (int)(CHUNK ? ((P.T - t_begin) < P.chunk_len ? (P.T - t_begin) : P.chunk_len) : P.T);
     const float *const u_base = P.u + t_begin * (SHARED_U ? 5 : N * 5);
     const float *const tgt_base = P.target + t_begin * (SHARED_TGT ? 1 : N);
-    const int64_t C = (T + KF - 1) / KF;
+    const int C = (T + KF - 1) / KF;
     // per-system rows that TMA cannot move (N % 4 != 0) go through 4-byte cp.async from all producer lanes: every
     // lane then arrives on the stage's barrier (count 32) instead of the one elected lane of the TMA path
     constexpr bool ANY_ROWS = !SHARED_U || !SHARED_TGT || CTRL;
@@ -91,19 +437,20 @@ __global__ void __launch_bounds__(TN + 32, MINB) rc_fwdsens_kernel(const FwdSens
 #pragma unroll
         for (int s = 0; s < S; ++s) {
             ptx::mbar_init(&full[s], async_rows ? 32 : 1);
-            ptx::mbar_init(&empty[s], TN / 32);
+            ptx::mbar_init(&empty[s], Cfg::CONSUMERS / 32);
         }
         ptx::fence_mbar_init();
     }
     __syncthreads();
 
-    if (tid >= TN) {  // ------------------------------- producer warp -------------------------------
-        const int lane = tid - TN;
+    if (tid >= Cfg::CONSUMERS) {  // ------------------------------- producer warp -------------------------------
+        const int lane = tid - Cfg::CONSUMERS;
         const uint64_t pol = ptx::policy_evict_first(), pol_keep = ptx::policy_evict_last();
-        auto load_chunk = [&](int64_t c) {
-            const int s = (int)(c % S);
-            const int64_t k0 = c * KF;
-            const int rows = (int)((T - k0) < KF ? (T - k0) : KF);
+        auto load_chunk = [&](int c) {
+            const int s = c % S;
+            const int r0 = T - (C - 1) * KF;  // chunk 0 holds the ragged part of the horizon (see the consumers)
+            const int64_t k0 = c == 0 ? 0 : r0 + (int64_t)(c - 1) * KF;
+            const int rows = c == 0 ? r0 : KF;
             float *du = s_in + s * Cfg::STAGE, *dtg = du + Cfg::U_STAGE;
             // Shared series: one bulk copy per block of rows when it is 16-byte aligned and sized (asynchronous, so the
             // producer does not pay an L2 round trip per chunk), else plain loads by the producer lanes.  Per-system
@@ -115,14 +462,14 @@ __global__ void __launch_bounds__(TN + 32, MINB) rc_fwdsens_kernel(const FwdSens
                 su_bulk = (reinterpret_cast<uintptr_t>(su) & 15) == 0 && ((rows * 20) & 15) == 0;
                 if (su_bulk) sh_tx += (uint32_t)rows * 20u;
                 else if (async_rows) ptx::copy_rows_async(du, 0, su, 0, 1, rows * 5, lane);
-                else for (int i = lane; i < rows * 5; i += 32) du[i] = __ldg(su + i);
+                else for (int e = lane; e < rows * 5; e += 32) du[e] = __ldg(su + e);
             }
             if constexpr (SHARED_TGT) {
                 const float *st = tgt_base + k0;
                 st_bulk = (reinterpret_cast<uintptr_t>(st) & 15) == 0 && ((rows * 4) & 15) == 0;
                 if (st_bulk) sh_tx += (uint32_t)rows * 4u;
                 else if (async_rows) ptx::copy_rows_async(dtg, 0, st, 0, 1, rows, lane);
-                else for (int i = lane; i < rows; i += 32) dtg[i] = __ldg(st + i);
+                else for (int e = lane; e < rows; e += 32) dtg[e] = __ldg(st + e);
             }
             float *dc = dtg + Cfg::T_STAGE;
             if (async_rows) {
@@ -156,292 +503,31 @@ __global__ void __launch_bounds__(TN + 32, MINB) rc_fwdsens_kernel(const FwdSens
                 }
             }
         };
-        for (int64_t c = 0; c < C && c < S; ++c) load_chunk(c);
-        for (int64_t c = 0; c + S < C; ++c) {
+        for (int c = 0; c < C && c < S; ++c) load_chunk(c);
+        for (int c = 0; c + S < C; ++c) {
             ptx::mbar_wait(&empty[c % S], (uint32_t)((c / S) & 1));
             load_chunk(c + S);
         }
         return;
     }
 
-    // --------------------------------- consumers ---------------------------------
-    const int lane = tid & 31;
-    const bool active = tid < valid;
-    const int64_t i = active ? (n0 + tid) : (N - 1);
-    RCModel M;
-    M.load(P.mp, i);
-    const float *th = P.mp.theta + i * P.mp.stride;
-    const float iCai = 1.0f / th[0], iCwe = 1.0f / th[1], iCwi = 1.0f / th[2];
-    const float iRe = 1.0f / th[3], iRi = 1.0f / th[4], iRw = 1.0f / th[5], iRg = 1.0f / th[6];
-    const float dt = P.dt;
-    // dt-scaled coefficients of the sensitivity recurrence
-    const float tA00 = dt * M.A00, tA02 = dt * M.A02, tA11 = dt * M.A11, tA12 = dt * M.A12, tA20 = dt * M.A20,
-                tA21 = dt * M.A21, tA22 = dt * M.A22;
-    const float tCai = -dt * iCai, tCwe = -dt * iCwe, tCwi = -dt * iCwi;
-    const float tRe = -dt * iCwe * iRe * iRe, tRg = -dt * iCai * iRg * iRg;
-    const float tRi0 = -dt * iCai * iRi * iRi, tRi2 = -dt * iCwi * iRi * iRi, tRw1 = -dt * iCwe * iRw * iRw,
-                tRw2 = -dt * iCwi * iRw * iRw;
-    const float *xs0 = P.x0 + (CHUNK ? cidx * P.x0_chunk_stride : 0) + i * 3;
-    float x0 = __ldg(xs0), x1 = __ldg(xs0 + 1), x2 = __ldg(xs0 + 2);
-    double gt[7], sqt = 0.0;
-    float sq = 0.f;
-#pragma unroll
-    for (int j = 0; j < 7; ++j) gt[j] = 0.0;
-    const float c2T = 2.0f / (float)P.T;  // the mean runs over the WHOLE horizon, also in a chunked launch
-
-    if constexpr (PACKED) {
-        // Packed-fp32 form (FFMA2/FMUL2/FADD2, sm_100: two IEEE fp32 operations per issue slot).
-        //   * the columns of S travel in pairs (Cai,Cwe) (Cwi,Re) (Ri,Rw) (Rg,0): the homogeneous part
-        //     S + dt A S and the gradient accumulation take 32 issue slots instead of 56;
-        //   * rows 0 and 1 of the rhs, the differences u0 - x, x2 - x and the update of (x0,x1) are pairs too.
-        // Every lane performs the operations of the scalar path in the same order (RCModel::rhs spells its order
-        // out with intrinsics), so x, the loss and S are bit-identical to it -- and x to every other kernel that
-        // steps the model; 78 instead of 108 instructions per step.
-        float2 X01 = make_float2(x0, x1);
-        const int ccol = CTRL ? P.ctrl_col : -1;
-        // fp64 totals live in shared memory ([j][tid]: conflict-free 8-byte accesses), touched once per
-        // kFsFoldSteps steps: 16 registers the loop needs for its coefficients
-        double *acc = reinterpret_cast<double *>(smem_raw + Cfg::ACC_OFF) + tid;
-#pragma unroll
-        for (int j = 0; j < Cfg::NACC; ++j) acc[j * TN] = 0.0;
-        // GX0: three more columns, d x / d x0 (identity at k = 0, no forcing): (Rg, x0_0) share pair 3, (x0_1, x0_2) pair 4.
-        // Without them the seventh column (Rg) has no partner: it travels as scalars (c0, c1, c2, gc) -- the same
-        // number of issue slots as a half-empty pair, but 8 plain FFMAs (either FMA pipe, half the arithmetic) in
-        // place of 8 FFMA2 on the heavy pipe, and four registers fewer.
-        constexpr int NP = GX0 ? 5 : 3;
-        float2 s0[NP], s1[NP], s2[NP], gp[NP];
-        float c0 = 0.f, c1 = 0.f, c2 = 0.f, gc = 0.f;
-#pragma unroll
-        for (int q = 0; q < NP; ++q) s0[q] = s1[q] = s2[q] = gp[q] = make_float2(0.f, 0.f);
-        if constexpr (GX0) {
-            s0[3].y = 1.f;
-            s1[4].x = 1.f;
-            s2[4].y = 1.f;
-        }
-        const float2 pA00 = make_float2(tA00, tA00), pA02 = make_float2(tA02, tA02), pA11 = make_float2(tA11, tA11),
-                     pA12 = make_float2(tA12, tA12), pA20 = make_float2(tA20, tA20), pA21 = make_float2(tA21, tA21),
-                     pA22 = make_float2(tA22, tA22);
-        const float2 rAd = make_float2(M.A00, M.A11), rAx2 = make_float2(M.A02, M.A12);   // rhs rows 0,1
-        const float2 rB0 = make_float2(M.B00, M.B10), rB1 = make_float2(M.B01, M.B13);
-        const float2 neg1 = make_float2(-1.f, -1.f), dt2 = make_float2(dt, dt), pR2 = make_float2(-tRi2, -tRw2);
-        // CHUNK: p_j = ((I + dt A)^T)^j e0 and w = sum_k gy_k p_(k-k0), so that the part of this chunk's gradient that
-        // comes from S at the chunk start is w^T S_start (added by the stitch over chunks)
-        float p0 = 1.f, p1 = 0.f, p2 = 0.f, w0 = 0.f, w1 = 0.f, w2 = 0.f;
-        for (int64_t c = 0; c < C; ++c) {
-            const int s = (int)(c % S);
-            const int64_t k0 = c * KF;
-            const int rows = (int)((T - k0) < KF ? (T - k0) : KF);
-            ptx::mbar_wait(&full[s], (uint32_t)((c / S) & 1));
-            const float *in = s_in + s * Cfg::STAGE + (SHARED_U ? 0 : tid * 5);
-            const float *tg = s_in + s * Cfg::STAGE + Cfg::U_STAGE + (SHARED_TGT ? 0 : tid);
-#pragma unroll
-            for (int jj = 0; jj < KF; ++jj) {
-                if (jj < rows) {
-                    float u0 = in[jj * Cfg::U_ROW], u1 = in[jj * Cfg::U_ROW + 1], u2 = in[jj * Cfg::U_ROW + 2],
-                          u3 = in[jj * Cfg::U_ROW + 3], u4 = in[jj * Cfg::U_ROW + 4];
-                    if constexpr (CTRL) {  // inputs assembled as in wrapper/envs/rc.py:128-131
-                        const float cv = tg[Cfg::T_STAGE + (SHARED_TGT ? tid : 0) + jj * TN];
-                        u0 = ccol == 0 ? cv : u0; u1 = ccol == 1 ? cv : u1; u2 = ccol == 2 ? cv : u2;
-                        u3 = ccol == 3 ? cv : u3; u4 = ccol == 4 ? cv : u4;
-                    }
-                    const float res = X01.x - tg[jj * Cfg::T_ROW];   // PRE-update state (simulator.py:38)
-                    sq = fmaf(res, res, sq);
-                    const float gy = c2T * res;
-                    const float2 gy2 = make_float2(gy, gy);
-#pragma unroll
-                    for (int q = 0; q < NP; ++q) gp[q] = __ffma2_rn(gy2, s0[q], gp[q]);
-                    if constexpr (!GX0) gc = fmaf(gy, c0, gc);
-                    if constexpr (CHUNK) {
-                        w0 = fmaf(gy, p0, w0); w1 = fmaf(gy, p1, w1); w2 = fmaf(gy, p2, w2);
-                        const float q0 = fmaf(tA20, p2, fmaf(tA00, p0, p0));                     // p + dt A^T p
-                        const float q1 = fmaf(tA21, p2, fmaf(tA11, p1, p1));
-                        const float q2 = fmaf(tA22, p2, fmaf(tA12, p1, fmaf(tA02, p0, p2)));
-                        p0 = q0; p1 = q1; p2 = q2;
-                    }
-                    // rhs = (A x) + (B u), rows 0 and 1 as a pair, row 2 scalar
-                    const float2 U0 = make_float2(u0, u0), X2 = make_float2(x2, x2);
-                    const float2 AX = __ffma2_rn(rAd, X01, __fmul2_rn(rAx2, X2));
-                    float2 BU = __ffma2_rn(rB0, U0, __fmul2_rn(rB1, make_float2(u1, u3)));
-                    BU.x = fmaf(M.B02, u2, BU.x);
-                    const float2 R01 = __fadd2_rn(AX, BU);
-                    const float r2 = __fadd_rn(fmaf(M.A22, x2, fmaf(M.A20, X01.x, __fmul_rn(M.A21, X01.y))), __fmul_rn(M.B24, u4));
-                    const float2 DU = __ffma2_rn(neg1, X01, U0);   // (u0 - x0, u0 - x1), exact as a subtraction
-                    const float2 DX = __ffma2_rn(neg1, X01, X2);   // (x2 - x0, x2 - x1)
-#pragma unroll
-                    for (int q = 0; q < NP; ++q) {
-                        const float2 a0 = s0[q], a1 = s1[q], a2 = s2[q];
-                        s0[q] = __ffma2_rn(pA02, a2, __ffma2_rn(pA00, a0, a0));
-                        s1[q] = __ffma2_rn(pA12, a2, __ffma2_rn(pA11, a1, a1));
-                        s2[q] = __ffma2_rn(pA22, a2, __ffma2_rn(pA21, a1, __ffma2_rn(pA20, a0, a2)));
-                    }
-                    if constexpr (!GX0) {  // the same three expressions, one lane
-                        const float a0 = c0, a1 = c1, a2 = c2;
-                        c0 = fmaf(tA02, a2, fmaf(tA00, a0, a0));
-                        c1 = fmaf(tA12, a2, fmaf(tA11, a1, a1));
-                        c2 = fmaf(tA22, a2, fmaf(tA21, a1, fmaf(tA20, a0, a2)));
-                    }
-                    s0[0].x = fmaf(tCai, R01.x, s0[0].x);      // d/dCai   (column 0)
-                    s1[0].y = fmaf(tCwe, R01.y, s1[0].y);      // d/dCwe   (column 1)
-                    s2[1].x = fmaf(tCwi, r2, s2[1].x);         // d/dCwi   (column 2)
-                    s1[1].y = fmaf(tRe, DU.y, s1[1].y);        // d/dRe    (column 3)
-                    s0[2].x = fmaf(tRi0, DX.x, s0[2].x);       // d/dRi    (column 4), row 0
-                    s1[2].y = fmaf(tRw1, DX.y, s1[2].y);       // d/dRw    (column 5), row 1
-                    s2[2] = __ffma2_rn(pR2, DX, s2[2]);        // d/dRi, d/dRw, row 2
-                    if constexpr (GX0) s0[3].x = fmaf(tRg, DU.x, s0[3].x);   // d/dRg    (column 6)
-                    else c0 = fmaf(tRg, DU.x, c0);
-                    X01 = __ffma2_rn(dt2, R01, X01);
-                    x2 = fmaf(dt, r2, x2);
-                }
-            }
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&empty[s]);
-            constexpr int FOLDC = kFsFoldSteps / KF > 0 ? kFsFoldSteps / KF : 1;
-            if ((c + 1) % FOLDC == 0 || c + 1 == C) {
-#pragma unroll
-                for (int q = 0; q < NP; ++q) {  // columns 2q, 2q+1; column 7 is the empty lane unless GX0 (then x0_0)
-                    acc[(2 * q) * TN] += (double)gp[q].x;
-                    if (2 * q + 1 != 7) acc[(2 * q + 1) * TN] += (double)gp[q].y;
-                    else if constexpr (GX0) acc[10 * TN] += (double)gp[q].y;   // x0_0 parks in slot 10 (7 holds sq)
-                    gp[q] = make_float2(0.f, 0.f);
-                }
-                if constexpr (!GX0) {
-                    acc[6 * TN] += (double)gc;
-                    gc = 0.f;
-                }
-                acc[7 * TN] += (double)sq;
-                sq = 0.f;
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < 7; ++j) gt[j] = acc[j * TN];
-        sqt = acc[7 * TN];
-        if constexpr (CHUNK) {  // local results of this chunk; the stitch kernel assembles loss and gradient
-            if (active) {
-                const int64_t o = cidx * N + i;
-#pragma unroll
-                for (int q = 0; q < 3; ++q) {
-                    P.s_end[o * 21 + 2 * q] = s0[q].x;
-                    P.s_end[o * 21 + 7 + 2 * q] = s1[q].x;
-                    P.s_end[o * 21 + 14 + 2 * q] = s2[q].x;
-                    P.s_end[o * 21 + 2 * q + 1] = s0[q].y;
-                    P.s_end[o * 21 + 7 + 2 * q + 1] = s1[q].y;
-                    P.s_end[o * 21 + 14 + 2 * q + 1] = s2[q].y;
-                }
-                P.s_end[o * 21 + 6] = c0;
-                P.s_end[o * 21 + 13] = c1;
-                P.s_end[o * 21 + 20] = c2;
-#pragma unroll
-                for (int j = 0; j < 7; ++j) P.g_loc[o * 8 + j] = gt[j];
-                P.g_loc[o * 8 + 7] = sqt;
-                P.w_out[o * 3 + 0] = w0; P.w_out[o * 3 + 1] = w1; P.w_out[o * 3 + 2] = w2;
-            }
-            return;
-        }
-        if constexpr (GX0) {  // slots 8, 9 = columns 8, 9 (x0_1, x0_2); slot 10 = x0_0
-            if (active && P.g_x0 != nullptr) {
-                P.g_x0[i * 3 + 0] = (float)acc[10 * TN];
-                P.g_x0[i * 3 + 1] = (float)acc[8 * TN];
-                P.g_x0[i * 3 + 2] = (float)acc[9 * TN];
-            }
-        }
+    // --------------------------------- consumers: role = warp-uniform ---------------------------------
+    const int role = SPLIT == 1 ? 0 : tid / TN, sys = SPLIT == 1 ? tid : tid % TN;
+#define DYNAX_FS_ROLE(R)                                                                                         \
+    fs_consumer<TN, KF, S, SPLIT, R, SHARED_U, SHARED_TGT, CTRL, GX0, CHUNK>(P, smem_raw, s_in, full, empty, sys, n0, \
+                                                                             valid, cidx, T, C)
+    if constexpr (SPLIT == 1) {
+        DYNAX_FS_ROLE(0);
+    } else if constexpr (SPLIT == 2) {
+        if (role == 0) DYNAX_FS_ROLE(0);
+        else DYNAX_FS_ROLE(1);
     } else {
-    float s0[7], s1[7], s2[7];  // rows of S = dx/dtheta
-    float gp[7];
-#pragma unroll
-    for (int j = 0; j < 7; ++j) {
-        s0[j] = s1[j] = s2[j] = 0.f;
-        gp[j] = 0.f;
+        if (role == 0) DYNAX_FS_ROLE(0);
+        else if (role == 1) DYNAX_FS_ROLE(1);
+        else if (role == 2) DYNAX_FS_ROLE(2);
+        else DYNAX_FS_ROLE(3);
     }
-
-    for (int64_t c = 0; c < C; ++c) {
-        const int s = (int)(c % S);
-        const int64_t k0 = c * KF;
-        const int rows = (int)((T - k0) < KF ? (T - k0) : KF);
-        ptx::mbar_wait(&full[s], (uint32_t)((c / S) & 1));
-        const float *in = s_in + s * Cfg::STAGE + (SHARED_U ? 0 : tid * 5);
-        const float *tg = s_in + s * Cfg::STAGE + Cfg::U_STAGE + (SHARED_TGT ? 0 : tid);
-        // (one predicated, fully unrolled loop: a separate unpredicated body for full chunks executes 3 % fewer
-        // instructions but makes ptxas spill at 96 registers and measured 3 % slower)
-#pragma unroll
-        for (int jj = 0; jj < KF; ++jj) {
-            if (jj < rows) {
-                const float u0 = in[jj * Cfg::U_ROW], u1 = in[jj * Cfg::U_ROW + 1], u2 = in[jj * Cfg::U_ROW + 2],
-                            u3 = in[jj * Cfg::U_ROW + 3], u4 = in[jj * Cfg::U_ROW + 4];
-                // loss and gradient use the PRE-update state (ysol[k] = x_k[0], simulator.py:38)
-                const float res = x0 - tg[jj * Cfg::T_ROW];
-                sq = fmaf(res, res, sq);
-                const float gy = c2T * res;
-#pragma unroll
-                for (int j = 0; j < 7; ++j) gp[j] = fmaf(gy, s0[j], gp[j]);
-                // rhs in the reference's order (fxx(x) + fxu(u))
-                float r[3];
-                {
-                    const float xx[3] = {x0, x1, x2}, uu[5] = {u0, u1, u2, u3, u4};
-                    M.rhs(xx, uu, r);
-                }
-                // S <- S + dt (A S + F) as FMA chains seeded with S: dt is folded into A's 7 non-zeros and into
-                // the 9 direct-partial coefficients (S still advances in residual form; I + dt A is never formed)
-                const float d_u0x0 = u0 - x0, d_u0x1 = u0 - x1, d_x2x0 = x2 - x0, d_x2x1 = x2 - x1;
-#pragma unroll
-                for (int j = 0; j < 7; ++j) {
-                    const float a0 = s0[j], a1 = s1[j], a2 = s2[j];
-                    s0[j] = fmaf(tA02, a2, fmaf(tA00, a0, a0));
-                    s1[j] = fmaf(tA12, a2, fmaf(tA11, a1, a1));
-                    s2[j] = fmaf(tA22, a2, fmaf(tA21, a1, fmaf(tA20, a0, a2)));
-                }
-                s0[0] = fmaf(tCai, r[0], s0[0]);         // d/dCai
-                s1[1] = fmaf(tCwe, r[1], s1[1]);         // d/dCwe
-                s2[2] = fmaf(tCwi, r[2], s2[2]);         // d/dCwi
-                s1[3] = fmaf(tRe, d_u0x1, s1[3]);        // d/dRe
-                s0[4] = fmaf(tRi0, d_x2x0, s0[4]);       // d/dRi
-                s2[4] = fmaf(-tRi2, d_x2x0, s2[4]);      //   (x0 - x2 = -(x2 - x0))
-                s1[5] = fmaf(tRw1, d_x2x1, s1[5]);       // d/dRw
-                s2[5] = fmaf(-tRw2, d_x2x1, s2[5]);      //   (x1 - x2 = -(x2 - x1))
-                s0[6] = fmaf(tRg, d_u0x0, s0[6]);        // d/dRg
-                x0 = fmaf(dt, r[0], x0);
-                x1 = fmaf(dt, r[1], x1);
-                x2 = fmaf(dt, r[2], x2);
-            }
-        }
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&empty[s]);
-        constexpr int FOLDC = kFsFoldSteps / KF > 0 ? kFsFoldSteps / KF : 1;  // chunks between folds
-        if ((c + 1) % FOLDC == 0 || c + 1 == C) {
-#pragma unroll
-            for (int j = 0; j < 7; ++j) {
-                gt[j] += (double)gp[j];
-                gp[j] = 0.f;
-            }
-            sqt += (double)sq;
-            sq = 0.f;
-        }
-    }
-    }
-    double loss = sqt / (double)T;
-    if (P.shared_acc != nullptr) {
-        // ONE parameter vector for all systems: sum the per-system gradients (warp shuffle in fp64 -> one atomic
-        // per warp and output); the penalty is added once by shared_finalize_kernel
-#pragma unroll
-        for (int j = 0; j < 7; ++j) {
-            const double v = warp_sum(active ? gt[j] : 0.0);
-            if (lane == 0) atomicAdd(P.shared_acc + j, v);
-        }
-        const double v = warp_sum(active ? loss : 0.0);
-        if (lane == 0) atomicAdd(P.shared_acc + 7, v);
-        return;
-    }
-    if (!active) return;
-    if (P.lb != nullptr && P.ub != nullptr) {
-#pragma unroll
-        for (int j = 0; j < 7; ++j) {  // 3-inverse.py:103-107, normaliser = ub
-            const double t = (double)th[j], lo = (double)P.lb[j], hi = (double)P.ub[j];
-            if (t > hi) { loss += (t - hi) / hi; gt[j] += 1.0 / hi; }
-            if (t < lo) { loss += (lo - t) / hi; gt[j] -= 1.0 / hi; }
-        }
-    }
-    P.loss[i] = (float)loss;
-#pragma unroll
-    for (int j = 0; j < 7; ++j) P.g_theta[i * 7 + j] = (float)gt[j];
+#undef DYNAX_FS_ROLE
 }
 
 }  // namespace dynax

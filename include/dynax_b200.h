@@ -64,6 +64,13 @@ int dynax_version(void);
 const char *dynax_last_error(void);
 /* 0 if the current CUDA device is compute capability 10.x, else DYNAX_ERR_NO_DEVICE. */
 int dynax_device_check(void);
+/* Debug hook for the variant-coverage tests (tests/test_gpu_variants.py): the library registers every rollout-kernel
+ * launch site it instantiates (template arguments included) when it is loaded and counts the launches of each, so a
+ * test can prove that the case it runs selected the kernel variant it means to check.  No reference counterpart. */
+int dynax_debug_kernel_count(void);
+const char *dynax_debug_kernel_tag(int i);        /* "" if i is out of range */
+long long dynax_debug_kernel_launches(int i);     /* launches of site i so far in this process; -1 if out of range */
+const char *dynax_debug_last_kernel(void);        /* tag of the calling thread's last launch ("" if none) */
 /* Bytes of device scratch `ws` the op needs (0 for forward ops). */
 size_t dynax_workspace_bytes(int op, int64_t N, int64_t T, int n, int m, int p, uint32_t flags);
 /* 1 if dense-LTI kernels are instantiated for (n,m,p), else 0. */

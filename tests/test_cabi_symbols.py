@@ -80,4 +80,9 @@ def test_no_device_fails_loudly(built):
     # argument validation happens before any device work
     assert L.dynax_rc_forward_f32(None, None, None, None, None, None, -1, 5, 1.0, 0, None) == -1
     assert L.dynax_lti_supported(4, 3, 4) == 1 and L.dynax_lti_supported(9, 9, 9) == 0
-    assert L.dynax_workspace_bytes(1, 1024, 8760, 3, 5, 1, 0) == 1024 + 4 * 1095 * 3 * 1024
+    # algorithm-aware: the default (forward-mode) loss+gradient needs no scratch, the checkpointed adjoint
+    # (general cotangents, or discrete stepping) 1 KB of fp64 sums + ceil(T/8) checkpoints of 3 floats per system
+    assert L.dynax_workspace_bytes(1, 1024, 8760, 3, 5, 1, 0) == 0
+    assert L.dynax_workspace_bytes(1, 1024, 8760, 3, 5, 1, _lib.SHARED_THETA) == 1024
+    assert L.dynax_workspace_bytes(2, 1024, 8760, 3, 5, 1, 0) == 1024 + 4 * 1095 * 3 * 1024
+    assert L.dynax_workspace_bytes(1, 1024, 8760, 3, 5, 1, _lib.DISCRETE) == 1024 + 4 * 1095 * 3 * 1024

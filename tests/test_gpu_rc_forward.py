@@ -112,7 +112,7 @@ def test_emit_flags_and_no_tma_path(T, ops, monkeypatch):
     assert T.equal(xs3, xs) and T.equal(ys3, ys)
 
 
-@pytest.mark.parametrize("cfg", ["0", "1", "2", "3"])
+@pytest.mark.parametrize("cfg", ["0", "3", "4"])
 def test_tile_configs_bit_identical(T, ops, monkeypatch, cfg):
     N, Tn = 1000, 203
     th, x0, u = orc.synth_theta(N, 25), orc.synth_x0(N, 25), orc.synth_u(Tn, N, 25)

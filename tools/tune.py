@@ -33,9 +33,9 @@ def main():
     ap.add_argument("--T", type=int, default=4380)
     ap.add_argument("--N", type=int, default=148 * 7 * 128)
     ap.add_argument("--what", default="fwd,tan,adj")
-    ap.add_argument("--fwd-cfgs", default="0,1,2,3")
-    ap.add_argument("--adj-cfgs", default="0,1,2,3,4")
-    ap.add_argument("--fs-cfgs", default="0,1,2")
+    ap.add_argument("--fwd-cfgs", default="0,3,4")
+    ap.add_argument("--adj-cfgs", default="0,1")
+    ap.add_argument("--fs-cfgs", default="0,2,3")
     a = ap.parse_args()
     N, T = a.N, a.T
     g = torch.Generator(device="cuda").manual_seed(0)
