@@ -10,7 +10,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdynax_b200.so")
+# DYNAX_B200_LIB: another build of the same library (A/B timing of kernel variants, tools/ab_tangent3.py)
+LIB_PATH = os.environ.get("DYNAX_B200_LIB") or os.path.join(_HERE, "libdynax_b200.so")
 
 # flags / ops (include/dynax_b200.h)
 SHARED_THETA, SHARED_U, SHARED_TARGET, DISCRETE, SOLVER_EULER = 1, 2, 4, 8, 16

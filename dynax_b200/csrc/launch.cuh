@@ -1,9 +1,12 @@
 // Kernel launch helpers shared by rc_api.cu and lti_api.cu.
 #pragma once
+#include <stdlib.h>
+
 #include "api_common.cuh"
 #include "rollout_adj.cuh"
 #include "rc_fwdsens.cuh"
 #include "rollout_fwd.cuh"
+#include "tmap.cuh"
 
 namespace dynax {
 
@@ -62,12 +65,27 @@ int launch_adj(const AdjParams<Model> &P, cudaStream_t st) {
 // Forward-mode (tangent) fused loss + gradient of the 4R3C model (rc_fwdsens.cuh).
 template <int TN, int KF, int S, int MINB, int SPLIT = 1, bool SU = false, bool STG = false, bool CTRL = false,
           bool GX0 = false, bool CHUNK = false>
-int launch_fwdsens(const FwdSensParams &P, cudaStream_t st) {
+int launch_fwdsens(const FwdSensParams &P0, cudaStream_t st) {
     using Cfg = FwdSensCfg<TN, KF, S, SPLIT, SU, STG, CTRL, GX0>;
     auto kern = rc_fwdsens_kernel<TN, KF, S, MINB, SPLIT, SU, STG, CTRL, GX0, CHUNK>;
     DYNAX_NOTE_LAUNCH();
     int rc = set_smem(kern, Cfg::SMEM_BYTES);
     if (rc != DYNAX_OK) return rc;
+    // Per-system rows through tensor maps (one copy per array and stage) whenever the layout allows it: rows that 1-D
+    // bulk copies can move (P0.bulk) and an inner extent of >= 32 floats dividing N*w and TN*w.  DYNAX_NO_TENSOR=1
+    // keeps the per-row copies (A/B timing, tests).
+    FwdSensParams P = P0;
+    P.tensor = 0;
+    if (P.bulk && (!SU || !STG || CTRL) && !getenv("DYNAX_NO_TENSOR")) {
+        const int iu = SU ? 1 : row_map_inner(P.N, 5, TN), it = (STG && !CTRL) ? 1 : row_map_inner(P.N, 1, TN);
+        if (iu > 0 && it > 0) {
+            if (!SU) rc = make_row_map(&P.map_u, P.u, P.N, 5, P.T, TN, KF, iu);
+            if (rc == DYNAX_OK && !STG) rc = make_row_map(&P.map_t, P.target, P.N, 1, P.T, TN, KF, it);
+            if (rc == DYNAX_OK && CTRL) rc = make_row_map(&P.map_c, P.ctrl, P.N, 1, P.T, TN, KF, it);
+            if (rc != DYNAX_OK) return rc;
+            P.tensor = 1; P.inner_u = iu; P.inner_t = it;
+        }
+    }
     const int64_t grid = (P.N + TN - 1) / TN;
     if (grid > 0x7fffffffLL) return fail(DYNAX_ERR_INVALID_ARGUMENT, "N too large for one launch");
     if (P.T > 0x7fffffffLL) return fail(DYNAX_ERR_INVALID_ARGUMENT, "T too large");

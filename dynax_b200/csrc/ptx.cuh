@@ -120,6 +120,16 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, u
         : "memory");
 }
 
+// global -> shared tensor copy through a 3-D tensor map (tmap.cuh): one box per call, completion (always the full
+// box in bytes) on an mbarrier.  dst 128-byte aligned; `map` must live in param/const space (__grid_constant__).
+__device__ __forceinline__ void tensor_g2s_3d(void *smem_dst, const void *map, int c0, int c1, int c2, uint64_t *bar,
+                                              uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+
 // shared -> global bulk copy (bulk async-group completion).
 __device__ __forceinline__ void bulk_s2g(void *gmem_dst, const void *smem_src, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst),

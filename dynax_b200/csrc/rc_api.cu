@@ -195,9 +195,10 @@ static int rc_adjoint(const float *theta, const float *x0, const float *u, const
         F.bulk = (N % 4) == 0 && (su || aligned16(u)) && (stg || aligned16(target)) && (!ctrl || aligned16(ctrl)) &&
                  !env_int("DYNAX_NO_BULK", 0);
         // Tile shape.  Every CTA runs the whole horizon, so a launch costs (waves x systems per CTA):
-        //   * launches that cannot fill the GPU with one thread per system give every system 4 (<= 2 x 32-system CTAs
-        //     per SM) or 2 (<= 2 x 64-system CTAs per SM) threads, each owning a subset of the sensitivity columns
-        //     (SPLIT, rc_fwdsens.cuh): the serial chain of 8760 steps per thread is what bounds such a launch;
+        //   * launches far too small to fill the GPU with one thread per system (N <= 32 systems per SM) give every
+        //     system 2 threads, each owning a subset of the sensitivity columns (SPLIT, rc_fwdsens.cuh; N = 4096,
+        //     T = 8760: 0.72 vs 0.84 ms); 4 threads per system (32-system CTAs) are instantiated but not selected:
+        //     their 640-byte rows cost as much per bulk copy as 2.5 KB ones, and the copies bound the launch;
         //   * up to sm_count x 128 systems with a control channel or d loss / d x0: 128-system CTAs, 16-row chunks;
         //   * 224-system CTAs when they save a wave (N = 65536: 293 CTAs fill the 296 slots once, 256 CTAs of 256
         //     leave 40 SMs half empty);   * else 256-system CTAs, 2 per SM (5 KB per TMA row copy).
@@ -210,7 +211,7 @@ static int rc_adjoint(const float *theta, const float *x0, const float *u, const
         const int cfg = env_int("DYNAX_FS_CFG", 0);
         int split = env_int("DYNAX_FS_SPLIT", 0);
         if (ctrl || g_x0) split = 1;
-        else if (split != 1 && split != 2 && split != 4) split = (cfg != 0) ? 1 : (N <= slots * 32) ? 4 : (N <= slots * 64) ? 2 : 1;
+        else if (split != 1 && split != 2 && split != 4) split = (cfg != 0) ? 1 : (N <= slots * 16) ? 2 : 1;
         int tn = 256;
         if (cfg == 2 || (cfg == 0 && (N + 127) / 128 <= di.sm_count)) tn = 128;
         else if (cfg == 0 && cost(224) < cost(256)) tn = 224;

@@ -110,11 +110,14 @@ def rc_forward(theta, x0, u, dt, emit_x=True, emit_y=True, emit_final=False, dis
     return xsol, ysol, xfin
 
 
-def rc_loss_grad(theta, x0, u, target, dt, lb=None, ub=None, want_gx0=False, discrete=False, time_chunks=None):
+def rc_loss_grad(theta, x0, u, target, dt, lb=None, ub=None, want_gx0=False, discrete=False, time_chunks=None,
+                 out=None):
     """Fused MSE(+box penalty) loss and its gradient (examples/3-inverse.py:96-112) for N candidates.
 
     theta[N,7] -> loss[N], grad[N,7];  theta[7] (shared) -> loss[1] (sum over systems), grad[7].
     target[T,N] or [T] (shared).  Returns (loss, grad, g_x0 or None).
+    ``out``: optional (loss, grad) float32 CUDA tensors to write into -- e.g. two views of ONE [8] buffer for a
+    shared parameter vector, so that the all-reduce over ranks (distributed.py) needs no packing kernel.
     ``time_chunks``: None = time-parallel chunked kernels only for small long launches (N <= 4096 and
     T >= 512 -- measured break-evens against the serial tangent kernel), 0 = never, k > 0 = k chunks.
     """
@@ -135,8 +138,16 @@ def rc_loss_grad(theta, x0, u, target, dt, lb=None, ub=None, want_gx0=False, dis
         lb = _f32c(torch.as_tensor(lb, dtype=torch.float32, device=dev), "lb").reshape(7)
         ub = _f32c(torch.as_tensor(ub, dtype=torch.float32, device=dev), "ub").reshape(7)
     nout = 1 if shared_th else N
-    loss = torch.empty((nout,), dtype=torch.float32, device=dev)
-    grad = torch.empty((nout, 7), dtype=torch.float32, device=dev)
+    if out is not None:
+        loss, grad = out
+        for t, nm, cnt in ((loss, "out[0]", nout), (grad, "out[1]", nout * 7)):
+            if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+                    and t.numel() == cnt):
+                raise ValueError(f"{nm} must be a contiguous float32 CUDA tensor of {cnt} elements")
+        grad = grad.view(nout, 7)
+    else:
+        loss = torch.empty((nout,), dtype=torch.float32, device=dev)
+        grad = torch.empty((nout, 7), dtype=torch.float32, device=dev)
     gx0 = torch.empty((N, 3), dtype=torch.float32, device=dev) if want_gx0 else None
     flags = ((SHARED_THETA if shared_th else 0) | (SHARED_U if shared_u else 0) |
              (SHARED_TARGET if shared_tg else 0) | (DISCRETE if discrete else 0))

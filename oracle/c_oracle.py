@@ -38,6 +38,9 @@ def lib(native=False):
     fp = ctypes.POINTER(ctypes.c_float)
     L.oracle_rc_forward_f32.argtypes = [fp] * 6 + [ctypes.c_long, ctypes.c_long, ctypes.c_float, ctypes.c_int, ctypes.c_int]
     L.oracle_rc_loss_grad_f32.argtypes = [fp] * 8 + [ctypes.c_long, ctypes.c_long, ctypes.c_float] + [ctypes.c_int] * 3
+    dp = ctypes.POINTER(ctypes.c_double)
+    L.oracle_rc_loss_grad_budget_f64.argtypes = [fp] * 4 + [dp] * 6 + [ctypes.c_long, ctypes.c_long, ctypes.c_double] + \
+        [ctypes.c_int] * 3 + [ctypes.c_double]
     L.oracle_num_threads.restype = ctypes.c_int
     L.oracle_set_num_threads.argtypes = [ctypes.c_int]
     _LIB = L
@@ -88,3 +91,22 @@ def rc_loss_grad(theta, x0, u, target, dt, lb=None, ub=None, native=False):
                                              int(u.shape[1] == 1 and N > 1), int(target.ndim == 1 or target.shape[1] == 1 and N > 1))
     assert rc == 0
     return loss, grad
+
+
+def rc_loss_grad_budget_f64(theta, x0, u, target, dt, lb=None, ub=None, traj_rtol=1e-5, native=False):
+    """fp64 forward-mode loss[N], grad[N,7] (box penalty included when lb/ub are given) and the conditioning budgets
+    loss_budget[N], grad_budget[N,7] of dynax_oracle.rc_output_sensitivity_budget, in one OpenMP sweep."""
+    theta, x0, u, target = _f32(np.atleast_2d(theta)), _f32(x0), _f32(u), _f32(target)
+    T, N = u.shape[0], x0.shape[0]
+    dp = ctypes.POINTER(ctypes.c_double)
+    d = lambda a: None if a is None else a.ctypes.data_as(dp)
+    lb64 = None if lb is None else np.ascontiguousarray(lb, dtype=np.float64)
+    ub64 = None if ub is None else np.ascontiguousarray(ub, dtype=np.float64)
+    loss, grad = np.empty((N,), np.float64), np.empty((N, 7), np.float64)
+    lbud, gbud = np.empty((N,), np.float64), np.empty((N, 7), np.float64)
+    rc = lib(native).oracle_rc_loss_grad_budget_f64(
+        _p(theta), _p(x0), _p(u), _p(target), d(lb64), d(ub64), d(loss), d(grad), d(lbud), d(gbud), N, T, float(dt),
+        int(theta.shape[0] == 1 and N > 1), int(u.shape[1] == 1 and N > 1),
+        int(target.ndim == 1 or target.shape[1] == 1 and N > 1), float(traj_rtol))
+    assert rc == 0
+    return loss, grad, lbud, gbud

@@ -229,3 +229,69 @@ int oracle_rc_loss_grad_f32(const float *theta, const float *x0, const float *u,
     }
     return fail ? -1 : 0;
 }
+
+/* fp64 "truth" for the parity samples of full-size runs (bench.py's parity block, tests/): loss, gradient and the
+ * conditioning budgets of oracle/dynax_oracle.py::rc_output_sensitivity_budget in ONE forward sweep per system,
+ * all arithmetic in double on the fp32 inputs.  The gradient is evaluated in forward mode (S = dx/dtheta beside the
+ * state, F = d rhs/d theta in closed form from RC.py:203-209,224-229), i.e. independently of the reverse-mode
+ * restatements above and in dynax_oracle.py (rc_loss_grad = hand adjoint + chain rule); tests/test_oracle_c.py pins
+ * the two against each other.  loss/grad include the box penalty of examples/3-inverse.py:103-107 when lb/ub are given.
+ * Budgets (may be NULL): loss_budget_i = (2/T) sum_k |r_k| rtol |y_k|,  grad_budget_ij = (2/T) sum_k |dy_k/dtheta_j| rtol |y_k|. */
+int oracle_rc_loss_grad_budget_f64(const float *theta, const float *x0, const float *u, const float *target,
+                                   const double *lb, const double *ub, double *loss, double *grad,
+                                   double *loss_budget, double *grad_budget, long N, long T, double dt,
+                                   int shared_theta, int shared_u, int shared_target, double traj_rtol) {
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < N; ++i) {
+        const float *th = theta + (shared_theta ? 0 : (size_t)i * 7);
+        const double Cai = th[0], Cwe = th[1], Cwi = th[2], Re = th[3], Ri = th[4], Rw = th[5], Rg = th[6];
+        const double iCai = 1.0 / Cai, iCwe = 1.0 / Cwe, iCwi = 1.0 / Cwi, iRe = 1.0 / Re, iRi = 1.0 / Ri, iRw = 1.0 / Rw,
+                     iRg = 1.0 / Rg;
+        const double A00 = -1.0 / Cai * (1.0 / Rg + 1.0 / Ri), A02 = 1.0 / (Cai * Ri), A11 = -1.0 / Cwe * (1.0 / Re + 1.0 / Rw),
+                     A12 = 1.0 / (Cwe * Rw), A20 = 1.0 / (Cwi * Ri), A21 = 1.0 / (Cwi * Rw),
+                     A22 = -1.0 / Cwi * (1.0 / Rw + 1.0 / Ri);
+        const double B00 = 1.0 / (Cai * Rg), B01 = 1.0 / Cai, B02 = 1.0 / Cai, B10 = 1.0 / (Cwe * Re), B13 = 1.0 / Cwe,
+                     B24 = 1.0 / Cwi;
+        double x[3] = {x0[(size_t)i * 3], x0[(size_t)i * 3 + 1], x0[(size_t)i * 3 + 2]};
+        double S[3][7], g[7], gb[7], sq = 0.0, lbud = 0.0;
+        memset(S, 0, sizeof S); memset(g, 0, sizeof g); memset(gb, 0, sizeof gb);
+        for (long k = 0; k < T; ++k) {
+            const float *uu = shared_u ? (u + (size_t)k * 5) : (u + ((size_t)k * N + i) * 5);
+            const double tg = shared_target ? target[k] : target[(size_t)k * N + i];
+            const double y = x[0], r = y - tg, w = traj_rtol * fabs(y);
+            sq += r * r;
+            lbud += fabs(r) * w;
+            for (int j = 0; j < 7; ++j) { g[j] += r * S[0][j]; gb[j] += fabs(S[0][j]) * w; }
+            const double r0 = (A00 * x[0] + A02 * x[2]) + (B00 * uu[0] + B01 * uu[1] + B02 * uu[2]);
+            const double r1 = (A11 * x[1] + A12 * x[2]) + (B10 * uu[0] + B13 * uu[3]);
+            const double r2 = (A20 * x[0] + A21 * x[1] + A22 * x[2]) + B24 * uu[4];
+            double F[3][7];
+            memset(F, 0, sizeof F);
+            F[0][0] = -r0 * iCai; F[1][1] = -r1 * iCwe; F[2][2] = -r2 * iCwi;
+            F[1][3] = -iCwe * iRe * iRe * (uu[0] - x[1]);
+            F[0][4] = -iCai * iRi * iRi * (x[2] - x[0]); F[2][4] = -iCwi * iRi * iRi * (x[0] - x[2]);
+            F[1][5] = -iCwe * iRw * iRw * (x[2] - x[1]); F[2][5] = -iCwi * iRw * iRw * (x[1] - x[2]);
+            F[0][6] = -iCai * iRg * iRg * (uu[0] - x[0]);
+            for (int j = 0; j < 7; ++j) {
+                const double a0 = S[0][j], a1 = S[1][j], a2 = S[2][j];
+                S[0][j] = a0 + dt * (A00 * a0 + A02 * a2 + F[0][j]);
+                S[1][j] = a1 + dt * (A11 * a1 + A12 * a2 + F[1][j]);
+                S[2][j] = a2 + dt * (A20 * a0 + A21 * a1 + A22 * a2 + F[2][j]);
+            }
+            x[0] += dt * r0; x[1] += dt * r1; x[2] += dt * r2;   /* simulator.py:40 */
+        }
+        double L = sq / (double)T;
+        for (int j = 0; j < 7; ++j) g[j] *= 2.0 / (double)T;
+        if (lb && ub)
+            for (int j = 0; j < 7; ++j) { /* 3-inverse.py:103-107, normaliser = ub */
+                const double over = (double)th[j] - ub[j], under = lb[j] - (double)th[j];
+                if (over > 0) { L += over / ub[j]; g[j] += 1.0 / ub[j]; }
+                if (under > 0) { L += under / ub[j]; g[j] -= 1.0 / ub[j]; }
+            }
+        loss[i] = L;
+        for (int j = 0; j < 7; ++j) grad[(size_t)i * 7 + j] = g[j];
+        if (loss_budget) loss_budget[i] = 2.0 / (double)T * lbud;
+        if (grad_budget) for (int j = 0; j < 7; ++j) grad_budget[(size_t)i * 7 + j] = 2.0 / (double)T * gb[j];
+    }
+    return 0;
+}

@@ -159,11 +159,14 @@ def test_tangent_wide_variants(T, ops, L, monkeypatch, N, tn, mode, gx0):
 
 
 @pytest.mark.parametrize("mode", ["per", "su", "stg", "su_stg"])
-@pytest.mark.parametrize("N,split,tn", [(N_SMALL, 4, 32), (N_MID, 2, 64)])
-def test_tangent_split_variants(T, ops, L, monkeypatch, N, split, tn, mode):
-    """Launches that cannot fill the GPU with one thread per system: 4 or 2 threads per system (automatic)."""
+@pytest.mark.parametrize("N,split,tn,force", [(N_SMALL, 2, 64, None), (N_SMALL, 4, 32, "4"), (N_MID, 2, 64, "2")])
+def test_tangent_split_variants(T, ops, L, monkeypatch, N, split, tn, force, mode):
+    """Launches that cannot fill the GPU with one thread per system: 2 threads per system (automatic for
+    N <= 32 systems per SM), 2 or 4 forced through DYNAX_FS_SPLIT."""
     Tn = 150
     monkeypatch.setenv("DYNAX_GRAD_ALGO", "1")
+    if force:
+        monkeypatch.setenv("DYNAX_FS_SPLIT", force)
     (out, idx, ref_in), sites = launched_by(L, lambda: _loss_grad_case(T, ops, N, Tn, mode, False, time_chunks=0))
     su, stg = mode in ("su", "su_stg"), mode.endswith("stg")
     expect(sites, "launch_fwdsens", f"TN = {tn};", f"SPLIT = {split};", f"SU = {str(su).lower()};",

@@ -50,3 +50,21 @@ def test_c_loss_grad_close_to_fp64_truth():
     # fp32 BPTT noise (SURVEY.md finding #9) -> norm-wise check per system
     nrm = np.linalg.norm(g32 - g64, axis=1) / np.linalg.norm(g64, axis=1)
     assert nrm.max() < 2e-3, nrm.max()
+
+
+def test_c_fp64_forward_mode_matches_numpy_adjoint_and_budgets():
+    """oracle_rc_loss_grad_budget_f64 (forward-mode sensitivities, closed-form d rhs/d theta) == the NumPy hand
+    adjoint + chain rule (reverse mode; itself pinned to torch-autograd fp64 in test_oracle_adjoint.py) == the NumPy
+    conditioning budgets -- for per-system and shared theta / u / target."""
+    T, N = 700, 19
+    th, x0, u = orc.synth_theta(N, 5), orc.synth_x0(N, 5), orc.synth_u(T, N, 5)
+    th[0, 0] = 4.0e4; th[1, 4] = 0.45      # above ub / below lb
+    target = (22 + np.random.default_rng(2).normal(size=(T, N))).astype(np.float32)
+    for thx, ux, tgx in ((th, u, target), (th[:1], u, target), (th, u[:, :1], target[:, 0])):
+        l, g, lb, gb = c_oracle.rc_loss_grad_budget_f64(thx, x0, ux, tgx, 3600.0, orc.RC_LB, orc.RC_UB)
+        thN = np.repeat(thx, N, 0) if thx.shape[0] == 1 else thx
+        tgN = tgx if tgx.ndim == 2 else np.repeat(tgx[:, None], N, 1)
+        l64, g64 = orc.rc_loss_grad(thN, x0, ux, tgN, 3600.0, orc.RC_LB, orc.RC_UB, np.float64)
+        lb64, gb64 = orc.rc_output_sensitivity_budget(thN, x0, ux, tgN, 3600.0)
+        assert np.allclose(l, l64, rtol=1e-12) and np.allclose(g, g64, rtol=1e-8, atol=1e-14 * np.abs(g64).max())
+        assert np.allclose(lb, lb64, rtol=1e-9) and np.allclose(gb, gb64, rtol=1e-5)   # NumPy budget: central differences of A(theta)

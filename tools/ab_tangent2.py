@@ -48,7 +48,11 @@ for N in sizes:
         fn = lambda: ops.rc_loss_grad(thx, x0, u, tg, 3600.0, time_chunks=0)
         variants = [("old", OLD, None)] if os.path.exists(OLD) else []
         variants += [("new", NEW, None)]
-        if N <= 40000:
+        for extra in os.environ.get("AB_LIBS", "").split(","):
+            pth = os.path.join(os.path.dirname(NEW), "_old", f"libdynax_{extra}.so")
+            if extra and os.path.exists(pth):
+                variants.append((extra, pth, None))
+        if N <= 40000 and not os.environ.get("AB_NO_SPLIT"):
             variants += [("new split1", NEW, "1"), ("new split2", NEW, "2"), ("new split4", NEW, "4")]
         for rep in range(2 if N > 100000 else 1):
             for name, path, split in variants:
@@ -58,13 +62,13 @@ for N in sizes:
                 best, mean, out = timeit(fn, 30 if N > 100000 else 20)
                 print(f"N={N:6d} shared_theta={int(shared_theta)} {name:11s}: best {best:7.3f} ms  sustained {mean:7.3f} ms  "
                       f"chk {float(out[0].double().sum()):.10e} {float(out[1].double().abs().sum()):.10e}", flush=True)
-        if N <= 40000 and not shared_theta:   # the time-parallel path for comparison
+        if N <= 40000 and not shared_theta and not os.environ.get("AB_NO_SPLIT"):   # the time-parallel path for comparison
             use(NEW); os.environ.pop("DYNAX_FS_SPLIT", None)
             best, mean, out = timeit(lambda: ops.rc_loss_grad(thx, x0, u, tg, 3600.0, time_chunks=-1), 20)
             print(f"N={N:6d} chunked(auto)          : best {best:7.3f} ms  sustained {mean:7.3f} ms", flush=True)
     del u, tg
 # config 3 as launched: candidates against ONE measured series
-for N in (65536, 8192):
+for N in ((65536, 8192) if not os.environ.get("AB_NO_SPLIT") else ()):
     th, x0, u, tg = data(N, shared_series=True)
     for name, path in ([("old", OLD)] if os.path.exists(OLD) else []) + [("new", NEW)]:
         use(path); os.environ.pop("DYNAX_FS_SPLIT", None)
