@@ -33,7 +33,7 @@ DT = 3600.0
 # `alg_bytes` is the algorithmic HBM traffic of the kernel actually launched, so roofline.frac is
 # comparable between the two; `value` (system-steps/s) is what the user sees.
 ALGOS = {
-    "tangent": {"alg_bytes": 24, "kernel": "rc_fwdsens_kernel<256,8,2,2,packed>", "env": "1"},
+    "tangent": {"alg_bytes": 24, "kernel": "rc_fwdsens_kernel<TN=256,KF=8,S=2,2 CTAs/SM,SPLIT=1> (packed fp32, TMA tensor maps)", "env": "1"},
     "adjoint": {"alg_bytes": 48, "kernel": "rollout_adj_kernel<RCModel,128,12,2,MSE>", "env": "0"},
 }
 WAVE = 148 * 2 * 256  # systems per full wave: 2 CTAs/SM x 256 (tangent) == 148 x 4 x 128; the adjoint's is 148*3*128
@@ -57,6 +57,11 @@ def parse():
     ap.add_argument("--cpu-systems", type=int, default=8192, help="bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the in-run parity sample against the fp64 oracle")
+    ap.add_argument("--parity-systems", type=int, default=4096, help="first K + K random systems of the timed run")
+    ap.add_argument("--no-config3", action="store_true", help="skip the BASELINE.json config-3 leg (strong scaling + all-reduce)")
+    ap.add_argument("--config3-systems", type=int, default=65536, help="systems in TOTAL over all ranks (strong scaling)")
+    ap.add_argument("--config3-steps", type=int, default=20)
     return ap.parse_args()
 
 
@@ -111,9 +116,35 @@ class ClockSampler:
         return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
+def _cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if "-" in part:
+            lo, hi = part.split("-")
+            cpus.update(range(int(lo), int(hi) + 1))
+        elif part:
+            cpus.add(int(part))
+    return cpus
+
+
 def bind_to_gpu_numa_node(index):
-    """Pin this rank to the CPUs NVML reports as local to its GPU, so first-touch places the pinned
-    host buffers of the e2e leg on the GPU's NUMA node (8 ranks otherwise share one node's memory)."""
+    """Pin this rank to the CPUs of its GPU's NUMA node, so that first-touch places the pinned host buffers of the
+    e2e leg next to the GPU (8 ranks otherwise share one node's memory).  The node comes from the PCI device in sysfs
+    (NVML's affinity mask was flat on the round-1 box); NVML is the fallback."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(index)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        nodes = [d for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()]
+        if node >= 0 and len(nodes) > 1:
+            cpus = _cpulist(open(f"/sys/devices/system/node/node{node}/cpulist").read()) & os.sched_getaffinity(0)
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                return f"gpu {bdf} on numa node {node} of {len(nodes)} (sysfs): bound to its {len(cpus)} cpus"
+        sys_note = f"sysfs: gpu {bdf} numa_node={node}, {len(nodes)} node(s)"
+    except Exception as e:
+        sys_note = f"sysfs probe failed ({type(e).__name__})"
     try:
         import pynvml
         pynvml.nvmlInit()
@@ -123,10 +154,10 @@ def bind_to_gpu_numa_node(index):
         cpus &= os.sched_getaffinity(0)
         if cpus:
             os.sched_setaffinity(0, cpus)
-            return f"bound to {len(cpus)} GPU-local cpus"
+            return f"{sys_note}; bound to {len(cpus)} GPU-local cpus (NVML affinity)"
     except Exception as e:  # not fatal: only a placement hint
-        return f"no numa binding ({type(e).__name__})"
-    return "no numa binding (empty intersection)"
+        return f"{sys_note}; no numa binding ({type(e).__name__})"
+    return f"{sys_note}; no numa binding (empty intersection)"
 
 
 def measured_peak():
@@ -191,6 +222,149 @@ def reference_arm(a):
                 "C/OpenMP port of the same arithmetic (all-fp32 BPTT storing per-step residuals like XLA's scan transpose)",
     }
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# in-run parity sample (SURVEY.md section 8(d) "Parity sampling"): first K + K random systems of the TIMED run
+# against the fp64 oracle, outside the timed region
+# ------------------------------------------------------------------------------------------------
+def parity_block(torch, theta, x0, u, target, loss, grad, tile, K, T):
+    """The timed step evaluates system s with theta[s], x0[s] and column (s mod tile) of the resident u/target tile.
+    Returns the `parity` object of the JSON line."""
+    import numpy as np
+    from oracle import c_oracle
+    S = theta.shape[0]
+    K = min(K, S // 2)
+    rng = np.random.default_rng(4242)
+    idx = np.concatenate([np.arange(K), np.sort(rng.choice(np.arange(K, S), K, replace=False))])
+    col = torch.as_tensor(idx % tile, device=theta.device)
+    sel = torch.as_tensor(idx, device=theta.device)
+    th, x0s = theta[sel].cpu().numpy(), x0[sel].cpu().numpy()
+    us, tgs = u[:, col].cpu().numpy(), target[:, col].cpu().numpy()
+    c_oracle.lib(native=True)
+    c_oracle.use_all_cores()
+    t0 = time.perf_counter()
+    l64, g64, lbud, gbud = c_oracle.rc_loss_grad_budget_f64(th, x0s, us, tgs, DT, native=True)
+    oracle_s = time.perf_counter() - t0
+    lg, gg = loss[sel].double().cpu().numpy(), grad[sel].double().cpu().numpy()
+    loss_frac = np.abs(lg - l64) / (1e-5 * np.abs(l64) + lbud)
+    grad_frac = np.abs(gg - g64) / (1e-4 * np.abs(g64) + gbud)
+    plain = np.abs(gg - g64) <= 1e-4 * np.abs(g64)
+    nw = np.linalg.norm(gg - g64, axis=1) / np.linalg.norm(g64, axis=1)
+    return {
+        "systems": int(len(idx)), "which": f"first {K} + {K} random systems of the timed run (seed 4242)",
+        "oracle": "oracle/dynax_oracle.c::oracle_rc_loss_grad_budget_f64 (fp64, forward mode), outside the timed region",
+        "oracle_seconds": round(oracle_s, 2),
+        "loss_max_rel_err": float((np.abs(lg - l64) / np.abs(l64)).max()),
+        "loss_max_frac_of_tolerance": float(loss_frac.max()),     # tolerance = 1e-5*|loss| + what a 1e-5 trajectory error does to the loss
+        "grad_frac_elements_within_plain_rel_1e-4": float(plain.mean()),
+        "grad_worst_normwise_err": float(nw.max()), "grad_median_normwise_err": float(np.median(nw)),
+        "grad_max_frac_of_tolerance": float(grad_frac.max()),     # tolerance = 1e-4*|g| + conditioning budget (tests/util.py)
+        "ok": bool(loss_frac.max() <= 1.0 and grad_frac.max() <= 1.0),
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json config 3: loss+gradient over N candidates / buildings sharing ONE parameter vector, sharded over the
+# ranks, gradients all-reduced over NCCL INSIDE the timed region (examples/3-inverse.py:112-113).  Strong scaling.
+# ------------------------------------------------------------------------------------------------
+def config3_leg(a, torch, dist, dev, rank, world):
+    from dynax_b200 import ops
+    from dynax_b200.distributed import shard_range
+    N3, T, K3 = a.config3_systems, a.T, a.config3_steps
+    theta = torch.tensor(NOMINAL, device=dev)
+
+    def shard(r):
+        lo, hi = shard_range(N3, r, world)
+        n = hi - lo
+        g = torch.Generator(device=dev).manual_seed(777 + 1000 * world + r)
+        x0 = torch.tensor([[20.0, 30.0, 26.0]], device=dev) + torch.empty((n, 3), device=dev).uniform_(-1, 1, generator=g)
+        u = torch.empty((T, n, 5), device=dev).uniform_(0, 1, generator=g)
+        u[..., 0] = 15 + 10 * u[..., 0]
+        tg = 20 + 2 * torch.empty((T, n), device=dev).uniform_(0, 1, generator=g)
+        return x0, u, tg
+
+    x0, u, tg = shard(rank)
+    buf = torch.zeros((8,), device=dev)                       # [loss, grad[7]]: ONE buffer, all-reduced in place
+    out = (buf[0:1], buf[1:8])
+
+    def step(reduce=True):
+        ops.rc_loss_grad(theta, x0, u, tg, DT, time_chunks=0, out=out)
+        if reduce and world > 1:
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+
+    def timed(fn, k):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / k
+
+    for _ in range(3):
+        step()
+    ms = timed(step, K3)
+    result = buf.double().clone()
+    kernel_ms = timed(lambda: step(False), K3)
+    ar_us = timed(lambda: dist.all_reduce(buf, op=dist.ReduceOp.SUM), 50) * 1e3 if world > 1 else 0.0
+    # the 1-rank answer, on every rank: the same shards one after the other, summed in fp64
+    del x0, u, tg
+    ref = torch.zeros((8,), device=dev, dtype=torch.float64)
+    for r in range(world):
+        x0r, ur, tgr = shard(r)
+        l, g, _ = ops.rc_loss_grad(theta, x0r, ur, tgr, DT, time_chunks=0)
+        ref[0] += l.double()[0]
+        ref[1:] += g.double()
+        del x0r, ur, tgr
+    err = float(((result - ref).norm() / ref.norm()).item())
+    errs = torch.tensor([err], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(errs, op=dist.ReduceOp.MAX)
+    err = float(errs.item())
+    assert err <= 1e-5, f"all-reduced shared-theta loss/gradient differs from the 1-rank result: {err:.3e}"
+    return {
+        "metric": "system-steps/s, fwd+grad RC rollout, ONE shared parameter vector (BASELINE.json configs[2])",
+        "value": N3 * T / (ms * 1e-3), "unit": "system-steps/s", "ms_per_step": ms, "steps": K3, "scaling": "strong",
+        "systems_total": N3, "systems_per_rank": shard_range(N3, rank, world)[1] - shard_range(N3, rank, world)[0], "T": T,
+        "collective": "NCCL all-reduce (sum) of 8 fp32 [loss, grad[7]] per step, inside the timed region" if world > 1 else "none (1 rank)",
+        "kernel_only_ms": kernel_ms, "allreduce_us": ar_us,
+        "vs_1rank_result_rel_err": err,
+        "inputs": "per-system x0, u[T,n,5], target[T,n] resident on each rank (13.8 GB in total), theta shared",
+    }
+
+
+def link_probe(torch, dist, dev, world, nbytes=1 << 30, reps=4):
+    """Plain pinned cudaMemcpyAsync H2D rate of this rank while all ranks copy at once (declared, outside the e2e
+    timing): the ceiling the e2e leg can reach.  Returns (GB/s of the slowest rank, sum over ranks)."""
+    h = torch.empty((nbytes,), dtype=torch.uint8, pin_memory=True)
+    h.zero_()
+    d = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+    d.copy_(h, non_blocking=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        d.copy_(h, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    gbs = nbytes * reps / (e0.elapsed_time(e1) * 1e-3) / 1e9
+    lo = torch.tensor([gbs], device=dev, dtype=torch.float64)
+    tot = lo.clone()
+    if world > 1:
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    del h, d
+    return float(lo.item()), float(tot.item())
 
 
 # ------------------------------------------------------------------------------------------------
@@ -278,6 +452,16 @@ def ours(a):
     launches = len(tiles) * a.steps
     assert bool(torch.isfinite(loss).all()) and bool(torch.isfinite(grad).all())
 
+    # ---- in-run parity sample: systems of THIS timed run against the fp64 oracle (rank 0, outside the timed region)
+    parity = None
+    if not a.no_parity and rank == 0:
+        parity = parity_block(torch, theta, x0, u, target, loss, grad, tile, a.parity_systems, T)
+
+    # ---- BASELINE.json config 3: shared parameters, sharded systems, NCCL all-reduce in the timed region
+    workloads = {}
+    if not a.no_config3:
+        workloads["config3"] = config3_leg(a, torch, dist, dev, rank, world)
+
     # ---- end to end: pinned HOST buffers -> host-API call (tiled H2D / kernel / D2H inside) -> host results
     e2e = None
     if not a.no_e2e:
@@ -292,6 +476,7 @@ def ours(a):
         hu.copy_(u[:, :nsrc].repeat(1, reps, 1)[:, :Ne]); ht.copy_(target[:, :nsrc].repeat(1, reps)[:, :Ne])
         hth.copy_(theta[:Ne]); hx0.copy_(x0[:Ne])
         torch.cuda.synchronize()
+        link_min, link_sum = link_probe(torch, dist, dev, world)      # declared: plain pinned H2D copies, all ranks at once
         args = (hth.numpy(), hx0.numpy(), hu.numpy(), ht.numpy(), DT)
         host.rc_loss_grad(*args)          # warm-up (allocates the cached device scratch)
         barrier()
@@ -310,6 +495,54 @@ def ours(a):
                "systems_per_step": Ne, "ms_per_step": e_sec / a.e2e_steps * 1e3,
                "api": "dynax_rc_loss_grad_host_f32 (pinned host buffers; tiled H2D/kernel/D2H on 2 streams)",
                "numa": numa_note}
+        # the link ceiling: a plain pinned cudaMemcpyAsync H2D stream per rank, all ranks copying at once
+        e2e["link_gbs_per_rank_min"] = link_min
+        e2e["link_gbs_all_ranks"] = link_sum
+        e2e["h2d_gbs_per_rank"] = e2e["h2d_bytes_per_step"] / (e2e["ms_per_step"] * 1e-3) / 1e9
+        e2e["link_frac"] = e2e["h2d_gbs_per_rank"] / link_min
+        # declared variant: u/target uploaded ONCE (dynax_rc_dataset_*), theta/x0 in and loss/grad out per call --
+        # what the 5000-epoch loop of examples/3-inverse.py:133-138 does with its one measured series
+        ds = host.RcDataset(hu.numpy(), ht.numpy())
+        ds.loss_grad(hth.numpy(), hx0.numpy(), DT)
+        barrier()
+        nrep = 5 * a.e2e_steps
+        t0 = time.perf_counter()
+        for _ in range(nrep):
+            l_d, g_d = ds.loss_grad(hth.numpy(), hx0.numpy(), DT)
+        d_sec = time.perf_counter() - t0
+        td = torch.tensor([d_sec], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(td, op=dist.ReduceOp.MAX)
+        assert np.array_equal(l_d, l_h) and np.array_equal(g_d, g_h)
+        ds.close()
+        e2e["resident_dataset_variant"] = {
+            "value": world * Ne * T * nrep / float(td.item()), "unit": "system-steps/s",
+            "h2d_bytes_per_step": int(hth.numel() + hx0.numel()) * 4, "d2h_bytes_per_step": int(l_d.size + g_d.size) * 4,
+            "ms_per_step": float(td.item()) / nrep * 1e3,
+            "api": "dynax_rc_dataset_loss_grad_f32 (u/target resident in HBM across calls; NOT the cold figure above)"}
+        if world == 1:
+            # what a NumPy caller really passes: pageable memory (the driver stages it), then the same arrays page-locked
+            # in place by dynax_host_register (registration timed separately: a one-off for long-lived arrays)
+            Np = min(Ne, 8192)
+            pu, pt = np.array(hu.numpy()[:, :Np]), np.array(ht.numpy()[:, :Np])
+            pth, px0 = np.array(hth.numpy()[:Np]), np.array(hx0.numpy()[:Np])
+            host.rc_loss_grad(pth, px0, pu, pt, DT)
+            t0 = time.perf_counter()
+            host.rc_loss_grad(pth, px0, pu, pt, DT)
+            p_sec = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            with host.pinned(pu, pt):
+                r_reg = time.perf_counter() - t0
+                host.rc_loss_grad(pth, px0, pu, pt, DT)
+                t0 = time.perf_counter()
+                host.rc_loss_grad(pth, px0, pu, pt, DT)
+                r_sec = time.perf_counter() - t0
+            e2e["pageable_variant"] = {"systems_per_step": Np, "value": Np * T / p_sec, "unit": "system-steps/s",
+                                       "h2d_gbs": (pu.nbytes + pt.nbytes) / p_sec / 1e9,
+                                       "registered_value": Np * T / r_sec, "registered_h2d_gbs": (pu.nbytes + pt.nbytes) / r_sec / 1e9,
+                                       "register_ms": r_reg * 1e3,
+                                       "api": "dynax_rc_loss_grad_host_f32 on pageable NumPy arrays / after dynax_host_register"}
+            del pu, pt
         # informational: the same loss+gradient when the disturbances are ONE shared series and only the
         # control channel is per system: 8 instead of 24 B/step over PCIe
         hc = torch.empty((T, Ne), dtype=torch.float32, pin_memory=True)
@@ -362,6 +595,7 @@ def ours(a):
                    "l2": "inputs larger than L2 (u+target tile %.1f GB re-read by each tile launch)" % ((u.numel() + target.numel()) * 4 / 1e9),
                    "parallelism": f"system axis sharded over {world} rank(s); no data-path collective"},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk.summary(),
+        "parity": parity, "workloads": workloads,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

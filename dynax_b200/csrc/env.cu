@@ -57,6 +57,15 @@ __device__ __forceinline__ float frac_index(const float *ts, int64_t R, float t,
     return (float)lo + (w > 0.f ? (t - ts[lo]) / w : 0.f);
 }
 
+// rc.py:238  h = int((int(t) % 86400) / 3600) with Python/jnp semantics: the remainder is non-negative also for
+// negative times (C's % is not), times beyond 2^31 s do not overflow, and the table index stays in [0, 23]
+__device__ __forceinline__ int hour_of_day(float t) {
+    const long long ti = (long long)t;
+    const long long r = ((ti % 86400) + 86400) % 86400;
+    const int h = (int)((float)r / 3600.0f);
+    return h < 0 ? 0 : (h > 23 ? 23 : h);
+}
+
 __global__ void rc_env_step_kernel(const EnvParams P) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.N) return;
@@ -66,9 +75,9 @@ __global__ void rc_env_step_kernel(const EnvParams P) {
     float x[3] = {P.x[i * 3], P.x[i * 3 + 1], P.x[i * 3 + 2]};
     float t = P.t[i];
     int64_t hint = 0;
-    const float scale = (P.u_high - P.u_low) / (float)(P.num_actions - 1);
     for (int64_t k = 0; k < P.K; ++k) {
-        const float control = (float)P.action[k * P.N + i] * scale + P.u_low;           // rc.py:166
+        // rc.py:166  action*(u_high-u_low)/(num_actions-1)+u_low, in the reference's order of operations
+        const float control = ((float)P.action[k * P.N + i] * (P.u_high - P.u_low)) / (float)(P.num_actions - 1) + P.u_low;
         const float idx = frac_index(P.ts, P.R, t, hint);                               // interpolate.py:63
         const float fl = floorf(idx);
         int64_t r0 = (int64_t)fl;
@@ -83,7 +92,7 @@ __global__ void rc_env_step_kernel(const EnvParams P) {
         M.step(x, u, P.dt, false);                                                      // simulator.py:38-40
         t = t + P.dt;                                                                   // rc.py:137
         const float power = -control / P.cop;                                           // rc.py:221
-        const int h = (int)((float)(((int)t) % 86400) / 3600.0f);                       // rc.py:238
+        const int h = hour_of_day(t);                                                   // rc.py:238
         const float energy = power * P.dt / 3600.0f;                                    // rc.py:241
         const float cst = P.price[h] * energy;                                          // rc.py:244
         const float dT = fmaxf(y - P.t_high[h], 0.f) + fmaxf(P.t_low[h] - y, 0.f);      // rc.py:247

@@ -264,6 +264,126 @@ static int loss_grad_host_impl(const float *theta, const float *x0, const float 
     return rc;
 }
 
+// ---- resident data set: u and target stay in device memory across calls -------------------------------------
+// examples/3-inverse.py:133-138 evaluates the SAME measured series 5000 times with changing parameters: uploading
+// u[T,N,5] and target[T,N] once leaves 40 bytes per system and call (theta, x0) on the way in and 32 on the way out.
+namespace {
+struct RcDataset {
+    float *d_u = nullptr, *d_tg = nullptr, *d_th = nullptr, *d_x0 = nullptr, *d_out = nullptr, *d_bounds = nullptr;
+    void *d_ws = nullptr;
+    size_t ws_bytes = 0;
+    int64_t N = 0, T = 0;
+    uint32_t flags = 0;
+    int device = -1;
+    cudaStream_t st = nullptr;
+};
+void dataset_free(RcDataset *d) {
+    if (!d) return;
+    cudaFree(d->d_u); cudaFree(d->d_tg); cudaFree(d->d_th); cudaFree(d->d_x0); cudaFree(d->d_out); cudaFree(d->d_bounds);
+    cudaFree(d->d_ws);
+    if (d->st) cudaStreamDestroy(d->st);
+    delete d;
+}
+}  // namespace
+
+int dynax_rc_dataset_create_f32(const float *u, const float *target, int64_t N, int64_t T, uint32_t flags, void **handle) {
+    if (!handle) return fail(DYNAX_ERR_INVALID_ARGUMENT, "handle must be non-NULL");
+    *handle = nullptr;
+    if (N < 1 || T < 1 || !u || !target) return fail(DYNAX_ERR_INVALID_ARGUMENT, "need N >= 1, T >= 1, u and target");
+    if (flags & ~(DYNAX_SHARED_U | DYNAX_SHARED_TARGET)) return fail(DYNAX_ERR_INVALID_ARGUMENT, "flags: DYNAX_SHARED_U / DYNAX_SHARED_TARGET");
+    TRY(require_sm100());
+    RcDataset *d = new RcDataset;
+    d->N = N; d->T = T; d->flags = flags;
+    const size_t ub = sizeof(float) * 5 * (size_t)T * ((flags & DYNAX_SHARED_U) ? 1 : N);
+    const size_t tb = sizeof(float) * (size_t)T * ((flags & DYNAX_SHARED_TARGET) ? 1 : N);
+    auto body = [&]() -> int {
+        DYNAX_CUDA_TRY(cudaGetDevice(&d->device));
+        DYNAX_CUDA_TRY(cudaStreamCreateWithFlags(&d->st, cudaStreamNonBlocking));
+        DYNAX_CUDA_TRY(cudaMalloc(&d->d_u, ub));
+        DYNAX_CUDA_TRY(cudaMalloc(&d->d_tg, tb));
+        DYNAX_CUDA_TRY(cudaMalloc(&d->d_th, sizeof(float) * 7 * N));
+        DYNAX_CUDA_TRY(cudaMalloc(&d->d_x0, sizeof(float) * 3 * N));
+        DYNAX_CUDA_TRY(cudaMalloc(&d->d_out, sizeof(float) * 8 * N));
+        DYNAX_CUDA_TRY(cudaMalloc(&d->d_bounds, sizeof(float) * 16));
+        // scratch for whichever algorithm a call may take (shared parameters: 1 KB; discrete stepping: checkpoints)
+        d->ws_bytes = dynax_workspace_bytes(DYNAX_OP_RC_LOSS_GRAD, N, T, 3, 5, 1, DYNAX_DISCRETE);
+        DYNAX_CUDA_TRY(cudaMalloc(&d->d_ws, d->ws_bytes));
+        DYNAX_CUDA_TRY(cudaMemcpyAsync(d->d_u, u, ub, cudaMemcpyHostToDevice, d->st));
+        DYNAX_CUDA_TRY(cudaMemcpyAsync(d->d_tg, target, tb, cudaMemcpyHostToDevice, d->st));
+        DYNAX_CUDA_TRY(cudaStreamSynchronize(d->st));
+        return DYNAX_OK;
+    };
+    const int rc = body();
+    if (rc != DYNAX_OK) {
+        dataset_free(d);
+        return rc;
+    }
+    *handle = d;
+    return DYNAX_OK;
+}
+
+int dynax_rc_dataset_loss_grad_f32(void *handle, const float *theta, const float *x0, const float *lb, const float *ub,
+                                   float dt, uint32_t flags, float *loss, float *g_theta) {
+    RcDataset *d = static_cast<RcDataset *>(handle);
+    if (!d || !theta || !x0 || !loss || !g_theta) return fail(DYNAX_ERR_INVALID_ARGUMENT, "handle, theta, x0, loss, g_theta must be non-NULL");
+    if ((lb == nullptr) != (ub == nullptr)) return fail(DYNAX_ERR_INVALID_ARGUMENT, "lb and ub go together");
+    if (flags & ~(DYNAX_SHARED_THETA | DYNAX_DISCRETE)) return fail(DYNAX_ERR_INVALID_ARGUMENT, "flags: DYNAX_SHARED_THETA / DYNAX_DISCRETE");
+    int dev = -1;
+    DYNAX_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev != d->device) return fail(DYNAX_ERR_INVALID_ARGUMENT, "data set lives on device %d, current device is %d", d->device, dev);
+    const bool sth = flags & DYNAX_SHARED_THETA;
+    const int64_t N = d->N, nout = sth ? 1 : N;
+    cudaStream_t st = d->st;
+    DYNAX_CUDA_TRY(cudaMemcpyAsync(d->d_th, theta, sizeof(float) * 7 * (sth ? 1 : N), cudaMemcpyHostToDevice, st));
+    DYNAX_CUDA_TRY(cudaMemcpyAsync(d->d_x0, x0, sizeof(float) * 3 * N, cudaMemcpyHostToDevice, st));
+    if (lb) {
+        DYNAX_CUDA_TRY(cudaMemcpyAsync(d->d_bounds, lb, sizeof(float) * 7, cudaMemcpyHostToDevice, st));
+        DYNAX_CUDA_TRY(cudaMemcpyAsync(d->d_bounds + 8, ub, sizeof(float) * 7, cudaMemcpyHostToDevice, st));
+    }
+    float *d_loss = d->d_out, *d_g = d->d_out + N;
+    const uint32_t f = d->flags | flags;
+    const bool chunked = !(f & DYNAX_DISCRETE) && N <= 4096 && d->T >= 512;   // break-even of ops.py
+    if (chunked) {
+        const size_t need = dynax_rc_loss_grad_chunked_workspace(N, d->T, 0);
+        if (need > d->ws_bytes) {
+            DYNAX_CUDA_TRY(cudaFree(d->d_ws));
+            d->d_ws = nullptr; d->ws_bytes = 0;
+            DYNAX_CUDA_TRY(cudaMalloc(&d->d_ws, need));
+            d->ws_bytes = need;
+        }
+        TRY(dynax_rc_loss_grad_chunked_f32(d->d_th, d->d_x0, d->d_u, d->d_tg, lb ? d->d_bounds : nullptr, lb ? d->d_bounds + 8 : nullptr,
+                                           d_loss, d_g, nullptr, N, d->T, dt, f, 0, d->d_ws, d->ws_bytes, st));
+    } else {
+        TRY(dynax_rc_loss_grad_f32(d->d_th, d->d_x0, d->d_u, d->d_tg, lb ? d->d_bounds : nullptr, lb ? d->d_bounds + 8 : nullptr, d_loss,
+                                   d_g, nullptr, N, d->T, dt, f, d->d_ws, d->ws_bytes, st));
+    }
+    DYNAX_CUDA_TRY(cudaMemcpyAsync(loss, d_loss, sizeof(float) * nout, cudaMemcpyDeviceToHost, st));
+    DYNAX_CUDA_TRY(cudaMemcpyAsync(g_theta, d_g, sizeof(float) * 7 * nout, cudaMemcpyDeviceToHost, st));
+    DYNAX_CUDA_TRY(cudaStreamSynchronize(st));
+    return DYNAX_OK;
+}
+
+int dynax_rc_dataset_destroy(void *handle) {
+    dataset_free(static_cast<RcDataset *>(handle));
+    return DYNAX_OK;
+}
+
+// ---- page-locking a caller's long-lived host buffers (NumPy arrays are pageable: the driver then stages every copy
+// through its own pinned buffer at a fraction of the link rate).  Thin wrappers so that a host program that never
+// links the CUDA runtime can pin the arrays it passes to the *_host entry points again and again.
+int dynax_host_register(const void *ptr, size_t bytes) {
+    if (!ptr || bytes == 0) return fail(DYNAX_ERR_INVALID_ARGUMENT, "ptr and bytes must be non-zero");
+    TRY(require_sm100());
+    DYNAX_CUDA_TRY(cudaHostRegister(const_cast<void *>(ptr), bytes, cudaHostRegisterDefault));
+    return DYNAX_OK;
+}
+
+int dynax_host_unregister(const void *ptr) {
+    if (!ptr) return fail(DYNAX_ERR_INVALID_ARGUMENT, "ptr must be non-NULL");
+    DYNAX_CUDA_TRY(cudaHostUnregister(const_cast<void *>(ptr)));
+    return DYNAX_OK;
+}
+
 int dynax_rc_loss_grad_host_f32(const float *theta, const float *x0, const float *u, const float *target,
                                 const float *lb, const float *ub, float *loss, float *g_theta, int64_t N,
                                 int64_t T, float dt, uint32_t flags, int64_t tile_systems) {

@@ -82,7 +82,9 @@ __global__ void __launch_bounds__(kMpcThreads) rc_mpc_cost_kernel(const MpcParam
         s.bd1 = M.B10 * dk[0] + M.B13 * dk[2];
         s.bd2 = M.B24 * dk[3];
         const float t_next = P.start_time + (float)(k + 1) * P.dt;      // rc.py:137 states.time + dt
-        const int h = (int)((((int)t_next) % 86400) / 3600.0f);        // rc.py:238
+        const long long ti = (long long)t_next;                         // rc.py:238, Python/jnp remainder (>= 0), h in [0,23]
+        int h = (int)((float)(((ti % 86400) + 86400) % 86400) / 3600.0f);
+        h = h < 0 ? 0 : (h > 23 ? 23 : h);
         s.ce = P.w_energy * (__ldg(P.price + h) * (P.dt / 3600.0f)) * (-1.0f / P.cop);
         s.lo = __ldg(P.t_low + h);
         s.hi = __ldg(P.t_high + h);

@@ -225,6 +225,28 @@ static int rc_adjoint(const float *theta, const float *x0, const float *u, const
 #define DYNAX_FS_LAUNCH_SPLIT(SU, STG)                                                                \
     (split == 4 ? launch_fwdsens<32, 16, 3, 4, 4, SU, STG>(F, st)                                       \
                 : split == 2 ? launch_fwdsens<64, 16, 3, 4, 2, SU, STG>(F, st) : DYNAX_FS_LAUNCH(SU, STG, false))
+#ifdef DYNAX_FS_EXPERIMENTS   // tile-shape sweep for launches that cannot fill the GPU (tools/ab_tangent3.py)
+        if (!ctrl && !g_x0 && !su && !stg) {
+            switch (env_int("DYNAX_FS_EXP", 0)) {
+#define FSX(...) launch_fwdsens<__VA_ARGS__>(F, st)
+                case 1: return FSX(64, 16, 3, 2, 2, false, false, false, false, false, false);
+                case 2: return FSX(64, 8, 4, 2, 4, false, false, false, false, false, false);
+                case 3: return FSX(64, 16, 3, 1, 4, false, false, false, false, false, false);
+                case 4: return FSX(128, 16, 2, 2, 1, false, false, false, false, false, false);
+                case 5: return FSX(64, 8, 4, 2, 2, false, false, false, false, false, false);
+                case 6: return FSX(32, 16, 3, 4, 4, false, false, false, false, false, false);
+                case 7: return FSX(32, 16, 6, 4, 2, false, false, false, false, false, false);
+                case 30: return FSX(224, 4, 2, 3, 1);
+                case 31: return FSX(192, 6, 2, 3, 1);
+                case 32: return FSX(192, 4, 3, 3, 1);
+                case 34: return FSX(256, 4, 3, 2, 1);
+                case 35: return FSX(224, 8, 2, 2, 1);
+                case 36: return FSX(256, 8, 2, 2, 1, false, false, false, false, false, false);
+#undef FSX
+                default: break;
+            }
+        }
+#endif
         if (ctrl && stg) return DYNAX_FS_LAUNCH(true, true, true);
         if (ctrl) return DYNAX_FS_LAUNCH(true, false, true);
         if (su && stg) return DYNAX_FS_LAUNCH_SPLIT(true, true);

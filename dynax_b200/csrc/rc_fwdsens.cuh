@@ -65,12 +65,6 @@ struct FwdSensParams {
     alignas(64) CUtensorMap map_u, map_t, map_c;   // u[T,N*5], target[T,N], ctrl[T,N]
 };
 
-#ifndef DYNAX_FS_FENCE
-#define DYNAX_FS_FENCE 1
-#endif
-#ifndef DYNAX_FS_PRED
-#define DYNAX_FS_PRED 1
-#endif
 #ifndef DYNAX_FS_DIAGLAST
 #define DYNAX_FS_DIAGLAST 0
 #endif
@@ -106,7 +100,7 @@ __host__ __device__ constexpr unsigned fs_pair_mask(int split, int role, bool gx
 }
 __host__ __device__ constexpr bool fs_has_c(int split, int role, bool gx0) { return !gx0 && role == split - 1; }
 
-template <int TN, int KF, int S, int SPLIT, int ROLE, bool SHARED_U, bool SHARED_TGT, bool CTRL, bool GX0, bool CHUNK>
+template <int TN, int KF, int S, int SPLIT, int ROLE, bool SHARED_U, bool SHARED_TGT, bool CTRL, bool GX0, bool CHUNK, bool PRED>
 __device__ __forceinline__ void fs_consumer(const FwdSensParams &P, unsigned char *smem_raw, float *s_in, uint64_t *full,
                                             uint64_t *empty, const int sys, const int64_t n0, const int valid,
                                             const int64_t cidx, const int T, const int C) {
@@ -305,7 +299,7 @@ __device__ __forceinline__ void fs_consumer(const FwdSensParams &P, unsigned cha
         x2 = fmaf(dt, r2, x2);
     };
 
-#if DYNAX_FS_PRED
+    if constexpr (PRED) {
     // One predicated, fully unrolled body per chunk; the last chunk may be ragged.  (Measured on B200: the per-row
     // predicates double as scheduling fences -- ptxas keeps the loads of step j+1 behind step j, live ranges stay
     // short at 96 registers -- and this form is 3-4 % FASTER than an unpredicated body for full chunks.)
@@ -341,7 +335,7 @@ __device__ __forceinline__ void fs_consumer(const FwdSensParams &P, unsigned cha
             }
         }
     }
-#else
+    } else {
     // Chunk 0 holds the ragged part of the horizon (r0 = T - (C-1) KF rows, 1..KF) and runs as a rolled loop; every
     // other chunk is full and runs the unrolled body without per-row predicates.
     const int r0 = T - (C - 1) * KF;
@@ -381,17 +375,13 @@ __device__ __forceinline__ void fs_consumer(const FwdSensParams &P, unsigned cha
 #pragma unroll
         for (int jj = 0; jj < KF; ++jj) {
             step(jj);
-#if DYNAX_FS_FENCE
-            asm volatile("" ::: "memory");  // keeps the loads of step jj+1 behind step jj: short live ranges (96 registers)
-#endif
         }
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&empty[s]);
         if (c % FOLDC == 0) fold();
     }
     fold();
-
-#endif
+    }
 
     // ---- outputs: every role reports the columns it owns ----
     // column j of the gradient lives in slot j (j < 7); x0 columns: x0_0 -> slot 10, x0_1 -> 8, x0_2 -> 9
@@ -469,7 +459,7 @@ __device__ __forceinline__ void fs_consumer(const FwdSensParams &P, unsigned cha
 }
 
 template <int TN, int KF, int S, int MINB, int SPLIT = 1, bool SHARED_U = false, bool SHARED_TGT = false,
-          bool CTRL = false, bool GX0 = false, bool CHUNK = false>
+          bool CTRL = false, bool GX0 = false, bool CHUNK = false, bool PRED = true>
 __global__ void __launch_bounds__(TN * SPLIT + 32, MINB) rc_fwdsens_kernel(const __grid_constant__ FwdSensParams P) {
     static_assert(!CTRL || SHARED_U, "the control channel replaces a column of a SHARED input series");
     static_assert(!CHUNK || (!GX0 && !CTRL), "time-chunked launches use the plain kernel");
@@ -510,14 +500,10 @@ __global__ void __launch_bounds__(TN * SPLIT + 32, MINB) rc_fwdsens_kernel(const
         const uint64_t pol = ptx::policy_evict_first(), pol_keep = ptx::policy_evict_last();
         auto load_chunk = [&](int c) {
             const int s = c % S;
-#if DYNAX_FS_PRED
-            const int64_t k0 = (int64_t)c * KF;
-            const int rows = (int)((T - k0) < KF ? (T - k0) : KF);
-#else
-            const int r0 = T - (C - 1) * KF;  // chunk 0 holds the ragged part of the horizon (see the consumers)
-            const int64_t k0 = c == 0 ? 0 : r0 + (int64_t)(c - 1) * KF;
-            const int rows = c == 0 ? r0 : KF;
-#endif
+            // !PRED: chunk 0 holds the ragged part of the horizon (see the consumers), every other chunk is full
+            const int r0 = T - (C - 1) * KF;
+            const int64_t k0 = PRED ? (int64_t)c * KF : (c == 0 ? 0 : r0 + (int64_t)(c - 1) * KF);
+            const int rows = PRED ? (int)((T - k0) < KF ? (T - k0) : KF) : (c == 0 ? r0 : KF);
             float *du = s_in + s * Cfg::STAGE, *dtg = du + Cfg::U_STAGE;
             // Shared series: one bulk copy per block of rows when it is 16-byte aligned and sized (asynchronous, so the
             // producer does not pay an L2 round trip per chunk), else plain loads by the producer lanes.  Per-system
@@ -597,8 +583,8 @@ __global__ void __launch_bounds__(TN * SPLIT + 32, MINB) rc_fwdsens_kernel(const
     // --------------------------------- consumers: role = warp-uniform ---------------------------------
     const int role = SPLIT == 1 ? 0 : tid / TN, sys = SPLIT == 1 ? tid : tid % TN;
 #define DYNAX_FS_ROLE(R)                                                                                         \
-    fs_consumer<TN, KF, S, SPLIT, R, SHARED_U, SHARED_TGT, CTRL, GX0, CHUNK>(P, smem_raw, s_in, full, empty, sys, n0, \
-                                                                             valid, cidx, T, C)
+    fs_consumer<TN, KF, S, SPLIT, R, SHARED_U, SHARED_TGT, CTRL, GX0, CHUNK, PRED>(P, smem_raw, s_in, full, empty, sys, \
+                                                                                   n0, valid, cidx, T, C)
     if constexpr (SPLIT == 1) {
         DYNAX_FS_ROLE(0);
     } else if constexpr (SPLIT == 2) {

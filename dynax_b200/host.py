@@ -11,7 +11,7 @@ import numpy as np
 
 from ._lib import DISCRETE, SHARED_TARGET, SHARED_THETA, SHARED_U, check, lib
 
-__all__ = ["rc_forward", "rc_loss_grad", "release"]
+__all__ = ["rc_forward", "rc_loss_grad", "rc_loss_grad_ctrl", "release", "RcDataset", "pinned"]
 
 
 def _f32(a):
@@ -109,3 +109,80 @@ def rc_loss_grad_ctrl(theta, x0, u_shared, ctrl, target, dt, ctrl_col=2, lb=None
                                                  _p(lb), _p(ub), _p(loss), _p(grad), N, T, float(dt), flags,
                                                  int(tile_systems)))
     return loss, grad
+
+
+class RcDataset:
+    """u and target resident in device memory across calls (``dynax_rc_dataset_*``): the calibration loop of
+    examples/3-inverse.py:133-138 re-evaluates ONE measured series for changing parameters, so per call only
+    theta and x0 cross the link.  ``ds = RcDataset(u, target); loss, grad = ds.loss_grad(theta, x0, dt)``."""
+
+    def __init__(self, u, target, n_systems=None):
+        import ctypes
+        u, target = _f32(u), _f32(target)
+        if u.ndim == 2:
+            u = u[:, None, :]
+        if u.ndim != 3 or u.shape[2] != 5:
+            raise ValueError(f"u must be [T,N,5] or [T,5], got {u.shape}")
+        T = u.shape[0]
+        if target.ndim == 2 and target.shape[0] == T:
+            N = target.shape[1]
+        elif target.size == T:
+            N, target = u.shape[1], target.reshape(T)
+        else:
+            raise ValueError(f"target must be [T,N] or [T], got {target.shape}")
+        N = max(N, u.shape[1], int(n_systems or 1))   # n_systems: needed when BOTH series are shared
+        if u.shape[1] not in (1, N):
+            raise ValueError("u and target disagree on the number of systems")
+        self.N, self.T = N, T
+        self._flags = (SHARED_U if (u.shape[1] == 1 and N != 1) else 0) | (SHARED_TARGET if (target.ndim == 1 and N != 1) else 0)
+        h = ctypes.c_void_p()
+        check(lib().dynax_rc_dataset_create_f32(_p(u), _p(target), N, T, self._flags, ctypes.byref(h)))
+        self._h = h
+
+    def loss_grad(self, theta, x0, dt, lb=None, ub=None, discrete=False):
+        theta, x0 = _f32(theta), _f32(x0)
+        if theta.ndim == 1:
+            theta = theta[None]
+        if x0.shape != (self.N, 3) or theta.shape[1:] != (7,) or theta.shape[0] not in (1, self.N):
+            raise ValueError(f"theta must be [N,7] or [7] and x0 [N,3] with N={self.N}")
+        if (lb is None) != (ub is None):
+            raise ValueError("lb and ub must be given together")
+        lb = None if lb is None else _f32(lb).reshape(7)
+        ub = None if ub is None else _f32(ub).reshape(7)
+        shared = theta.shape[0] == 1 and self.N != 1
+        loss = np.empty((1 if shared else self.N,), np.float32)
+        grad = np.empty((7,) if shared else (self.N, 7), np.float32)
+        check(lib().dynax_rc_dataset_loss_grad_f32(self._h, _p(theta), _p(x0), _p(lb), _p(ub), float(dt),
+                                                   (SHARED_THETA if shared else 0) | (DISCRETE if discrete else 0),
+                                                   _p(loss), _p(grad)))
+        return loss, grad
+
+    def close(self):
+        if getattr(self, "_h", None):
+            check(lib().dynax_rc_dataset_destroy(self._h))
+            self._h = None
+
+    __del__ = close
+
+
+class pinned:
+    """Context manager: page-locks NumPy arrays for the duration of the block (``dynax_host_register``), so that the
+    *_host calls copy them at the pinned PCIe rate instead of through the driver's staging buffer."""
+
+    def __init__(self, *arrays):
+        self._arrays = [a for a in arrays if a is not None]
+        self._done = []
+
+    def __enter__(self):
+        for a in self._arrays:
+            if a.dtype != np.float32 or not a.flags["C_CONTIGUOUS"]:
+                raise ValueError("pin contiguous float32 arrays (the *_host calls would copy anything else first)")
+            check(lib().dynax_host_register(a.ctypes.data, a.nbytes))
+            self._done.append(a)
+        return self
+
+    def __exit__(self, *exc):
+        for a in self._done:
+            lib().dynax_host_unregister(a.ctypes.data)
+        self._done = []
+        return False

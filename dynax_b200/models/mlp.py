@@ -43,7 +43,15 @@ class NeuralODE(BaseContinuousBlockSSM):
             out += [fx[f"dense_{k}"]["kernel"].transpose(-1, -2).contiguous(), fx[f"dense_{k}"]["bias"].contiguous()]
         return out  # W1, b1, W2, b2, W3, b3  (row-major [out,in])
 
+    supports_rk4 = True
+
     def _rollout(self, params, x0, u, dt, discrete, solver="euler"):
         if discrete:
-            raise NotImplementedError("NeuralODE is a continuous model")
+            # BaseBlockSSM.apply evaluates the model ONCE (rhs, y) as a T=1 launch with x_next = rhs
+            # (base_block_state_space.py:51-57).  For the general fx/fy model: one Euler step of size 1 gives
+            # x + rhs, so rhs = xsol - x; y comes from the pre-update state as in every rollout.
+            if u.shape[0] != 1:
+                raise NotImplementedError("NeuralODE is a continuous model: discrete stepping is the single evaluation of model.apply only")
+            xsol, ysol = ops.node_rollout(*self.matrices(params), x0, u, 1.0, euler=True)
+            return xsol - x0[None], ysol
         return ops.node_rollout(*self.matrices(params), x0, u, dt, euler=(solver == "euler"))

@@ -609,10 +609,11 @@ def node_rk4_vjp(W1, b1, W2, b2, W3, b3, x0, u, xsol, dt, g_xsol=None, g_ysol=No
     x0, u, xsol = _f32c(x0, "x0"), _f32c(u, "u"), _f32c(xsol, "xsol")
     hidden, n = ws_[1].numel(), ws_[5].numel()
     m = ws_[0].shape[1] - n
-    N = x0.shape[0]
-    if u.dim() == 2:
-        u = u[:, None, :].expand(u.shape[0], N, m).contiguous()
-    T = u.shape[0]
+    # same shape rules as the forward (a shared series is u[T,m] or u[T,1,m]); the VJP kernels index u per system, so a
+    # shared series is materialised here and its g_u summed over systems below
+    x0, u, N, T, shared_u = _canon_batch(None, x0, u, n, m)
+    if shared_u:
+        u = u.expand(T, N, m).contiguous()
     dev = x0.device
     if g_xsol is not None:
         g_xsol = _f32c(g_xsol, "g_xsol").reshape(T, N, n)
@@ -629,6 +630,8 @@ def node_rk4_vjp(W1, b1, W2, b2, W3, b3, x0, u, xsol, dt, g_xsol=None, g_ysol=No
                                                   _ptr(g_xsol), _ptr(g_ysol), *[_ptr(t) for t in gw], _ptr(gx0),
                                                   _ptr(gu), N, T, n, m, 1, hidden, float(dt),
                                                   _lib.SOLVER_EULER if euler else 0, _ptr(wsb), wsb.numel(), _stream()))
+    if gu is not None and shared_u:
+        gu = gu.sum(dim=1, keepdim=True)
     return (*gw, gx0, gu)
 
 
@@ -651,8 +654,8 @@ class _NodeRollout(torch.autograd.Function):
         out = node_rk4_vjp(*W, x0, u, xsol, ctx.dt, g_xsol, g_ysol, need_u=ctx.needs_input_grad[7], euler=ctx.euler,
                            stage_x=stages)
         gu = out[7]
-        if gu is not None and u.dim() == 2:
-            gu = gu.sum(1)
+        if gu is not None:
+            gu = gu.reshape(u.shape)        # [T,1,m] (summed over systems by node_rk4_vjp) -> the caller's [T,m] / [T,1,m]
         return (*out[:6], out[6], gu, None, None)
 
 

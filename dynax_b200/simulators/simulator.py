@@ -51,6 +51,9 @@ class DifferentiableSimulator:
             u = u[:, None, :]
         params = variables["params"]["model"]
         if self.solver == "rk4":
+            if not getattr(model, "supports_rk4", False):
+                raise ValueError(f"solver='rk4' is available for models with general fx/fy dynamics (NeuralODE); "
+                                 f"{type(model).__name__} is stepped with explicit Euler like the reference (simulator.py:40)")
             xsol, ysol = model._rollout(params, x0, u, float(self.dt), False, solver="rk4")
         else:
             xsol, ysol = model._rollout(params, x0, u, float(self.dt), False)   # simulator.py:40 always Euler

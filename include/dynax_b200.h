@@ -311,6 +311,21 @@ int dynax_rc_loss_grad_ctrl_host_f32(const float *theta, const float *x0, const 
                                      float *loss, float *g_theta,
                                      int64_t N, int64_t T, float dt, uint32_t flags, int64_t tile_systems);
 
+/* Resident data set: upload u[T,N,5] (or [T,5] with DYNAX_SHARED_U) and target[T,N] (or [T] with
+ * DYNAX_SHARED_TARGET) ONCE, then evaluate loss and gradient for changing parameters -- the loop of
+ * examples/3-inverse.py:133-138 (5000 epochs over the same measured series).  Per call only theta[N,7] ([7] with
+ * DYNAX_SHARED_THETA) and x0[N,3] go in and loss[N|1], g_theta[N|1,7] come out (HOST pointers); returns when the
+ * results are in the host buffers.  The handle belongs to the device that was current at creation. */
+int dynax_rc_dataset_create_f32(const float *u, const float *target, int64_t N, int64_t T, uint32_t flags, void **handle);
+int dynax_rc_dataset_loss_grad_f32(void *handle, const float *theta, const float *x0, const float *lb, const float *ub,
+                                   float dt, uint32_t flags, float *loss, float *g_theta);
+int dynax_rc_dataset_destroy(void *handle);
+
+/* Page-lock / unlock a long-lived HOST buffer (cudaHostRegister): pageable memory -- what NumPy allocates -- is staged
+ * by the driver at a fraction of the link rate; a registered buffer is copied at the pinned rate by the *_host calls. */
+int dynax_host_register(const void *ptr, size_t bytes);
+int dynax_host_unregister(const void *ptr);
+
 /* Frees the device scratch the *_host entry points cache between calls. */
 int dynax_host_release(void);
 

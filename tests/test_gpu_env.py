@@ -57,3 +57,24 @@ def test_batched_multi_step_vs_oracle(T):
         xr, tr = r["x_next"], r["t_next"]
     assert rel_err(out["x_next"].cpu().numpy(), xr) < 1e-5
     assert out["terminated"].sum().item() > 0
+
+
+def test_negative_and_late_start_times(T):
+    """rc.py:238 h = int((int(t) % 86400)/3600) with Python/jnp semantics: a negative start time gives a non-negative
+    remainder (C's % does not), so price/comfort tables are never read out of bounds (round-1 advisor finding)."""
+    from dynax_b200.wrapper import RC, EnvStates
+    rng = np.random.default_rng(141)
+    R, N, K, dt = 300, 64, 5, 900.0
+    ts = (np.arange(R) - 150) * 900.0                                   # table covers negative times too
+    dist = np.stack([15 + 10 * rng.random(R), rng.random(R), 2 * rng.random(R), rng.random(R)], 1)
+    env = RC(ts, dist, dt=dt, num_actions=11)
+    x = (np.array([20.0, 30.0, 26.0])[None] + rng.uniform(-1, 1, size=(N, 3))).astype(np.float32)
+    t = (rng.integers(-140, 100, size=N) * 900.0).astype(np.float32)     # many envs start before t = 0
+    actions = rng.integers(0, 11, size=(K, N))
+    out = env.rollout(T.tensor(actions).cuda(), EnvStates(x=T.tensor(x).cuda(), time=T.tensor(t).cuda()))
+    xr, tr = x.copy(), t.copy()
+    for k in range(K):
+        r = orc.rc_env_step(orc.RC_NOMINAL, xr, tr, actions[k], ts, dist, dt, num_actions=11, dtype=np.float64)
+        assert np.allclose(out["reward"][k].cpu().numpy(), r["reward"], rtol=1e-4, atol=1e-5)
+        xr, tr = r["x_next"], r["t_next"]
+    assert bool(T.isfinite(out["reward"]).all())

@@ -162,3 +162,26 @@ def test_neural_ode_through_simulator(T):
         assert all(layer["kernel"].grad is not None and bool(T.isfinite(layer["kernel"].grad).all()) for layer in fx.values())
     xs1, _ = DifferentiableSimulator(model, dt=0.1, solver="rk4").apply(variables, x0[0], u[:, 0])   # unbatched call shape
     assert xs1.shape == (Tn, 3)
+
+
+def test_model_apply_and_solver_errors_for_every_model(T):
+    """BaseBlockSSM.__call__ -> (rhs, y) (base_block_state_space.py:51-57) works for the general fx/fy model too, and
+    solver='rk4' on a model without RK4 support is a clear ValueError, not a TypeError from a forwarded kwarg."""
+    from dynax_b200.models import Continuous4R3C, NeuralODE
+    from dynax_b200.simulators import DifferentiableSimulator
+    rng = np.random.default_rng(181)
+    model = NeuralODE()
+    x = T.tensor(rng.normal(size=(5, 3)), dtype=T.float32).cuda()
+    u = T.tensor(rng.normal(size=(5, 5)), dtype=T.float32).cuda()
+    variables = model.init(4, x, u)
+    rhs, y = model.apply(variables, x, u)
+    W = [w.detach().cpu().double() for w in model.matrices(variables["params"])]
+    z = T.cat([x.cpu().double(), u.cpu().double()], -1)
+    ref = T.tanh(T.tanh(z @ W[0].T + W[1]) @ W[2].T + W[3]) @ W[4].T + W[5]
+    assert rel_err(rhs.cpu().numpy(), ref.numpy(), floor=1.0) < 1e-5 and T.equal(y.cpu(), x.cpu()[:, :1])
+    r1, y1 = model.apply(variables, x[0], u[0])                       # unbatched, like the reference's model(x, u)
+    assert r1.shape == (3,) and T.allclose(r1, rhs[0])
+    rc = Continuous4R3C()
+    v = DifferentiableSimulator(rc, dt=60.0).init(0, x[0], u)            # x0[3], inputs[T=5,5]
+    with pytest.raises(ValueError, match="rk4"):
+        DifferentiableSimulator(rc, dt=60.0, solver="rk4").apply(v, x[0], u)

@@ -64,3 +64,42 @@ def test_loss_grad_ctrl_host_matches_device_api():
     c = lambda a: torch.tensor(np.ascontiguousarray(a)).cuda()
     ld, gd, _ = ops.rc_loss_grad_ctrl(c(th), c(x0), c(d), c(ctrl), c(target), 3600.0, lb=orc.RC_LB, ub=orc.RC_UB)
     assert np.array_equal(ld.cpu().numpy(), loss) and np.array_equal(gd.cpu().numpy(), grad)
+
+
+def test_resident_dataset_matches_host_call():
+    """dynax_rc_dataset_*: u/target uploaded once, theta/x0 per call (the loop of examples/3-inverse.py:133-138) gives
+    exactly what the one-shot host call gives, for per-system and shared theta / u / target, with and without bounds."""
+    from dynax_b200 import host
+    N, Tn = 300, 700
+    th, x0, u = orc.synth_theta(N, 71), orc.synth_x0(N, 71), orc.synth_u(Tn, N, 71)
+    tg = (22 + np.random.default_rng(3).normal(size=(Tn, N))).astype(np.float32)
+    th[2, 3] = 50.0
+    for uu, tt in ((u, tg), (u[:, :1], tg[:, 0])):
+        ds = host.RcDataset(uu, tt, n_systems=N)
+        for thx in (th, th[0]):
+            for k in range(2):                                     # second call: parameters changed, data resident
+                thk = (thx * (1.0 + 0.01 * k)).astype(np.float32)
+                l1, g1 = ds.loss_grad(thk, x0, 3600.0, orc.RC_LB, orc.RC_UB)
+                l2, g2 = host.rc_loss_grad(thk, x0, uu, tt, 3600.0, orc.RC_LB, orc.RC_UB)
+                if thx.ndim == 2:
+                    assert np.array_equal(l1, l2) and np.array_equal(g1, g2)
+                else:   # shared theta: fp64 atomics across warps -> order-dependent last bits
+                    assert np.allclose(l1, l2, rtol=1e-6) and np.allclose(g1, g2, rtol=1e-5, atol=1e-9 * np.abs(g2).max())
+        ds.close()
+    # the oracle on a sample
+    ds = host.RcDataset(u, tg)
+    l, g = ds.loss_grad(th, x0, 3600.0)
+    l64, g64 = orc.rc_loss_grad(th[:16], x0[:16], u[:, :16], tg[:, :16], 3600.0, None, None, np.float64)
+    assert np.allclose(l[:16], l64, rtol=1e-4)
+    ds.close()
+
+
+def test_host_register_pins_numpy_buffers():
+    from dynax_b200 import host
+    N, Tn = 256, 300
+    th, x0, u = orc.synth_theta(N, 72), orc.synth_x0(N, 72), orc.synth_u(Tn, N, 72)
+    tg = (22 + np.random.default_rng(4).normal(size=(Tn, N))).astype(np.float32)
+    l0, g0 = host.rc_loss_grad(th, x0, u, tg, 3600.0)
+    with host.pinned(u, tg):
+        l1, g1 = host.rc_loss_grad(th, x0, u, tg, 3600.0)
+    assert np.array_equal(l0, l1) and np.array_equal(g0, g1)

@@ -137,3 +137,29 @@ def test_vjp_with_saved_stage_points(T, monkeypatch, impl):
     # Euler has no stage points; a shared input series runs on the CUDA-core forward kernel, which does not emit them
     assert ops.node_rk4_forward(*W, cu(T, x0), cu(T, u), 0.25, euler=True, emit_stages=True)[3] is None
     assert ops.node_rk4_forward(*W, cu(T, x0), cu(T, u[:, 0]), 0.25, emit_stages=True)[3] is None
+
+
+@pytest.mark.parametrize("shape", ["T1m", "Tm"])
+def test_vjp_shared_input_series(T, shape):
+    """A shared input series (u[T,1,5] or u[T,5] with N > 1 systems) through autograd: the forward accepts it, the
+    VJP kernels index u per system -- the glue materialises the broadcast and sums g_u back to the caller's shape
+    (round-1 advisor finding: u[T,1,5] reached the kernel as a T*5 buffer)."""
+    from dynax_b200 import ops
+    N, Tn = 70, 19
+    Wnp = orc.synth_mlp(130, scale=0.5)
+    x0, u = inputs(N, Tn, 131)
+    u1 = u[:, :1] if shape == "T1m" else u[:, 0]
+    rng = np.random.default_rng(132)
+    gx = rng.normal(size=(Tn, N, 3)).astype(np.float32); gy = rng.normal(size=(Tn, N, 1)).astype(np.float32)
+    Wd = [T.tensor(w, dtype=T.float64, requires_grad=True) for w in Wnp]
+    x0d = T.tensor(x0, dtype=T.float64, requires_grad=True); ud = T.tensor(u1, dtype=T.float64, requires_grad=True)
+    ub = ud.expand(Tn, N, 5) if shape == "T1m" else ud[:, None, :].expand(Tn, N, 5)
+    xs, ys = _torch_node_rollout(T, Wd, x0d, ub, 0.25, False)
+    ((xs * T.tensor(gx, dtype=T.float64)).sum() + (ys * T.tensor(gy, dtype=T.float64)).sum()).backward()
+    Wc = [cu(T, w).requires_grad_(True) for w in Wnp]
+    x0c = cu(T, x0).requires_grad_(True); uc = cu(T, u1).requires_grad_(True)
+    xs_c, ys_c = ops.node_rollout(*Wc, x0c, uc, 0.25)
+    ((xs_c * cu(T, gx)).sum() + (ys_c * cu(T, gy)).sum()).backward()
+    assert uc.grad.shape == uc.shape
+    for got, ref, nm in zip(Wc + [x0c, uc], Wd + [x0d, ud], ["W1", "b1", "W2", "b2", "W3", "b3", "x0", "u"]):
+        assert rel_err(got.grad.cpu().numpy(), ref.grad.numpy(), floor=1.0) < 1e-4, nm

@@ -28,7 +28,7 @@ if os.environ.get("AB_CHILD"):
         e0.record()
         for _ in range(reps): out = fn()
         e1.record(); torch.cuda.synchronize()
-        print(f"N={N:7d} {os.environ.get('AB_NAME'):10s}: best {best:7.3f} ms  sustained {e0.elapsed_time(e1)/reps:7.3f} ms  "
+        print(f"N={N:7d} {os.environ.get('AB_NAME'):34s}: best {best:7.3f} ms  sustained {e0.elapsed_time(e1)/reps:7.3f} ms = {N*T/(e0.elapsed_time(e1)/reps*1e-3):.4e} steps/s  "
               f"chk {float(out[0].double().sum()):.10e} {float(out[1].double().abs().sum()):.10e}", flush=True)
         del u, tg
     sys.exit(0)
@@ -36,7 +36,12 @@ names = sys.argv[1].split(",")
 sizes = sys.argv[2] if len(sys.argv) > 2 else "227328,65536"
 for rep in range(2):
     for nm in names:
+        nm, _, own = nm.partition("#")        # name#N,N: this variant's own sizes
         env = dict(os.environ, AB_CHILD="1", AB_NAME=nm)
-        if nm != "new":
-            env["DYNAX_B200_LIB"] = os.path.join(ROOT, "dynax_b200", "_old", f"libdynax_{nm}.so")
-        subprocess.run([sys.executable, os.path.abspath(__file__), sizes], env=env)
+        lib, *sets = nm.split("@")          # e.g. new@DYNAX_FS_SPLIT=2@DYNAX_NO_TENSOR=1
+        for kv in sets:
+            k, v = kv.split("=")
+            env[k] = v
+        if lib != "new":
+            env["DYNAX_B200_LIB"] = os.path.join(ROOT, "dynax_b200", "_old", f"libdynax_{lib}.so")
+        subprocess.run([sys.executable, os.path.abspath(__file__), own or sizes], env=env)
