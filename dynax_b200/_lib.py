@@ -46,6 +46,7 @@ SIGNATURES = {
     "dynax_lti_vjp_f32": (_int, [_f] * 14 + [_i64, _i64, _int, _int, _int, _flt, _u32, _f, _sz, _f]),
     "dynax_rc_forward_host_f32": (_int, [_f] * 6 + [_i64, _i64, _flt, _u32, _i64]),
     "dynax_rc_loss_grad_host_f32": (_int, [_f] * 8 + [_i64, _i64, _flt, _u32, _i64]),
+    "dynax_nonfinite_rows_f32": (_int, [_f, _i64, _int, _f, _f, _f]),
     "dynax_host_release": (_int, []),
     "dynax_rc_dataset_create_f32": (_int, [_f, _f, _i64, _i64, _u32, ctypes.POINTER(ctypes.c_void_p)]),
     "dynax_rc_dataset_loss_grad_f32": (_int, [_f, _f, _f, _f, _f, _flt, _u32, _f, _f]),

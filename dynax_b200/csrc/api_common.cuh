@@ -2,6 +2,7 @@
 // launch helpers.
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -28,6 +29,14 @@ inline int fail(int code, const char *fmt, ...) {
             return ::dynax::fail(DYNAX_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), \
                                  __FILE__, __LINE__);                                            \
     } while (0)
+
+// NVTX range around every C-ABI entry point: shows up as "dynax_..." in Nsight Systems / ncu
+// --nvtx; header-only NVTX3, a no-op unless a tool is attached.
+struct ApiRange {
+    explicit ApiRange(const char *name) { nvtxRangePushA(name); }
+    ~ApiRange() { nvtxRangePop(); }
+};
+#define DYNAX_API_RANGE() ::dynax::ApiRange dynax_api_range_(__func__)
 
 // There is no CPU fallback: refuse to run unless the current device is Blackwell (cc 10.x).
 int require_sm100();

@@ -121,6 +121,7 @@ extern "C" int dynax_rc_env_step_f32(const float *theta, const float *x, const f
                                      float w_comfort, float u_low, float u_high, int num_actions, float *x_next,
                                      float *t_next, float *obs, float *reward, float *terminated, float *cost,
                                      float *dTz, int64_t N, int64_t K, float dt, uint32_t flags, void *stream) {
+    DYNAX_API_RANGE();
     if (N < 0 || K < 1) return fail(DYNAX_ERR_INVALID_ARGUMENT, "need N >= 0 and K >= 1");
     if (N == 0) return DYNAX_OK;
     if (!theta || !x || !t || !action || !ts || !dist || !price || !t_low || !t_high || !x_next || !t_next || !obs ||

@@ -101,6 +101,7 @@ int copy_tile(float *dst, size_t dpitch_f, const float *src, size_t spitch_f, in
 extern "C" {
 
 int dynax_host_release(void) {
+    DYNAX_API_RANGE();
     HostCtx &c = ctx();
     std::lock_guard<std::mutex> lk(c.mu);
     for (int b = 0; b < 2; ++b) {
@@ -114,6 +115,7 @@ int dynax_host_release(void) {
 
 int dynax_rc_forward_host_f32(const float *theta, const float *x0, const float *u, float *xsol, float *ysol,
                               float *x_final, int64_t N, int64_t T, float dt, uint32_t flags, int64_t tile_systems) {
+    DYNAX_API_RANGE();
     if (N < 0 || T < 0) return fail(DYNAX_ERR_INVALID_ARGUMENT, "negative N or T");
     if (N == 0) return DYNAX_OK;
     if (!theta || !x0 || (!u && T > 0)) return fail(DYNAX_ERR_INVALID_ARGUMENT, "theta, x0 and u must be non-NULL");
@@ -287,6 +289,7 @@ void dataset_free(RcDataset *d) {
 }  // namespace
 
 int dynax_rc_dataset_create_f32(const float *u, const float *target, int64_t N, int64_t T, uint32_t flags, void **handle) {
+    DYNAX_API_RANGE();
     if (!handle) return fail(DYNAX_ERR_INVALID_ARGUMENT, "handle must be non-NULL");
     *handle = nullptr;
     if (N < 1 || T < 1 || !u || !target) return fail(DYNAX_ERR_INVALID_ARGUMENT, "need N >= 1, T >= 1, u and target");
@@ -324,6 +327,7 @@ int dynax_rc_dataset_create_f32(const float *u, const float *target, int64_t N, 
 
 int dynax_rc_dataset_loss_grad_f32(void *handle, const float *theta, const float *x0, const float *lb, const float *ub,
                                    float dt, uint32_t flags, float *loss, float *g_theta) {
+    DYNAX_API_RANGE();
     RcDataset *d = static_cast<RcDataset *>(handle);
     if (!d || !theta || !x0 || !loss || !g_theta) return fail(DYNAX_ERR_INVALID_ARGUMENT, "handle, theta, x0, loss, g_theta must be non-NULL");
     if ((lb == nullptr) != (ub == nullptr)) return fail(DYNAX_ERR_INVALID_ARGUMENT, "lb and ub go together");
@@ -364,6 +368,7 @@ int dynax_rc_dataset_loss_grad_f32(void *handle, const float *theta, const float
 }
 
 int dynax_rc_dataset_destroy(void *handle) {
+    DYNAX_API_RANGE();
     dataset_free(static_cast<RcDataset *>(handle));
     return DYNAX_OK;
 }
@@ -372,6 +377,7 @@ int dynax_rc_dataset_destroy(void *handle) {
 // through its own pinned buffer at a fraction of the link rate).  Thin wrappers so that a host program that never
 // links the CUDA runtime can pin the arrays it passes to the *_host entry points again and again.
 int dynax_host_register(const void *ptr, size_t bytes) {
+    DYNAX_API_RANGE();
     if (!ptr || bytes == 0) return fail(DYNAX_ERR_INVALID_ARGUMENT, "ptr and bytes must be non-zero");
     TRY(require_sm100());
     DYNAX_CUDA_TRY(cudaHostRegister(const_cast<void *>(ptr), bytes, cudaHostRegisterDefault));
@@ -379,6 +385,7 @@ int dynax_host_register(const void *ptr, size_t bytes) {
 }
 
 int dynax_host_unregister(const void *ptr) {
+    DYNAX_API_RANGE();
     if (!ptr) return fail(DYNAX_ERR_INVALID_ARGUMENT, "ptr must be non-NULL");
     DYNAX_CUDA_TRY(cudaHostUnregister(const_cast<void *>(ptr)));
     return DYNAX_OK;
@@ -387,6 +394,7 @@ int dynax_host_unregister(const void *ptr) {
 int dynax_rc_loss_grad_host_f32(const float *theta, const float *x0, const float *u, const float *target,
                                 const float *lb, const float *ub, float *loss, float *g_theta, int64_t N,
                                 int64_t T, float dt, uint32_t flags, int64_t tile_systems) {
+    DYNAX_API_RANGE();
     return loss_grad_host_impl(theta, x0, u, nullptr, 0, target, lb, ub, loss, g_theta, N, T, dt, flags, tile_systems);
 }
 
@@ -394,6 +402,7 @@ int dynax_rc_loss_grad_ctrl_host_f32(const float *theta, const float *x0, const 
                                      int ctrl_col, const float *target, const float *lb, const float *ub, float *loss,
                                      float *g_theta, int64_t N, int64_t T, float dt, uint32_t flags,
                                      int64_t tile_systems) {
+    DYNAX_API_RANGE();
     if (!ctrl && N > 0) return fail(DYNAX_ERR_INVALID_ARGUMENT, "ctrl must be non-NULL");
     return loss_grad_host_impl(theta, x0, u_shared, ctrl, ctrl_col, target, lb, ub, loss, g_theta, N, T, dt, flags,
                                tile_systems);

@@ -70,6 +70,7 @@ int dynax_lti_supported(int n, int m, int p) {
 int dynax_lti_forward_f32(const float *A, const float *B, const float *C, const float *D, const float *x0,
                           const float *u, float *xsol, float *ysol, float *x_final, int64_t N, int64_t T, int n,
                           int m, int p, float dt, uint32_t flags, void *stream) {
+    DYNAX_API_RANGE();
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (N < 0 || T < 0) return fail(DYNAX_ERR_INVALID_ARGUMENT, "negative N or T");
     if (N == 0) return DYNAX_OK;
@@ -107,6 +108,7 @@ int dynax_lti_vjp_f32(const float *A, const float *B, const float *C, const floa
                       const float *u, const float *g_xsol, const float *g_ysol, float *g_A, float *g_B, float *g_C,
                       float *g_D, float *g_x0, float *g_u, int64_t N, int64_t T, int n, int m, int p, float dt,
                       uint32_t flags, void *ws, size_t ws_bytes, void *stream) {
+    DYNAX_API_RANGE();
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (N < 0 || T < 1) return fail(DYNAX_ERR_INVALID_ARGUMENT, "need N >= 0 and T >= 1");
     if (N == 0) return DYNAX_OK;

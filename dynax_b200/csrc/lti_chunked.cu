@@ -381,6 +381,7 @@ size_t dynax_rc_forward_chunked_workspace(int64_t N, int64_t T, int64_t chunk_le
 int dynax_rc_forward_chunked_f32(const float *theta, const float *x0, const float *u, float *xsol, float *ysol,
                                  float *x_final, int64_t N, int64_t T, float dt, uint32_t flags, int64_t chunk_len,
                                  void *ws, size_t ws_bytes, void *stream) {
+    DYNAX_API_RANGE();
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (N < 0 || T < 1) return fail(DYNAX_ERR_INVALID_ARGUMENT, "need N >= 0 and T >= 1");
     if (N == 0) return DYNAX_OK;
@@ -418,6 +419,7 @@ int dynax_lti_forward_chunked_f32(const float *A, const float *B, const float *C
                                   const float *u, float *xsol, float *ysol, float *x_final, int64_t N, int64_t T, int n,
                                   int m, int p, float dt, uint32_t flags, int64_t chunk_len, void *ws, size_t ws_bytes,
                                   void *stream) {
+    DYNAX_API_RANGE();
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (N < 0 || T < 0) return fail(DYNAX_ERR_INVALID_ARGUMENT, "negative N or T");
     if (N == 0) return DYNAX_OK;
@@ -471,6 +473,7 @@ size_t dynax_rc_vjp_chunked_workspace(int64_t N, int64_t T, int64_t chunk_len) {
 int dynax_rc_vjp_chunked_f32(const float *theta, const float *x0, const float *u, const float *g_xsol,
                              const float *g_ysol, float *g_theta, float *g_x0, float *g_u, int64_t N, int64_t T,
                              float dt, uint32_t flags, int64_t chunk_len, void *ws, size_t ws_bytes, void *stream) {
+    DYNAX_API_RANGE();
     if (N < 0 || T < 1) return fail(DYNAX_ERR_INVALID_ARGUMENT, "need N >= 0 and T >= 1");
     if (N == 0) return DYNAX_OK;
     if (!theta || !x0 || !u) return fail(DYNAX_ERR_INVALID_ARGUMENT, "theta, x0 and u must be non-NULL");
@@ -496,6 +499,7 @@ int dynax_lti_vjp_chunked_f32(const float *A, const float *B, const float *C, co
                               float *g_C, float *g_D, float *g_x0, float *g_u, int64_t N, int64_t T, int n, int m,
                               int p, float dt, uint32_t flags, int64_t chunk_len, void *ws, size_t ws_bytes,
                               void *stream) {
+    DYNAX_API_RANGE();
     if (N < 0 || T < 1) return fail(DYNAX_ERR_INVALID_ARGUMENT, "need N >= 0 and T >= 1");
     if (N == 0) return DYNAX_OK;
     if (!A || !B || !C || !D || !x0 || !u) return fail(DYNAX_ERR_INVALID_ARGUMENT, "A,B,C,D,x0,u must be non-NULL");
@@ -530,6 +534,7 @@ int dynax_rc_loss_grad_chunked_f32(const float *theta, const float *x0, const fl
                                    const float *lb, const float *ub, float *loss, float *g_theta, float *g_x0,
                                    int64_t N, int64_t T, float dt, uint32_t flags, int64_t chunk_len, void *ws,
                                    size_t ws_bytes, void *stream) {
+    DYNAX_API_RANGE();
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (N < 0 || T < 1) return fail(DYNAX_ERR_INVALID_ARGUMENT, "need N >= 0 and T >= 1");
     if (N == 0) return DYNAX_OK;

@@ -174,6 +174,7 @@ extern "C" int dynax_rc_mpc_cost_f32(const float *theta, const float *x0, const 
                                      float w_energy, float w_comfort, float start_time, float *cost,
                                      long long *argmin, float *min_cost, int64_t N, int64_t H, float dt, void *ws,
                                      size_t ws_bytes, void *stream) {
+    DYNAX_API_RANGE();
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (N < 0 || H < 1) return fail(DYNAX_ERR_INVALID_ARGUMENT, "need N >= 0 and H >= 1");
     if (N == 0) return DYNAX_OK;

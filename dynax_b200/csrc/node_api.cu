@@ -13,6 +13,7 @@ extern "C" int dynax_node_rk4_forward_f32(const float *W1, const float *b1, cons
                                           const float *W3, const float *b3, const float *x0, const float *u,
                                           float *xsol, float *ysol, float *x_final, int64_t N, int64_t T, int n,
                                           int m, int p, int hidden, float dt, uint32_t flags, void *stream) {
+    DYNAX_API_RANGE();
     return dynax_node_rk4_forward_stages_f32(W1, b1, W2, b2, W3, b3, x0, u, xsol, ysol, x_final, nullptr, N, T, n, m, p,
                                              hidden, dt, flags, stream);
 }
@@ -22,6 +23,7 @@ extern "C" int dynax_node_rk4_forward_stages_f32(const float *W1, const float *b
                                                  float *xsol, float *ysol, float *x_final, float *stage_x, int64_t N,
                                                  int64_t T, int n, int m, int p, int hidden, float dt, uint32_t flags,
                                                  void *stream) {
+    DYNAX_API_RANGE();
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (N < 0 || T < 0) return fail(DYNAX_ERR_INVALID_ARGUMENT, "negative N or T");
     if (N == 0) return DYNAX_OK;

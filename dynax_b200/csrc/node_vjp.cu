@@ -300,6 +300,7 @@ int dynax_node_rk4_vjp_f32(const float *W1, const float *b1, const float *W2, co
                            const float *g_ysol, float *gW1, float *gb1, float *gW2, float *gb2, float *gW3, float *gb3,
                            float *g_x0, float *g_u, int64_t N, int64_t T, int n, int m, int p, int hidden, float dt,
                            uint32_t flags, void *ws, size_t ws_bytes, void *stream) {
+    DYNAX_API_RANGE();
     return dynax_node_rk4_vjp_stages_f32(W1, b1, W2, b2, W3, b3, x0, u, xsol, nullptr, g_xsol, g_ysol, gW1, gb1, gW2, gb2,
                                          gW3, gb3, g_x0, g_u, N, T, n, m, p, hidden, dt, flags, ws, ws_bytes, stream);
 }
@@ -310,6 +311,7 @@ int dynax_node_rk4_vjp_stages_f32(const float *W1, const float *b1, const float 
                                   float *gW2, float *gb2, float *gW3, float *gb3, float *g_x0, float *g_u, int64_t N,
                                   int64_t T, int n, int m, int p, int hidden, float dt, uint32_t flags, void *ws,
                                   size_t ws_bytes, void *stream) {
+    DYNAX_API_RANGE();
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (N < 0 || T < 1) return fail(DYNAX_ERR_INVALID_ARGUMENT, "need N >= 0 and T >= 1");
     if (N == 0) return DYNAX_OK;

@@ -70,10 +70,27 @@ __global__ void resample_mean_kernel(const float *in, float *out, int64_t rows, 
 
 using namespace dynax;
 
+namespace dynax {
+// Per-system non-finite guard: x + dt*rhs can blow up inside the parameter box of
+// examples/3-inverse.py:66-85 (dt*|lambda| > 2), and the caller should learn it from a flag, not from an inf loss
+// three calls later.  flags[i] = 1 if any of the `width` values of row i is NaN/Inf; *count += number of such rows.
+__global__ void nonfinite_rows_kernel(const float *a, int64_t rows, int width, int32_t *flags, int *count) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int bad = 0;
+    if (i < rows) {
+        for (int j = 0; j < width; ++j) bad |= !isfinite(a[i * width + j]);
+        if (flags) flags[i] = bad;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0 && m && count) atomicAdd(count, __popc(m));
+}
+}  // namespace dynax
+
 extern "C" {
 
 int dynax_lamb_update_f32(float *theta, const float *grad, float *m, float *v, int64_t n, int64_t step, float lr,
                           float b1, float b2, float eps, void *stream) {
+    DYNAX_API_RANGE();
     if (n < 0 || step < 1) return fail(DYNAX_ERR_INVALID_ARGUMENT, "need n >= 0 and step >= 1");
     if (n == 0) return DYNAX_OK;
     if (!theta || !grad || !m || !v) return fail(DYNAX_ERR_INVALID_ARGUMENT, "theta, grad, m, v must be non-NULL");
@@ -89,6 +106,7 @@ int dynax_lamb_update_f32(float *theta, const float *grad, float *m, float *v, i
 
 int dynax_lamb_update_dev_f32(float *theta, const float *grad, float *m, float *v, int64_t n, int64_t *step_counter,
                               float lr, float b1, float b2, float eps, void *stream) {
+    DYNAX_API_RANGE();
     if (n < 0) return fail(DYNAX_ERR_INVALID_ARGUMENT, "need n >= 0");
     if (n == 0) return DYNAX_OK;
     if (!theta || !grad || !m || !v || !step_counter) return fail(DYNAX_ERR_INVALID_ARGUMENT, "NULL argument");
@@ -104,6 +122,7 @@ int dynax_lamb_update_dev_f32(float *theta, const float *grad, float *m, float *
 }
 
 int dynax_resample_mean_f32(const float *in, float *out, int64_t rows, int cols, int64_t factor, void *stream) {
+    DYNAX_API_RANGE();
     if (rows < 0 || cols < 1 || factor < 1) return fail(DYNAX_ERR_INVALID_ARGUMENT, "need rows >= 0, cols >= 1, factor >= 1");
     if (rows == 0) return DYNAX_OK;
     if (!in || !out) return fail(DYNAX_ERR_INVALID_ARGUMENT, "in and out must be non-NULL");
@@ -113,6 +132,22 @@ int dynax_resample_mean_f32(const float *in, float *out, int64_t rows, int cols,
     const int tb = 256;
     resample_mean_kernel<<<(unsigned)((out_rows * cols + tb - 1) / tb), tb, 0, static_cast<cudaStream_t>(stream)>>>(
         in, out, rows, cols, factor, out_rows);
+    DYNAX_CUDA_TRY(cudaGetLastError());
+    return DYNAX_OK;
+}
+
+int dynax_nonfinite_rows_f32(const float *a, int64_t rows, int width, int32_t *flags, int *count, void *stream) {
+    DYNAX_API_RANGE();
+    if (rows < 0 || width < 1) return fail(DYNAX_ERR_INVALID_ARGUMENT, "need rows >= 0 and width >= 1");
+    if (!a && rows > 0) return fail(DYNAX_ERR_INVALID_ARGUMENT, "a must be non-NULL");
+    if (!flags && !count) return fail(DYNAX_ERR_INVALID_ARGUMENT, "need flags or count");
+    int rc = require_sm100();
+    if (rc != DYNAX_OK) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (count) DYNAX_CUDA_TRY(cudaMemsetAsync(count, 0, sizeof(int), st));
+    if (rows == 0) return DYNAX_OK;
+    const int tb = 256;
+    nonfinite_rows_kernel<<<(unsigned)((rows + tb - 1) / tb), tb, 0, st>>>(a, rows, width, flags, count);
     DYNAX_CUDA_TRY(cudaGetLastError());
     return DYNAX_OK;
 }

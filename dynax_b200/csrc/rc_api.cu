@@ -195,14 +195,18 @@ static int rc_adjoint(const float *theta, const float *x0, const float *u, const
         F.bulk = (N % 4) == 0 && (su || aligned16(u)) && (stg || aligned16(target)) && (!ctrl || aligned16(ctrl)) &&
                  !env_int("DYNAX_NO_BULK", 0);
         // Tile shape.  Every CTA runs the whole horizon, so a launch costs (waves x systems per CTA):
-        //   * launches far too small to fill the GPU with one thread per system (N <= 32 systems per SM) give every
-        //     system 2 threads, each owning a subset of the sensitivity columns (SPLIT, rc_fwdsens.cuh; N = 4096,
-        //     T = 8760: 0.72 vs 0.84 ms); 4 threads per system (32-system CTAs) are instantiated but not selected:
-        //     their 640-byte rows cost as much per bulk copy as 2.5 KB ones, and the copies bound the launch;
+        //   * launches that fit one 64-system CTA per SM (N <= 9472; BASELINE.json config 3 sharded over 8 GPUs is 8192
+        //     systems per rank) give every system 2 threads, each owning a subset of the sensitivity columns (SPLIT,
+        //     rc_fwdsens.cuh), with 64-row chunks rolled 8 steps at a time: such a launch runs ONE warp per scheduler,
+        //     so the serial chain of 8760 steps and the per-chunk hand-shakes bound it (N = 8192, T = 8760, same box:
+        //     round-1 kernel 0.87 ms; + tensor maps 0.73; + 2 threads per system 0.57; + 64-row chunks 0.50 ms).
+        //     Measured and NOT kept (profiles/r02_small_launch_sweep.txt): 4 threads per system (x is stepped 4 times
+        //     per system: 0.61-0.70 ms), row prefetch into registers (0.63-0.70), unpredicated chunk bodies (0.66),
+        //     32-system CTAs (0.81);
         //   * up to sm_count x 128 systems with a control channel or d loss / d x0: 128-system CTAs, 16-row chunks;
         //   * 224-system CTAs when they save a wave (N = 65536: 293 CTAs fill the 296 slots once, 256 CTAs of 256
         //     leave 40 SMs half empty);   * else 256-system CTAs, 2 per SM (5 KB per TMA row copy).
-        // DYNAX_FS_CFG: 2 = always 128-wide, 3 = always 256-wide; DYNAX_FS_SPLIT: 1, 2 or 4 forces the threads per system.
+        // DYNAX_FS_CFG: 2 = always 128-wide, 3 = always 256-wide; DYNAX_FS_SPLIT: 1 or 2 forces the threads per system.
         DeviceInfo di;
         rc = device_info(&di);
         if (rc != DYNAX_OK) return rc;
@@ -211,7 +215,7 @@ static int rc_adjoint(const float *theta, const float *x0, const float *u, const
         const int cfg = env_int("DYNAX_FS_CFG", 0);
         int split = env_int("DYNAX_FS_SPLIT", 0);
         if (ctrl || g_x0) split = 1;
-        else if (split != 1 && split != 2 && split != 4) split = (cfg != 0) ? 1 : (N <= slots * 16) ? 2 : 1;
+        else if (split != 1 && split != 2) split = (cfg != 0) ? 1 : (N <= (int64_t)di.sm_count * 64) ? 2 : 1;
         int tn = 256;
         if (cfg == 2 || (cfg == 0 && (N + 127) / 128 <= di.sm_count)) tn = 128;
         else if (cfg == 0 && cost(224) < cost(256)) tn = 224;
@@ -223,30 +227,8 @@ static int rc_adjoint(const float *theta, const float *x0, const float *u, const
                       : tn == 224 ? launch_fwdsens<224, 8, 2, 2, 1, SU, STG, CTRL>(F, st)               \
                                   : launch_fwdsens<256, 8, 2, 2, 1, SU, STG, CTRL>(F, st))
 #define DYNAX_FS_LAUNCH_SPLIT(SU, STG)                                                                \
-    (split == 4 ? launch_fwdsens<32, 16, 3, 4, 4, SU, STG>(F, st)                                       \
-                : split == 2 ? launch_fwdsens<64, 16, 3, 4, 2, SU, STG>(F, st) : DYNAX_FS_LAUNCH(SU, STG, false))
-#ifdef DYNAX_FS_EXPERIMENTS   // tile-shape sweep for launches that cannot fill the GPU (tools/ab_tangent3.py)
-        if (!ctrl && !g_x0 && !su && !stg) {
-            switch (env_int("DYNAX_FS_EXP", 0)) {
-#define FSX(...) launch_fwdsens<__VA_ARGS__>(F, st)
-                case 1: return FSX(64, 16, 3, 2, 2, false, false, false, false, false, false);
-                case 2: return FSX(64, 8, 4, 2, 4, false, false, false, false, false, false);
-                case 3: return FSX(64, 16, 3, 1, 4, false, false, false, false, false, false);
-                case 4: return FSX(128, 16, 2, 2, 1, false, false, false, false, false, false);
-                case 5: return FSX(64, 8, 4, 2, 2, false, false, false, false, false, false);
-                case 6: return FSX(32, 16, 3, 4, 4, false, false, false, false, false, false);
-                case 7: return FSX(32, 16, 6, 4, 2, false, false, false, false, false, false);
-                case 30: return FSX(224, 4, 2, 3, 1);
-                case 31: return FSX(192, 6, 2, 3, 1);
-                case 32: return FSX(192, 4, 3, 3, 1);
-                case 34: return FSX(256, 4, 3, 2, 1);
-                case 35: return FSX(224, 8, 2, 2, 1);
-                case 36: return FSX(256, 8, 2, 2, 1, false, false, false, false, false, false);
-#undef FSX
-                default: break;
-            }
-        }
-#endif
+    (split == 2 ? launch_fwdsens<64, 64, 2, 1, 2, SU, STG, false, false, false, true, false, 8>(F, st) \
+                : DYNAX_FS_LAUNCH(SU, STG, false))
         if (ctrl && stg) return DYNAX_FS_LAUNCH(true, true, true);
         if (ctrl) return DYNAX_FS_LAUNCH(true, false, true);
         if (su && stg) return DYNAX_FS_LAUNCH_SPLIT(true, true);
@@ -337,12 +319,14 @@ size_t dynax_workspace_bytes(int op, int64_t N, int64_t T, int n, int m, int p, 
 
 int dynax_rc_forward_f32(const float *theta, const float *x0, const float *u, float *xsol, float *ysol,
                          float *x_final, int64_t N, int64_t T, float dt, uint32_t flags, void *stream) {
+    DYNAX_API_RANGE();
     return rc_forward(theta, x0, u, xsol, ysol, x_final, N, T, dt, flags, static_cast<cudaStream_t>(stream));
 }
 
 int dynax_rc_loss_grad_f32(const float *theta, const float *x0, const float *u, const float *target,
                            const float *lb, const float *ub, float *loss, float *g_theta, float *g_x0, int64_t N,
                            int64_t T, float dt, uint32_t flags, void *ws, size_t ws_bytes, void *stream) {
+    DYNAX_API_RANGE();
     return rc_adjoint<ADJ_MSE>(theta, x0, u, target, lb, ub, nullptr, nullptr, loss, g_theta, g_x0, nullptr, N, T, dt,
                                flags, ws, ws_bytes, static_cast<cudaStream_t>(stream));
 }
@@ -350,6 +334,7 @@ int dynax_rc_loss_grad_f32(const float *theta, const float *x0, const float *u, 
 int dynax_rc_forward_ctrl_f32(const float *theta, const float *x0, const float *u_shared, const float *ctrl,
                               int ctrl_col, float *xsol, float *ysol, float *x_final, int64_t N, int64_t T, float dt,
                               uint32_t flags, void *stream) {
+    DYNAX_API_RANGE();
     if (!ctrl && N > 0 && T > 0) return fail(DYNAX_ERR_INVALID_ARGUMENT, "ctrl must be non-NULL");
     return rc_forward(theta, x0, u_shared, xsol, ysol, x_final, N, T, dt, flags | DYNAX_SHARED_U,
                       static_cast<cudaStream_t>(stream), ctrl, ctrl_col);
@@ -359,6 +344,7 @@ int dynax_rc_loss_grad_ctrl_f32(const float *theta, const float *x0, const float
                                 int ctrl_col, const float *target, const float *lb, const float *ub, float *loss,
                                 float *g_theta, float *g_x0, int64_t N, int64_t T, float dt, uint32_t flags, void *ws,
                                 size_t ws_bytes, void *stream) {
+    DYNAX_API_RANGE();
     if (!ctrl && N > 0) return fail(DYNAX_ERR_INVALID_ARGUMENT, "ctrl must be non-NULL");
     return rc_adjoint<ADJ_MSE>(theta, x0, u_shared, target, lb, ub, nullptr, nullptr, loss, g_theta, g_x0, nullptr, N, T,
                                dt, flags | DYNAX_SHARED_U, ws, ws_bytes, static_cast<cudaStream_t>(stream), ctrl, ctrl_col);
@@ -367,6 +353,7 @@ int dynax_rc_loss_grad_ctrl_f32(const float *theta, const float *x0, const float
 int dynax_rc_vjp_f32(const float *theta, const float *x0, const float *u, const float *g_xsol, const float *g_ysol,
                      float *g_theta, float *g_x0, float *g_u, int64_t N, int64_t T, float dt, uint32_t flags,
                      void *ws, size_t ws_bytes, void *stream) {
+    DYNAX_API_RANGE();
     return rc_adjoint<ADJ_VJP>(theta, x0, u, nullptr, nullptr, nullptr, g_xsol, g_ysol, nullptr, g_theta, g_x0, g_u, N,
                                T, dt, flags, ws, ws_bytes, static_cast<cudaStream_t>(stream));
 }

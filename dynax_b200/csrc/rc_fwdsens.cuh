@@ -100,7 +100,8 @@ __host__ __device__ constexpr unsigned fs_pair_mask(int split, int role, bool gx
 }
 __host__ __device__ constexpr bool fs_has_c(int split, int role, bool gx0) { return !gx0 && role == split - 1; }
 
-template <int TN, int KF, int S, int SPLIT, int ROLE, bool SHARED_U, bool SHARED_TGT, bool CTRL, bool GX0, bool CHUNK, bool PRED>
+template <int TN, int KF, int S, int SPLIT, int ROLE, bool SHARED_U, bool SHARED_TGT, bool CTRL, bool GX0, bool CHUNK, bool PRED,
+          bool PREFETCH, int UNR>
 __device__ __forceinline__ void fs_consumer(const FwdSensParams &P, unsigned char *smem_raw, float *s_in, uint64_t *full,
                                             uint64_t *empty, const int sys, const int64_t n0, const int valid,
                                             const int64_t cidx, const int T, const int C) {
@@ -167,15 +168,24 @@ __device__ __forceinline__ void fs_consumer(const FwdSensParams &P, unsigned cha
     float p0 = 1.f, p1 = 0.f, p2 = 0.f, w0 = 0.f, w1 = 0.f, w2 = 0.f;
 
     const float *in = nullptr, *tg = nullptr;
-    auto step = [&](const int jj) {
-        float u0 = in[jj * Cfg::U_ROW], u1 = in[jj * Cfg::U_ROW + 1], u2 = in[jj * Cfg::U_ROW + 2],
-              u3 = in[jj * Cfg::U_ROW + 3], u4 = in[jj * Cfg::U_ROW + 4];
+    struct Row {
+        float u0, u1, u2, u3, u4, t;
+    };
+    auto load_row = [&](const int jj) {
+        Row r;
+        r.u0 = in[jj * Cfg::U_ROW]; r.u1 = in[jj * Cfg::U_ROW + 1]; r.u2 = in[jj * Cfg::U_ROW + 2];
+        r.u3 = in[jj * Cfg::U_ROW + 3]; r.u4 = in[jj * Cfg::U_ROW + 4];
         if constexpr (CTRL) {  // inputs assembled as in wrapper/envs/rc.py:128-131
             const float cv = tg[Cfg::T_STAGE + (SHARED_TGT ? sys : 0) + jj * TN];
-            u0 = ccol == 0 ? cv : u0; u1 = ccol == 1 ? cv : u1; u2 = ccol == 2 ? cv : u2;
-            u3 = ccol == 3 ? cv : u3; u4 = ccol == 4 ? cv : u4;
+            r.u0 = ccol == 0 ? cv : r.u0; r.u1 = ccol == 1 ? cv : r.u1; r.u2 = ccol == 2 ? cv : r.u2;
+            r.u3 = ccol == 3 ? cv : r.u3; r.u4 = ccol == 4 ? cv : r.u4;
         }
-        const float res = X01.x - tg[jj * Cfg::T_ROW];   // PRE-update state (simulator.py:38)
+        r.t = tg[jj * Cfg::T_ROW];
+        return r;
+    };
+    auto step = [&](const Row &row) {
+        const float u0 = row.u0, u1 = row.u1, u2 = row.u2, u3 = row.u3, u4 = row.u4;
+        const float res = X01.x - row.t;   // PRE-update state (simulator.py:38)
         if constexpr (LOSS_ROLE) sq = fmaf(res, res, sq);
         const float gy = c2T * res;
         const float2 gy2 = make_float2(gy, gy);
@@ -311,9 +321,23 @@ __device__ __forceinline__ void fs_consumer(const FwdSensParams &P, unsigned cha
         ptx::mbar_wait(&full[s], (uint32_t)((c / S) & 1));
         in = s_in + s * Cfg::STAGE + (SHARED_U ? 0 : sys * 5);
         tg = s_in + s * Cfg::STAGE + Cfg::U_STAGE + (SHARED_TGT ? 0 : sys);
-#pragma unroll
-        for (int jj = 0; jj < KF; ++jj)
-            if (jj < rows) step(jj);
+        if constexpr (PREFETCH) {
+            // a launch with one warp per scheduler cannot hide the shared-memory latency of a step's loads behind other
+            // warps, and the per-row predicates keep ptxas from hoisting them: fetch row j+1 while row j computes
+            Row nxt = load_row(0);
+#pragma unroll UNR
+            for (int jj = 0; jj < KF; ++jj) {
+                if (jj < rows) {
+                    const Row cur = nxt;
+                    if (jj + 1 < rows) nxt = load_row(jj + 1);
+                    step(cur);
+                }
+            }
+        } else {
+#pragma unroll UNR
+            for (int jj = 0; jj < KF; ++jj)
+                if (jj < rows) step(load_row(jj));
+        }
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&empty[s]);
         if ((c + 1) % FOLDC == 0 || c + 1 == C) {
@@ -363,7 +387,7 @@ __device__ __forceinline__ void fs_consumer(const FwdSensParams &P, unsigned cha
         in = s_in + (SHARED_U ? 0 : sys * 5);
         tg = s_in + Cfg::U_STAGE + (SHARED_TGT ? 0 : sys);
 #pragma unroll 1
-        for (int jj = 0; jj < r0; ++jj) step(jj);
+        for (int jj = 0; jj < r0; ++jj) step(load_row(jj));
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&empty[0]);
     }
@@ -373,9 +397,7 @@ __device__ __forceinline__ void fs_consumer(const FwdSensParams &P, unsigned cha
         in = s_in + s * Cfg::STAGE + (SHARED_U ? 0 : sys * 5);
         tg = s_in + s * Cfg::STAGE + Cfg::U_STAGE + (SHARED_TGT ? 0 : sys);
 #pragma unroll
-        for (int jj = 0; jj < KF; ++jj) {
-            step(jj);
-        }
+        for (int jj = 0; jj < KF; ++jj) step(load_row(jj));
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&empty[s]);
         if (c % FOLDC == 0) fold();
@@ -459,7 +481,7 @@ __device__ __forceinline__ void fs_consumer(const FwdSensParams &P, unsigned cha
 }
 
 template <int TN, int KF, int S, int MINB, int SPLIT = 1, bool SHARED_U = false, bool SHARED_TGT = false,
-          bool CTRL = false, bool GX0 = false, bool CHUNK = false, bool PRED = true>
+          bool CTRL = false, bool GX0 = false, bool CHUNK = false, bool PRED = true, bool PREFETCH = false, int UNR = KF>
 __global__ void __launch_bounds__(TN * SPLIT + 32, MINB) rc_fwdsens_kernel(const __grid_constant__ FwdSensParams P) {
     static_assert(!CTRL || SHARED_U, "the control channel replaces a column of a SHARED input series");
     static_assert(!CHUNK || (!GX0 && !CTRL), "time-chunked launches use the plain kernel");
@@ -583,8 +605,8 @@ __global__ void __launch_bounds__(TN * SPLIT + 32, MINB) rc_fwdsens_kernel(const
     // --------------------------------- consumers: role = warp-uniform ---------------------------------
     const int role = SPLIT == 1 ? 0 : tid / TN, sys = SPLIT == 1 ? tid : tid % TN;
 #define DYNAX_FS_ROLE(R)                                                                                         \
-    fs_consumer<TN, KF, S, SPLIT, R, SHARED_U, SHARED_TGT, CTRL, GX0, CHUNK, PRED>(P, smem_raw, s_in, full, empty, sys, \
-                                                                                   n0, valid, cidx, T, C)
+    fs_consumer<TN, KF, S, SPLIT, R, SHARED_U, SHARED_TGT, CTRL, GX0, CHUNK, PRED, PREFETCH, UNR>(                      \
+        P, smem_raw, s_in, full, empty, sys, n0, valid, cidx, T, C)
     if constexpr (SPLIT == 1) {
         DYNAX_FS_ROLE(0);
     } else if constexpr (SPLIT == 2) {

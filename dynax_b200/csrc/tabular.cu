@@ -54,6 +54,7 @@ using namespace dynax;
 
 extern "C" int dynax_tabular_interp_f32(const float *ts, const float *xs, int64_t n_rows, int n_cols, const float *at,
                                         int64_t n_at, int mode, float *out, void *stream) {
+    DYNAX_API_RANGE();
     if (n_at < 0 || n_rows < 1 || n_cols < 1) return fail(DYNAX_ERR_INVALID_ARGUMENT, "need n_rows >= 1, n_cols >= 1, n_at >= 0");
     if (mode != 0 && mode != 1) return fail(DYNAX_ERR_INVALID_ARGUMENT, "mode must be 0 (constant/nearest) or 1 (linear)");
     if (n_at == 0) return DYNAX_OK;

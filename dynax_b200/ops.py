@@ -588,6 +588,20 @@ def lamb_update_dev_(theta, grad, m, v, step_counter, lr=1e-3, b1=0.9, b2=0.999,
     return theta
 
 
+def nonfinite_rows(a):
+    """Per-system non-finite guard for any per-system output a[N, ...] (loss, x_final, gradients): returns
+    (flags int32[N], count 0-d int32) -- flags[i] = 1 if system i holds a NaN/Inf.  Euler can blow up inside the
+    parameter box of examples/3-inverse.py:66-85; check after a rollout instead of discovering an inf loss later."""
+    a = _f32c(a, "a")
+    rows = a.shape[0] if a.dim() > 0 else 1
+    width = max(1, a.numel() // max(rows, 1))
+    flags = torch.empty((rows,), dtype=torch.int32, device=a.device)
+    count = torch.empty((), dtype=torch.int32, device=a.device)
+    with torch.cuda.device(a.device):
+        check(lib().dynax_nonfinite_rows_f32(_ptr(a), rows, width, _ptr(flags), _ptr(count), _stream()))
+    return flags, count
+
+
 def resample_mean(x, factor):
     """``data.groupby(index // factor).mean()`` (examples/1-forward.py:26-27) for x[rows, cols] on the device."""
     x = _f32c(x, "x")
@@ -640,7 +654,8 @@ class _NodeRollout(torch.autograd.Function):
     def forward(ctx, W1, b1, W2, b2, W3, b3, x0, u, dt, euler):
         # the stage points cost 36 B per trajectory-step; they are kept only when a gradient can be asked for
         want = any(t.requires_grad for t in (W1, b1, W2, b2, W3, b3, x0, u))
-        xsol, ysol, _, stages = node_rk4_forward(W1, b1, W2, b2, W3, b3, x0, u, dt, euler=euler, emit_stages=want)
+        out = node_rk4_forward(W1, b1, W2, b2, W3, b3, x0, u, dt, euler=euler, emit_stages=want)
+        xsol, ysol, stages = out[0], out[1], (out[3] if want else None)
         ctx.save_for_backward(W1, b1, W2, b2, W3, b3, x0, u, xsol, *([stages] if stages is not None else []))
         ctx.dt, ctx.euler = dt, euler
         return xsol, ysol

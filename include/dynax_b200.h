@@ -293,6 +293,12 @@ int dynax_lamb_update_dev_f32(float *theta, const float *grad, float *m, float *
                               float lr, float b1, float b2, float eps, void *stream);
 int dynax_resample_mean_f32(const float *in, float *out, int64_t rows, int cols, int64_t factor, void *stream);
 
+/* Non-finite guard: explicit Euler is only conditionally stable, and the parameter box of examples/3-inverse.py:66-85
+ * contains corners where x + dt*rhs blows up (dt*|lambda| > 2).  For any per-system output a[rows,width] (loss[N,1],
+ * x_final[N,3], g_theta[N,7] ...): flags[i] = 1 if row i holds a NaN/Inf (int32[rows] or NULL), *count = number of such
+ * rows (device int or NULL).  No reference counterpart (there the caller sees an inf loss). */
+int dynax_nonfinite_rows_f32(const float *a, int64_t rows, int width, int32_t *flags, int *count, void *stream);
+
 /* ---- Host-buffer entry points (the call a reference user makes with NumPy/JAX-CPU arrays):
  *      pageable or pinned HOST pointers in, results in HOST buffers on return.  The system axis is
  *      processed in tiles of `tile_systems` (0 = library default) with copies overlapped. ------ */

@@ -21,13 +21,13 @@ def lib(native=False):
     if _LIB is not None:
         return _LIB
     names = (["libdynax_oracle_native.so"] if native else []) + ["libdynax_oracle.so"]
-    if native and not os.path.exists(os.path.join(_DIR, names[0])):
+    # make rebuilds whatever is older than dynax_oracle.c (a stale .so travels to the GPU box with the snapshot)
+    for tgt in (["native"] if native else []) + ["all"]:
         try:
-            build(native=True)
+            build(native=(tgt == "native"))
         except Exception:
-            pass
-    if not os.path.exists(os.path.join(_DIR, "libdynax_oracle.so")):
-        build()
+            if tgt == "all" and not os.path.exists(os.path.join(_DIR, "libdynax_oracle.so")):
+                raise
     for nm in names:
         path = os.path.join(_DIR, nm)
         if os.path.exists(path):

@@ -65,3 +65,23 @@ def test_no_out_of_bounds_writes(N, Tn):
     ar.check()
     assert bool(torch.isfinite(xs).all()) and bool(torch.isfinite(grad).all()) and bool(torch.isfinite(gu).all())
     assert bool(torch.isfinite(grad3).all()) and bool(torch.isfinite(xn).all())
+
+
+def test_nonfinite_rows_flags_unstable_systems():
+    """A parameter vector from the unstable corner of the box (Cai = 3e3, Ri = 0.5: dt*|lambda| = 2.6 > 2, SURVEY.md
+    H3) blows up; dynax_nonfinite_rows_f32 names the systems, the others stay finite."""
+    import torch
+    from dynax_b200 import ops
+    from oracle import dynax_oracle as orc
+    N, Tn = 300, 600
+    th, x0, u = orc.synth_theta(N, 91), orc.synth_x0(N, 91), orc.synth_u(Tn, N, 91)
+    bad = [3, 77, 299]
+    th[bad, 0] = 3.0e3; th[bad, 4] = 0.5
+    c = lambda a: torch.tensor(np.ascontiguousarray(a, dtype=np.float32)).cuda()
+    _, _, xf = ops.rc_forward(c(th), c(x0), c(u), 3600.0, emit_x=False, emit_y=False, emit_final=True, time_chunks=0)
+    flags, count = ops.nonfinite_rows(xf)
+    assert count.item() == len(bad) and flags.nonzero().flatten().tolist() == bad
+    tg = (22 + np.random.default_rng(5).normal(size=(Tn, N))).astype(np.float32)
+    loss, grad, _ = ops.rc_loss_grad(c(th), c(x0), c(u), c(tg), 3600.0, time_chunks=0)
+    assert ops.nonfinite_rows(loss)[0].nonzero().flatten().tolist() == bad
+    assert ops.nonfinite_rows(grad)[1].item() == len(bad)

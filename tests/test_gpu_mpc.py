@@ -110,3 +110,29 @@ def test_four_candidates_per_thread_matches_one(T, monkeypatch):
     ur = u[:, :N + 3].contiguous()                             # N % 4 == 3: one candidate per thread
     cr, ar, _ = ops.rc_mpc_cost(*args, ur, *sched(T), 900.0, start_time=5 * 3600.0)
     assert T.equal(cr[:N], c4) and ar.item() == int(T.argmin(cr).item())
+
+
+def test_config4_full_size(T):
+    """BASELINE.json config 4 as stated: N = 2^22 candidate control sequences, 96-step (15-min, 24 h) horizon through
+    one shared model.  Properties that do not depend on the size -- argmin/min agree with a torch reduction of the cost
+    vector, splitting the candidate axis in two gives the same costs bit for bit (a candidate does not depend on its
+    position) -- and 128 sampled candidates against the fp64 oracle."""
+    from dynax_b200 import ops
+    N, H = 1 << 22, 96
+    g = T.Generator(device="cuda").manual_seed(3456)
+    u = -10 * T.rand((H, N), device="cuda", generator=g)
+    for k in range(1, H):                                        # AR(1) smoothing, rho = 0.9 (SURVEY.md section 8(d) C4)
+        u[k] = 0.9 * u[k - 1] + 0.1 * u[k]
+    rng = np.random.default_rng(3457)
+    d = cu(T, np.stack([10 + 15 * rng.random(H), rng.random(H), 2 * rng.random(H), rng.random(H)], 1))
+    args = (cu(T, orc.RC_NOMINAL), cu(T, [20.0, 35.8, 26.0]), d)
+    cost, amin, cmin = ops.rc_mpc_cost(*args, u, *sched(T), 900.0)
+    assert amin.item() == int(T.argmin(cost).item()) and cmin.item() == cost.min().item()
+    half = N // 2
+    ca, _, _ = ops.rc_mpc_cost(*args, u[:, :half].contiguous(), *sched(T), 900.0)
+    cb, _, _ = ops.rc_mpc_cost(*args, u[:, half:].contiguous(), *sched(T), 900.0)
+    assert T.equal(T.cat([ca, cb]), cost)
+    idx = np.sort(np.random.default_rng(4).choice(N, 128, replace=False))
+    ref = orc.mpc_cost(orc.RC_NOMINAL, [20.0, 35.8, 26.0], d.cpu().numpy(), u[:, T.as_tensor(idx, device="cuda")].cpu().numpy(),
+                       900.0, dtype=np.float64)
+    assert rel_err(cost[T.as_tensor(idx, device="cuda")].cpu().numpy(), ref, floor=1.0) < 1e-5

@@ -85,7 +85,7 @@ def test_adj_tile_configs(T, ops, monkeypatch, cfg):
     assert_grad_parity(grad.cpu().numpy(), g64, gbud)
 
 
-@pytest.mark.parametrize("cfg,split", [("0", "0"), ("2", "0"), ("3", "0"), ("0", "1"), ("0", "2"), ("0", "4")])
+@pytest.mark.parametrize("cfg,split", [("0", "0"), ("2", "0"), ("3", "0"), ("0", "1"), ("0", "2")])
 def test_tangent_tile_configs(T, ops, monkeypatch, cfg, split):
     th, x0, u, target = make_case(300, 777, 32)
     monkeypatch.setenv("DYNAX_GRAD_ALGO", "1")
@@ -99,14 +99,14 @@ def test_tangent_tile_configs(T, ops, monkeypatch, cfg, split):
 
 
 def test_tangent_split_roles_bit_identical(T, ops, monkeypatch):
-    """1, 2 or 4 threads per system (SPLIT, rc_fwdsens.cuh): every role steps x with the same IEEE operations and owns
+    """1 or 2 threads per system (SPLIT, rc_fwdsens.cuh): every role steps x with the same IEEE operations and owns
     whole sensitivity columns, so loss and gradient do not depend on the split -- bit for bit."""
     th, x0, u, target = make_case(1000, 1237, 40)
     a = [cu(T, v) for v in (th, x0, u, target)]
     monkeypatch.setenv("DYNAX_GRAD_ALGO", "1")
     monkeypatch.setenv("DYNAX_FS_SPLIT", "1")
     l0, g0, _ = ops.rc_loss_grad(*a, 3600.0, orc.RC_LB, orc.RC_UB, time_chunks=0)
-    for split in ("2", "4"):
+    for split in ("2",):
         monkeypatch.setenv("DYNAX_FS_SPLIT", split)
         l1, g1, _ = ops.rc_loss_grad(*a, 3600.0, orc.RC_LB, orc.RC_UB, time_chunks=0)
         assert T.equal(l0, l1) and T.equal(g0, g1), split
