@@ -64,10 +64,10 @@ int launch_adj(const AdjParams<Model> &P, cudaStream_t st) {
 
 // Forward-mode (tangent) fused loss + gradient of the 4R3C model (rc_fwdsens.cuh).
 template <int TN, int KF, int S, int MINB, int SPLIT = 1, bool SU = false, bool STG = false, bool CTRL = false,
-          bool GX0 = false, bool CHUNK = false, bool PRED = true, bool PREFETCH = false, int UNR = KF>
+          bool GX0 = false, bool CHUNK = false, int UNR = KF>
 int launch_fwdsens(const FwdSensParams &P0, cudaStream_t st) {
     using Cfg = FwdSensCfg<TN, KF, S, SPLIT, SU, STG, CTRL, GX0>;
-    auto kern = rc_fwdsens_kernel<TN, KF, S, MINB, SPLIT, SU, STG, CTRL, GX0, CHUNK, PRED, PREFETCH, UNR>;
+    auto kern = rc_fwdsens_kernel<TN, KF, S, MINB, SPLIT, SU, STG, CTRL, GX0, CHUNK, UNR>;
     DYNAX_NOTE_LAUNCH();
     int rc = set_smem(kern, Cfg::SMEM_BYTES);
     if (rc != DYNAX_OK) return rc;

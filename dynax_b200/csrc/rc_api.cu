@@ -227,7 +227,7 @@ static int rc_adjoint(const float *theta, const float *x0, const float *u, const
                       : tn == 224 ? launch_fwdsens<224, 8, 2, 2, 1, SU, STG, CTRL>(F, st)               \
                                   : launch_fwdsens<256, 8, 2, 2, 1, SU, STG, CTRL>(F, st))
 #define DYNAX_FS_LAUNCH_SPLIT(SU, STG)                                                                \
-    (split == 2 ? launch_fwdsens<64, 64, 2, 1, 2, SU, STG, false, false, false, true, false, 8>(F, st) \
+    (split == 2 ? launch_fwdsens<64, 64, 2, 1, 2, SU, STG, false, false, false, 8>(F, st)       \
                 : DYNAX_FS_LAUNCH(SU, STG, false))
         if (ctrl && stg) return DYNAX_FS_LAUNCH(true, true, true);
         if (ctrl) return DYNAX_FS_LAUNCH(true, false, true);

@@ -65,15 +65,6 @@ struct FwdSensParams {
     alignas(64) CUtensorMap map_u, map_t, map_c;   // u[T,N*5], target[T,N], ctrl[T,N]
 };
 
-#ifndef DYNAX_FS_DIAGLAST
-#define DYNAX_FS_DIAGLAST 0
-#endif
-#ifndef DYNAX_FS_PACKF
-#define DYNAX_FS_PACKF 0
-#endif
-#ifndef DYNAX_FS_ORDER
-#define DYNAX_FS_ORDER 0
-#endif
 
 constexpr int kFsFoldSteps = 32;  // fp32 partial sums are folded into the fp64 totals every this many steps
 
@@ -100,8 +91,7 @@ __host__ __device__ constexpr unsigned fs_pair_mask(int split, int role, bool gx
 }
 __host__ __device__ constexpr bool fs_has_c(int split, int role, bool gx0) { return !gx0 && role == split - 1; }
 
-template <int TN, int KF, int S, int SPLIT, int ROLE, bool SHARED_U, bool SHARED_TGT, bool CTRL, bool GX0, bool CHUNK, bool PRED,
-          bool PREFETCH, int UNR>
+template <int TN, int KF, int S, int SPLIT, int ROLE, bool SHARED_U, bool SHARED_TGT, bool CTRL, bool GX0, bool CHUNK, int UNR>
 __device__ __forceinline__ void fs_consumer(const FwdSensParams &P, unsigned char *smem_raw, float *s_in, uint64_t *full,
                                             uint64_t *empty, const int sys, const int64_t n0, const int valid,
                                             const int64_t cidx, const int T, const int C) {
@@ -210,85 +200,22 @@ __device__ __forceinline__ void fs_consumer(const FwdSensParams &P, unsigned cha
         float2 DU = make_float2(0.f, 0.f), DX = make_float2(0.f, 0.f);
         if constexpr (NEED_DU) DU = __ffma2_rn(neg1, X01, U0);   // (u0 - x0, u0 - x1), exact as a subtraction
         if constexpr (NEED_DX) DX = __ffma2_rn(neg1, X01, X2);   // (x2 - x0, x2 - x1)
-#if DYNAX_FS_ORDER == 1
-        // S <- S + dt A S, coefficient by coefficient: consecutive FFMA2s share their scalar operand, which the
-        // operand-reuse cache then serves (the loop is bound by register-file reads, not by issue slots)
-        float2 t0[NP], t1[NP], t2[NP];
-#pragma unroll
-        for (int q = 0; q < NP; ++q)
-            if (PM >> q & 1u) t0[q] = __ffma2_rn(pA00, s0[q], s0[q]);
-        const float d0 = fmaf(tA00, c0, c0);
-#pragma unroll
-        for (int q = 0; q < NP; ++q)
-            if (PM >> q & 1u) t1[q] = __ffma2_rn(pA11, s1[q], s1[q]);
-        const float d1 = fmaf(tA11, c1, c1);
-#pragma unroll
-        for (int q = 0; q < NP; ++q)
-            if (PM >> q & 1u) t2[q] = __ffma2_rn(pA20, s0[q], s2[q]);
-        float d2 = fmaf(tA20, c0, c2);
-#pragma unroll
-        for (int q = 0; q < NP; ++q)
-            if (PM >> q & 1u) t2[q] = __ffma2_rn(pA21, s1[q], t2[q]);
-        d2 = fmaf(tA21, c1, d2);
-#pragma unroll
-        for (int q = 0; q < NP; ++q)
-            if (PM >> q & 1u) s0[q] = __ffma2_rn(pA02, s2[q], t0[q]);
-        if constexpr (HAS_C) c0 = fmaf(tA02, c2, d0);
-#pragma unroll
-        for (int q = 0; q < NP; ++q)
-            if (PM >> q & 1u) s1[q] = __ffma2_rn(pA12, s2[q], t1[q]);
-        if constexpr (HAS_C) c1 = fmaf(tA12, c2, d1);
-#pragma unroll
-        for (int q = 0; q < NP; ++q)
-            if (PM >> q & 1u) s2[q] = __ffma2_rn(pA22, s2[q], t2[q]);
-        if constexpr (HAS_C) c2 = fmaf(tA22, c2, d2);
-#else
         // S <- S + dt A S
 #pragma unroll
         for (int q = 0; q < NP; ++q) {
             if (PM >> q & 1u) {
                 const float2 a0 = s0[q], a1 = s1[q], a2 = s2[q];
-                // (the diagonal term goes LAST: fma(c, a, a) reads one register pair through two operand slots, which
-                // ptxas resolves with a pair copy in straight-line code)
-#if DYNAX_FS_DIAGLAST
-                s0[q] = __ffma2_rn(pA00, a0, __ffma2_rn(pA02, a2, a0));
-                s1[q] = __ffma2_rn(pA11, a1, __ffma2_rn(pA12, a2, a1));
-#else
                 s0[q] = __ffma2_rn(pA02, a2, __ffma2_rn(pA00, a0, a0));
                 s1[q] = __ffma2_rn(pA12, a2, __ffma2_rn(pA11, a1, a1));
-#endif
                 s2[q] = __ffma2_rn(pA22, a2, __ffma2_rn(pA21, a1, __ffma2_rn(pA20, a0, a2)));
             }
         }
         if constexpr (HAS_C) {  // the same three expressions, one lane
             const float a0 = c0, a1 = c1, a2 = c2;
-#if DYNAX_FS_DIAGLAST
-            c0 = fmaf(tA00, a0, fmaf(tA02, a2, a0));
-            c1 = fmaf(tA11, a1, fmaf(tA12, a2, a1));
-#else
             c0 = fmaf(tA02, a2, fmaf(tA00, a0, a0));
             c1 = fmaf(tA12, a2, fmaf(tA11, a1, a1));
-#endif
             c2 = fmaf(tA22, a2, fmaf(tA21, a1, fmaf(tA20, a0, a2)));
         }
-#endif
-#if DYNAX_FS_PACKF
-        // direct partials as packed FMAs with a zero coefficient in the lane that is not forced (x + 0*y == x exactly
-        // for finite y): a scalar update of one half of a register pair costs ptxas a pair copy
-        if constexpr ((PM & 0x1u) != 0) {
-            s0[0] = __ffma2_rn(fCai, R01, s0[0]);      // d/dCai   (column 0), row 0
-            s1[0] = __ffma2_rn(fCwe, R01, s1[0]);      // d/dCwe   (column 1), row 1
-        }
-        if constexpr ((PM & 0x2u) != 0) {
-            s2[1] = __ffma2_rn(fCwi, make_float2(r2, r2), s2[1]);   // d/dCwi   (column 2), row 2
-            s1[1] = __ffma2_rn(fRe, DU, s1[1]);                     // d/dRe    (column 3), row 1
-        }
-        if constexpr ((PM & 0x4u) != 0) {
-            s0[2] = __ffma2_rn(fRi0, DX, s0[2]);       // d/dRi    (column 4), row 0
-            s1[2] = __ffma2_rn(fRw1, DX, s1[2]);       // d/dRw    (column 5), row 1
-            s2[2] = __ffma2_rn(pR2, DX, s2[2]);        // d/dRi, d/dRw, row 2
-        }
-#else
         if constexpr ((PM & 0x1u) != 0) {
             s0[0].x = fmaf(tCai, R01.x, s0[0].x);      // d/dCai   (column 0)
             s1[0].y = fmaf(tCwe, R01.y, s1[0].y);      // d/dCwe   (column 1)
@@ -302,67 +229,20 @@ __device__ __forceinline__ void fs_consumer(const FwdSensParams &P, unsigned cha
             s1[2].y = fmaf(tRw1, DX.y, s1[2].y);       // d/dRw    (column 5), row 1
             s2[2] = __ffma2_rn(pR2, DX, s2[2]);        // d/dRi, d/dRw, row 2
         }
-#endif
         if constexpr ((PM & 0x8u) != 0) s0[3].x = fmaf(tRg, DU.x, s0[3].x);   // d/dRg    (column 6)
         if constexpr (HAS_C) c0 = fmaf(tRg, DU.x, c0);
         X01 = __ffma2_rn(dt2, R01, X01);
         x2 = fmaf(dt, r2, x2);
     };
 
-    if constexpr (PRED) {
-    // One predicated, fully unrolled body per chunk; the last chunk may be ragged.  (Measured on B200: the per-row
-    // predicates double as scheduling fences -- ptxas keeps the loads of step j+1 behind step j, live ranges stay
-    // short at 96 registers -- and this form is 3-4 % FASTER than an unpredicated body for full chunks.)
-    constexpr int FOLDC = kFsFoldSteps / KF > 0 ? kFsFoldSteps / KF : 1;
-    for (int c = 0; c < C; ++c) {
-        const int s = c % S;
-        const int k0 = c * KF;
-        const int rows = (T - k0) < KF ? (T - k0) : KF;
-        ptx::mbar_wait(&full[s], (uint32_t)((c / S) & 1));
-        in = s_in + s * Cfg::STAGE + (SHARED_U ? 0 : sys * 5);
-        tg = s_in + s * Cfg::STAGE + Cfg::U_STAGE + (SHARED_TGT ? 0 : sys);
-        if constexpr (PREFETCH) {
-            // a launch with one warp per scheduler cannot hide the shared-memory latency of a step's loads behind other
-            // warps, and the per-row predicates keep ptxas from hoisting them: fetch row j+1 while row j computes
-            Row nxt = load_row(0);
-#pragma unroll UNR
-            for (int jj = 0; jj < KF; ++jj) {
-                if (jj < rows) {
-                    const Row cur = nxt;
-                    if (jj + 1 < rows) nxt = load_row(jj + 1);
-                    step(cur);
-                }
-            }
-        } else {
-#pragma unroll UNR
-            for (int jj = 0; jj < KF; ++jj)
-                if (jj < rows) step(load_row(jj));
-        }
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&empty[s]);
-        if ((c + 1) % FOLDC == 0 || c + 1 == C) {
-#pragma unroll
-            for (int q = 0; q < NP; ++q) {
-                if (PM >> q & 1u) {
-                    acc[(2 * q) * TN] += (double)gp[q].x;
-                    acc[(2 * q + 1 != 7 ? 2 * q + 1 : 10) * TN] += (double)gp[q].y;
-                    gp[q] = make_float2(0.f, 0.f);
-                }
-            }
-            if constexpr (HAS_C) {
-                acc[6 * TN] += (double)gc;
-                gc = 0.f;
-            }
-            if constexpr (LOSS_ROLE) {
-                acc[7 * TN] += (double)sq;
-                sq = 0.f;
-            }
-        }
-    }
-    } else {
-    // Chunk 0 holds the ragged part of the horizon (r0 = T - (C-1) KF rows, 1..KF) and runs as a rolled loop; every
-    // other chunk is full and runs the unrolled body without per-row predicates.
-    const int r0 = T - (C - 1) * KF;
+    // One predicated body per chunk, unrolled UNR steps at a time; the last chunk may be ragged.  (Measured on B200: the
+    // per-row predicates double as scheduling fences -- ptxas keeps the loads of step j+1 behind step j, live ranges
+    // stay short at 96 registers -- and this form is 3-4 % FASTER than an unpredicated body for full chunks; fetching
+    // row j+1 into registers while row j computes is slower too: profiles/r02_headline_variants.txt.)
+    // fp32 partial sums are folded into the fp64 totals at every multiple of kFsFoldSteps steps of the horizon and at
+    // its end, whatever the chunk length: results do not depend on the tile shape (bit for bit).
+    static_assert(KF % kFsFoldSteps == 0 || kFsFoldSteps % KF == 0, "chunk length and fold interval must nest");
+    constexpr int FR = KF > kFsFoldSteps ? kFsFoldSteps : KF;       // rows between folds inside a chunk
     constexpr int FOLDC = kFsFoldSteps / KF > 0 ? kFsFoldSteps / KF : 1;
     auto fold = [&]() {
 #pragma unroll
@@ -382,27 +262,23 @@ __device__ __forceinline__ void fs_consumer(const FwdSensParams &P, unsigned cha
             sq = 0.f;
         }
     };
-    {
-        ptx::mbar_wait(&full[0], 0u);
-        in = s_in + (SHARED_U ? 0 : sys * 5);
-        tg = s_in + Cfg::U_STAGE + (SHARED_TGT ? 0 : sys);
-#pragma unroll 1
-        for (int jj = 0; jj < r0; ++jj) step(load_row(jj));
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&empty[0]);
-    }
-    for (int c = 1; c < C; ++c) {
+    for (int c = 0; c < C; ++c) {
         const int s = c % S;
+        const int k0 = c * KF;
+        const int rows = (T - k0) < KF ? (T - k0) : KF;
         ptx::mbar_wait(&full[s], (uint32_t)((c / S) & 1));
         in = s_in + s * Cfg::STAGE + (SHARED_U ? 0 : sys * 5);
         tg = s_in + s * Cfg::STAGE + Cfg::U_STAGE + (SHARED_TGT ? 0 : sys);
-#pragma unroll
-        for (int jj = 0; jj < KF; ++jj) step(load_row(jj));
+#pragma unroll 1
+        for (int j0 = 0; j0 < KF; j0 += FR) {
+#pragma unroll UNR
+            for (int jj = 0; jj < FR; ++jj)
+                if (j0 + jj < rows) step(load_row(j0 + jj));
+            if (KF > kFsFoldSteps && j0 + FR < KF) fold();      // inside a long chunk; its last block folds below
+        }
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&empty[s]);
-        if (c % FOLDC == 0) fold();
-    }
-    fold();
+        if ((c + 1) % FOLDC == 0 || c + 1 == C) fold();
     }
 
     // ---- outputs: every role reports the columns it owns ----
@@ -481,7 +357,7 @@ __device__ __forceinline__ void fs_consumer(const FwdSensParams &P, unsigned cha
 }
 
 template <int TN, int KF, int S, int MINB, int SPLIT = 1, bool SHARED_U = false, bool SHARED_TGT = false,
-          bool CTRL = false, bool GX0 = false, bool CHUNK = false, bool PRED = true, bool PREFETCH = false, int UNR = KF>
+          bool CTRL = false, bool GX0 = false, bool CHUNK = false, int UNR = KF>
 __global__ void __launch_bounds__(TN * SPLIT + 32, MINB) rc_fwdsens_kernel(const __grid_constant__ FwdSensParams P) {
     static_assert(!CTRL || SHARED_U, "the control channel replaces a column of a SHARED input series");
     static_assert(!CHUNK || (!GX0 && !CTRL), "time-chunked launches use the plain kernel");
@@ -522,10 +398,8 @@ __global__ void __launch_bounds__(TN * SPLIT + 32, MINB) rc_fwdsens_kernel(const
         const uint64_t pol = ptx::policy_evict_first(), pol_keep = ptx::policy_evict_last();
         auto load_chunk = [&](int c) {
             const int s = c % S;
-            // !PRED: chunk 0 holds the ragged part of the horizon (see the consumers), every other chunk is full
-            const int r0 = T - (C - 1) * KF;
-            const int64_t k0 = PRED ? (int64_t)c * KF : (c == 0 ? 0 : r0 + (int64_t)(c - 1) * KF);
-            const int rows = PRED ? (int)((T - k0) < KF ? (T - k0) : KF) : (c == 0 ? r0 : KF);
+            const int64_t k0 = (int64_t)c * KF;
+            const int rows = (int)((T - k0) < KF ? (T - k0) : KF);
             float *du = s_in + s * Cfg::STAGE, *dtg = du + Cfg::U_STAGE;
             // Shared series: one bulk copy per block of rows when it is 16-byte aligned and sized (asynchronous, so the
             // producer does not pay an L2 round trip per chunk), else plain loads by the producer lanes.  Per-system
@@ -605,8 +479,8 @@ __global__ void __launch_bounds__(TN * SPLIT + 32, MINB) rc_fwdsens_kernel(const
     // --------------------------------- consumers: role = warp-uniform ---------------------------------
     const int role = SPLIT == 1 ? 0 : tid / TN, sys = SPLIT == 1 ? tid : tid % TN;
 #define DYNAX_FS_ROLE(R)                                                                                         \
-    fs_consumer<TN, KF, S, SPLIT, R, SHARED_U, SHARED_TGT, CTRL, GX0, CHUNK, PRED, PREFETCH, UNR>(                      \
-        P, smem_raw, s_in, full, empty, sys, n0, valid, cidx, T, C)
+    fs_consumer<TN, KF, S, SPLIT, R, SHARED_U, SHARED_TGT, CTRL, GX0, CHUNK, UNR>(P, smem_raw, s_in, full, empty, sys, n0, \
+                                                                                  valid, cidx, T, C)
     if constexpr (SPLIT == 1) {
         DYNAX_FS_ROLE(0);
     } else if constexpr (SPLIT == 2) {
