@@ -513,7 +513,10 @@ def ours(a):
         td = torch.tensor([d_sec], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(td, op=dist.ReduceOp.MAX)
-        assert np.array_equal(l_d, l_h) and np.array_equal(g_d, g_h)
+        # (the tiled host call runs its last, small tile on the time-parallel kernels: same results within the
+        # gradient tolerance, not bit for bit)
+        assert np.allclose(l_d, l_h, rtol=1e-5)
+        assert (np.linalg.norm(g_d - g_h, axis=1) <= 1e-4 * np.linalg.norm(g_h, axis=1)).all()
         ds.close()
         e2e["resident_dataset_variant"] = {
             "value": world * Ne * T * nrep / float(td.item()), "unit": "system-steps/s",

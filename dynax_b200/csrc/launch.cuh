@@ -20,12 +20,36 @@ inline size_t adj_workspace_bytes(int64_t N, int64_t T, int n) {
 }
 
 template <class Model, int TN, int KF, int S, bool SHARED_U, int MINB>
-int launch_fwd(const FwdParams<Model> &P, cudaStream_t st) {
+int launch_fwd(const FwdParams<Model> &P0, cudaStream_t st) {
     using Cfg = FwdCfg<Model, TN, KF, S, SHARED_U>;
     auto kern = rollout_fwd_kernel<Model, TN, KF, S, SHARED_U, MINB>;
     DYNAX_NOTE_LAUNCH();
     int rc = set_smem(kern, Cfg::SMEM_BYTES);
     if (rc != DYNAX_OK) return rc;
+    // tensor maps (one copy per array and stage) wherever the layout allows; DYNAX_NO_TENSOR=1 keeps per-row copies
+    FwdParams<Model> P = P0;
+    P.tensor_in = P.tensor_out = 0;
+    if (!getenv("DYNAX_NO_TENSOR") && P.T > 0) {
+        constexpr int n = Model::n, m = Model::m, p = Model::p;
+        if (P.bulk_in && (!SHARED_U || P.ctrl)) {
+            const int iu = SHARED_U ? 1 : row_map_inner(P.N, m, TN), ic = P.ctrl ? row_map_inner(P.N, 1, TN) : 1;
+            if (iu > 0 && ic > 0) {
+                if (!SHARED_U) rc = make_row_map(&P.map_u, P.u, P.N, m, P.T, TN, KF, iu);
+                if (rc == DYNAX_OK && P.ctrl) rc = make_row_map(&P.map_c, P.ctrl, P.N, 1, P.T, TN, KF, ic);
+                if (rc != DYNAX_OK) return rc;
+                P.tensor_in = 1; P.inner_u = iu; P.inner_c = ic;
+            }
+        }
+        if (P.bulk_out && (P.xsol || P.ysol)) {
+            const int ix = P.xsol ? row_map_inner(P.N, n, TN) : 1, iy = P.ysol ? row_map_inner(P.N, p, TN) : 1;
+            if (ix > 0 && iy > 0) {
+                if (P.xsol) rc = make_row_map(&P.map_x, P.xsol, P.N, n, P.T, TN, KF, ix);
+                if (rc == DYNAX_OK && P.ysol) rc = make_row_map(&P.map_y, P.ysol, P.N, p, P.T, TN, KF, iy);
+                if (rc != DYNAX_OK) return rc;
+                P.tensor_out = 1; P.inner_x = ix; P.inner_y = iy;
+            }
+        }
+    }
     const int64_t grid = (P.N + TN - 1) / TN;
     if (grid > 0x7fffffffLL) return fail(DYNAX_ERR_INVALID_ARGUMENT, "N too large for one launch");
     const int64_t chunks = P.chunk_len > 0 ? (P.T + P.chunk_len - 1) / P.chunk_len : 1;

@@ -130,6 +130,14 @@ __device__ __forceinline__ void tensor_g2s_3d(void *smem_dst, const void *map, i
         : "memory");
 }
 
+// shared -> global tensor copy through a 3-D tensor map (bulk async-group completion); elements of the box that fall
+// outside the tensor are not written.
+__device__ __forceinline__ void tensor_s2g_3d(const void *map, int c0, int c1, int c2, const void *smem_src) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(map), "r"(c0),
+                 "r"(c1), "r"(c2), "r"(smem_u32(smem_src))
+                 : "memory");
+}
+
 // shared -> global bulk copy (bulk async-group completion).
 __device__ __forceinline__ void bulk_s2g(void *gmem_dst, const void *smem_src, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst),

@@ -13,6 +13,8 @@
 // CTA drift freely within the ring.  If N is not a multiple of 4 (rows not 16-byte multiples) the
 // producer warp falls back to plain coalesced ld/st for that launch -- same pipeline, no TMA.
 #pragma once
+#include <cuda.h>
+
 #include "models.cuh"
 #include "ptx.cuh"
 
@@ -42,16 +44,22 @@ struct FwdParams {
     // sampling-based control needs; it cuts the streamed input from 4m to 4 bytes per system-step.
     const float *ctrl = nullptr;  // [T,N] or NULL
     int ctrl_col = 0;
+    // 3-D tensor maps over the row arrays (tmap.cuh): ONE cp.async.bulk.tensor per array and stage instead of one 1-D
+    // bulk copy per row.  tensor_in: u (per-system) and ctrl; tensor_out: xsol and ysol.  inner_* = the maps' inner
+    // extents in floats (the second coordinate of a CTA's box is n0*w/inner).
+    int tensor_in = 0, tensor_out = 0, inner_u = 0, inner_c = 0, inner_x = 0, inner_y = 0;
+    alignas(64) CUtensorMap map_u, map_c, map_x, map_y;
 };
 
 __host__ __device__ constexpr int align4i(int x) { return (x + 3) & ~3; }
+__host__ __device__ constexpr int align32i(int x) { return (x + 31) & ~31; }   // 128 bytes: tensor-copy destinations
 
 template <class Model, int TN, int KF, int S, bool SHARED_U>
 struct FwdCfg {
     static constexpr int n = Model::n, m = Model::m, p = Model::p;
     static constexpr int IN_ROW = SHARED_U ? m : TN * m;
-    static constexpr int CTRL_OFF = align4i(KF * IN_ROW);               // per-system channel rows [KF][TN]
-    static constexpr int IN_STAGE = CTRL_OFF + (SHARED_U ? KF * TN : 0);
+    static constexpr int CTRL_OFF = align32i(KF * IN_ROW);              // per-system channel rows [KF][TN]
+    static constexpr int IN_STAGE = align32i(CTRL_OFF + (SHARED_U ? KF * TN : 0));
     static constexpr int XO_STAGE = KF * TN * n;
     static constexpr int YO_STAGE = KF * TN * p;
     static constexpr int NBAR = 2 * S + 4;
@@ -62,7 +70,7 @@ struct FwdCfg {
 };
 
 template <class Model, int TN, int KF, int S, bool SHARED_U, int MINB>
-__global__ void __launch_bounds__(TN + 32, MINB) rollout_fwd_kernel(const FwdParams<Model> P) {
+__global__ void __launch_bounds__(TN + 32, MINB) rollout_fwd_kernel(const __grid_constant__ FwdParams<Model> P) {
     using Cfg = FwdCfg<Model, TN, KF, S, SHARED_U>;
     constexpr int n = Cfg::n, m = Cfg::m, p = Cfg::p;
     constexpr int IN_ROW = Cfg::IN_ROW, IN_STAGE = Cfg::IN_STAGE, XO_STAGE = Cfg::XO_STAGE,
@@ -151,13 +159,23 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_fwd_kernel(const FwdPar
                 if (lane == 0) {
                     if (sh_bulk || c_bulk) {
                         const uint32_t row_bytes = (uint32_t)valid * 4u;
-                        ptx::mbar_arrive_expect_tx(&full[s], (sh_bulk ? sh_bytes : 0u) + (c_bulk ? row_bytes * (uint32_t)rows : 0u));
+                        const uint32_t c_bytes = P.tensor_in ? (uint32_t)(KF * TN * 4) : row_bytes * (uint32_t)rows;
+                        ptx::mbar_arrive_expect_tx(&full[s], (sh_bulk ? sh_bytes : 0u) + (c_bulk ? c_bytes : 0u));
                         if (sh_bulk) ptx::bulk_g2s(dst, src, sh_bytes, &full[s], pol_keep);
-                        if (c_bulk)
+                        if (c_bulk && P.tensor_in)   // the whole stage of the channel in one tensor copy
+                            ptx::tensor_g2s_3d(cdst, &P.map_c, 0, (int)(n0 / P.inner_c), (int)(t_begin + k0), &full[s], pol);
+                        else if (c_bulk)
                             for (int r = 0; r < rows; ++r) ptx::bulk_g2s(cdst + r * TN, csrc + r * N, row_bytes, &full[s], pol);
                     } else {
                         ptx::mbar_arrive(&full[s]);
                     }
+                }
+            } else if (P.tensor_in) {
+                // one tensor copy for the stage: KF rows x this CTA's slice (rows past the horizon and systems past N
+                // arrive as zeros; the transaction count is always the full box)
+                if (lane == 0) {
+                    ptx::mbar_arrive_expect_tx(&full[s], (uint32_t)(KF * TN * m * 4));
+                    ptx::tensor_g2s_3d(dst, &P.map_u, 0, (int)(n0 * m / P.inner_u), (int)(t_begin + k0), &full[s], pol);
                 }
             } else if (P.bulk_in) {
                 if (lane == 0) {
@@ -179,11 +197,18 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_fwd_kernel(const FwdPar
             const float *sx = s_xo + o * XO_STAGE;
             const float *sy = s_yo + o * YO_STAGE;
             if (lane == 0) {
-                for (int r = 0; r < rows; ++r) {
-                    if (emit_x)
-                        ptx::bulk_s2g(xsol_base + ((k0 + r) * N + n0) * n, sx + r * TN * n, (uint32_t)valid * n * 4u);
-                    if (emit_y)
-                        ptx::bulk_s2g(ysol_base + ((k0 + r) * N + n0) * p, sy + r * TN * p, (uint32_t)valid * p * 4u);
+                if (P.tensor_out && rows == KF) {
+                    // full stage: one tensor store per array (systems past N are clipped by the map).  A ragged stage goes
+                    // row by row: in a time-chunked launch the rows behind it belong to the next chunk's CTA.
+                    if (emit_x) ptx::tensor_s2g_3d(&P.map_x, 0, (int)(n0 * n / P.inner_x), (int)(t_begin + k0), sx);
+                    if (emit_y) ptx::tensor_s2g_3d(&P.map_y, 0, (int)(n0 * p / P.inner_y), (int)(t_begin + k0), sy);
+                } else {
+                    for (int r = 0; r < rows; ++r) {
+                        if (emit_x)
+                            ptx::bulk_s2g(xsol_base + ((k0 + r) * N + n0) * n, sx + r * TN * n, (uint32_t)valid * n * 4u);
+                        if (emit_y)
+                            ptx::bulk_s2g(ysol_base + ((k0 + r) * N + n0) * p, sy + r * TN * p, (uint32_t)valid * p * 4u);
+                    }
                 }
                 ptx::bulk_commit();
                 ptx::bulk_wait_read<0>();  // out-tile may be overwritten once TMA has read it

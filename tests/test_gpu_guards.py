@@ -42,12 +42,13 @@ def test_no_out_of_bounds_writes(N, Tn):
                                       xf.data_ptr(), N, Tn, 3600.0, 0, None))
     loss, grad, gx0 = ar.out(N), ar.out(N, 7), ar.out(N, 3)
     nws = L.dynax_workspace_bytes(_lib.OP_RC_LOSS_GRAD, N, Tn, 3, 5, 1, 0)
-    ws = ar.out((nws + 3) // 4)
+    ws = ar.out(max(4, (nws + 3) // 4))
     _lib.check(L.dynax_rc_loss_grad_f32(th.data_ptr(), x0.data_ptr(), u.data_ptr(), tg.data_ptr(), None, None,
                                         loss.data_ptr(), grad.data_ptr(), gx0.data_ptr(), N, Tn, 3600.0, 0,
                                         ws.data_ptr(), ws.numel() * 4, None))
     gth, gx0b, gu = ar.out(N, 7), ar.out(N, 3), ar.out(Tn, N, 5)
-    ws2 = ar.out((nws + 3) // 4)
+    nwv = L.dynax_workspace_bytes(_lib.OP_RC_VJP, N, Tn, 3, 5, 1, 0)       # the adjoint's checkpoints
+    ws2 = ar.out((nwv + 3) // 4)
     ones3, ones1 = torch.ones((Tn, N, 3), device="cuda"), torch.ones((Tn, N, 1), device="cuda")
     _lib.check(L.dynax_rc_vjp_f32(th.data_ptr(), x0.data_ptr(), u.data_ptr(), ones3.data_ptr(), ones1.data_ptr(),
                                   gth.data_ptr(), gx0b.data_ptr(), gu.data_ptr(), N, Tn, 3600.0, 0, ws2.data_ptr(),
