@@ -515,7 +515,7 @@ def ours(a):
             dist.all_reduce(td, op=dist.ReduceOp.MAX)
         # (the tiled host call runs its last, small tile on the time-parallel kernels: same results within the
         # gradient tolerance, not bit for bit)
-        assert np.allclose(l_d, l_h, rtol=1e-5)
+        assert np.allclose(l_d, l_h, rtol=1e-4)
         assert (np.linalg.norm(g_d - g_h, axis=1) <= 1e-4 * np.linalg.norm(g_h, axis=1)).all()
         ds.close()
         e2e["resident_dataset_variant"] = {
