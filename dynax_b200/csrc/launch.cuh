@@ -60,13 +60,34 @@ int launch_fwd(const FwdParams<Model> &P0, cudaStream_t st) {
 }
 
 template <class Model, int TN, int KC, int S, int MODE, bool SHARED_U, bool SHARED_TGT, int MINB>
-int launch_adj(const AdjParams<Model> &P, cudaStream_t st) {
+int launch_adj(const AdjParams<Model> &P0, cudaStream_t st) {
     using Cfg = AdjCfg<Model, TN, KC, S, MODE, SHARED_U, SHARED_TGT>;
     static_assert(KC >= kMinKC, "workspace sizing assumes KC >= kMinKC");
     auto kern = rollout_adj_kernel<Model, TN, KC, S, MODE, SHARED_U, SHARED_TGT, MINB>;
     DYNAX_NOTE_LAUNCH();
     int rc = set_smem(kern, Cfg::SMEM_BYTES);
     if (rc != DYNAX_OK) return rc;
+    // tensor maps (one copy per array and stage) when every per-system array of this launch allows one;
+    // DYNAX_NO_TENSOR=1 keeps the per-row copies
+    AdjParams<Model> P = P0;
+    P.tensor = 0;
+    if (P.bulk && !getenv("DYNAX_NO_TENSOR")) {
+        constexpr int n = Model::n, m = Model::m, p = Model::p;
+        const float *a1 = MODE == ADJ_MSE ? (SHARED_TGT ? nullptr : P.target) : P.g_ysol;
+        const float *a2 = MODE == ADJ_MSE ? nullptr : P.g_xsol;
+        const int w1 = MODE == ADJ_MSE ? 1 : p;
+        const int iu = SHARED_U ? 1 : row_map_inner(P.N, m, TN), ic = (SHARED_U && P.ctrl) ? row_map_inner(P.N, 1, TN) : 1;
+        const int i1 = a1 ? row_map_inner(P.N, w1, TN) : 1, i2 = a2 ? row_map_inner(P.N, n, TN) : 1;
+        const bool any = !SHARED_U || (SHARED_U && P.ctrl) || a1 || a2;
+        if (any && iu > 0 && ic > 0 && i1 > 0 && i2 > 0) {
+            if (!SHARED_U) rc = make_row_map(&P.map_u, P.u, P.N, m, P.T, TN, KC, iu);
+            if (rc == DYNAX_OK && SHARED_U && P.ctrl) rc = make_row_map(&P.map_c, P.ctrl, P.N, 1, P.T, TN, KC, ic);
+            if (rc == DYNAX_OK && a1) rc = make_row_map(&P.map_a1, a1, P.N, w1, P.T, TN, KC, i1);
+            if (rc == DYNAX_OK && a2) rc = make_row_map(&P.map_a2, a2, P.N, n, P.T, TN, KC, i2);
+            if (rc != DYNAX_OK) return rc;
+            P.tensor = 1; P.inner_u = iu; P.inner_c = ic; P.inner_a1 = i1; P.inner_a2 = i2;
+        }
+    }
     const int64_t grid = (P.N + TN - 1) / TN;
     if (grid > 0x7fffffffLL) return fail(DYNAX_ERR_INVALID_ARGUMENT, "N too large for one launch");
     if (P.chunk_len > 0) {  // time-chunked launch: the caller (rc_chunked_adj.cu) owns zeroing and finalisation

@@ -18,9 +18,11 @@
 // within a segment and folded into fp64 totals once per segment, which removes the O(T) fp32
 // accumulation error that dominates an all-fp32 BPTT.
 #pragma once
+#include <cuda.h>
+
 #include "models.cuh"
 #include "ptx.cuh"
-#include "rollout_fwd.cuh"  // align4i
+#include "rollout_fwd.cuh"  // align4i, align32i
 
 namespace dynax {
 
@@ -56,6 +58,10 @@ struct AdjParams {
     float *a_start;           // [C,N,n] out: adjoint at each chunk's first step, or NULL
     double *chunk_acc;        // [N,NOUT+1] out: per-system fp64 sums over chunks (atomics), or NULL
     int skip_grads;           // only a_start is wanted: skip the outer-product accumulation
+    // 3-D tensor maps over the per-system row arrays (tmap.cuh): ONE cp.async.bulk.tensor per array and stage instead of
+    // one 1-D bulk copy per row.  a1 = target (MSE) or g_ysol (VJP), a2 = g_xsol; inner_* = inner extents in floats.
+    int tensor, inner_u, inner_c, inner_a1, inner_a2;
+    alignas(64) CUtensorMap map_u, map_c, map_a1, map_a2;
 };
 
 template <class Model, int TN, int KC, int S, int MODE, bool SHARED_U, bool SHARED_TGT>
@@ -65,10 +71,11 @@ struct AdjCfg {
     static constexpr int A1_ROW = (MODE == ADJ_MSE) ? (SHARED_TGT ? 1 : TN) : TN * p;  // target | g_y
     static constexpr int A2_ROW = (MODE == ADJ_MSE) ? 0 : TN * n;                      // g_x
     static constexpr int U_OFF = 0;
-    static constexpr int A1_OFF = align4i(KC * U_ROW);
-    static constexpr int A2_OFF = A1_OFF + align4i(KC * A1_ROW);
-    static constexpr int A3_OFF = A2_OFF + align4i(KC * A2_ROW);                       // per-system channel (ctrl)
-    static constexpr int STAGE = A3_OFF + (SHARED_U ? KC * TN : 0);
+    // every block of a stage starts on a 128-byte boundary (destination alignment of cp.async.bulk.tensor)
+    static constexpr int A1_OFF = align32i(KC * U_ROW);
+    static constexpr int A2_OFF = A1_OFF + align32i(KC * A1_ROW);
+    static constexpr int A3_OFF = A2_OFF + align32i(KC * A2_ROW);                      // per-system channel (ctrl)
+    static constexpr int STAGE = A3_OFF + (SHARED_U ? align32i(KC * TN) : 0);
     static constexpr int NBAR = 2 * S;
     // Models with many gradient accumulators (dense LTI: n*n + n*m + p*n + p*m) keep the fp64 totals in shared
     // memory ([NG][TN] doubles, conflict-free 8-byte accesses) and fold into them every GT_FOLD segments: as 2*NG
@@ -88,7 +95,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 template <class Model, int TN, int KC, int S, int MODE, bool SHARED_U, bool SHARED_TGT, int MINB>
-__global__ void __launch_bounds__(TN + 32, MINB) rollout_adj_kernel(const AdjParams<Model> P) {
+__global__ void __launch_bounds__(TN + 32, MINB) rollout_adj_kernel(const __grid_constant__ AdjParams<Model> P) {
     using Cfg = AdjCfg<Model, TN, KC, S, MODE, SHARED_U, SHARED_TGT>;
     constexpr int n = Cfg::n, m = Cfg::m, p = Cfg::p;
     constexpr int NG = Model::NG, NOUT = Model::NOUT;
@@ -140,8 +147,15 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_adj_kernel(const AdjPar
         // everything when !bulk: cp.async if the launch is in async_rows mode, plain loads otherwise); pass 1: TMA
         // bulk copies by lane 0.
         auto stream = [&](int pass, float *dst, int row_stride, const float *g, int w, bool shared, int64_t k0,
-                          int rows, uint64_t *bar) -> uint32_t {
+                          int rows, uint64_t *bar, const CUtensorMap *map, int inner) -> uint32_t {
             if (g == nullptr) return 0;
+            if (!shared && P.tensor) {
+                // the whole stage of this array in one tensor copy (rows past the horizon / systems past N arrive as
+                // zeros or as the neighbouring chunk's rows, which nobody reads; the transaction is always the full box)
+                if (pass == 1 && lane == 0)
+                    ptx::tensor_g2s_3d(dst, map, 0, (int)(n0 * w / inner), (int)(t_begin + k0), bar, pol);
+                return (uint32_t)(KC * TN * w * 4);
+            }
             if (shared) {
                 if (pass == 0) {  // [T,1,w] is contiguous in k and the smem rows are packed (row_stride == w)
                     const float *src = g + k0 * w;
@@ -171,14 +185,14 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_adj_kernel(const AdjPar
             uint32_t bytes = 0;
 #pragma unroll
             for (int pass = 0; pass < 2; ++pass) {
-                uint32_t b = stream(pass, st + Cfg::U_OFF, U_ROW, u_base, m, SHARED_U, k0, rows, &full[s]);
-                if (SHARED_U) b += stream(pass, st + Cfg::A3_OFF, TN, ctrl_base, 1, false, k0, rows, &full[s]);
+                uint32_t b = stream(pass, st + Cfg::U_OFF, U_ROW, u_base, m, SHARED_U, k0, rows, &full[s], &P.map_u, P.inner_u);
+                if (SHARED_U) b += stream(pass, st + Cfg::A3_OFF, TN, ctrl_base, 1, false, k0, rows, &full[s], &P.map_c, P.inner_c);
                 if (!fwd) {
                     if (MODE == ADJ_MSE) {
-                        b += stream(pass, st + Cfg::A1_OFF, A1_ROW, tgt_base, 1, SHARED_TGT, k0, rows, &full[s]);
+                        b += stream(pass, st + Cfg::A1_OFF, A1_ROW, tgt_base, 1, SHARED_TGT, k0, rows, &full[s], &P.map_a1, P.inner_a1);
                     } else {
-                        b += stream(pass, st + Cfg::A1_OFF, A1_ROW, gy_base, p, false, k0, rows, &full[s]);
-                        b += stream(pass, st + Cfg::A2_OFF, A2_ROW, gx_base, n, false, k0, rows, &full[s]);
+                        b += stream(pass, st + Cfg::A1_OFF, A1_ROW, gy_base, p, false, k0, rows, &full[s], &P.map_a1, P.inner_a1);
+                        b += stream(pass, st + Cfg::A2_OFF, A2_ROW, gx_base, n, false, k0, rows, &full[s], &P.map_a2, P.inner_a2);
                     }
                 }
                 if (pass == 0) {
