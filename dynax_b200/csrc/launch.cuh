@@ -16,7 +16,12 @@ constexpr int kMinKC = 8;  // smallest checkpoint interval any instantiated conf
 
 inline size_t adj_workspace_bytes(int64_t N, int64_t T, int n) {
     const int64_t C = (T + kMinKC - 1) / kMinKC;
-    return kAccBytes + sizeof(float) * (size_t)C * (size_t)n * (size_t)N;
+    return (kAccBytes + sizeof(float) * (size_t)C * (size_t)n * (size_t)N + 15) / 16 * 16;
+}
+// VJP with a SHARED input series: per-CTA partial sums of g_u ([ceil(N/128)][T][m] floats) behind the checkpoints
+constexpr int kGuPartTN = 128;
+inline size_t gu_part_bytes(int64_t N, int64_t T, int m) {
+    return sizeof(float) * (size_t)((N + kGuPartTN - 1) / kGuPartTN) * (size_t)T * (size_t)m;
 }
 
 template <class Model, int TN, int KF, int S, bool SHARED_U, int MINB>
@@ -71,6 +76,7 @@ int launch_adj(const AdjParams<Model> &P0, cudaStream_t st) {
     // DYNAX_NO_TENSOR=1 keeps the per-row copies
     AdjParams<Model> P = P0;
     P.tensor = 0;
+    if (MODE == ADJ_VJP && SHARED_U) P.g_u = nullptr;   // a shared series gets ONE g_u row per step: gu_part + gu_reduce_kernel
     if (P.bulk && !getenv("DYNAX_NO_TENSOR")) {
         constexpr int n = Model::n, m = Model::m, p = Model::p;
         const float *a1 = MODE == ADJ_MSE ? (SHARED_TGT ? nullptr : P.target) : P.g_ysol;
@@ -98,8 +104,14 @@ int launch_adj(const AdjParams<Model> &P0, cudaStream_t st) {
         return DYNAX_OK;
     }
     if (P.shared_theta) DYNAX_CUDA_TRY(cudaMemsetAsync(P.shared_acc, 0, kAccBytes, st));
+    static_assert(!(MODE == ADJ_VJP && SHARED_U) || TN == kGuPartTN, "gu_part is sized for 128-system CTAs");
     kern<<<(unsigned)grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(P);
     DYNAX_CUDA_TRY(cudaGetLastError());
+    if (MODE == ADJ_VJP && SHARED_U && P.gu_part != nullptr && P0.g_u != nullptr) {
+        const int64_t elems = P.T * Model::m;
+        gu_reduce_kernel<<<(unsigned)((elems + 255) / 256), 256, 0, st>>>(P.gu_part, P0.g_u, elems, grid);
+        DYNAX_CUDA_TRY(cudaGetLastError());
+    }
     if (P.shared_theta) {
         shared_finalize_kernel<Model, MODE><<<1, 32, 0, st>>>(P.shared_acc, P.mp, P.gp, P.lb, P.ub, P.loss);
         DYNAX_CUDA_TRY(cudaGetLastError());

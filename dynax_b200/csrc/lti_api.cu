@@ -116,13 +116,11 @@ int dynax_lti_vjp_f32(const float *A, const float *B, const float *C, const floa
     if (flags & ~(DYNAX_SHARED_THETA | DYNAX_SHARED_U | DYNAX_DISCRETE))
         return fail(DYNAX_ERR_INVALID_ARGUMENT, "unsupported flags 0x%x for lti_vjp", flags);
     if (!g_xsol && !g_ysol) return fail(DYNAX_ERR_INVALID_ARGUMENT, "need g_xsol or g_ysol");
-    if (g_u && (flags & DYNAX_SHARED_U))
-        return fail(DYNAX_ERR_INVALID_ARGUMENT, "g_u is not available with DYNAX_SHARED_U");
     if (!dynax_lti_supported(n, m, p))
         return fail(DYNAX_ERR_UNSUPPORTED_DIMS, "no dense-LTI kernel instantiated for (n,m,p)=(%d,%d,%d)", n, m, p);
     int rc = require_sm100();
     if (rc != DYNAX_OK) return rc;
-    const size_t need = adj_workspace_bytes(N, T, n);
+    const size_t need = adj_workspace_bytes(N, T, n) + ((flags & DYNAX_SHARED_U) ? gu_part_bytes(N, T, m) : 0);
     if (!ws || ws_bytes < need)
         return fail(DYNAX_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", need, ws ? ws_bytes : (size_t)0);
     if (!aligned16(ws)) return fail(DYNAX_ERR_WORKSPACE, "workspace must be 16-byte aligned");
@@ -135,6 +133,8 @@ int dynax_lti_vjp_f32(const float *A, const float *B, const float *C, const floa
         P.mp.shared = (flags & DYNAX_SHARED_THETA) ? 1 : 0;                                      \
         P.gp.gA = g_A; P.gp.gB = g_B; P.gp.gC = g_C; P.gp.gD = g_D;                              \
         P.x0 = x0; P.u = u; P.g_xsol = g_xsol; P.g_ysol = g_ysol; P.g_x0 = g_x0; P.g_u = g_u;    \
+        if (g_u && (flags & DYNAX_SHARED_U))   /* g_u is [T,m] then: summed over systems in the kernel */ \
+            P.gu_part = reinterpret_cast<float *>(reinterpret_cast<char *>(ws) + adj_workspace_bytes(N, T, a)); \
         P.shared_acc = reinterpret_cast<double *>(ws);                                           \
         P.ckpt = reinterpret_cast<float *>(reinterpret_cast<char *>(ws) + kAccBytes);            \
         P.N = N; P.T = T; P.dt = dt; P.discrete = (flags & DYNAX_DISCRETE) ? 1 : 0;              \

@@ -77,7 +77,8 @@ static bool rc_uses_tangent(uint32_t flags) { return env_int("DYNAX_GRAD_ALGO", 
 
 static size_t rc_workspace_bytes(int op, int64_t N, int64_t T, uint32_t flags) {
     if (op == DYNAX_OP_RC_LOSS_GRAD && rc_uses_tangent(flags)) return (flags & DYNAX_SHARED_THETA) ? kAccBytes : 0;
-    return adj_workspace_bytes(N, T, 3);
+    // general cotangents with a shared input series: + the per-CTA partial sums of g_u over systems
+    return adj_workspace_bytes(N, T, 3) + ((op == DYNAX_OP_RC_VJP && (flags & DYNAX_SHARED_U)) ? gu_part_bytes(N, T, 5) : 0);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -147,8 +148,6 @@ static int rc_adjoint(const float *theta, const float *x0, const float *u, const
     if (MODE == ADJ_MSE && ((lb == nullptr) != (ub == nullptr)))
         return fail(DYNAX_ERR_INVALID_ARGUMENT, "lb and ub must both be given or both be NULL");
     if (MODE == ADJ_VJP && !g_xsol && !g_ysol) return fail(DYNAX_ERR_INVALID_ARGUMENT, "need g_xsol or g_ysol");
-    if (MODE == ADJ_VJP && g_u && (flags & DYNAX_SHARED_U))
-        return fail(DYNAX_ERR_INVALID_ARGUMENT, "g_u is not available with DYNAX_SHARED_U (sum it on the caller side)");
     int rc = require_sm100();
     if (rc != DYNAX_OK) return rc;
     // the forward-mode kernel needs no scratch beyond the 1 KB of fp64 sums of a shared parameter vector; the
@@ -165,6 +164,8 @@ static int rc_adjoint(const float *theta, const float *x0, const float *u, const
     P.gp.g_theta = g_theta;
     P.x0 = x0; P.u = u; P.target = target; P.lb = lb; P.ub = ub; P.loss = loss;
     P.g_xsol = g_xsol; P.g_ysol = g_ysol; P.g_x0 = g_x0; P.g_u = g_u;
+    if (MODE == ADJ_VJP && g_u && (flags & DYNAX_SHARED_U))   // g_u is [T,5] then: summed over systems inside the kernel
+        P.gu_part = reinterpret_cast<float *>(reinterpret_cast<char *>(ws) + adj_workspace_bytes(N, T, 3));
     P.shared_acc = reinterpret_cast<double *>(ws);
     P.ckpt = ws ? reinterpret_cast<float *>(reinterpret_cast<char *>(ws) + kAccBytes) : nullptr;
     P.N = N; P.T = T; P.dt = dt;
@@ -308,11 +309,11 @@ long long dynax_debug_kernel_launches(int i) {
 const char *dynax_debug_last_kernel(void) { return dynax_debug_kernel_tag(last_launch_id); }
 
 size_t dynax_workspace_bytes(int op, int64_t N, int64_t T, int n, int m, int p, uint32_t flags) {
-    (void)m; (void)p;
+    (void)p;
     switch (op) {
         case DYNAX_OP_RC_LOSS_GRAD:
         case DYNAX_OP_RC_VJP: return rc_workspace_bytes(op, N, T, flags);
-        case DYNAX_OP_LTI_VJP: return adj_workspace_bytes(N, T, n);
+        case DYNAX_OP_LTI_VJP: return adj_workspace_bytes(N, T, n) + ((flags & DYNAX_SHARED_U) ? gu_part_bytes(N, T, m) : 0);
         default: return 0;
     }
 }

@@ -40,7 +40,8 @@ struct AdjParams {
     const float *g_xsol;  // VJP: [T,N,n] or NULL
     const float *g_ysol;  // VJP: [T,N,p] or NULL
     float *g_x0;          // [N,n] or NULL
-    float *g_u;           // VJP: [T,N,m] or NULL
+    float *g_u;           // VJP: [T,N,m] or NULL (SHARED_U: not used, see gu_part)
+    float *gu_part;       // VJP + SHARED_U: [gridDim.x][T][m] per-CTA sums of g_u over the CTA's systems (ws), or NULL
     float *ckpt;          // ws: [C][n][N]
     double *shared_acc;   // ws: [NOUT+1] when shared_theta (zeroed by the caller)
     int64_t N, T;
@@ -84,7 +85,13 @@ struct AdjCfg {
     static constexpr int GT_FOLD = GT_SMEM ? 4 : 1;
     static constexpr size_t RING_BYTES = sizeof(float) * (size_t)(S * STAGE) + sizeof(uint64_t) * NBAR;
     static constexpr size_t GT_OFF = (RING_BYTES + 15) / 16 * 16;
-    static constexpr size_t SMEM_BYTES = GT_SMEM ? GT_OFF + sizeof(double) * Model::NG * (size_t)TN : RING_BYTES;
+    static constexpr size_t GT_BYTES = GT_SMEM ? sizeof(double) * Model::NG * (size_t)TN : 0;
+    // a shared input series gets ONE g_u row per step: every thread parks its per-system row in this tile
+    // ([KC][m][TN], conflict-free), the CTA sums it over its systems once per segment (gu_part)
+    static constexpr bool GU_TILE = MODE == ADJ_VJP && SHARED_U;
+    static constexpr size_t GU_OFF = GT_OFF + GT_BYTES;
+    static constexpr size_t SMEM_BYTES = GU_TILE ? GU_OFF + sizeof(float) * KC * m * (size_t)TN
+                                                 : (GT_SMEM ? GT_OFF + GT_BYTES : RING_BYTES);
     static constexpr int THREADS = TN + 32;
 };
 
@@ -343,6 +350,15 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_adj_kernel(const __grid
 #pragma unroll
                     for (int d = 0; d < m; ++d) dst[d] = gu[d];
                 }
+                if constexpr (Cfg::GU_TILE) {
+                    if (P.gu_part != nullptr) {
+                        float gu[m];
+                        M.adj_u(sv, gy, gu);
+                        float *tile = reinterpret_cast<float *>(smem_raw + Cfg::GU_OFF);
+#pragma unroll
+                        for (int d = 0; d < m; ++d) tile[(j * m + d) * TN + tid] = active ? gu[d] : 0.f;
+                    }
+                }
                 M.adj_x(sv, gy, ax);
 #pragma unroll
                 for (int d = 0; d < n; ++d) a[d] = discrete ? ax[d] : (a[d] + ax[d]);
@@ -350,6 +366,22 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_adj_kernel(const __grid
         }
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&empty[s]);
+        if constexpr (Cfg::GU_TILE) {
+            if (P.gu_part != nullptr) {  // sum the segment's g_u rows over the CTA's systems: rows*m sums of TN values
+                asm volatile("bar.sync 1, %0;" ::"n"(TN) : "memory");
+                const float *tile = reinterpret_cast<const float *>(smem_raw + Cfg::GU_OFF);
+                float *part = P.gu_part + ((int64_t)blockIdx.x * P.T + t_begin + k0) * m;
+                for (int r = tid >> 5; r < rows * m; r += TN / 32) {
+                    float v = 0.f;
+#pragma unroll
+                    for (int e = 0; e < TN / 32; ++e) v += tile[r * TN + e * 32 + lane];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                    if (lane == 0) part[r] = v;
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(TN) : "memory");  // the tile is rewritten by the next segment
+            }
+        }
         // fold the fp32 partial sums into the fp64 totals (every segment; every GT_FOLD segments if they live in smem)
         if (Cfg::GT_FOLD == 1 || seg == 0 || (C - seg) % Cfg::GT_FOLD == 0) {
 #pragma unroll
@@ -496,6 +528,15 @@ __global__ void chunk_finalize_kernel(const double *chunk_acc, typename Model::P
         const double v = warp_sum(L);
         if ((threadIdx.x & 31) == 0) atomicAdd(shared_acc + NOUT, v);
     }
+}
+
+// g_u of a SHARED input series: sum the per-CTA partial rows (gu_part[cta][T*m]) into g_u[T*m], in a fixed order.
+static __global__ void gu_reduce_kernel(const float *part, float *g_u, int64_t elems, int64_t ctas) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= elems) return;
+    float v = 0.f;
+    for (int64_t c = 0; c < ctas; ++c) v += part[c * elems + e];
+    g_u[e] = v;
 }
 
 }  // namespace dynax

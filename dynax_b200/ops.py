@@ -187,11 +187,10 @@ def rc_vjp(theta, x0, u, dt, g_xsol=None, g_ysol=None, need_theta=True, need_x0=
         g_ysol = _f32c(g_ysol, "g_ysol").reshape(T, N, 1)
     gth = torch.empty((1 if shared_th else N, 7), dtype=torch.float32, device=dev) if need_theta else None
     gx0 = torch.empty((N, 3), dtype=torch.float32, device=dev) if need_x0 else None
-    # with a shared input series the per-system g_u is produced against a broadcast view and summed here
-    u_k = u.expand(T, N, 5).contiguous() if (shared_u and need_u) else u
-    gu = torch.empty((T, N, 5), dtype=torch.float32, device=dev) if need_u else None
-    flags = ((SHARED_THETA if shared_th else 0) | (SHARED_U if (shared_u and not need_u) else 0) |
-             (DISCRETE if discrete else 0))
+    # a shared input series has ONE cotangent row per step: the kernel sums g_u over the systems (no [T,N,5] array)
+    u_k = u
+    gu = torch.empty((T, 1 if shared_u else N, 5), dtype=torch.float32, device=dev) if need_u else None
+    flags = ((SHARED_THETA if shared_th else 0) | (SHARED_U if shared_u else 0) | (DISCRETE if discrete else 0))
     if time_chunks is None:
         time_chunks = -1 if (not discrete and 0 < N <= 8192 and T >= 512) else 0
     chunked = time_chunks != 0 and not discrete and not (flags & SHARED_U) and N > 0
@@ -206,8 +205,6 @@ def rc_vjp(theta, x0, u, dt, g_xsol=None, g_ysol=None, need_theta=True, need_x0=
             ws = _ws(lib().dynax_workspace_bytes(_lib.OP_RC_VJP, N, T, 3, 5, 1, flags), dev)
             check(lib().dynax_rc_vjp_f32(_ptr(theta), _ptr(x0), _ptr(u_k), _ptr(g_xsol), _ptr(g_ysol), _ptr(gth),
                                          _ptr(gx0), _ptr(gu), N, T, float(dt), flags, _ptr(ws), ws.numel(), _stream()))
-    if gu is not None and shared_u:
-        gu = gu.sum(dim=1, keepdim=True)
     return gth, gx0, gu
 
 
@@ -320,10 +317,9 @@ def lti_vjp(A, B, C, D, x0, u, dt, g_xsol=None, g_ysol=None, need_mats=True, nee
     gm = [torch.empty((L,) + s, dtype=torch.float32, device=dev) if need_mats else None
           for s in ((n, n), (n, m), (p, n), (p, m))]
     gx0 = torch.empty((N, n), dtype=torch.float32, device=dev) if need_x0 else None
-    u_k = u.expand(T, N, m).contiguous() if (shared_u and need_u) else u
-    gu = torch.empty((T, N, m), dtype=torch.float32, device=dev) if need_u else None
-    flags = ((SHARED_THETA if shared_th else 0) | (SHARED_U if (shared_u and not need_u) else 0) |
-             (DISCRETE if discrete else 0))
+    u_k = u      # a shared input series: g_u[T,1,m] is summed over the systems inside the kernel
+    gu = torch.empty((T, 1 if shared_u else N, m), dtype=torch.float32, device=dev) if need_u else None
+    flags = ((SHARED_THETA if shared_th else 0) | (SHARED_U if shared_u else 0) | (DISCRETE if discrete else 0))
     if time_chunks is None:
         time_chunks = -1 if (not discrete and 0 < N <= 4096 and T >= 512) else 0
     chunked = time_chunks != 0 and not discrete and not (flags & SHARED_U) and N > 0
@@ -340,8 +336,6 @@ def lti_vjp(A, B, C, D, x0, u, dt, g_xsol=None, g_ysol=None, need_mats=True, nee
             check(lib().dynax_lti_vjp_f32(_ptr(A), _ptr(B), _ptr(C), _ptr(D), _ptr(x0), _ptr(u_k), _ptr(g_xsol),
                                           _ptr(g_ysol), _ptr(gm[0]), _ptr(gm[1]), _ptr(gm[2]), _ptr(gm[3]), _ptr(gx0),
                                           _ptr(gu), N, T, n, m, p, float(dt), flags, _ptr(ws), ws.numel(), _stream()))
-    if gu is not None and shared_u:
-        gu = gu.sum(dim=1, keepdim=True)
     return gm[0], gm[1], gm[2], gm[3], gx0, gu
 
 

@@ -151,7 +151,8 @@ int dynax_tabular_interp_f32(const float *ts, const float *xs, int64_t n_rows, i
 /* General-cotangent VJP of dynax_rc_forward_f32 (what jax.vjp/jax.grad of simulator.apply needs
  * for an arbitrary downstream loss).  g_xsol:[T,N,3] or NULL, g_ysol:[T,N,1] or NULL (at least
  * one non-NULL).  Outputs (each may be NULL): g_theta:[N,7] ([7] if SHARED_THETA), g_x0:[N,3],
- * g_u:[T,N,5] (not available with DYNAX_SHARED_U). */
+ * g_u:[T,N,5]; with DYNAX_SHARED_U g_u:[T,5], the cotangent of the ONE shared series = the sum over systems, reduced
+ * inside the kernel (per-CTA sums in the workspace, then a fixed-order reduction: bit-reproducible). */
 int dynax_rc_vjp_f32(const float *theta, const float *x0, const float *u,
                      const float *g_xsol, const float *g_ysol,
                      float *g_theta, float *g_x0, float *g_u,

@@ -163,3 +163,20 @@ def test_vjp_time_parallel(T, ops, n, m, p, N, Tn, chunks, shared):
         ref = r[key].sum(0, keepdims=True) if (shared and key in ("gA", "gB", "gC", "gD")) else r[key]
         assert rel_err(got.cpu().numpy().reshape(ref.shape), ref, floor=1.0) < 1e-4, key
         assert rel_err(got.cpu().numpy(), s_.cpu().numpy(), floor=1.0) < 1e-4, key
+
+
+@pytest.mark.parametrize("n,m,p", [(4, 3, 4), (3, 5, 1), (2, 1, 1)])
+def test_vjp_shared_input_series(T, ops, n, m, p):
+    """g_u of a shared input series u[T,1,m]: summed over systems inside the kernel (dense models)."""
+    N, Tn, dt = 150, 60, 0.05
+    A, B, C, D, x0, u = make(N, Tn, n, m, p, 47)
+    u1 = u[:, :1]
+    rng = np.random.default_rng(48)
+    gx = rng.normal(size=(Tn, N, n)).astype(np.float32)
+    gy = rng.normal(size=(Tn, N, p)).astype(np.float32)
+    out = ops.lti_vjp(*(cu(T, v) for v in (A, B, C, D, x0, u1)), dt, cu(T, gx), cu(T, gy), time_chunks=0)
+    r = orc.lti_vjp(A, B, C, D, x0, np.repeat(u1, N, 1), dt, gx, gy, np.float64)
+    assert out[5].shape == (Tn, 1, m)
+    assert rel_err(out[5].cpu().numpy()[:, 0], r["gu"].sum(1), floor=1.0) < 1e-4
+    for got, key in zip(out[:5], ("gA", "gB", "gC", "gD", "gx0")):
+        assert rel_err(got.cpu().numpy(), r[key], floor=1.0) < 1e-4, key

@@ -288,3 +288,29 @@ def test_workspace_and_errors(T, ops):
     rc = L.dynax_rc_loss_grad_f32(th.data_ptr(), x0.data_ptr(), u.data_ptr(), target.data_ptr(), None, None,
                                   loss.data_ptr(), grad.data_ptr(), None, 8, 0, 3600.0, 0, None, 0, None)
     assert rc == -1      # T must be >= 1 for a mean over time
+
+
+@pytest.mark.parametrize("N,Tn", [(300, 190), (1, 40), (129, 13)])
+def test_vjp_shared_input_series_sums_g_u_in_kernel(T, ops, N, Tn):
+    """A shared input series u[T,1,5] has ONE cotangent row per step = the sum over systems of the per-system rows; the
+    kernel reduces it (per-CTA sums + a fixed-order reduction), no [T,N,5] array is materialised.  Against the fp64
+    oracle's per-system g_u summed over systems; bit-reproducible from run to run; and through autograd."""
+    rng = np.random.default_rng(46)
+    th, x0, u = orc.synth_theta(N, 46), orc.synth_x0(N, 46), orc.synth_u(Tn, 1, 46)
+    gx = rng.normal(size=(Tn, N, 3)).astype(np.float32)
+    gy = rng.normal(size=(Tn, N, 1)).astype(np.float32)
+    a = (cu(T, th), cu(T, x0), cu(T, u))
+    gth, gx0, gu = ops.rc_vjp(*a, 3600.0, cu(T, gx), cu(T, gy), time_chunks=0)
+    assert gu.shape == (Tn, 1, 5)
+    uN = np.repeat(u, N, 1)
+    rth, rx0, ru = orc.rc_vjp(th, x0, uN, 3600.0, gx, gy, np.float64)
+    fth, fx0, fu = orc.rc_vjp(th, x0, uN, 3600.0, gx, gy, np.float32)
+    e, e32 = rel_err(gu.cpu().numpy()[:, 0], ru.sum(1), floor=1.0), rel_err(fu.astype(np.float64).sum(1), ru.sum(1), floor=1.0)
+    assert e < max(GRAD_RTOL, 1.25 * e32), (e, e32)
+    assert normwise(gth.cpu().numpy(), rth).max() <= max(GRAD_RTOL, 1.25 * normwise(fth, rth).max())
+    gth2, _, gu2 = ops.rc_vjp(*a, 3600.0, cu(T, gx), cu(T, gy), time_chunks=0)
+    assert T.equal(gu, gu2)                                        # fixed-order reduction
+    tu = cu(T, u[:, 0]).requires_grad_(True)                       # u[T,5] through autograd
+    xs, ys = ops.rc_rollout(a[0], a[1], tu, 3600.0)
+    ((xs * cu(T, gx)).sum() + (ys * cu(T, gy)).sum()).backward()
+    assert tu.grad.shape == (Tn, 5) and T.allclose(tu.grad, gu[:, 0], rtol=1e-5, atol=1e-6 * float(gu.abs().max()))
