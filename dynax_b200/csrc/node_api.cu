@@ -9,6 +9,16 @@
 
 using namespace dynax;
 
+template <int HID>
+static int launch_node_tc(const NodeTcParams &Q, int64_t grid, cudaStream_t st) {
+    using C = tcf::Cfg<HID>;
+    int rc = set_smem(node_tc_kernel<HID>, C::SMEM_BYTES);
+    if (rc != DYNAX_OK) return rc;
+    node_tc_kernel<HID><<<(unsigned)grid, C::NTHR, C::SMEM_BYTES, st>>>(Q);
+    DYNAX_CUDA_TRY(cudaGetLastError());
+    return DYNAX_OK;
+}
+
 extern "C" int dynax_node_rk4_forward_f32(const float *W1, const float *b1, const float *W2, const float *b2,
                                           const float *W3, const float *b3, const float *x0, const float *u,
                                           float *xsol, float *ysol, float *x_final, int64_t N, int64_t T, int n,
@@ -31,32 +41,33 @@ extern "C" int dynax_node_rk4_forward_stages_f32(const float *W1, const float *b
         return fail(DYNAX_ERR_INVALID_ARGUMENT, "weights, x0 and u must be non-NULL");
     if (flags & ~(DYNAX_SHARED_U | DYNAX_SOLVER_EULER))
         return fail(DYNAX_ERR_INVALID_ARGUMENT, "unsupported flags 0x%x for node_rk4_forward", flags);
-    if (!(n == 3 && m == 5 && p == 1 && hidden == 64))
-        return fail(DYNAX_ERR_UNSUPPORTED_DIMS, "MLP kernel is instantiated for (n,m,p,hidden)=(3,5,1,64), got (%d,%d,%d,%d)", n, m, p, hidden);
+    if (!(n == 3 && m == 5 && p == 1 && (hidden == 32 || hidden == 64 || hidden == 128)))
+        return fail(DYNAX_ERR_UNSUPPORTED_DIMS, "MLP kernel is instantiated for (n,m,p)=(3,5,1), hidden in {32,64,128}; got (%d,%d,%d,%d)", n, m, p, hidden);
     int rc = require_sm100();
     if (rc != DYNAX_OK) return rc;
     if (T == 0) {
         if (x_final) DYNAX_CUDA_TRY(cudaMemcpyAsync(x_final, x0, sizeof(float) * n * N, cudaMemcpyDeviceToDevice, st));
         return DYNAX_OK;
     }
-    // Default: tensor-core kernel (tcgen05 + TMEM, node_tc.cuh).  DYNAX_NODE_IMPL=0 selects the CUDA-core
-    // policy kernel (mlp_model.cuh), which is also what a shared input series uses.
+    // Product path: the tcgen05 kernel (node_tc.cuh), per-system or shared input series.  DYNAX_NODE_IMPL=0 selects the
+    // CUDA-core policy kernel (mlp_model.cuh, hidden = 64 only), kept as an independent cross-check for the tests.
     const char *impl = getenv("DYNAX_NODE_IMPL");
-    if (!(flags & DYNAX_SHARED_U) && !(impl && impl[0] == '0')) {
+    if (!(impl && impl[0] == '0')) {
         NodeTcParams Q;
         Q.W1 = W1; Q.b1 = b1; Q.W2 = W2; Q.b2 = b2; Q.W3 = W3; Q.b3 = b3;
         Q.x0 = x0; Q.u = u; Q.xsol = xsol; Q.ysol = ysol; Q.x_final = x_final; Q.stage_x = stage_x;
         Q.N = N; Q.T = T; Q.dt = dt; Q.rk4 = (flags & DYNAX_SOLVER_EULER) ? 0 : 1;
+        Q.shared_u = (flags & DYNAX_SHARED_U) ? 1 : 0;
         const bool r16 = (N % 4) == 0;
         Q.bulk_in = r16 && aligned16(u);
         Q.bulk_out = r16 && (!xsol || aligned16(xsol)) && (!ysol || aligned16(ysol)) && (!stage_x || aligned16(stage_x));
-        rc = set_smem(node_tc_kernel, tc::SMEM_BYTES);
-        if (rc != DYNAX_OK) return rc;
         const int64_t grid = (N + tc::TN - 1) / tc::TN;
-        node_tc_kernel<<<(unsigned)grid, tc::TN + 32, tc::SMEM_BYTES, st>>>(Q);
-        DYNAX_CUDA_TRY(cudaGetLastError());
-        return DYNAX_OK;
+        if (hidden == 32) return launch_node_tc<32>(Q, grid, st);
+        if (hidden == 64) return launch_node_tc<64>(Q, grid, st);
+        return launch_node_tc<128>(Q, grid, st);
     }
+    if (hidden != 64)
+        return fail(DYNAX_ERR_UNSUPPORTED_DIMS, "the CUDA-core cross-check kernel (DYNAX_NODE_IMPL=0) is instantiated for hidden = 64 only");
     if (stage_x != nullptr && !(flags & DYNAX_SOLVER_EULER))
         return fail(DYNAX_ERR_INVALID_ARGUMENT, "stage points are emitted by the tcgen05 kernel only (per-system u, DYNAX_NODE_IMPL != 0)");
     using M = MlpModel<3, 5, 1, 64>;

@@ -40,6 +40,35 @@ def test_matches_oracle(T, monkeypatch, N, Tn, euler, impl):
     assert np.array_equal(xf.cpu().numpy(), xs[-1].cpu().numpy())
 
 
+@pytest.mark.parametrize("hidden", [32, 64, 128])
+@pytest.mark.parametrize("N,Tn,euler,scale,shared", [(300, 40, False, 0.1, False), (131, 19, True, 1.0, False),
+                                                      (517, 24, False, 1.0, True), (5, 9, False, 3.0, False)])
+def test_hidden_widths_match_oracle(T, hidden, N, Tn, euler, scale, shared):
+    """The tcgen05 kernel is instantiated for hidden widths 32, 64 and 128 (TMEM 128 / 256 / 512 columns); per-system
+    and shared input series; O(1)..O(3) weights drive tanh into saturation (the quad reciprocal's clamp)."""
+    from dynax_b200 import ops
+    W = orc.synth_mlp(300 + hidden, hidden=hidden, scale=scale)
+    x0, u = inputs(N, Tn, 301 + hidden)
+    ud = cu(T, u[:, 0]) if shared else cu(T, u)
+    xs, ys, xf = ops.node_rk4_forward(*(cu(T, w) for w in W), cu(T, x0), ud, 0.1, emit_final=True, euler=euler)
+    xr, yr = orc.node_rk4_rollout(*W, x0, u[:, :1] if shared else u, 0.1, np.float64, euler=euler)
+    assert rel_err(xs.cpu().numpy(), xr, floor=1.0) < 1e-5
+    assert rel_err(ys.cpu().numpy(), yr, floor=1.0) < 1e-5
+    assert np.array_equal(xf.cpu().numpy(), xs[-1].cpu().numpy())
+
+
+def test_tanh_saturation_is_exact(T):
+    """Pre-activations far beyond the clamp of the shared reciprocal (|x| ~ 1e3) give tanh = +-1 exactly, never NaN."""
+    from dynax_b200 import ops
+    W = [w.copy() for w in orc.synth_mlp(311, scale=1.0)]
+    W[0] *= 300.0                                              # layer-1 pre-activations of order 1e3, both signs
+    x0, u = inputs(256, 6, 312)
+    xs, _, _ = ops.node_rk4_forward(*(cu(T, w) for w in W), cu(T, x0), cu(T, u), 0.05)
+    xr, _ = orc.node_rk4_rollout(*W, x0, u, 0.05, np.float64)
+    assert np.isfinite(xs.cpu().numpy()).all()
+    assert rel_err(xs.cpu().numpy(), xr, floor=1.0) < 1e-5
+
+
 def test_tensor_core_kernel_saturating_tanh_and_chaining(T):
     """tcgen05 kernel with O(1) weights (saturating tanh), ragged N, and T steps == T1 + (T-T1) steps."""
     from dynax_b200 import ops
@@ -67,7 +96,7 @@ def test_strong_nonlinearity_and_shared_u(T):
 def test_unsupported_dims(T):
     from dynax_b200 import ops
     from dynax_b200._lib import DynaxError
-    W = orc.synth_mlp(105, hidden=32)
+    W = orc.synth_mlp(105, hidden=48)                          # instantiated: 32, 64, 128
     x0, u = inputs(8, 4, 106)
     with pytest.raises(DynaxError) as e:
         ops.node_rk4_forward(*(cu(T, w) for w in W), cu(T, x0), cu(T, u), 0.1)
