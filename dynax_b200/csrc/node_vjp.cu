@@ -25,20 +25,31 @@
 namespace dynax {
 
 namespace nv {
-constexpr int TN = 128, HID = 64, NX = 3, NU = 5, NIN = 8, LD = 132;  // LD: padded tile row (bank-conflict-free float4 rows)
-using M = MlpModel<3, 5, 1, 64>;
-constexpr int O_TILES = (M::SMEM_FLOATS + 3) & ~3;
-constexpr int O_H1 = O_TILES, O_H2 = O_H1 + HID * LD, O_D2 = O_H2 + HID * LD, O_D1 = O_D2 + HID * LD,
-              O_Z = O_D1 + HID * LD, O_D3 = O_Z + NIN * LD, O_END = O_D3 + 4 * LD;
-constexpr size_t SMEM_BYTES = sizeof(float) * O_END;
-// fp64 accumulator layout
-constexpr int A_W1 = 0, A_B1 = A_W1 + HID * NIN, A_W2 = A_B1 + HID, A_B2 = A_W2 + HID * HID, A_W3 = A_B2 + HID,
-              A_B3 = A_W3 + NX * HID, A_END = A_B3 + NX;
+constexpr int TN = 128, NX = 3, NU = 5, NIN = 8, LD = 132;  // LD: padded tile row (bank-conflict-free float4 rows)
 constexpr int FLUSH = 16;
+// Per hidden width (32 or 64 here; the tcgen05 kernel of node_vjp_tc.cuh is the hidden = 64 product path):
+template <int HID>
+struct L {
+    static_assert(HID == 32 || HID == 64, "tile GEMM thread mappings below");
+    using M = MlpModel<3, 5, 1, HID>;
+    static constexpr int O_TILES = (M::SMEM_FLOATS + 3) & ~3;
+    static constexpr int O_H1 = O_TILES, O_H2 = O_H1 + HID * LD, O_D2 = O_H2 + HID * LD, O_D1 = O_D2 + HID * LD,
+                         O_Z = O_D1 + HID * LD, O_D3 = O_Z + NIN * LD, O_END = O_D3 + 4 * LD;
+    static constexpr size_t SMEM_BYTES = sizeof(float) * O_END;
+    // fp64 accumulator layout
+    static constexpr int A_W1 = 0, A_B1 = A_W1 + HID * NIN, A_W2 = A_B1 + HID, A_B2 = A_W2 + HID * HID, A_W3 = A_B2 + HID,
+                         A_B3 = A_W3 + NX * HID, A_END = A_B3 + NX;
+    // thread mappings of the batch contractions (128 threads):
+    static constexpr int PJ = HID / 16, PI = HID / 8;  // dW2: 16 x 8 threads, PJ rows x PI interleaved columns each
+    static constexpr int W1PT = HID / 16;              // dW1: HID*8 entries, W1PT consecutive ones of a row each
+    static constexpr int W3PT = HID / 32;              // dW3: 3 x 32 threads, W3PT columns (32 apart) each
+};
+constexpr int A_END_MAX = L<64>::A_END;
 }  // namespace nv
 
+template <int HID>
 struct NodeVjpParams {
-    nv::M::Ptrs mp;
+    typename nv::L<HID>::M::Ptrs mp;
     const float *x0, *u, *xsol, *g_xsol, *g_ysol;
     const float *stage_x;  // [T,N,9] stage points saved by the forward kernel, or NULL (recomputed)
     float *g_x0, *g_u;
@@ -47,8 +58,14 @@ struct NodeVjpParams {
     float dt;
 };
 
-__global__ void __launch_bounds__(nv::TN, 1) node_vjp_kernel(const NodeVjpParams P) {
+template <int HID>
+__global__ void __launch_bounds__(nv::TN, 1) node_vjp_kernel(const NodeVjpParams<HID> P) {
     using namespace nv;
+    using Ly = L<HID>;
+    using M = typename Ly::M;
+    constexpr int O_H1 = Ly::O_H1, O_H2 = Ly::O_H2, O_D2 = Ly::O_D2, O_D1 = Ly::O_D1, O_Z = Ly::O_Z, O_D3 = Ly::O_D3;
+    constexpr int A_W1 = Ly::A_W1, A_B1 = Ly::A_B1, A_W2 = Ly::A_W2, A_B2 = Ly::A_B2, A_W3 = Ly::A_W3, A_B3 = Ly::A_B3;
+    constexpr int PJ = Ly::PJ, PI = Ly::PI, W1PT = Ly::W1PT, W3PT = Ly::W3PT;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *sm = reinterpret_cast<float *>(smem_raw);
     float *H1 = sm + O_H1, *H2 = sm + O_H2, *D2 = sm + O_D2, *D1 = sm + O_D1, *Z = sm + O_Z, *D3 = sm + O_D3;
@@ -65,39 +82,42 @@ __global__ void __launch_bounds__(nv::TN, 1) node_vjp_kernel(const NodeVjpParams
     const bool rk4 = P.mp.rk4 != 0;
 
     // register accumulators (this thread's share of every weight gradient)
-    float aW2[4][8], aW1[4], aW3[2], aB = 0.f, aB3 = 0.f;
+    float aW2[PJ][PI], aW1[W1PT], aW3[W3PT], aB = 0.f, aB3 = 0.f;
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-        aW1[a] = 0.f;
+    for (int a = 0; a < PJ; ++a)
 #pragma unroll
-        for (int b = 0; b < 8; ++b) aW2[a][b] = 0.f;
-    }
-    aW3[0] = aW3[1] = 0.f;
-    // dW2 patch: rows j0..j0+3, cols i0 + 8b (interleaved: the 8 lanes of a quarter-warp then read 8 CONSECUTIVE tile
+        for (int b = 0; b < PI; ++b) aW2[a][b] = 0.f;
+#pragma unroll
+    for (int a = 0; a < W1PT; ++a) aW1[a] = 0.f;
+#pragma unroll
+    for (int a = 0; a < W3PT; ++a) aW3[a] = 0.f;
+    // dW2 patch: rows j0..j0+PJ-1, cols i0 + 8b (interleaved: the 8 lanes of a quarter-warp then read 8 CONSECUTIVE tile
     // rows, which LD = 132 spreads over all 32 banks; 8 rows apart they would all hit the same banks)
-    const int j0 = (tid >> 3) * 4, i0 = tid & 7;
-    const int w1i = tid >> 1, w1c = (tid & 1) * 4;              // dW1[w1i][w1c..w1c+3]
-    const int w3d = tid >> 5, w3j = tid & 31;                   // dW3[w3d][w3j], dW3[w3d][w3j + 32]   (tid < 96)
+    const int j0 = (tid >> 3) * PJ, i0 = tid & 7;
+    const int w1i = (tid * W1PT) / NIN, w1c = (tid * W1PT) % NIN;  // dW1[w1i][w1c..w1c+W1PT-1]
+    const int w3d = tid >> 5, w3j = tid & 31;                      // dW3[w3d][w3j + 32a], a < W3PT   (tid < 96)
+    const bool has_b = tid < 2 * HID;                              // db2[tid] (tid < HID) or db1[tid - HID]
 
     auto flush = [&]() {
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+        for (int a = 0; a < PJ; ++a)
 #pragma unroll
-            for (int b = 0; b < 8; ++b) {
+            for (int b = 0; b < PI; ++b) {
                 atomicAdd(P.acc + A_W2 + (j0 + a) * HID + i0 + 8 * b, (double)aW2[a][b]);
                 aW2[a][b] = 0.f;
             }
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
+        for (int a = 0; a < W1PT; ++a) {
             atomicAdd(P.acc + A_W1 + w1i * NIN + w1c + a, (double)aW1[a]);
             aW1[a] = 0.f;
         }
         if (tid < 96) {
-            atomicAdd(P.acc + A_W3 + w3d * HID + w3j, (double)aW3[0]);
-            atomicAdd(P.acc + A_W3 + w3d * HID + w3j + 32, (double)aW3[1]);
+#pragma unroll
+            for (int a = 0; a < W3PT; ++a) atomicAdd(P.acc + A_W3 + w3d * HID + w3j + 32 * a, (double)aW3[a]);
         }
-        aW3[0] = aW3[1] = 0.f;
-        atomicAdd(P.acc + (tid < 64 ? A_B2 + tid : A_B1 + tid - 64), (double)aB);
+#pragma unroll
+        for (int a = 0; a < W3PT; ++a) aW3[a] = 0.f;
+        if (has_b) atomicAdd(P.acc + (tid < HID ? A_B2 + tid : A_B1 + tid - HID), (double)aB);
         aB = 0.f;
         if (tid < NX) atomicAdd(P.acc + A_B3 + tid, (double)aB3);
         aB3 = 0.f;
@@ -163,21 +183,21 @@ __global__ void __launch_bounds__(nv::TN, 1) node_vjp_kernel(const NodeVjpParams
         __syncthreads();
         // ---- batch contractions over the CTA's 128 rows
         for (int r = 0; r < TN; r += 4) {
-            float4 dj[4], hi[8];
+            float4 dj[PJ], hi[PI];
 #pragma unroll
-            for (int a = 0; a < 4; ++a) dj[a] = *reinterpret_cast<const float4 *>(D2 + (j0 + a) * LD + r);
+            for (int a = 0; a < PJ; ++a) dj[a] = *reinterpret_cast<const float4 *>(D2 + (j0 + a) * LD + r);
 #pragma unroll
-            for (int b = 0; b < 8; ++b) hi[b] = *reinterpret_cast<const float4 *>(H1 + (i0 + 8 * b) * LD + r);
+            for (int b = 0; b < PI; ++b) hi[b] = *reinterpret_cast<const float4 *>(H1 + (i0 + 8 * b) * LD + r);
 #pragma unroll
-            for (int a = 0; a < 4; ++a)
+            for (int a = 0; a < PJ; ++a)
 #pragma unroll
-                for (int b = 0; b < 8; ++b) {
+                for (int b = 0; b < PI; ++b) {
                     aW2[a][b] = fmaf(dj[a].x, hi[b].x, aW2[a][b]); aW2[a][b] = fmaf(dj[a].y, hi[b].y, aW2[a][b]);
                     aW2[a][b] = fmaf(dj[a].z, hi[b].z, aW2[a][b]); aW2[a][b] = fmaf(dj[a].w, hi[b].w, aW2[a][b]);
                 }
             const float4 d1r = *reinterpret_cast<const float4 *>(D1 + w1i * LD + r);
 #pragma unroll
-            for (int a = 0; a < 4; ++a) {
+            for (int a = 0; a < W1PT; ++a) {
                 const float4 zr = *reinterpret_cast<const float4 *>(Z + (w1c + a) * LD + r);
                 aW1[a] = fmaf(d1r.x, zr.x, aW1[a]); aW1[a] = fmaf(d1r.y, zr.y, aW1[a]);
                 aW1[a] = fmaf(d1r.z, zr.z, aW1[a]); aW1[a] = fmaf(d1r.w, zr.w, aW1[a]);
@@ -185,14 +205,16 @@ __global__ void __launch_bounds__(nv::TN, 1) node_vjp_kernel(const NodeVjpParams
             if (tid < 96) {
                 const float4 d3r = *reinterpret_cast<const float4 *>(D3 + w3d * LD + r);
 #pragma unroll
-                for (int a = 0; a < 2; ++a) {
+                for (int a = 0; a < W3PT; ++a) {
                     const float4 hr = *reinterpret_cast<const float4 *>(H2 + (w3j + 32 * a) * LD + r);
                     aW3[a] = fmaf(d3r.x, hr.x, aW3[a]); aW3[a] = fmaf(d3r.y, hr.y, aW3[a]);
                     aW3[a] = fmaf(d3r.z, hr.z, aW3[a]); aW3[a] = fmaf(d3r.w, hr.w, aW3[a]);
                 }
             }
-            const float4 br = *reinterpret_cast<const float4 *>((tid < 64 ? D2 + tid * LD : D1 + (tid - 64) * LD) + r);
-            aB += (br.x + br.y) + (br.z + br.w);
+            if (has_b) {
+                const float4 br = *reinterpret_cast<const float4 *>((tid < HID ? D2 + tid * LD : D1 + (tid - HID) * LD) + r);
+                aB += (br.x + br.y) + (br.z + br.w);
+            }
             if (tid < NX) {
                 const float4 b3 = *reinterpret_cast<const float4 *>(D3 + tid * LD + r);
                 aB3 += (b3.x + b3.y) + (b3.z + b3.w);
@@ -273,18 +295,36 @@ __global__ void __launch_bounds__(nv::TN, 1) node_vjp_kernel(const NodeVjpParams
     }
 }
 
-__global__ void node_vjp_finalize_kernel(const double *acc, float *gW1, float *gb1, float *gW2, float *gb2, float *gW3,
-                                         float *gb3) {
+__global__ void node_vjp_finalize_kernel(const double *acc, int hid, float *gW1, float *gb1, float *gW2, float *gb2,
+                                         float *gW3, float *gb3) {
     using namespace nv;
+    const int A_B1 = hid * NIN, A_W2 = A_B1 + hid, A_B2 = A_W2 + hid * hid, A_W3 = A_B2 + hid, A_B3 = A_W3 + NX * hid,
+              A_END = A_B3 + NX;  // the layout of L<hid>
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= A_END) return;
     const float v = (float)acc[t];
-    if (t < A_B1) { if (gW1) gW1[t - A_W1] = v; }
+    if (t < A_B1) { if (gW1) gW1[t] = v; }
     else if (t < A_W2) { if (gb1) gb1[t - A_B1] = v; }
     else if (t < A_B2) { if (gW2) gW2[t - A_W2] = v; }
     else if (t < A_W3) { if (gb2) gb2[t - A_B2] = v; }
     else if (t < A_B3) { if (gW3) gW3[t - A_W3] = v; }
     else { if (gb3) gb3[t - A_B3] = v; }
+}
+
+template <int HID>
+static int launch_node_vjp_cc(const float *W1, const float *b1, const float *W2, const float *b2, const float *W3,
+                              const float *b3, const float *x0, const float *u, const float *xsol, const float *stage_x,
+                              const float *g_xsol, const float *g_ysol, float *g_x0, float *g_u, double *acc, int64_t N,
+                              int64_t T, float dt, int rk4, cudaStream_t st) {
+    NodeVjpParams<HID> P;
+    P.mp.W1 = W1; P.mp.b1 = b1; P.mp.W2 = W2; P.mp.b2 = b2; P.mp.W3 = W3; P.mp.b3 = b3; P.mp.rk4 = rk4;
+    P.x0 = x0; P.u = u; P.xsol = xsol; P.stage_x = stage_x; P.g_xsol = g_xsol; P.g_ysol = g_ysol; P.g_x0 = g_x0; P.g_u = g_u;
+    P.acc = acc; P.N = N; P.T = T; P.dt = dt;
+    int rc = set_smem(node_vjp_kernel<HID>, nv::L<HID>::SMEM_BYTES);
+    if (rc != DYNAX_OK) return rc;
+    node_vjp_kernel<HID><<<(unsigned)((N + nv::TN - 1) / nv::TN), nv::TN, nv::L<HID>::SMEM_BYTES, st>>>(P);
+    DYNAX_CUDA_TRY(cudaGetLastError());
+    return DYNAX_OK;
 }
 
 }  // namespace dynax
@@ -293,7 +333,7 @@ using namespace dynax;
 
 extern "C" {
 
-size_t dynax_node_rk4_vjp_workspace(void) { return sizeof(double) * ((nv::A_END + 31) & ~31); }
+size_t dynax_node_rk4_vjp_workspace(void) { return sizeof(double) * ((nv::A_END_MAX + 31) & ~31); }
 
 int dynax_node_rk4_vjp_f32(const float *W1, const float *b1, const float *W2, const float *b2, const float *W3,
                            const float *b3, const float *x0, const float *u, const float *xsol, const float *g_xsol,
@@ -319,35 +359,36 @@ int dynax_node_rk4_vjp_stages_f32(const float *W1, const float *b1, const float 
     if (!xsol && T > 1) return fail(DYNAX_ERR_INVALID_ARGUMENT, "xsol (the forward trajectory) must be given");
     if (!g_xsol && !g_ysol) return fail(DYNAX_ERR_INVALID_ARGUMENT, "need g_xsol or g_ysol");
     if (flags & ~DYNAX_SOLVER_EULER) return fail(DYNAX_ERR_INVALID_ARGUMENT, "unsupported flags 0x%x for node_rk4_vjp", flags);
-    if (!(n == 3 && m == 5 && p == 1 && hidden == 64))
-        return fail(DYNAX_ERR_UNSUPPORTED_DIMS, "MLP kernel is instantiated for (n,m,p,hidden)=(3,5,1,64), got (%d,%d,%d,%d)", n, m, p, hidden);
+    if (!(n == 3 && m == 5 && p == 1 && (hidden == 32 || hidden == 64)))
+        return fail(DYNAX_ERR_UNSUPPORTED_DIMS, "MLP gradient kernels are instantiated for (n,m,p)=(3,5,1), hidden in {32,64}; got (%d,%d,%d,%d)", n, m, p, hidden);
     const size_t need = dynax_node_rk4_vjp_workspace();
     if (!ws || ws_bytes < need || !aligned16(ws)) return fail(DYNAX_ERR_WORKSPACE, "workspace must hold %zu bytes (16-byte aligned)", need);
     int rc = require_sm100();
     if (rc != DYNAX_OK) return rc;
-    NodeVjpParams P;
-    P.mp.W1 = W1; P.mp.b1 = b1; P.mp.W2 = W2; P.mp.b2 = b2; P.mp.W3 = W3; P.mp.b3 = b3;
-    P.mp.rk4 = (flags & DYNAX_SOLVER_EULER) ? 0 : 1;
-    P.x0 = x0; P.u = u; P.xsol = xsol; P.stage_x = stage_x; P.g_xsol = g_xsol; P.g_ysol = g_ysol; P.g_x0 = g_x0; P.g_u = g_u;
-    P.acc = reinterpret_cast<double *>(ws); P.N = N; P.T = T; P.dt = dt;
+    double *acc = reinterpret_cast<double *>(ws);
+    const int rk4 = (flags & DYNAX_SOLVER_EULER) ? 0 : 1;
     DYNAX_CUDA_TRY(cudaMemsetAsync(ws, 0, need, st));
-    static_assert(vtc::A_END == nv::A_END, "both kernels share the accumulator layout");
-    const char *impl = getenv("DYNAX_NODE_VJP_IMPL");  // "0": CUDA-core kernel; default: tcgen05 kernel
-    if (impl && impl[0] == '0') {
-        rc = set_smem(node_vjp_kernel, nv::SMEM_BYTES);
-        if (rc != DYNAX_OK) return rc;
-        node_vjp_kernel<<<(unsigned)((N + nv::TN - 1) / nv::TN), nv::TN, nv::SMEM_BYTES, st>>>(P);
+    static_assert(vtc::A_END == nv::L<64>::A_END, "both kernels share the accumulator layout");
+    // hidden = 64: tcgen05 kernel (node_vjp_tc.cuh); DYNAX_NODE_VJP_IMPL=0 and hidden = 32: CUDA-core kernel
+    const char *impl = getenv("DYNAX_NODE_VJP_IMPL");
+    if (hidden == 32) {
+        rc = launch_node_vjp_cc<32>(W1, b1, W2, b2, W3, b3, x0, u, xsol, stage_x, g_xsol, g_ysol, g_x0, g_u, acc, N, T, dt, rk4, st);
+    } else if (impl && impl[0] == '0') {
+        rc = launch_node_vjp_cc<64>(W1, b1, W2, b2, W3, b3, x0, u, xsol, stage_x, g_xsol, g_ysol, g_x0, g_u, acc, N, T, dt, rk4, st);
     } else {
         NodeVjpTcParams Q;
         Q.W1 = W1; Q.b1 = b1; Q.W2 = W2; Q.b2 = b2; Q.W3 = W3; Q.b3 = b3;
         Q.x0 = x0; Q.u = u; Q.xsol = xsol; Q.stage_x = stage_x; Q.g_xsol = g_xsol; Q.g_ysol = g_ysol; Q.g_x0 = g_x0; Q.g_u = g_u;
-        Q.acc = P.acc; Q.N = N; Q.T = T; Q.dt = dt; Q.rk4 = P.mp.rk4;
+        Q.acc = acc; Q.N = N; Q.T = T; Q.dt = dt; Q.rk4 = rk4;
         rc = set_smem(node_vjp_tc_kernel, vtc::SMEM_BYTES);
         if (rc != DYNAX_OK) return rc;
         node_vjp_tc_kernel<<<(unsigned)((N + vtc::TN - 1) / vtc::TN), vtc::NTHR, vtc::SMEM_BYTES, st>>>(Q);
+        DYNAX_CUDA_TRY(cudaGetLastError());
+        rc = DYNAX_OK;
     }
-    DYNAX_CUDA_TRY(cudaGetLastError());
-    node_vjp_finalize_kernel<<<(nv::A_END + 255) / 256, 256, 0, st>>>(P.acc, gW1, gb1, gW2, gb2, gW3, gb3);
+    if (rc != DYNAX_OK) return rc;
+    const int a_end = hidden * 8 + hidden + hidden * hidden + hidden + 3 * hidden + 3;
+    node_vjp_finalize_kernel<<<(a_end + 255) / 256, 256, 0, st>>>(acc, hidden, gW1, gb1, gW2, gb2, gW3, gb3);
     DYNAX_CUDA_TRY(cudaGetLastError());
     return DYNAX_OK;
 }

@@ -408,7 +408,8 @@ def node_rk4_forward(W1, b1, W2, b2, W3, b3, x0, u, dt, emit_x=True, emit_y=True
 
     Weights are row-major [out,in] matrices shared by all systems; x0[N,3], u[T,N,5]|[T,5].
     ``emit_stages``: also return stage_x[T,N,9], the RK4 stage points of every step, which ``node_rk4_vjp`` can
-    reuse instead of recomputing them (tcgen05 kernel, per-system u, RK4 only; None otherwise).
+    reuse instead of recomputing them (tcgen05 kernel, RK4 only; None otherwise).
+    Hidden widths 32, 64 and 128 (gradient: 32 and 64).
     """
     ws = [_f32c(t, nm) for t, nm in ((W1, "W1"), (b1, "b1"), (W2, "W2"), (b2, "b2"), (W3, "W3"), (b3, "b3"))]
     x0, u = _f32c(x0, "x0"), _f32c(u, "u")
@@ -425,7 +426,7 @@ def node_rk4_forward(W1, b1, W2, b2, W3, b3, x0, u, dt, emit_x=True, emit_y=True
     xfin = torch.empty((N, n), dtype=torch.float32, device=dev) if emit_final else None
     flags = (SHARED_U if shared_u else 0) | (_lib.SOLVER_EULER if euler else 0)
     stages = None
-    if emit_stages and not euler and not shared_u and os.environ.get("DYNAX_NODE_IMPL", "1")[:1] != "0":
+    if emit_stages and not euler and os.environ.get("DYNAX_NODE_IMPL", "1")[:1] != "0":
         stages = torch.empty((T, N, 3 * n), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         check(lib().dynax_node_rk4_forward_stages_f32(*[_ptr(t) for t in ws], _ptr(x0), _ptr(u), _ptr(xsol), _ptr(ysol),

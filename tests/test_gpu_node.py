@@ -101,6 +101,11 @@ def test_unsupported_dims(T):
     with pytest.raises(DynaxError) as e:
         ops.node_rk4_forward(*(cu(T, w) for w in W), cu(T, x0), cu(T, u), 0.1)
     assert e.value.code == -2
+    W = [cu(T, w) for w in orc.synth_mlp(105, hidden=128)]     # gradient kernels: hidden 32 and 64
+    xs, _, _ = ops.node_rk4_forward(*W, cu(T, x0), cu(T, u), 0.1)
+    with pytest.raises(DynaxError) as e:
+        ops.node_rk4_vjp(*W, cu(T, x0), cu(T, u), xs, 0.1, T.ones_like(xs), None)
+    assert e.value.code == -2
 
 
 def _torch_node_rollout(T, W, x0, u, dt, euler):
@@ -119,15 +124,15 @@ def _torch_node_rollout(T, W, x0, u, dt, euler):
     return T.stack(xs), T.stack(ys)
 
 
-@pytest.mark.parametrize("impl", ["tc", "cuda_core"])
+@pytest.mark.parametrize("impl,hidden", [("tc", 64), ("cuda_core", 64), ("cuda_core", 32)])
 @pytest.mark.parametrize("N,Tn,euler,scale", [(200, 24, False, 0.5), (130, 17, True, 1.0), (3, 5, False, 0.3), (256, 40, False, 0.1)])
-def test_vjp_matches_torch_autograd_fp64(T, monkeypatch, N, Tn, euler, scale, impl):
+def test_vjp_matches_torch_autograd_fp64(T, monkeypatch, N, Tn, euler, scale, impl, hidden):
     """Oracle = torch autograd (fp64, CPU) over the restated RK4-MLP rollout (the reference has neither).
-    Both VJP kernels: tcgen05 (default) and CUDA cores (DYNAX_NODE_VJP_IMPL=0)."""
+    Both VJP kernels: tcgen05 (default for hidden = 64) and CUDA cores (DYNAX_NODE_VJP_IMPL=0; hidden = 32 always)."""
     from dynax_b200 import ops
     if impl == "cuda_core":
         monkeypatch.setenv("DYNAX_NODE_VJP_IMPL", "0")
-    Wnp = orc.synth_mlp(109, scale=scale)
+    Wnp = orc.synth_mlp(109, hidden=hidden, scale=scale)
     x0, u = inputs(N, Tn, 110)
     rng = np.random.default_rng(111)
     gx = rng.normal(size=(Tn, N, 3)).astype(np.float32); gy = rng.normal(size=(Tn, N, 1)).astype(np.float32)
@@ -163,9 +168,11 @@ def test_vjp_with_saved_stage_points(T, monkeypatch, impl):
     b = ops.node_rk4_vjp(*W, cu(T, x0), cu(T, u), xs, 0.25, gx, gy, stage_x=st)
     for p_, q_, nm in zip(a, b, ["W1", "b1", "W2", "b2", "W3", "b3", "x0", "u"]):
         assert rel_err(q_.cpu().numpy(), p_.cpu().numpy(), floor=1.0) < 2e-5, nm
-    # Euler has no stage points; a shared input series runs on the CUDA-core forward kernel, which does not emit them
+    # Euler has no stage points; a shared input series emits them like a per-system one (they are per trajectory)
     assert ops.node_rk4_forward(*W, cu(T, x0), cu(T, u), 0.25, euler=True, emit_stages=True)[3] is None
-    assert ops.node_rk4_forward(*W, cu(T, x0), cu(T, u[:, 0]), 0.25, emit_stages=True)[3] is None
+    st1 = ops.node_rk4_forward(*W, cu(T, x0), cu(T, u[:, 0]), 0.25, emit_stages=True)[3]
+    st2 = ops.node_rk4_forward(*W, cu(T, x0), cu(T, np.repeat(u[:, :1], 300, 1)), 0.25, emit_stages=True)[3]
+    assert st1 is not None and T.equal(st1, st2)
 
 
 @pytest.mark.parametrize("shape", ["T1m", "Tm"])
