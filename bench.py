@@ -62,6 +62,7 @@ def parse():
     ap.add_argument("--no-config3", action="store_true", help="skip the BASELINE.json config-3 leg (strong scaling + all-reduce)")
     ap.add_argument("--config3-systems", type=int, default=65536, help="systems in TOTAL over all ranks (strong scaling)")
     ap.add_argument("--config3-steps", type=int, default=20)
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the legs for BASELINE.json configs[1], [3], [4]")
     return ap.parse_args()
 
 
@@ -349,6 +350,85 @@ def config3_leg(a, torch, dist, dev, rank, world):
     }
 
 
+def other_configs_leg(a, torch, dist, dev, rank, world, views, T):
+    """BASELINE.json configs[1], [3] and [4] on the same box, same run (weak scaling: the per-rank size is the config's):
+    forward rollout emitting x and y (reference semantics) over the headline run's resident inputs, the MPC candidate
+    cost + argmin, the MLP-dynamics RK4 rollout.  CUDA events, max over ranks; results stay on the device."""
+    from dynax_b200 import ops
+    from dynax_b200.distributed import sharded_argmin
+    from tools import _synth as syn
+
+    def timed(fn, k, warm=2):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / k
+
+    peak, peak_src = measured_peak()
+    out = {}
+    # ---- configs[1]: N = 2^20 systems x T = 8760, x and y emitted (36 B per system-step), the headline run's tiles
+    S = sum(v[5] for v in views)
+
+    def fwd():
+        for th_t, x0_t, u_t, tg_t, o, n in views:
+            ops.rc_forward(th_t, x0_t, u_t, DT, time_chunks=0)
+    ms = timed(fwd, 3, warm=1)
+    v = world * S * T / (ms * 1e-3)
+    out["config2_forward"] = {
+        "metric": "system-steps/s, RC forward rollout emitting x and y (BASELINE.json configs[1])", "value": v,
+        "unit": "system-steps/s", "ms_per_step": ms, "systems_per_rank": S, "T": T, "scaling": "weak",
+        "launches_per_step": len(views), "alg_bytes_per_system_step": 36,
+        "roofline_frac": S * T * 36 / (ms * 1e-3) / 1e9 / peak, "peak_gbs": peak, "peak_source": peak_src}
+    # ---- configs[3]: 4M candidate control sequences x 96 steps through one shared model, cost + global argmin
+    Nm, H = 1 << 22, 96
+    g = torch.Generator(device=dev).manual_seed(3456 + rank)
+    um = -10 * torch.rand((H, Nm), device=dev, generator=g)
+    d = torch.rand((H, 4), device=dev, generator=g)
+    d[:, 0] = 15 + 10 * d[:, 0]
+    sch = [torch.tensor(x, dtype=torch.float32, device=dev) for x in (syn.RC_PRICE, syn.RC_T_LOW, syn.RC_T_HIGH)]
+    nom = torch.tensor(NOMINAL, device=dev)
+    xm = torch.tensor([20.0, 35.8, 26.0], device=dev)
+
+    def mpc():
+        cost, amin, cmin = ops.rc_mpc_cost(nom, xm, d, um, *sch, 900.0)
+        if world > 1:
+            sharded_argmin(cmin, amin, rank * Nm)
+    ms = timed(mpc, 20)
+    out["config4_mpc"] = {
+        "metric": "candidate-steps/s, MPC cost of N candidate control sequences + argmin (BASELINE.json configs[3])",
+        "value": world * Nm * H / (ms * 1e-3), "unit": "candidate-steps/s", "ms_per_step": ms, "candidates_per_rank": Nm,
+        "horizon": H, "scaling": "weak", "alg_bytes_per_candidate_step": 4,
+        "roofline_frac": Nm * H * 4 / (ms * 1e-3) / 1e9 / peak,
+        "collective": "all-gather of one (cost, index) pair per rank inside the timed region" if world > 1 else "none (1 rank)"}
+    del um
+    # ---- configs[4]: MLP dynamics 8 -> 64 -> 64 -> 3 with RK4 on tcgen05, N = 262144 trajectories x T = 2048
+    Nn, Tn = 262144, 2048
+    W = [torch.tensor(w).to(dev) for w in syn.synth_mlp(4567)]
+    xn = torch.randn((Nn, 3), device=dev, generator=g)
+    un = torch.randn((Tn, Nn, 5), device=dev, generator=g)
+    ms = timed(lambda: ops.node_rk4_forward(*W, xn, un, 0.25), 2, warm=1)
+    flop = 2 * (8 * 64 + 64 * 64 + 3 * 64) * 4
+    out["config5_node"] = {
+        "metric": "trajectory-steps/s, MLP-dynamics RK4 rollout (BASELINE.json configs[4])",
+        "value": world * Nn * Tn / (ms * 1e-3), "unit": "trajectory-steps/s", "ms_per_step": ms, "trajectories_per_rank": Nn,
+        "T": Tn, "scaling": "weak", "hidden": 64, "mlp_tflops_fp32_grade": Nn * Tn * flop / (ms * 1e-3) / 1e12,
+        "tensor_tflops_issued_tf32": 3 * Nn * Tn * 4 * 2 * (8 * 64 + 64 * 64) / (ms * 1e-3) / 1e12,
+        "kernel": "node_tc_kernel<64> (tcgen05.mma kind::tf32, 3xTF32 split, accumulators in TMEM)"}
+    return out
+
+
 def link_probe(torch, dist, dev, world, nbytes=1 << 30, reps=4):
     """Plain pinned cudaMemcpyAsync H2D rate of this rank while all ranks copy at once (declared, outside the e2e
     timing): the ceiling the e2e leg can reach.  Returns (GB/s of the slowest rank, sum over ranks)."""
@@ -469,6 +549,8 @@ def ours(a):
     workloads = {}
     if not a.no_config3:
         workloads["config3"] = config3_leg(a, torch, dist, dev, rank, world)
+    if not a.no_other_configs:
+        workloads.update(other_configs_leg(a, torch, dist, dev, rank, world, views, T))
 
     # ---- end to end: pinned HOST buffers -> host-API call (tiled H2D / kernel / D2H inside) -> host results
     e2e = None

@@ -94,7 +94,7 @@ __host__ __device__ constexpr bool fs_has_c(int split, int role, bool gx0) { ret
 template <int TN, int KF, int S, int SPLIT, int ROLE, bool SHARED_U, bool SHARED_TGT, bool CTRL, bool GX0, bool CHUNK, int UNR>
 __device__ __forceinline__ void fs_consumer(const FwdSensParams &P, unsigned char *smem_raw, float *s_in, uint64_t *full,
                                             uint64_t *empty, const int sys, const int64_t n0, const int valid,
-                                            const int64_t cidx, const int T, const int C) {
+                                            const int64_t cidx, const int T, const int C, const bool self_rows) {
     using Cfg = FwdSensCfg<TN, KF, S, SPLIT, SHARED_U, SHARED_TGT, CTRL, GX0>;
     constexpr unsigned PM = fs_pair_mask(SPLIT, ROLE, GX0);
     constexpr bool HAS_C = fs_has_c(SPLIT, ROLE, GX0);
@@ -262,11 +262,37 @@ __device__ __forceinline__ void fs_consumer(const FwdSensParams &P, unsigned cha
             sq = 0.f;
         }
     };
+    // self_rows (rows TMA cannot move, per-system u and target, one thread per system): this thread copies ITS OWN six
+    // floats of every row of a chunk into its slice of the ring with 4-byte cp.async -- nobody else reads them, so the
+    // stage needs no barrier, only the thread's own cp.async groups (one per chunk, committed even when empty)
+    auto self_load = [&](const int c) {
+        if constexpr (SPLIT == 1 && !SHARED_U && !SHARED_TGT && !CTRL) {
+            if (c < C && active) {
+                const int64_t k0 = (int64_t)(CHUNK ? cidx * P.chunk_len : 0) + (int64_t)c * KF;
+                const int rows = (T - c * KF) < KF ? (T - c * KF) : KF;
+                float *du = s_in + (c % S) * Cfg::STAGE + sys * 5, *dtg = s_in + (c % S) * Cfg::STAGE + Cfg::U_STAGE + sys;
+                const float *su = P.u + (k0 * N + i) * 5, *st = P.target + k0 * N + i;
+#pragma unroll
+                for (int j = 0; j < KF; ++j) {
+                    if (j < rows) {
+#pragma unroll
+                        for (int d = 0; d < 5; ++d) ptx::cp_async4(du + j * Cfg::U_ROW + d, su + j * N * 5 + d);
+                        ptx::cp_async4(dtg + j * Cfg::T_ROW, st + j * N);
+                    }
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+    };
+    if (self_rows) {
+        for (int c = 0; c < S; ++c) self_load(c);
+    }
     for (int c = 0; c < C; ++c) {
         const int s = c % S;
         const int k0 = c * KF;
         const int rows = (T - k0) < KF ? (T - k0) : KF;
-        ptx::mbar_wait(&full[s], (uint32_t)((c / S) & 1));
+        if (self_rows) asm volatile("cp.async.wait_group %0;" ::"n"(S - 1) : "memory");
+        else ptx::mbar_wait(&full[s], (uint32_t)((c / S) & 1));
         in = s_in + s * Cfg::STAGE + (SHARED_U ? 0 : sys * 5);
         tg = s_in + s * Cfg::STAGE + Cfg::U_STAGE + (SHARED_TGT ? 0 : sys);
 #pragma unroll 1
@@ -276,6 +302,7 @@ __device__ __forceinline__ void fs_consumer(const FwdSensParams &P, unsigned cha
                 if (j0 + jj < rows) step(load_row(j0 + jj));
             if (KF > kFsFoldSteps && j0 + FR < KF) fold();      // inside a long chunk; its last block folds below
         }
+        if (self_rows) self_load(c + S);
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&empty[s]);
         if ((c + 1) % FOLDC == 0 || c + 1 == C) fold();
@@ -382,7 +409,11 @@ __global__ void __launch_bounds__(TN * SPLIT + 32, MINB) rc_fwdsens_kernel(const
     // per-system rows that TMA cannot move (N % 4 != 0) go through 4-byte cp.async from all producer lanes: every
     // lane then arrives on the stage's barrier (count 32) instead of the one elected lane of the TMA path
     constexpr bool ANY_ROWS = !SHARED_U || !SHARED_TGT || CTRL;
-    const bool async_rows = ANY_ROWS && !P.bulk;
+    // ... except in the headline layout (per-system u and target, one thread per system), where every computing thread
+    // fetches its own rows (fs_consumer: self_load) and the producer warp has nothing to do (N = 151 553, T = 2000:
+    // 3.05 -> 2.04 ms; the forward kernel, which also stores x and y per thread, stays with the producer lanes)
+    const bool self_rows = SPLIT == 1 && !SHARED_U && !SHARED_TGT && !CTRL && !P.bulk;
+    const bool async_rows = ANY_ROWS && !P.bulk && !self_rows;
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < S; ++s) {
@@ -394,6 +425,7 @@ __global__ void __launch_bounds__(TN * SPLIT + 32, MINB) rc_fwdsens_kernel(const
     __syncthreads();
 
     if (tid >= Cfg::CONSUMERS) {  // ------------------------------- producer warp -------------------------------
+        if (self_rows) return;
         const int lane = tid - Cfg::CONSUMERS;
         const uint64_t pol = ptx::policy_evict_first(), pol_keep = ptx::policy_evict_last();
         auto load_chunk = [&](int c) {
@@ -480,7 +512,7 @@ __global__ void __launch_bounds__(TN * SPLIT + 32, MINB) rc_fwdsens_kernel(const
     const int role = SPLIT == 1 ? 0 : tid / TN, sys = SPLIT == 1 ? tid : tid % TN;
 #define DYNAX_FS_ROLE(R)                                                                                         \
     fs_consumer<TN, KF, S, SPLIT, R, SHARED_U, SHARED_TGT, CTRL, GX0, CHUNK, UNR>(P, smem_raw, s_in, full, empty, sys, n0, \
-                                                                                  valid, cidx, T, C)
+                                                                                  valid, cidx, T, C, self_rows)
     if constexpr (SPLIT == 1) {
         DYNAX_FS_ROLE(0);
     } else if constexpr (SPLIT == 2) {

@@ -134,7 +134,13 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_adj_kernel(const __grid
 
     // Per-system rows that TMA cannot move (N % 4 != 0 or unaligned arrays) go through 4-byte cp.async from all
     // producer lanes: every lane then arrives on the stage's barrier (count 32) instead of one elected lane.
-    const bool async_rows = !P.bulk && (!SHARED_U || P.ctrl != nullptr || MODE != ADJ_MSE || !SHARED_TGT);
+    // ... except in the fused loss+gradient with per-system u and target: each computing thread then fetches ITS OWN floats
+    // of every row (self_load below) -- nobody else reads them, so the ring needs no barriers, only the thread's own
+    // cp.async groups, and the copies are issued by all warps instead of one (N = 151 553, T = 2000: 3.85 -> 3.60 ms;
+    // the general-cotangent mode, which also stores g_u per thread, is faster with the producer lanes: 4.61 vs 4.94 ms).
+    constexpr bool SELF_OK = MODE == ADJ_MSE && !SHARED_U && !SHARED_TGT;
+    const bool self_rows = SELF_OK && !P.bulk;
+    const bool async_rows = !self_rows && !P.bulk && (!SHARED_U || P.ctrl != nullptr || MODE != ADJ_MSE || !SHARED_TGT);
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < S; ++s) {
@@ -147,6 +153,7 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_adj_kernel(const __grid
 
     if (tid >= TN) {
         // ------------------------------- producer warp -------------------------------
+        if (self_rows) return;
         const int lane = tid - TN;
         const uint64_t pol = ptx::policy_evict_first();
 
@@ -246,6 +253,49 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_adj_kernel(const __grid
         }
     };
 
+    // self_rows: this thread's own floats of every row of ring chunk qq (same order as the producer's load_q: C-1 forward
+    // segments, then C segments in reverse); one cp.async group per chunk, committed even when empty
+    auto self_load = [&](int64_t qq) {
+        if constexpr (SELF_OK) {
+            if (qq < Q && active) {
+                float *st = s_in + (int)(qq % S) * Cfg::STAGE;
+                const bool fwd = qq < C - 1;
+                const int64_t k0 = (fwd ? qq : (2 * C - 2 - qq)) * KC;
+                const int rows = (int)((T - k0) < KC ? (T - k0) : KC);
+#pragma unroll
+                for (int j = 0; j < KC; ++j) {
+                    if (j < rows) {
+                        const int64_t r = (k0 + j) * N + i;  // row k0 + j of this CTA's time slice, this thread's system
+#pragma unroll
+                        for (int d = 0; d < m; ++d) ptx::cp_async4(st + Cfg::U_OFF + j * U_ROW + tid * m + d, u_base + r * m + d);
+                        if (!fwd) {
+                            if (MODE == ADJ_MSE) {
+                                ptx::cp_async4(st + Cfg::A1_OFF + j * A1_ROW + tid, tgt_base + r);
+                            } else {
+                                if (gy_base != nullptr) {
+#pragma unroll
+                                    for (int d = 0; d < p; ++d) ptx::cp_async4(st + Cfg::A1_OFF + j * A1_ROW + tid * p + d, gy_base + r * p + d);
+                                }
+                                if (gx_base != nullptr) {
+#pragma unroll
+                                    for (int d = 0; d < n; ++d) ptx::cp_async4(st + Cfg::A2_OFF + j * A2_ROW + tid * n + d, gx_base + r * n + d);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+    };
+    auto stage_wait = [&](int64_t qq) {  // ring chunk qq is in shared memory
+        if (self_rows) asm volatile("cp.async.wait_group %0;" ::"n"(S - 1) : "memory");
+        else ptx::mbar_wait(&full[qq % S], (uint32_t)((qq / S) & 1));
+    };
+    if (self_rows) {
+        for (int64_t qq = 0; qq < S; ++qq) self_load(qq);
+    }
+
     int64_t q = 0;
     // ---- phase 1: forward sweep over segments 0..C-2, checkpointing the state at each start
     for (; q < C - 1; ++q) {
@@ -254,7 +304,7 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_adj_kernel(const __grid
 #pragma unroll
             for (int d = 0; d < n; ++d) ck[(q * n + d) * N] = xc[d];
         }
-        ptx::mbar_wait(&full[s], (uint32_t)((q / S) & 1));
+        stage_wait(q);
         const float *in = s_in + s * Cfg::STAGE + Cfg::U_OFF + (SHARED_U ? 0 : tid * m);
 #pragma unroll
         for (int j = 0; j < KC; ++j) {
@@ -266,6 +316,7 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_adj_kernel(const __grid
 #pragma unroll
             for (int d = 0; d < n; ++d) xc[d] = discrete ? r[d] : fmaf(dt, r[d], xc[d]);
         }
+        if (self_rows) self_load(q + S);
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&empty[s]);
     }
@@ -299,7 +350,7 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_adj_kernel(const __grid
 #pragma unroll
             for (int d = 0; d < n; ++d) xc[d] = ck[((seg - 1) * n + d) * N];
         }
-        ptx::mbar_wait(&full[s], (uint32_t)((q / S) & 1));
+        stage_wait(q);
         const float *st = s_in + s * Cfg::STAGE;
         const float *in = st + Cfg::U_OFF + (SHARED_U ? 0 : tid * m);
 
@@ -364,6 +415,7 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_adj_kernel(const __grid
                 for (int d = 0; d < n; ++d) a[d] = discrete ? ax[d] : (a[d] + ax[d]);
             }
         }
+        if (self_rows) self_load(q + S);
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&empty[s]);
         if constexpr (Cfg::GU_TILE) {
