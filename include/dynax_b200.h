@@ -212,7 +212,9 @@ int dynax_lti_vjp_chunked_f32(const float *A, const float *B, const float *C, co
  *          rhs = W3 tanh(W2 tanh(W1 [x;u] + b1) + b2) + b3,   y = x[0:p]
  *      stepped with classical RK4 (u held constant over a step) or Euler (DYNAX_SOLVER_EULER).
  *      Weights are row-major [out,in] matrices shared by all systems: W1:[hidden,n+m] b1:[hidden]
- *      W2:[hidden,hidden] b2:[hidden] W3:[n,hidden] b3:[n].  Instantiated for (n,m,p,hidden)=(3,5,1,64).
+ *      W2:[hidden,hidden] b2:[hidden] W3:[n,hidden] b3:[n].  Instantiated for (n,m,p)=(3,5,1) and hidden = 32, 64
+ *      or 128 (forward; the gradient kernels: hidden = 32 or 64); anything else: DYNAX_ERR_UNSUPPORTED_DIMS.
+ *      u: [T,N,5], or ONE series [T,5] for all trajectories with DYNAX_SHARED_U.
  *      Output convention as dynax_rc_forward_f32.  PARITY UNPINNED BY THE REFERENCE. ---- */
 int dynax_node_rk4_forward_f32(const float *W1, const float *b1, const float *W2, const float *b2,
                                const float *W3, const float *b3, const float *x0, const float *u,
@@ -221,7 +223,8 @@ int dynax_node_rk4_forward_f32(const float *W1, const float *b1, const float *W2
                                uint32_t flags, void *stream);
 /* Same rollout, additionally emitting stage_x:[T,N,9] = the state parts of the RK4 stage points z2, z3, z4 of
  * every step (36 B per trajectory-step).  Passing them to dynax_node_rk4_vjp_stages_f32 saves the backward pass the
- * three forward evaluations per step it would spend recomputing them.  tcgen05 kernel only (per-system u). */
+ * three forward evaluations per step it would spend recomputing them.  tcgen05 kernel only (the product path;
+ * DYNAX_NODE_IMPL=0 selects the CUDA-core cross-check kernel, hidden = 64, which does not emit them). */
 int dynax_node_rk4_forward_stages_f32(const float *W1, const float *b1, const float *W2, const float *b2,
                                       const float *W3, const float *b3, const float *x0, const float *u,
                                       float *xsol, float *ysol, float *x_final, float *stage_x,
@@ -230,8 +233,9 @@ int dynax_node_rk4_forward_stages_f32(const float *W1, const float *b1, const fl
 
 /* Reverse-mode gradient of dynax_node_rk4_forward_f32 (exact discrete adjoint of RK4 / Euler): cotangents
  * g_xsol:[T,N,3] and/or g_ysol:[T,N,1] in; weight gradients (summed over systems, each may be NULL),
- * g_x0:[N,3], g_u:[T,N,5] out.  xsol is the forward trajectory (x_{k+1} at row k).  tcgen05 kernel by default
- * (node_vjp_tc.cuh), CUDA-core kernel with DYNAX_NODE_VJP_IMPL=0.
+ * g_x0:[N,3], g_u:[T,N,5] out.  xsol is the forward trajectory (x_{k+1} at row k).  hidden = 64: tcgen05 kernel
+ * (node_vjp_tc.cuh), CUDA-core kernel with DYNAX_NODE_VJP_IMPL=0; hidden = 32: CUDA-core kernel.  u is per system
+ * here ([T,N,5]; the Python glue broadcasts a shared series and sums its g_u).
  * ws: dynax_node_rk4_vjp_workspace() bytes.  PARITY UNPINNED BY THE REFERENCE. */
 size_t dynax_node_rk4_vjp_workspace(void);
 int dynax_node_rk4_vjp_f32(const float *W1, const float *b1, const float *W2, const float *b2,
