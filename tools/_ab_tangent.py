@@ -1,11 +1,11 @@
 """A/B timing of the fused loss+gradient (tangent kernel) between two builds of the library (see tools/_ab_fwd.py for how
-the second build gets to dynax_b200/_old/).  Prints the best single launch, the mean of 30 launches back to back (the
+the second build gets to dynax_b200/_old/; one build per process -- two copies of the library in one process crashed).  Prints the best single launch, the mean of 30 launches back to back (the
 power-capped steady state) and fp64 sums of loss and gradient (equal sums = same results)."""
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from dynax_b200 import ops, _lib
 from tools._synth import RC_NOMINAL
-libs = {"new": _lib.LIB_PATH, "old": os.path.join(os.path.dirname(_lib.LIB_PATH), "_old", "libdynax_old.so")}
+name = os.environ.get("AB_NAME", "new")   # one build per process: DYNAX_B200_LIB=dynax_b200/_old/libdynax_old.so AB_NAME=old python tools/_ab_tangent.py
 g = torch.Generator(device="cuda").manual_seed(0)
 T = 8760
 for N in (227328, 65536, 16384):
@@ -15,8 +15,7 @@ for N in (227328, 65536, 16384):
     tg = 20 + 2 * torch.rand((T, N), device="cuda", generator=g)
     fn = lambda: ops.rc_loss_grad(th, x0, u, tg, 3600.0, time_chunks=0)
     for rep in range(2):
-        for name, path in libs.items():
-            _lib._LIB = None; _lib.LIB_PATH = path; _lib.lib()
+        if True:
             for _ in range(3): fn()
             torch.cuda.synchronize()
             best = 1e9
