@@ -24,10 +24,11 @@ inline size_t gu_part_bytes(int64_t N, int64_t T, int m) {
     return sizeof(float) * (size_t)((N + kGuPartTN - 1) / kGuPartTN) * (size_t)T * (size_t)m;
 }
 
-template <class Model, int TN, int KF, int S, bool SHARED_U, int MINB>
+template <class Model, int TN, int KF, int S, bool SHARED_U, int MINB, bool SHIFT = false>
 int launch_fwd(const FwdParams<Model> &P0, cudaStream_t st) {
-    using Cfg = FwdCfg<Model, TN, KF, S, SHARED_U>;
-    auto kern = rollout_fwd_kernel<Model, TN, KF, S, SHARED_U, MINB>;
+    using Cfg = FwdCfg<Model, TN, KF, S, SHARED_U, SHIFT>;
+    auto kern = rollout_fwd_kernel<Model, TN, KF, S, SHARED_U, MINB, SHIFT>;
+    if (SHIFT && P0.bulk_in) return fail(DYNAX_ERR_INVALID_ARGUMENT, "shifted-row instantiation launched on rows TMA can move");
     DYNAX_NOTE_LAUNCH();
     int rc = set_smem(kern, Cfg::SMEM_BYTES);
     if (rc != DYNAX_OK) return rc;
@@ -64,11 +65,13 @@ int launch_fwd(const FwdParams<Model> &P0, cudaStream_t st) {
     return DYNAX_OK;
 }
 
-template <class Model, int TN, int KC, int S, int MODE, bool SHARED_U, bool SHARED_TGT, int MINB>
+template <class Model, int TN, int KC, int S, int MODE, bool SHARED_U, bool SHARED_TGT, int MINB, bool SHIFT = false>
 int launch_adj(const AdjParams<Model> &P0, cudaStream_t st) {
-    using Cfg = AdjCfg<Model, TN, KC, S, MODE, SHARED_U, SHARED_TGT>;
+    using Cfg = AdjCfg<Model, TN, KC, S, MODE, SHARED_U, SHARED_TGT, SHIFT>;
     static_assert(KC >= kMinKC, "workspace sizing assumes KC >= kMinKC");
-    auto kern = rollout_adj_kernel<Model, TN, KC, S, MODE, SHARED_U, SHARED_TGT, MINB>;
+    auto kern = rollout_adj_kernel<Model, TN, KC, S, MODE, SHARED_U, SHARED_TGT, MINB, SHIFT>;
+    if (SHIFT && (P0.bulk || P0.ctrl || P0.chunk_len > 0))
+        return fail(DYNAX_ERR_INVALID_ARGUMENT, "shifted-row instantiation launched on rows TMA can move / a chunked launch");
     DYNAX_NOTE_LAUNCH();
     int rc = set_smem(kern, Cfg::SMEM_BYTES);
     if (rc != DYNAX_OK) return rc;
@@ -121,10 +124,11 @@ int launch_adj(const AdjParams<Model> &P0, cudaStream_t st) {
 
 // Forward-mode (tangent) fused loss + gradient of the 4R3C model (rc_fwdsens.cuh).
 template <int TN, int KF, int S, int MINB, int SPLIT = 1, bool SU = false, bool STG = false, bool CTRL = false,
-          bool GX0 = false, bool CHUNK = false, int UNR = KF>
+          bool GX0 = false, bool CHUNK = false, int UNR = KF, bool SHIFT = false>
 int launch_fwdsens(const FwdSensParams &P0, cudaStream_t st) {
-    using Cfg = FwdSensCfg<TN, KF, S, SPLIT, SU, STG, CTRL, GX0>;
-    auto kern = rc_fwdsens_kernel<TN, KF, S, MINB, SPLIT, SU, STG, CTRL, GX0, CHUNK, UNR>;
+    using Cfg = FwdSensCfg<TN, KF, S, SPLIT, SU, STG, CTRL, GX0, SHIFT>;
+    auto kern = rc_fwdsens_kernel<TN, KF, S, MINB, SPLIT, SU, STG, CTRL, GX0, CHUNK, UNR, SHIFT>;
+    if (SHIFT && P0.bulk) return fail(DYNAX_ERR_INVALID_ARGUMENT, "shifted-row instantiation launched on rows TMA can move");
     DYNAX_NOTE_LAUNCH();
     int rc = set_smem(kern, Cfg::SMEM_BYTES);
     if (rc != DYNAX_OK) return rc;

@@ -103,6 +103,11 @@ __device__ __forceinline__ void copy_rows_async(float *dst, int dst_stride, cons
     }
 }
 
+// Rows that start on a 4-byte boundary only (N % 4 != 0): row r lands in its shared slot at the offset its global address
+// has modulo 16 bytes (`row_shift`), so that the interior of the row is 16-byte aligned on both sides (see
+// copy_rows_shift_bulk below).  Consumers read row r at dst + r * dst_pitch + row_shift(src + r * src_stride).
+__device__ __forceinline__ int row_shift(const float *row) { return (int)((reinterpret_cast<uintptr_t>(row) >> 2) & 3); }
+
 // L2 policy for data every CTA re-reads (a shared input series).
 __device__ __forceinline__ uint64_t policy_evict_last() {
     uint64_t pol;
@@ -161,6 +166,47 @@ __device__ __forceinline__ void bulk_wait() {
 // Order generic-proxy st.shared before async-proxy (bulk copy) reads of the same bytes.
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// Shifted layout (row_shift above): the interior of every row as ONE 1-D bulk copy (TMA) -- 16-byte aligned on both sides
+// thanks to the shift; lane r issues row r's copy --, the < 16-byte head and tail as 4-byte cp.async.  The bulk bytes are
+// announced on `bar` with expect_tx; the caller then lets EVERY lane arrive (cp_async_arrive, barrier count 32), which
+// also covers the lanes' own copies.  dst 16-byte aligned, dst_pitch a multiple of 4 floats with room for the shift (row
+// length + 4), rows <= 32.  Measured at N = 151 553 (profiles/r02_unaligned_ab.txt): 4-byte cp.async by the producer lanes
+// 0.36-0.62 of the HBM roof, 16-byte cp.async by the lanes no better (the producer warp shares its issue slots with the
+// computing warps: its instruction count per stage is what matters), one bulk copy per row from lane 0 0.57-0.71, from
+// lanes in parallel 0.69-0.82.
+__device__ __forceinline__ void copy_rows_shift_bulk(float *dst, int dst_pitch, const float *src, int64_t src_stride, int rows,
+                                                     int count, int lane, uint64_t *bar, uint64_t policy) {
+    // lane r issues row r's bulk copy (rows <= 32): the copies leave together instead of one every ~45 ns from one thread
+    uint32_t body = 0;
+    int mis = 0, head = 0;
+    if (lane < rows) {
+        mis = row_shift(src + lane * src_stride);
+        head = (4 - mis) & 3;
+        head = head < count ? head : count;
+        body = (uint32_t)((count - head) >> 2) * 16u;
+    }
+    uint32_t bytes = body;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, o);
+    if (lane == 0 && bytes) mbar_expect_tx(bar, bytes);
+    __syncwarp();
+    if (lane < rows && body) bulk_g2s(dst + lane * dst_pitch + mis + head, src + lane * src_stride + head, body, bar, policy);
+    // head and tail: lane -> (row lane / 4 of a group of eight rows, element lane % 4 < 3), two predicated copies per lane
+    for (int r0 = 0; r0 < rows; r0 += 8) {
+        const int r = r0 + (lane >> 2), e = lane & 3;
+        if (r < rows && e < 3) {
+            const float *s = src + r * src_stride;
+            const int m2 = row_shift(s);
+            int h2 = (4 - m2) & 3;
+            h2 = h2 < count ? h2 : count;
+            const int b2 = (count - h2) & ~3, t2 = count - h2 - b2;
+            float *d = dst + r * dst_pitch + m2;
+            if (e < h2) cp_async4(d + e, s + e);
+            if (e < t2) cp_async4(d + h2 + b2 + e, s + h2 + b2 + e);
+        }
+    }
 }
 
 }  // namespace ptx

@@ -126,6 +126,8 @@ static int rc_forward(const float *theta, const float *x0, const float *u, float
         if (rc != DYNAX_OK) return rc;
         cfg = ((N + 127) / 128 <= di.sm_count) ? 4 : ((N + 255) / 256 <= di.sm_count) ? 3 : 0;
     }
+    // rows TMA cannot move (N % 4 != 0) on launches of more than one wave: the shifted-row instantiation (16-byte cp.async)
+    if (cfg == 0 && !P.bulk_in && !env_int("DYNAX_NO_SHIFT", 0)) return launch_fwd<RCModel, 256, 4, 4, false, 1, true>(P, st);
     switch (cfg) {
         default:
         case 0: return launch_fwd<RCModel, 256, 4, 4, false, 1>(P, st);
@@ -230,6 +232,13 @@ static int rc_adjoint(const float *theta, const float *x0, const float *u, const
 #define DYNAX_FS_LAUNCH_SPLIT(SU, STG)                                                                \
     (split == 2 ? launch_fwdsens<64, 64, 2, 1, 2, SU, STG, false, false, false, 8>(F, st)       \
                 : DYNAX_FS_LAUNCH(SU, STG, false))
+        // rows TMA cannot move (N % 4 != 0), per-system u and target, more than one 128-system CTA per SM: the shifted-row
+        // instantiation (one bulk copy per row; N = 151 553, T = 2000: 3.05 ms with 4-byte copies by the producer lanes,
+        // 2.04 ms with every thread fetching its own rows, 1.60 ms shifted; (224,4,4) 2.08, (256,8,2) 1.66, (128,8,4) 2.40,
+        // (128,16,2) 1.87 ms; profiles/r02_unaligned_ab.txt)
+        if (!F.bulk && !su && !stg && !ctrl && !g_x0 && split == 1 && tn != 128 && !env_int("DYNAX_NO_SHIFT", 0)) {
+            return launch_fwdsens<224, 8, 2, 2, 1, false, false, false, false, false, 8, true>(F, st);
+        }
         if (ctrl && stg) return DYNAX_FS_LAUNCH(true, true, true);
         if (ctrl) return DYNAX_FS_LAUNCH(true, false, true);
         if (su && stg) return DYNAX_FS_LAUNCH_SPLIT(true, true);
@@ -250,6 +259,9 @@ static int rc_adjoint(const float *theta, const float *x0, const float *u, const
         }
         // full cotangents in and g_u out (79 B per system-step): 12-step segments, 6.24 vs 6.00 TB/s; with g_ysol only
         // (47 B) 8-step segments are faster (5.66 vs 4.99 TB/s)
+        // rows TMA cannot move (N % 4 != 0), more than one CTA per SM: the shifted-row instantiation (16-byte cp.async)
+        if (!P.bulk && (N + 127) / 128 > 148 && !env_int("DYNAX_NO_SHIFT", 0))
+            return launch_adj<RCModel, 128, 8, 2, ADJ_VJP, false, false, 2, true>(P, st);
         if (g_xsol && g_u) return launch_adj<RCModel, 128, 12, 2, ADJ_VJP, false, false, 2>(P, st);
         return launch_adj<RCModel, 128, 8, 2, ADJ_VJP, false, false, 2>(P, st);
     } else {
@@ -271,6 +283,9 @@ static int rc_adjoint(const float *theta, const float *x0, const float *u, const
             const double cost3 = (double)((ctas + s3 - 1) / s3 * s3) / 1.04, cost2 = (double)((ctas + s2 - 1) / s2 * s2);
             cfg = (ctas <= s3 || cost3 <= cost2) ? 0 : 1;
         }
+        // rows TMA cannot move (N % 4 != 0) on launches of more than one CTA per SM: the shifted-row instantiation
+        if (!P.bulk && (N + 127) / 128 > 148 && !env_int("DYNAX_NO_SHIFT", 0))
+            return launch_adj<RCModel, 128, 12, 2, ADJ_MSE, false, false, 3, true>(P, st);
         switch (cfg) {
             default:
             case 0: return launch_adj<RCModel, 128, 12, 2, ADJ_MSE, false, false, 3>(P, st);

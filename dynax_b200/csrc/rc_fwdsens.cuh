@@ -68,12 +68,17 @@ struct FwdSensParams {
 
 constexpr int kFsFoldSteps = 32;  // fp32 partial sums are folded into the fp64 totals every this many steps
 
+// SHIFT: the instantiation for rows TMA cannot move (N % 4 != 0; per-system u and target, one thread per system): rows are
+// staged at their global offset modulo 16 bytes, so that the interior of a row moves as ONE bulk copy and only its < 16-byte
+// head and tail by lanes (ptx::copy_rows_shift_bulk), the row pitches grow by 4 floats, and the computing threads add the
+// (warp-uniform) shift of each row to their shared address.
 template <int TN, int KF, int S, int SPLIT = 1, bool SHARED_U = false, bool SHARED_TGT = false, bool CTRL = false,
-          bool GX0 = false>
+          bool GX0 = false, bool SHIFT = false>
 struct FwdSensCfg {
+    static_assert(!SHIFT || (SPLIT == 1 && !SHARED_U && !SHARED_TGT && !CTRL), "shifted rows: the per-system layout only");
     static constexpr int NACC = GX0 ? 11 : 8;  // fp64 totals per system: 7 gradient entries (+3 for x0) + squared residual
     // a shared series occupies KF rows of 5 (or 1) floats per stage instead of KF x TN of them
-    static constexpr int U_ROW = SHARED_U ? 5 : TN * 5, T_ROW = SHARED_TGT ? 1 : TN;
+    static constexpr int U_ROW = SHARED_U ? 5 : TN * 5 + (SHIFT ? 4 : 0), T_ROW = SHARED_TGT ? 1 : TN + (SHIFT ? 4 : 0);
     // every block of a stage starts on a 128-byte boundary (destination alignment of cp.async.bulk.tensor)
     static constexpr int U_STAGE = (KF * U_ROW + 31) / 32 * 32, T_STAGE = (KF * T_ROW + 31) / 32 * 32;
     static constexpr int C_STAGE = CTRL ? (KF * TN + 31) / 32 * 32 : 0, STAGE = U_STAGE + T_STAGE + C_STAGE;
@@ -91,11 +96,12 @@ __host__ __device__ constexpr unsigned fs_pair_mask(int split, int role, bool gx
 }
 __host__ __device__ constexpr bool fs_has_c(int split, int role, bool gx0) { return !gx0 && role == split - 1; }
 
-template <int TN, int KF, int S, int SPLIT, int ROLE, bool SHARED_U, bool SHARED_TGT, bool CTRL, bool GX0, bool CHUNK, int UNR>
+template <int TN, int KF, int S, int SPLIT, int ROLE, bool SHARED_U, bool SHARED_TGT, bool CTRL, bool GX0, bool CHUNK, int UNR,
+          bool SHIFT>
 __device__ __forceinline__ void fs_consumer(const FwdSensParams &P, unsigned char *smem_raw, float *s_in, uint64_t *full,
                                             uint64_t *empty, const int sys, const int64_t n0, const int valid,
                                             const int64_t cidx, const int T, const int C, const bool self_rows) {
-    using Cfg = FwdSensCfg<TN, KF, S, SPLIT, SHARED_U, SHARED_TGT, CTRL, GX0>;
+    using Cfg = FwdSensCfg<TN, KF, S, SPLIT, SHARED_U, SHARED_TGT, CTRL, GX0, SHIFT>;
     constexpr unsigned PM = fs_pair_mask(SPLIT, ROLE, GX0);
     constexpr bool HAS_C = fs_has_c(SPLIT, ROLE, GX0);
     constexpr bool LOSS_ROLE = ROLE == SPLIT - 1;   // squared residual, chunk weights, the loss output
@@ -158,19 +164,21 @@ __device__ __forceinline__ void fs_consumer(const FwdSensParams &P, unsigned cha
     float p0 = 1.f, p1 = 0.f, p2 = 0.f, w0 = 0.f, w1 = 0.f, w2 = 0.f;
 
     const float *in = nullptr, *tg = nullptr;
+    unsigned shu = 0, sht = 0;  // SHIFT: global float index of this chunk's first u / target row (row jj: + jj * N * 5 / N)
     struct Row {
         float u0, u1, u2, u3, u4, t;
     };
     auto load_row = [&](const int jj) {
         Row r;
-        r.u0 = in[jj * Cfg::U_ROW]; r.u1 = in[jj * Cfg::U_ROW + 1]; r.u2 = in[jj * Cfg::U_ROW + 2];
-        r.u3 = in[jj * Cfg::U_ROW + 3]; r.u4 = in[jj * Cfg::U_ROW + 4];
+        const float *inj = in + jj * Cfg::U_ROW + (SHIFT ? (int)((shu + (unsigned)jj * (unsigned)(N * 5)) & 3u) : 0);
+        r.u0 = inj[0]; r.u1 = inj[1]; r.u2 = inj[2];
+        r.u3 = inj[3]; r.u4 = inj[4];
         if constexpr (CTRL) {  // inputs assembled as in wrapper/envs/rc.py:128-131
             const float cv = tg[Cfg::T_STAGE + (SHARED_TGT ? sys : 0) + jj * TN];
             r.u0 = ccol == 0 ? cv : r.u0; r.u1 = ccol == 1 ? cv : r.u1; r.u2 = ccol == 2 ? cv : r.u2;
             r.u3 = ccol == 3 ? cv : r.u3; r.u4 = ccol == 4 ? cv : r.u4;
         }
-        r.t = tg[jj * Cfg::T_ROW];
+        r.t = tg[jj * Cfg::T_ROW + (SHIFT ? (int)((sht + (unsigned)jj * (unsigned)N) & 3u) : 0)];
         return r;
     };
     auto step = [&](const Row &row) {
@@ -295,6 +303,11 @@ __device__ __forceinline__ void fs_consumer(const FwdSensParams &P, unsigned cha
         else ptx::mbar_wait(&full[s], (uint32_t)((c / S) & 1));
         in = s_in + s * Cfg::STAGE + (SHARED_U ? 0 : sys * 5);
         tg = s_in + s * Cfg::STAGE + Cfg::U_STAGE + (SHARED_TGT ? 0 : sys);
+        if constexpr (SHIFT) {
+            const int64_t kg = (int64_t)(CHUNK ? cidx * P.chunk_len : 0) + k0;
+            shu = (unsigned)((reinterpret_cast<uintptr_t>(P.u) >> 2) + (uint64_t)((kg * N + n0) * 5));
+            sht = (unsigned)((reinterpret_cast<uintptr_t>(P.target) >> 2) + (uint64_t)(kg * N + n0));
+        }
 #pragma unroll 1
         for (int j0 = 0; j0 < KF; j0 += FR) {
 #pragma unroll UNR
@@ -384,13 +397,13 @@ __device__ __forceinline__ void fs_consumer(const FwdSensParams &P, unsigned cha
 }
 
 template <int TN, int KF, int S, int MINB, int SPLIT = 1, bool SHARED_U = false, bool SHARED_TGT = false,
-          bool CTRL = false, bool GX0 = false, bool CHUNK = false, int UNR = KF>
+          bool CTRL = false, bool GX0 = false, bool CHUNK = false, int UNR = KF, bool SHIFT = false>
 __global__ void __launch_bounds__(TN * SPLIT + 32, MINB) rc_fwdsens_kernel(const __grid_constant__ FwdSensParams P) {
     static_assert(!CTRL || SHARED_U, "the control channel replaces a column of a SHARED input series");
     static_assert(!CHUNK || (!GX0 && !CTRL), "time-chunked launches use the plain kernel");
     static_assert(SPLIT == 1 || SPLIT == 2 || SPLIT == 4, "1, 2 or 4 threads per system");
     static_assert(TN % 32 == 0, "a warp holds one role");
-    using Cfg = FwdSensCfg<TN, KF, S, SPLIT, SHARED_U, SHARED_TGT, CTRL, GX0>;
+    using Cfg = FwdSensCfg<TN, KF, S, SPLIT, SHARED_U, SHARED_TGT, CTRL, GX0, SHIFT>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *s_in = reinterpret_cast<float *>(smem_raw);
     uint64_t *full = reinterpret_cast<uint64_t *>(s_in + S * Cfg::STAGE);
@@ -412,7 +425,7 @@ __global__ void __launch_bounds__(TN * SPLIT + 32, MINB) rc_fwdsens_kernel(const
     // ... except in the headline layout (per-system u and target, one thread per system), where every computing thread
     // fetches its own rows (fs_consumer: self_load) and the producer warp has nothing to do (N = 151 553, T = 2000:
     // 3.05 -> 2.04 ms; the forward kernel, which also stores x and y per thread, stays with the producer lanes)
-    const bool self_rows = SPLIT == 1 && !SHARED_U && !SHARED_TGT && !CTRL && !P.bulk;
+    const bool self_rows = !SHIFT && SPLIT == 1 && !SHARED_U && !SHARED_TGT && !CTRL && !P.bulk;
     const bool async_rows = ANY_ROWS && !P.bulk && !self_rows;
     if (tid == 0) {
 #pragma unroll
@@ -459,8 +472,13 @@ __global__ void __launch_bounds__(TN * SPLIT + 32, MINB) rc_fwdsens_kernel(const
                     if (SHARED_U && su_bulk) ptx::bulk_g2s(du, u_base + k0 * 5, (uint32_t)rows * 20u, &full[s], pol_keep);
                     if (SHARED_TGT && st_bulk) ptx::bulk_g2s(dtg, tgt_base + k0, (uint32_t)rows * 4u, &full[s], pol_keep);
                 }
-                if constexpr (!SHARED_U) ptx::copy_rows_async(du, TN * 5, u_base + (k0 * N + n0) * 5, N * 5, rows, valid * 5, lane);
-                if constexpr (!SHARED_TGT) ptx::copy_rows_async(dtg, TN, tgt_base + k0 * N + n0, N, rows, valid, lane);
+                if constexpr (SHIFT) {
+                    ptx::copy_rows_shift_bulk(du, Cfg::U_ROW, u_base + (k0 * N + n0) * 5, N * 5, rows, valid * 5, lane, &full[s], pol);
+                    ptx::copy_rows_shift_bulk(dtg, Cfg::T_ROW, tgt_base + k0 * N + n0, N, rows, valid, lane, &full[s], pol);
+                } else {
+                    if constexpr (!SHARED_U) ptx::copy_rows_async(du, TN * 5, u_base + (k0 * N + n0) * 5, N * 5, rows, valid * 5, lane);
+                    if constexpr (!SHARED_TGT) ptx::copy_rows_async(dtg, TN, tgt_base + k0 * N + n0, N, rows, valid, lane);
+                }
                 if constexpr (CTRL) ptx::copy_rows_async(dc, TN, P.ctrl + k0 * N + n0, N, rows, valid, lane);
                 ptx::cp_async_arrive(&full[s]);  // every lane: arrives once its own copies have landed
                 return;
@@ -482,22 +500,25 @@ __global__ void __launch_bounds__(TN * SPLIT + 32, MINB) rc_fwdsens_kernel(const
                 }
                 return;
             }
+            // per-row copies (no tensor map for this layout): lane r issues row r -- one thread gets a bulk copy out every
+            // ~45 ns only (profiles/r02_tma_probe.txt), the lanes' copies leave together
+            const uint32_t ub = SHARED_U ? 0u : (uint32_t)valid * 20u, tb = SHARED_TGT ? 0u : (uint32_t)valid * 4u,
+                           cb = CTRL ? (uint32_t)valid * 4u : 0u;
+            const uint32_t tx = sh_tx + (ANY_ROWS ? (ub + tb + cb) * (uint32_t)rows : 0u);
             if (lane == 0) {
-                const uint32_t ub = SHARED_U ? 0u : (uint32_t)valid * 20u, tb = SHARED_TGT ? 0u : (uint32_t)valid * 4u,
-                               cb = CTRL ? (uint32_t)valid * 4u : 0u;
-                const uint32_t tx = sh_tx + (ANY_ROWS ? (ub + tb + cb) * (uint32_t)rows : 0u);
                 if (tx == 0) {
                     ptx::mbar_arrive(&full[s]);  // everything was staged with plain stores
                 } else {
                     ptx::mbar_arrive_expect_tx(&full[s], tx);
                     if (SHARED_U && su_bulk) ptx::bulk_g2s(du, u_base + k0 * 5, (uint32_t)rows * 20u, &full[s], pol_keep);
                     if (SHARED_TGT && st_bulk) ptx::bulk_g2s(dtg, tgt_base + k0, (uint32_t)rows * 4u, &full[s], pol_keep);
-                    for (int r = 0; ANY_ROWS && r < rows; ++r) {
-                        if constexpr (!SHARED_U) ptx::bulk_g2s(du + r * TN * 5, u_base + ((k0 + r) * N + n0) * 5, ub, &full[s], pol);
-                        if constexpr (!SHARED_TGT) ptx::bulk_g2s(dtg + r * TN, tgt_base + (k0 + r) * N + n0, tb, &full[s], pol);
-                        if constexpr (CTRL) ptx::bulk_g2s(dc + r * TN, P.ctrl + (k0 + r) * N + n0, cb, &full[s], pol);
-                    }
                 }
+            }
+            __syncwarp();
+            for (int r = lane; ANY_ROWS && tx != 0 && r < rows; r += 32) {
+                if constexpr (!SHARED_U) ptx::bulk_g2s(du + r * TN * 5, u_base + ((k0 + r) * N + n0) * 5, ub, &full[s], pol);
+                if constexpr (!SHARED_TGT) ptx::bulk_g2s(dtg + r * TN, tgt_base + (k0 + r) * N + n0, tb, &full[s], pol);
+                if constexpr (CTRL) ptx::bulk_g2s(dc + r * TN, P.ctrl + (k0 + r) * N + n0, cb, &full[s], pol);
             }
         };
         for (int c = 0; c < C && c < S; ++c) load_chunk(c);
@@ -511,7 +532,7 @@ __global__ void __launch_bounds__(TN * SPLIT + 32, MINB) rc_fwdsens_kernel(const
     // --------------------------------- consumers: role = warp-uniform ---------------------------------
     const int role = SPLIT == 1 ? 0 : tid / TN, sys = SPLIT == 1 ? tid : tid % TN;
 #define DYNAX_FS_ROLE(R)                                                                                         \
-    fs_consumer<TN, KF, S, SPLIT, R, SHARED_U, SHARED_TGT, CTRL, GX0, CHUNK, UNR>(P, smem_raw, s_in, full, empty, sys, n0, \
+    fs_consumer<TN, KF, S, SPLIT, R, SHARED_U, SHARED_TGT, CTRL, GX0, CHUNK, UNR, SHIFT>(P, smem_raw, s_in, full, empty, sys, n0, \
                                                                                   valid, cidx, T, C, self_rows)
     if constexpr (SPLIT == 1) {
         DYNAX_FS_ROLE(0);

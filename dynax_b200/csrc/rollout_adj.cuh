@@ -65,12 +65,17 @@ struct AdjParams {
     alignas(64) CUtensorMap map_u, map_c, map_a1, map_a2;
 };
 
-template <class Model, int TN, int KC, int S, int MODE, bool SHARED_U, bool SHARED_TGT>
+// SHIFT: the instantiation for rows TMA cannot move (N % 4 != 0; every streamed array per-system): rows are staged with
+// 16-byte cp.async at their global offset modulo 16 bytes (ptx::copy_rows_async16), the row pitches grow by 4 floats, and
+// the computing threads add the (warp-uniform) shift of each row to their shared address.
+template <class Model, int TN, int KC, int S, int MODE, bool SHARED_U, bool SHARED_TGT, bool SHIFT = false>
 struct AdjCfg {
+    static_assert(!SHIFT || (!SHARED_U && !SHARED_TGT), "shifted rows: per-system arrays only");
     static constexpr int n = Model::n, m = Model::m, p = Model::p;
-    static constexpr int U_ROW = SHARED_U ? m : TN * m;
-    static constexpr int A1_ROW = (MODE == ADJ_MSE) ? (SHARED_TGT ? 1 : TN) : TN * p;  // target | g_y
-    static constexpr int A2_ROW = (MODE == ADJ_MSE) ? 0 : TN * n;                      // g_x
+    static constexpr int PAD = SHIFT ? 4 : 0;
+    static constexpr int U_ROW = SHARED_U ? m : TN * m + PAD;
+    static constexpr int A1_ROW = (MODE == ADJ_MSE) ? (SHARED_TGT ? 1 : TN + PAD) : TN * p + PAD;  // target | g_y
+    static constexpr int A2_ROW = (MODE == ADJ_MSE) ? 0 : TN * n + PAD;                            // g_x
     static constexpr int U_OFF = 0;
     // every block of a stage starts on a 128-byte boundary (destination alignment of cp.async.bulk.tensor)
     static constexpr int A1_OFF = align32i(KC * U_ROW);
@@ -101,9 +106,9 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-template <class Model, int TN, int KC, int S, int MODE, bool SHARED_U, bool SHARED_TGT, int MINB>
+template <class Model, int TN, int KC, int S, int MODE, bool SHARED_U, bool SHARED_TGT, int MINB, bool SHIFT = false>
 __global__ void __launch_bounds__(TN + 32, MINB) rollout_adj_kernel(const __grid_constant__ AdjParams<Model> P) {
-    using Cfg = AdjCfg<Model, TN, KC, S, MODE, SHARED_U, SHARED_TGT>;
+    using Cfg = AdjCfg<Model, TN, KC, S, MODE, SHARED_U, SHARED_TGT, SHIFT>;
     constexpr int n = Cfg::n, m = Cfg::m, p = Cfg::p;
     constexpr int NG = Model::NG, NOUT = Model::NOUT;
     constexpr int U_ROW = Cfg::U_ROW, A1_ROW = Cfg::A1_ROW, A2_ROW = Cfg::A2_ROW;
@@ -138,7 +143,7 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_adj_kernel(const __grid
     // of every row (self_load below) -- nobody else reads them, so the ring needs no barriers, only the thread's own
     // cp.async groups, and the copies are issued by all warps instead of one (N = 151 553, T = 2000: 3.85 -> 3.60 ms;
     // the general-cotangent mode, which also stores g_u per thread, is faster with the producer lanes: 4.61 vs 4.94 ms).
-    constexpr bool SELF_OK = MODE == ADJ_MSE && !SHARED_U && !SHARED_TGT;
+    constexpr bool SELF_OK = !SHIFT && MODE == ADJ_MSE && !SHARED_U && !SHARED_TGT;
     const bool self_rows = SELF_OK && !P.bulk;
     const bool async_rows = !self_rows && !P.bulk && (!SHARED_U || P.ctrl != nullptr || MODE != ADJ_MSE || !SHARED_TGT);
     if (tid == 0) {
@@ -179,13 +184,16 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_adj_kernel(const __grid
                 return 0;
             }
             if (!P.bulk) {
-                if (pass == 0) ptx::copy_rows_async(dst, row_stride, g + (k0 * N + n0) * w, N * w, rows, valid * w, lane);
+                if (pass == 0) {
+                    if constexpr (SHIFT) ptx::copy_rows_shift_bulk(dst, row_stride, g + (k0 * N + n0) * w, N * w, rows, valid * w, lane, bar, pol);
+                    else ptx::copy_rows_async(dst, row_stride, g + (k0 * N + n0) * w, N * w, rows, valid * w, lane);
+                }
                 return 0;
             }
+            // per-row copies: lane r issues row r (one thread gets a bulk copy out every ~45 ns only; these leave together)
             const uint32_t row_bytes = (uint32_t)valid * w * 4u;
-            if (pass == 1 && lane == 0)
-                for (int r = 0; r < rows; ++r)
-                    ptx::bulk_g2s(dst + r * row_stride, g + ((k0 + r) * N + n0) * w, row_bytes, bar, pol);
+            if (pass == 1 && lane < rows)
+                ptx::bulk_g2s(dst + lane * row_stride, g + ((k0 + lane) * N + n0) * w, row_bytes, bar, pol);
             return row_bytes * (uint32_t)rows;
         };
 
@@ -220,6 +228,7 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_adj_kernel(const __grid
                         if (bytes) ptx::mbar_arrive_expect_tx(&full[s], bytes);
                         else ptx::mbar_arrive(&full[s]);
                     }
+                    __syncwarp();  // pass 1: the other lanes' copies must not complete before the bytes are expected
                 }
             }
         };
@@ -244,6 +253,15 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_adj_kernel(const __grid
     const float dt = P.dt;
     const bool discrete = P.discrete != 0;
     float *ck = P.ckpt + cidx * P.ckpt_chunk_stride + (n0 + tid);  // ckpt[(seg*n + d)*N + system]; only touched when active
+    // SHIFT: row k of this CTA's time slice sits in its slot at its global offset modulo 16 bytes (ptx::copy_rows_async16)
+    constexpr int W1 = MODE == ADJ_MSE ? 1 : p;
+    const float *const a1_base = MODE == ADJ_MSE ? tgt_base : gy_base;
+    const unsigned su0 = SHIFT ? (unsigned)((reinterpret_cast<uintptr_t>(u_base) >> 2) + (uint64_t)(n0 * m)) : 0u;
+    const unsigned s10 = SHIFT ? (unsigned)((reinterpret_cast<uintptr_t>(a1_base) >> 2) + (uint64_t)(n0 * W1)) : 0u;
+    const unsigned s20 = SHIFT ? (unsigned)((reinterpret_cast<uintptr_t>(gx_base) >> 2) + (uint64_t)(n0 * n)) : 0u;
+    auto shu = [&](int64_t k) { return SHIFT ? (int)((su0 + (unsigned)k * (unsigned)(N * m)) & 3u) : 0; };
+    auto sh1 = [&](int64_t k) { return SHIFT ? (int)((s10 + (unsigned)k * (unsigned)(N * W1)) & 3u) : 0; };
+    auto sh2 = [&](int64_t k) { return SHIFT ? (int)((s20 + (unsigned)k * (unsigned)(N * n)) & 3u) : 0; };
     // shared input series + one per-system channel (rc.py:128-131): replace column ctrl_col
     auto override_ctrl = [&](float *u, const float *stage, int j) {
         if (SHARED_U && P.ctrl != nullptr) {
@@ -309,8 +327,9 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_adj_kernel(const __grid
 #pragma unroll
         for (int j = 0; j < KC; ++j) {
             float u[m], r[n];
+            const int o = j * U_ROW + shu(q * KC + j);
 #pragma unroll
-            for (int d = 0; d < m; ++d) u[d] = in[j * U_ROW + d];
+            for (int d = 0; d < m; ++d) u[d] = in[o + d];
             override_ctrl(u, s_in + s * Cfg::STAGE, j);
             M.rhs(xc, u, r);
 #pragma unroll
@@ -359,8 +378,9 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_adj_kernel(const __grid
         for (int j = 0; j + 1 < KC; ++j) {
             if (j + 1 < rows) {
                 float u[m], r[n];
+                const int o = j * U_ROW + shu(k0 + j);
 #pragma unroll
-                for (int d = 0; d < m; ++d) u[d] = in[j * U_ROW + d];
+                for (int d = 0; d < m; ++d) u[d] = in[o + d];
                 override_ctrl(u, st, j);
                 M.rhs(xs[j], u, r);
 #pragma unroll
@@ -372,23 +392,24 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_adj_kernel(const __grid
         for (int j = KC - 1; j >= 0; --j) {
             if (j < rows) {
                 float u[m], gy[p], sv[n], ax[n];
+                const int o = j * U_ROW + shu(k0 + j);
 #pragma unroll
-                for (int d = 0; d < m; ++d) u[d] = in[j * U_ROW + d];
+                for (int d = 0; d < m; ++d) u[d] = in[o + d];
                 override_ctrl(u, st, j);
                 if (MODE == ADJ_MSE) {
                     float y[p];
                     M.out(xs[j], u, y);
-                    const float tg = st[Cfg::A1_OFF + j * A1_ROW + (SHARED_TGT ? 0 : tid)];
+                    const float tg = st[Cfg::A1_OFF + j * A1_ROW + sh1(k0 + j) + (SHARED_TGT ? 0 : tid)];
                     const float res = y[0] - tg;  // 3-inverse.py:100
                     sq = fmaf(res, res, sq);
                     gy[0] = c2T * res;  // d mean(res^2)/dy_k
                 } else {
 #pragma unroll
                     for (int d = 0; d < p; ++d)
-                        gy[d] = P.g_ysol ? st[Cfg::A1_OFF + j * A1_ROW + tid * p + d] : 0.f;
+                        gy[d] = P.g_ysol ? st[Cfg::A1_OFF + j * A1_ROW + sh1(k0 + j) + tid * p + d] : 0.f;
                     if (P.g_xsol) {
 #pragma unroll
-                        for (int d = 0; d < n; ++d) a[d] += st[Cfg::A2_OFF + j * A2_ROW + tid * n + d];
+                        for (int d = 0; d < n; ++d) a[d] += st[Cfg::A2_OFF + j * A2_ROW + sh2(k0 + j) + tid * n + d];
                     }
                 }
 #pragma unroll

@@ -54,10 +54,14 @@ struct FwdParams {
 __host__ __device__ constexpr int align4i(int x) { return (x + 3) & ~3; }
 __host__ __device__ constexpr int align32i(int x) { return (x + 31) & ~31; }   // 128 bytes: tensor-copy destinations
 
-template <class Model, int TN, int KF, int S, bool SHARED_U>
+// SHIFT: the instantiation for per-system rows TMA cannot move (N % 4 != 0): rows are staged with 16-byte cp.async at
+// their global offset modulo 16 bytes (ptx::copy_rows_async16), the row pitch grows by 4 floats, and the computing
+// threads add the (warp-uniform) shift of each row to their shared address.
+template <class Model, int TN, int KF, int S, bool SHARED_U, bool SHIFT = false>
 struct FwdCfg {
+    static_assert(!SHIFT || !SHARED_U, "shifted rows are per-system rows");
     static constexpr int n = Model::n, m = Model::m, p = Model::p;
-    static constexpr int IN_ROW = SHARED_U ? m : TN * m;
+    static constexpr int IN_ROW = SHARED_U ? m : TN * m + (SHIFT ? 4 : 0);   // row pitch in the stage
     static constexpr int CTRL_OFF = align32i(KF * IN_ROW);              // per-system channel rows [KF][TN]
     static constexpr int IN_STAGE = align32i(CTRL_OFF + (SHARED_U ? KF * TN : 0));
     static constexpr int XO_STAGE = KF * TN * n;
@@ -69,9 +73,9 @@ struct FwdCfg {
     static constexpr int THREADS = TN + 32;
 };
 
-template <class Model, int TN, int KF, int S, bool SHARED_U, int MINB>
+template <class Model, int TN, int KF, int S, bool SHARED_U, int MINB, bool SHIFT = false>
 __global__ void __launch_bounds__(TN + 32, MINB) rollout_fwd_kernel(const __grid_constant__ FwdParams<Model> P) {
-    using Cfg = FwdCfg<Model, TN, KF, S, SHARED_U>;
+    using Cfg = FwdCfg<Model, TN, KF, S, SHARED_U, SHIFT>;
     constexpr int n = Cfg::n, m = Cfg::m, p = Cfg::p;
     constexpr int IN_ROW = Cfg::IN_ROW, IN_STAGE = Cfg::IN_STAGE, XO_STAGE = Cfg::XO_STAGE,
                   YO_STAGE = Cfg::YO_STAGE;
@@ -156,20 +160,21 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_fwd_kernel(const __grid
                     for (int i = lane; i < rows * m; i += 32) dst[i] = __ldg(src + i);
                 const bool c_bulk = csrc != nullptr;  // (not async_rows => bulk_in whenever there is a ctrl channel)
                 __syncwarp();
+                const uint32_t row_bytes = (uint32_t)valid * 4u;
                 if (lane == 0) {
                     if (sh_bulk || c_bulk) {
-                        const uint32_t row_bytes = (uint32_t)valid * 4u;
                         const uint32_t c_bytes = P.tensor_in ? (uint32_t)(KF * TN * 4) : row_bytes * (uint32_t)rows;
                         ptx::mbar_arrive_expect_tx(&full[s], (sh_bulk ? sh_bytes : 0u) + (c_bulk ? c_bytes : 0u));
                         if (sh_bulk) ptx::bulk_g2s(dst, src, sh_bytes, &full[s], pol_keep);
                         if (c_bulk && P.tensor_in)   // the whole stage of the channel in one tensor copy
                             ptx::tensor_g2s_3d(cdst, &P.map_c, 0, (int)(n0 / P.inner_c), (int)(t_begin + k0), &full[s], pol);
-                        else if (c_bulk)
-                            for (int r = 0; r < rows; ++r) ptx::bulk_g2s(cdst + r * TN, csrc + r * N, row_bytes, &full[s], pol);
                     } else {
                         ptx::mbar_arrive(&full[s]);
                     }
                 }
+                __syncwarp();
+                if (c_bulk && !P.tensor_in && lane < rows)   // per-row copies: lane r issues row r (they leave together)
+                    ptx::bulk_g2s(cdst + lane * TN, csrc + lane * N, row_bytes, &full[s], pol);
             } else if (P.tensor_in) {
                 // one tensor copy for the stage: KF rows x this CTA's slice (rows past the horizon and systems past N
                 // arrive as zeros; the transaction count is always the full box)
@@ -178,14 +183,15 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_fwd_kernel(const __grid
                     ptx::tensor_g2s_3d(dst, &P.map_u, 0, (int)(n0 * m / P.inner_u), (int)(t_begin + k0), &full[s], pol);
                 }
             } else if (P.bulk_in) {
-                if (lane == 0) {
-                    const uint32_t row_bytes = (uint32_t)valid * m * 4u;
-                    ptx::mbar_arrive_expect_tx(&full[s], row_bytes * (uint32_t)rows);
-                    for (int r = 0; r < rows; ++r)
-                        ptx::bulk_g2s(dst + r * IN_ROW, u_base + ((k0 + r) * N + n0) * m, row_bytes, &full[s], pol);
-                }
+                // per-row copies (N % 4 == 0 but no tensor map for this layout): lane r issues row r -- one thread gets a
+                // bulk copy out every ~45 ns only (profiles/r02_tma_probe.txt), the lanes' copies leave together
+                const uint32_t row_bytes = (uint32_t)valid * m * 4u;
+                if (lane == 0) ptx::mbar_arrive_expect_tx(&full[s], row_bytes * (uint32_t)rows);
+                __syncwarp();
+                if (lane < rows) ptx::bulk_g2s(dst + lane * IN_ROW, u_base + ((k0 + lane) * N + n0) * m, row_bytes, &full[s], pol);
             } else {
-                ptx::copy_rows_async(dst, IN_ROW, u_base + (k0 * N + n0) * m, N * m, rows, valid * m, lane);
+                if constexpr (SHIFT) ptx::copy_rows_shift_bulk(dst, IN_ROW, u_base + (k0 * N + n0) * m, N * m, rows, valid * m, lane, &full[s], pol);
+                else ptx::copy_rows_async(dst, IN_ROW, u_base + (k0 * N + n0) * m, N * m, rows, valid * m, lane);
                 ptx::cp_async_arrive(&full[s]);
             }
         };
@@ -196,24 +202,28 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_fwd_kernel(const __grid
             const int rows = (int)((T - k0) < KF ? (T - k0) : KF);
             const float *sx = s_xo + o * XO_STAGE;
             const float *sy = s_yo + o * YO_STAGE;
-            if (lane == 0) {
-                if (P.tensor_out && rows == KF) {
-                    // full stage: one tensor store per array (systems past N are clipped by the map).  A ragged stage goes
-                    // row by row: in a time-chunked launch the rows behind it belong to the next chunk's CTA.
+            if (P.tensor_out && rows == KF) {
+                // full stage: one tensor store per array (systems past N are clipped by the map).  A ragged stage goes
+                // row by row: in a time-chunked launch the rows behind it belong to the next chunk's CTA.
+                if (lane == 0) {
                     if (emit_x) ptx::tensor_s2g_3d(&P.map_x, 0, (int)(n0 * n / P.inner_x), (int)(t_begin + k0), sx);
                     if (emit_y) ptx::tensor_s2g_3d(&P.map_y, 0, (int)(n0 * p / P.inner_y), (int)(t_begin + k0), sy);
-                } else {
-                    for (int r = 0; r < rows; ++r) {
-                        if (emit_x)
-                            ptx::bulk_s2g(xsol_base + ((k0 + r) * N + n0) * n, sx + r * TN * n, (uint32_t)valid * n * 4u);
-                        if (emit_y)
-                            ptx::bulk_s2g(ysol_base + ((k0 + r) * N + n0) * p, sy + r * TN * p, (uint32_t)valid * p * 4u);
-                    }
+                    ptx::bulk_commit();
+                    ptx::bulk_wait_read<0>();  // out-tile may be overwritten once TMA has read it
                 }
-                ptx::bulk_commit();
-                ptx::bulk_wait_read<0>();  // out-tile may be overwritten once TMA has read it
-                ptx::mbar_arrive(&ofree[o]);
+            } else {
+                // per-row stores: lane r stores row r (bulk groups are per thread: every lane waits for its own)
+                if (lane < rows) {
+                    if (emit_x)
+                        ptx::bulk_s2g(xsol_base + ((k0 + lane) * N + n0) * n, sx + lane * TN * n, (uint32_t)valid * n * 4u);
+                    if (emit_y)
+                        ptx::bulk_s2g(ysol_base + ((k0 + lane) * N + n0) * p, sy + lane * TN * p, (uint32_t)valid * p * 4u);
+                    ptx::bulk_commit();
+                    ptx::bulk_wait_read<0>();
+                }
             }
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&ofree[o]);
         };
 
         for (int64_t c = 0; c < C && c < S; ++c) load_chunk(c);
@@ -226,7 +236,7 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_fwd_kernel(const __grid
                 store_chunk(c);
             }
         }
-        if (lane == 0) ptx::bulk_wait<0>();
+        ptx::bulk_wait<0>();  // every lane: its own store groups have landed
         return;
     }
 
@@ -250,6 +260,9 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_fwd_kernel(const __grid
         ptx::mbar_wait(&full[s], (uint32_t)((c / S) & 1));
         if (emit) ptx::mbar_wait(&ofree[o], (uint32_t)(((c >> 1) & 1) ^ 1));
         const float *in = s_in + s * IN_STAGE + (SHARED_U ? 0 : tid * m);
+        // SHIFT: row j of this stage sits at its global offset modulo 16 bytes (see ptx::copy_rows_async16)
+        const unsigned sh0 = SHIFT ? (unsigned)((reinterpret_cast<uintptr_t>(u_base) >> 2) + (uint64_t)((k0 * N + n0) * m)) : 0u;
+        const unsigned shd = SHIFT ? (unsigned)(N * m) : 0u;
         float *xo = s_xo + o * XO_STAGE + tid * n;
         float *yo = s_yo + o * YO_STAGE + tid * p;
 #pragma unroll
@@ -257,7 +270,7 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_fwd_kernel(const __grid
             if (j < rows) {
                 float u[m];
 #pragma unroll
-                for (int d = 0; d < m; ++d) u[d] = in[j * IN_ROW + d];
+                for (int d = 0; d < m; ++d) u[d] = in[j * IN_ROW + (SHIFT ? (int)((sh0 + j * shd) & 3u) : 0) + d];
                 if (SHARED_U && P.ctrl != nullptr) {
                     const float cv = s_in[s * IN_STAGE + Cfg::CTRL_OFF + j * TN + tid];
 #pragma unroll

@@ -297,6 +297,47 @@ def test_chunked_forward_variants(T, ops, L, su):
 
 
 # ----------------------------------------------------------------------------------------------
+# rows TMA cannot move (N % 4 != 0) on launches of more than one wave: the shifted-row instantiations
+# (rows staged at their global offset modulo 16 bytes, one bulk copy per row interior)
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N", [148 * 2 * 256 + 1, 75777, 75778, 75779])   # N % 4 = 1, 1, 2, 3
+def test_shifted_row_variants(T, ops, L, monkeypatch, N):
+    Tn = 43
+    th, x0, u, tg = rc_data(N, Tn)
+    idx = sample_idx(N)
+    thd, x0d, ud, tgd = cu(T, th), cu(T, x0), cu(T, u), cu(T, tg)
+    (xs, ys, _), sites = launched_by(L, lambda: ops.rc_forward(thd, x0d, ud, DT, time_chunks=0))
+    expect(sites, "launch_fwd<", "RCModel", "TN = 256;", "SHIFT = true")
+    x64, y64 = orc.rc_rollout(th[idx], x0[idx], u[:, idx], DT, np.float64)
+    assert rel_err(xs.cpu().numpy()[:, idx], x64) < TRAJ_RTOL and rel_err(ys.cpu().numpy()[:, idx], y64) < TRAJ_RTOL
+    lb, ub = orc.RC_LB, orc.RC_UB
+    outs = {}
+    for algo in ("1", "0"):                        # tangent kernel, adjoint kernel
+        monkeypatch.setenv("DYNAX_GRAD_ALGO", algo)
+        (out, sites) = launched_by(L, lambda: ops.rc_loss_grad(thd, x0d, ud, tgd, DT, lb, ub, time_chunks=0))
+        expect(sites, "launch_fwdsens" if algo == "1" else "launch_adj", "SHIFT = true")
+        outs[algo] = out
+        _check_loss_grad(out, idx, (th[idx], x0[idx], u[:, idx], tg[:, idx]), False)
+    monkeypatch.delenv("DYNAX_GRAD_ALGO")
+    # the unshifted paths (4-byte copies) give the same numbers bit for bit: same arithmetic on the same inputs
+    monkeypatch.setenv("DYNAX_NO_SHIFT", "1")
+    xs2, ys2, _ = ops.rc_forward(thd, x0d, ud, DT, time_chunks=0)
+    l2, g2, _ = ops.rc_loss_grad(thd, x0d, ud, tgd, DT, lb, ub, time_chunks=0)
+    monkeypatch.delenv("DYNAX_NO_SHIFT")
+    assert T.equal(xs, xs2) and T.equal(ys, ys2)
+    assert T.equal(outs["1"][0], l2) and T.equal(outs["1"][1], g2)
+    rng = np.random.default_rng(6)
+    g_x = rng.normal(size=(Tn, N, 3)).astype(np.float32)
+    g_y = rng.normal(size=(Tn, N, 1)).astype(np.float32)
+    (gth, gx0, gu), sites = launched_by(L, lambda: ops.rc_vjp(thd, x0d, ud, DT, cu(T, g_x), cu(T, g_y), time_chunks=0))
+    expect(sites, "launch_adj", "MODE = 1", "SHIFT = true")
+    rth, rx0, ru = orc.rc_vjp(th[idx], x0[idx], u[:, idx], DT, g_x[:, idx], g_y[:, idx], np.float64)
+    fth, fx0, fu = orc.rc_vjp(th[idx], x0[idx], u[:, idx], DT, g_x[:, idx], g_y[:, idx], np.float32)
+    assert normwise(gth.cpu().numpy()[idx], rth).max() <= max(GRAD_RTOL, 1.25 * normwise(fth, rth).max())
+    assert rel_err(gu.cpu().numpy()[:, idx], ru, floor=1.0) < max(GRAD_RTOL, 1.25 * rel_err(fu, ru, floor=1.0))
+
+
+# ----------------------------------------------------------------------------------------------
 # dense LTI shapes: forward (shared u / small / wide), VJP (shared u / narrow / wide tile), chunked
 # ----------------------------------------------------------------------------------------------
 DIMS = [(1, 1, 1), (2, 1, 1), (2, 2, 1), (2, 2, 2), (3, 1, 1), (3, 3, 1), (3, 3, 3), (3, 5, 1), (4, 1, 1), (4, 2, 2),

@@ -16,7 +16,7 @@ def best(fn, it=6):
     return b
 g = torch.Generator(device="cuda").manual_seed(0)
 T = 2000
-for N in (151553, 151552, 75777):
+for N in [int(x) for x in os.environ.get('AB_N', '151553,151552,75777').split(',')]:
     th = torch.tensor(RC_NOMINAL, device="cuda", dtype=torch.float32)[None] * torch.exp(torch.empty((N, 7), device="cuda").uniform_(-0.2, 0.2, generator=g))
     x0 = torch.tensor([[20.0, 30.0, 26.0]], device="cuda").repeat(N, 1)
     u = torch.rand((T, N, 5), device="cuda", generator=g); u[..., 0] = 15 + 10 * u[..., 0]
