@@ -108,17 +108,72 @@ __device__ __forceinline__ void split_tf32(float a, uint32_t &hi, uint32_t &lo) 
     lo = __float_as_uint(a - __uint_as_float(hi));
 }
 
-// Two tanh for THREE MUFU ops (the kernel is bound by the MUFU pipe): tanh(x) = 1 - 2/(e^{2x}+1) and the two
-// reciprocals share one rcp:  r = 1/(a b),  1/a = r b,  1/b = r a.  The exponent is clamped at 2^60 so
-// a*b stays finite (tanh is 1 to fp32 precision far below that).
-__device__ __forceinline__ void fast_tanh2(float x0, float x1, float &t0, float &t1) {
-    float e0, e1, r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fminf(x0 * 2.885390081777927f, 60.f)));  // e^(2x)
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fminf(x1 * 2.885390081777927f, 60.f)));
-    const float a = e0 + 1.0f, b = e1 + 1.0f;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a * b));
-    t0 = fmaf(-2.0f, r * b, 1.0f);
-    t1 = fmaf(-2.0f, r * a, 1.0f);
+constexpr float K2LOG2E = 2.885390081777927f;
+
+__device__ __forceinline__ float ex2v(float x) {  // volatile: the MUFU stream keeps the order of the source
+    float e;
+    asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x));
+    return e;
+}
+__device__ __forceinline__ float rcpv(float x) {
+    float r;
+    asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// Four tanh for FIVE MUFU ops, in stages so that the caller can fix the order of the MUFU stream (a warp issues in
+// order and the MUFU pipe takes one instruction per 8 cycles: reciprocals queued behind all 16 exponentials of a slice
+// would expose the whole tail of the slice).  Inputs: pre-activations (v0,v1),(v2,v3) WITHOUT bias and
+// bk = b * 2log2(e) - 1.  With h_i = 2^(s_i - 1) = e^{2x_i}/2 (clamped at 2^29, so the product of four denominators
+// stays finite):  a_i = h_i + 1/2,  d_i = h_i - 1/2 (exact),  tanh(x_i) = d_i / a_i;  r = 1/(a0 a1 a2 a3),
+// 1/a0 = r (a2 a3) a1, ...  Outputs (tanh0, tanh2), (tanh1, tanh3).
+struct TanhQuad {
+    float s[4];          // clamped exponents
+    float2 a02, a13, d02, d13, pp;
+    float r;
+    __device__ __forceinline__ void front(float2 v01, float2 v23, float4 bk) {
+        const float2 kk = make_float2(K2LOG2E, K2LOG2E);
+        const float2 s01 = __ffma2_rn(v01, kk, make_float2(bk.x, bk.y));
+        const float2 s23 = __ffma2_rn(v23, kk, make_float2(bk.z, bk.w));
+        s[0] = fminf(s01.x, 29.f); s[1] = fminf(s01.y, 29.f); s[2] = fminf(s23.x, 29.f); s[3] = fminf(s23.y, 29.f);
+    }
+    __device__ __forceinline__ void exps() {  // 4 MUFU
+        const float e0 = ex2v(s[0]), e1 = ex2v(s[1]), e2 = ex2v(s[2]), e3 = ex2v(s[3]);
+        const float2 half2 = make_float2(0.5f, 0.5f), mhalf2 = make_float2(-0.5f, -0.5f);
+        const float2 h02 = make_float2(e0, e2), h13 = make_float2(e1, e3);
+        a02 = __fadd2_rn(h02, half2); a13 = __fadd2_rn(h13, half2);
+        d02 = __fadd2_rn(h02, mhalf2); d13 = __fadd2_rn(h13, mhalf2);
+        pp = __fmul2_rn(a02, a13);  // (a0 a1, a2 a3)
+    }
+    __device__ __forceinline__ void recip() { r = rcpv(pp.x * pp.y); }  // 1 MUFU
+    // d/a rather than 1 - 1/a: d is exact, so small |x| keep their RELATIVE accuracy up to ex2.approx's own error (1 - 1/a
+    // cancels: 2.5e-7 absolute whatever |tanh|; measured on config 5 at dt = 900, 2048 steps: 90th percentile of the
+    // per-trajectory error 6.9e-5 against 4.6e-5), for two more packed multiplications per pair (-2.7 % throughput).
+    __device__ __forceinline__ void finish(float2 &t02, float2 &t13) const {
+        const float2 q = make_float2(r * pp.y, r * pp.x);  // (1/(a0 a1), 1/(a2 a3))
+        t02 = __fmul2_rn(__fmul2_rn(d02, a13), q);          // d0 a1 / (a0 a1), d2 a3 / (a2 a3)
+        t13 = __fmul2_rn(__fmul2_rn(d13, a02), q);
+    }
+};
+
+// Sixteen tanh in natural order: t[i] = tanh(x_i + b_i) from the pre-activations v[i] and bk[i] = b_i * 2log2(e) - 1
+// (16-byte aligned shared array).
+__device__ __forceinline__ void tanh16(const float (&v)[16], const float *bk, float (&t)[16]) {
+    TanhQuad Q[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        Q[q].front(make_float2(v[4 * q], v[4 * q + 1]), make_float2(v[4 * q + 2], v[4 * q + 3]),
+                   *reinterpret_cast<const float4 *>(bk + 4 * q));
+#pragma unroll
+    for (int q = 0; q < 4; ++q) Q[q].exps();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) Q[q].recip();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float2 t02, t13;
+        Q[q].finish(t02, t13);
+        t[4 * q] = t02.x; t[4 * q + 2] = t02.y; t[4 * q + 1] = t13.x; t[4 * q + 3] = t13.y;
+    }
 }
 
 }  // namespace tc
@@ -144,8 +199,7 @@ __device__ __forceinline__ void fast_tanh2(float x0, float x1, float &t0, float 
 // the staged copies of W2 (K index) and W3 follow that permutation (free: staged once per CTA).
 // ------------------------------------------------------------------------------------------------------------
 namespace tcf {
-using tc::TN; using tc::NX; using tc::NU; using tc::NIN; using tc::S; using tc::SBO;
-constexpr float K2LOG2E = 2.885390081777927f;
+using tc::TN; using tc::NX; using tc::NU; using tc::NIN; using tc::S; using tc::SBO; using tc::K2LOG2E; using tc::TanhQuad;
 __host__ __device__ constexpr int perm4(int k) { return (k & ~3) | (((k & 1) << 1) | ((k >> 1) & 1)); }  // 0,2,1,3 (involution)
 
 template <int HID>
@@ -200,52 +254,6 @@ __device__ __forceinline__ void ld_fence(uint32_t (&r)[16]) {  // the operands t
                  :
                  : "memory");
 }
-
-__device__ __forceinline__ float ex2v(float x) {  // volatile: the MUFU stream keeps the order of the source
-    float e;
-    asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x));
-    return e;
-}
-__device__ __forceinline__ float rcpv(float x) {
-    float r;
-    asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-
-// Four tanh for FIVE MUFU ops, in stages so that the caller can fix the order of the MUFU stream (a warp issues in
-// order and the MUFU pipe takes one instruction per 8 cycles: reciprocals queued behind all 16 exponentials of a slice
-// would expose the whole tail of the slice).  Inputs: pre-activations (v0,v1),(v2,v3) WITHOUT bias and
-// bk = b * 2log2(e) - 1.  With h_i = 2^(s_i - 1) = e^{2x_i}/2 (clamped at 2^29, so the product of four denominators
-// stays finite):  a_i = h_i + 1/2,  d_i = h_i - 1/2 (exact),  tanh(x_i) = d_i / a_i;  r = 1/(a0 a1 a2 a3),
-// 1/a0 = r (a2 a3) a1, ...  Outputs (tanh0, tanh2), (tanh1, tanh3).
-struct TanhQuad {
-    float s[4];          // clamped exponents
-    float2 a02, a13, d02, d13, pp;
-    float r;
-    __device__ __forceinline__ void front(float2 v01, float2 v23, float4 bk) {
-        const float2 kk = make_float2(K2LOG2E, K2LOG2E);
-        const float2 s01 = __ffma2_rn(v01, kk, make_float2(bk.x, bk.y));
-        const float2 s23 = __ffma2_rn(v23, kk, make_float2(bk.z, bk.w));
-        s[0] = fminf(s01.x, 29.f); s[1] = fminf(s01.y, 29.f); s[2] = fminf(s23.x, 29.f); s[3] = fminf(s23.y, 29.f);
-    }
-    __device__ __forceinline__ void exps() {  // 4 MUFU
-        const float e0 = ex2v(s[0]), e1 = ex2v(s[1]), e2 = ex2v(s[2]), e3 = ex2v(s[3]);
-        const float2 half2 = make_float2(0.5f, 0.5f), mhalf2 = make_float2(-0.5f, -0.5f);
-        const float2 h02 = make_float2(e0, e2), h13 = make_float2(e1, e3);
-        a02 = __fadd2_rn(h02, half2); a13 = __fadd2_rn(h13, half2);
-        d02 = __fadd2_rn(h02, mhalf2); d13 = __fadd2_rn(h13, mhalf2);
-        pp = __fmul2_rn(a02, a13);  // (a0 a1, a2 a3)
-    }
-    __device__ __forceinline__ void recip() { r = rcpv(pp.x * pp.y); }  // 1 MUFU
-    // d/a rather than 1 - 1/a: d is exact, so small |x| keep their RELATIVE accuracy up to ex2.approx's own error (1 - 1/a
-    // cancels: 2.5e-7 absolute whatever |tanh|; measured on config 5 at dt = 900, 2048 steps: 90th percentile of the
-    // per-trajectory error 6.9e-5 against 4.6e-5), for two more packed multiplications per pair (-2.7 % throughput).
-    __device__ __forceinline__ void finish(float2 &t02, float2 &t13) const {
-        const float2 q = make_float2(r * pp.y, r * pp.x);  // (1/(a0 a1), 1/(a2 a3))
-        t02 = __fmul2_rn(__fmul2_rn(d02, a13), q);          // d0 a1 / (a0 a1), d2 a3 / (a2 a3)
-        t13 = __fmul2_rn(__fmul2_rn(d13, a02), q);
-    }
-};
 
 }  // namespace tcf
 

@@ -121,8 +121,8 @@ __global__ void __launch_bounds__(vtc::NTHR, 1) node_vjp_tc_kernel(const NodeVjp
         sm[G_W1TLO + wofs16(c, a)] = __uint_as_float(lo);
     }
     for (int e = tid; e < HID; e += NTHR) {
-        sm[G_B1 + e] = __ldg(P.b1 + e);
-        sm[G_B2 + e] = __ldg(P.b2 + e);
+        sm[G_B1 + e] = fmaf(__ldg(P.b1 + e), K2LOG2E, -1.0f);  // pre-scaled for tc::tanh16
+        sm[G_B2 + e] = fmaf(__ldg(P.b2 + e), K2LOG2E, -1.0f);
     }
     for (int e = tid; e < NX * HID; e += NTHR) sm[G_W3 + e] = __ldg(P.W3 + e);
     if (tid < NX) sm[G_B3 + tid] = __ldg(P.b3 + tid);
@@ -314,15 +314,11 @@ __global__ void __launch_bounds__(vtc::NTHR, 1) node_vjp_tc_kernel(const NodeVjp
 #pragma unroll
         for (int cc = 0; cc < HC; cc += 16) {
             const int c = c_lo + cc;
-            float v[16];
+            float v[16], t[16];
             tmem_ld16(lane_base + COL_D + c, v);
+            tanh16(v, sm + G_B1 + c, t);
 #pragma unroll
-            for (int j = 0; j < 16; j += 2) {
-                float t0, t1;
-                fast_tanh2(v[j] + sm[G_B1 + c + j], v[j + 1] + sm[G_B1 + c + j + 1], t0, t1);
-                split_tf32(t0, hi[j], lo[j]);
-                split_tf32(t1, hi[j + 1], lo[j + 1]);
-            }
+            for (int j = 0; j < 16; ++j) split_tf32(t[j], hi[j], lo[j]);
             tmem_st16(lane_base + COL_AHI + c, hi);
             tmem_st16(lane_base + COL_ALO + c, lo);
         }
@@ -336,16 +332,16 @@ __global__ void __launch_bounds__(vtc::NTHR, 1) node_vjp_tc_kernel(const NodeVjp
 #pragma unroll
         for (int cc = 0; cc < HC; cc += 16) {
             const int c = c_lo + cc;
-            float v[16];
+            float v[16], t[16];
             tmem_ld16(lane_base + COL_D + c, v);
+            tanh16(v, sm + G_B2 + c, t);
 #pragma unroll
-            for (int j = 0; j < 16; j += 2) {
-                float h0, h1;
-                fast_tanh2(v[j] + sm[G_B2 + c + j], v[j + 1] + sm[G_B2 + c + j + 1], h0, h1);
+            for (int j = 0; j < 16; j += 4) {
 #pragma unroll
                 for (int d = 0; d < NX; ++d) {
-                    pr[d] = fmaf(sm[G_W3 + d * HID + c + j], h0, pr[d]);
-                    pr[d] = fmaf(sm[G_W3 + d * HID + c + j + 1], h1, pr[d]);
+                    const float4 w = *reinterpret_cast<const float4 *>(sm + G_W3 + d * HID + c + j);
+                    pr[d] = fmaf(w.x, t[j], pr[d]); pr[d] = fmaf(w.y, t[j + 1], pr[d]);
+                    pr[d] = fmaf(w.z, t[j + 2], pr[d]); pr[d] = fmaf(w.w, t[j + 3], pr[d]);
                 }
             }
         }
@@ -377,18 +373,14 @@ __global__ void __launch_bounds__(vtc::NTHR, 1) node_vjp_tc_kernel(const NodeVjp
 #pragma unroll
         for (int cc = 0; cc < HC; cc += 16) {
             const int c = c_lo + cc;
-            float v[16];
+            float v[16], t[16];
             tmem_ld16(lane_base + COL_D + c, v);
+            tanh16(v, sm + G_B1 + c, t);
 #pragma unroll
-            for (int j = 0; j < 16; j += 2) {
-                float t0, t1;
-                fast_tanh2(v[j] + sm[G_B1 + c + j], v[j + 1] + sm[G_B1 + c + j + 1], t0, t1);
-                h1[cc + j] = t0;
-                h1[cc + j + 1] = t1;
-                H1[(c + j) * LD + row] = t0;
-                H1[(c + j + 1) * LD + row] = t1;
-                split_tf32(t0, hi[j], lo[j]);
-                split_tf32(t1, hi[j + 1], lo[j + 1]);
+            for (int j = 0; j < 16; ++j) {
+                h1[cc + j] = t[j];
+                H1[(c + j) * LD + row] = t[j];
+                split_tf32(t[j], hi[j], lo[j]);
             }
             tmem_st16(lane_base + COL_AHI + c, hi);
             tmem_st16(lane_base + COL_ALO + c, lo);
@@ -401,25 +393,25 @@ __global__ void __launch_bounds__(vtc::NTHR, 1) node_vjp_tc_kernel(const NodeVjp
 #pragma unroll
         for (int cc = 0; cc < HC; cc += 16) {
             const int c = c_lo + cc;
-            float v[16];
+            float v[16], t[16];
             tmem_ld16(lane_base + COL_D + c, v);
+            tanh16(v, sm + G_B2 + c, t);
 #pragma unroll
-            for (int j = 0; j < 16; j += 2) {
-                float t0, t1;
-                fast_tanh2(v[j] + sm[G_B2 + c + j], v[j + 1] + sm[G_B2 + c + j + 1], t0, t1);
-                float g0 = 0.f, g1 = 0.f;
+            for (int j = 0; j < 16; j += 4) {
+                float g[4] = {0.f, 0.f, 0.f, 0.f};   // (W3^T d3)_(c+j..c+j+3)
 #pragma unroll
                 for (int d = 0; d < NX; ++d) {
-                    g0 = fmaf(sm[G_W3 + d * HID + c + j], d3[d], g0);
-                    g1 = fmaf(sm[G_W3 + d * HID + c + j + 1], d3[d], g1);
+                    const float4 w = *reinterpret_cast<const float4 *>(sm + G_W3 + d * HID + c + j);
+                    g[0] = fmaf(w.x, d3[d], g[0]); g[1] = fmaf(w.y, d3[d], g[1]);
+                    g[2] = fmaf(w.z, d3[d], g[2]); g[3] = fmaf(w.w, d3[d], g[3]);
                 }
-                const float e0 = g0 * (1.f - t0 * t0), e1 = g1 * (1.f - t1 * t1);
-                H2[(c + j) * LD + row] = t0;
-                H2[(c + j + 1) * LD + row] = t1;
-                D2[(c + j) * LD + row] = e0;
-                D2[(c + j + 1) * LD + row] = e1;
-                split_tf32(e0, hi[j], lo[j]);
-                split_tf32(e1, hi[j + 1], lo[j + 1]);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float tq = t[j + q], e = g[q] * (1.f - tq * tq);
+                    H2[(c + j + q) * LD + row] = tq;
+                    D2[(c + j + q) * LD + row] = e;
+                    split_tf32(e, hi[j + q], lo[j + q]);
+                }
             }
             tmem_st16(lane_base + COL_AHI + c, hi);
             tmem_st16(lane_base + COL_ALO + c, lo);
