@@ -270,7 +270,7 @@ __global__ void tangent_stitch_kernel(const float *psi, const float *s_end, cons
         }
     }
     if (jj == 0) loss[i] = (float)L;
-    g_theta[i * 7 + jj] = (float)g;
+    if (g_theta != nullptr) g_theta[i * 7 + jj] = (float)g;   // (NULL: loss only, as dynax_rc_loss_grad_f32)
 }
 
 struct ChunkedAdjWs {

@@ -120,7 +120,7 @@ int dynax_rc_loss_grad_chunked_f32(const float *theta, const float *x0, const fl
  *   required either way.
  * lb/ub: [7] device arrays or NULL (no penalty).  loss:[N], g_theta:[N,7]; with DYNAX_SHARED_THETA
  * loss:[1] (mean over systems is NOT taken: it is the SUM over systems of the MSE terms plus one
- * penalty) and g_theta:[7].  g_x0:[N,3] or NULL. */
+ * penalty) and g_theta:[7].  g_theta may be NULL (loss only), g_x0:[N,3] or NULL. */
 int dynax_rc_loss_grad_f32(const float *theta, const float *x0, const float *u, const float *target,
                            const float *lb, const float *ub,
                            float *loss, float *g_theta, float *g_x0,

@@ -58,6 +58,13 @@ def test_no_out_of_bounds_writes(N, Tn):
     _lib.check(L.dynax_rc_loss_grad_chunked_f32(th.data_ptr(), x0.data_ptr(), u.data_ptr(), tg.data_ptr(), None, None,
                                                 loss3.data_ptr(), grad3.data_ptr(), None, N, Tn, 3600.0, 0, 8,
                                                 ws3.data_ptr(), ws3.numel() * 4, None))
+    # loss only (g_theta = NULL) through the time-chunked entry point: same loss, no store through the NULL pointer
+    loss4 = ar.out(N)
+    _lib.check(L.dynax_rc_loss_grad_chunked_f32(th.data_ptr(), x0.data_ptr(), u.data_ptr(), tg.data_ptr(), None, None,
+                                                loss4.data_ptr(), None, None, N, Tn, 3600.0, 0, 8,
+                                                ws3.data_ptr(), ws3.numel() * 4, None))
+    torch.cuda.synchronize()
+    assert torch.equal(loss4, loss3)
     W = [c(w) for w in orc.synth_mlp(152)]
     xn, yn = ar.out(Tn, N, 3), ar.out(Tn, N, 1)
     _lib.check(L.dynax_node_rk4_forward_f32(*[w.data_ptr() for w in W], x0.data_ptr(), u.data_ptr(), xn.data_ptr(),
