@@ -56,6 +56,7 @@ struct NodeVjpParams {
     double *acc;
     int64_t N, T;
     float dt;
+    int shared_u;  // u is ONE series [T,5]; g_u is then [T,5], summed over trajectories (zeroed by the caller)
 };
 
 template <int HID>
@@ -233,7 +234,7 @@ __global__ void __launch_bounds__(nv::TN, 1) node_vjp_kernel(const NodeVjpParams
             if (active && P.g_xsol) lam[d] += P.g_xsol[(k * N + iu) * NX + d];   // cotangent of xsol[k] = x_{k+1}
         }
 #pragma unroll
-        for (int d = 0; d < NU; ++d) u[d] = active ? P.u[(k * N + iu) * NU + d] : 0.f;
+        for (int d = 0; d < NU; ++d) u[d] = active ? P.u[(P.shared_u ? k : k * N + iu) * NU + d] : 0.f;
         const int stages = rk4 ? 4 : 1;
         // stage points
 #pragma unroll
@@ -282,9 +283,19 @@ __global__ void __launch_bounds__(nv::TN, 1) node_vjp_kernel(const NodeVjpParams
 #pragma unroll
         for (int d = 0; d < NX; ++d) lam[d] += xbar[d];
         if (active && P.g_ysol) lam[0] += P.g_ysol[k * N + iu];   // y_k = x_k[0]
-        if (active && P.g_u) {
+        if (P.g_u) {
+            if (P.shared_u) {  // one row per step: sum over this warp's trajectories, one atomic per warp and channel
 #pragma unroll
-            for (int d = 0; d < NU; ++d) P.g_u[(k * N + iu) * NU + d] = ubar[d];
+                for (int d = 0; d < NU; ++d) {
+                    float v = active ? ubar[d] : 0.f;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                    if ((tid & 31) == 0) atomicAdd(P.g_u + k * NU + d, v);
+                }
+            } else if (active) {
+#pragma unroll
+                for (int d = 0; d < NU; ++d) P.g_u[(k * N + iu) * NU + d] = ubar[d];
+            }
         }
         if (((T - 1 - k) % FLUSH) == FLUSH - 1) flush();
     }
@@ -315,11 +326,11 @@ template <int HID>
 static int launch_node_vjp_cc(const float *W1, const float *b1, const float *W2, const float *b2, const float *W3,
                               const float *b3, const float *x0, const float *u, const float *xsol, const float *stage_x,
                               const float *g_xsol, const float *g_ysol, float *g_x0, float *g_u, double *acc, int64_t N,
-                              int64_t T, float dt, int rk4, cudaStream_t st) {
+                              int64_t T, float dt, int rk4, int shared_u, cudaStream_t st) {
     NodeVjpParams<HID> P;
     P.mp.W1 = W1; P.mp.b1 = b1; P.mp.W2 = W2; P.mp.b2 = b2; P.mp.W3 = W3; P.mp.b3 = b3; P.mp.rk4 = rk4;
     P.x0 = x0; P.u = u; P.xsol = xsol; P.stage_x = stage_x; P.g_xsol = g_xsol; P.g_ysol = g_ysol; P.g_x0 = g_x0; P.g_u = g_u;
-    P.acc = acc; P.N = N; P.T = T; P.dt = dt;
+    P.acc = acc; P.N = N; P.T = T; P.dt = dt; P.shared_u = shared_u;
     int rc = set_smem(node_vjp_kernel<HID>, nv::L<HID>::SMEM_BYTES);
     if (rc != DYNAX_OK) return rc;
     node_vjp_kernel<HID><<<(unsigned)((N + nv::TN - 1) / nv::TN), nv::TN, nv::L<HID>::SMEM_BYTES, st>>>(P);
@@ -358,7 +369,7 @@ int dynax_node_rk4_vjp_stages_f32(const float *W1, const float *b1, const float 
     if (!W1 || !b1 || !W2 || !b2 || !W3 || !b3 || !x0 || !u) return fail(DYNAX_ERR_INVALID_ARGUMENT, "weights, x0, u must be non-NULL");
     if (!xsol && T > 1) return fail(DYNAX_ERR_INVALID_ARGUMENT, "xsol (the forward trajectory) must be given");
     if (!g_xsol && !g_ysol) return fail(DYNAX_ERR_INVALID_ARGUMENT, "need g_xsol or g_ysol");
-    if (flags & ~DYNAX_SOLVER_EULER) return fail(DYNAX_ERR_INVALID_ARGUMENT, "unsupported flags 0x%x for node_rk4_vjp", flags);
+    if (flags & ~(DYNAX_SOLVER_EULER | DYNAX_SHARED_U)) return fail(DYNAX_ERR_INVALID_ARGUMENT, "unsupported flags 0x%x for node_rk4_vjp", flags);
     if (!(n == 3 && m == 5 && p == 1 && (hidden == 32 || hidden == 64)))
         return fail(DYNAX_ERR_UNSUPPORTED_DIMS, "MLP gradient kernels are instantiated for (n,m,p)=(3,5,1), hidden in {32,64}; got (%d,%d,%d,%d)", n, m, p, hidden);
     const size_t need = dynax_node_rk4_vjp_workspace();
@@ -368,18 +379,20 @@ int dynax_node_rk4_vjp_stages_f32(const float *W1, const float *b1, const float 
     double *acc = reinterpret_cast<double *>(ws);
     const int rk4 = (flags & DYNAX_SOLVER_EULER) ? 0 : 1;
     DYNAX_CUDA_TRY(cudaMemsetAsync(ws, 0, need, st));
+    const int shared_u = (flags & DYNAX_SHARED_U) ? 1 : 0;
+    if (shared_u && g_u) DYNAX_CUDA_TRY(cudaMemsetAsync(g_u, 0, sizeof(float) * 5 * (size_t)T, st));  // summed with atomics
     static_assert(vtc::A_END == nv::L<64>::A_END, "both kernels share the accumulator layout");
     // hidden = 64: tcgen05 kernel (node_vjp_tc.cuh); DYNAX_NODE_VJP_IMPL=0 and hidden = 32: CUDA-core kernel
     const char *impl = getenv("DYNAX_NODE_VJP_IMPL");
     if (hidden == 32) {
-        rc = launch_node_vjp_cc<32>(W1, b1, W2, b2, W3, b3, x0, u, xsol, stage_x, g_xsol, g_ysol, g_x0, g_u, acc, N, T, dt, rk4, st);
+        rc = launch_node_vjp_cc<32>(W1, b1, W2, b2, W3, b3, x0, u, xsol, stage_x, g_xsol, g_ysol, g_x0, g_u, acc, N, T, dt, rk4, shared_u, st);
     } else if (impl && impl[0] == '0') {
-        rc = launch_node_vjp_cc<64>(W1, b1, W2, b2, W3, b3, x0, u, xsol, stage_x, g_xsol, g_ysol, g_x0, g_u, acc, N, T, dt, rk4, st);
+        rc = launch_node_vjp_cc<64>(W1, b1, W2, b2, W3, b3, x0, u, xsol, stage_x, g_xsol, g_ysol, g_x0, g_u, acc, N, T, dt, rk4, shared_u, st);
     } else {
         NodeVjpTcParams Q;
         Q.W1 = W1; Q.b1 = b1; Q.W2 = W2; Q.b2 = b2; Q.W3 = W3; Q.b3 = b3;
         Q.x0 = x0; Q.u = u; Q.xsol = xsol; Q.stage_x = stage_x; Q.g_xsol = g_xsol; Q.g_ysol = g_ysol; Q.g_x0 = g_x0; Q.g_u = g_u;
-        Q.acc = acc; Q.N = N; Q.T = T; Q.dt = dt; Q.rk4 = rk4;
+        Q.acc = acc; Q.N = N; Q.T = T; Q.dt = dt; Q.rk4 = rk4; Q.shared_u = shared_u;
         rc = set_smem(node_vjp_tc_kernel, vtc::SMEM_BYTES);
         if (rc != DYNAX_OK) return rc;
         node_vjp_tc_kernel<<<(unsigned)((N + vtc::TN - 1) / vtc::TN), vtc::NTHR, vtc::SMEM_BYTES, st>>>(Q);

@@ -38,6 +38,7 @@ struct NodeVjpTcParams {
     int64_t N, T;
     float dt;
     int rk4;
+    int shared_u;  // u is ONE series [T,5] for every trajectory; g_u is then [T,5], summed over trajectories (zeroed by the caller)
 };
 
 namespace vtc {
@@ -460,7 +461,7 @@ __global__ void __launch_bounds__(vtc::NTHR, 1) node_vjp_tc_kernel(const NodeVjp
             if (active && P.g_xsol) lam[d] += __ldg(P.g_xsol + (k * N + iu) * NX + d);  // cotangent of xsol[k] = x_{k+1}
         }
 #pragma unroll
-        for (int d = 0; d < NU; ++d) u[d] = active ? __ldg(P.u + (k * N + iu) * NU + d) : 0.f;
+        for (int d = 0; d < NU; ++d) u[d] = active ? __ldg(P.u + (P.shared_u ? k : k * N + iu) * NU + d) : 0.f;
         // stage points (x parts; the u part is the same for all four)
 #pragma unroll
         for (int d = 0; d < NX; ++d) zx[0][d] = x[d];
@@ -510,9 +511,19 @@ __global__ void __launch_bounds__(vtc::NTHR, 1) node_vjp_tc_kernel(const NodeVjp
 #pragma unroll
         for (int d = 0; d < NX; ++d) lam[d] += xbar[d];
         if (active && P.g_ysol) lam[0] += __ldg(P.g_ysol + k * N + iu);  // y_k = x_k[0]
-        if (active && P.g_u && half == 0) {
+        if (P.g_u && half == 0) {
+            if (P.shared_u) {  // one row per step: sum over this warp's trajectories, one atomic per warp and channel
 #pragma unroll
-            for (int d = 0; d < NU; ++d) P.g_u[(k * N + iu) * NU + d] = ubar[d];
+                for (int d = 0; d < NU; ++d) {
+                    float v = active ? ubar[d] : 0.f;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                    if ((tid & 31) == 0) atomicAdd(P.g_u + k * NU + d, v);
+                }
+            } else if (active) {
+#pragma unroll
+                for (int d = 0; d < NU; ++d) P.g_u[(k * N + iu) * NU + d] = ubar[d];
+            }
         }
         if (((T - 1 - k) % FLUSH) == FLUSH - 1) flush();  // (pending tile work lands in a later flush)
     }

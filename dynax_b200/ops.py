@@ -618,11 +618,9 @@ def node_rk4_vjp(W1, b1, W2, b2, W3, b3, x0, u, xsol, dt, g_xsol=None, g_ysol=No
     x0, u, xsol = _f32c(x0, "x0"), _f32c(u, "u"), _f32c(xsol, "xsol")
     hidden, n = ws_[1].numel(), ws_[5].numel()
     m = ws_[0].shape[1] - n
-    # same shape rules as the forward (a shared series is u[T,m] or u[T,1,m]); the VJP kernels index u per system, so a
-    # shared series is materialised here and its g_u summed over systems below
+    # same shape rules as the forward (a shared series is u[T,m] or u[T,1,m]: DYNAX_SHARED_U, g_u is then [T,1,m], summed
+    # over the systems inside the kernel)
     x0, u, N, T, shared_u = _canon_batch(None, x0, u, n, m)
-    if shared_u:
-        u = u.expand(T, N, m).contiguous()
     dev = x0.device
     if g_xsol is not None:
         g_xsol = _f32c(g_xsol, "g_xsol").reshape(T, N, n)
@@ -630,7 +628,7 @@ def node_rk4_vjp(W1, b1, W2, b2, W3, b3, x0, u, xsol, dt, g_xsol=None, g_ysol=No
         g_ysol = _f32c(g_ysol, "g_ysol").reshape(T, N, 1)
     gw = [torch.empty_like(t) for t in ws_]
     gx0 = torch.empty((N, n), dtype=torch.float32, device=dev)
-    gu = torch.empty((T, N, m), dtype=torch.float32, device=dev) if need_u else None
+    gu = torch.empty((T, 1 if shared_u else N, m), dtype=torch.float32, device=dev) if need_u else None
     wsb = _ws(lib().dynax_node_rk4_vjp_workspace(), dev)
     with torch.cuda.device(dev):
         if stage_x is not None:
@@ -638,9 +636,8 @@ def node_rk4_vjp(W1, b1, W2, b2, W3, b3, x0, u, xsol, dt, g_xsol=None, g_ysol=No
         check(lib().dynax_node_rk4_vjp_stages_f32(*[_ptr(t) for t in ws_], _ptr(x0), _ptr(u), _ptr(xsol), _ptr(stage_x),
                                                   _ptr(g_xsol), _ptr(g_ysol), *[_ptr(t) for t in gw], _ptr(gx0),
                                                   _ptr(gu), N, T, n, m, 1, hidden, float(dt),
-                                                  _lib.SOLVER_EULER if euler else 0, _ptr(wsb), wsb.numel(), _stream()))
-    if gu is not None and shared_u:
-        gu = gu.sum(dim=1, keepdim=True)
+                                                  (_lib.SOLVER_EULER if euler else 0) | (SHARED_U if shared_u else 0),
+                                                  _ptr(wsb), wsb.numel(), _stream()))
     return (*gw, gx0, gu)
 
 

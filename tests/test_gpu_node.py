@@ -175,14 +175,17 @@ def test_vjp_with_saved_stage_points(T, monkeypatch, impl):
     assert st1 is not None and T.equal(st1, st2)
 
 
+@pytest.mark.parametrize("impl,hidden", [("tc", 64), ("cuda_core", 64), ("cuda_core", 32)])
 @pytest.mark.parametrize("shape", ["T1m", "Tm"])
-def test_vjp_shared_input_series(T, shape):
-    """A shared input series (u[T,1,5] or u[T,5] with N > 1 systems) through autograd: the forward accepts it, the
-    VJP kernels index u per system -- the glue materialises the broadcast and sums g_u back to the caller's shape
+def test_vjp_shared_input_series(T, monkeypatch, shape, impl, hidden):
+    """A shared input series (u[T,1,5] or u[T,5] with N > 1 systems) through autograd: forward and VJP kernels take it as
+    ONE series (DYNAX_SHARED_U); g_u comes back in the caller's shape, summed over the systems inside the kernel
     (round-1 advisor finding: u[T,1,5] reached the kernel as a T*5 buffer)."""
     from dynax_b200 import ops
+    if impl == "cuda_core":
+        monkeypatch.setenv("DYNAX_NODE_VJP_IMPL", "0")
     N, Tn = 70, 19
-    Wnp = orc.synth_mlp(130, scale=0.5)
+    Wnp = orc.synth_mlp(130, hidden=hidden, scale=0.5)
     x0, u = inputs(N, Tn, 131)
     u1 = u[:, :1] if shape == "T1m" else u[:, 0]
     rng = np.random.default_rng(132)
