@@ -357,6 +357,48 @@ def _rel(a, ref, floor):
     return float((np.abs(a - ref) / np.maximum(np.abs(ref), floor * np.abs(ref).max() + 1e-300)).max())
 
 
+# In-run parity samples of the other legs: the oracle as the CHECKER of what was just timed, outside the timed regions.
+def parity_forward(torch, ops, view, dev):
+    import numpy as np
+    from oracle import dynax_oracle as orc
+    th_t, x0_t, u_t, _, _, n = view
+    xs, ys, _ = ops.rc_forward(th_t, x0_t, u_t, DT, time_chunks=0)
+    idx = np.sort(np.random.default_rng(4243).choice(n, min(32, n), replace=False))
+    sel = torch.as_tensor(idx, device=dev)
+    x64, y64 = orc.rc_rollout(th_t[sel].cpu().numpy(), x0_t[sel].cpu().numpy(), u_t[:, sel].cpu().numpy(), DT, np.float64)
+    ex, ey = _rel(xs[:, sel].cpu().numpy(), x64, 1e-3), _rel(ys[:, sel].cpu().numpy(), y64, 1e-3)
+    return {"systems": int(len(idx)), "oracle": "oracle/dynax_oracle.py::rc_rollout (fp64)", "x_max_rel_err": ex,
+            "y_max_rel_err": ey, "tolerance": 1e-5, "ok": bool(ex <= 1e-5 and ey <= 1e-5)}
+
+
+def parity_mpc(torch, ops, nom, xm, d, um, sch, dev):
+    import numpy as np
+    from oracle import dynax_oracle as orc
+    cost, amin, cmin = ops.rc_mpc_cost(nom, xm, d, um, *sch, 900.0)
+    idx = np.sort(np.random.default_rng(4244).choice(um.shape[1], 64, replace=False))
+    sel = torch.as_tensor(idx, device=dev)
+    ref = orc.mpc_cost(np.asarray(NOMINAL, np.float64), [20.0, 35.8, 26.0], d.cpu().numpy(), um[:, sel].cpu().numpy(), 900.0,
+                       dtype=np.float64)
+    ec = _rel(cost[sel].cpu().numpy(), ref, 1.0)
+    arg_ok = bool(amin.item() == int(torch.argmin(cost).item()) and cmin.item() == cost.min().item())
+    return {"candidates": 64, "oracle": "oracle/dynax_oracle.py::mpc_cost (fp64)", "cost_max_rel_err": ec, "tolerance": 1e-5,
+            "argmin_matches_costs": arg_ok, "ok": bool(ec <= 1e-5 and arg_ok)}
+
+
+def parity_node(torch, ops, W, xn, un, dev):
+    import numpy as np
+    from oracle import dynax_oracle as orc
+    xs, ys, _ = ops.node_rk4_forward(*W, xn, un, 0.25)
+    idx = np.sort(np.random.default_rng(4245).choice(xn.shape[0], 16, replace=False))
+    sel = torch.as_tensor(idx, device=dev)
+    x64, y64 = orc.node_rk4_rollout(*[w.double().cpu().numpy() for w in W], xn[sel].cpu().numpy(), un[:, sel].cpu().numpy(),
+                                    0.25, np.float64)
+    ex, ey = _rel(xs[:, sel].cpu().numpy(), x64, 1.0), _rel(ys[:, sel].cpu().numpy(), y64, 1.0)
+    return {"trajectories": 16, "oracle": "oracle/dynax_oracle.py::node_rk4_rollout (fp64; PARITY UNPINNED BY THE REFERENCE, "
+            "pinned to a torch-fp64 restatement)", "x_max_rel_err": ex, "y_max_rel_err": ey, "tolerance": 1e-5,
+            "ok": bool(ex <= 1e-5 and ey <= 1e-5)}
+
+
 def other_configs_leg(a, torch, dist, dev, rank, world, views, T):
     """BASELINE.json configs[1], [3] and [4] on the same box, same run (weak scaling: the per-rank size is the config's):
     forward rollout emitting x and y (reference semantics) over the headline run's resident inputs, the MPC candidate
@@ -401,17 +443,7 @@ def other_configs_leg(a, torch, dist, dev, rank, world, views, T):
         "launches_per_step": len(views), "alg_bytes_per_system_step": 36,
         "roofline_frac": S * T * 36 / (ms * 1e-3) / 1e9 / peak, "peak_gbs": peak, "peak_source": peak_src}
     if rank == 0 and not a.no_parity:   # 32 systems of the last tile launch against the fp64 oracle
-        from oracle import dynax_oracle as orc
-        th_t, x0_t, u_t, _, _, n = views[-1]
-        xs, ys, _ = ops.rc_forward(th_t, x0_t, u_t, DT, time_chunks=0)
-        idx = np.sort(np.random.default_rng(4243).choice(n, min(32, n), replace=False))
-        sel = torch.as_tensor(idx, device=dev)
-        x64, y64 = orc.rc_rollout(th_t[sel].cpu().numpy(), x0_t[sel].cpu().numpy(), u_t[:, sel].cpu().numpy(), DT, np.float64)
-        ex, ey = _rel(xs[:, sel].cpu().numpy(), x64, 1e-3), _rel(ys[:, sel].cpu().numpy(), y64, 1e-3)
-        out["config2_forward"]["parity"] = {"systems": int(len(idx)), "oracle": "oracle/dynax_oracle.py::rc_rollout (fp64)",
-                                            "x_max_rel_err": ex, "y_max_rel_err": ey, "tolerance": 1e-5,
-                                            "ok": bool(ex <= 1e-5 and ey <= 1e-5)}
-        del xs, ys
+        out["config2_forward"]["parity"] = parity_forward(torch, ops, views[-1], dev)
     # ---- configs[3]: 4M candidate control sequences x 96 steps through one shared model, cost + global argmin
     Nm, H = 1 << 22, 96
     g = torch.Generator(device=dev).manual_seed(3456 + rank)
@@ -434,17 +466,7 @@ def other_configs_leg(a, torch, dist, dev, rank, world, views, T):
         "roofline_frac": Nm * H * 4 / (ms * 1e-3) / 1e9 / peak,
         "collective": "all-gather of one (cost, index) pair per rank inside the timed region" if world > 1 else "none (1 rank)"}
     if rank == 0 and not a.no_parity:   # 64 candidates against the fp64 oracle; the argmin against the costs themselves
-        from oracle import dynax_oracle as orc
-        cost, amin, cmin = ops.rc_mpc_cost(nom, xm, d, um, *sch, 900.0)
-        idx = np.sort(np.random.default_rng(4244).choice(Nm, 64, replace=False))
-        ref = orc.mpc_cost(np.asarray(NOMINAL, np.float64), [20.0, 35.8, 26.0], d.cpu().numpy(),
-                           um[:, torch.as_tensor(idx, device=dev)].cpu().numpy(), 900.0, dtype=np.float64)
-        ec = _rel(cost[torch.as_tensor(idx, device=dev)].cpu().numpy(), ref, 1.0)
-        arg_ok = bool(amin.item() == int(torch.argmin(cost).item()) and cmin.item() == cost.min().item())
-        out["config4_mpc"]["parity"] = {"candidates": 64, "oracle": "oracle/dynax_oracle.py::mpc_cost (fp64)",
-                                        "cost_max_rel_err": ec, "tolerance": 1e-5, "argmin_matches_costs": arg_ok,
-                                        "ok": bool(ec <= 1e-5 and arg_ok)}
-        del cost
+        out["config4_mpc"]["parity"] = parity_mpc(torch, ops, nom, xm, d, um, sch, dev)
     del um
     # ---- configs[4]: MLP dynamics 8 -> 64 -> 64 -> 3 with RK4 on tcgen05, N = 262144 trajectories x T = 2048
     Nn, Tn = 262144, 2048
@@ -460,17 +482,7 @@ def other_configs_leg(a, torch, dist, dev, rank, world, views, T):
         "tensor_tflops_issued_tf32": 3 * Nn * Tn * 4 * 2 * (8 * 64 + 64 * 64) / (ms * 1e-3) / 1e12,
         "kernel": "node_tc_kernel<64> (tcgen05.mma kind::tf32, 3xTF32 split, accumulators in TMEM)"}
     if rank == 0 and not a.no_parity:   # 16 trajectories of the timed launch, all 2048 steps, against the fp64 oracle
-        from oracle import dynax_oracle as orc
-        xs, ys, _ = ops.node_rk4_forward(*W, xn, un, 0.25)
-        idx = np.sort(np.random.default_rng(4245).choice(Nn, 16, replace=False))
-        sel = torch.as_tensor(idx, device=dev)
-        x64, y64 = orc.node_rk4_rollout(*[w.double().cpu().numpy() for w in W], xn[sel].cpu().numpy(),
-                                        un[:, sel].cpu().numpy(), 0.25, np.float64)
-        ex, ey = _rel(xs[:, sel].cpu().numpy(), x64, 1.0), _rel(ys[:, sel].cpu().numpy(), y64, 1.0)
-        out["config5_node"]["parity"] = {"trajectories": 16, "oracle": "oracle/dynax_oracle.py::node_rk4_rollout (fp64; "
-                                         "PARITY UNPINNED BY THE REFERENCE, pinned to a torch-fp64 restatement)",
-                                         "x_max_rel_err": ex, "y_max_rel_err": ey, "tolerance": 1e-5,
-                                         "ok": bool(ex <= 1e-5 and ey <= 1e-5)}
+        out["config5_node"]["parity"] = parity_node(torch, ops, W, xn, un, dev)
     return out
 
 
