@@ -42,7 +42,8 @@ def test_matches_oracle(T, monkeypatch, N, Tn, euler, impl):
 
 @pytest.mark.parametrize("hidden", [32, 64, 128])
 @pytest.mark.parametrize("N,Tn,euler,scale,shared", [(300, 40, False, 0.1, False), (131, 19, True, 1.0, False),
-                                                      (517, 24, False, 1.0, True), (5, 9, False, 3.0, False)])
+                                                      (517, 24, False, 1.0, True), (5, 9, False, 3.0, False),
+                                                      (260, 700, False, 0.1, False)])   # (long horizon: barrier phases)
 def test_hidden_widths_match_oracle(T, hidden, N, Tn, euler, scale, shared):
     """The tcgen05 kernel is instantiated for hidden widths 32, 64 and 128 (TMEM 128 / 256 / 512 columns); per-system
     and shared input series; O(1)..O(3) weights drive tanh into saturation (the quad reciprocal's clamp)."""
