@@ -76,6 +76,7 @@ template <int TN, int KF, int S, int SPLIT = 1, bool SHARED_U = false, bool SHAR
           bool GX0 = false, bool SHIFT = false>
 struct FwdSensCfg {
     static_assert(!SHIFT || (SPLIT == 1 && !SHARED_U && !SHARED_TGT && !CTRL), "shifted rows: the per-system layout only");
+    static_assert(!SHIFT || KF <= 32, "copy_rows_shift_bulk: one lane per row of a stage");
     static constexpr int NACC = GX0 ? 11 : 8;  // fp64 totals per system: 7 gradient entries (+3 for x0) + squared residual
     // a shared series occupies KF rows of 5 (or 1) floats per stage instead of KF x TN of them
     static constexpr int U_ROW = SHARED_U ? 5 : TN * 5 + (SHIFT ? 4 : 0), T_ROW = SHARED_TGT ? 1 : TN + (SHIFT ? 4 : 0);

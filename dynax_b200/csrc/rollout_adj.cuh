@@ -65,12 +65,14 @@ struct AdjParams {
     alignas(64) CUtensorMap map_u, map_c, map_a1, map_a2;
 };
 
-// SHIFT: the instantiation for rows TMA cannot move (N % 4 != 0; every streamed array per-system): rows are staged with
-// 16-byte cp.async at their global offset modulo 16 bytes (ptx::copy_rows_async16), the row pitches grow by 4 floats, and
-// the computing threads add the (warp-uniform) shift of each row to their shared address.
+// SHIFT: the instantiation for rows TMA cannot move (N % 4 != 0; every streamed array per-system): rows are staged at
+// their global offset modulo 16 bytes, so that the interior of a row moves as one bulk copy (ptx::copy_rows_shift_bulk),
+// the row pitches grow by 4 floats, and the computing threads add the (warp-uniform) shift of each row to their shared
+// address.
 template <class Model, int TN, int KC, int S, int MODE, bool SHARED_U, bool SHARED_TGT, bool SHIFT = false>
 struct AdjCfg {
     static_assert(!SHIFT || (!SHARED_U && !SHARED_TGT), "shifted rows: per-system arrays only");
+    static_assert(!SHIFT || KC <= 32, "copy_rows_shift_bulk: one lane per row of a stage");
     static constexpr int n = Model::n, m = Model::m, p = Model::p;
     static constexpr int PAD = SHIFT ? 4 : 0;
     static constexpr int U_ROW = SHARED_U ? m : TN * m + PAD;
@@ -253,7 +255,7 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_adj_kernel(const __grid
     const float dt = P.dt;
     const bool discrete = P.discrete != 0;
     float *ck = P.ckpt + cidx * P.ckpt_chunk_stride + (n0 + tid);  // ckpt[(seg*n + d)*N + system]; only touched when active
-    // SHIFT: row k of this CTA's time slice sits in its slot at its global offset modulo 16 bytes (ptx::copy_rows_async16)
+    // SHIFT: row k of this CTA's time slice sits in its slot at its global offset modulo 16 bytes (ptx::copy_rows_shift_bulk)
     constexpr int W1 = MODE == ADJ_MSE ? 1 : p;
     const float *const a1_base = MODE == ADJ_MSE ? tgt_base : gy_base;
     const unsigned su0 = SHIFT ? (unsigned)((reinterpret_cast<uintptr_t>(u_base) >> 2) + (uint64_t)(n0 * m)) : 0u;

@@ -54,12 +54,13 @@ struct FwdParams {
 __host__ __device__ constexpr int align4i(int x) { return (x + 3) & ~3; }
 __host__ __device__ constexpr int align32i(int x) { return (x + 31) & ~31; }   // 128 bytes: tensor-copy destinations
 
-// SHIFT: the instantiation for per-system rows TMA cannot move (N % 4 != 0): rows are staged with 16-byte cp.async at
-// their global offset modulo 16 bytes (ptx::copy_rows_async16), the row pitch grows by 4 floats, and the computing
-// threads add the (warp-uniform) shift of each row to their shared address.
+// SHIFT: the instantiation for per-system rows TMA cannot move (N % 4 != 0): rows are staged at their global offset modulo
+// 16 bytes, so that the interior of a row moves as one bulk copy (ptx::copy_rows_shift_bulk), the row pitch grows by 4
+// floats, and the computing threads add the (warp-uniform) shift of each row to their shared address.
 template <class Model, int TN, int KF, int S, bool SHARED_U, bool SHIFT = false>
 struct FwdCfg {
     static_assert(!SHIFT || !SHARED_U, "shifted rows are per-system rows");
+    static_assert(!SHIFT || KF <= 32, "copy_rows_shift_bulk: one lane per row of a stage");
     static constexpr int n = Model::n, m = Model::m, p = Model::p;
     static constexpr int IN_ROW = SHARED_U ? m : TN * m + (SHIFT ? 4 : 0);   // row pitch in the stage
     static constexpr int CTRL_OFF = align32i(KF * IN_ROW);              // per-system channel rows [KF][TN]
@@ -260,7 +261,7 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_fwd_kernel(const __grid
         ptx::mbar_wait(&full[s], (uint32_t)((c / S) & 1));
         if (emit) ptx::mbar_wait(&ofree[o], (uint32_t)(((c >> 1) & 1) ^ 1));
         const float *in = s_in + s * IN_STAGE + (SHARED_U ? 0 : tid * m);
-        // SHIFT: row j of this stage sits at its global offset modulo 16 bytes (see ptx::copy_rows_async16)
+        // SHIFT: row j of this stage sits at its global offset modulo 16 bytes (see ptx::copy_rows_shift_bulk)
         const unsigned sh0 = SHIFT ? (unsigned)((reinterpret_cast<uintptr_t>(u_base) >> 2) + (uint64_t)((k0 * N + n0) * m)) : 0u;
         const unsigned shd = SHIFT ? (unsigned)(N * m) : 0u;
         float *xo = s_xo + o * XO_STAGE + tid * n;
