@@ -136,12 +136,14 @@ def test_inverse_step_like_example3(T):
     assert_grad_parity(gotN, g64, gbud)
 
 
-def test_neural_ode_through_simulator(T):
+@pytest.mark.parametrize("hidden", [64, 32])
+def test_neural_ode_through_simulator(T, hidden):
     """General fx/fy path (base_block_state_space.py:62-63,72-73) through the same simulator facade,
-    Euler (the reference's integrator) and RK4 (extension); gradients flow to the Dense kernels."""
+    Euler (the reference's integrator) and RK4 (extension); gradients flow to the Dense kernels.  Hidden widths 64
+    (tcgen05 gradient kernel) and 32 (CUDA-core gradient kernel)."""
     from dynax_b200.models import NeuralODE
     from dynax_b200.simulators import DifferentiableSimulator
-    model = NeuralODE()
+    model = NeuralODE(hidden=hidden)
     N, Tn = 96, 30
     rng = np.random.default_rng(171)
     x0 = T.tensor(rng.normal(size=(N, 3)), dtype=T.float32).cuda()
@@ -150,7 +152,7 @@ def test_neural_ode_through_simulator(T):
         sim = DifferentiableSimulator(model, dt=0.1, solver=solver)
         variables = sim.init(3, x0, u)
         fx = variables["params"]["model"]["_fx"]
-        assert fx["dense_0"]["kernel"].shape == (8, 64) and fx["dense_2"]["kernel"].shape == (64, 3)
+        assert fx["dense_0"]["kernel"].shape == (8, hidden) and fx["dense_2"]["kernel"].shape == (hidden, 3)
         for layer in fx.values():
             layer["kernel"].requires_grad_(True); layer["bias"].requires_grad_(True)
         xsol, ysol = sim.apply(variables, x0, u)
