@@ -21,6 +21,7 @@
 #include "api_common.cuh"
 #include "mlp_model.cuh"
 #include "node_vjp_tc.cuh"
+#include "node_vjp_wide.cuh"
 
 namespace dynax {
 
@@ -44,7 +45,8 @@ struct L {
     static constexpr int W1PT = HID / 16;              // dW1: HID*8 entries, W1PT consecutive ones of a row each
     static constexpr int W3PT = HID / 32;              // dW3: 3 x 32 threads, W3PT columns (32 apart) each
 };
-constexpr int A_END_MAX = L<64>::A_END;
+constexpr int A_END_MAX = nvw::A_END;  // the widest instantiated hidden layer (128: node_vjp_wide.cuh)
+static_assert(nvw::A_END >= L<64>::A_END, "workspace covers every hidden width");
 }  // namespace nv
 
 template <int HID>
@@ -370,8 +372,8 @@ int dynax_node_rk4_vjp_stages_f32(const float *W1, const float *b1, const float 
     if (!xsol && T > 1) return fail(DYNAX_ERR_INVALID_ARGUMENT, "xsol (the forward trajectory) must be given");
     if (!g_xsol && !g_ysol) return fail(DYNAX_ERR_INVALID_ARGUMENT, "need g_xsol or g_ysol");
     if (flags & ~(DYNAX_SOLVER_EULER | DYNAX_SHARED_U)) return fail(DYNAX_ERR_INVALID_ARGUMENT, "unsupported flags 0x%x for node_rk4_vjp", flags);
-    if (!(n == 3 && m == 5 && p == 1 && (hidden == 32 || hidden == 64)))
-        return fail(DYNAX_ERR_UNSUPPORTED_DIMS, "MLP gradient kernels are instantiated for (n,m,p)=(3,5,1), hidden in {32,64}; got (%d,%d,%d,%d)", n, m, p, hidden);
+    if (!(n == 3 && m == 5 && p == 1 && (hidden == 32 || hidden == 64 || hidden == 128)))
+        return fail(DYNAX_ERR_UNSUPPORTED_DIMS, "MLP gradient kernels are instantiated for (n,m,p)=(3,5,1), hidden in {32,64,128}; got (%d,%d,%d,%d)", n, m, p, hidden);
     const size_t need = dynax_node_rk4_vjp_workspace();
     if (!ws || ws_bytes < need || !aligned16(ws)) return fail(DYNAX_ERR_WORKSPACE, "workspace must hold %zu bytes (16-byte aligned)", need);
     int rc = require_sm100();
@@ -382,9 +384,20 @@ int dynax_node_rk4_vjp_stages_f32(const float *W1, const float *b1, const float 
     const int shared_u = (flags & DYNAX_SHARED_U) ? 1 : 0;
     if (shared_u && g_u) DYNAX_CUDA_TRY(cudaMemsetAsync(g_u, 0, sizeof(float) * 5 * (size_t)T, st));  // summed with atomics
     static_assert(vtc::A_END == nv::L<64>::A_END, "both kernels share the accumulator layout");
-    // hidden = 64: tcgen05 kernel (node_vjp_tc.cuh); DYNAX_NODE_VJP_IMPL=0 and hidden = 32: CUDA-core kernel
+    // hidden = 64: tcgen05 kernel (node_vjp_tc.cuh); DYNAX_NODE_VJP_IMPL=0 and hidden = 32: CUDA-core kernel;
+    // hidden = 128: the wide CUDA-core kernel (node_vjp_wide.cuh)
     const char *impl = getenv("DYNAX_NODE_VJP_IMPL");
-    if (hidden == 32) {
+    if (hidden == 128) {
+        NodeVjpWideParams Q;
+        Q.mp.W1 = W1; Q.mp.b1 = b1; Q.mp.W2 = W2; Q.mp.b2 = b2; Q.mp.W3 = W3; Q.mp.b3 = b3; Q.mp.rk4 = rk4;
+        Q.x0 = x0; Q.u = u; Q.xsol = xsol; Q.stage_x = stage_x; Q.g_xsol = g_xsol; Q.g_ysol = g_ysol; Q.g_x0 = g_x0; Q.g_u = g_u;
+        Q.acc = acc; Q.N = N; Q.T = T; Q.dt = dt; Q.shared_u = shared_u;
+        rc = set_smem(node_vjp_wide_kernel, nvw::SMEM_BYTES);
+        if (rc != DYNAX_OK) return rc;
+        node_vjp_wide_kernel<<<(unsigned)((N + nvw::TR - 1) / nvw::TR), nvw::NTHR, nvw::SMEM_BYTES, st>>>(Q);
+        DYNAX_CUDA_TRY(cudaGetLastError());
+        rc = DYNAX_OK;
+    } else if (hidden == 32) {
         rc = launch_node_vjp_cc<32>(W1, b1, W2, b2, W3, b3, x0, u, xsol, stage_x, g_xsol, g_ysol, g_x0, g_u, acc, N, T, dt, rk4, shared_u, st);
     } else if (impl && impl[0] == '0') {
         rc = launch_node_vjp_cc<64>(W1, b1, W2, b2, W3, b3, x0, u, xsol, stage_x, g_xsol, g_ysol, g_x0, g_u, acc, N, T, dt, rk4, shared_u, st);

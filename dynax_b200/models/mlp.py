@@ -5,8 +5,7 @@
 dispatched through ``BaseBlockSSM._call_state`` / ``_call_observation``'s general branch
 (dynax/core/base_block_state_space.py:62-63,72-73).  Parameters follow Flax ``nn.Dense`` naming and
 layout (``params/_fx/dense_{0,1,2}/{kernel[in,out],bias}``); the CUDA kernels take the transposed
-(row-major [out,in]) matrices.  Instantiated for (state, input, output) = (3, 5, 1) and hidden widths 32, 64, 128
-(gradient kernels: 32 and 64).
+(row-major [out,in]) matrices.  Instantiated for (state, input, output) = (3, 5, 1) and hidden widths 32, 64, 128.
 """
 from __future__ import annotations
 

@@ -409,7 +409,7 @@ def node_rk4_forward(W1, b1, W2, b2, W3, b3, x0, u, dt, emit_x=True, emit_y=True
     Weights are row-major [out,in] matrices shared by all systems; x0[N,3], u[T,N,5]|[T,5].
     ``emit_stages``: also return stage_x[T,N,9], the RK4 stage points of every step, which ``node_rk4_vjp`` can
     reuse instead of recomputing them (tcgen05 kernel, RK4 only; None otherwise).
-    Hidden widths 32, 64 and 128 (gradient: 32 and 64).
+    Hidden widths 32, 64 and 128.
     """
     ws = [_f32c(t, nm) for t, nm in ((W1, "W1"), (b1, "b1"), (W2, "W2"), (b2, "b2"), (W3, "W3"), (b3, "b3"))]
     x0, u = _f32c(x0, "x0"), _f32c(u, "u")

@@ -213,7 +213,7 @@ int dynax_lti_vjp_chunked_f32(const float *A, const float *B, const float *C, co
  *      stepped with classical RK4 (u held constant over a step) or Euler (DYNAX_SOLVER_EULER).
  *      Weights are row-major [out,in] matrices shared by all systems: W1:[hidden,n+m] b1:[hidden]
  *      W2:[hidden,hidden] b2:[hidden] W3:[n,hidden] b3:[n].  Instantiated for (n,m,p)=(3,5,1) and hidden = 32, 64
- *      or 128 (forward; the gradient kernels: hidden = 32 or 64); anything else: DYNAX_ERR_UNSUPPORTED_DIMS.
+ *      or 128 (forward and gradient); anything else: DYNAX_ERR_UNSUPPORTED_DIMS.
  *      u: [T,N,5], or ONE series [T,5] for all trajectories with DYNAX_SHARED_U.
  *      Output convention as dynax_rc_forward_f32.  PARITY UNPINNED BY THE REFERENCE. ---- */
 int dynax_node_rk4_forward_f32(const float *W1, const float *b1, const float *W2, const float *b2,
@@ -234,7 +234,8 @@ int dynax_node_rk4_forward_stages_f32(const float *W1, const float *b1, const fl
 /* Reverse-mode gradient of dynax_node_rk4_forward_f32 (exact discrete adjoint of RK4 / Euler): cotangents
  * g_xsol:[T,N,3] and/or g_ysol:[T,N,1] in; weight gradients (summed over systems, each may be NULL),
  * g_x0:[N,3], g_u:[T,N,5] out.  xsol is the forward trajectory (x_{k+1} at row k).  hidden = 64: tcgen05 kernel
- * (node_vjp_tc.cuh), CUDA-core kernel with DYNAX_NODE_VJP_IMPL=0; hidden = 32: CUDA-core kernel.  With DYNAX_SHARED_U
+ * (node_vjp_tc.cuh), CUDA-core kernel with DYNAX_NODE_VJP_IMPL=0; hidden = 32: CUDA-core kernel; hidden = 128: the wide
+ * CUDA-core kernel (node_vjp_wide.cuh: 32-trajectory CTAs, four threads per trajectory).  With DYNAX_SHARED_U
  * u is ONE series [T,5] and g_u:[T,5] its gradient summed over the trajectories (fp32 atomics: one per warp, step and
  * channel, so the last bits depend on the order).
  * ws: dynax_node_rk4_vjp_workspace() bytes.  PARITY UNPINNED BY THE REFERENCE. */

@@ -136,11 +136,11 @@ def test_inverse_step_like_example3(T):
     assert_grad_parity(gotN, g64, gbud)
 
 
-@pytest.mark.parametrize("hidden", [64, 32])
+@pytest.mark.parametrize("hidden", [64, 32, 128])
 def test_neural_ode_through_simulator(T, hidden):
     """General fx/fy path (base_block_state_space.py:62-63,72-73) through the same simulator facade,
     Euler (the reference's integrator) and RK4 (extension); gradients flow to the Dense kernels.  Hidden widths 64
-    (tcgen05 gradient kernel) and 32 (CUDA-core gradient kernel)."""
+    (tcgen05 gradient kernel), 32 and 128 (CUDA-core gradient kernels)."""
     from dynax_b200.models import NeuralODE
     from dynax_b200.simulators import DifferentiableSimulator
     model = NeuralODE(hidden=hidden)

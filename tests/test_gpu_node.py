@@ -102,10 +102,9 @@ def test_unsupported_dims(T):
     with pytest.raises(DynaxError) as e:
         ops.node_rk4_forward(*(cu(T, w) for w in W), cu(T, x0), cu(T, u), 0.1)
     assert e.value.code == -2
-    W = [cu(T, w) for w in orc.synth_mlp(105, hidden=128)]     # gradient kernels: hidden 32 and 64
-    xs, _, _ = ops.node_rk4_forward(*W, cu(T, x0), cu(T, u), 0.1)
-    with pytest.raises(DynaxError) as e:
-        ops.node_rk4_vjp(*W, cu(T, x0), cu(T, u), xs, 0.1, T.ones_like(xs), None)
+    xs = T.zeros((4, 8, 3), device="cuda")
+    with pytest.raises(DynaxError) as e:                       # the gradient kernels: same widths
+        ops.node_rk4_vjp(*(cu(T, w) for w in W), cu(T, x0), cu(T, u), xs, 0.1, T.ones_like(xs), None)
     assert e.value.code == -2
 
 
@@ -125,11 +124,12 @@ def _torch_node_rollout(T, W, x0, u, dt, euler):
     return T.stack(xs), T.stack(ys)
 
 
-@pytest.mark.parametrize("impl,hidden", [("tc", 64), ("cuda_core", 64), ("cuda_core", 32)])
+@pytest.mark.parametrize("impl,hidden", [("tc", 64), ("cuda_core", 64), ("cuda_core", 32), ("wide", 128)])
 @pytest.mark.parametrize("N,Tn,euler,scale", [(200, 24, False, 0.5), (130, 17, True, 1.0), (3, 5, False, 0.3), (256, 40, False, 0.1)])
 def test_vjp_matches_torch_autograd_fp64(T, monkeypatch, N, Tn, euler, scale, impl, hidden):
     """Oracle = torch autograd (fp64, CPU) over the restated RK4-MLP rollout (the reference has neither).
-    Both VJP kernels: tcgen05 (default for hidden = 64) and CUDA cores (DYNAX_NODE_VJP_IMPL=0; hidden = 32 always)."""
+    The VJP kernels: tcgen05 (default for hidden = 64), CUDA cores (DYNAX_NODE_VJP_IMPL=0; hidden = 32 always), and the
+    wide CUDA-core kernel (hidden = 128: 32-trajectory CTAs, four threads per trajectory)."""
     from dynax_b200 import ops
     if impl == "cuda_core":
         monkeypatch.setenv("DYNAX_NODE_VJP_IMPL", "0")
@@ -149,15 +149,15 @@ def test_vjp_matches_torch_autograd_fp64(T, monkeypatch, N, Tn, euler, scale, im
         assert rel_err(got.grad.cpu().numpy(), ref.grad.numpy(), floor=1.0) < 1e-4, nm
 
 
-@pytest.mark.parametrize("impl", ["tc", "cuda_core"])
-def test_vjp_with_saved_stage_points(T, monkeypatch, impl):
+@pytest.mark.parametrize("impl,hidden", [("tc", 64), ("cuda_core", 64), ("cuda_core", 32), ("wide", 128)])
+def test_vjp_with_saved_stage_points(T, monkeypatch, impl, hidden):
     """The forward kernel can save the RK4 stage points (stage_x[T,N,9]); the VJP kernels then skip the three
     forward evaluations per step that recompute them.  Same gradient within rounding (the recomputation sums the
     64 -> 3 output layer in a different order)."""
     from dynax_b200 import ops
     if impl == "cuda_core":
         monkeypatch.setenv("DYNAX_NODE_VJP_IMPL", "0")
-    Wnp = orc.synth_mlp(120, scale=0.5)
+    Wnp = orc.synth_mlp(120, hidden=hidden, scale=0.5)
     x0, u = inputs(300, 33, 121)
     W = [cu(T, w) for w in Wnp]
     xs, ys, _, st = ops.node_rk4_forward(*W, cu(T, x0), cu(T, u), 0.25, emit_stages=True)
@@ -176,7 +176,7 @@ def test_vjp_with_saved_stage_points(T, monkeypatch, impl):
     assert st1 is not None and T.equal(st1, st2)
 
 
-@pytest.mark.parametrize("impl,hidden", [("tc", 64), ("cuda_core", 64), ("cuda_core", 32)])
+@pytest.mark.parametrize("impl,hidden", [("tc", 64), ("cuda_core", 64), ("cuda_core", 32), ("wide", 128)])
 @pytest.mark.parametrize("shape", ["T1m", "Tm"])
 def test_vjp_shared_input_series(T, monkeypatch, shape, impl, hidden):
     """A shared input series (u[T,1,5] or u[T,5] with N > 1 systems) through autograd: forward and VJP kernels take it as
