@@ -1,4 +1,4 @@
-// Issue-rate probe for the sm_100a pipes the compute-bound kernels lean on (MUFU ex2/rcp, packed FP32, FMNMX/LOP3):
+// Issue-rate probe for the sm_100a pipes the compute-bound kernels lean on (MUFU ex2, packed FP32, FMNMX):
 // cycles per warp-instruction and SM sub-partition, for 1 / 2 / 4 warps per sub-partition, 8 independent chains per thread.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/pipe_probe tools/pipe_probe.cu && tools/pipe_probe
 #include <cstdio>
@@ -17,7 +17,6 @@ __global__ void probe(float *out, long long *cyc, int iters) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             if (OP == 0) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(v[i]));
-            if (OP == 1) asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(v[i]));
             if (OP == 2) p[i] = __ffma2_rn(p[i], c1, c2);                       // three distinct register operands
             if (OP == 3) p[i] = __ffma2_rn(p[i], make_float2(1.0001f, 1.0001f), c2);  // one immediate
             if (OP == 4) p[i] = __fadd2_rn(p[i], make_float2(0.5f, 0.5f));
@@ -56,7 +55,6 @@ int main() {
     cudaMalloc(&out, sizeof(float) * (1 + 148 * 1024)); cudaMemset(out, 0, sizeof(float) * (1 + 148 * 1024));
     cudaMalloc(&cyc, sizeof(long long));
     run<0>("MUFU.EX2", 8, out, cyc);
-    run<1>("MUFU.RCP", 8, out, cyc);
     run<2>("FFMA2 (3 register operands)", 8, out, cyc);
     run<3>("FFMA2 (immediate multiplier)", 8, out, cyc);
     run<4>("FADD2 (immediate)", 8, out, cyc);
