@@ -212,6 +212,42 @@ def test_node_shapes(monkeypatch, N, Tn, euler):
             assert rel_err(a.cpu().numpy(), b.cpu().numpy(), floor=1.0) < 3e-5, (nm, N, Tn, euler)
 
 
+@pytest.mark.parametrize("hidden", [32, 128])
+@pytest.mark.parametrize("N,Tn,euler", [(1, 1, False), (5, 9, False), (31, 3, True), (33, 7, False), (129, 4, False),
+                                        (65, 18, True), (2, 33, False)])
+def test_node_shapes_other_hidden_widths(N, Tn, euler, hidden):
+    """The same ragged shapes at hidden widths 32 and 128 (one forward and one gradient kernel each): forward against the
+    fp64 oracle, gradient with saved against recomputed stage points, shared input series against the materialised one."""
+    import torch as T
+    from dynax_b200 import ops
+    seed = 6000 + 7 * N + Tn + hidden
+    W = orc.synth_mlp(seed, hidden=hidden, scale=0.5)
+    rng = np.random.default_rng(seed)
+    x0 = rng.normal(size=(N, 3)).astype(np.float32)
+    u = rng.normal(size=(Tn, N, 5)).astype(np.float32)
+    Wc = [cu(T, w) for w in W]
+    xr, yr = orc.node_rk4_rollout(*W, x0, u, 0.25, np.float64, euler=euler)
+    xs, ys, _, st = ops.node_rk4_forward(*Wc, cu(T, x0), cu(T, u), 0.25, euler=euler, emit_stages=True)
+    assert rel_err(xs.cpu().numpy(), xr, floor=1.0) < 1e-5 and rel_err(ys.cpu().numpy(), yr, floor=1.0) < 1e-5
+    assert (st is None) == euler
+    gx = cu(T, rng.normal(size=(Tn, N, 3))); gy = cu(T, rng.normal(size=(Tn, N, 1)))
+    g0 = ops.node_rk4_vjp(*Wc, cu(T, x0), cu(T, u), xs, 0.25, gx, gy, euler=euler)
+    if st is not None:
+        g1 = ops.node_rk4_vjp(*Wc, cu(T, x0), cu(T, u), xs, 0.25, gx, gy, euler=euler, stage_x=st)
+        for a, b, nm in zip(g1, g0, ["W1", "b1", "W2", "b2", "W3", "b3", "x0", "u"]):
+            assert rel_err(a.cpu().numpy(), b.cpu().numpy(), floor=1.0) < 3e-5, (nm, N, Tn, hidden)
+    # ONE series for all trajectories == the same series materialised per trajectory (g_u summed over trajectories)
+    us = np.repeat(u[:, :1], N, 1)
+    xs2, _, _ = ops.node_rk4_forward(*Wc, cu(T, x0), cu(T, us), 0.25, euler=euler)
+    xs1, _, _ = ops.node_rk4_forward(*Wc, cu(T, x0), cu(T, u[:, 0]), 0.25, euler=euler)
+    assert T.equal(xs1, xs2)
+    ga = ops.node_rk4_vjp(*Wc, cu(T, x0), cu(T, u[:, 0]), xs1, 0.25, gx, gy, euler=euler)
+    gb = ops.node_rk4_vjp(*Wc, cu(T, x0), cu(T, us), xs2, 0.25, gx, gy, euler=euler)
+    for a, b, nm in zip(ga[:7], gb[:7], ["W1", "b1", "W2", "b2", "W3", "b3", "x0"]):
+        assert rel_err(a.cpu().numpy(), b.cpu().numpy(), floor=1.0) < 3e-5, (nm, N, Tn, hidden)
+    assert rel_err(ga[7].cpu().numpy(), gb[7].sum(dim=1, keepdim=True).cpu().numpy(), floor=1.0) < 3e-5
+
+
 @pytest.mark.parametrize("N,H", [(1, 1), (3, 7), (31, 8), (257, 9), (1000, 96), (4099, 17)])
 def test_mpc_shapes(N, H):
     import torch as T
