@@ -4,16 +4,16 @@
 // [feature][row] tiles of a 128-trajectory CTA alone would be 270 KB, and a thread cannot hold 128 hidden activations
 // plus a 128-entry patch of dW2, so the work is laid out differently:
 //
-//   * a CTA owns 32 trajectories; 4 warps, warp q = hidden units [32 q, 32 q + 32), lane = trajectory.  The four threads
-//     of a trajectory carry the same x / lambda / stage points (cheap) and split every layer four ways; whatever a layer
+//   * a CTA owns 32 trajectories; 8 warps, warp q = hidden units [16 q, 16 q + 16), lane = trajectory.  The eight threads
+//     of a trajectory carry the same x / lambda / stage points (cheap) and split every layer eight ways; whatever a layer
 //     needs from the whole hidden vector it reads from the shared tiles H1 / D2 ([feature][row], 36-float rows);
-//   * the weight gradients are contracted over the tile's 32 rows by all 128 threads (dW2: an 8 x 16 patch per thread in
-//     two passes of 8 x 8 registers) and accumulated in fp32 SHARED-memory accumulators (every entry has one owner:
-//     no atomics), flushed to the fp64 global accumulators every 16 steps (as node_vjp.cu);
+//   * the weight gradients are contracted over the tile's 32 rows by all 256 threads (dW2: an 8 x 8 patch per thread)
+//     and accumulated in fp32 SHARED-memory accumulators (every entry has one owner: no atomics), flushed to the fp64
+//     global accumulators every 16 steps (as node_vjp.cu);
 //   * weights are read from shared memory as warp-uniform float4 broadcasts (W2 rows for both directions: the backward
-//     pass of layer 2 walks W2[j][32 q .. 32 q + 31] for every j, so no transposed copy is needed).
+//     pass of layer 2 walks W2[j][16 q .. 16 q + 15] for every j, so no transposed copy is needed).
 //
-// Shared memory: weights 72 KB + tiles 74 KB + accumulators 71 KB + exchange 7 KB = 221 KB, one CTA per SM.
+// Shared memory: weights 72 KB + tiles 74 KB + accumulators 72 KB + exchange 10 KB = 224 KB, one CTA per SM.
 // tanhf is the accurate one (as the other CUDA-core kernels).  PARITY UNPINNED BY THE REFERENCE; the test oracle is torch
 // autograd (fp64) over the restated rollout.
 #pragma once
@@ -23,14 +23,14 @@
 namespace dynax {
 
 namespace nvw {
-constexpr int HID = 128, TR = 32, NTHR = 128, HQ = HID / 4;  // rows per CTA, threads, hidden units per warp
+constexpr int HID = 128, TR = 32, NW = 8, NTHR = 32 * NW, HQ = HID / NW;  // rows per CTA, warps, threads, hidden units per warp
 constexpr int NX = 3, NU = 5, NIN = 8, LDT = TR + 4;          // tile rows: 32 trajectories + 4 floats (float4-aligned)
-constexpr int SW2 = HID + 1;                                  // row pitch of the dW2 accumulator (bank spread, see flush)
+constexpr int SW2 = HID + 2;                                  // row pitch of the dW2 accumulator (bank spread of the patch owners)
 using M = MlpModel<3, 5, 1, HID>;
 constexpr int O_W = 0;
 constexpr int O_H1 = (M::SMEM_FLOATS + 3) & ~3, O_H2 = O_H1 + HID * LDT, O_D2 = O_H2 + HID * LDT, O_D1 = O_D2 + HID * LDT,
-              O_Z = O_D1 + HID * LDT, O_D3 = O_Z + NIN * LDT, O_ZB = O_D3 + 4 * LDT, O_PR = O_ZB + 4 * NIN * TR,
-              O_AW2 = O_PR + 4 * 4 * TR, O_AW1 = O_AW2 + HID * SW2, O_AW3 = O_AW1 + HID * NIN, O_AB1 = O_AW3 + NX * HID,
+              O_Z = O_D1 + HID * LDT, O_D3 = O_Z + NIN * LDT, O_ZB = O_D3 + 4 * LDT, O_PR = O_ZB,  // (PR: forward evaluations only)
+              O_AW2 = O_ZB + NW * NIN * TR, O_AW1 = O_AW2 + HID * SW2, O_AW3 = O_AW1 + HID * NIN, O_AB1 = O_AW3 + NX * HID,
               O_AB2 = O_AB1 + HID, O_AB3 = O_AB2 + HID, O_END = O_AB3 + 4;
 constexpr size_t SMEM_BYTES = sizeof(float) * O_END;
 static_assert(SMEM_BYTES <= 227 * 1024, "one CTA per SM");
@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(nvw::NTHR, 1) node_vjp_wide_kernel(const NodeV
     float *H1 = sm + O_H1, *H2 = sm + O_H2, *D2 = sm + O_D2, *D1 = sm + O_D1, *Z = sm + O_Z, *D3 = sm + O_D3;
     float *ZB = sm + O_ZB, *PR = sm + O_PR;
     float *aW2 = sm + O_AW2, *aW1 = sm + O_AW1, *aW3 = sm + O_AW3, *aB1 = sm + O_AB1, *aB2 = sm + O_AB2, *aB3 = sm + O_AB3;
-    const int tid = threadIdx.x, q = tid >> 5, r = tid & 31;   // warp = quarter of the hidden units, lane = trajectory
+    const int tid = threadIdx.x, q = tid >> 5, r = tid & 31;   // warp = its share of the hidden units, lane = trajectory
     const int h0 = q * HQ;
     const int64_t N = P.N, T = P.T;
     const int64_t i = (int64_t)blockIdx.x * TR + r;
@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(nvw::NTHR, 1) node_vjp_wide_kernel(const NodeV
         }
     };
 
-    // forward evaluation only (stage points): rhs = MLP(z).  All four threads of a trajectory return the same value.
+    // forward evaluation only (stage points): rhs = MLP(z).  All threads of a trajectory return the same value.
     auto mlp_forward = [&](const float *z, float *rhs) {
         float h1[HQ], pre[HQ];
         layer1(z, h1);
@@ -118,12 +118,16 @@ __global__ void __launch_bounds__(nvw::NTHR, 1) node_vjp_wide_kernel(const NodeV
         for (int d = 0; d < NX; ++d) PR[(q * 4 + d) * TR + r] = pr[d];
         __syncthreads();
 #pragma unroll
-        for (int d = 0; d < NX; ++d)
-            rhs[d] = w[M::O_B3 + d] + ((PR[(0 * 4 + d) * TR + r] + PR[(1 * 4 + d) * TR + r]) + (PR[(2 * 4 + d) * TR + r] + PR[(3 * 4 + d) * TR + r]));
+        for (int d = 0; d < NX; ++d) {
+            float s = 0.f;
+#pragma unroll
+            for (int qq = 0; qq < NW; ++qq) s += PR[(qq * 4 + d) * TR + r];   // same order in every thread of the trajectory
+            rhs[d] = w[M::O_B3 + d] + s;
+        }
         __syncthreads();  // PR and H1 are rewritten by the next evaluation
     };
 
-    // backward pass of the MLP at stage point z with output cotangent d3 -> zbar (all four threads of a trajectory);
+    // backward pass of the MLP at stage point z with output cotangent d3 -> zbar (all threads of a trajectory);
     // adds this stage's contribution to the shared weight-gradient accumulators (collective over the CTA)
     auto mlp_backward = [&](const float *z, const float *d3, float *zbar) {
         float h1[HQ], pre[HQ];
@@ -147,7 +151,7 @@ __global__ void __launch_bounds__(nvw::NTHR, 1) node_vjp_wide_kernel(const NodeV
             D2[j * LDT + r] = g * (1.f - h2 * h2);
         }
         __syncthreads();
-        // delta1 for this warp's hidden units: (W2^T delta2)_i (1 - h1_i^2), walking W2[j][h0 .. h0 + 31] for every j
+        // delta1 for this warp's hidden units: (W2^T delta2)_i (1 - h1_i^2), walking W2[j][h0 .. h0 + HQ - 1] for every j
         float *acc1 = pre;  // (pre is dead)
 #pragma unroll
         for (int ii = 0; ii < HQ; ++ii) acc1[ii] = 0.f;
@@ -178,40 +182,41 @@ __global__ void __launch_bounds__(nvw::NTHR, 1) node_vjp_wide_kernel(const NodeV
         for (int c = 0; c < NIN; ++c) ZB[(q * NIN + c) * TR + r] = zp[c];
         __syncthreads();
 #pragma unroll
-        for (int c = 0; c < NIN; ++c)
-            zbar[c] = (ZB[(0 * NIN + c) * TR + r] + ZB[(1 * NIN + c) * TR + r]) + (ZB[(2 * NIN + c) * TR + r] + ZB[(3 * NIN + c) * TR + r]);
-        // ---- batch contractions over the tile's 32 rows into the shared accumulators (one owner per entry)
-        {   // dW2[j][i] += sum_r D2[j][r] H1[i][r]: rows j0 .. j0+7, columns i0 + 8 b, two passes of eight columns
-            const int j0 = (tid >> 3) * 8, i0 = tid & 7;
-#pragma unroll 1
-            for (int pass = 0; pass < 2; ++pass) {
-                float p[8][8];
+        for (int c = 0; c < NIN; ++c) {
+            float s = 0.f;
 #pragma unroll
-                for (int a = 0; a < 8; ++a)
-#pragma unroll
-                    for (int b = 0; b < 8; ++b) p[a][b] = 0.f;
-#pragma unroll 1
-                for (int rr = 0; rr < TR; rr += 4) {
-                    float4 dj[8], hi[8];
-#pragma unroll
-                    for (int a = 0; a < 8; ++a) dj[a] = *reinterpret_cast<const float4 *>(D2 + (j0 + a) * LDT + rr);
-#pragma unroll
-                    for (int b = 0; b < 8; ++b) hi[b] = *reinterpret_cast<const float4 *>(H1 + (i0 + 8 * (8 * pass + b)) * LDT + rr);
-#pragma unroll
-                    for (int a = 0; a < 8; ++a)
-#pragma unroll
-                        for (int b = 0; b < 8; ++b) {
-                            p[a][b] = fmaf(dj[a].x, hi[b].x, p[a][b]); p[a][b] = fmaf(dj[a].y, hi[b].y, p[a][b]);
-                            p[a][b] = fmaf(dj[a].z, hi[b].z, p[a][b]); p[a][b] = fmaf(dj[a].w, hi[b].w, p[a][b]);
-                        }
-                }
-#pragma unroll
-                for (int a = 0; a < 8; ++a)
-#pragma unroll
-                    for (int b = 0; b < 8; ++b) aW2[(j0 + a) * SW2 + i0 + 8 * (8 * pass + b)] += p[a][b];
-            }
+            for (int qq = 0; qq < NW; ++qq) s += ZB[(qq * NIN + c) * TR + r];   // same order in every thread of the trajectory
+            zbar[c] = s;
         }
-        {   // thread t owns hidden unit t: dW1[t][0..7], dW3[0..2][t], db1[t], db2[t]
+        // ---- batch contractions over the tile's 32 rows into the shared accumulators (one owner per entry)
+        {   // dW2[j][i] += sum_r D2[j][r] H1[i][r]: rows j0 .. j0+7, columns i0 + 16 b (16 x 16 threads, 8 x 8 patches)
+            const int j0 = (tid >> 4) * 8, i0 = tid & 15;
+            float p[8][8];
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+#pragma unroll
+                for (int b = 0; b < 8; ++b) p[a][b] = 0.f;
+#pragma unroll 1
+            for (int rr = 0; rr < TR; rr += 4) {
+                float4 dj[8], hi[8];
+#pragma unroll
+                for (int a = 0; a < 8; ++a) dj[a] = *reinterpret_cast<const float4 *>(D2 + (j0 + a) * LDT + rr);
+#pragma unroll
+                for (int b = 0; b < 8; ++b) hi[b] = *reinterpret_cast<const float4 *>(H1 + (i0 + 16 * b) * LDT + rr);
+#pragma unroll
+                for (int a = 0; a < 8; ++a)
+#pragma unroll
+                    for (int b = 0; b < 8; ++b) {
+                        p[a][b] = fmaf(dj[a].x, hi[b].x, p[a][b]); p[a][b] = fmaf(dj[a].y, hi[b].y, p[a][b]);
+                        p[a][b] = fmaf(dj[a].z, hi[b].z, p[a][b]); p[a][b] = fmaf(dj[a].w, hi[b].w, p[a][b]);
+                    }
+            }
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+#pragma unroll
+                for (int b = 0; b < 8; ++b) aW2[(j0 + a) * SW2 + i0 + 16 * b] += p[a][b];
+        }
+        if (tid < HID) {   // thread t < 128 owns hidden unit t: dW1[t][0..7], dW3[0..2][t], db1[t], db2[t]
             float s1[NIN], s3[NX], sb1 = 0.f, sb2 = 0.f;
 #pragma unroll
             for (int c = 0; c < NIN; ++c) s1[c] = 0.f;
@@ -260,8 +265,10 @@ __global__ void __launch_bounds__(nvw::NTHR, 1) node_vjp_wide_kernel(const NodeV
         }
         for (int e = tid; e < HID * NIN; e += NTHR) { atomicAdd(P.acc + A_W1 + e, (double)aW1[e]); aW1[e] = 0.f; }
         for (int e = tid; e < NX * HID; e += NTHR) { atomicAdd(P.acc + A_W3 + e, (double)aW3[e]); aW3[e] = 0.f; }
-        atomicAdd(P.acc + A_B1 + tid, (double)aB1[tid]); aB1[tid] = 0.f;
-        atomicAdd(P.acc + A_B2 + tid, (double)aB2[tid]); aB2[tid] = 0.f;
+        if (tid < HID) {
+            atomicAdd(P.acc + A_B1 + tid, (double)aB1[tid]); aB1[tid] = 0.f;
+            atomicAdd(P.acc + A_B2 + tid, (double)aB2[tid]); aB2[tid] = 0.f;
+        }
         if (tid < NX) { atomicAdd(P.acc + A_B3 + tid, (double)aB3[tid]); aB3[tid] = 0.f; }
         __syncthreads();
     };

@@ -235,7 +235,7 @@ int dynax_node_rk4_forward_stages_f32(const float *W1, const float *b1, const fl
  * g_xsol:[T,N,3] and/or g_ysol:[T,N,1] in; weight gradients (summed over systems, each may be NULL),
  * g_x0:[N,3], g_u:[T,N,5] out.  xsol is the forward trajectory (x_{k+1} at row k).  hidden = 64: tcgen05 kernel
  * (node_vjp_tc.cuh), CUDA-core kernel with DYNAX_NODE_VJP_IMPL=0; hidden = 32: CUDA-core kernel; hidden = 128: the wide
- * CUDA-core kernel (node_vjp_wide.cuh: 32-trajectory CTAs, four threads per trajectory).  With DYNAX_SHARED_U
+ * CUDA-core kernel (node_vjp_wide.cuh: 32-trajectory CTAs, eight threads per trajectory).  With DYNAX_SHARED_U
  * u is ONE series [T,5] and g_u:[T,5] its gradient summed over the trajectories (fp32 atomics: one per warp, step and
  * channel, so the last bits depend on the order).
  * ws: dynax_node_rk4_vjp_workspace() bytes.  PARITY UNPINNED BY THE REFERENCE. */

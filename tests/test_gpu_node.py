@@ -129,7 +129,7 @@ def _torch_node_rollout(T, W, x0, u, dt, euler):
 def test_vjp_matches_torch_autograd_fp64(T, monkeypatch, N, Tn, euler, scale, impl, hidden):
     """Oracle = torch autograd (fp64, CPU) over the restated RK4-MLP rollout (the reference has neither).
     The VJP kernels: tcgen05 (default for hidden = 64), CUDA cores (DYNAX_NODE_VJP_IMPL=0; hidden = 32 always), and the
-    wide CUDA-core kernel (hidden = 128: 32-trajectory CTAs, four threads per trajectory)."""
+    wide CUDA-core kernel (hidden = 128: 32-trajectory CTAs, eight threads per trajectory)."""
     from dynax_b200 import ops
     if impl == "cuda_core":
         monkeypatch.setenv("DYNAX_NODE_VJP_IMPL", "0")
