@@ -148,7 +148,8 @@ struct TanhQuad {
     __device__ __forceinline__ void recip() { r = rcpv(pp.x * pp.y); }  // 1 MUFU
     // d/a rather than 1 - 1/a: d is exact, so small |x| keep their RELATIVE accuracy up to ex2.approx's own error (1 - 1/a
     // cancels: 2.5e-7 absolute whatever |tanh|; measured on config 5 at dt = 900, 2048 steps: 90th percentile of the
-    // per-trajectory error 6.9e-5 against 4.6e-5), for two more packed multiplications per pair (-2.7 % throughput).
+    // per-trajectory error 6.5e-5 with 1 - 1/a, 3.8e-5 with d/a), for two more packed multiplications per pair
+    // (-2.7 % throughput).
     __device__ __forceinline__ void finish(float2 &t02, float2 &t13) const {
         const float2 q = make_float2(r * pp.y, r * pp.x);  // (1/(a0 a1), 1/(a2 a3))
         t02 = __fmul2_rn(__fmul2_rn(d02, a13), q);          // d0 a1 / (a0 a1), d2 a3 / (a2 a3)
