@@ -1,7 +1,9 @@
 """A/B timing of the forward kernel between two builds of the library, same process, same inputs.
 
     git stash; python -m dynax_b200.build; mkdir -p dynax_b200/_old; cp dynax_b200/libdynax_b200.so dynax_b200/_old/libdynax_old.so
-    git stash pop; python -m dynax_b200.build; gpurun -- python tools/_ab_fwd.py
+    git stash pop; python -m dynax_b200.build
+    gpurun -- 'python tools/_ab_fwd.py; DYNAX_B200_LIB=dynax_b200/_old/libdynax_old.so AB_NAME=old python tools/_ab_fwd.py'
+(one build per process: two copies of the library in one process crashed on this image)
 
 Prints ms for x+y and y-only per shape and the fp64 sums of both outputs (equal sums = same results)."""
 import os, sys, torch
@@ -17,15 +19,14 @@ def t(fn, it=10):
         e0.record(); fn(); e1.record(); torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1))
     return best
-libs = {"new": _lib.LIB_PATH, "old": os.path.join(os.path.dirname(_lib.LIB_PATH), "_old", "libdynax_old.so")}
+name = os.environ.get("AB_NAME", "new")
 g = torch.Generator(device="cuda").manual_seed(0)
 for N, T, tc in ((1, 8760, -1), (1, 8760, 0), (129, 8760, -1), (1023, 8760, 0), (75777, 2000, 0), (151553, 2000, 0), (151552, 2000, 0), (16384, 8760, 0)):
     th = torch.tensor(NOM, device="cuda")[None].repeat(N, 1)
     x0 = torch.tensor([[20.0, 30.0, 26.0]], device="cuda").repeat(N, 1)
     u = torch.rand((T, N, 5), device="cuda", generator=g)
     for rep in range(2):
-        for name, path in libs.items():
-            _lib._LIB = None; _lib.LIB_PATH = path; _lib.lib()
+        if True:
             a = t(lambda: ops.rc_forward(th, x0, u, 3600.0, time_chunks=tc))
             b = t(lambda: ops.rc_forward(th, x0, u, 3600.0, emit_x=False, time_chunks=tc))
             xs, ys, _ = ops.rc_forward(th, x0, u, 3600.0, time_chunks=tc)
