@@ -206,18 +206,39 @@ def time_cpu(n_sys, T, steps, warmup):
     return n_sys * T * steps / dt, cores, dt / steps
 
 
+def time_cpu_numba(n_sys, T):
+    """Second, independently written CPU implementation (oracle/numba_oracle.py) on the same
+    sample: the C port's figure is only trusted as the baseline if the two agree within a small factor."""
+    try:
+        from oracle import numba_oracle
+    except ImportError as e:
+        return {"unavailable": f"{type(e).__name__}: {e}"}
+    tiny = cpu_sample(64, 16)
+    cores = numba_oracle.use_all_cores()
+    numba_oracle.rc_loss_grad(*tiny, DT)           # JIT / cache load outside the timed region
+    th, x0, u, target = cpu_sample(n_sys, T)
+    numba_oracle.rc_loss_grad(th, x0, u, target, DT)
+    t0 = time.perf_counter()
+    numba_oracle.rc_loss_grad(th, x0, u, target, DT)
+    dt = time.perf_counter() - t0
+    return {"value": n_sys * T / dt, "unit": "system-steps/s", "cores": cores,
+            "impl": "numba @njit(parallel=True), all-fp32 BPTT", "sample": f"{n_sys} systems x {T} steps"}
+
+
 def reference_arm(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     val, cores, sec = time_cpu(a.cpu_systems, a.T, a.steps, a.warmup)
+    numba_check = time_cpu_numba(a.cpu_systems, a.T)
     sample = f"{a.cpu_systems} systems x {a.T} steps per step (bounded sample of the {a.systems}-system workload)"
     line = {
         "impl": "reference", "metric": "system-steps/s, fwd+grad RC rollout", "value": val, "unit": "system-steps/s",
         "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"rc_fwd_grad N={a.systems} T={a.T} dt=3600 per-system theta/u/target (per rank)", "sample": sample},
-        "cpu_baseline": {"value": val, "unit": "system-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "system-steps/s", "cores": cores, "kind": "port", "sample": sample,
+                         "numba_cross_check": numba_check},
         "e2e": {"value": val, "unit": "system-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference is JAX/Flax (not installable here: no jax wheel, no network); this arm times the oracle's "
                 "C/OpenMP port of the same arithmetic (all-fp32 BPTT storing per-step residuals like XLA's scan transpose)",
@@ -733,7 +754,8 @@ def ours(a):
     if not a.no_cpu_baseline and world == 1:
         v, cores, s = time_cpu(a.cpu_systems, T, 2, 1)
         cpu = {"value": v, "unit": "system-steps/s", "cores": cores, "kind": "port",
-               "sample": f"{a.cpu_systems} systems x {T} steps, oracle/dynax_oracle.c (all-fp32 BPTT, OpenMP, -march=native)"}
+               "sample": f"{a.cpu_systems} systems x {T} steps, oracle/dynax_oracle.c (all-fp32 BPTT, OpenMP, -march=native)",
+               "numba_cross_check": time_cpu_numba(a.cpu_systems, T)}
 
     line = {
         "metric": "system-steps/s, fwd+grad RC rollout", "value": value, "unit": "system-steps/s", "n_gpus": world,
