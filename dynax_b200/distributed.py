@@ -66,15 +66,21 @@ def sharded_argmin(local_min, local_argmin, offset, group=None):
     One all-gather of two 8-byte values per rank; ties go to the lowest global index, like ``argmin``
     over the unsharded axis.  Returns (min_cost, global_index) as 0-d tensors, identical on every rank.
     """
-    pair = torch.stack([local_min.reshape(()).to(torch.float64),
-                        (local_argmin.reshape(()) + int(offset)).to(torch.float64)])   # indices < 2^53 are exact
+    # few launches: this runs inside the control loop next to a 0.3 ms kernel (bench.py workloads.config4_mpc)
+    pair = torch.empty((2,), dtype=torch.float64, device=local_min.device)   # indices < 2^53 are exact
+    pair[0].copy_(local_min.reshape(()))
+    pair[1].copy_(local_argmin.reshape(()))
+    pair[1] += int(offset)
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        allp = [torch.empty_like(pair) for _ in range(dist.get_world_size(group))]
-        dist.all_gather(allp, pair, group=group)
-        allp = torch.stack(allp)
+        allp = torch.empty((dist.get_world_size(group), 2), dtype=torch.float64, device=pair.device)
+        if pair.is_cuda:   # NCCL: one collective into the [world, 2] buffer
+            dist.all_gather_into_tensor(allp, pair, group=group)
+        else:              # gloo (CPU tests) has no all_gather_into_tensor
+            dist.all_gather(list(allp.unbind(0)), pair, group=group)
     else:
         allp = pair[None]
-    cost, idx = allp[:, 0], allp[:, 1]
-    best = cost.min()
-    winner = torch.where(cost == best, idx, torch.full_like(idx, float("inf"))).min()
-    return best.to(local_min.dtype), winner.to(torch.int64)
+    # argmin returns the FIRST minimal entry = the lowest rank = the lowest global index among equal costs
+    # (within a rank the kernel has already kept the lowest index)
+    # (index_select: indexing with a 0-d tensor would synchronise the stream to read it)
+    win = allp.index_select(0, torch.argmin(allp[:, 0]).reshape(1)).reshape(2)
+    return win[0].to(local_min.dtype), win[1].to(torch.int64)
