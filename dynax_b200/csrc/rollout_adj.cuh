@@ -84,7 +84,15 @@ struct AdjCfg {
     static constexpr int A2_OFF = A1_OFF + align32i(KC * A1_ROW);
     static constexpr int A3_OFF = A2_OFF + align32i(KC * A2_ROW);                      // per-system channel (ctrl)
     static constexpr int STAGE = A3_OFF + (SHARED_U ? align32i(KC * TN) : 0);
-    static constexpr int NBAR = 2 * S;
+    // Forward sweep (phase 1) of the general-cotangent mode: only u moves, so each stage buffer -- sized for u + g_y + g_x
+    // -- holds NSUB chunks of u: the sweep runs through S * NSUB sub-stages with their own barriers (two stages of u
+    // alone keep ~18 KB per SM in flight, 40 % of the HBM roof by Little's law).  NSUB == 1: one ring straight through
+    // both phases, as before.
+    static constexpr int U_SUB = align32i(KC * U_ROW);
+    static constexpr int NSUB = (SHARED_U || SHIFT || MODE == ADJ_MSE) ? 1 : (STAGE / U_SUB > 4 ? 4 : STAGE / U_SUB);
+    static constexpr bool TWO_RING = NSUB > 1;
+    static constexpr int P1S = S * NSUB;
+    static constexpr int NBAR = 2 * S + (TWO_RING ? 2 * P1S + 1 : 0);
     // Models with many gradient accumulators (dense LTI: n*n + n*m + p*n + p*m) keep the fp64 totals in shared
     // memory ([NG][TN] doubles, conflict-free 8-byte accesses) and fold into them every GT_FOLD segments: as 2*NG
     // registers they push the kernel to 255 registers plus spills and one CTA per SM.
@@ -121,6 +129,9 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_adj_kernel(const __grid
     float *s_in = reinterpret_cast<float *>(smem_raw);
     uint64_t *full = reinterpret_cast<uint64_t *>(s_in + S * Cfg::STAGE);
     uint64_t *empty = full + S;
+    uint64_t *full1 = empty + S, *empty1 = full1 + Cfg::P1S, *p1done = empty1 + Cfg::P1S;  // TWO_RING only
+    constexpr bool TWO_RING = Cfg::TWO_RING;
+    constexpr int P1S = Cfg::P1S, NSUB = Cfg::NSUB;
 
     const int tid = threadIdx.x;
     const int64_t N = P.N;
@@ -153,6 +164,13 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_adj_kernel(const __grid
         for (int s = 0; s < S; ++s) {
             ptx::mbar_init(&full[s], async_rows ? 32 : 1);
             ptx::mbar_init(&empty[s], TN / 32);
+        }
+        if constexpr (TWO_RING) {
+            for (int r = 0; r < P1S; ++r) {
+                ptx::mbar_init(&full1[r], async_rows ? 32 : 1);
+                ptx::mbar_init(&empty1[r], TN / 32);
+            }
+            ptx::mbar_init(p1done, TN / 32);
         }
         ptx::fence_mbar_init();
     }
@@ -199,42 +217,57 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_adj_kernel(const __grid
             return row_bytes * (uint32_t)rows;
         };
 
-        auto load_q = [&](int64_t q) {
-            const int s = (int)(q % S);
-            float *st = s_in + s * Cfg::STAGE;
-            const bool fwd = q < C - 1;
-            const int64_t seg = fwd ? q : (2 * C - 2 - q);
+        // one chunk = segment `seg` into the buffer `st`, published on `bar`; fwd: the forward sweep (u only)
+        auto load_chunk = [&](const bool fwd, const int64_t seg, float *st, uint64_t *bar) {
             const int64_t k0 = seg * KC;
             const int rows = (int)((T - k0) < KC ? (T - k0) : KC);
             uint32_t bytes = 0;
 #pragma unroll
             for (int pass = 0; pass < 2; ++pass) {
-                uint32_t b = stream(pass, st + Cfg::U_OFF, U_ROW, u_base, m, SHARED_U, k0, rows, &full[s], &P.map_u, P.inner_u);
-                if (SHARED_U) b += stream(pass, st + Cfg::A3_OFF, TN, ctrl_base, 1, false, k0, rows, &full[s], &P.map_c, P.inner_c);
+                uint32_t b = stream(pass, st + Cfg::U_OFF, U_ROW, u_base, m, SHARED_U, k0, rows, bar, &P.map_u, P.inner_u);
+                if (SHARED_U) b += stream(pass, st + Cfg::A3_OFF, TN, ctrl_base, 1, false, k0, rows, bar, &P.map_c, P.inner_c);
                 if (!fwd) {
                     if (MODE == ADJ_MSE) {
-                        b += stream(pass, st + Cfg::A1_OFF, A1_ROW, tgt_base, 1, SHARED_TGT, k0, rows, &full[s], &P.map_a1, P.inner_a1);
+                        b += stream(pass, st + Cfg::A1_OFF, A1_ROW, tgt_base, 1, SHARED_TGT, k0, rows, bar, &P.map_a1, P.inner_a1);
                     } else {
-                        b += stream(pass, st + Cfg::A1_OFF, A1_ROW, gy_base, p, false, k0, rows, &full[s], &P.map_a1, P.inner_a1);
-                        b += stream(pass, st + Cfg::A2_OFF, A2_ROW, gx_base, n, false, k0, rows, &full[s], &P.map_a2, P.inner_a2);
+                        b += stream(pass, st + Cfg::A1_OFF, A1_ROW, gy_base, p, false, k0, rows, bar, &P.map_a1, P.inner_a1);
+                        b += stream(pass, st + Cfg::A2_OFF, A2_ROW, gx_base, n, false, k0, rows, bar, &P.map_a2, P.inner_a2);
                     }
                 }
                 if (pass == 0) {
                     if (async_rows) {  // every lane: arrives once its own copies have landed; nothing left for pass 1
-                        ptx::cp_async_arrive(&full[s]);
+                        ptx::cp_async_arrive(bar);
                         break;
                     }
                     bytes = b;
                     __syncwarp();
                     if (lane == 0) {
-                        if (bytes) ptx::mbar_arrive_expect_tx(&full[s], bytes);
-                        else ptx::mbar_arrive(&full[s]);
+                        if (bytes) ptx::mbar_arrive_expect_tx(bar, bytes);
+                        else ptx::mbar_arrive(bar);
                     }
                     __syncwarp();  // pass 1: the other lanes' copies must not complete before the bytes are expected
                 }
             }
         };
 
+        auto load_q = [&](int64_t q) {  // one ring through both phases: chunk q = C-1 forward segments, then C in reverse
+            const bool fwd = q < C - 1;
+            load_chunk(fwd, fwd ? q : (2 * C - 2 - q), s_in + (int)(q % S) * Cfg::STAGE, &full[q % S]);
+        };
+        if constexpr (TWO_RING) {
+            for (int64_t q = 0; q < C - 1; ++q) {  // forward sweep through the S * NSUB sub-stages
+                const int r = (int)(q % P1S);
+                if (q >= P1S) ptx::mbar_wait(&empty1[r], (uint32_t)((q / P1S - 1) & 1));
+                load_chunk(true, q, s_in + (r / NSUB) * Cfg::STAGE + (r % NSUB) * Cfg::U_SUB, &full1[r]);
+            }
+            ptx::mbar_wait(p1done, 0);  // the stage buffers are free: every warp has left the forward sweep
+            for (int64_t q2 = 0; q2 < C; ++q2) {
+                const int s2 = (int)(q2 % S);
+                if (q2 >= S) ptx::mbar_wait(&empty[s2], (uint32_t)((q2 / S - 1) & 1));
+                load_chunk(false, C - 1 - q2, s_in + s2 * Cfg::STAGE, &full[s2]);
+            }
+            return;
+        }
         for (int64_t q = 0; q < Q && q < S; ++q) load_q(q);
         for (int64_t q = 0; q + S < Q; ++q) {
             ptx::mbar_wait(&empty[q % S], (uint32_t)((q / S) & 1));
@@ -320,27 +353,36 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_adj_kernel(const __grid
     // ---- phase 1: forward sweep over segments 0..C-2, checkpointing the state at each start
     for (; q < C - 1; ++q) {
         const int s = (int)(q % S);
+        const int r1 = TWO_RING ? (int)(q % P1S) : 0;  // sub-stage of the forward sweep's own ring
         if (active) {
 #pragma unroll
             for (int d = 0; d < n; ++d) ck[(q * n + d) * N] = xc[d];
         }
-        stage_wait(q);
-        const float *in = s_in + s * Cfg::STAGE + Cfg::U_OFF + (SHARED_U ? 0 : tid * m);
+        if constexpr (TWO_RING) ptx::mbar_wait(&full1[r1], (uint32_t)((q / P1S) & 1));
+        else stage_wait(q);
+        const float *stg = TWO_RING ? s_in + (r1 / NSUB) * Cfg::STAGE + (r1 % NSUB) * Cfg::U_SUB : s_in + s * Cfg::STAGE;
+        const float *in = stg + Cfg::U_OFF + (SHARED_U ? 0 : tid * m);
 #pragma unroll
         for (int j = 0; j < KC; ++j) {
             float u[m], r[n];
             const int o = j * U_ROW + shu(q * KC + j);
 #pragma unroll
             for (int d = 0; d < m; ++d) u[d] = in[o + d];
-            override_ctrl(u, s_in + s * Cfg::STAGE, j);
+            override_ctrl(u, stg, j);
             M.rhs(xc, u, r);
 #pragma unroll
             for (int d = 0; d < n; ++d) xc[d] = discrete ? r[d] : fmaf(dt, r[d], xc[d]);
         }
         if (self_rows) self_load(q + S);
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&empty[s]);
+        if (lane == 0) ptx::mbar_arrive(TWO_RING ? &empty1[r1] : &empty[s]);
     }
+    if constexpr (TWO_RING) {  // this warp is done with the sub-stages: the producer may refill the stage buffers
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(p1done);
+    }
+    // ring position of the reverse sweep's chunks: its own count with two rings, the running count with one
+    const int64_t qoff = TWO_RING ? (C - 1) : 0;
 
     // ---- phase 2: reverse sweep
     float a[n];  // adjoint of x_{k+1}
@@ -361,7 +403,7 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_adj_kernel(const __grid
     const float c2T = 2.0f / (float)P.T;  // the mean runs over the WHOLE horizon, also in a chunked launch
 
     for (int64_t seg = C - 1; seg >= 0; --seg, ++q) {
-        const int s = (int)(q % S);
+        const int s = (int)((q - qoff) % S);
         const int64_t k0 = seg * KC;
         const int rows = (int)((T - k0) < KC ? (T - k0) : KC);
         float xs[KC][n];
@@ -371,7 +413,7 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_adj_kernel(const __grid
 #pragma unroll
             for (int d = 0; d < n; ++d) xc[d] = ck[((seg - 1) * n + d) * N];
         }
-        stage_wait(q);
+        stage_wait(q - qoff);
         const float *st = s_in + s * Cfg::STAGE;
         const float *in = st + Cfg::U_OFF + (SHARED_U ? 0 : tid * m);
 
