@@ -213,51 +213,65 @@ struct DenseModel {
         }
     }
 
+    // G[0..w) += a * v[0..w): two entries per FFMA2 (the same IEEE operations as w scalar fused multiply-adds)
+    template <int w>
+    __device__ __forceinline__ static void axpy_row(float *G, const float a, const float *v) {
+        const float2 aa = make_float2(a, a);
+#pragma unroll
+        for (int j = 0; j + 1 < w; j += 2) {
+            const float2 r = __ffma2_rn(aa, make_float2(v[j], v[j + 1]), make_float2(G[j], G[j + 1]));
+            G[j] = r.x;
+            G[j + 1] = r.y;
+        }
+        if constexpr (w % 2 == 1) G[w - 1] = fmaf(a, v[w - 1], G[w - 1]);
+    }
+
     __device__ __forceinline__ void accum(float *G, const float *s, const float *gy, const float *x,
                                           const float *u) const {
 #pragma unroll
         for (int i = 0; i < n; ++i) {
-#pragma unroll
-            for (int j = 0; j < n; ++j) G[i * n + j] = fmaf(s[i], x[j], G[i * n + j]);
-#pragma unroll
-            for (int j = 0; j < m; ++j) G[n * n + i * m + j] = fmaf(s[i], u[j], G[n * n + i * m + j]);
+            axpy_row<n>(G + i * n, s[i], x);
+            axpy_row<m>(G + n * n + i * m, s[i], u);
         }
 #pragma unroll
         for (int i = 0; i < p; ++i) {
-#pragma unroll
-            for (int j = 0; j < n; ++j)
-                G[n * n + n * m + i * n + j] = fmaf(gy[i], x[j], G[n * n + n * m + i * n + j]);
-#pragma unroll
-            for (int j = 0; j < m; ++j)
-                G[n * n + n * m + p * n + i * m + j] = fmaf(gy[i], u[j], G[n * n + n * m + p * n + i * m + j]);
+            axpy_row<n>(G + n * n + n * m + i * n, gy[i], x);
+            axpy_row<m>(G + n * n + n * m + p * n + i * m, gy[i], u);
         }
     }
 
-    __device__ __forceinline__ void adj_x(const float *s, const float *gy, float *ax) const {
+    // out[0..w) = Ma^T s + Mb^T gy for row-major Ma[n][w], Mb[p][w]: column pairs per FFMA2 (the same IEEE operations, in the
+    // same order, as the scalar loops: product of row 0, fused multiply-adds over the other rows, one addition)
+    template <int w>
+    __device__ __forceinline__ static void adj_cols(const float *Ma, const float *Mb, const float *s, const float *gy,
+                                                    float *out) {
 #pragma unroll
-        for (int j = 0; j < n; ++j) {
-            float v = A[j] * s[0];
+        for (int j = 0; j + 1 < w; j += 2) {
+            float2 v = __fmul2_rn(make_float2(Ma[j], Ma[j + 1]), make_float2(s[0], s[0]));
 #pragma unroll
-            for (int i = 1; i < n; ++i) v = fmaf(A[i * n + j], s[i], v);
-            float w = C[j] * gy[0];
+            for (int i = 1; i < n; ++i) v = __ffma2_rn(make_float2(Ma[i * w + j], Ma[i * w + j + 1]), make_float2(s[i], s[i]), v);
+            float2 q = __fmul2_rn(make_float2(Mb[j], Mb[j + 1]), make_float2(gy[0], gy[0]));
 #pragma unroll
-            for (int i = 1; i < p; ++i) w = fmaf(C[i * n + j], gy[i], w);
-            ax[j] = v + w;
+            for (int i = 1; i < p; ++i) q = __ffma2_rn(make_float2(Mb[i * w + j], Mb[i * w + j + 1]), make_float2(gy[i], gy[i]), q);
+            const float2 r = __fadd2_rn(v, q);
+            out[j] = r.x;
+            out[j + 1] = r.y;
+        }
+        if constexpr (w % 2 == 1) {
+            constexpr int j = w - 1;
+            float v = __fmul_rn(Ma[j], s[0]);
+#pragma unroll
+            for (int i = 1; i < n; ++i) v = fmaf(Ma[i * w + j], s[i], v);
+            float q = __fmul_rn(Mb[j], gy[0]);
+#pragma unroll
+            for (int i = 1; i < p; ++i) q = fmaf(Mb[i * w + j], gy[i], q);
+            out[j] = __fadd_rn(v, q);
         }
     }
 
-    __device__ __forceinline__ void adj_u(const float *s, const float *gy, float *gu) const {
-#pragma unroll
-        for (int j = 0; j < m; ++j) {
-            float v = B[j] * s[0];
-#pragma unroll
-            for (int i = 1; i < n; ++i) v = fmaf(B[i * m + j], s[i], v);
-            float w = D[j] * gy[0];
-#pragma unroll
-            for (int i = 1; i < p; ++i) w = fmaf(D[i * m + j], gy[i], w);
-            gu[j] = v + w;
-        }
-    }
+    __device__ __forceinline__ void adj_x(const float *s, const float *gy, float *ax) const { adj_cols<n>(A, C, s, gy, ax); }
+
+    __device__ __forceinline__ void adj_u(const float *s, const float *gy, float *gu) const { adj_cols<m>(B, D, s, gy, gu); }
 
     __device__ __forceinline__ void finalize(const double *G, const Ptrs &, int64_t, double *g) const {
 #pragma unroll

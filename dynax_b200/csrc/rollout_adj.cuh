@@ -266,12 +266,12 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_adj_kernel(const __grid
                 if (q2 >= S) ptx::mbar_wait(&empty[s2], (uint32_t)((q2 / S - 1) & 1));
                 load_chunk(false, C - 1 - q2, s_in + s2 * Cfg::STAGE, &full[s2]);
             }
-            return;
-        }
-        for (int64_t q = 0; q < Q && q < S; ++q) load_q(q);
-        for (int64_t q = 0; q + S < Q; ++q) {
-            ptx::mbar_wait(&empty[q % S], (uint32_t)((q / S) & 1));
-            load_q(q + S);
+        } else {
+            for (int64_t q = 0; q < Q && q < S; ++q) load_q(q);
+            for (int64_t q = 0; q + S < Q; ++q) {
+                ptx::mbar_wait(&empty[q % S], (uint32_t)((q / S) & 1));
+                load_q(q + S);
+            }
         }
         return;
     }
