@@ -192,26 +192,46 @@ struct DenseModel {
     static constexpr int SMEM_FLOATS = 0;  // no block-shared model data
     __device__ __forceinline__ static void block_init(float *, const Ptrs &, int, int) {}
     __device__ __forceinline__ void load(const Ptrs &P, int64_t i, const float *) { load(P, i); }
+    // out[i] = (Ma x)_i + (Mb u)_i for row-major Ma[R][n], Mb[R][m]: two ROWS per FFMA2.  Each row goes through exactly
+    // the operations of rhs()/the scalar loops (product of column 0, fused multiply-adds over the other columns, one
+    // addition), so the states are bit-identical to the kernels that use rhs().  For the forward kernel only: the
+    // gradient kernels pair the COLUMNS of the same matrices (adj_cols), and one register layout cannot serve both.
+    template <int R>
+    __device__ __forceinline__ static void rows2(const float *Ma, const float *Mb, const float *x, const float *u, float *out) {
+#pragma unroll
+        for (int i = 0; i + 1 < R; i += 2) {
+            float2 a = __fmul2_rn(make_float2(Ma[i * n], Ma[(i + 1) * n]), make_float2(x[0], x[0]));
+#pragma unroll
+            for (int j = 1; j < n; ++j) a = __ffma2_rn(make_float2(Ma[i * n + j], Ma[(i + 1) * n + j]), make_float2(x[j], x[j]), a);
+            float2 b = __fmul2_rn(make_float2(Mb[i * m], Mb[(i + 1) * m]), make_float2(u[0], u[0]));
+#pragma unroll
+            for (int j = 1; j < m; ++j) b = __ffma2_rn(make_float2(Mb[i * m + j], Mb[(i + 1) * m + j]), make_float2(u[j], u[j]), b);
+            const float2 r = __fadd2_rn(a, b);
+            out[i] = r.x;
+            out[i + 1] = r.y;
+        }
+        if constexpr (R % 2 == 1) {
+            constexpr int i = R - 1;
+            float a = __fmul_rn(Ma[i * n], x[0]);
+#pragma unroll
+            for (int j = 1; j < n; ++j) a = fmaf(Ma[i * n + j], x[j], a);
+            float b = __fmul_rn(Mb[i * m], u[0]);
+#pragma unroll
+            for (int j = 1; j < m; ++j) b = fmaf(Mb[i * m + j], u[j], b);
+            out[i] = __fadd_rn(a, b);
+        }
+    }
+
     // explicit Euler in residual form (simulator.py:40); `discrete` steps x_{k+1} = rhs instead
     __device__ __forceinline__ void step(float *x, const float *u, float dt, bool discrete) const {
         float r[n];
-        rhs(x, u, r);
+        rows2<n>(A, B, x, u, r);  // fxx(x) + fxu(u)   base_block_state_space.py:61
 #pragma unroll
         for (int d = 0; d < n; ++d) x[d] = discrete ? r[d] : fmaf(dt, r[d], x[d]);
     }
 
-    __device__ __forceinline__ void out(const float *x, const float *u, float *y) const {
-#pragma unroll
-        for (int i = 0; i < p; ++i) {
-            float cx = __fmul_rn(C[i * n], x[0]);
-#pragma unroll
-            for (int j = 1; j < n; ++j) cx = fmaf(C[i * n + j], x[j], cx);
-            float du = __fmul_rn(D[i * m], u[0]);
-#pragma unroll
-            for (int j = 1; j < m; ++j) du = fmaf(D[i * m + j], u[j], du);
-            y[i] = __fadd_rn(cx, du);  // fyx(x) + fyu(u)   base_block_state_space.py:69
-        }
-    }
+    // fyx(x) + fyu(u)   base_block_state_space.py:69
+    __device__ __forceinline__ void out(const float *x, const float *u, float *y) const { rows2<p>(C, D, x, u, y); }
 
     // G[0..w) += a * v[0..w): two entries per FFMA2 (the same IEEE operations as w scalar fused multiply-adds)
     template <int w>
