@@ -107,6 +107,23 @@ def test_vjp_wide_tile(T, ops, n, m, p, N, monkeypatch):
         assert rel_err(got.cpu().numpy()[0], rs[key].sum(0), floor=1.0) < 1e-4, key
 
 
+@pytest.mark.parametrize("n,m,p", DIMS)
+@pytest.mark.parametrize("Tn", [1, 7, 8, 9, 65, 203])
+def test_vjp_forward_sweep_substages(T, ops, n, m, p, Tn):
+    """The forward sweep of the general-cotangent kernel runs through sub-stages of the stage buffers (AdjCfg::NSUB, up to
+    four per stage: the deeper ring wraps several times at T = 203) and hands the buffers back before the reverse sweep:
+    every instantiated shape, horizons of one segment, one segment + 1 step, and many segments, ragged N."""
+    N, dt = 131, 0.05
+    A, B, C, D, x0, u = make(N, Tn, n, m, p, 60 + Tn)
+    rng = np.random.default_rng(61 + Tn)
+    gx = rng.normal(size=(Tn, N, n)).astype(np.float32)
+    gy = rng.normal(size=(Tn, N, p)).astype(np.float32)
+    out = ops.lti_vjp(*(cu(T, v) for v in (A, B, C, D, x0, u)), dt, cu(T, gx), cu(T, gy), time_chunks=0)
+    r = orc.lti_vjp(A, B, C, D, x0, u, dt, gx, gy, np.float64)
+    for got, key in zip(out, ("gA", "gB", "gC", "gD", "gx0", "gu")):
+        assert rel_err(got.cpu().numpy(), r[key], floor=1.0) < 1e-4, key
+
+
 def test_vjp_shared_matrices_sums_over_systems(T, ops):
     N, Tn, dt = 256, 64, 0.05
     A, B, C, D, x0, u = make(N, Tn, 3, 3, 1, 45, L=1)
