@@ -24,10 +24,10 @@ inline size_t gu_part_bytes(int64_t N, int64_t T, int m) {
     return sizeof(float) * (size_t)((N + kGuPartTN - 1) / kGuPartTN) * (size_t)T * (size_t)m;
 }
 
-template <class Model, int TN, int KF, int S, bool SHARED_U, int MINB, bool SHIFT = false>
+template <class Model, int TN, int KF, int S, bool SHARED_U, int MINB, bool SHIFT = false, int NO = 2>
 int launch_fwd(const FwdParams<Model> &P0, cudaStream_t st) {
-    using Cfg = FwdCfg<Model, TN, KF, S, SHARED_U, SHIFT>;
-    auto kern = rollout_fwd_kernel<Model, TN, KF, S, SHARED_U, MINB, SHIFT>;
+    using Cfg = FwdCfg<Model, TN, KF, S, SHARED_U, SHIFT, NO>;
+    auto kern = rollout_fwd_kernel<Model, TN, KF, S, SHARED_U, MINB, SHIFT, NO>;
     if (SHIFT && P0.bulk_in) return fail(DYNAX_ERR_INVALID_ARGUMENT, "shifted-row instantiation launched on rows TMA can move");
     DYNAX_NOTE_LAUNCH();
     int rc = set_smem(kern, Cfg::SMEM_BYTES);

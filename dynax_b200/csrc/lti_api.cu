@@ -14,12 +14,16 @@ namespace dynax {
 template <int n, int m, int p>
 static int lti_forward_t(const FwdParams<DenseModel<n, m, p>> &P, bool shared_u, cudaStream_t st) {
     using M = DenseModel<n, m, p>;
-    if (shared_u) return launch_fwd<M, 128, 4, 2, true, 2>(P, st);
-    // launches that fit one 128-system CTA per SM are bound by the per-chunk hand-shakes of the serial chain:
-    // 16-row chunks (see rc_api.cu: 1.18 vs 1.91 ms per 8760 steps)
     DeviceInfo di;
     const int rc = device_info(&di);
     if (rc != DYNAX_OK) return rc;
+    // a shared input series on launches of at most two 128-system CTAs per SM: 16-row chunks, 4-stage ring (rc_api.cu)
+    if (shared_u) {
+        if (P.N <= (int64_t)di.sm_count * 256) return launch_fwd<M, 128, 16, 4, true, 2>(P, st);
+        return launch_fwd<M, 128, 4, 2, true, 2>(P, st);
+    }
+    // launches that fit one 128-system CTA per SM are bound by the per-chunk hand-shakes of the serial chain:
+    // 16-row chunks (see rc_api.cu: 1.18 vs 1.91 ms per 8760 steps)
     if ((P.N + 127) / 128 <= di.sm_count) return launch_fwd<M, 128, 16, 2, false, 2>(P, st);
     return launch_fwd<M, 256, 4, 4, false, 1>(P, st);  // wide rows: 5 KB+ per bulk copy (see rc_api.cu)
 }

@@ -113,7 +113,18 @@ static int rc_forward(const float *theta, const float *x0, const float *u, float
         P.ctrl = ctrl;
         P.ctrl_col = ctrl_col;
     }
-    if (flags & DYNAX_SHARED_U) return launch_fwd<RCModel, 128, 4, 4, true, 4>(P, st);
+    if (flags & DYNAX_SHARED_U) {
+        // A shared input series leaves almost nothing to stream in, so the short chunks that suit many CTAs per SM
+        // (4 rows: the out-tiles stay small) make a launch of few CTAs wait on its own hand-shakes: up to two
+        // 128-system CTAs per SM take 16-row chunks and a 4-stage ring (N = 128 .. 18 944, T = 8760, x+y: 1.70-1.72 ->
+        // 0.97-1.07 ms; with a control channel 2.03-2.06 -> 1.17-1.26 ms; N = 65 536: 2.46 -> 2.23 ms but 1.47 -> 1.97 ms
+        // without outputs, so the short chunks stay above the threshold).  DYNAX_FWD_CFG=0 forces the short chunks.
+        DeviceInfo di;
+        rc = device_info(&di);
+        if (rc != DYNAX_OK) return rc;
+        if (N <= (int64_t)di.sm_count * 256 && env_int("DYNAX_FWD_CFG", -1) != 0) return launch_fwd<RCModel, 128, 16, 4, true, 2>(P, st);
+        return launch_fwd<RCModel, 128, 4, 4, true, 4>(P, st);
+    }
     // Tile shapes measured on B200 (tools/tune.py, N=132608, T=8760): wide rows win because each
     // cp.async.bulk then moves 5 KB: 256-system CTAs 6.45 TB/s (x+y), 128-system 5.43, 64-system 5.31.
     // Launches that leave at most one 256-system CTA per SM are bound by the per-chunk hand-shakes of the serial
@@ -124,7 +135,9 @@ static int rc_forward(const float *theta, const float *x0, const float *u, float
         DeviceInfo di;
         rc = device_info(&di);
         if (rc != DYNAX_OK) return rc;
-        cfg = ((N + 127) / 128 <= di.sm_count) ? 4 : ((N + 255) / 256 <= di.sm_count) ? 3 : 0;
+        // (one 128-system CTA per SM on more than half of the SMs: a 4-stage ring, N = 16 384: 0.98 -> 0.92 ms, 18 944: 1.05 ->
+        // 0.96 ms; below that the ring depth makes no difference)
+        cfg = ((N + 127) / 128 <= di.sm_count) ? (N > (int64_t)di.sm_count * 64 ? 5 : 4) : ((N + 255) / 256 <= di.sm_count) ? 3 : 0;
     }
     // rows TMA cannot move (N % 4 != 0) on launches of more than one wave: the shifted-row instantiation (16-byte cp.async)
     if (cfg == 0 && !P.bulk_in && !env_int("DYNAX_NO_SHIFT", 0)) return launch_fwd<RCModel, 256, 4, 4, false, 1, true>(P, st);
@@ -133,6 +146,7 @@ static int rc_forward(const float *theta, const float *x0, const float *u, float
         case 0: return launch_fwd<RCModel, 256, 4, 4, false, 1>(P, st);
         case 3: return launch_fwd<RCModel, 128, 8, 2, false, 3>(P, st);
         case 4: return launch_fwd<RCModel, 128, 16, 2, false, 2>(P, st);
+        case 5: return launch_fwd<RCModel, 128, 16, 4, false, 1>(P, st);
     }
 }
 

@@ -57,7 +57,9 @@ __host__ __device__ constexpr int align32i(int x) { return (x + 31) & ~31; }   /
 // SHIFT: the instantiation for per-system rows TMA cannot move (N % 4 != 0): rows are staged at their global offset modulo
 // 16 bytes, so that the interior of a row moves as one bulk copy (ptx::copy_rows_shift_bulk), the row pitch grows by 4
 // floats, and the computing threads add the (warp-uniform) shift of each row to their shared address.
-template <class Model, int TN, int KF, int S, bool SHARED_U, bool SHIFT = false>
+// NO: out-tiles (x and y of one stage each).  Two suffice when several CTAs share an SM; a launch of one CTA per SM is a
+// serial chain that stalls whenever the TMA unit has not finished reading the tile written two stages ago: four tiles.
+template <class Model, int TN, int KF, int S, bool SHARED_U, bool SHIFT = false, int NO = 2>
 struct FwdCfg {
     static_assert(!SHIFT || !SHARED_U, "shifted rows are per-system rows");
     static_assert(!SHIFT || KF <= 32, "copy_rows_shift_bulk: one lane per row of a stage");
@@ -67,16 +69,17 @@ struct FwdCfg {
     static constexpr int IN_STAGE = align32i(CTRL_OFF + (SHARED_U ? KF * TN : 0));
     static constexpr int XO_STAGE = KF * TN * n;
     static constexpr int YO_STAGE = KF * TN * p;
-    static constexpr int NBAR = 2 * S + 4;
+    static constexpr int NBAR = 2 * S + 2 * NO;
     static constexpr int MODEL_FLOATS = align4i(Model::SMEM_FLOATS);  // block-shared model data (MLP weights)
     static constexpr size_t SMEM_BYTES =
-        sizeof(float) * (size_t)(S * IN_STAGE + 2 * XO_STAGE + 2 * YO_STAGE + MODEL_FLOATS) + sizeof(uint64_t) * NBAR;
+        sizeof(float) * (size_t)(S * IN_STAGE + NO * XO_STAGE + NO * YO_STAGE + MODEL_FLOATS) + sizeof(uint64_t) * NBAR;
     static constexpr int THREADS = TN + 32;
 };
 
-template <class Model, int TN, int KF, int S, bool SHARED_U, int MINB, bool SHIFT = false>
+template <class Model, int TN, int KF, int S, bool SHARED_U, int MINB, bool SHIFT = false, int NO = 2>
 __global__ void __launch_bounds__(TN + 32, MINB) rollout_fwd_kernel(const __grid_constant__ FwdParams<Model> P) {
-    using Cfg = FwdCfg<Model, TN, KF, S, SHARED_U, SHIFT>;
+    using Cfg = FwdCfg<Model, TN, KF, S, SHARED_U, SHIFT, NO>;
+    static_assert(NO >= 2, "at least two out-tiles");
     constexpr int n = Cfg::n, m = Cfg::m, p = Cfg::p;
     constexpr int IN_ROW = Cfg::IN_ROW, IN_STAGE = Cfg::IN_STAGE, XO_STAGE = Cfg::XO_STAGE,
                   YO_STAGE = Cfg::YO_STAGE;
@@ -85,12 +88,12 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_fwd_kernel(const __grid
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *s_in = reinterpret_cast<float *>(smem_raw);
     float *s_xo = s_in + S * IN_STAGE;
-    float *s_yo = s_xo + 2 * XO_STAGE;
-    float *s_model = s_yo + 2 * YO_STAGE;
+    float *s_yo = s_xo + NO * XO_STAGE;
+    float *s_model = s_yo + NO * YO_STAGE;
     uint64_t *full = reinterpret_cast<uint64_t *>(s_model + Cfg::MODEL_FLOATS);
     uint64_t *empty = full + S;
     uint64_t *ofull = empty + S;
-    uint64_t *ofree = ofull + 2;
+    uint64_t *ofree = ofull + NO;
 
     const int tid = threadIdx.x;
     const int64_t N = P.N;
@@ -119,10 +122,11 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_fwd_kernel(const __grid
             ptx::mbar_init(&full[s], async_rows ? 32 : 1);
             ptx::mbar_init(&empty[s], TN / 32);
         }
-        ptx::mbar_init(&ofull[0], TN / 32);
-        ptx::mbar_init(&ofull[1], TN / 32);
-        ptx::mbar_init(&ofree[0], 1);
-        ptx::mbar_init(&ofree[1], 1);
+#pragma unroll
+        for (int o = 0; o < NO; ++o) {
+            ptx::mbar_init(&ofull[o], TN / 32);
+            ptx::mbar_init(&ofree[o], 1);
+        }
         ptx::fence_mbar_init();
     }
     Model::block_init(s_model, P.mp, tid, TN + 32);  // no-op unless the model keeps shared data
@@ -197,8 +201,11 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_fwd_kernel(const __grid
             }
         };
 
+        // The tile of chunk c is handed back once the TMA unit has READ it.  Two tiles: right after the store is issued.
+        // More: one chunk later (the newest store group stays in flight), so the producer never sits in the wait.
+        constexpr int LAG = NO > 2 ? 1 : 0;
         auto store_chunk = [&](int64_t c) {
-            const int o = (int)(c & 1);
+            const int o = (int)(c % NO);
             const int64_t k0 = c * KF;
             const int rows = (int)((T - k0) < KF ? (T - k0) : KF);
             const float *sx = s_xo + o * XO_STAGE;
@@ -210,7 +217,7 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_fwd_kernel(const __grid
                     if (emit_x) ptx::tensor_s2g_3d(&P.map_x, 0, (int)(n0 * n / P.inner_x), (int)(t_begin + k0), sx);
                     if (emit_y) ptx::tensor_s2g_3d(&P.map_y, 0, (int)(n0 * p / P.inner_y), (int)(t_begin + k0), sy);
                     ptx::bulk_commit();
-                    ptx::bulk_wait_read<0>();  // out-tile may be overwritten once TMA has read it
+                    ptx::bulk_wait_read<LAG>();  // out-tile may be overwritten once TMA has read it
                 }
             } else {
                 // per-row stores: lane r stores row r (bulk groups are per thread: every lane waits for its own)
@@ -219,12 +226,12 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_fwd_kernel(const __grid
                         ptx::bulk_s2g(xsol_base + ((k0 + lane) * N + n0) * n, sx + lane * TN * n, (uint32_t)valid * n * 4u);
                     if (emit_y)
                         ptx::bulk_s2g(ysol_base + ((k0 + lane) * N + n0) * p, sy + lane * TN * p, (uint32_t)valid * p * 4u);
-                    ptx::bulk_commit();
-                    ptx::bulk_wait_read<0>();
                 }
+                ptx::bulk_commit();   // every lane, also without a row: the group counts stay in step
+                ptx::bulk_wait_read<LAG>();
             }
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&ofree[o]);
+            if (lane == 0 && c >= LAG) ptx::mbar_arrive(&ofree[(c - LAG) % NO]);
         };
 
         for (int64_t c = 0; c < C && c < S; ++c) load_chunk(c);
@@ -233,7 +240,7 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_fwd_kernel(const __grid
             ptx::mbar_wait(&empty[s], (uint32_t)((c / S) & 1));  // consumers are done with chunk c
             if (c + S < C) load_chunk(c + S);
             if (emit) {
-                ptx::mbar_wait(&ofull[c & 1], (uint32_t)((c >> 1) & 1));
+                ptx::mbar_wait(&ofull[c % NO], (uint32_t)((c / NO) & 1));
                 store_chunk(c);
             }
         }
@@ -255,11 +262,11 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_fwd_kernel(const __grid
 
     for (int64_t c = 0; c < C; ++c) {
         const int s = (int)(c % S);
-        const int o = (int)(c & 1);
+        const int o = (int)(c % NO);
         const int64_t k0 = c * KF;
         const int rows = (int)((T - k0) < KF ? (T - k0) : KF);
         ptx::mbar_wait(&full[s], (uint32_t)((c / S) & 1));
-        if (emit) ptx::mbar_wait(&ofree[o], (uint32_t)(((c >> 1) & 1) ^ 1));
+        if (emit) ptx::mbar_wait(&ofree[o], (uint32_t)(((c / NO) & 1) ^ 1));
         const float *in = s_in + s * IN_STAGE + (SHARED_U ? 0 : tid * m);
         // SHIFT: row j of this stage sits at its global offset modulo 16 bytes (see ptx::copy_rows_shift_bulk)
         const unsigned sh0 = SHIFT ? (unsigned)((reinterpret_cast<uintptr_t>(u_base) >> 2) + (uint64_t)((k0 * N + n0) * m)) : 0u;

@@ -269,15 +269,15 @@ def test_chunked_vjp_variants(T, ops, L):
 # ----------------------------------------------------------------------------------------------
 # forward kernel
 # ----------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("N,su,tn,kf", [(N_SMALL, False, 128, 16), (148 * 200, False, 128, 8), (N_256, False, 256, 4),
-                                        (N_224, True, 128, 4)])
-def test_forward_variants(T, ops, L, N, su, tn, kf):
+@pytest.mark.parametrize("N,su,tn,kf,stages", [(N_SMALL, False, 128, 16, 2), (N_128, False, 128, 16, 4), (148 * 200, False, 128, 8, 2),
+                                               (N_256, False, 256, 4, 4), (N_SMALL, True, 128, 16, 4), (N_224, True, 128, 4, 4)])
+def test_forward_variants(T, ops, L, N, su, tn, kf, stages):
     Tn = 50
     th, x0, u, _ = rc_data(N, Tn)
     u_k = u[:, :1] if su else u
     (xs, ys, xf), sites = launched_by(L, lambda: ops.rc_forward(cu(T, th), cu(T, x0), cu(T, u_k), DT, emit_final=True,
                                                                 time_chunks=0))
-    expect(sites, "launch_fwd<", "RCModel", f"TN = {tn};", f"KF = {kf};", f"SHARED_U = {str(su).lower()};")
+    expect(sites, "launch_fwd<", "RCModel", f"TN = {tn};", f"KF = {kf};", f"S = {stages};", f"SHARED_U = {str(su).lower()};")
     idx = sample_idx(N)
     us = np.repeat(u_k, len(idx), 1) if su else u[:, idx]
     x64, y64 = orc.rc_rollout(th[idx], x0[idx], us, DT, np.float64)
@@ -356,14 +356,15 @@ def lti_data(N, Tn, n, m, p, seed=11):
 
 
 @pytest.mark.parametrize("n,m,p", DIMS)
-@pytest.mark.parametrize("N,su", [(300, False), (300, True), (148 * 128 + 4000, False)])
+@pytest.mark.parametrize("N,su", [(300, False), (300, True), (148 * 256 + 300, True), (148 * 128 + 4000, False)])
 def test_lti_forward_variants(T, ops, L, n, m, p, N, su):
     Tn, dt = 40, 0.05
     A, B, C, D, x0, u = lti_data(N, Tn, n, m, p)
     u_k = u[:, :1] if su else u
     (xs, ys, _), sites = launched_by(L, lambda: ops.lti_forward(*(cu(T, v) for v in (A, B, C, D, x0, u_k)), dt, time_chunks=0))
     expect(sites, "launch_fwd<", f"DenseModel<{n}, {m}, {p}>", f"SHARED_U = {str(su).lower()};",
-           "TN = 256;" if N > 148 * 128 else "TN = 128;")
+           "TN = 256;" if (N > 148 * 128 and not su) else "TN = 128;",
+           *([("KF = 16;" if N <= 148 * 256 else "KF = 4;")] if su else []))
     idx = sample_idx(N)
     us = np.repeat(u_k, len(idx), 1) if su else u[:, idx]
     xr, yr = orc.lti_rollout(A[idx], B[idx], C[idx], D[idx], x0[idx], us, dt, np.float64)
