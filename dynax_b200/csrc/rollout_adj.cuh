@@ -195,9 +195,17 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_adj_kernel(const __grid
                     ptx::tensor_g2s_3d(dst, map, 0, (int)(n0 * w / inner), (int)(t_begin + k0), bar, pol);
                 return (uint32_t)(KC * TN * w * 4);
             }
-            if (shared) {
-                if (pass == 0) {  // [T,1,w] is contiguous in k and the smem rows are packed (row_stride == w)
-                    const float *src = g + k0 * w;
+            if (shared) {  // [T,1,w] is contiguous in k and the smem rows are packed (row_stride == w)
+                const float *src = g + k0 * w;
+                // one asynchronous bulk copy when the block is 16-byte aligned and sized: plain loads would cost the
+                // producer an L2 round trip per chunk, which a short segment of a small launch cannot hide
+                const uint32_t sbytes = (uint32_t)(rows * w) * 4u;
+                const bool sbulk = !async_rows && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (sbytes & 15u) == 0;
+                if (sbulk) {
+                    if (pass == 1 && lane == 0) ptx::bulk_g2s(dst, src, sbytes, bar, ptx::policy_evict_last());
+                    return sbytes;
+                }
+                if (pass == 0) {
                     if (async_rows) ptx::copy_rows_async(dst, 0, src, 0, 1, rows * w, lane);
                     else for (int i = lane; i < rows * w; i += 32) dst[i] = __ldg(src + i);
                 }
