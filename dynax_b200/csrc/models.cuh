@@ -174,16 +174,24 @@ struct DenseModel {
         for (int k = 0; k < p * m; ++k) D[k] = __ldg(P.D + s * (p * m) + k);
     }
 
+    // Even state and output counts: the gradient kernel pairs the ROWS of all four matrices (rhs through rows2, the
+    // transposed products through adj_rows), so that one register layout serves its recomputation and its adjoint step.
+    static constexpr bool ROWPAIR = (n % 2 == 0) && (p % 2 == 0);
+
     __device__ __forceinline__ void rhs(const float *x, const float *u, float *r) const {
+        if constexpr (ROWPAIR) {
+            rows2<n>(A, B, x, u, r);  // the same operations per row as below
+        } else {
 #pragma unroll
-        for (int i = 0; i < n; ++i) {
-            float ax = __fmul_rn(A[i * n], x[0]);  // (intrinsics: no context-dependent contraction, see RCModel::rhs)
+            for (int i = 0; i < n; ++i) {
+                float ax = __fmul_rn(A[i * n], x[0]);  // (intrinsics: no context-dependent contraction, see RCModel::rhs)
 #pragma unroll
-            for (int j = 1; j < n; ++j) ax = fmaf(A[i * n + j], x[j], ax);
-            float bu = __fmul_rn(B[i * m], u[0]);
+                for (int j = 1; j < n; ++j) ax = fmaf(A[i * n + j], x[j], ax);
+                float bu = __fmul_rn(B[i * m], u[0]);
 #pragma unroll
-            for (int j = 1; j < m; ++j) bu = fmaf(B[i * m + j], u[j], bu);
-            r[i] = __fadd_rn(ax, bu);  // fxx(x) + fxu(u)   base_block_state_space.py:61
+                for (int j = 1; j < m; ++j) bu = fmaf(B[i * m + j], u[j], bu);
+                r[i] = __fadd_rn(ax, bu);  // fxx(x) + fxu(u)   base_block_state_space.py:61
+            }
         }
     }
 
@@ -194,8 +202,9 @@ struct DenseModel {
     __device__ __forceinline__ void load(const Ptrs &P, int64_t i, const float *) { load(P, i); }
     // out[i] = (Ma x)_i + (Mb u)_i for row-major Ma[R][n], Mb[R][m]: two ROWS per FFMA2.  Each row goes through exactly
     // the operations of rhs()/the scalar loops (product of column 0, fused multiply-adds over the other columns, one
-    // addition), so the states are bit-identical to the kernels that use rhs().  For the forward kernel only: the
-    // gradient kernels pair the COLUMNS of the same matrices (adj_cols), and one register layout cannot serve both.
+    // addition), so the states are bit-identical to the scalar loops of rhs().  One register layout cannot serve row pairs
+    // and column pairs of the same matrix: the gradient kernel pairs rows throughout for ROWPAIR models (rhs + adj_rows) and
+    // columns otherwise (scalar rhs + adj_cols).
     template <int R>
     __device__ __forceinline__ static void rows2(const float *Ma, const float *Mb, const float *x, const float *u, float *out) {
 #pragma unroll
@@ -289,9 +298,33 @@ struct DenseModel {
         }
     }
 
-    __device__ __forceinline__ void adj_x(const float *s, const float *gy, float *ax) const { adj_cols<n>(A, C, s, gy, ax); }
+    // out[j] = (Ma^T s)_j + (Mb^T gy)_j with ROW pairs (ROWPAIR models): the sum over rows runs as two interleaved partial
+    // sums (even rows, odd rows) per column, added at the end
+    template <int w>
+    __device__ __forceinline__ static void adj_rows(const float *Ma, const float *Mb, const float *s, const float *gy,
+                                                    float *out) {
+#pragma unroll
+        for (int j = 0; j < w; ++j) {
+            float2 v = __fmul2_rn(make_float2(Ma[j], Ma[w + j]), make_float2(s[0], s[1]));
+#pragma unroll
+            for (int i = 2; i < n; i += 2)
+                v = __ffma2_rn(make_float2(Ma[i * w + j], Ma[(i + 1) * w + j]), make_float2(s[i], s[i + 1]), v);
+#pragma unroll
+            for (int i = 0; i < p; i += 2)
+                v = __ffma2_rn(make_float2(Mb[i * w + j], Mb[(i + 1) * w + j]), make_float2(gy[i], gy[i + 1]), v);
+            out[j] = __fadd_rn(v.x, v.y);
+        }
+    }
 
-    __device__ __forceinline__ void adj_u(const float *s, const float *gy, float *gu) const { adj_cols<m>(B, D, s, gy, gu); }
+    __device__ __forceinline__ void adj_x(const float *s, const float *gy, float *ax) const {
+        if constexpr (ROWPAIR) adj_rows<n>(A, C, s, gy, ax);
+        else adj_cols<n>(A, C, s, gy, ax);
+    }
+
+    __device__ __forceinline__ void adj_u(const float *s, const float *gy, float *gu) const {
+        if constexpr (ROWPAIR) adj_rows<m>(B, D, s, gy, gu);
+        else adj_cols<m>(B, D, s, gy, gu);
+    }
 
     __device__ __forceinline__ void finalize(const double *G, const Ptrs &, int64_t, double *g) const {
 #pragma unroll
