@@ -409,6 +409,10 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_adj_kernel(const __grid
         else Gt[g] = 0.0;
     }
     const float c2T = 2.0f / (float)P.T;  // the mean runs over the WHOLE horizon, also in a chunked launch
+    // launch-uniform switches of the step body, evaluated once (ncu source page: the 64-bit null tests were re-done every step)
+    const bool has_gy = P.g_ysol != nullptr, has_gx = P.g_xsol != nullptr, do_grads = !P.skip_grads;
+    const bool store_gu = MODE == ADJ_VJP && gu_base != nullptr && active && do_grads;
+    const int64_t gu_row = N * m;  // floats between consecutive rows of g_u
 
     for (int64_t seg = C - 1; seg >= 0; --seg, ++q) {
         const int s = (int)((q - qoff) % S);
@@ -423,6 +427,7 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_adj_kernel(const __grid
         }
         stage_wait(q - qoff);
         const float *st = s_in + s * Cfg::STAGE;
+        float *const gu_seg = store_gu ? gu_base + (k0 * N + i) * m : nullptr;  // row k0 of this system's g_u
         const float *in = st + Cfg::U_OFF + (SHARED_U ? 0 : tid * m);
 
         // recompute x_{k0+1} .. x_{k0+rows-1} into registers
@@ -458,19 +463,19 @@ __global__ void __launch_bounds__(TN + 32, MINB) rollout_adj_kernel(const __grid
                 } else {
 #pragma unroll
                     for (int d = 0; d < p; ++d)
-                        gy[d] = P.g_ysol ? st[Cfg::A1_OFF + j * A1_ROW + sh1(k0 + j) + tid * p + d] : 0.f;
-                    if (P.g_xsol) {
+                        gy[d] = has_gy ? st[Cfg::A1_OFF + j * A1_ROW + sh1(k0 + j) + tid * p + d] : 0.f;
+                    if (has_gx) {
 #pragma unroll
                         for (int d = 0; d < n; ++d) a[d] += st[Cfg::A2_OFF + j * A2_ROW + sh2(k0 + j) + tid * n + d];
                     }
                 }
 #pragma unroll
                 for (int d = 0; d < n; ++d) sv[d] = discrete ? a[d] : dt * a[d];  // cotangent of rhs
-                if (!P.skip_grads) M.accum(Gp, sv, gy, xs[j], u);
-                if (MODE == ADJ_VJP && gu_base != nullptr && active && !P.skip_grads) {
+                if (do_grads) M.accum(Gp, sv, gy, xs[j], u);
+                if (store_gu) {
                     float gu[m];
                     M.adj_u(sv, gy, gu);
-                    float *dst = gu_base + ((k0 + j) * N + i) * m;
+                    float *dst = gu_seg + j * gu_row;
 #pragma unroll
                     for (int d = 0; d < m; ++d) dst[d] = gu[d];
                 }
