@@ -112,7 +112,7 @@ def test_emit_flags_and_no_tma_path(T, ops, monkeypatch):
     assert T.equal(xs3, xs) and T.equal(ys3, ys)
 
 
-@pytest.mark.parametrize("cfg", ["0", "3", "4"])
+@pytest.mark.parametrize("cfg", ["0", "3", "4", "5"])
 def test_tile_configs_bit_identical(T, ops, monkeypatch, cfg):
     N, Tn = 1000, 203
     th, x0, u = orc.synth_theta(N, 25), orc.synth_x0(N, 25), orc.synth_u(Tn, N, 25)
@@ -122,6 +122,31 @@ def test_tile_configs_bit_identical(T, ops, monkeypatch, cfg):
     monkeypatch.setenv("DYNAX_FWD_CFG", cfg)
     got = ops.rc_forward(*a, 3600.0)
     assert T.equal(ref[0], got[0]) and T.equal(ref[1], got[1])
+
+
+@pytest.mark.parametrize("Tn", [1, 15, 16, 17, 64, 65, 203])
+def test_shared_series_tile_shapes(T, ops, monkeypatch, Tn):
+    """A shared input series (with and without a per-system control channel) on a small launch: the long-chunk tile
+    (16 rows, 4-stage ring: the default for up to two CTAs per SM) against the fp64 oracle and, bit for bit, against the
+    4-row tile (DYNAX_FWD_CFG=0); horizons around one chunk and one ring."""
+    N = 517
+    th, x0, u = orc.synth_theta(N, 26), orc.synth_x0(N, 26), orc.synth_u(Tn, N, 26)
+    us = u[:, :1]
+    ctrl = -5.0 * np.random.default_rng(27).random((Tn, N), dtype=np.float32)
+    a = [cu(T, v) for v in (th, x0, us)]
+    got = ops.rc_forward(*a, 3600.0, emit_final=True)
+    gotc = ops.rc_forward_ctrl(cu(T, th), cu(T, x0), cu(T, us[:, 0]), cu(T, ctrl), 3600.0, ctrl_col=2)
+    monkeypatch.setenv("DYNAX_FWD_CFG", "0")
+    ref = ops.rc_forward(*a, 3600.0, emit_final=True)
+    refc = ops.rc_forward_ctrl(cu(T, th), cu(T, x0), cu(T, us[:, 0]), cu(T, ctrl), 3600.0, ctrl_col=2)
+    for g, r in zip(got + gotc[:2], ref + refc[:2]):
+        assert T.equal(g, r)
+    x64, y64 = orc.rc_rollout(th, x0, np.repeat(us, N, 1), 3600.0, np.float64)
+    assert rel_err(got[0].cpu().numpy(), x64) < TRAJ_RTOL and rel_err(got[1].cpu().numpy(), y64) < TRAJ_RTOL
+    uc = np.repeat(us, N, 1).copy()
+    uc[:, :, 2] = ctrl
+    xc64, _ = orc.rc_rollout(th, x0, uc, 3600.0, np.float64)
+    assert rel_err(gotc[0].cpu().numpy(), xc64) < TRAJ_RTOL
 
 
 def test_chaining_property_large(T, ops):
